@@ -1,0 +1,206 @@
+/*
+ * tsidb.h — C ABI of the B200-native batched TSID tick (libtsidb.so).
+ *
+ * This is the drop-in boundary for the per-tick hot path of
+ * UW-RoboSoccer/tsid_control.  In the reference that path crosses the
+ * boost.python binding of the `tsid` C++ library four times per tick
+ * (ref:main.py:119-127):
+ *
+ *     HQPData = formulation.computeProblemData(t, q, v)      ref:main.py:119
+ *     sol     = solver.solve(HQPData)                        ref:main.py:121
+ *     tau     = formulation.getActuatorForces(sol)           ref:main.py:126
+ *     dv      = formulation.getAccelerations(sol)            ref:main.py:127
+ *     f       = formulation.getContactForce(name, sol)       ref:ctrl/WalkController.py:263,273
+ *
+ * for ONE robot.  Here one call does the same for n_envs independent robots.
+ * Plain pointers and sizes only; no torch types.  All floating point is IEEE
+ * fp64.  Per-env solver outcome is reported in status[] with the TSID
+ * HQP_STATUS enum values so `status != 0` keeps the meaning it has at
+ * ref:main.py:122.
+ *
+ * Ownership: the caller owns every buffer; the library owns the model/conf
+ * constants and its workspace.  One handle per device; a handle is not
+ * re-entrant.  Device entry points are asynchronous on `cuda_stream`.
+ * There is no CPU fallback: every entry point fails (<0) without a CUDA device.
+ */
+#ifndef TSIDB_H_
+#define TSIDB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSIDB_MAX_BODIES 24 /* floating base + revolute joints             */
+#define TSIDB_MAX_NA 23     /* actuated joints                             */
+#define TSIDB_MAX_NV 29
+#define TSIDB_NFORCE 12     /* Contact6d: 4 corner forces, sole frame      */
+
+/* TSID HQP_STATUS_* [UPSTREAM tsid solvers/fwd.hpp]; ref:main.py:122 tests != 0 */
+enum {
+  TSIDB_STATUS_UNKNOWN = -1,
+  TSIDB_STATUS_OPTIMAL = 0,
+  TSIDB_STATUS_INFEASIBLE = 1,
+  TSIDB_STATUS_UNBOUNDED = 2,
+  TSIDB_STATUS_MAX_ITER_REACHED = 3,
+  TSIDB_STATUS_ERROR = 4
+};
+
+/* contact_mask bits (replaces formulation.addRigidContact/removeRigidContact,
+ * ref:ctrl/WalkController.py:83-85,124-126, ref:legacy/biped.py:174,183,191-197,205-211) */
+enum { TSIDB_CONTACT_LF = 1, TSIDB_CONTACT_RF = 2 };
+
+/*
+ * Compiled robot model — what tsid.RobotWrapper(urdf, [root], FreeFlyer)
+ * holds after ref:ctrl/WalkController.py:13-19.  Produced by
+ * tsid_control_b200/model_compiler.py.  Body 0 is the free-flyer; bodies
+ * 1..na are JointModelRZ in Pinocchio order.  Matrices are row-major.
+ */
+typedef struct tsidb_model {
+  int32_t nb;                               /* bodies = na + 1                       */
+  int32_t parent[TSIDB_MAX_BODIES];         /* parent body, -1 for body 0            */
+  double jR[TSIDB_MAX_BODIES][9];           /* joint placement in the parent body    */
+  double jp[TSIDB_MAX_BODIES][3];
+  double mass[TSIDB_MAX_BODIES];
+  double com[TSIDB_MAX_BODIES][3];          /* lever, body frame                     */
+  double inertia[TSIDB_MAX_BODIES][9];      /* about the CoM, body frame             */
+  int32_t foot_body[2];                     /* [0]=LF, [1]=RF: parent body of sole   */
+  double fR[2][9];                          /* sole frame placement in that body     */
+  double fp[2][3];
+  double gravity[3];                        /* (0,0,-9.81)                           */
+} tsidb_model;
+
+/*
+ * Controller constants — the values ref:ctrl/conf.py:21-72 /
+ * ref:legacy/op3_conf.py:4-50 feed into the tsid task objects at
+ * ref:ctrl/WalkController.py:55-187 / ref:legacy/biped.py:31-151.
+ */
+typedef struct tsidb_conf {
+  /* Contact6d (ref:ctrl/WalkController.py:55-70) */
+  double contact_points[3][4];              /* corners in the sole frame             */
+  double contact_normal[3];
+  double mu, fmin, fmax;
+  double kp_contact[6], kd_contact[6];
+  double w_force_reg;                       /* conf.w_forceRef                        */
+  double force_reg_weights[6];              /* [UPSTREAM Contact6d] 1,1,1e-3,2,2,2   */
+  /* TaskSE3Equality feet (ref:ctrl/WalkController.py:90-104,131-144) */
+  double w_foot, kp_foot[6], kd_foot[6];
+  /* TaskComEquality (ref:ctrl/WalkController.py:147-152) */
+  double w_com, kp_com[3], kd_com[3];
+  /* TaskJointPosture (ref:ctrl/WalkController.py:159-165) */
+  double w_posture, kp_posture[TSIDB_MAX_NA], kd_posture[TSIDB_MAX_NA];
+  /* legacy TaskAMEquality (ref:legacy/biped.py:82-87); w_am <= 0 disables */
+  double w_am, kp_am[3];
+  /* TaskActuationBounds (ref:ctrl/WalkController.py:168-176); enabled iff w_torque_bounds > 0 */
+  int32_t use_torque_bounds;
+  double tau_min[TSIDB_MAX_NA], tau_max[TSIDB_MAX_NA];
+  /* TaskJointBounds (ref:ctrl/WalkController.py:178-184); enabled iff w_joint_bounds > 0 */
+  int32_t use_joint_bounds;
+  double v_min[TSIDB_MAX_NA], v_max[TSIDB_MAX_NA];
+  double joint_bounds_dt;                   /* [UPSTREAM TaskJointBounds] 2*conf.dt  */
+  /* SolverHQuadProgFast (ref:ctrl/WalkController.py:186-187) */
+  double hessian_reg;                       /* [UPSTREAM] 1e-8                       */
+  int32_t max_iter;                         /* [UPSTREAM] 1000                       */
+  int32_t pad_;
+} tsidb_conf;
+
+typedef struct tsidb_handle tsidb_handle;
+
+/* Per-env task references, one struct of device (or host) pointers.
+ * Every array is addressed as  a[dof * ld_dof + env * ld_env]  with the
+ * strides below, so both SoA ([dof][N]: ld_dof=N, ld_env=1) and the
+ * PyTorch-natural [N][dof] (ld_dof=1, ld_env=dof) layouts work without a
+ * transposing copy.  A NULL pointer selects the reference the controller was
+ * constructed with (tsidb_set_default_refs), broadcast to every env.        */
+typedef struct tsidb_refs {
+  const double* com;        /* [9]  pos, vel, acc            TaskComEquality.setReference  ref:ctrl/WalkController.py:152 */
+  const double* foot_lf;    /* [24] SE3 pos (p, R col-major) 12, vel 6, acc 6   task_LF.setReference ref:ctrl/WalkController.py:196 */
+  const double* foot_rf;    /* [24]                                             task_RF.setReference ref:ctrl/WalkController.py:197 */
+  const double* contact_lf; /* [12] SE3 (p, R col-major)     contactLF.setReference ref:ctrl/WalkController.py:81 */
+  const double* contact_rf; /* [12]                          contactRF.setReference ref:ctrl/WalkController.py:122 */
+  const double* posture;    /* [na]                          postureTask.setReference ref:ctrl/WalkController.py:165 */
+} tsidb_refs;
+
+/* Optional per-env diagnostics/outputs (any pointer may be NULL). */
+typedef struct tsidb_aux_out {
+  double* com;        /* [9]  com, vcom, acom_drift   robot.com(data) ref:main.py:135          */
+  double* foot_lf;    /* [12] sole placement (p, R col-major)  robot.framePosition ref:main.py:139 */
+  double* foot_rf;    /* [12]                                                     ref:main.py:141 */
+  double* wrench;     /* [12] T*f per foot (LF 6, RF 6), the f_lf/f_rf of ref:ctrl/WalkController.py:263,273 */
+} tsidb_aux_out;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+/* replaces WalkController.__init__ / Biped.__init__ up to solver.resize
+ * (ref:ctrl/WalkController.py:12-187, ref:legacy/biped.py:7-151) */
+int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, int max_envs, int device,
+                 tsidb_handle** out);
+void tsidb_destroy(tsidb_handle* h);
+const char* tsidb_last_error(void);
+/* model sizes: na, nv, nq, and the reference's one-sided inequality count 2*nIn
+ * (for mapping active_set bits to CI rows) */
+int tsidb_sizes(const tsidb_handle* h, int* na, int* nv, int* nq);
+
+/* default references broadcast when a tsidb_refs pointer is NULL (host pointers,
+ * same element order as tsidb_refs, contiguous) */
+int tsidb_set_default_refs(tsidb_handle* h, const double* com9, const double* foot_lf24,
+                           const double* foot_rf24, const double* contact_lf12,
+                           const double* contact_rf12, const double* posture_na);
+
+/* ---- the tick ------------------------------------------------------------------- */
+/*
+ * computeProblemData + solve + getActuatorForces/getAccelerations/getContactForce
+ * for n_envs robots (ref:main.py:119-127).  All pointers are DEVICE pointers.
+ *   q [nq], v [nv]            state, strides ld_env/ld_dof as described above
+ *   contact_mask [n_envs]     TSIDB_CONTACT_* bits
+ *   tau [na], ddq [nv]        outputs, same stride convention
+ *   f [24]                    LF corner forces 0..11, RF 12..23, 0 for a foot not in contact
+ *   status, iters [n_envs]    HQP status / eiquadprog iteration count
+ *   active_set [3][n_envs]    (may be NULL) bit r of the 192-bit word = one-sided
+ *                             canonical inequality row r is in the final working set;
+ *                             row numbering in tsidb_ci_row()
+ */
+int tsidb_compute(tsidb_handle* h, int n_envs, int ld_env, int ld_dof,
+                  const double* q, const double* v, const uint8_t* contact_mask,
+                  const tsidb_refs* refs, double* tau, double* ddq, double* f,
+                  int32_t* status, int32_t* iters, uint64_t* active_set,
+                  const tsidb_aux_out* aux, void* cuda_stream);
+
+/* Same tick with HOST buffers ([N][dof] row-major, contiguous): pinned staging,
+ * H2D, kernels, D2H inside the call; returns after the results are in host memory.
+ * This is the call the reference-side binding makes.            */
+int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, const double* v,
+                       const uint8_t* contact_mask, const tsidb_refs* refs_host,
+                       double* tau, double* ddq, double* f, int32_t* status, int32_t* iters,
+                       uint64_t* active_set);
+
+/* controller.integrate_dv(q, v, dv, dt) (ref:ctrl/WalkController.py:291-295,
+ * ref:legacy/biped.py:236-240): v_mean = v + dt/2*dv; v += dt*dv;
+ * q = pin.integrate(q, dt*v_mean).  In place on device arrays.                   */
+int tsidb_integrate(tsidb_handle* h, int n_envs, int ld_env, int ld_dof, double* q, double* v,
+                    const double* dv, double dt, void* cuda_stream);
+
+/* robot.framePosition / robot.com without a solve (ref:ctrl/WalkController.py:73,79,120,151):
+ * used at construction and at contact switches.                                   */
+int tsidb_kinematics(tsidb_handle* h, int n_envs, int ld_env, int ld_dof, const double* q,
+                     const double* v, const tsidb_aux_out* aux, void* cuda_stream);
+
+/* canonical one-sided inequality row numbering used by active_set:
+ *   block 0: LF force rows (17), block 1: RF force rows (17),
+ *   block 2: actuation rows (na), block 3: joint-bound rows (nv)
+ *   row = 2*offset(block) + side*rows(block) + i   (side 0 = lower, 1 = upper),
+ *   i.e. each two-sided block is stacked [lower rows; upper rows] exactly as
+ *   [UPSTREAM SolverHQuadProgFast] stacks CI.  Returns -1 when out of range.      */
+int tsidb_ci_row(const tsidb_handle* h, int block, int side, int i);
+
+/* measured FP64 DFMA throughput of this device (TFLOP/s), the roofline
+ * denominator for the solver kernels (BASELINE.md §2 asks for it).               */
+int tsidb_fp64_peak(int device, double* tflops_out);
+
+/* counters: kernel launches issued by this handle since creation */
+int64_t tsidb_launch_count(const tsidb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSIDB_H_ */
