@@ -54,4 +54,5 @@ template <class T> inline T __shfl_sync(unsigned, T x, int src) { return emu::ex
 template <class T> inline T __shfl_xor_sync(unsigned, T x, int m) { return emu::exchange(x, emu::W.cur ^ m); }
 inline void __syncwarp() { emu::barrier(); }
 inline void sincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
+inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 #endif

@@ -13,7 +13,8 @@ struct Job { const DevConst* C; double* sm; const TickArgs* a; int env; };
 static Job g_job;
 
 static void lane_entry(int lane) {
-  tick_env(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane);
+  if (g_job.C->nv == 26) tick_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane);
+  else tick_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane);
   emu::W.done[lane] = true;
   swapcontext(&emu::W.ctx[lane], &emu::W.sched);
 }

@@ -1,0 +1,143 @@
+#!/usr/bin/env python
+"""Join an ncu SASS-level source page (CSV) with nvdisasm line info of the same cubin and aggregate
+stall samples / executed instructions per CUDA source line range (kernel phase).
+
+usage: tools/ncu_by_line.py <report.ncu-rep> <lib.so> [kernel_name]
+"""
+import csv
+import os
+import re
+import subprocess
+import sys
+import tempfile
+from collections import defaultdict
+
+PHASES = None
+
+
+def phase_table(src):
+    """(start_line, name) from marker comments / function heads in tsidb_kernels.cuh"""
+    marks = []
+    pats = [
+        (r"^TSIDB_DEV void log6_dev", "log6"), (r"^TSIDB_DEV void k1_dynamics", "K1 dynamics"),
+        (r"^TSIDB_DEV void se3_rhs", "K2 se3_rhs"), (r"^TSIDB_DEV void k2_assemble", "K2 assemble"),
+        (r"^TSIDB_DEV int fvar0", "K3 row helpers"), (r"^TSIDB_DEV void qp_delete", "K3 delete_constraint"),
+        (r"^TSIDB_DEV int k3_solve", "K3 cholesky"), (r"B\[:, e\] = L\^-1 CE", "K3 build B = L^-1 CE^T"),
+        (r"Householder QR of B", "K3 QR of B"), (r"w_hat\[0:neq\]", "K3 w_hat / w0"),
+        (r"Q2 = Q \[0; I_m\]", "K3 form Q2"), (r"back-substitute with L\^T", "K3 J2 = L^-T Q2, x0"),
+        (r"active-set iterations on the reduced basis", "K3 AS setup"), (r"for \(;;\) \{ /\* l1 \*/", "K3 AS l1: s, psi"),
+        (r"for \(;;\) \{ /\* l2 \*/", "K3 AS l2: pick"), (r"for \(;;\) \{ /\* l2a \*/", "K3 AS l2a: d,z,r,steps"),
+        (r"if \(t == t2\) \{", "K3 AS add (Householder)"), (r"partial step: drop the blocking", "K3 AS partial-step drop"),
+        (r"^TSIDB_DEV void tick_env", "tick_env io/decode"), (r"^extern \"C\" __global__", "kernel loop"),
+    ]
+    for i, line in enumerate(open(src), 1):
+        for p, n in pats:
+            if re.search(p, line):
+                marks.append((i, n))
+    return sorted(marks)
+
+
+def main():
+    rep, so = sys.argv[1], sys.argv[2]
+    kern = sys.argv[3] if len(sys.argv) > 3 else "tsidb_tick_kernel"
+    src = os.path.join(os.path.dirname(so), "tsidb_kernels.cuh")
+    tmp = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    # instruction index -> (file, line)
+    lines_of = []
+    cur = (None, 0)
+    inside = False
+    for l in dis.splitlines():
+        if l.startswith("\t.section\t.text."):
+            inside = l.startswith(f"\t.section\t.text.{kern},")
+            continue
+        if not inside:
+            continue
+        m = re.match(r'\s*//## File "([^"]+)", line (\d+)', l)
+        if m:
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            continue
+        if re.match(r"\s*/\*[0-9a-f]{4,}\*/", l):
+            lines_of.append(cur)
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr = rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    body = rows[2:]
+    if len(body) != len(lines_of):
+        print(f"warning: {len(body)} SASS rows in the report, {len(lines_of)} in the cubin", file=sys.stderr)
+    marks = phase_table(src)
+    agg = defaultdict(lambda: [0, 0, 0, defaultdict(int)])
+    stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    tot_s = tot_i = 0
+    per_line = defaultdict(lambda: [0, 0])
+    for k, r in enumerate(body[: len(lines_of)]):
+        f, ln = lines_of[k]
+        smp = int(r[ix["# Samples"]] or 0)
+        ins = int(r[ix["Instructions Executed"]] or 0)
+        wf = int(r[ix["L1 Wavefronts Shared"]] or 0) if "L1 Wavefronts Shared" in ix else 0
+        name = "other"
+        if f == "tsidb_kernels.cuh":
+            for s, n in marks:
+                if ln >= s:
+                    name = n
+        a = agg[name]
+        a[0] += smp; a[1] += ins; a[2] += wf
+        for c in stall_cols:
+            v = int(r[ix[c]] or 0)
+            if v:
+                a[3][c] += v
+        tot_s += smp; tot_i += ins
+        per_line[(f, ln)][0] += smp; per_line[(f, ln)][1] += ins
+    print(f"{'phase':34s} {'samples%':>8s} {'inst%':>7s} {'smem wf (M)':>11s}  top stalls")
+    for name, (smp, ins, wf, st) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        top = sorted(st.items(), key=lambda kv: -kv[1])[:3]
+        print(f"{name:34s} {100*smp/max(1,tot_s):8.1f} {100*ins/max(1,tot_i):7.1f} {wf/1e6:11.1f}  " +
+              ", ".join(f"{k[6:]} {100*v/max(1,smp):.0f}%" for k, v in top))
+    print("\nhottest source lines:")
+    for (f, ln), (smp, ins) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:25]:
+        print(f"  {f}:{ln:5d}  samples {100*smp/max(1,tot_s):5.1f}%  inst {100*ins/max(1,tot_i):5.1f}%")
+
+
+
+
+def sass_size(so, kern="tsidb_tick_kernel"):
+    """SASS instruction count per phase (code size), no report needed: tools/ncu_by_line.py --size <lib.so>"""
+    src = os.path.join(os.path.dirname(so), "tsidb_kernels.cuh")
+    tmp = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    marks = phase_table(src)
+    cnt = defaultdict(int)
+    cur, inside, tot = (None, 0), False, 0
+    for l in dis.splitlines():
+        if l.startswith("\t.section\t.text."):
+            inside = kern in l
+            continue
+        if not inside:
+            continue
+        m = re.match(r'\s*//## File "([^"]+)", line (\d+)', l)
+        if m:
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            continue
+        if re.match(r"\s*/\*[0-9a-f]{4,}\*/", l):
+            name = "other"
+            if cur[0] == "tsidb_kernels.cuh":
+                for s, n in marks:
+                    if cur[1] >= s:
+                        name = n
+            cnt[name] += 1
+            tot += 1
+    for n, c in sorted(cnt.items(), key=lambda kv: -kv[1]):
+        print(f"{n:34s} {c:7d} instr  {c*16/1024:7.1f} KB")
+    print(f"{'total':34s} {tot:7d} instr  {tot*16/1024:7.1f} KB")
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "--size":
+        sass_size(sys.argv[2])
+    else:
+        main()

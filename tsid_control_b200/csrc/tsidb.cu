@@ -171,7 +171,12 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
     g_err = "tsidb_create: device offers less opt-in shared memory per block than the kernel needs";
     return -2;
   }
-  CK(cudaFuncSetAttribute(tsidb_tick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (h->dc.nv != 26 && h->dc.nv != 24) {
+    g_err = "tsidb_create: this build instantiates the tick kernel for nv = 26 (robot/v1) and nv = 24 (robot/v0)";
+    return -1;
+  }
+  CK(cudaFuncSetAttribute(tsidb_tick_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(tsidb_tick_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaMalloc(&h->counter, sizeof(int32_t)));
   if (upload_const(h) != 0) return -2;
   /* host-call staging: inputs q(nq) v(nv) refs(9+24+24+12+12+na); outputs tau(na) ddq(nv) f(24) */
@@ -239,7 +244,8 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st) {
   int blocks = (a.n_envs + warps - 1) / warps;
   if (blocks > h->sm_count) blocks = h->sm_count; /* persistent: one CTA per SM */
   const size_t smem = (size_t)warps * SM_PER_ENV * sizeof(double);
-  tsidb_tick_kernel<<<blocks, 32 * warps, smem, st>>>(a);
+  if (h->dc.nv == 26) tsidb_tick_kernel<26><<<blocks, 32 * warps, smem, st>>>(a);
+  else tsidb_tick_kernel<24><<<blocks, 32 * warps, smem, st>>>(a);
   CK(cudaGetLastError());
   h->launches += 1;
   return 0;

@@ -9,7 +9,7 @@
 #define TSIDB_NX 50    /* nv + 24                                                          */
 #define TSIDB_MRED 32  /* n - nEq = na + 6*nc <= 32: one lane per reduced coordinate       */
 #define TSIDB_WARPS_PER_BLOCK 6
-#define TSIDB_MAX_SLOTS 4
+#define TSIDB_MAX_SLOTS 6
 
 struct DevConst {
   int32_t nb, na, nv, nq;
@@ -74,10 +74,16 @@ struct DevConst {
 #define FR_COM 48  /* com 3, vcom 3, acom 3 */
 #define FR_L 57    /* angular momentum about the CoM 3, its drift 3 */
 /* union region, phase E (equality elimination) */
-#define UE_L 0                    /* L  26 x 27                   702 */
+#define UE_L 0                    /* H -> L  26 x 27              702 */
 #define UE_ILD (UE_L + 702)       /* 1/L_ii                        26 */
-#define UE_B (UE_ILD + 26)        /* B  50 x 19                   950 */
-#define UE_TAU (UE_B + 950)       /* Householder tau               18 */
+#define UE_TAU (UE_ILD + 26)      /* Householder tau               18 */
+#define UE_RD (UE_TAU + 18)       /* diagonal of R1 (beta)         18 */
+/* J2 region while the equalities are being eliminated (J2 itself is stored last) */
+#define JE_VT 0                   /* dense reflectors [18][N]     900 */
+#define JE_R1 (JE_VT + 900)       /* R1 [18][SM_LDB]              342 */
+#define JE_G (JE_R1 + 342)        /* gradient / Q^T w_unc / w_hat  50 */
+#define JE_COL (JE_G + 50)        /* published column              50 */
+#define JE_W0 (JE_COL + 50)       /* w0                            64 */
 /* union region, phase F (active set) */
 #define UF_R 0                    /* R packed by columns: col j at j(j+1)/2       528 */
 #define UF_IRD (UF_R + 528)       /* 1/R_jj                        32 */

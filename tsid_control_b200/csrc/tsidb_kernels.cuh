@@ -40,6 +40,7 @@ __constant__ DevConst g_const[TSIDB_MAX_SLOTS];
 #endif
 
 #define FULL 0xffffffffu
+#define SCHED_FENCE() asm volatile("" ::: "memory")
 #define TS_EPS 2.220446049250313e-16
 #define TS_INF 1.7976931348623157e308
 
@@ -577,7 +578,7 @@ TSIDB_DEV void k2_assemble(const DevConst& C, double* sm, const TickArgs& a, int
   const double* Jcom = sm + SM_oJcom;
   const double* Ag = sm + SM_oAg;
   double* H = sm + SM_oU + UE_L;
-  double* B = sm + SM_oU + UE_B;
+  double* gv = sm + SM_oJ2 + JE_G;
   const int j = lane;
   if (j < nv) {
     double jf[12], jc[3], ja[3] = {0, 0, 0};
@@ -616,10 +617,10 @@ TSIDB_DEV void k2_assemble(const DevConst& C, double* sm, const TickArgs& a, int
       g += C.w_am * ga;
     }
     if (j >= 6) g += C.w_post * bv[BV_POST + j - 6];
-    B[j * SM_LDB + neq] = -g; /* g itself (g = -sum w A^T b) */
+    gv[j] = -g; /* the QP gradient: g = -sum w A^T b */
   }
   /* force part of g is zero (force regularisation has zero reference) */
-  for (int k = nv + lane; k < n; k += 32) B[k * SM_LDB + neq] = 0.0;
+  for (int k = nv + lane; k < TSIDB_NX; k += 32) gv[k] = 0.0;
   __syncwarp();
 }
 
@@ -815,231 +816,305 @@ TSIDB_DEV void qp_delete(double* sm, int n, int& iq, int qq, int lane) {
   __syncwarp();
 }
 
-/* The full QP: returns status; on return x (sm+SM_oX) holds the solution, iters and the active words. */
-TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc, int n, int neq,
-                       int& iters_out, uint64_t* act_words) {
-  const int nv = C.nv, na = C.na;
-  const int m = n - neq; /* reduced dimension, <= 32 */
-  double* U = sm + SM_oU;
-  double* L = U + UE_L;
-  double* ild = U + UE_ILD;
-  double* B = U + UE_B;
-  double* tauq = U + UE_TAU;
-  double* J2 = sm + SM_oJ2;
-  double* x = sm + SM_oX;
-  double* x0 = sm + SM_oX0;
-  const double* Mm = sm + SM_oM;
-  const double* JF = sm + SM_oJF;
-  const double* bv = sm + SM_oBv;
-  iters_out = 0;
-  act_words[0] = act_words[1] = act_words[2] = 0;
+/* ---- register-blocked building blocks of the equality elimination (template on nv) ----
+ * Each lane keeps ONE column (of B, of Q2/J2) or ONE row (of the Cholesky factor) in registers; all
+ * register-array indices are compile-time constants (fully unrolled loops), the operands shared by the
+ * warp (factor entries, Householder vectors) are broadcast reads from shared memory. */
 
-  /* ---- Cholesky of the dv block (left-looking, lane <-> row), c1 = trace(H), c2 = trace(L^-T) ---- */
-  double c1 = 0.0;
-  {
-    double dg = (lane < nv) ? L[lane * SM_LDM + lane] : 0.0;
-    c1 = warp_sum(dg) + nc * C.Hf_trace;
+/* q <- L^-T q for the dv block (axpy form: the updates of one step are independent), then the constant
+ * force blocks q_f <- Lf^-T q_f */
+template <int NV>
+TSIDB_DEV void backsub_LT(double (&q)[NV + 24], const double* L, const double* ild, const DevConst& C, int nc) {
+#pragma unroll
+  for (int k = NV - 1; k >= 0; k--) {
+    SCHED_FENCE(); /* keep the compiler from hoisting the factor loads of later steps (register pressure) */
+    q[k] *= ild[k];
+#pragma unroll
+    for (int i = 0; i < k; i++) q[i] -= L[k * SM_LDM + i] * q[k];
   }
-  int bad = 0;
-  for (int j = 0; j < nv; j++) {
-    double s = 0.0;
-    if (lane >= j && lane < nv) {
-      double s0 = L[lane * SM_LDM + j], s1 = 0.0;
-      int k = 0;
-      for (; k + 1 < j; k += 2) {
-        s0 -= L[lane * SM_LDM + k] * L[j * SM_LDM + k];
-        s1 -= L[lane * SM_LDM + k + 1] * L[j * SM_LDM + k + 1];
-      }
-      if (k < j) s0 -= L[lane * SM_LDM + k] * L[j * SM_LDM + k];
-      s = s0 + s1;
-    }
-    double sj = shfl(s, j);
-    if (!(sj > 0.0)) { bad = 1; break; }
-    double ljj = sqrt(sj);
-    __syncwarp();
-    if (lane == j) { L[j * SM_LDM + j] = ljj; ild[j] = 1.0 / ljj; }
-    else if (lane > j && lane < nv) L[lane * SM_LDM + j] = s / ljj;
-    __syncwarp();
-  }
-  if (bad) return ST_INFEASIBLE; /* eiquadprog: Cholesky failure -> UNBOUNDED -> HQP_STATUS_INFEASIBLE */
-  double c2 = warp_sum(lane < nv ? ild[lane] : 0.0) + nc * C.Lfinv_trace;
-
-  /* ---- B[:, e] = L^-1 CE[e,:]^T for the neq equalities; column neq = L^-1 g (lane <-> column) ---- */
-  if (lane < neq) {
-    const int e = lane;
-    if (e < 6) {
-      /* base dynamics row e: [M(e,:) | -Jc(:,e)^T] */
-      for (int k = 0; k < nv; k++) B[k * SM_LDB + e] = Mm[e * SM_LDM + k];
-      for (int k = nv; k < n; k++) {
-        const int o = k - nv;
-        const int f = (mask == 3) ? (o / 12) : ((mask & 1) ? 0 : 1);
-        B[k * SM_LDB + e] = -jc_entry(C, JF, f, o % 12, e);
-      }
-    } else {
-      /* contact motion row: [JF_f(r,:) | 0], contacts in x order */
-      const int s = (e - 6) / 6, r = (e - 6) % 6;
-      const int f = (mask == 3) ? s : ((mask & 1) ? 0 : 1);
-      for (int k = 0; k < nv; k++) B[k * SM_LDB + e] = JF[(f * 6 + r) * TSIDB_NVX + k];
-      for (int k = nv; k < n; k++) B[k * SM_LDB + e] = 0.0;
-    }
-  }
-  __syncwarp();
-  if (lane <= neq) {
-    const int e = lane;
-    /* forward substitution with the dv block */
-    for (int i = 0; i < nv; i++) {
-      double s0 = B[i * SM_LDB + e], s1 = 0.0;
-      int k = 0;
-      for (; k + 1 < i; k += 2) {
-        s0 -= L[i * SM_LDM + k] * B[k * SM_LDB + e];
-        s1 -= L[i * SM_LDM + k + 1] * B[(k + 1) * SM_LDB + e];
-      }
-      if (k < i) s0 -= L[i * SM_LDM + k] * B[k * SM_LDB + e];
-      B[i * SM_LDB + e] = (s0 + s1) * ild[i];
-    }
-    /* force blocks: y = Lf^-1 b (constant inverse) */
-    for (int s = 0; s < nc; s++) {
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    if (s < nc) {
       double t[12];
 #pragma unroll
-      for (int i = 0; i < 12; i++) t[i] = B[(nv + 12 * s + i) * SM_LDB + e];
+      for (int i = 0; i < 12; i++) t[i] = q[NV + 12 * s + i];
+#pragma unroll
+      for (int i = 0; i < 12; i++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = i; k < 12; k++) acc += C.Lfinv[k][i] * t[k];
+        q[NV + 12 * s + i] = acc;
+      }
+    }
+  }
+}
+
+/* b <- L^-1 b (dv block, axpy form) and b_f <- Lf^-1 b_f */
+template <int NV>
+TSIDB_DEV void fwdsub_L(double (&b)[NV + 24], const double* L, const double* ild, const DevConst& C, int nc) {
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    SCHED_FENCE();
+    b[k] *= ild[k];
+#pragma unroll
+    for (int i = k + 1; i < NV; i++) b[i] -= L[i * SM_LDM + k] * b[k];
+  }
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    if (s < nc) {
+      double t[12];
+#pragma unroll
+      for (int i = 0; i < 12; i++) t[i] = b[NV + 12 * s + i];
 #pragma unroll
       for (int i = 0; i < 12; i++) {
         double acc = 0.0;
 #pragma unroll
         for (int k = 0; k <= i; k++) acc += C.Lfinv[i][k] * t[k];
-        B[(nv + 12 * s + i) * SM_LDB + e] = acc;
+        b[NV + 12 * s + i] = acc;
       }
     }
-    /* the last column is w_unc = -L^-1 g */
-    if (e == neq)
-      for (int k = 0; k < n; k++) B[k * SM_LDB + e] = -B[k * SM_LDB + e];
   }
-  __syncwarp();
+}
 
-  /* ---- Householder QR of B[:, 0:neq]; column neq (w_unc) is carried along ---- */
-  double R_norm = 1.0;
-  for (int i = 0; i < neq; i++) {
-    /* norm of B[i:, i] by all lanes (lanes over rows) */
-    double part = 0.0;
-    for (int k = i + 1 + lane; k < n; k += 32) { double t = B[k * SM_LDB + i]; part += t * t; }
-    double sigma = warp_sum(part);
-    double alpha = B[i * SM_LDB + i];
-    double nrm = sqrt(alpha * alpha + sigma);
-    double beta = (alpha >= 0.0) ? -nrm : nrm;
-    /* dependent equality row [eiquadprog add_constraint: |d(iq)| <= eps * R_norm] */
-    if (fabs(beta) <= TS_EPS * R_norm) return ST_ERROR;
-    R_norm = fmax(R_norm, fabs(beta));
-    double tau = (beta - alpha) / beta;
-    double scal = 1.0 / (alpha - beta);
-    __syncwarp();
-    for (int k = i + 1 + lane; k < n; k += 32) B[k * SM_LDB + i] *= scal; /* v, v[i] = 1 implicit */
-    if (lane == 0) { B[i * SM_LDB + i] = beta; tauq[i] = tau; }
-    __syncwarp();
-    if (lane > i && lane <= neq) {
-      const int c = lane;
-      double w0 = B[i * SM_LDB + c], w1 = 0.0;
-      int k = i + 1;
-      for (; k + 1 < n; k += 2) {
-        w0 += B[k * SM_LDB + i] * B[k * SM_LDB + c];
-        w1 += B[(k + 1) * SM_LDB + i] * B[(k + 1) * SM_LDB + c];
+/* c <- (I - tau v v^T) c with the dense reflector v (explicit zeros above its head, 1 at the head) */
+template <int N>
+TSIDB_DEV void reflect(double (&c)[N], const double* v, double tau) {
+  double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+#pragma unroll
+  for (int k = 0; k + 1 < N; k += 4) {
+    w0 += v[k] * c[k];
+    w1 += v[k + 1] * c[k + 1];
+    if (k + 2 < N) w2 += v[k + 2] * c[k + 2];
+    if (k + 3 < N) w3 += v[k + 3] * c[k + 3];
+  }
+  const double w = tau * ((w0 + w1) + (w2 + w3));
+#pragma unroll
+  for (int k = 0; k < N; k++) c[k] -= w * v[k];
+}
+
+/* The equality elimination.  In: H (dv block) in U+UE_L, gradient in JE_G, M/JF/bv from K1/K2.
+ * Out: x = x0 (the equality-constrained minimiser), J2 (n x m), c1*c2 product and R_norm; status 0 or an
+ * HQP error status. */
+template <int NV>
+TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, int nc, int n, int neq,
+                           double& c1c2, double& R_norm_out) {
+  constexpr int N = NV + 24;
+  const int m = n - neq;
+  double* U = sm + SM_oU;
+  double* L = U + UE_L;
+  double* ild = U + UE_ILD;
+  double* tauq = U + UE_TAU;
+  double* Rd = U + UE_RD;
+  double* JE = sm + SM_oJ2;
+  double* Vt = JE + JE_VT;   /* [neq][N] dense reflectors */
+  double* R1 = JE + JE_R1;   /* [18][SM_LDB] */
+  double* gv = JE + JE_G;    /* gradient, later Q^T w_unc / w_hat */
+  double* colp = JE + JE_COL;
+  double* w0v = JE + JE_W0;
+  double* J2 = sm + SM_oJ2;
+  double* x = sm + SM_oX;
+  const double* Mm = sm + SM_oM;
+  const double* JF = sm + SM_oJF;
+  const double* bv = sm + SM_oBv;
+
+  /* ---- Cholesky of the dv block: lane i keeps row i; c1 = trace(H), c2 = trace(L^-T) ---- */
+  double c1, c2;
+  {
+    const int i = lane < NV ? lane : NV - 1;
+    double l[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) l[k] = L[i * SM_LDM + k];
+    c1 = warp_sum(lane < NV ? L[i * SM_LDM + i] : 0.0) + nc * C.Hf_trace;
+    bool bad = false;
+    double c2p = 0.0;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      double a0 = l[j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < j; k++) {
+        const double ljk = L[j * SM_LDM + k];
+        if ((k & 3) == 0) a0 -= l[k] * ljk;
+        else if ((k & 3) == 1) a1 -= l[k] * ljk;
+        else if ((k & 3) == 2) a2 -= l[k] * ljk;
+        else a3 -= l[k] * ljk;
       }
-      if (k < n) w0 += B[k * SM_LDB + i] * B[k * SM_LDB + c];
-      double w = tau * (w0 + w1);
-      B[i * SM_LDB + c] -= w;
-      for (k = i + 1; k < n; k++) B[k * SM_LDB + c] -= w * B[k * SM_LDB + i];
+      const double s = (a0 + a1) + (a2 + a3);
+      const double sj = shfl(s, j);
+      if (!(sj > 0.0)) bad = true;
+      const double inv = rsqrt(sj);
+      l[j] = (lane == j) ? sj * inv : s * inv;
+      c2p += inv;
+      __syncwarp();
+      if (lane >= j && lane < NV) L[lane * SM_LDM + j] = l[j];
+      if (lane == j) ild[j] = inv;
+      __syncwarp();
+    }
+    if (bad) return ST_INFEASIBLE; /* eiquadprog: Cholesky failure -> UNBOUNDED -> HQP_STATUS_INFEASIBLE */
+    c2 = c2p + nc * C.Lfinv_trace;
+  }
+  c1c2 = c1 * c2;
+
+  /* ---- B = L^-1 [CE^T | g]: lane e keeps column e; Householder QR; the last column becomes Q^T w_unc ---- */
+  double R_norm = 1.0;
+  {
+    double b[N];
+    const int e = lane;
+    const int f0 = (mask & 1) ? 0 : 1; /* foot of force block 0 */
+#pragma unroll
+    for (int k = 0; k < N; k++) b[k] = 0.0;
+    if (e < 6) {
+      /* base dynamics row e: [M(e,:) | -Jc(:,e)^T] */
+#pragma unroll
+      for (int k = 0; k < NV; k++) b[k] = Mm[e * SM_LDM + k];
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        if (s < nc) {
+          const int f = (s == 0) ? f0 : 1;
+          double jf[6];
+#pragma unroll
+          for (int r = 0; r < 6; r++) jf[r] = JF[(f * 6 + r) * TSIDB_NVX + e];
+#pragma unroll
+          for (int o = 0; o < 12; o++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) acc += C.T[r][o] * jf[r];
+            b[NV + 12 * s + o] = -acc;
+          }
+        }
+      }
+    } else if (e < neq) {
+      /* contact motion row: [JF_f(r,:) | 0], contacts in x order */
+      const int s = (e - 6) / 6, r = (e - 6) % 6;
+      const int f = (s == 0) ? f0 : 1;
+#pragma unroll
+      for (int k = 0; k < NV; k++) b[k] = JF[(f * 6 + r) * TSIDB_NVX + k];
+    } else if (e == neq) {
+#pragma unroll
+      for (int k = 0; k < N; k++) b[k] = gv[k];
+    }
+    fwdsub_L<NV>(b, L, ild, C, nc);
+    if (e == neq) {
+#pragma unroll
+      for (int k = 0; k < N; k++) b[k] = -b[k]; /* w_unc = -L^-1 g */
+    }
+    for (int i = 0; i < neq; i++) {
+      __syncwarp();
+      if (lane == i) {
+#pragma unroll
+        for (int k = 0; k < N; k++) colp[k] = b[k];
+      }
+      __syncwarp();
+      double part = 0.0;
+      for (int k = i + 1 + lane; k < n; k += 32) { const double t = colp[k]; part += t * t; }
+      const double sigma = warp_sum(part);
+      const double alpha = colp[i];
+      const double nrm = sqrt(alpha * alpha + sigma);
+      const double beta = (alpha >= 0.0) ? -nrm : nrm;
+      /* dependent equality row [eiquadprog add_constraint: |d(iq)| <= eps * R_norm] */
+      if (fabs(beta) <= TS_EPS * R_norm) return ST_ERROR;
+      R_norm = fmax(R_norm, fabs(beta));
+      const double tau = (beta - alpha) / beta;
+      const double scal = 1.0 / (alpha - beta);
+      for (int k = lane; k < N; k += 32) Vt[i * N + k] = (k < i || k >= n) ? 0.0 : ((k == i) ? 1.0 : colp[k] * scal);
+      if (lane == 0) { tauq[i] = tau; Rd[i] = beta; }
+      __syncwarp();
+      if (lane > i && lane <= neq) reflect<N>(b, Vt + i * N, tau);
+    }
+    __syncwarp();
+    /* R1 (strictly upper part; the diagonal is Rd) and the carried column */
+    if (lane <= neq) {
+#pragma unroll
+      for (int k = 0; k < 18; k++)
+        if (k < neq) R1[k * SM_LDB + lane] = b[k];
+    }
+    if (lane == neq) {
+#pragma unroll
+      for (int k = 0; k < N; k++) gv[k] = b[k];
     }
     __syncwarp();
   }
-  /* ---- w_hat[0:neq] = -R1^-T ce0 (forward substitution, lane <-> equation) ----
-   * ce0 = -rhs: base rows rhs = -h_u, motion rows rhs = b_mot  =>  -ce0 = rhs              */
+  /* ---- w_hat[0:neq] = R1^-T rhs (forward substitution, lane <-> equation); rhs = -ce0 ---- */
   {
     double rhs = 0.0;
     if (lane < neq) {
       if (lane < 6) rhs = -sm[SM_oNle + lane];
       else {
         const int s = (lane - 6) / 6, r = (lane - 6) % 6;
-        const int f = (mask == 3) ? s : ((mask & 1) ? 0 : 1);
+        const int f = (s == 0) ? ((mask & 1) ? 0 : 1) : 1;
         rhs = bv[BV_MOT + 6 * f + r];
       }
     }
     double accv = rhs;
     for (int i = 0; i < neq; i++) {
-      double wi = shfl(accv, i) / B[i * SM_LDB + i];
+      const double wi = shfl(accv, i) / Rd[i];
       if (lane == i) accv = wi;
-      else if (lane > i && lane < neq) accv -= B[i * SM_LDB + lane] * wi;
+      else if (lane > i && lane < neq) accv -= R1[i * SM_LDB + lane] * wi;
     }
-    __syncwarp();
-    if (lane < neq) B[lane * SM_LDB + neq] = accv;
+    if (lane < neq) gv[lane] = accv;
     __syncwarp();
   }
-  /* ---- w0 = Q w_hat: reflectors in reverse, lanes over rows; result -> x0 (still in w space) ---- */
+  /* ---- w0 = Q w_hat: reflectors in reverse, lanes over rows ---- */
   {
-    /* each lane keeps rows lane, lane+32 of the vector */
-    double y0 = (lane < n) ? B[lane * SM_LDB + neq] : 0.0;
-    double y1 = (lane + 32 < n) ? B[(lane + 32) * SM_LDB + neq] : 0.0;
+    double y0 = (lane < n) ? gv[lane] : 0.0;
+    double y1 = (lane + 32 < n) ? gv[lane + 32] : 0.0;
     for (int i = neq - 1; i >= 0; i--) {
-      double v0 = (lane == i) ? 1.0 : ((lane > i && lane < n) ? B[lane * SM_LDB + i] : 0.0);
-      double v1 = (lane + 32 > i && lane + 32 < n) ? B[(lane + 32) * SM_LDB + i] : 0.0;
-      if (lane + 32 == i) v1 = 1.0;
-      double w = tauq[i] * warp_sum(v0 * y0 + v1 * y1);
+      const double v0 = Vt[i * N + lane];
+      const double v1 = (lane + 32 < N) ? Vt[i * N + lane + 32] : 0.0;
+      const double w = tauq[i] * warp_sum(v0 * y0 + v1 * y1);
       y0 -= w * v0;
       y1 -= w * v1;
     }
-    if (lane < n) x0[lane] = y0;
-    if (lane + 32 < n) x0[lane + 32] = y1;
+    w0v[lane] = y0;
+    if (lane + 32 < N) w0v[lane + 32] = y1;
+    __syncwarp();
   }
-  /* ---- Q2 = Q [0; I_m]: lane <-> column, built in place in J2 ---- */
-  if (lane < m) {
-    const int c = lane;
-    for (int k = 0; k < n; k++) J2[k * SM_LDJ + c] = (k == neq + c) ? 1.0 : 0.0;
-    for (int i = neq - 1; i >= 0; i--) {
-      double w0 = J2[i * SM_LDJ + c], w1 = 0.0;
-      int k = i + 1;
-      for (; k + 1 < n; k += 2) {
-        w0 += B[k * SM_LDB + i] * J2[k * SM_LDJ + c];
-        w1 += B[(k + 1) * SM_LDB + i] * J2[(k + 1) * SM_LDJ + c];
-      }
-      if (k < n) w0 += B[k * SM_LDB + i] * J2[k * SM_LDJ + c];
-      double w = tauq[i] * (w0 + w1);
-      J2[i * SM_LDJ + c] -= w;
-      for (k = i + 1; k < n; k++) J2[k * SM_LDJ + c] -= w * B[k * SM_LDB + i];
+  /* ---- x0 = L^-T w0 (every lane computes it redundantly from broadcast reads; lane 0 stores) ---- */
+  {
+    double q[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) q[k] = w0v[k];
+    backsub_LT<NV>(q, L, ild, C, nc);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < N; k++) x[k] = q[k];
     }
   }
-  __syncwarp();
-  /* ---- back-substitute with L^T: x0 = L^-T w0 (one extra column, lane m if free, else a second pass),
-   *      J2[:, c] = L^-T Q2[:, c] ---- */
-  for (int pass = 0; pass < 2; pass++) {
-    const bool mine = pass == 0 ? (lane < m) : (lane == 0);
-    if (mine) {
-      double* col = pass == 0 ? (J2 + lane) : x0;
-      const int ld = pass == 0 ? SM_LDJ : 1;
-      for (int i = nv - 1; i >= 0; i--) {
-        double s0 = col[i * ld], s1 = 0.0;
-        int k = i + 1;
-        for (; k + 1 < nv; k += 2) {
-          s0 -= L[k * SM_LDM + i] * col[k * ld];
-          s1 -= L[(k + 1) * SM_LDM + i] * col[(k + 1) * ld];
-        }
-        if (k < nv) s0 -= L[k * SM_LDM + i] * col[k * ld];
-        col[i * ld] = (s0 + s1) * ild[i];
-      }
-      for (int s = 0; s < nc; s++) {
-        double t[12];
+  /* ---- J2[:, c] = L^-T Q [0; e_c]: lane c keeps the column in registers ---- */
+  {
+    double q[N];
+    if (lane < m) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) t[i] = col[(nv + 12 * s + i) * ld];
+      for (int k = 0; k < N; k++) q[k] = (k == neq + lane) ? 1.0 : 0.0;
+      for (int i = neq - 1; i >= 0; i--) reflect<N>(q, Vt + i * N, tauq[i]);
+      backsub_LT<NV>(q, L, ild, C, nc);
+    }
+    __syncwarp(); /* every lane is done with Vt / R1 / w0, which live in the J2 region */
+    if (lane < m) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) {
-          double acc = 0.0;
-#pragma unroll
-          for (int k = i; k < 12; k++) acc += C.Lfinv[k][i] * t[k];
-          col[(nv + 12 * s + i) * ld] = acc;
-        }
-      }
+      for (int k = 0; k < N; k++) J2[k * SM_LDJ + lane] = q[k];
     }
     __syncwarp();
   }
-  for (int k = lane; k < n; k += 32) x[k] = x0[k];
-  __syncwarp();
+  R_norm_out = R_norm;
+  return ST_OPTIMAL;
+}
+
+/* The full QP: returns status; on return x (sm+SM_oX) holds the solution, iters and the active words. */
+template <int NV>
+TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc, int n, int neq,
+                       int& iters_out, uint64_t* act_words) {
+  const int nv = C.nv, na = C.na;
+  const int m = n - neq; /* reduced dimension, <= 32 */
+  double* U = sm + SM_oU;
+  double* J2 = sm + SM_oJ2;
+  double* x = sm + SM_oX;
+  iters_out = 0;
+  act_words[0] = act_words[1] = act_words[2] = 0;
+  double c1c2 = 0.0, R_norm = 1.0;
+  {
+    const int st = k3_eliminate<NV>(C, sm, lane, mask, nc, n, neq, c1c2, R_norm);
+    if (st != ST_OPTIMAL) return st;
+  }
 
   /* ================= active-set iterations on the reduced basis ================= */
   double* Rp = U + UF_R;
@@ -1057,7 +1132,7 @@ TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc
 
   const int ncid = cid_count(C);
   const int nin_ref = C.nin_ref_fixed + 34 * nc;
-  const double psi_thresh = (double)nin_ref * TS_EPS * c1 * c2 * 100.0;
+  const double psi_thresh = (double)nin_ref * TS_EPS * c1c2 * 100.0;
   int iq = 0, iter = 0, status = ST_OPTIMAL;
   unsigned actbits = 0;  /* lane owns cids lane + 32*b, b = 0..3: bit b = in the working set */
   unsigned exclbits = 0;
@@ -1278,6 +1353,7 @@ TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc
 }
 
 /* ================================================================= the tick of one env */
+template <int NV>
 TSIDB_DEV void tick_env(const DevConst& C, double* sm, const TickArgs& a, int env, int lane) {
   const int nv = C.nv, na = C.na, nq = C.nq;
   /* stage q, v */
@@ -1302,7 +1378,7 @@ TSIDB_DEV void tick_env(const DevConst& C, double* sm, const TickArgs& a, int en
   k2_assemble(C, sm, a, env, lane, mask, neq, n);
   int iters = 0;
   uint64_t words[3];
-  int status = k3_solve(C, sm, lane, mask, nc, n, neq, iters, words);
+  int status = k3_solve<NV>(C, sm, lane, mask, nc, n, neq, iters, words);
   const bool ok = (status == ST_OPTIMAL || status == ST_MAX_ITER);
   const double* x = sm + SM_oX;
   double* wr = sm + SM_oX0;
@@ -1343,7 +1419,8 @@ TSIDB_DEV void tick_env(const DevConst& C, double* sm, const TickArgs& a, int en
 }
 
 #ifndef TSIDB_EMU
-extern "C" __global__ void __launch_bounds__(32 * TSIDB_WARPS_PER_BLOCK, 1)
+template <int NV>
+__global__ void __launch_bounds__(32 * TSIDB_WARPS_PER_BLOCK, 1)
 tsidb_tick_kernel(const TickArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1354,7 +1431,7 @@ tsidb_tick_kernel(const TickArgs a) {
     if (lane == 0) env = atomicAdd(a.counter, 1);
     env = __shfl_sync(FULL, env, 0);
     if (env >= a.n_envs) break;
-    tick_env(C, sm, a, env, lane);
+    tick_env<NV>(C, sm, a, env, lane);
   }
 }
 #endif
