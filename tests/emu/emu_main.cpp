@@ -9,12 +9,16 @@ static DevConst g_const[TSIDB_MAX_SLOTS];
 
 namespace emu { Warp W; }
 
-struct Job { const DevConst* C; double* sm; const TickArgs* a; int env; };
+struct Job { const DevConst* C; double* sm; const TickArgs* a; int env; int stage; };
 static Job g_job;
 
 static void lane_entry(int lane) {
-  if (g_job.C->nv == 26) tick_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane);
-  else tick_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane);
+  if (g_job.stage == 0) {
+    if (g_job.C->nv == 26) prepare_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
+    else prepare_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
+  } else {
+    activeset_env(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
+  }
   emu::W.done[lane] = true;
   swapcontext(&emu::W.ctx[lane], &emu::W.sched);
 }
@@ -35,39 +39,57 @@ extern "C" int emu_fill_const(const tsidb_model* m, const tsidb_conf* c, const d
 }
 
 /* run envs [0, n_envs) sequentially; also returns a copy of the shared-memory image of the LAST env */
-extern "C" int emu_tick(const TickArgs* a, double* sm_out) {
+static int run_warp(int env) {
+  const size_t STK = 1 << 20;
+  emu::Warp& W = emu::W;
+  W.arrived = 0;
+  for (int l = 0; l < 32; l++) {
+    W.done[l] = false;
+    getcontext(&W.ctx[l]);
+    W.ctx[l].uc_stack.ss_sp = W.stacks + l * STK;
+    W.ctx[l].uc_stack.ss_size = STK;
+    W.ctx[l].uc_link = &W.sched;
+    makecontext(&W.ctx[l], (void (*)())lane_entry, 1, l);
+  }
+  long spins = 0;
+  for (;;) {
+    bool all = true;
+    for (int l = 0; l < 32; l++) {
+      if (W.done[l]) continue;
+      all = false;
+      W.cur = l;
+      swapcontext(&W.sched, &W.ctx[l]);
+    }
+    if (all) break;
+    if (++spins > 3000000L) { fprintf(stderr, "emu: env %d: lanes diverged at a collective (deadlock)\n", env); return -2; }
+  }
+  if (W.arrived != 0) { fprintf(stderr, "emu: env %d: %d lanes left waiting at a collective\n", env, W.arrived); return -3; }
+  return 0;
+}
+
+/* run envs [0, n_envs) sequentially through both kernels' per-env bodies (prepare, then active set);
+ * also returns a copy of the active-set shared-memory image of the LAST env */
+extern "C" int emu_tick(const TickArgs* a_in, double* sm_out) {
   const size_t STK = 1 << 20;
   emu::Warp& W = emu::W;
   if (!W.stacks) W.stacks = (char*)malloc(32 * STK);
-  double* sm = (double*)calloc(SM_PER_ENV, sizeof(double));
-  for (int env = 0; env < a->n_envs; env++) {
-    for (int k = 0; k < SM_PER_ENV; k++) sm[k] = NAN; /* poison: catches reads of unwritten smem */
-    g_job = Job{&g_const[0], sm, a, env};
-    W.arrived = 0;
-    for (int l = 0; l < 32; l++) {
-      W.done[l] = false;
-      getcontext(&W.ctx[l]);
-      W.ctx[l].uc_stack.ss_sp = W.stacks + l * STK;
-      W.ctx[l].uc_stack.ss_size = STK;
-      W.ctx[l].uc_link = &W.sched;
-      makecontext(&W.ctx[l], (void (*)())lane_entry, 1, l);
+  TickArgs a = *a_in;
+  const int smn = SM_PER_ENV > SA_PER_ENV ? SM_PER_ENV : SA_PER_ENV;
+  double* sm = (double*)calloc(smn, sizeof(double));
+  double* ws = (double*)calloc((size_t)a.n_envs * SA_IMAGE, sizeof(double));
+  a.ws = ws;
+  a.perm = nullptr;
+  int rc = 0;
+  for (int env = 0; env < a.n_envs && rc == 0; env++) {
+    for (int stage = 0; stage < (a.kin_only ? 1 : 2) && rc == 0; stage++) {
+      for (int k = 0; k < smn; k++) sm[k] = NAN; /* poison: catches reads of unwritten smem */
+      g_job = Job{&g_const[0], sm, &a, env, stage};
+      rc = run_warp(env);
     }
-    long spins = 0;
-    for (;;) {
-      bool all = true;
-      for (int l = 0; l < 32; l++) {
-        if (W.done[l]) continue;
-        all = false;
-        W.cur = l;
-        swapcontext(&W.sched, &W.ctx[l]);
-      }
-      if (all) break;
-      if (++spins > 3000000L) { fprintf(stderr, "emu: env %d: lanes diverged at a collective (deadlock)\n", env); free(sm); return -2; }
-    }
-    if (W.arrived != 0) { fprintf(stderr, "emu: env %d: %d lanes left waiting at a collective\n", env, W.arrived); free(sm); return -3; }
   }
-  if (sm_out) memcpy(sm_out, sm, SM_PER_ENV * sizeof(double));
+  if (sm_out) memcpy(sm_out, sm, SA_PER_ENV * sizeof(double));
   free(sm);
-  return 0;
+  free(ws);
+  return rc;
 }
-extern "C" int emu_sm_per_env() { return SM_PER_ENV; }
+extern "C" int emu_sm_per_env() { return SM_PER_ENV > SA_PER_ENV ? SM_PER_ENV : SA_PER_ENV; }

@@ -22,18 +22,21 @@ def phase_table(src):
         (r"^TSIDB_DEV void log6_dev", "log6"), (r"^TSIDB_DEV void k1_dynamics", "K1 dynamics"),
         (r"^TSIDB_DEV void se3_rhs", "K2 se3_rhs"), (r"^TSIDB_DEV void k2_assemble", "K2 assemble"),
         (r"^TSIDB_DEV int fvar0", "K3 row helpers"), (r"^TSIDB_DEV void qp_delete", "K3 delete_constraint"),
-        (r"^TSIDB_DEV int k3_solve", "K3 cholesky"), (r"B\[:, e\] = L\^-1 CE", "K3 build B = L^-1 CE^T"),
-        (r"Householder QR of B", "K3 QR of B"), (r"w_hat\[0:neq\]", "K3 w_hat / w0"),
-        (r"Q2 = Q \[0; I_m\]", "K3 form Q2"), (r"back-substitute with L\^T", "K3 J2 = L^-T Q2, x0"),
-        (r"active-set iterations on the reduced basis", "K3 AS setup"), (r"for \(;;\) \{ /\* l1 \*/", "K3 AS l1: s, psi"),
+        (r"^TSIDB_DEV void backsub_LT", "E backsub_LT"), (r"^TSIDB_DEV void fwdsub_L", "E fwdsub_L"),
+        (r"^TSIDB_DEV void reflect", "E reflect"), (r"^TSIDB_DEV int k3_eliminate", "E setup"),
+        (r"Cholesky of the dv block: lane i keeps row", "E cholesky"), (r"B = L\^-1 \[CE\^T \| g\]", "E build B + QR"),
+        (r"w_hat\[0:neq\] = R1\^-T", "E w_hat"), (r"w0 = Q w_hat", "E w0"), (r"x0 = L\^-T w0", "E x0"),
+        (r"J2\[:, c\] = L\^-T Q", "E J2 columns"),
+        (r"^TSIDB_DEV int k3_solve", "K3 AS setup"), (r"for \(;;\) \{ /\* l1 \*/", "K3 AS l1: s, psi"),
         (r"for \(;;\) \{ /\* l2 \*/", "K3 AS l2: pick"), (r"for \(;;\) \{ /\* l2a \*/", "K3 AS l2a: d,z,r,steps"),
         (r"if \(t == t2\) \{", "K3 AS add (Householder)"), (r"partial step: drop the blocking", "K3 AS partial-step drop"),
-        (r"^TSIDB_DEV void tick_env", "tick_env io/decode"), (r"^extern \"C\" __global__", "kernel loop"),
+        (r"^TSIDB_DEV void tick_env", "tick_env io/decode"), (r"^__global__ void", "kernel loop"),
     ]
     for i, line in enumerate(open(src), 1):
         for p, n in pats:
             if re.search(p, line):
                 marks.append((i, n))
+                break
     return sorted(marks)
 
 

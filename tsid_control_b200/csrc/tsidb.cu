@@ -28,7 +28,10 @@ static bool g_slot_used[8][TSIDB_MAX_SLOTS]; /* per device */
 struct tsidb_handle {
   int device, slot, max_envs, sm_count;
   DevConst dc;
-  int32_t* counter;      /* device: dynamic work counter */
+  int32_t* counter;      /* device: [0] work counter of the active-set kernel, [1..3] class counts */
+  double* ws;            /* device: hand-off images, SA_IMAGE doubles per slot */
+  int32_t* perm;         /* device: slot -> env */
+  int32_t* cls_pos;      /* device: per-env (class, position) */
   int64_t launches;
   /* staging for tsidb_compute_host */
   double *h_in, *h_out;  /* pinned */
@@ -172,12 +175,21 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
     return -2;
   }
   if (h->dc.nv != 26 && h->dc.nv != 24) {
-    g_err = "tsidb_create: this build instantiates the tick kernel for nv = 26 (robot/v1) and nv = 24 (robot/v0)";
+    g_err = "tsidb_create: this build instantiates the tick kernels for nv = 26 (robot/v1) and nv = 24 (robot/v0)";
     return -1;
   }
-  CK(cudaFuncSetAttribute(tsidb_tick_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(tsidb_tick_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaMalloc(&h->counter, sizeof(int32_t)));
+  const size_t smem_as = (size_t)TSIDB_AS_WARPS * SA_PER_ENV * sizeof(double);
+  if ((size_t)prop.sharedMemPerBlockOptin < smem_as) {
+    g_err = "tsidb_create: device offers less opt-in shared memory per block than the active-set kernel needs";
+    return -2;
+  }
+  CK(cudaFuncSetAttribute(tsidb_prepare_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(tsidb_prepare_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(tsidb_activeset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_as));
+  CK(cudaMalloc(&h->counter, 4 * sizeof(int32_t)));
+  CK(cudaMalloc(&h->ws, (size_t)max_envs * SA_IMAGE * sizeof(double)));
+  CK(cudaMalloc(&h->perm, (size_t)max_envs * sizeof(int32_t)));
+  CK(cudaMalloc(&h->cls_pos, (size_t)max_envs * sizeof(int32_t)));
   if (upload_const(h) != 0) return -2;
   /* host-call staging: inputs q(nq) v(nv) refs(9+24+24+12+12+na); outputs tau(na) ddq(nv) f(24) */
   const int na = h->dc.na, nv = h->dc.nv, nq = h->dc.nq;
@@ -200,7 +212,7 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
 extern "C" void tsidb_destroy(tsidb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaFree(h->counter);
+  cudaFree(h->counter); cudaFree(h->ws); cudaFree(h->perm); cudaFree(h->cls_pos);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFree(h->d_in); cudaFree(h->d_out);
   cudaFreeHost(h->h_mask); cudaFree(h->d_mask);
   cudaFreeHost(h->h_int); cudaFree(h->d_int);
@@ -237,17 +249,42 @@ extern "C" int tsidb_set_default_refs(tsidb_handle* h, const double* com9, const
 
 static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st) {
   CK(cudaSetDevice(h->device));
+  if (a.n_envs > h->max_envs) { g_err = "n_envs exceeds the handle's max_envs (workspace size)"; return -1; }
   a.counter = h->counter;
   a.slot = h->slot;
-  CK(cudaMemsetAsync(h->counter, 0, sizeof(int32_t), st));
-  const int warps = TSIDB_WARPS_PER_BLOCK;
-  int blocks = (a.n_envs + warps - 1) / warps;
-  if (blocks > h->sm_count) blocks = h->sm_count; /* persistent: one CTA per SM */
-  const size_t smem = (size_t)warps * SM_PER_ENV * sizeof(double);
-  if (h->dc.nv == 26) tsidb_tick_kernel<26><<<blocks, 32 * warps, smem, st>>>(a);
-  else tsidb_tick_kernel<24><<<blocks, 32 * warps, smem, st>>>(a);
-  CK(cudaGetLastError());
-  h->launches += 1;
+  a.ws = h->ws;
+  a.perm = nullptr;
+  const int n = a.n_envs;
+  if (!a.kin_only) {
+    CK(cudaMemsetAsync(h->counter, 0, 4 * sizeof(int32_t), st));
+    if (a.mask) {
+      /* class sort (double support, single support, flight) -> slot order */
+      const int th = 256;
+      tsidb_classify_kernel<<<(n + th - 1) / th, th, 0, st>>>(n, a.mask, h->cls_pos, h->counter + 1);
+      tsidb_permute_kernel<<<(n + th - 1) / th, th, 0, st>>>(n, h->cls_pos, h->counter + 1, h->perm);
+      a.perm = h->perm;
+      h->launches += 2;
+    }
+  }
+  {
+    const int warps = TSIDB_WARPS_PER_BLOCK;
+    int blocks = (n + warps - 1) / warps;
+    if (blocks > h->sm_count) blocks = h->sm_count; /* persistent: one CTA per SM */
+    const size_t smem = (size_t)warps * SM_PER_ENV * sizeof(double);
+    if (h->dc.nv == 26) tsidb_prepare_kernel<26><<<blocks, 32 * warps, smem, st>>>(a);
+    else tsidb_prepare_kernel<24><<<blocks, 32 * warps, smem, st>>>(a);
+    CK(cudaGetLastError());
+    h->launches += 1;
+  }
+  if (!a.kin_only) {
+    const int warps = TSIDB_AS_WARPS;
+    int blocks = (n + warps - 1) / warps;
+    if (blocks > h->sm_count) blocks = h->sm_count;
+    const size_t smem = (size_t)warps * SA_PER_ENV * sizeof(double);
+    tsidb_activeset_kernel<<<blocks, 32 * warps, smem, st>>>(a);
+    CK(cudaGetLastError());
+    h->launches += 1;
+  }
   return 0;
 }
 

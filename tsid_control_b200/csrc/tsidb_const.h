@@ -94,8 +94,7 @@ struct DevConst {
 #define UF_U (UF_Z + 50)          /* u                             34 */
 #define UF_UO (UF_U + 34)         /* u_old                         34 */
 #define UF_XO (UF_UO + 34)        /* x_old                         50 */
-#define UF_S (UF_XO + 50)         /* s                            128 */
-#define UF_A (UF_S + 128)         /* A, A_old as int32: 2 x 34 ints = 34 doubles */
+#define UF_A (UF_XO + 50)         /* A, A_old as int32: 2 x 34 ints = 34 doubles */
 #define UF_END (UF_A + 34)
 
 struct TickArgs {
@@ -116,7 +115,9 @@ struct TickArgs {
   double* o_com;      /* aux outputs, may be null */
   double* o_foot[2];
   double* o_wrench;
-  int32_t* counter;   /* dynamic work counter */
+  int32_t* counter;   /* dynamic work counter of the active-set kernel */
+  double* ws;         /* hand-off images, SA_IMAGE doubles per slot */
+  const int32_t* perm; /* slot -> env (class sort), null = identity */
   int32_t kin_only;   /* stop after the kinematics (tsidb_kinematics) */
   int32_t slot;       /* constant-memory slot of the handle */
 };

@@ -41,6 +41,14 @@ __constant__ DevConst g_const[TSIDB_MAX_SLOTS];
 
 #define FULL 0xffffffffu
 #define SCHED_FENCE() asm volatile("" ::: "memory")
+/* CTA-wide phase alignment: the warps of a CTA work on different envs but run the same phase at the same
+ * time, so an instruction-cache line fetched by one warp serves all of them (the kernel is fetch-bound
+ * otherwise: profiles/ r1b).  A no-op in the single-warp host emulation. */
+#ifdef TSIDB_EMU
+#define PHASE_SYNC() ((void)0)
+#else
+#define PHASE_SYNC() __syncthreads()
+#endif
 #define TS_EPS 2.220446049250313e-16
 #define TS_INF 1.7976931348623157e308
 
@@ -625,197 +633,6 @@ TSIDB_DEV void k2_assemble(const DevConst& C, double* sm, const TickArgs& a, int
 }
 
 /* ================================================================= K3: the QP */
-/* x index of foot f's first force variable */
-TSIDB_DEV int fvar0(int nv, int mask, int f) { return nv + ((f == 1 && (mask & 1)) ? 12 : 0); }
-
-/* Jc entry: (T^T JF_f)[j][col] for contact f, force component j (0..11), dv column col */
-TSIDB_DEV double jc_entry(const DevConst& C, const double* JF, int f, int j, int col) {
-  double s = 0.0;
-#pragma unroll
-  for (int k = 0; k < 6; k++) s += C.T[k][j] * JF[(f * 6 + k) * TSIDB_NVX + col];
-  return s;
-}
-
-/* one-sided candidate rows ("cid"), fixed numbering:
- *   0..31   friction pyramid upper sides: f = cid/16, corner = (cid%16)/4, k = cid%4
- *   32..35  normal force: f = (cid-32)/2, side = (cid-32)%2  (0: >= fmin, 1: <= fmax)
- *   36..36+2na-1        actuation, side-major
- *   36+2na..36+4na-1    joint (velocity) bounds, side-major
- * The never-active sides of the reference's two-sided blocks (friction lower side at -1e10, the six
- * base rows of the joint-bounds block at +-1e10) are not enumerated: they can neither be violated
- * nor change the violation sum. */
-TSIDB_DEV int cid_count(const DevConst& C) { return 36 + 4 * C.na; }
-TSIDB_DEV bool cid_valid(const DevConst& C, int cid, int mask) {
-  const int na = C.na;
-  if (cid < 32) return (mask >> (cid >> 4)) & 1;
-  if (cid < 36) return (mask >> ((cid - 32) >> 1)) & 1;
-  if (cid < 36 + 2 * na) return C.use_tb != 0;
-  if (cid < 36 + 4 * na) return C.use_jb != 0;
-  return false;
-}
-/* bit index in the 192-bit active-set word = row numbering of tsidb_ci_row() */
-TSIDB_DEV int cid_bit(const DevConst& C, int cid) {
-  const int na = C.na, nv = C.nv;
-  if (cid < 32) return 34 * (cid >> 4) + 17 + (cid & 15);
-  if (cid < 36) return 34 * ((cid - 32) >> 1) + (((cid - 32) & 1) ? 33 : 16);
-  if (cid < 36 + 2 * na) { int k = cid - 36; return 68 + k; }
-  int k = cid - 36 - 2 * na;
-  int side = k >= na ? 1 : 0, i = k - side * na;
-  return 68 + 2 * na + side * nv + 6 + i;
-}
-
-/* s = n^T x + c for row cid */
-TSIDB_DEV double cid_eval(const DevConst& C, const double* sm, int cid, int mask, const double* x, const double* wr) {
-  const int na = C.na, nv = C.nv;
-  if (cid < 32) {
-    const int f = cid >> 4, c = (cid & 15) >> 2, k = cid & 3;
-    const double* ff = x + fvar0(nv, mask, f) + 3 * c;
-    return -(C.fric[k][0] * ff[0] + C.fric[k][1] * ff[1] + C.fric[k][2] * ff[2]);
-  }
-  if (cid < 36) {
-    const int f = (cid - 32) >> 1, side = (cid - 32) & 1;
-    const double* ff = x + fvar0(nv, mask, f);
-    double s = 0.0;
-#pragma unroll
-    for (int c = 0; c < 4; c++) s += C.nrm[0] * ff[3 * c] + C.nrm[1] * ff[3 * c + 1] + C.nrm[2] * ff[3 * c + 2];
-    return side ? (C.fmax - s) : (s - C.fmin);
-  }
-  if (cid < 36 + 2 * na) {
-    int k = cid - 36;
-    const int side = k >= na ? 1 : 0, r = k - side * na;
-    /* tau_r - h_r = M_a(r,:) dv - sum_f JF_f(:,6+r)^T (T f_f) */
-    const double* Mr = sm + SM_oM + (6 + r) * SM_LDM;
-    const double* JF = sm + SM_oJF;
-    double s0 = 0.0, s1 = 0.0;
-    for (int j = 0; j < nv; j += 2) { s0 += Mr[j] * x[j]; s1 += (j + 1 < nv) ? Mr[j + 1] * x[j + 1] : 0.0; }
-    double s = s0 + s1;
-#pragma unroll
-    for (int q = 0; q < 12; q++) s -= JF[q * TSIDB_NVX + 6 + r] * wr[q];
-    const double h = sm[SM_oNle + 6 + r];
-    return side ? ((C.tau_max[r] - h) - s) : (s - (C.tau_min[r] - h));
-  }
-  {
-    int k = cid - 36 - 2 * na;
-    const int side = k >= na ? 1 : 0, i = k - side * na;
-    const double vj = sm[SM_oQV + 32 + 6 + i];
-    if (side) { double ub = fmin((C.v_max[i] - vj) / C.jb_dt, 1e10); return ub - x[6 + i]; }
-    double lb = fmax((C.v_min[i] - vj) / C.jb_dt, -1e10);
-    return x[6 + i] - lb;
-  }
-}
-
-/* materialise the normal of row cid into np[0..n) (all lanes cooperate) */
-TSIDB_DEV void cid_normal(const DevConst& C, const double* sm, int cid, int mask, int n, double* np, int lane) {
-  const int na = C.na, nv = C.nv;
-  for (int k = lane; k < n; k += 32) {
-    double val = 0.0;
-    if (cid < 32) {
-      const int f = cid >> 4, c = (cid & 15) >> 2, kk = cid & 3;
-      const int o = k - (fvar0(nv, mask, f) + 3 * c);
-      if (o >= 0 && o < 3) val = -C.fric[kk][o];
-    } else if (cid < 36) {
-      const int f = (cid - 32) >> 1, side = (cid - 32) & 1;
-      const int o = k - fvar0(nv, mask, f);
-      if (o >= 0 && o < 12) val = side ? -C.nrm[o % 3] : C.nrm[o % 3];
-    } else if (cid < 36 + 2 * na) {
-      int q = cid - 36;
-      const int side = q >= na ? 1 : 0, r = q - side * na;
-      if (k < nv) val = sm[SM_oM + (6 + r) * SM_LDM + k];
-      else {
-        const int o = k - nv;
-        const int f = (mask == 3) ? (o / 12) : ((mask & 1) ? 0 : 1);
-        val = -jc_entry(C, sm + SM_oJF, f, o % 12, 6 + r);
-      }
-      if (side) val = -val;
-    } else {
-      int q = cid - 36 - 2 * na;
-      const int side = q >= na ? 1 : 0, i = q - side * na;
-      if (k == 6 + i) val = side ? -1.0 : 1.0;
-    }
-    np[k] = val;
-  }
-}
-
-/* wrench T f of both feet -> wr[12] (zero for a foot not in contact); lanes 0..11 */
-TSIDB_DEV void wrench_of(const DevConst& C, const double* x, int mask, double* wr, int lane) {
-  if (lane < 12) {
-    const int f = lane / 6, r = lane % 6;
-    double s = 0.0;
-    if ((mask >> f) & 1) {
-      const double* ff = x + fvar0(C.nv, mask, f);
-#pragma unroll
-      for (int j = 0; j < 12; j++) s += C.T[r][j] * ff[j];
-    }
-    wr[lane] = s;
-  }
-}
-
-/* Remove the active constraint at position qq (0-based among the active inequalities): shift A, u and
- * the columns of R, restore R to upper-triangular with Givens rotations of rows (j, j+1) and apply the
- * same rotations to columns j, j+1 of J2.  [eiquadprog-fast delete_constraint] */
-TSIDB_DEV void qp_delete(double* sm, int n, int& iq, int qq, int lane) {
-  double* U = sm + SM_oU;
-  double* Rp = U + UF_R;
-  double* u = U + UF_U;
-  int* A = (int*)(U + UF_A);
-  double* J2 = sm + SM_oJ2;
-  __syncwarp(); /* every lane has finished reading A/u/R of the current working set */
-  /* shift columns qq+1..iq-1 one to the left; a column keeps its length, so column c (length c+1 in
-   * packed storage) moves into slot c-1 (capacity c): element c sits on the sub-diagonal and is carried
-   * in `sub` until the rotation that annihilates it. */
-  double sub = 0.0; /* lane c holds sub-diagonal entry R[c+1][c] of the shifted matrix (c >= qq) */
-  for (int c = qq; c < iq - 1; c++) {
-    /* new column c = old column c+1, rows 0..c+1 */
-    double v0 = (lane <= c + 1) ? Rp[(c + 1) * (c + 2) / 2 + lane] : 0.0;
-    __syncwarp();
-    if (lane <= c) Rp[c * (c + 1) / 2 + lane] = v0;
-    double sd = shfl(v0, c + 1);
-    if (lane == c) sub = sd;
-    if (lane == 0) { A[c] = A[c + 1]; u[c] = u[c + 1]; }
-    __syncwarp();
-  }
-  if (lane == 0) { A[iq - 1] = A[iq]; u[iq - 1] = u[iq]; A[iq] = 0; u[iq] = 0.0; }
-  iq--;
-  __syncwarp();
-  for (int j = qq; j < iq; j++) {
-    double cc = Rp[j * (j + 1) / 2 + j];
-    double ss = shfl(sub, j);
-    /* eiquadprog distance() */
-    double a1 = fabs(cc), b1 = fabs(ss), h;
-    if (a1 > b1) { double t = b1 / a1; h = a1 * sqrt(1.0 + t * t); }
-    else if (b1 > a1) { double t = a1 / b1; h = b1 * sqrt(1.0 + t * t); }
-    else h = a1 * sqrt(2.0);
-    if (h == 0.0) continue;
-    cc = cc / h; ss = ss / h;
-    double dj = h;
-    if (cc < 0.0) { dj = -h; cc = -cc; ss = -ss; }
-    const double xny = ss / (1.0 + cc);
-    __syncwarp();
-    if (lane == j) Rp[j * (j + 1) / 2 + j] = dj;
-    /* rows j, j+1 of columns k > j: lane k owns column k */
-    if (lane > j && lane < iq) {
-      /* k >= j+1, so rows j and j+1 are both regular stored entries of column k */
-      double t1 = Rp[lane * (lane + 1) / 2 + j];
-      double t2 = Rp[lane * (lane + 1) / 2 + j + 1];
-      double n1 = t1 * cc + t2 * ss;
-      double n2 = xny * (t1 + n1) - t2;
-      Rp[lane * (lane + 1) / 2 + j] = n1;
-      Rp[lane * (lane + 1) / 2 + j + 1] = n2;
-    }
-    /* columns j, j+1 of J2: lanes over rows */
-    for (int k = lane; k < n; k += 32) {
-      double t1 = J2[k * SM_LDJ + j], t2 = J2[k * SM_LDJ + j + 1];
-      double n1 = t1 * cc + t2 * ss;
-      J2[k * SM_LDJ + j] = n1;
-      J2[k * SM_LDJ + j + 1] = xny * (n1 + t1) - t2;
-    }
-    __syncwarp();
-  }
-  /* refresh reciprocal diagonal */
-  if (lane < iq) U[UF_IRD + lane] = 1.0 / Rp[lane * (lane + 1) / 2 + lane];
-  __syncwarp();
-}
-
 /* ---- register-blocked building blocks of the equality elimination (template on nv) ----
  * Each lane keeps ONE column (of B, of Q2/J2) or ONE row (of the Cholesky factor) in registers; all
  * register-array indices are compile-time constants (fully unrolled loops), the operands shared by the
@@ -917,6 +734,8 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
   const double* JF = sm + SM_oJF;
   const double* bv = sm + SM_oBv;
 
+  int err = ST_OPTIMAL; /* an error status is carried to the end: every warp must reach every PHASE_SYNC */
+  PHASE_SYNC();
   /* ---- Cholesky of the dv block: lane i keeps row i; c1 = trace(H), c2 = trace(L^-T) ---- */
   double c1, c2;
   {
@@ -949,11 +768,12 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
       if (lane == j) ild[j] = inv;
       __syncwarp();
     }
-    if (bad) return ST_INFEASIBLE; /* eiquadprog: Cholesky failure -> UNBOUNDED -> HQP_STATUS_INFEASIBLE */
+    if (bad) err = ST_INFEASIBLE; /* eiquadprog: Cholesky failure -> UNBOUNDED -> HQP_STATUS_INFEASIBLE */
     c2 = c2p + nc * C.Lfinv_trace;
   }
   c1c2 = c1 * c2;
 
+  PHASE_SYNC();
   /* ---- B = L^-1 [CE^T | g]: lane e keeps column e; Householder QR; the last column becomes Q^T w_unc ---- */
   double R_norm = 1.0;
   {
@@ -997,7 +817,10 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
 #pragma unroll
       for (int k = 0; k < N; k++) b[k] = -b[k]; /* w_unc = -L^-1 g */
     }
-    for (int i = 0; i < neq; i++) {
+    PHASE_SYNC();
+    for (int i = 0; i < 18; i++) {
+      PHASE_SYNC();
+      if (i >= neq) continue;
       __syncwarp();
       if (lane == i) {
 #pragma unroll
@@ -1011,7 +834,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
       const double nrm = sqrt(alpha * alpha + sigma);
       const double beta = (alpha >= 0.0) ? -nrm : nrm;
       /* dependent equality row [eiquadprog add_constraint: |d(iq)| <= eps * R_norm] */
-      if (fabs(beta) <= TS_EPS * R_norm) return ST_ERROR;
+      if (fabs(beta) <= TS_EPS * R_norm && err == ST_OPTIMAL) err = ST_ERROR;
       R_norm = fmax(R_norm, fabs(beta));
       const double tau = (beta - alpha) / beta;
       const double scal = 1.0 / (alpha - beta);
@@ -1033,6 +856,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
     }
     __syncwarp();
   }
+  PHASE_SYNC();
   /* ---- w_hat[0:neq] = R1^-T rhs (forward substitution, lane <-> equation); rhs = -ce0 ---- */
   {
     double rhs = 0.0;
@@ -1068,6 +892,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
     if (lane + 32 < N) w0v[lane + 32] = y1;
     __syncwarp();
   }
+  PHASE_SYNC();
   /* ---- x0 = L^-T w0 (every lane computes it redundantly from broadcast reads; lane 0 stores) ---- */
   {
     double q[N];
@@ -1079,6 +904,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
       for (int k = 0; k < N; k++) x[k] = q[k];
     }
   }
+  PHASE_SYNC();
   /* ---- J2[:, c] = L^-T Q [0; e_c]: lane c keeps the column in registers ---- */
   {
     double q[N];
@@ -1086,8 +912,9 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
 #pragma unroll
       for (int k = 0; k < N; k++) q[k] = (k == neq + lane) ? 1.0 : 0.0;
       for (int i = neq - 1; i >= 0; i--) reflect<N>(q, Vt + i * N, tauq[i]);
-      backsub_LT<NV>(q, L, ild, C, nc);
     }
+    PHASE_SYNC();
+    if (lane < m) backsub_LT<NV>(q, L, ild, C, nc);
     __syncwarp(); /* every lane is done with Vt / R1 / w0, which live in the J2 region */
     if (lane < m) {
 #pragma unroll
@@ -1096,27 +923,294 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
     __syncwarp();
   }
   R_norm_out = R_norm;
-  return ST_OPTIMAL;
+  return err;
 }
 
-/* The full QP: returns status; on return x (sm+SM_oX) holds the solution, iters and the active words. */
-template <int NV>
-TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc, int n, int neq,
-                       int& iters_out, uint64_t* act_words) {
-  const int nv = C.nv, na = C.na;
-  const int m = n - neq; /* reduced dimension, <= 32 */
-  double* U = sm + SM_oU;
-  double* J2 = sm + SM_oJ2;
-  double* x = sm + SM_oX;
-  iters_out = 0;
-  act_words[0] = act_words[1] = act_words[2] = 0;
-  double c1c2 = 0.0, R_norm = 1.0;
-  {
-    const int st = k3_eliminate<NV>(C, sm, lane, mask, nc, n, neq, c1c2, R_norm);
-    if (st != ST_OPTIMAL) return st;
-  }
+/* ================================================================= hand-off between the two kernels */
+/* Kernel F (tsidb_prepare_kernel: K1 dynamics, K2 assembly, equality elimination) leaves one image per env
+ * in a global workspace; kernel A (tsidb_activeset_kernel: active-set iterations + decode) pulls images from a
+ * work counter.  The image is the active-set kernel's shared-memory layout, so the load is one linear copy.
+ * Cost: 20.3 KB written + read per tick, ~3 % of the tick time at the measured HBM rate; what it buys is that
+ * F runs in CTA-wide phase lock-step with no idle waiting, and A balances the data-dependent iteration
+ * counts (1..40) dynamically at 8 envs per SM.                                                           */
+#define SA_LDJA 20                        /* JFa row stride                                  */
+#define SA_oJ2 0                          /* J2   50 x 33                              1650 */
+#define SA_oMa (SA_oJ2 + 1650)            /* M_a  na x 27 (rows 6.. of M)               540 */
+#define SA_oJFa (SA_oMa + 540)            /* JF columns 6.., 12 x 20                     240 */
+#define SA_oNle (SA_oJFa + 240)           /* nle_a                                        20 */
+#define SA_oVj (SA_oNle + 20)             /* joint velocities                             20 */
+#define SA_oX (SA_oVj + 20)               /* x                                            50 */
+#define SA_oSc (SA_oX + 50)               /* c1*c2, R_norm, error status, contact mask     4 */
+#define SA_IMAGE (SA_oSc + 4)             /* doubles handed over per env                2524 */
+#define SA_oWr (SA_IMAGE)                 /* wrenches                                     12 */
+#define SA_oU (SA_oWr + 12)               /* active-set work arrays (UF_*)                   */
+#define SA_PER_ENV (SA_oU + UF_END)
+#define TSIDB_AS_WARPS 8
 
-  /* ================= active-set iterations on the reduced basis ================= */
+struct ASCtx {
+  double* J2;
+  const double* Ma;
+  const double* JFa;
+  const double* nle_a;
+  const double* vj;
+  double* x;
+  double* wr;
+  double* U;
+};
+
+/* x index of foot f's first force variable */
+TSIDB_DEV int fvar0(int nv, int mask, int f) { return nv + ((f == 1 && (mask & 1)) ? 12 : 0); }
+
+/* one-sided candidate rows ("cid"), fixed numbering:
+ *   0..31   friction pyramid upper sides: f = cid/16, corner = (cid%16)/4, k = cid%4
+ *   32..35  normal force: f = (cid-32)/2, side = (cid-32)%2  (0: >= fmin, 1: <= fmax)
+ *   36..36+2na-1        actuation, side-major
+ *   36+2na..36+4na-1    joint (velocity) bounds, side-major
+ * The never-active sides of the reference's two-sided blocks (friction lower side at -1e10, the six
+ * base rows of the joint-bounds block at +-1e10) are not enumerated: they can neither be violated
+ * nor change the violation sum.
+ * Lane ownership: lane l evaluates "slot" 0: cid l (friction), 1: cid 32+l (l < 4), 2/3: actuation row l
+ * lower/upper, 4/5: joint-bound row l lower/upper (l < na). */
+TSIDB_DEV int cid_of(int na, int lane, int slot) {
+  return slot == 0 ? lane : (slot == 1 ? 32 + lane : 36 + (slot - 2) * na + lane);
+}
+TSIDB_DEV void cid_owner(int na, int cid, int& lane, int& slot) {
+  if (cid < 32) { lane = cid; slot = 0; }
+  else if (cid < 36) { lane = cid - 32; slot = 1; }
+  else { const int k = cid - 36; slot = 2 + k / na; lane = k - (slot - 2) * na; }
+}
+/* bit index in the 192-bit active-set word = row numbering of tsidb_ci_row() */
+TSIDB_DEV int cid_bit(const DevConst& C, int cid) {
+  const int na = C.na, nv = C.nv;
+  if (cid < 32) return 34 * (cid >> 4) + 17 + (cid & 15);
+  if (cid < 36) return 34 * ((cid - 32) >> 1) + (((cid - 32) & 1) ? 33 : 16);
+  if (cid < 36 + 2 * na) { int k = cid - 36; return 68 + k; }
+  int k = cid - 36 - 2 * na;
+  int side = k >= na ? 1 : 0, i = k - side * na;
+  return 68 + 2 * na + side * nv + 6 + i;
+}
+
+/* s = CI x + ci0 for the rows this lane owns; invalid rows get +inf */
+TSIDB_DEV void eval_rows(const DevConst& C, const ASCtx& S, int lane, int mask, double (&s)[6]) {
+  const int na = C.na, nv = C.nv;
+  const double* x = S.x;
+#pragma unroll
+  for (int k = 0; k < 6; k++) s[k] = TS_INF;
+  {
+    const int f = lane >> 4, c = (lane & 15) >> 2, k = lane & 3;
+    if ((mask >> f) & 1) {
+      const double* ff = x + fvar0(nv, mask, f) + 3 * c;
+      s[0] = -(C.fric[k][0] * ff[0] + C.fric[k][1] * ff[1] + C.fric[k][2] * ff[2]);
+    }
+  }
+  if (lane < 4) {
+    const int f = lane >> 1, side = lane & 1;
+    if ((mask >> f) & 1) {
+      const double* ff = x + fvar0(nv, mask, f);
+      double t = 0.0;
+#pragma unroll
+      for (int c = 0; c < 4; c++) t += C.nrm[0] * ff[3 * c] + C.nrm[1] * ff[3 * c + 1] + C.nrm[2] * ff[3 * c + 2];
+      s[1] = side ? (C.fmax - t) : (t - C.fmin);
+    }
+  }
+  if (lane < na) {
+    if (C.use_tb) {
+      /* tau_r = h_r + M_a(r,:) dv - sum_f JF_f(:,6+r)^T (T f_f) */
+      const double* Mr = S.Ma + lane * SM_LDM;
+      double t0 = S.nle_a[lane], t1 = 0.0, t2 = 0.0, t3 = 0.0;
+      int j = 0;
+      for (; j + 3 < nv; j += 4) {
+        t0 += Mr[j] * x[j]; t1 += Mr[j + 1] * x[j + 1]; t2 += Mr[j + 2] * x[j + 2]; t3 += Mr[j + 3] * x[j + 3];
+      }
+      for (; j < nv; j++) t0 += Mr[j] * x[j];
+      double t = (t0 + t1) + (t2 + t3);
+#pragma unroll
+      for (int q = 0; q < 12; q++) t -= S.JFa[q * SA_LDJA + lane] * S.wr[q];
+      s[2] = t - C.tau_min[lane];
+      s[3] = C.tau_max[lane] - t;
+    }
+    if (C.use_jb) {
+      const double vj = S.vj[lane];
+      const double ub = fmin((C.v_max[lane] - vj) / C.jb_dt, 1e10);
+      const double lb = fmax((C.v_min[lane] - vj) / C.jb_dt, -1e10);
+      s[4] = x[6 + lane] - lb;
+      s[5] = ub - x[6 + lane];
+    }
+  }
+}
+/* s of one row (after a partial step) — lane-uniform call, every lane computes the same value */
+TSIDB_DEV double eval_one(const DevConst& C, const ASCtx& S, int cid, int mask) {
+  const int na = C.na, nv = C.nv;
+  const double* x = S.x;
+  if (cid < 32) {
+    const int f = cid >> 4, c = (cid & 15) >> 2, k = cid & 3;
+    const double* ff = x + fvar0(nv, mask, f) + 3 * c;
+    return -(C.fric[k][0] * ff[0] + C.fric[k][1] * ff[1] + C.fric[k][2] * ff[2]);
+  }
+  if (cid < 36) {
+    const int f = (cid - 32) >> 1, side = (cid - 32) & 1;
+    const double* ff = x + fvar0(nv, mask, f);
+    double t = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) t += C.nrm[0] * ff[3 * c] + C.nrm[1] * ff[3 * c + 1] + C.nrm[2] * ff[3 * c + 2];
+    return side ? (C.fmax - t) : (t - C.fmin);
+  }
+  if (cid < 36 + 2 * na) {
+    const int k = cid - 36, side = k >= na ? 1 : 0, r = k - side * na;
+    const double* Mr = S.Ma + r * SM_LDM;
+    double t = S.nle_a[r];
+    for (int j = 0; j < nv; j++) t += Mr[j] * x[j];
+#pragma unroll
+    for (int q = 0; q < 12; q++) t -= S.JFa[q * SA_LDJA + r] * S.wr[q];
+    return side ? (C.tau_max[r] - t) : (t - C.tau_min[r]);
+  }
+  {
+    const int k = cid - 36 - 2 * na, side = k >= na ? 1 : 0, i = k - side * na;
+    const double vj = S.vj[i];
+    if (side) return fmin((C.v_max[i] - vj) / C.jb_dt, 1e10) - x[6 + i];
+    return x[6 + i] - fmax((C.v_min[i] - vj) / C.jb_dt, -1e10);
+  }
+}
+
+/* d_c = n_cid^T J2[:, c] for this lane's column c, using the sparsity of the row: 3 entries for a pyramid
+ * row, 12 for a normal-force row, 1 for a joint bound; actuation rows are dense (normal built in np). */
+TSIDB_DEV double row_dot_col(const DevConst& C, const ASCtx& S, int cid, int mask, int n, int lane, double* np) {
+  const int na = C.na, nv = C.nv;
+  const double* Jc = S.J2 + lane;
+  if (cid < 32) {
+    const int f = cid >> 4, c = (cid & 15) >> 2, k = cid & 3;
+    const int r0 = fvar0(nv, mask, f) + 3 * c;
+    return -(C.fric[k][0] * Jc[r0 * SM_LDJ] + C.fric[k][1] * Jc[(r0 + 1) * SM_LDJ] + C.fric[k][2] * Jc[(r0 + 2) * SM_LDJ]);
+  }
+  if (cid < 36) {
+    const int f = (cid - 32) >> 1, side = (cid - 32) & 1;
+    const int r0 = fvar0(nv, mask, f);
+    double t = 0.0;
+#pragma unroll
+    for (int o = 0; o < 12; o++) t += C.nrm[o % 3] * Jc[(r0 + o) * SM_LDJ];
+    return side ? -t : t;
+  }
+  if (cid >= 36 + 2 * na) {
+    const int k = cid - 36 - 2 * na, side = k >= na ? 1 : 0, i = k - side * na;
+    const double t = Jc[(6 + i) * SM_LDJ];
+    return side ? -t : t;
+  }
+  /* actuation row r: n = +-[M_a(r,:) | -Jc(:,6+r)^T]; every lane reads the normal from np */
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+  int k = 0;
+  for (; k + 3 < n; k += 4) {
+    d0 += np[k] * Jc[k * SM_LDJ]; d1 += np[k + 1] * Jc[(k + 1) * SM_LDJ];
+    d2 += np[k + 2] * Jc[(k + 2) * SM_LDJ]; d3 += np[k + 3] * Jc[(k + 3) * SM_LDJ];
+  }
+  for (; k < n; k++) d0 += np[k] * Jc[k * SM_LDJ];
+  return (d0 + d1) + (d2 + d3);
+}
+/* dense normal of an actuation row into np[0..n) (all lanes cooperate) */
+TSIDB_DEV void actuation_normal(const DevConst& C, const ASCtx& S, int cid, int mask, int n, double* np, int lane) {
+  const int na = C.na, nv = C.nv;
+  const int q = cid - 36, side = q >= na ? 1 : 0, r = q - side * na;
+  for (int k = lane; k < n; k += 32) {
+    double val;
+    if (k < nv) val = S.Ma[r * SM_LDM + k];
+    else {
+      const int o = k - nv;
+      const int f = (mask == 3) ? (o / 12) : ((mask & 1) ? 0 : 1);
+      const int j = o % 12;
+      double t = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 6; kk++) t += C.T[kk][j] * S.JFa[(f * 6 + kk) * SA_LDJA + r];
+      val = -t;
+    }
+    np[k] = side ? -val : val;
+  }
+}
+
+/* wrench T f of both feet -> wr[12] (zero for a foot not in contact); lanes 0..11 */
+TSIDB_DEV void wrench_of(const DevConst& C, const double* x, int mask, double* wr, int lane) {
+  if (lane < 12) {
+    const int f = lane / 6, r = lane % 6;
+    double s = 0.0;
+    if ((mask >> f) & 1) {
+      const double* ff = x + fvar0(C.nv, mask, f);
+#pragma unroll
+      for (int j = 0; j < 12; j++) s += C.T[r][j] * ff[j];
+    }
+    wr[lane] = s;
+  }
+}
+
+/* Remove the active constraint at position qq (0-based among the active inequalities): shift A, u and
+ * the columns of R, restore R to upper-triangular with Givens rotations of rows (j, j+1) and apply the
+ * same rotations to columns j, j+1 of J2.  [eiquadprog-fast delete_constraint] */
+TSIDB_DEVNI void qp_delete(const ASCtx& S, int n, int& iq, int qq, int lane) {
+  double* U = S.U;
+  double* Rp = U + UF_R;
+  double* u = U + UF_U;
+  int* A = (int*)(U + UF_A);
+  double* J2 = S.J2;
+  __syncwarp(); /* every lane has finished reading A/u/R of the current working set */
+  /* shift columns qq+1..iq-1 one to the left; a column keeps its length, so column c (length c+1 in
+   * packed storage) moves into slot c-1 (capacity c): element c sits on the sub-diagonal and is carried
+   * in `sub` until the rotation that annihilates it. */
+  double sub = 0.0; /* lane c holds sub-diagonal entry R[c+1][c] of the shifted matrix (c >= qq) */
+  for (int c = qq; c < iq - 1; c++) {
+    double v0 = (lane <= c + 1) ? Rp[(c + 1) * (c + 2) / 2 + lane] : 0.0;
+    __syncwarp();
+    if (lane <= c) Rp[c * (c + 1) / 2 + lane] = v0;
+    double sd = shfl(v0, c + 1);
+    if (lane == c) sub = sd;
+    if (lane == 0) { A[c] = A[c + 1]; u[c] = u[c + 1]; }
+    __syncwarp();
+  }
+  if (lane == 0) { A[iq - 1] = A[iq]; u[iq - 1] = u[iq]; A[iq] = 0; u[iq] = 0.0; }
+  iq--;
+  __syncwarp();
+  for (int j = qq; j < iq; j++) {
+    double cc = Rp[j * (j + 1) / 2 + j];
+    double ss = shfl(sub, j);
+    /* eiquadprog distance() */
+    double a1 = fabs(cc), b1 = fabs(ss), h;
+    if (a1 > b1) { double t = b1 / a1; h = a1 * sqrt(1.0 + t * t); }
+    else if (b1 > a1) { double t = a1 / b1; h = b1 * sqrt(1.0 + t * t); }
+    else h = a1 * sqrt(2.0);
+    if (h == 0.0) continue;
+    cc = cc / h; ss = ss / h;
+    double dj = h;
+    if (cc < 0.0) { dj = -h; cc = -cc; ss = -ss; }
+    const double xny = ss / (1.0 + cc);
+    __syncwarp();
+    if (lane == j) Rp[j * (j + 1) / 2 + j] = dj;
+    /* rows j, j+1 of columns k > j: lane k owns column k (k >= j+1: both rows are regular stored entries) */
+    if (lane > j && lane < iq) {
+      double t1 = Rp[lane * (lane + 1) / 2 + j];
+      double t2 = Rp[lane * (lane + 1) / 2 + j + 1];
+      double n1 = t1 * cc + t2 * ss;
+      double n2 = xny * (t1 + n1) - t2;
+      Rp[lane * (lane + 1) / 2 + j] = n1;
+      Rp[lane * (lane + 1) / 2 + j + 1] = n2;
+    }
+    /* columns j, j+1 of J2: lanes over rows */
+    for (int k = lane; k < n; k += 32) {
+      double t1 = J2[k * SM_LDJ + j], t2 = J2[k * SM_LDJ + j + 1];
+      double n1 = t1 * cc + t2 * ss;
+      J2[k * SM_LDJ + j] = n1;
+      J2[k * SM_LDJ + j + 1] = xny * (n1 + t1) - t2;
+    }
+    __syncwarp();
+  }
+  if (lane < iq) U[UF_IRD + lane] = 1.0 / Rp[lane * (lane + 1) / 2 + lane];
+  __syncwarp();
+}
+
+/* Active-set iterations on the reduced basis [eiquadprog-fast solve_quadprog, after the equality phase]. */
+TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, int lane, int mask, int nc, int n, int neq,
+                       double c1c2, double R_norm, int& iters_out, uint64_t* act_words) {
+  const int na = C.na;
+  const int m = n - neq; /* reduced dimension, <= 32 */
+  double* U = S.U;
+  double* J2 = S.J2;
+  double* x = S.x;
+  double* wr = S.wr;
   double* Rp = U + UF_R;
   double* ird = U + UF_IRD;
   double* np = U + UF_NP;
@@ -1128,38 +1222,27 @@ TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc
   double* xo = U + UF_XO;
   int* A = (int*)(U + UF_A);
   int* Ao = A + 34;
-  double* wr = sm + SM_oX0; /* x0 is dead from here on: reuse its first 12 slots for the wrenches */
+  iters_out = 0;
+  act_words[0] = act_words[1] = act_words[2] = 0;
 
-  const int ncid = cid_count(C);
   const int nin_ref = C.nin_ref_fixed + 34 * nc;
   const double psi_thresh = (double)nin_ref * TS_EPS * c1c2 * 100.0;
   int iq = 0, iter = 0, status = ST_OPTIMAL;
-  unsigned actbits = 0;  /* lane owns cids lane + 32*b, b = 0..3: bit b = in the working set */
+  unsigned actbits = 0;  /* bit k: the row of slot k owned by this lane is in the working set */
   unsigned exclbits = 0;
-  (void)na;
 
   for (;;) { /* l1 */
     iter++;
     if (iter >= C.max_iter) { status = ST_MAX_ITER; break; }
     wrench_of(C, x, mask, wr, lane);
     __syncwarp();
-    double sl[4];
+    double sl[6];
+    eval_rows(C, S, lane, mask, sl);
     double part = 0.0;
 #pragma unroll
-    for (int bq = 0; bq < 4; bq++) {
-      const int cid = lane + 32 * bq;
-      double s = TS_INF;
-      if (cid < ncid && cid_valid(C, cid, mask)) {
-        s = cid_eval(C, sm, cid, mask, x, wr);
-        part += fmin(s, 0.0);
-      }
-      sl[bq] = s;
-    }
+    for (int k = 0; k < 6; k++) part += (sl[k] < 0.0) ? sl[k] : 0.0;
     exclbits = 0;
     double psi = warp_sum(part);
-#ifdef TSIDB_EMU_TRACE
-    if (lane == 8) printf("[emu] l1 iter %d lane8 s=%.6g act=%u psi=%.6g thr=%.6g\n", iter, sl[0], actbits, psi, psi_thresh);
-#endif
     if (fabs(psi) <= psi_thresh) { status = ST_OPTIMAL; break; }
     /* save x, u, A */
     for (int k = lane; k < n; k += 32) xo[k] = x[k];
@@ -1171,11 +1254,11 @@ TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc
       double best = 0.0;
       int bcid = -1, bbit = 1 << 30;
 #pragma unroll
-      for (int bq = 0; bq < 4; bq++) {
-        const int cid = lane + 32 * bq;
-        if (cid < ncid && !((actbits >> bq) & 1u) && !((exclbits >> bq) & 1u) && sl[bq] < 0.0) {
+      for (int k = 0; k < 6; k++) {
+        if (!((actbits >> k) & 1u) && !((exclbits >> k) & 1u) && sl[k] < 0.0) {
+          const int cid = cid_of(na, lane, k);
           const int bit = cid_bit(C, cid);
-          if (sl[bq] < best || (sl[bq] == best && bit < bbit)) { best = sl[bq]; bcid = cid; bbit = bit; }
+          if (sl[k] < best || (sl[k] == best && bit < bbit)) { best = sl[k]; bcid = cid; bbit = bit; }
         }
       }
 #pragma unroll
@@ -1187,33 +1270,44 @@ TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc
       }
       if (bcid < 0) { status = ST_OPTIMAL; done = true; break; }
       const int ip = bcid;
+      int ip_lane, ip_slot;
+      cid_owner(na, ip, ip_lane, ip_slot);
+      const bool dense_row = (ip >= 36 && ip < 36 + 2 * na);
       double s_ip = best;
 #ifdef TSIDB_EMU_TRACE
       if (lane == 0) printf("[emu] iter %d pick bit %d s=%.17g iq=%d\n", iter, cid_bit(C, ip), s_ip, iq);
 #endif
-      cid_normal(C, sm, ip, mask, n, np, lane);
+      if (dense_row) actuation_normal(C, S, ip, mask, n, np, lane);
       if (lane == 0) { u[iq] = 0.0; A[iq] = ip; }
       __syncwarp();
       for (;;) { /* l2a */
-        /* d = J2^T np (lane <-> column) */
+        /* d = J2^T n_ip (lane <-> column) */
         double dl = 0.0;
         if (lane < m) {
-          double d0 = 0.0, d1 = 0.0;
-          int k = 0;
-          for (; k + 1 < n; k += 2) { d0 += np[k] * J2[k * SM_LDJ + lane]; d1 += np[k + 1] * J2[(k + 1) * SM_LDJ + lane]; }
-          if (k < n) d0 += np[k] * J2[k * SM_LDJ + lane];
-          dl = d0 + d1;
+          dl = row_dot_col(C, S, ip, mask, n, lane, np);
           dd[lane] = dl;
         }
         __syncwarp();
         /* z = J2[:, iq:] d[iq:] (lanes over rows); zero if no free direction is left */
         double z0 = 0.0, z1 = 0.0;
         if (iq < m) {
-          if (lane < n) for (int c = iq; c < m; c++) z0 += J2[lane * SM_LDJ + c] * dd[c];
-          if (lane + 32 < n) for (int c = iq; c < m; c++) z1 += J2[(lane + 32) * SM_LDJ + c] * dd[c];
+          if (lane < n) {
+            const double* Jr = J2 + lane * SM_LDJ;
+            double a0 = 0.0, a1 = 0.0;
+            int c = iq;
+            for (; c + 1 < m; c += 2) { a0 += Jr[c] * dd[c]; a1 += Jr[c + 1] * dd[c + 1]; }
+            if (c < m) a0 += Jr[c] * dd[c];
+            z0 = a0 + a1;
+          }
+          if (lane + 32 < n) {
+            const double* Jr = J2 + (lane + 32) * SM_LDJ;
+            double a0 = 0.0, a1 = 0.0;
+            int c = iq;
+            for (; c + 1 < m; c += 2) { a0 += Jr[c] * dd[c]; a1 += Jr[c + 1] * dd[c + 1]; }
+            if (c < m) a0 += Jr[c] * dd[c];
+            z1 = a0 + a1;
+          }
         }
-        if (lane < n) zz_[lane] = z0;
-        if (lane + 32 < n) zz_[lane + 32] = z1;
         /* r = R^-1 d[0:iq] (back substitution, lane <-> row) */
         {
           double accv = (lane < iq) ? dl : 0.0;
@@ -1237,15 +1331,13 @@ TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc
           int ol = __shfl_xor_sync(FULL, lpos, o);
           if (ol >= 0 && (lpos < 0 || ot < t1 || (ot == t1 && ol < lpos))) { t1 = ot; lpos = ol; }
         }
-        /* full step t2 = -s_ip / z.np */
-        double pz = 0.0, pn = 0.0;
-        if (lane < n) { pz += z0 * z0; pn += z0 * np[lane]; }
-        if (lane + 32 < n) { pz += z1 * z1; pn += z1 * np[lane + 32]; }
-        double zz = warp_sum(pz), znp = warp_sum(pn);
-        double t2 = (fabs(zz) > TS_EPS) ? (-s_ip / znp) : TS_INF;
+        /* full step t2 = -s_ip / z.n_ip, with z.n_ip = |d[iq:]|^2 (z = J2 d2, d2 = J2^T n) */
+        const double zz = warp_sum(z0 * z0 + z1 * z1);
+        const double d2sum = warp_sum((lane >= iq && lane < m) ? dl * dl : 0.0);
+        double t2 = (fabs(zz) > TS_EPS) ? (-s_ip / d2sum) : TS_INF;
         double t = fmin(t1, t2);
 #ifdef TSIDB_EMU_TRACE
-        if (lane == 0) printf("[emu]   t1=%.17g (pos %d) t2=%.17g zz=%.6g znp=%.6g\n", t1, lpos, t2, zz, znp);
+        if (lane == 0) printf("[emu]   t1=%.17g (pos %d) t2=%.17g zz=%.6g znp=%.6g\n", t1, lpos, t2, zz, d2sum);
 #endif
         if (t >= TS_INF) { status = ST_INFEASIBLE; done = true; break; } /* eiquadprog UNBOUNDED -> HQP INFEASIBLE */
         __syncwarp();
@@ -1255,10 +1347,11 @@ TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc
           if (lane == 0) u[iq] += t;
           __syncwarp();
           {
-            const int lc = A[lpos];
-            if (lane == (lc & 31)) actbits &= ~(1u << (lc >> 5));
+            int ol, os;
+            cid_owner(na, A[lpos], ol, os);
+            if (lane == ol) actbits &= ~(1u << os);
           }
-          qp_delete(sm, n, iq, lpos, lane);
+          qp_delete(S, n, iq, lpos, lane);
           continue;
         }
         /* step in primal and dual space */
@@ -1270,33 +1363,39 @@ TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc
         if (t == t2) {
           /* full step: add ip.  Householder on the free columns iq..m-1 maps d[iq:] to beta e_iq; the
            * row sums needed for the update are z and column iq (already known). */
-          double d2 = (lane >= iq && lane < m) ? dl * dl : 0.0;
-          double nrm = sqrt(warp_sum(d2));
-          double d0 = shfl(dl, iq < 32 ? iq : 31);
+          const double nrm = sqrt(d2sum);
+          const double d0 = shfl(dl, iq < 32 ? iq : 31);
           bool degenerate;
           if (iq >= m) degenerate = true; /* no free direction: |d(iq)| = 0 */
           else {
-            double beta = (d0 >= 0.0) ? -nrm : nrm;
+            const double beta = (d0 >= 0.0) ? -nrm : nrm;
             degenerate = !(fabs(beta) > TS_EPS * R_norm);
             if (!degenerate) {
-              double tauh = (beta - d0) / beta;
-              double scal = 1.0 / (d0 - beta);
+              const double tauh = (beta - d0) / beta;
+              const double scal = 1.0 / (d0 - beta);
               /* v_c = d_c * scal (c > iq), v_iq = 1;  w_k = sum_c J2[k][c] v_c = (z_k - beta J2[k][iq]) * scal */
-              double w0 = (lane < n) ? (z0 - beta * J2[lane * SM_LDJ + iq]) * scal : 0.0;
-              double w1 = (lane + 32 < n) ? (z1 - beta * J2[(lane + 32) * SM_LDJ + iq]) * scal : 0.0;
+              const double w0 = (lane < n) ? (z0 - beta * J2[lane * SM_LDJ + iq]) * scal : 0.0;
+              const double w1 = (lane + 32 < n) ? (z1 - beta * J2[(lane + 32) * SM_LDJ + iq]) * scal : 0.0;
               __syncwarp();
               if (lane < n) zz_[lane] = tauh * w0;
               if (lane + 32 < n) zz_[lane + 32] = tauh * w1;
               __syncwarp();
               if (lane >= iq && lane < m) {
                 const double vc = (lane == iq) ? 1.0 : dl * scal;
-                for (int k = 0; k < n; k++) J2[k * SM_LDJ + lane] -= zz_[k] * vc;
+                double* Jc = J2 + lane;
+                int k = 0;
+                for (; k + 3 < n; k += 4) {
+                  const double j0 = Jc[k * SM_LDJ], j1 = Jc[(k + 1) * SM_LDJ], j2 = Jc[(k + 2) * SM_LDJ], j3 = Jc[(k + 3) * SM_LDJ];
+                  Jc[k * SM_LDJ] = j0 - zz_[k] * vc; Jc[(k + 1) * SM_LDJ] = j1 - zz_[k + 1] * vc;
+                  Jc[(k + 2) * SM_LDJ] = j2 - zz_[k + 2] * vc; Jc[(k + 3) * SM_LDJ] = j3 - zz_[k + 3] * vc;
+                }
+                for (; k < n; k++) Jc[k * SM_LDJ] -= zz_[k] * vc;
               }
               /* new column of R: [d[0:iq]; beta] */
               if (lane < iq) Rp[iq * (iq + 1) / 2 + lane] = dl;
               if (lane == 0) { Rp[iq * (iq + 1) / 2 + iq] = beta; ird[iq] = 1.0 / beta; }
               R_norm = fmax(R_norm, fabs(beta));
-              if (lane == (ip & 31)) actbits |= 1u << (ip >> 5);
+              if (lane == ip_lane) actbits |= 1u << ip_slot;
               iq++;
               __syncwarp();
             }
@@ -1306,14 +1405,15 @@ TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc
 #endif
           if (degenerate) {
             /* eiquadprog: exclude ip, restore the saved x, u, A for the first iq entries, retry l2 */
-            if (lane == (ip & 31)) exclbits |= 1u << (ip >> 5);
+            if (lane == ip_lane) exclbits |= 1u << ip_slot;
             actbits = 0;
             if (lane < iq) { A[lane] = Ao[lane]; u[lane] = uo[lane]; }
             for (int k = lane; k < n; k += 32) x[k] = xo[k];
             __syncwarp();
             for (int i = 0; i < iq; i++) {
-              const int c = A[i];
-              if (lane == (c & 31)) actbits |= 1u << (c >> 5);
+              int ol, os;
+              cid_owner(na, A[i], ol, os);
+              if (lane == ol) actbits |= 1u << os;
             }
             break; /* back to l2 with the same s */
           }
@@ -1322,23 +1422,20 @@ TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc
         }
         /* partial step: drop the blocking constraint, recompute s(ip), try again */
         {
-          const int lc = A[lpos];
-          if (lane == (lc & 31)) actbits &= ~(1u << (lc >> 5));
+          int ol, os;
+          cid_owner(na, A[lpos], ol, os);
+          if (lane == ol) actbits &= ~(1u << os);
         }
-        qp_delete(sm, n, iq, lpos, lane);
+        qp_delete(S, n, iq, lpos, lane);
         wrench_of(C, x, mask, wr, lane);
         __syncwarp();
-        {
-          double sn = (lane == 0) ? cid_eval(C, sm, ip, mask, x, wr) : 0.0;
-          s_ip = shfl(sn, 0);
-        }
+        s_ip = eval_one(C, S, ip, mask);
       } /* l2a */
       if (done || restart_l1) break;
     } /* l2 */
     if (done) break;
   } /* l1 */
   iters_out = iter;
-  /* active-set words */
   if (status == ST_OPTIMAL || status == ST_MAX_ITER) {
     uint64_t w0 = 0, w1 = 0, w2 = 0;
     for (int i = 0; i < iq; i++) {
@@ -1352,10 +1449,11 @@ TSIDB_DEV int k3_solve(const DevConst& C, double* sm, int lane, int mask, int nc
   return status;
 }
 
-/* ================================================================= the tick of one env */
+/* ================================================================= kernel F: one env up to the hand-off */
 template <int NV>
-TSIDB_DEV void tick_env(const DevConst& C, double* sm, const TickArgs& a, int env, int lane) {
+TSIDB_DEV void prepare_env(const DevConst& C, double* sm, const TickArgs& a, int env, int slot, int lane) {
   const int nv = C.nv, na = C.na, nq = C.nq;
+  PHASE_SYNC();
   /* stage q, v */
   if (lane < nq) sm[SM_oQV + lane] = ldin(a.q, a, env, lane, nq);
   if (lane < nv) sm[SM_oQV + 32 + lane] = a.v ? ldin(a.v, a, env, lane, nv) : 0.0;
@@ -1375,13 +1473,44 @@ TSIDB_DEV void tick_env(const DevConst& C, double* sm, const TickArgs& a, int en
   const int mask = a.mask ? (a.mask[env] & 3) : 3;
   const int nc = (mask & 1) + ((mask >> 1) & 1);
   const int n = nv + 12 * nc, neq = 6 + 6 * nc;
+  PHASE_SYNC();
   k2_assemble(C, sm, a, env, lane, mask, neq, n);
+  double c1c2 = 0.0, R_norm = 1.0;
+  const int err = k3_eliminate<NV>(C, sm, lane, mask, nc, n, neq, c1c2, R_norm);
+  /* hand-off image (layout SA_*) */
+  double* img = a.ws + (size_t)slot * SA_IMAGE;
+  for (int k = lane; k < 1650; k += 32) img[SA_oJ2 + k] = sm[SM_oJ2 + k];
+  for (int k = lane; k < na * SM_LDM; k += 32) img[SA_oMa + k] = sm[SM_oM + 6 * SM_LDM + k];
+  for (int k = lane; k < 12 * SA_LDJA; k += 32) {
+    const int q = k / SA_LDJA, r = k % SA_LDJA;
+    img[SA_oJFa + k] = (r < na) ? sm[SM_oJF + q * TSIDB_NVX + 6 + r] : 0.0;
+  }
+  if (lane < na) { img[SA_oNle + lane] = sm[SM_oNle + 6 + lane]; img[SA_oVj + lane] = sm[SM_oQV + 32 + 6 + lane]; }
+  for (int k = lane; k < TSIDB_NX; k += 32) img[SA_oX + k] = (k < n) ? sm[SM_oX + k] : 0.0;
+  if (lane == 0) { img[SA_oSc] = c1c2; img[SA_oSc + 1] = R_norm; img[SA_oSc + 2] = (double)err; img[SA_oSc + 3] = (double)mask; }
+  __syncwarp();
+}
+
+/* ================================================================= kernel A: active set + decode of one env */
+TSIDB_DEV void activeset_env(const DevConst& C, double* sm, const TickArgs& a, int env, int slot, int lane) {
+  const int nv = C.nv, na = C.na;
+  const double* img = a.ws + (size_t)slot * SA_IMAGE;
+  for (int k = lane; k < SA_IMAGE; k += 32) sm[k] = img[k];
+  __syncwarp();
+  ASCtx S;
+  S.J2 = sm + SA_oJ2; S.Ma = sm + SA_oMa; S.JFa = sm + SA_oJFa; S.nle_a = sm + SA_oNle; S.vj = sm + SA_oVj;
+  S.x = sm + SA_oX; S.wr = sm + SA_oWr; S.U = sm + SA_oU;
+  const double c1c2 = sm[SA_oSc], R_norm = sm[SA_oSc + 1];
+  const int err = (int)sm[SA_oSc + 2], mask = (int)sm[SA_oSc + 3];
+  const int nc = (mask & 1) + ((mask >> 1) & 1);
+  const int n = nv + 12 * nc, neq = 6 + 6 * nc;
   int iters = 0;
-  uint64_t words[3];
-  int status = k3_solve<NV>(C, sm, lane, mask, nc, n, neq, iters, words);
+  uint64_t words[3] = {0, 0, 0};
+  int status = err;
+  if (err == ST_OPTIMAL) status = as_solve(C, S, lane, mask, nc, n, neq, c1c2, R_norm, iters, words);
   const bool ok = (status == ST_OPTIMAL || status == ST_MAX_ITER);
-  const double* x = sm + SM_oX;
-  double* wr = sm + SM_oX0;
+  const double* x = S.x;
+  double* wr = S.wr;
   if (ok) wrench_of(C, x, mask, wr, lane);
   __syncwarp();
   /* decode: dv = x[:nv], f = x[nv:], tau = h_a + M_a dv - J_a^T f  (ref:main.py:126-127) */
@@ -1395,12 +1524,12 @@ TSIDB_DEV void tick_env(const DevConst& C, double* sm, const TickArgs& a, int en
   if (lane < na) {
     double val = 0.0;
     if (ok) {
-      const double* Mr = sm + SM_oM + (6 + lane) * SM_LDM;
-      double s0 = sm[SM_oNle + 6 + lane], s1 = 0.0;
+      const double* Mr = S.Ma + lane * SM_LDM;
+      double s0 = S.nle_a[lane], s1 = 0.0;
       for (int j = 0; j < nv; j += 2) { s0 += Mr[j] * x[j]; s1 += (j + 1 < nv) ? Mr[j + 1] * x[j + 1] : 0.0; }
       double s = s0 + s1;
 #pragma unroll
-      for (int q = 0; q < 12; q++) s -= sm[SM_oJF + q * TSIDB_NVX + 6 + lane] * wr[q];
+      for (int q = 0; q < 12; q++) s -= S.JFa[q * SA_LDJA + lane] * wr[q];
       val = s;
     }
     a.tau[eidx(a, env, lane, na)] = val;
@@ -1419,19 +1548,57 @@ TSIDB_DEV void tick_env(const DevConst& C, double* sm, const TickArgs& a, int en
 }
 
 #ifndef TSIDB_EMU
+/* class sort: slots ordered double support, single support, flight, so that the warps of a CTA round in
+ * kernel F have equal trip counts and kernel A starts with the longest jobs. */
+__global__ void tsidb_classify_kernel(int n_envs, const uint8_t* mask, int32_t* cls_pos, int32_t* counts) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n_envs) return;
+  const int m = mask ? (mask[env] & 3) : 3;
+  const int cls = 2 - ((m & 1) + ((m >> 1) & 1)); /* 0: DS, 1: SS, 2: flight */
+  const int pos = atomicAdd(&counts[cls], 1);
+  cls_pos[env] = (cls << 28) | pos;
+}
+__global__ void tsidb_permute_kernel(int n_envs, const int32_t* cls_pos, const int32_t* counts, int32_t* perm) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n_envs) return;
+  const int cp = cls_pos[env], cls = cp >> 28, pos = cp & 0x0fffffff;
+  const int base = (cls > 0 ? counts[0] : 0) + (cls > 1 ? counts[1] : 0);
+  perm[base + pos] = env;
+}
+
 template <int NV>
 __global__ void __launch_bounds__(32 * TSIDB_WARPS_PER_BLOCK, 1)
-tsidb_tick_kernel(const TickArgs a) {
+tsidb_prepare_kernel(const TickArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* sm = smem + wid * SM_PER_ENV;
   const DevConst& C = g_const[a.slot];
+  /* rounds: in every round the CTA's warps take TSIDB_WARPS_PER_BLOCK consecutive slots and move through the
+   * phases together (PHASE_SYNC).  A warp without a slot of its own in the last round repeats the last slot
+   * (it must reach the barriers); it stores the same values again. */
+  const int per_round = gridDim.x * TSIDB_WARPS_PER_BLOCK;
+  const int rounds = (a.n_envs + per_round - 1) / per_round;
+  for (int r = 0; r < rounds; r++) {
+    int slot = (r * gridDim.x + blockIdx.x) * TSIDB_WARPS_PER_BLOCK + wid;
+    if (slot >= a.n_envs) slot = a.n_envs - 1;
+    const int env = a.perm ? a.perm[slot] : slot;
+    prepare_env<NV>(C, sm, a, env, slot, lane);
+  }
+}
+
+__global__ void __launch_bounds__(32 * TSIDB_AS_WARPS, 1)
+tsidb_activeset_kernel(const TickArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* sm = smem + wid * SA_PER_ENV;
+  const DevConst& C = g_const[a.slot];
   for (;;) {
-    int env = 0;
-    if (lane == 0) env = atomicAdd(a.counter, 1);
-    env = __shfl_sync(FULL, env, 0);
-    if (env >= a.n_envs) break;
-    tick_env<NV>(C, sm, a, env, lane);
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(a.counter, 1);
+    slot = __shfl_sync(FULL, slot, 0);
+    if (slot >= a.n_envs) break;
+    const int env = a.perm ? a.perm[slot] : slot;
+    activeset_env(C, sm, a, env, slot, lane);
   }
 }
 #endif
