@@ -55,4 +55,6 @@ template <class T> inline T __shfl_xor_sync(unsigned, T x, int m) { return emu::
 inline void __syncwarp() { emu::barrier(); }
 inline void sincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+struct double2 { double x, y; };
+inline double2 __ldcs(const double2* p) { return *p; }
 #endif

@@ -27,10 +27,11 @@ def phase_table(src):
         (r"Cholesky of the dv block: lane i keeps row", "E cholesky"), (r"B = L\^-1 \[CE\^T \| g\]", "E build B + QR"),
         (r"w_hat\[0:neq\] = R1\^-T", "E w_hat"), (r"w0 = Q w_hat", "E w0"), (r"x0 = L\^-T w0", "E x0"),
         (r"J2\[:, c\] = L\^-T Q", "E J2 columns"),
-        (r"^TSIDB_DEV int k3_solve", "K3 AS setup"), (r"for \(;;\) \{ /\* l1 \*/", "K3 AS l1: s, psi"),
+        (r"^TSIDB_DEV int as_solve", "K3 AS setup"), (r"for \(;;\) \{ /\* l1 \*/", "K3 AS l1: s, psi"),
         (r"for \(;;\) \{ /\* l2 \*/", "K3 AS l2: pick"), (r"for \(;;\) \{ /\* l2a \*/", "K3 AS l2a: d,z,r,steps"),
         (r"if \(t == t2\) \{", "K3 AS add (Householder)"), (r"partial step: drop the blocking", "K3 AS partial-step drop"),
-        (r"^TSIDB_DEV void tick_env", "tick_env io/decode"), (r"^__global__ void", "kernel loop"),
+        (r"^TSIDB_DEV void prepare_env", "F io + hand-off store"), (r"^TSIDB_DEV void activeset_env", "A load + decode"), (r"^__global__ void tsidb_classify", "kernel loops"),
+        (r"^TSIDB_DEV void eval_rows", "K3 eval rows"), (r"^TSIDB_DEV double row_dot_col", "K3 row_dot_col"), (r"^TSIDB_DEVNI void qp_delete", "K3 delete_constraint"),
     ]
     for i, line in enumerate(open(src), 1):
         for p, n in pats:
@@ -64,7 +65,9 @@ def main():
             continue
         if re.match(r"\s*/\*[0-9a-f]{4,}\*/", l):
             lines_of.append(cur)
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    filt = os.environ.get("NCU_KERNEL_FILTER")
+    cmd = ["ncu", "-i", rep, "--page", "source", "--csv"] + (["-k", "regex:" + filt] if filt else [])
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[1]
     ix = {h: i for i, h in enumerate(hdr)}

@@ -705,6 +705,7 @@ TSIDB_DEV void reflect(double (&c)[N], const double* v, double tau) {
     if (k + 3 < N) w3 += v[k + 3] * c[k + 3];
   }
   const double w = tau * ((w0 + w1) + (w2 + w3));
+  SCHED_FENCE(); /* reload v for the update instead of keeping 50 more values live (spills otherwise) */
 #pragma unroll
   for (int k = 0; k < N; k++) c[k] -= w * v[k];
 }
@@ -1494,8 +1495,21 @@ TSIDB_DEV void prepare_env(const DevConst& C, double* sm, const TickArgs& a, int
 /* ================================================================= kernel A: active set + decode of one env */
 TSIDB_DEV void activeset_env(const DevConst& C, double* sm, const TickArgs& a, int env, int slot, int lane) {
   const int nv = C.nv, na = C.na;
-  const double* img = a.ws + (size_t)slot * SA_IMAGE;
-  for (int k = lane; k < SA_IMAGE; k += 32) sm[k] = img[k];
+  {
+    /* 20 KB image: 16-byte loads, 8 in flight per lane before the first store */
+    const double2* img2 = reinterpret_cast<const double2*>(a.ws + (size_t)slot * SA_IMAGE);
+    double2* sm2 = reinterpret_cast<double2*>(sm);
+    constexpr int NV2 = SA_IMAGE / 2;
+    int k = lane;
+    for (; k + 7 * 32 < NV2; k += 8 * 32) {
+      double2 t[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) t[j] = __ldcs(img2 + k + 32 * j);
+#pragma unroll
+      for (int j = 0; j < 8; j++) sm2[k + 32 * j] = t[j];
+    }
+    for (; k < NV2; k += 32) sm2[k] = __ldcs(img2 + k);
+  }
   __syncwarp();
   ASCtx S;
   S.J2 = sm + SA_oJ2; S.Ma = sm + SA_oMa; S.JFa = sm + SA_oJFa; S.nle_a = sm + SA_oNle; S.vj = sm + SA_oVj;
