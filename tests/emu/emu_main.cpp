@@ -16,6 +16,9 @@ static void lane_entry(int lane) {
   if (g_job.stage == 0) {
     if (g_job.C->nv == 26) prepare_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
     else prepare_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
+  } else if (g_job.stage == 1) {
+    if (g_job.C->nv == 26) j2_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane);
+    else j2_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane);
   } else {
     activeset_env(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
   }
@@ -77,11 +80,13 @@ extern "C" int emu_tick(const TickArgs* a_in, double* sm_out) {
   const int smn = SM_PER_ENV > SA_PER_ENV ? SM_PER_ENV : SA_PER_ENV;
   double* sm = (double*)calloc(smn, sizeof(double));
   double* ws = (double*)calloc((size_t)a.n_envs * SA_IMAGE, sizeof(double));
+  double* ws2 = (double*)calloc((size_t)a.n_envs * SG_IMAGE, sizeof(double));
   a.ws = ws;
+  a.ws2 = ws2;
   a.perm = nullptr;
   int rc = 0;
   for (int env = 0; env < a.n_envs && rc == 0; env++) {
-    for (int stage = 0; stage < (a.kin_only ? 1 : 2) && rc == 0; stage++) {
+    for (int stage = 0; stage < (a.kin_only ? 1 : 3) && rc == 0; stage++) {
       for (int k = 0; k < smn; k++) sm[k] = NAN; /* poison: catches reads of unwritten smem */
       g_job = Job{&g_const[0], sm, &a, env, stage};
       rc = run_warp(env);
@@ -90,6 +95,7 @@ extern "C" int emu_tick(const TickArgs* a_in, double* sm_out) {
   if (sm_out) memcpy(sm_out, sm, SA_PER_ENV * sizeof(double));
   free(sm);
   free(ws);
+  free(ws2);
   return rc;
 }
 extern "C" int emu_sm_per_env() { return SM_PER_ENV > SA_PER_ENV ? SM_PER_ENV : SA_PER_ENV; }

@@ -8,7 +8,7 @@
 #define TSIDB_NVX 26   /* largest nv this build keeps in shared memory (robot/v1)          */
 #define TSIDB_NX 50    /* nv + 24                                                          */
 #define TSIDB_MRED 32  /* n - nEq = na + 6*nc <= 32: one lane per reduced coordinate       */
-#define TSIDB_WARPS_PER_BLOCK 6
+#define TSIDB_WARPS_PER_BLOCK 8
 #define TSIDB_MAX_SLOTS 6
 
 struct DevConst {
@@ -57,10 +57,9 @@ struct DevConst {
 #define SM_oFr (SM_oBv + 64)            /* frames and CoM                          64 */
 #define SM_oQV (SM_oFr + 64)            /* q (32) and v (32)                       64 */
 #define SM_oX (SM_oQV + 64)             /* x        50                             50 */
-#define SM_oX0 (SM_oX + 50)             /* x0       50                             50 */
-#define SM_oJ2 (SM_oX0 + 50)            /* J2       50 x 33                      1650 */
-#define SM_oU (SM_oJ2 + 1650)           /* union region                          1700 */
-#define SM_PER_ENV (SM_oU + 1700)       /*                                       4838 */
+#define SM_oJ2 (SM_oX + 50)             /* elimination scratch (JE_*)            1406 */
+#define SM_oU (SM_oJ2 + 1406)           /* factor region (UE_*)                   764 */
+#define SM_PER_ENV (SM_oU + 764)        /*                                       3608 */
 /* task vectors inside oBv */
 #define BV_MOT 0   /* 2 x 6 contact motion rhs, by foot */
 #define BV_FOOT 12 /* 2 x 6 foot task rhs               */
@@ -73,18 +72,18 @@ struct DevConst {
 #define FR_AF 36   /* 2 x 6 */
 #define FR_COM 48  /* com 3, vcom 3, acom 3 */
 #define FR_L 57    /* angular momentum about the CoM 3, its drift 3 */
-/* union region, phase E (equality elimination) */
+/* factor region of the prepare kernel (equality elimination) */
 #define UE_L 0                    /* H -> L  26 x 27              702 */
 #define UE_ILD (UE_L + 702)       /* 1/L_ii                        26 */
 #define UE_TAU (UE_ILD + 26)      /* Householder tau               18 */
 #define UE_RD (UE_TAU + 18)       /* diagonal of R1 (beta)         18 */
-/* J2 region while the equalities are being eliminated (J2 itself is stored last) */
+/* elimination scratch of the prepare kernel */
 #define JE_VT 0                   /* dense reflectors [18][N]     900 */
 #define JE_R1 (JE_VT + 900)       /* R1 [18][SM_LDB]              342 */
 #define JE_G (JE_R1 + 342)        /* gradient / Q^T w_unc / w_hat  50 */
 #define JE_COL (JE_G + 50)        /* published column              50 */
 #define JE_W0 (JE_COL + 50)       /* w0                            64 */
-/* union region, phase F (active set) */
+/* work arrays of the active-set kernel */
 #define UF_R 0                    /* R packed by columns: col j at j(j+1)/2       528 */
 #define UF_IRD (UF_R + 528)       /* 1/R_jj                        32 */
 #define UF_NP (UF_IRD + 32)       /* constraint normal             50 */
@@ -116,7 +115,8 @@ struct TickArgs {
   double* o_foot[2];
   double* o_wrench;
   int32_t* counter;   /* dynamic work counter of the active-set kernel */
-  double* ws;         /* hand-off images, SA_IMAGE doubles per slot */
+  double* ws;         /* hand-off images of the active-set kernel, SA_IMAGE doubles per slot */
+  double* ws2;        /* hand-off images prepare -> J2 kernel, SG_IMAGE doubles per slot */
   const int32_t* perm; /* slot -> env (class sort), null = identity */
   int32_t kin_only;   /* stop after the kinematics (tsidb_kinematics) */
   int32_t slot;       /* constant-memory slot of the handle */

@@ -693,31 +693,47 @@ TSIDB_DEV void fwdsub_L(double (&b)[NV + 24], const double* L, const double* ild
   }
 }
 
-/* c <- (I - tau v v^T) c with the dense reflector v (explicit zeros above its head, 1 at the head) */
-template <int N>
+/* c[0:K) <- (I - tau v v^T) c[0:K) with the dense reflector v (explicit zeros above its head, 1 at the head);
+ * rows K.. of v are zero by construction and are not visited */
+template <int N, int K>
 TSIDB_DEV void reflect(double (&c)[N], const double* v, double tau) {
   double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
 #pragma unroll
-  for (int k = 0; k + 1 < N; k += 4) {
+  for (int k = 0; k + 1 < K; k += 4) {
     w0 += v[k] * c[k];
     w1 += v[k + 1] * c[k + 1];
-    if (k + 2 < N) w2 += v[k + 2] * c[k + 2];
-    if (k + 3 < N) w3 += v[k + 3] * c[k + 3];
+    if (k + 2 < K) w2 += v[k + 2] * c[k + 2];
+    if (k + 3 < K) w3 += v[k + 3] * c[k + 3];
   }
   const double w = tau * ((w0 + w1) + (w2 + w3));
   SCHED_FENCE(); /* reload v for the update instead of keeping 50 more values live (spills otherwise) */
 #pragma unroll
-  for (int k = 0; k < N; k++) c[k] -= w * v[k];
+  for (int k = 0; k < K; k++) c[k] -= w * v[k];
+}
+
+/* head row of reflector k for a class with NCM contact-motion equalities (see k3_eliminate) */
+template <int NV, int NCM>
+TSIDB_DEV constexpr int head_row(int k) { return (k < NCM || NCM == 0) ? k : NV + (k - NCM); }
+
+template <int N, int NV, int NCM, int NEQ>
+TSIDB_DEV void store_R1(double* R1, const double (&b)[N], int lane) {
+#pragma unroll
+  for (int k = 0; k < NEQ; k++) R1[k * SM_LDB + lane] = b[head_row<NV, NCM>(k)];
 }
 
 /* The equality elimination.  In: H (dv block) in U+UE_L, gradient in JE_G, M/JF/bv from K1/K2.
- * Out: x = x0 (the equality-constrained minimiser), J2 (n x m), c1*c2 product and R_norm; status 0 or an
- * HQP error status. */
+ * Out: x = x0 (the equality-constrained minimiser), the Cholesky factor L (U+UE_L, UE_ILD) and the Householder
+ * reflectors of B = L^-1 CE^T (JE_VT, UE_TAU) from which the J2 kernel builds the null-space basis, the c1*c2
+ * product and R_norm; returns 0 or an HQP error status.
+ *
+ * Column order of B: the 6*nc contact-motion rows first, then the 6 base-dynamics rows.  Any order yields the
+ * same null space, x0 and projector; this one keeps the first 6*nc reflectors inside the dv rows (a contact-motion
+ * row has no force entries), which halves their cost here and in the J2 kernel. */
 template <int NV>
 TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, int nc, int n, int neq,
                            double& c1c2, double& R_norm_out) {
   constexpr int N = NV + 24;
-  const int m = n - neq;
+  const int ncm = 6 * nc;
   double* U = sm + SM_oU;
   double* L = U + UE_L;
   double* ild = U + UE_ILD;
@@ -729,11 +745,11 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
   double* gv = JE + JE_G;    /* gradient, later Q^T w_unc / w_hat */
   double* colp = JE + JE_COL;
   double* w0v = JE + JE_W0;
-  double* J2 = sm + SM_oJ2;
   double* x = sm + SM_oX;
   const double* Mm = sm + SM_oM;
   const double* JF = sm + SM_oJF;
   const double* bv = sm + SM_oBv;
+  const int f0 = (mask & 1) ? 0 : 1; /* foot of force block 0 */
 
   int err = ST_OPTIMAL; /* an error status is carried to the end: every warp must reach every PHASE_SYNC */
   PHASE_SYNC();
@@ -780,20 +796,26 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
   {
     double b[N];
     const int e = lane;
-    const int f0 = (mask & 1) ? 0 : 1; /* foot of force block 0 */
 #pragma unroll
     for (int k = 0; k < N; k++) b[k] = 0.0;
-    if (e < 6) {
-      /* base dynamics row e: [M(e,:) | -Jc(:,e)^T] */
+    if (e < ncm) {
+      /* contact motion row: [JF_f(r,:) | 0], contacts in x order */
+      const int s = e / 6, r = e % 6;
+      const int f = (s == 0) ? f0 : 1;
 #pragma unroll
-      for (int k = 0; k < NV; k++) b[k] = Mm[e * SM_LDM + k];
+      for (int k = 0; k < NV; k++) b[k] = JF[(f * 6 + r) * TSIDB_NVX + k];
+    } else if (e < neq) {
+      /* base dynamics row u: [M(u,:) | -Jc(:,u)^T] */
+      const int u = e - ncm;
+#pragma unroll
+      for (int k = 0; k < NV; k++) b[k] = Mm[u * SM_LDM + k];
 #pragma unroll
       for (int s = 0; s < 2; s++) {
         if (s < nc) {
           const int f = (s == 0) ? f0 : 1;
           double jf[6];
 #pragma unroll
-          for (int r = 0; r < 6; r++) jf[r] = JF[(f * 6 + r) * TSIDB_NVX + e];
+          for (int r = 0; r < 6; r++) jf[r] = JF[(f * 6 + r) * TSIDB_NVX + u];
 #pragma unroll
           for (int o = 0; o < 12; o++) {
             double acc = 0.0;
@@ -803,12 +825,6 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
           }
         }
       }
-    } else if (e < neq) {
-      /* contact motion row: [JF_f(r,:) | 0], contacts in x order */
-      const int s = (e - 6) / 6, r = (e - 6) % 6;
-      const int f = (s == 0) ? f0 : 1;
-#pragma unroll
-      for (int k = 0; k < NV; k++) b[k] = JF[(f * 6 + r) * TSIDB_NVX + k];
     } else if (e == neq) {
 #pragma unroll
       for (int k = 0; k < N; k++) b[k] = gv[k];
@@ -822,6 +838,15 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
     for (int i = 0; i < 18; i++) {
       PHASE_SYNC();
       if (i >= neq) continue;
+      /* Reflector i < ncm (contact motion): head row i, span = dv rows i..NV-1.  Reflector i >= ncm (base
+       * dynamics): head = force row NV + (i - ncm), span = dv rows ncm..NV-1 and the force rows from the head
+       * on.  The base-dynamics columns carry their largest entries in the force rows (scaled by Lf^-1), so
+       * pivoting on those keeps the factorisation row-wise stable; with the head on a small dv row the
+       * result is 40x further from the 80-bit truth (measured).  Without contacts there are no
+       * force rows: head i, span i..NV-1. */
+      const bool top = i < ncm || nc == 0;
+      const int head = top ? i : NV + (i - ncm);
+      const int lo = top ? i : ncm;          /* first dv row of the span */
       __syncwarp();
       if (lane == i) {
 #pragma unroll
@@ -829,9 +854,12 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
       }
       __syncwarp();
       double part = 0.0;
-      for (int k = i + 1 + lane; k < n; k += 32) { const double t = colp[k]; part += t * t; }
+      for (int k = lane; k < n; k += 32) {
+        const bool in_span = (k >= lo && k < NV) || (!top && k > head);
+        if (in_span && k != head) { const double t = colp[k]; part += t * t; }
+      }
       const double sigma = warp_sum(part);
-      const double alpha = colp[i];
+      const double alpha = colp[head];
       const double nrm = sqrt(alpha * alpha + sigma);
       const double beta = (alpha >= 0.0) ? -nrm : nrm;
       /* dependent equality row [eiquadprog add_constraint: |d(iq)| <= eps * R_norm] */
@@ -839,17 +867,24 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
       R_norm = fmax(R_norm, fabs(beta));
       const double tau = (beta - alpha) / beta;
       const double scal = 1.0 / (alpha - beta);
-      for (int k = lane; k < N; k += 32) Vt[i * N + k] = (k < i || k >= n) ? 0.0 : ((k == i) ? 1.0 : colp[k] * scal);
+      for (int k = lane; k < N; k += 32) {
+        const bool in_span = k < n && ((k >= lo && k < NV) || (!top && k > head));
+        Vt[i * N + k] = (k == head) ? 1.0 : (in_span ? colp[k] * scal : 0.0);
+      }
       if (lane == 0) { tauq[i] = tau; Rd[i] = beta; }
       __syncwarp();
-      if (lane > i && lane <= neq) reflect<N>(b, Vt + i * N, tau);
+      if (lane > i && lane <= neq) {
+        if (top) reflect<N, NV>(b, Vt + i * N, tau);
+        else reflect<N, N>(b, Vt + i * N, tau);
+      }
     }
     __syncwarp();
     /* R1 (strictly upper part; the diagonal is Rd) and the carried column */
     if (lane <= neq) {
-#pragma unroll
-      for (int k = 0; k < 18; k++)
-        if (k < neq) R1[k * SM_LDB + lane] = b[k];
+      /* R1[k][j] = entry of column j at the head row of reflector k */
+      if (nc == 2) store_R1<N, NV, 12, 18>(R1, b, lane);
+      else if (nc == 1) store_R1<N, NV, 6, 12>(R1, b, lane);
+      else store_R1<N, NV, 0, 6>(R1, b, lane);
     }
     if (lane == neq) {
 #pragma unroll
@@ -861,13 +896,12 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
   /* ---- w_hat[0:neq] = R1^-T rhs (forward substitution, lane <-> equation); rhs = -ce0 ---- */
   {
     double rhs = 0.0;
-    if (lane < neq) {
-      if (lane < 6) rhs = -sm[SM_oNle + lane];
-      else {
-        const int s = (lane - 6) / 6, r = (lane - 6) % 6;
-        const int f = (s == 0) ? ((mask & 1) ? 0 : 1) : 1;
-        rhs = bv[BV_MOT + 6 * f + r];
-      }
+    if (lane < ncm) {
+      const int s = lane / 6, r = lane % 6;
+      const int f = (s == 0) ? f0 : 1;
+      rhs = bv[BV_MOT + 6 * f + r];
+    } else if (lane < neq) {
+      rhs = -sm[SM_oNle + lane - ncm];
     }
     double accv = rhs;
     for (int i = 0; i < neq; i++) {
@@ -875,65 +909,59 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
       if (lane == i) accv = wi;
       else if (lane > i && lane < neq) accv -= R1[i * SM_LDB + lane] * wi;
     }
-    if (lane < neq) gv[lane] = accv;
+    __syncwarp();
+    if (lane < neq) gv[(lane < ncm || nc == 0) ? lane : NV + (lane - ncm)] = accv; /* head row of reflector `lane` */
     __syncwarp();
   }
   /* ---- w0 = Q w_hat: reflectors in reverse, lanes over rows ---- */
-  {
-    double y0 = (lane < n) ? gv[lane] : 0.0;
-    double y1 = (lane + 32 < n) ? gv[lane + 32] : 0.0;
-    for (int i = neq - 1; i >= 0; i--) {
-      const double v0 = Vt[i * N + lane];
-      const double v1 = (lane + 32 < N) ? Vt[i * N + lane + 32] : 0.0;
-      const double w = tauq[i] * warp_sum(v0 * y0 + v1 * y1);
-      y0 -= w * v0;
-      y1 -= w * v1;
-    }
-    w0v[lane] = y0;
-    if (lane + 32 < N) w0v[lane + 32] = y1;
-    __syncwarp();
+  double y0 = (lane < n) ? gv[lane] : 0.0;
+  double y1 = (lane + 32 < n) ? gv[lane + 32] : 0.0;
+  for (int i = neq - 1; i >= 0; i--) {
+    const double v0 = Vt[i * N + lane];
+    const double v1 = (lane + 32 < N) ? Vt[i * N + lane + 32] : 0.0;
+    const double w = tauq[i] * warp_sum(v0 * y0 + v1 * y1);
+    y0 -= w * v0;
+    y1 -= w * v1;
   }
-  PHASE_SYNC();
-  /* ---- x0 = L^-T w0 (every lane computes it redundantly from broadcast reads; lane 0 stores) ---- */
-  {
-    double q[N];
-#pragma unroll
-    for (int k = 0; k < N; k++) q[k] = w0v[k];
-    backsub_LT<NV>(q, L, ild, C, nc);
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < N; k++) x[k] = q[k];
-    }
+  /* ---- x0 = L^-T w0: force rows through the constant Lf^-T, dv rows by a column-oriented back substitution
+   *      (lane <-> row; one broadcast and one FMA per step) ---- */
+  w0v[lane] = y0;
+  if (lane + 32 < N) w0v[lane + 32] = y1;
+  __syncwarp();
+  if (lane < 12 * nc) {
+    const int s = lane / 12, i = lane % 12;
+    double acc = 0.0;
+    for (int k = i; k < 12; k++) acc += C.Lfinv[k][i] * w0v[NV + 12 * s + k];
+    x[NV + lane] = acc;
   }
-  PHASE_SYNC();
-  /* ---- J2[:, c] = L^-T Q [0; e_c]: lane c keeps the column in registers ---- */
-  {
-    double q[N];
-    if (lane < m) {
-#pragma unroll
-      for (int k = 0; k < N; k++) q[k] = (k == neq + lane) ? 1.0 : 0.0;
-      for (int i = neq - 1; i >= 0; i--) reflect<N>(q, Vt + i * N, tauq[i]);
-    }
-    PHASE_SYNC();
-    if (lane < m) backsub_LT<NV>(q, L, ild, C, nc);
-    __syncwarp(); /* every lane is done with Vt / R1 / w0, which live in the J2 region */
-    if (lane < m) {
-#pragma unroll
-      for (int k = 0; k < N; k++) J2[k * SM_LDJ + lane] = q[k];
-    }
-    __syncwarp();
+  for (int k = NV - 1; k >= 0; k--) {
+    const double xk = shfl(y0, k) * ild[k];
+    if (lane == k) y0 = xk;
+    else if (lane < k) y0 -= L[k * SM_LDM + lane] * xk;
   }
+  if (lane < NV) x[lane] = y0;
+  __syncwarp();
   R_norm_out = R_norm;
   return err;
 }
 
-/* ================================================================= hand-off between the two kernels */
-/* Kernel F (tsidb_prepare_kernel: K1 dynamics, K2 assembly, equality elimination) leaves one image per env
- * in a global workspace; kernel A (tsidb_activeset_kernel: active-set iterations + decode) pulls images from a
- * work counter.  The image is the active-set kernel's shared-memory layout, so the load is one linear copy.
- * Cost: 20.3 KB written + read per tick, ~3 % of the tick time at the measured HBM rate; what it buys is that
- * F runs in CTA-wide phase lock-step with no idle waiting, and A balances the data-dependent iteration
- * counts (1..40) dynamically at 8 envs per SM.                                                           */
+/* ================================================================= hand-off between the kernels */
+/* Kernel F (tsidb_prepare_kernel: K1 dynamics, K2 assembly, equality elimination) leaves two images per env in
+ * global workspaces: the factor image (SG_*: Cholesky factor + Householder reflectors) for kernel G
+ * (tsidb_j2_kernel: null-space basis J2 = L^-T Q2, one thread per column at 16 warps per SM), and the solver
+ * image (SA_*) for kernel A (tsidb_activeset_kernel: active-set iterations + decode), which pulls images from a
+ * work counter.  The solver image is kernel A's shared-memory layout, so its load is one linear copy.
+ * Cost: 13 KB + 20 KB written and read per tick, a few % of the tick time at the measured HBM rate; what it
+ * buys is that every stage runs at the occupancy and the thread mapping that suits it: F in CTA-wide phase
+ * lock-step, G register-blocked with no cross-lane traffic, A balancing the data-dependent iteration counts
+ * (1..40) dynamically.                                                                                     */
+#define SG_LDV (TSIDB_NVX + 24)           /* reflector stride written by F (JE_VT rows)      */
+#define SG_oL 0                           /* L      26 x 27                             702 */
+#define SG_oILD (SG_oL + 702)             /* 1/L_ii                                      26 */
+#define SG_oTAU (SG_oILD + 26)            /* Householder tau                             18 */
+#define SG_oVT (SG_oTAU + 18)             /* reflectors [18][50]                        900 */
+#define SG_IMAGE (SG_oVT + 900)           /* doubles handed over per env               1646 */
+#define TSIDB_G_WARPS 16
 #define SA_LDJA 20                        /* JFa row stride                                  */
 #define SA_oJ2 0                          /* J2   50 x 33                              1650 */
 #define SA_oMa (SA_oJ2 + 1650)            /* M_a  na x 27 (rows 6.. of M)               540 */
@@ -1478,9 +1506,8 @@ TSIDB_DEV void prepare_env(const DevConst& C, double* sm, const TickArgs& a, int
   k2_assemble(C, sm, a, env, lane, mask, neq, n);
   double c1c2 = 0.0, R_norm = 1.0;
   const int err = k3_eliminate<NV>(C, sm, lane, mask, nc, n, neq, c1c2, R_norm);
-  /* hand-off image (layout SA_*) */
+  /* solver image (layout SA_*; J2 is filled in by kernel G) */
   double* img = a.ws + (size_t)slot * SA_IMAGE;
-  for (int k = lane; k < 1650; k += 32) img[SA_oJ2 + k] = sm[SM_oJ2 + k];
   for (int k = lane; k < na * SM_LDM; k += 32) img[SA_oMa + k] = sm[SM_oM + 6 * SM_LDM + k];
   for (int k = lane; k < 12 * SA_LDJA; k += 32) {
     const int q = k / SA_LDJA, r = k % SA_LDJA;
@@ -1489,6 +1516,104 @@ TSIDB_DEV void prepare_env(const DevConst& C, double* sm, const TickArgs& a, int
   if (lane < na) { img[SA_oNle + lane] = sm[SM_oNle + 6 + lane]; img[SA_oVj + lane] = sm[SM_oQV + 32 + 6 + lane]; }
   for (int k = lane; k < TSIDB_NX; k += 32) img[SA_oX + k] = (k < n) ? sm[SM_oX + k] : 0.0;
   if (lane == 0) { img[SA_oSc] = c1c2; img[SA_oSc + 1] = R_norm; img[SA_oSc + 2] = (double)err; img[SA_oSc + 3] = (double)mask; }
+  /* factor image (layout SG_*): L, 1/diag, tau are contiguous in the factor region, the reflectors in the scratch */
+  double* fimg = a.ws2 + (size_t)slot * SG_IMAGE;
+  for (int k = lane; k < SG_oVT; k += 32) fimg[k] = sm[SM_oU + k];
+  for (int k = lane; k < 18 * SG_LDV; k += 32) fimg[SG_oVT + k] = sm[SM_oJ2 + JE_VT + k];
+  __syncwarp();
+}
+
+/* ================================================================= kernel G: the null-space basis of one env */
+/* J2[:, c] = L^-T Q [0; e_c], one lane per column c < m = n - neq, the column in registers, every index a
+ * compile-time constant.  The reflectors are applied in reverse: the base-dynamics ones (rows i..n-1) first,
+ * after which the force rows are final and leave through the constant Lf^-T; then the contact-motion ones
+ * (rows i..nv-1) and the back substitution with L on the dv rows.  Operands shared by the warp (reflector and
+ * factor entries) are broadcast reads from shared memory. */
+template <int NV, int NC>
+TSIDB_DEV void j2_columns(const DevConst& C, const double* sg, double* img, int lane) {
+  constexpr int NS = NV + 24;
+  constexpr int N = NV + 12 * NC, NEQ = 6 + 6 * NC, NCM = 6 * NC, M = N - NEQ;
+  if (lane >= M) return;
+  const double* L = sg + SG_oL;
+  const double* ild = sg + SG_oILD;
+  const double* tauq = sg + SG_oTAU;
+  const double* Vt = sg + SG_oVT;
+  /* column c starts as the unit vector of the c-th row that is not a reflector head: dv rows NCM..NV-1, then
+   * the force rows NV+6.. (without contacts: rows 6..NV-1) */
+  double q[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const int col = (NC == 0) ? k - 6 : ((k < NV) ? k - NCM : ((k >= NV + 6) ? (NV - NCM) + (k - NV - 6) : -1));
+    q[k] = (col >= 0 && col == lane) ? 1.0 : 0.0;
+  }
+#pragma unroll
+  for (int i = NEQ - 1; i >= 0; i--) {
+    const bool top = (i < NCM) || NC == 0;
+    const int head = top ? i : NV + (i - NCM);
+    const int lo = top ? i + 1 : NCM;            /* dv rows lo..NV-1 */
+    const int flo = top ? N : head + 1;          /* force rows flo..N-1 */
+    const double* v = Vt + i * NS;
+    /* the head row is still zero here (no reflector applied so far touches it) and v[head] = 1 */
+    double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+#pragma unroll
+    for (int k = lo; k < NV; k++) {
+      if ((k & 3) == 0) w0 += v[k] * q[k];
+      else if ((k & 3) == 1) w1 += v[k] * q[k];
+      else if ((k & 3) == 2) w2 += v[k] * q[k];
+      else w3 += v[k] * q[k];
+    }
+#pragma unroll
+    for (int k = flo; k < N; k++) {
+      if ((k & 3) == 0) w0 += v[k] * q[k];
+      else if ((k & 3) == 1) w1 += v[k] * q[k];
+      else if ((k & 3) == 2) w2 += v[k] * q[k];
+      else w3 += v[k] * q[k];
+    }
+    const double w = tauq[i] * ((w0 + w1) + (w2 + w3));
+    q[head] = -w;
+#pragma unroll
+    for (int k = lo; k < NV; k++) q[k] -= w * v[k];
+#pragma unroll
+    for (int k = flo; k < N; k++) q[k] -= w * v[k];
+    if (i == NCM) {
+      /* force rows are final: J2_f = Lf^-T q_f, stored right away */
+#pragma unroll
+      for (int s = 0; s < NC; s++) {
+#pragma unroll
+        for (int r = 0; r < 12; r++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = r; k < 12; k++) acc += C.Lfinv[k][r] * q[NV + 12 * s + k];
+          img[SA_oJ2 + (NV + 12 * s + r) * SM_LDJ + lane] = acc;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = NV - 1; k >= 0; k--) {
+    q[k] *= ild[k];
+#pragma unroll
+    for (int i = 0; i < k; i++) q[i] -= L[k * SM_LDM + i] * q[k];
+  }
+#pragma unroll
+  for (int k = 0; k < NV; k++) img[SA_oJ2 + k * SM_LDJ + lane] = q[k];
+}
+
+template <int NV>
+TSIDB_DEV void j2_env(const DevConst& C, double* sg, const TickArgs& a, int slot, int lane) {
+  double* img = a.ws + (size_t)slot * SA_IMAGE;
+  const int err = (int)img[SA_oSc + 2], mask = (int)img[SA_oSc + 3];
+  if (err != ST_OPTIMAL) return; /* the active-set kernel reports the status and never reads J2 */
+  {
+    const double2* src = reinterpret_cast<const double2*>(a.ws2 + (size_t)slot * SG_IMAGE);
+    double2* dst = reinterpret_cast<double2*>(sg);
+    for (int k = lane; k < SG_IMAGE / 2; k += 32) dst[k] = __ldcs(src + k);
+  }
+  __syncwarp();
+  const int nc = (mask & 1) + ((mask >> 1) & 1);
+  if (nc == 2) j2_columns<NV, 2>(C, sg, img, lane);
+  else if (nc == 1) j2_columns<NV, 1>(C, sg, img, lane);
+  else j2_columns<NV, 0>(C, sg, img, lane);
   __syncwarp();
 }
 
@@ -1598,6 +1723,19 @@ tsidb_prepare_kernel(const TickArgs a) {
     const int env = a.perm ? a.perm[slot] : slot;
     prepare_env<NV>(C, sm, a, env, slot, lane);
   }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(32 * TSIDB_G_WARPS, 1)
+tsidb_j2_kernel(const TickArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* sg = smem + wid * SG_IMAGE;
+  const DevConst& C = g_const[a.slot];
+  /* every column costs the same within a contact class and the slots are class-sorted: a static stride
+   * spreads each class evenly over the SMs */
+  for (int slot = blockIdx.x * TSIDB_G_WARPS + wid; slot < a.n_envs; slot += gridDim.x * TSIDB_G_WARPS)
+    j2_env<NV>(C, sg, a, slot, lane);
 }
 
 __global__ void __launch_bounds__(32 * TSIDB_AS_WARPS, 1)
