@@ -53,6 +53,17 @@ template <class T> inline T exchange(T x, int src) {
 template <class T> inline T __shfl_sync(unsigned, T x, int src) { return emu::exchange(x, src); }
 template <class T> inline T __shfl_xor_sync(unsigned, T x, int m) { return emu::exchange(x, emu::W.cur ^ m); }
 inline void __syncwarp() { emu::barrier(); }
+inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+  unsigned m = v;
+  for (int o = 16; o > 0; o >>= 1) { unsigned t = emu::exchange(m, emu::W.cur ^ o); m = t < m ? t : m; }
+  return m;
+}
+inline unsigned __ballot_sync(unsigned, bool p) {
+  unsigned m = p ? (1u << emu::W.cur) : 0u;
+  for (int o = 16; o > 0; o >>= 1) m |= emu::exchange(m, emu::W.cur ^ o);
+  return m;
+}
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline void sincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 struct double2 { double x, y; };

@@ -20,7 +20,8 @@ static void lane_entry(int lane) {
     if (g_job.C->nv == 26) j2_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane);
     else j2_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane);
   } else {
-    activeset_env(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
+    unsigned parity = 0;
+    activeset_env(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
   }
   emu::W.done[lane] = true;
   swapcontext(&emu::W.ctx[lane], &emu::W.sched);

@@ -87,10 +87,10 @@ struct DevConst {
 #define UF_R 0                    /* R packed by columns: col j at j(j+1)/2       528 */
 #define UF_IRD (UF_R + 528)       /* 1/R_jj                        32 */
 #define UF_NP (UF_IRD + 32)       /* constraint normal             50 */
-#define UF_D (UF_NP + 50)         /* d                             32 */
-#define UF_RR (UF_D + 32)         /* r                             32 */
-#define UF_Z (UF_RR + 32)         /* z                             50 */
-#define UF_U (UF_Z + 50)          /* u                             34 */
+#define UF_D (UF_NP + 50)         /* d (free columns), padded      34 */
+#define UF_RR (UF_D + 34)         /* r                             32 */
+#define UF_VV (UF_RR + 32)        /* Householder vector, padded    34 */
+#define UF_U (UF_VV + 34)         /* u                             34 */
 #define UF_UO (UF_U + 34)         /* u_old                         34 */
 #define UF_XO (UF_UO + 34)        /* x_old                         50 */
 #define UF_A (UF_XO + 50)         /* A, A_old as int32: 2 x 34 ints = 34 doubles */

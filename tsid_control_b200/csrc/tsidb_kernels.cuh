@@ -963,18 +963,77 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
 #define SG_IMAGE (SG_oVT + 900)           /* doubles handed over per env               1646 */
 #define TSIDB_G_WARPS 16
 #define SA_LDJA 20                        /* JFa row stride                                  */
-#define SA_oJ2 0                          /* J2   50 x 33                              1650 */
-#define SA_oMa (SA_oJ2 + 1650)            /* M_a  na x 27 (rows 6.. of M)               540 */
-#define SA_oJFa (SA_oMa + 540)            /* JF columns 6.., 12 x 20                     240 */
+#define SA_LDJ 34                         /* J2 row stride: even (16-byte row accesses), conflict-free by rows and by columns */
+#define SA_LDM 30                         /* M_a row stride: even, 16-byte lane-strided reads are conflict-free           */
+#define SA_oJ2 0                          /* J2   50 x 34                              1700 */
+#define SA_oMa (SA_oJ2 + 1700)            /* M_a  na x 30 (rows 6.. of M)               600 */
+#define SA_oJFa (SA_oMa + 600)            /* JF columns 6.., 12 x 20                     240 */
 #define SA_oNle (SA_oJFa + 240)           /* nle_a                                        20 */
 #define SA_oVj (SA_oNle + 20)             /* joint velocities                             20 */
 #define SA_oX (SA_oVj + 20)               /* x                                            50 */
 #define SA_oSc (SA_oX + 50)               /* c1*c2, R_norm, error status, contact mask     4 */
-#define SA_IMAGE (SA_oSc + 4)             /* doubles handed over per env                2524 */
+#define SA_IMAGE (SA_oSc + 4)             /* doubles handed over per env                2634 */
 #define SA_oWr (SA_IMAGE)                 /* wrenches                                     12 */
 #define SA_oU (SA_oWr + 12)               /* active-set work arrays (UF_*)                   */
-#define SA_PER_ENV (SA_oU + UF_END)
+#define SA_oBar (SA_oU + UF_END)          /* mbarrier of the image load                    2 */
+#define SA_PER_ENV (SA_oBar + 2)
 #define TSIDB_AS_WARPS 8
+
+/* ---- bulk asynchronous copy global -> shared (TMA, 1-D) completed through an mbarrier ---- */
+#ifndef TSIDB_EMU
+TSIDB_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+TSIDB_DEV void mbar_init(void* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+/* issued by ONE lane: every generic-proxy access of the destination by this warp must be ordered before
+ * (caller: __syncwarp) */
+TSIDB_DEV void bulk_load(void* dst, const void* src, unsigned bytes, void* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+TSIDB_DEV void mbar_wait(void* bar, unsigned parity) {
+  unsigned ok = 0;
+  const unsigned addr = smem_u32(bar);
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+#endif
+
+/* order-preserving map double -> uint64 (smaller double <-> smaller key) */
+TSIDB_DEV unsigned long long sortable(double v) {
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+/* lane holding the smallest `val` among the lanes with `valid`, ties to the smallest `tiebreak` (unique per
+ * lane); -1 if no lane is valid.  Three REDUX instead of a 5-level shuffle tree on (double, int, int). */
+TSIDB_DEV int warp_argmin(double val, bool valid, int tiebreak) {
+  const unsigned long long key = sortable(val);
+  const unsigned hi = valid ? (unsigned)(key >> 32) : 0xffffffffu;
+  const unsigned mhi = __reduce_min_sync(FULL, hi);
+  const bool v1 = valid && hi == mhi;
+  const unsigned lo = v1 ? (unsigned)key : 0xffffffffu;
+  const unsigned mlo = __reduce_min_sync(FULL, lo);
+  const bool v2 = v1 && lo == mlo;
+  const unsigned tb = v2 ? (unsigned)tiebreak : 0xffffffffu;
+  const unsigned mtb = __reduce_min_sync(FULL, tb);
+  const unsigned win = __ballot_sync(FULL, v2 && tb == mtb);
+  return win ? (__ffs(win) - 1) : -1;
+}
+
+/* per-lane constants of one env, kept in registers across the iterations */
+struct LaneConst {
+  double lb, ub;     /* joint-bound row `lane`: lb <= dv_j <= ub */
+  double Trow[12];   /* row lane%6 of the force generator */
+};
 
 struct ASCtx {
   double* J2;
@@ -1020,7 +1079,7 @@ TSIDB_DEV int cid_bit(const DevConst& C, int cid) {
 }
 
 /* s = CI x + ci0 for the rows this lane owns; invalid rows get +inf */
-TSIDB_DEV void eval_rows(const DevConst& C, const ASCtx& S, int lane, int mask, double (&s)[6]) {
+TSIDB_DEV void eval_rows(const DevConst& C, const ASCtx& S, const LaneConst& K, int lane, int mask, double (&s)[6]) {
   const int na = C.na, nv = C.nv;
   const double* x = S.x;
 #pragma unroll
@@ -1044,14 +1103,16 @@ TSIDB_DEV void eval_rows(const DevConst& C, const ASCtx& S, int lane, int mask, 
   }
   if (lane < na) {
     if (C.use_tb) {
-      /* tau_r = h_r + M_a(r,:) dv - sum_f JF_f(:,6+r)^T (T f_f) */
-      const double* Mr = S.Ma + lane * SM_LDM;
+      /* tau_r = h_r + M_a(r,:) dv - sum_f JF_f(:,6+r)^T (T f_f); 16-byte reads of the row and of x */
+      const double2* Mr = reinterpret_cast<const double2*>(S.Ma + lane * SA_LDM);
+      const double2* x2 = reinterpret_cast<const double2*>(x);
       double t0 = S.nle_a[lane], t1 = 0.0, t2 = 0.0, t3 = 0.0;
       int j = 0;
-      for (; j + 3 < nv; j += 4) {
-        t0 += Mr[j] * x[j]; t1 += Mr[j + 1] * x[j + 1]; t2 += Mr[j + 2] * x[j + 2]; t3 += Mr[j + 3] * x[j + 3];
+      for (; j + 1 < nv / 2; j += 2) {
+        const double2 m0 = Mr[j], m1 = Mr[j + 1], x0 = x2[j], x1 = x2[j + 1];
+        t0 += m0.x * x0.x; t1 += m0.y * x0.y; t2 += m1.x * x1.x; t3 += m1.y * x1.y;
       }
-      for (; j < nv; j++) t0 += Mr[j] * x[j];
+      for (; j < nv / 2; j++) { const double2 m0 = Mr[j], x0 = x2[j]; t0 += m0.x * x0.x; t1 += m0.y * x0.y; }
       double t = (t0 + t1) + (t2 + t3);
 #pragma unroll
       for (int q = 0; q < 12; q++) t -= S.JFa[q * SA_LDJA + lane] * S.wr[q];
@@ -1059,11 +1120,8 @@ TSIDB_DEV void eval_rows(const DevConst& C, const ASCtx& S, int lane, int mask, 
       s[3] = C.tau_max[lane] - t;
     }
     if (C.use_jb) {
-      const double vj = S.vj[lane];
-      const double ub = fmin((C.v_max[lane] - vj) / C.jb_dt, 1e10);
-      const double lb = fmax((C.v_min[lane] - vj) / C.jb_dt, -1e10);
-      s[4] = x[6 + lane] - lb;
-      s[5] = ub - x[6 + lane];
+      s[4] = x[6 + lane] - K.lb;
+      s[5] = K.ub - x[6 + lane];
     }
   }
 }
@@ -1086,7 +1144,7 @@ TSIDB_DEV double eval_one(const DevConst& C, const ASCtx& S, int cid, int mask) 
   }
   if (cid < 36 + 2 * na) {
     const int k = cid - 36, side = k >= na ? 1 : 0, r = k - side * na;
-    const double* Mr = S.Ma + r * SM_LDM;
+    const double* Mr = S.Ma + r * SA_LDM;
     double t = S.nle_a[r];
     for (int j = 0; j < nv; j++) t += Mr[j] * x[j];
 #pragma unroll
@@ -1109,29 +1167,29 @@ TSIDB_DEV double row_dot_col(const DevConst& C, const ASCtx& S, int cid, int mas
   if (cid < 32) {
     const int f = cid >> 4, c = (cid & 15) >> 2, k = cid & 3;
     const int r0 = fvar0(nv, mask, f) + 3 * c;
-    return -(C.fric[k][0] * Jc[r0 * SM_LDJ] + C.fric[k][1] * Jc[(r0 + 1) * SM_LDJ] + C.fric[k][2] * Jc[(r0 + 2) * SM_LDJ]);
+    return -(C.fric[k][0] * Jc[r0 * SA_LDJ] + C.fric[k][1] * Jc[(r0 + 1) * SA_LDJ] + C.fric[k][2] * Jc[(r0 + 2) * SA_LDJ]);
   }
   if (cid < 36) {
     const int f = (cid - 32) >> 1, side = (cid - 32) & 1;
     const int r0 = fvar0(nv, mask, f);
     double t = 0.0;
 #pragma unroll
-    for (int o = 0; o < 12; o++) t += C.nrm[o % 3] * Jc[(r0 + o) * SM_LDJ];
+    for (int o = 0; o < 12; o++) t += C.nrm[o % 3] * Jc[(r0 + o) * SA_LDJ];
     return side ? -t : t;
   }
   if (cid >= 36 + 2 * na) {
     const int k = cid - 36 - 2 * na, side = k >= na ? 1 : 0, i = k - side * na;
-    const double t = Jc[(6 + i) * SM_LDJ];
+    const double t = Jc[(6 + i) * SA_LDJ];
     return side ? -t : t;
   }
   /* actuation row r: n = +-[M_a(r,:) | -Jc(:,6+r)^T]; every lane reads the normal from np */
   double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
   int k = 0;
   for (; k + 3 < n; k += 4) {
-    d0 += np[k] * Jc[k * SM_LDJ]; d1 += np[k + 1] * Jc[(k + 1) * SM_LDJ];
-    d2 += np[k + 2] * Jc[(k + 2) * SM_LDJ]; d3 += np[k + 3] * Jc[(k + 3) * SM_LDJ];
+    d0 += np[k] * Jc[k * SA_LDJ]; d1 += np[k + 1] * Jc[(k + 1) * SA_LDJ];
+    d2 += np[k + 2] * Jc[(k + 2) * SA_LDJ]; d3 += np[k + 3] * Jc[(k + 3) * SA_LDJ];
   }
-  for (; k < n; k++) d0 += np[k] * Jc[k * SM_LDJ];
+  for (; k < n; k++) d0 += np[k] * Jc[k * SA_LDJ];
   return (d0 + d1) + (d2 + d3);
 }
 /* dense normal of an actuation row into np[0..n) (all lanes cooperate) */
@@ -1140,7 +1198,7 @@ TSIDB_DEV void actuation_normal(const DevConst& C, const ASCtx& S, int cid, int 
   const int q = cid - 36, side = q >= na ? 1 : 0, r = q - side * na;
   for (int k = lane; k < n; k += 32) {
     double val;
-    if (k < nv) val = S.Ma[r * SM_LDM + k];
+    if (k < nv) val = S.Ma[r * SA_LDM + k];
     else {
       const int o = k - nv;
       const int f = (mask == 3) ? (o / 12) : ((mask & 1) ? 0 : 1);
@@ -1155,14 +1213,14 @@ TSIDB_DEV void actuation_normal(const DevConst& C, const ASCtx& S, int cid, int 
 }
 
 /* wrench T f of both feet -> wr[12] (zero for a foot not in contact); lanes 0..11 */
-TSIDB_DEV void wrench_of(const DevConst& C, const double* x, int mask, double* wr, int lane) {
+TSIDB_DEV void wrench_of(const DevConst& C, const LaneConst& K, const double* x, int mask, double* wr, int lane) {
   if (lane < 12) {
-    const int f = lane / 6, r = lane % 6;
+    const int f = lane / 6;
     double s = 0.0;
     if ((mask >> f) & 1) {
       const double* ff = x + fvar0(C.nv, mask, f);
 #pragma unroll
-      for (int j = 0; j < 12; j++) s += C.T[r][j] * ff[j];
+      for (int j = 0; j < 12; j++) s += K.Trow[j] * ff[j];
     }
     wr[lane] = s;
   }
@@ -1220,10 +1278,10 @@ TSIDB_DEVNI void qp_delete(const ASCtx& S, int n, int& iq, int qq, int lane) {
     }
     /* columns j, j+1 of J2: lanes over rows */
     for (int k = lane; k < n; k += 32) {
-      double t1 = J2[k * SM_LDJ + j], t2 = J2[k * SM_LDJ + j + 1];
+      double t1 = J2[k * SA_LDJ + j], t2 = J2[k * SA_LDJ + j + 1];
       double n1 = t1 * cc + t2 * ss;
-      J2[k * SM_LDJ + j] = n1;
-      J2[k * SM_LDJ + j + 1] = xny * (n1 + t1) - t2;
+      J2[k * SA_LDJ + j] = n1;
+      J2[k * SA_LDJ + j + 1] = xny * (n1 + t1) - t2;
     }
     __syncwarp();
   }
@@ -1232,7 +1290,7 @@ TSIDB_DEVNI void qp_delete(const ASCtx& S, int n, int& iq, int qq, int lane) {
 }
 
 /* Active-set iterations on the reduced basis [eiquadprog-fast solve_quadprog, after the equality phase]. */
-TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, int lane, int mask, int nc, int n, int neq,
+TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, int lane, int mask, int nc, int n, int neq,
                        double c1c2, double R_norm, int& iters_out, uint64_t* act_words) {
   const int na = C.na;
   const int m = n - neq; /* reduced dimension, <= 32 */
@@ -1243,9 +1301,9 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, int lane, int mask, in
   double* Rp = U + UF_R;
   double* ird = U + UF_IRD;
   double* np = U + UF_NP;
-  double* dd = U + UF_D;
+  double* dd = U + UF_D;   /* d with the entries of the active columns zeroed, zero padded to 34 */
   double* rr = U + UF_RR;
-  double* zz_ = U + UF_Z;
+  double* vv = U + UF_VV;  /* Householder vector over the columns, zero below iq, zero padded to 34 */
   double* u = U + UF_U;
   double* uo = U + UF_UO;
   double* xo = U + UF_XO;
@@ -1253,6 +1311,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, int lane, int mask, in
   int* Ao = A + 34;
   iters_out = 0;
   act_words[0] = act_words[1] = act_words[2] = 0;
+  if (lane < 2) { dd[32 + lane] = 0.0; vv[32 + lane] = 0.0; }
 
   const int nin_ref = C.nin_ref_fixed + 34 * nc;
   const double psi_thresh = (double)nin_ref * TS_EPS * c1c2 * 100.0;
@@ -1263,10 +1322,10 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, int lane, int mask, in
   for (;;) { /* l1 */
     iter++;
     if (iter >= C.max_iter) { status = ST_MAX_ITER; break; }
-    wrench_of(C, x, mask, wr, lane);
+    wrench_of(C, K, x, mask, wr, lane);
     __syncwarp();
     double sl[6];
-    eval_rows(C, S, lane, mask, sl);
+    eval_rows(C, S, K, lane, mask, sl);
     double part = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; k++) part += (sl[k] < 0.0) ? sl[k] : 0.0;
@@ -1290,19 +1349,13 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, int lane, int mask, in
           if (sl[k] < best || (sl[k] == best && bit < bbit)) { best = sl[k]; bcid = cid; bbit = bit; }
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        double ob = __shfl_xor_sync(FULL, best, o);
-        int oc = __shfl_xor_sync(FULL, bcid, o);
-        int obit = __shfl_xor_sync(FULL, bbit, o);
-        if (oc >= 0 && (bcid < 0 || ob < best || (ob == best && obit < bbit))) { best = ob; bcid = oc; bbit = obit; }
-      }
-      if (bcid < 0) { status = ST_OPTIMAL; done = true; break; }
-      const int ip = bcid;
+      const int src = warp_argmin(best, bcid >= 0, bbit);
+      if (src < 0) { status = ST_OPTIMAL; done = true; break; }
+      const int ip = __shfl_sync(FULL, bcid, src);
+      double s_ip = shfl(best, src);
       int ip_lane, ip_slot;
       cid_owner(na, ip, ip_lane, ip_slot);
       const bool dense_row = (ip >= 36 && ip < 36 + 2 * na);
-      double s_ip = best;
 #ifdef TSIDB_EMU_TRACE
       if (lane == 0) printf("[emu] iter %d pick bit %d s=%.17g iq=%d\n", iter, cid_bit(C, ip), s_ip, iq);
 #endif
@@ -1312,28 +1365,25 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, int lane, int mask, in
       for (;;) { /* l2a */
         /* d = J2^T n_ip (lane <-> column) */
         double dl = 0.0;
-        if (lane < m) {
-          dl = row_dot_col(C, S, ip, mask, n, lane, np);
-          dd[lane] = dl;
-        }
+        if (lane < m) dl = row_dot_col(C, S, ip, mask, n, lane, np);
+        dd[lane] = (lane >= iq && lane < m) ? dl : 0.0;
         __syncwarp();
-        /* z = J2[:, iq:] d[iq:] (lanes over rows); zero if no free direction is left */
+        /* z = J2[:, iq:] d[iq:] (lanes over rows, 16-byte reads of the row and of d); zero if no free
+         * direction is left */
         double z0 = 0.0, z1 = 0.0;
         if (iq < m) {
+          const int c0 = iq >> 1, c1 = (m + 1) >> 1;
+          const double2* d2 = reinterpret_cast<const double2*>(dd);
           if (lane < n) {
-            const double* Jr = J2 + lane * SM_LDJ;
+            const double2* Jr = reinterpret_cast<const double2*>(J2 + lane * SA_LDJ);
             double a0 = 0.0, a1 = 0.0;
-            int c = iq;
-            for (; c + 1 < m; c += 2) { a0 += Jr[c] * dd[c]; a1 += Jr[c + 1] * dd[c + 1]; }
-            if (c < m) a0 += Jr[c] * dd[c];
+            for (int c = c0; c < c1; c++) { const double2 jv = Jr[c], dv = d2[c]; a0 += jv.x * dv.x; a1 += jv.y * dv.y; }
             z0 = a0 + a1;
           }
           if (lane + 32 < n) {
-            const double* Jr = J2 + (lane + 32) * SM_LDJ;
+            const double2* Jr = reinterpret_cast<const double2*>(J2 + (lane + 32) * SA_LDJ);
             double a0 = 0.0, a1 = 0.0;
-            int c = iq;
-            for (; c + 1 < m; c += 2) { a0 += Jr[c] * dd[c]; a1 += Jr[c + 1] * dd[c + 1]; }
-            if (c < m) a0 += Jr[c] * dd[c];
+            for (int c = c0; c < c1; c++) { const double2 jv = Jr[c], dv = d2[c]; a0 += jv.x * dv.x; a1 += jv.y * dv.y; }
             z1 = a0 + a1;
           }
         }
@@ -1349,17 +1399,13 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, int lane, int mask, in
         }
         /* partial step t1 = min u_k / r_k over r_k > 0, first index on ties */
         double t1 = TS_INF;
-        int lpos = -1;
+        bool t1_valid = false;
         if (lane < iq) {
           double rk = rr[lane];
-          if (rk > 0.0) { t1 = u[lane] / rk; lpos = lane; }
+          if (rk > 0.0) { t1 = u[lane] / rk; t1_valid = true; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          double ot = __shfl_xor_sync(FULL, t1, o);
-          int ol = __shfl_xor_sync(FULL, lpos, o);
-          if (ol >= 0 && (lpos < 0 || ot < t1 || (ot == t1 && ol < lpos))) { t1 = ot; lpos = ol; }
-        }
+        const int lpos = warp_argmin(t1, t1_valid, lane);
+        t1 = (lpos >= 0) ? shfl(t1, lpos) : TS_INF;
         /* full step t2 = -s_ip / z.n_ip, with z.n_ip = |d[iq:]|^2 (z = J2 d2, d2 = J2^T n) */
         const double zz = warp_sum(z0 * z0 + z1 * z1);
         const double d2sum = warp_sum((lane >= iq && lane < m) ? dl * dl : 0.0);
@@ -1402,23 +1448,33 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, int lane, int mask, in
             if (!degenerate) {
               const double tauh = (beta - d0) / beta;
               const double scal = 1.0 / (d0 - beta);
-              /* v_c = d_c * scal (c > iq), v_iq = 1;  w_k = sum_c J2[k][c] v_c = (z_k - beta J2[k][iq]) * scal */
-              const double w0 = (lane < n) ? (z0 - beta * J2[lane * SM_LDJ + iq]) * scal : 0.0;
-              const double w1 = (lane + 32 < n) ? (z1 - beta * J2[(lane + 32) * SM_LDJ + iq]) * scal : 0.0;
+              /* v_c = d_c * scal (c > iq), v_iq = 1;  w_k = sum_c J2[k][c] v_c = (z_k - beta J2[k][iq]) * scal;
+               * J2[k][c] -= tau w_k v_c: lanes over rows, 16-byte read-modify-write of the row */
+              vv[lane] = (lane < iq || lane >= m) ? 0.0 : ((lane == iq) ? 1.0 : dl * scal);
+              const double w0 = (lane < n) ? tauh * (z0 - beta * J2[lane * SA_LDJ + iq]) * scal : 0.0;
+              const double w1 = (lane + 32 < n) ? tauh * (z1 - beta * J2[(lane + 32) * SA_LDJ + iq]) * scal : 0.0;
               __syncwarp();
-              if (lane < n) zz_[lane] = tauh * w0;
-              if (lane + 32 < n) zz_[lane + 32] = tauh * w1;
-              __syncwarp();
-              if (lane >= iq && lane < m) {
-                const double vc = (lane == iq) ? 1.0 : dl * scal;
-                double* Jc = J2 + lane;
-                int k = 0;
-                for (; k + 3 < n; k += 4) {
-                  const double j0 = Jc[k * SM_LDJ], j1 = Jc[(k + 1) * SM_LDJ], j2 = Jc[(k + 2) * SM_LDJ], j3 = Jc[(k + 3) * SM_LDJ];
-                  Jc[k * SM_LDJ] = j0 - zz_[k] * vc; Jc[(k + 1) * SM_LDJ] = j1 - zz_[k + 1] * vc;
-                  Jc[(k + 2) * SM_LDJ] = j2 - zz_[k + 2] * vc; Jc[(k + 3) * SM_LDJ] = j3 - zz_[k + 3] * vc;
+              {
+                const int c0 = iq >> 1, c1 = (m + 1) >> 1;
+                const double2* v2 = reinterpret_cast<const double2*>(vv);
+                if (lane < n) {
+                  double2* Jr = reinterpret_cast<double2*>(J2 + lane * SA_LDJ);
+                  for (int c = c0; c < c1; c++) {
+                    double2 jv = Jr[c];
+                    const double2 vc = v2[c];
+                    jv.x -= w0 * vc.x; jv.y -= w0 * vc.y;
+                    Jr[c] = jv;
+                  }
                 }
-                for (; k < n; k++) Jc[k * SM_LDJ] -= zz_[k] * vc;
+                if (lane + 32 < n) {
+                  double2* Jr = reinterpret_cast<double2*>(J2 + (lane + 32) * SA_LDJ);
+                  for (int c = c0; c < c1; c++) {
+                    double2 jv = Jr[c];
+                    const double2 vc = v2[c];
+                    jv.x -= w1 * vc.x; jv.y -= w1 * vc.y;
+                    Jr[c] = jv;
+                  }
+                }
               }
               /* new column of R: [d[0:iq]; beta] */
               if (lane < iq) Rp[iq * (iq + 1) / 2 + lane] = dl;
@@ -1456,7 +1512,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, int lane, int mask, in
           if (lane == ol) actbits &= ~(1u << os);
         }
         qp_delete(S, n, iq, lpos, lane);
-        wrench_of(C, x, mask, wr, lane);
+        wrench_of(C, K, x, mask, wr, lane);
         __syncwarp();
         s_ip = eval_one(C, S, ip, mask);
       } /* l2a */
@@ -1508,7 +1564,10 @@ TSIDB_DEV void prepare_env(const DevConst& C, double* sm, const TickArgs& a, int
   const int err = k3_eliminate<NV>(C, sm, lane, mask, nc, n, neq, c1c2, R_norm);
   /* solver image (layout SA_*; J2 is filled in by kernel G) */
   double* img = a.ws + (size_t)slot * SA_IMAGE;
-  for (int k = lane; k < na * SM_LDM; k += 32) img[SA_oMa + k] = sm[SM_oM + 6 * SM_LDM + k];
+  for (int k = lane; k < na * SA_LDM; k += 32) {
+    const int r = k / SA_LDM, c = k % SA_LDM;
+    img[SA_oMa + k] = (c < nv) ? sm[SM_oM + (6 + r) * SM_LDM + c] : 0.0;
+  }
   for (int k = lane; k < 12 * SA_LDJA; k += 32) {
     const int q = k / SA_LDJA, r = k % SA_LDJA;
     img[SA_oJFa + k] = (r < na) ? sm[SM_oJF + q * TSIDB_NVX + 6 + r] : 0.0;
@@ -1584,7 +1643,7 @@ TSIDB_DEV void j2_columns(const DevConst& C, const double* sg, double* img, int 
           double acc = 0.0;
 #pragma unroll
           for (int k = r; k < 12; k++) acc += C.Lfinv[k][r] * q[NV + 12 * s + k];
-          img[SA_oJ2 + (NV + 12 * s + r) * SM_LDJ + lane] = acc;
+          img[SA_oJ2 + (NV + 12 * s + r) * SA_LDJ + lane] = acc;
         }
       }
     }
@@ -1596,7 +1655,7 @@ TSIDB_DEV void j2_columns(const DevConst& C, const double* sg, double* img, int 
     for (int i = 0; i < k; i++) q[i] -= L[k * SM_LDM + i] * q[k];
   }
 #pragma unroll
-  for (int k = 0; k < NV; k++) img[SA_oJ2 + k * SM_LDJ + lane] = q[k];
+  for (int k = 0; k < NV; k++) img[SA_oJ2 + k * SA_LDJ + lane] = q[k];
 }
 
 template <int NV>
@@ -1618,23 +1677,23 @@ TSIDB_DEV void j2_env(const DevConst& C, double* sg, const TickArgs& a, int slot
 }
 
 /* ================================================================= kernel A: active set + decode of one env */
-TSIDB_DEV void activeset_env(const DevConst& C, double* sm, const TickArgs& a, int env, int slot, int lane) {
+TSIDB_DEV void activeset_env(const DevConst& C, double* sm, const TickArgs& a, int env, int slot, int lane, unsigned& parity) {
   const int nv = C.nv, na = C.na;
-  {
-    /* 20 KB image: 16-byte loads, 8 in flight per lane before the first store */
-    const double2* img2 = reinterpret_cast<const double2*>(a.ws + (size_t)slot * SA_IMAGE);
-    double2* sm2 = reinterpret_cast<double2*>(sm);
-    constexpr int NV2 = SA_IMAGE / 2;
-    int k = lane;
-    for (; k + 7 * 32 < NV2; k += 8 * 32) {
-      double2 t[8];
+  __syncwarp(); /* every lane is done with the previous env's shared memory */
+#ifndef TSIDB_EMU
+  /* the 21 KB solver image arrives as ONE bulk asynchronous copy (TMA); the warp waits on its mbarrier */
+  if (lane == 0) bulk_load(sm, a.ws + (size_t)slot * SA_IMAGE, SA_IMAGE * sizeof(double), sm + SA_oBar);
+  /* per-lane constants while the copy is in flight */
+#else
+  for (int k = lane; k < SA_IMAGE; k += 32) sm[k] = a.ws[(size_t)slot * SA_IMAGE + k];
+#endif
+  LaneConst K;
 #pragma unroll
-      for (int j = 0; j < 8; j++) t[j] = __ldcs(img2 + k + 32 * j);
-#pragma unroll
-      for (int j = 0; j < 8; j++) sm2[k + 32 * j] = t[j];
-    }
-    for (; k < NV2; k += 32) sm2[k] = __ldcs(img2 + k);
-  }
+  for (int j = 0; j < 12; j++) K.Trow[j] = C.T[lane % 6][j];
+#ifndef TSIDB_EMU
+  mbar_wait(sm + SA_oBar, parity);
+  parity ^= 1u;
+#endif
   __syncwarp();
   ASCtx S;
   S.J2 = sm + SA_oJ2; S.Ma = sm + SA_oMa; S.JFa = sm + SA_oJFa; S.nle_a = sm + SA_oNle; S.vj = sm + SA_oVj;
@@ -1643,14 +1702,21 @@ TSIDB_DEV void activeset_env(const DevConst& C, double* sm, const TickArgs& a, i
   const int err = (int)sm[SA_oSc + 2], mask = (int)sm[SA_oSc + 3];
   const int nc = (mask & 1) + ((mask >> 1) & 1);
   const int n = nv + 12 * nc, neq = 6 + 6 * nc;
+  K.lb = K.ub = 0.0;
+  if (lane < na && C.use_jb) {
+    /* [tsid TaskJointBounds] (v_min - v)/dt <= dv <= (v_max - v)/dt, clipped to +-1e10 */
+    const double vj = S.vj[lane];
+    K.ub = fmin((C.v_max[lane] - vj) / C.jb_dt, 1e10);
+    K.lb = fmax((C.v_min[lane] - vj) / C.jb_dt, -1e10);
+  }
   int iters = 0;
   uint64_t words[3] = {0, 0, 0};
   int status = err;
-  if (err == ST_OPTIMAL) status = as_solve(C, S, lane, mask, nc, n, neq, c1c2, R_norm, iters, words);
+  if (err == ST_OPTIMAL) status = as_solve(C, S, K, lane, mask, nc, n, neq, c1c2, R_norm, iters, words);
   const bool ok = (status == ST_OPTIMAL || status == ST_MAX_ITER);
   const double* x = S.x;
   double* wr = S.wr;
-  if (ok) wrench_of(C, x, mask, wr, lane);
+  if (ok) wrench_of(C, K, x, mask, wr, lane);
   __syncwarp();
   /* decode: dv = x[:nv], f = x[nv:], tau = h_a + M_a dv - J_a^T f  (ref:main.py:126-127) */
   if (lane < nv) a.ddq[eidx(a, env, lane, nv)] = ok ? x[lane] : 0.0;
@@ -1663,7 +1729,7 @@ TSIDB_DEV void activeset_env(const DevConst& C, double* sm, const TickArgs& a, i
   if (lane < na) {
     double val = 0.0;
     if (ok) {
-      const double* Mr = S.Ma + lane * SM_LDM;
+      const double* Mr = S.Ma + lane * SA_LDM;
       double s0 = S.nle_a[lane], s1 = 0.0;
       for (int j = 0; j < nv; j += 2) { s0 += Mr[j] * x[j]; s1 += (j + 1 < nv) ? Mr[j + 1] * x[j + 1] : 0.0; }
       double s = s0 + s1;
@@ -1744,13 +1810,16 @@ tsidb_activeset_kernel(const TickArgs a) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* sm = smem + wid * SA_PER_ENV;
   const DevConst& C = g_const[a.slot];
+  if (lane == 0) mbar_init(sm + SA_oBar, 1);
+  __syncwarp();
+  unsigned parity = 0;
   for (;;) {
     int slot = 0;
     if (lane == 0) slot = atomicAdd(a.counter, 1);
     slot = __shfl_sync(FULL, slot, 0);
     if (slot >= a.n_envs) break;
     const int env = a.perm ? a.perm[slot] : slot;
-    activeset_env(C, sm, a, env, slot, lane);
+    activeset_env(C, sm, a, env, slot, lane, parity);
   }
 }
 #endif
