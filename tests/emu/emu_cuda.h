@@ -67,5 +67,6 @@ inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline void sincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 inline double2 __ldcs(const double2* p) { return *p; }
 #endif

@@ -17,8 +17,10 @@ static void lane_entry(int lane) {
     if (g_job.C->nv == 26) prepare_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
     else prepare_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
   } else if (g_job.stage == 1) {
-    if (g_job.C->nv == 26) j2_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane);
-    else j2_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane);
+    G2Pipe P;
+    P.bars = nullptr; P.next = nullptr; P.pv = P.pl = 0;
+    if (g_job.C->nv == 26) j2_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
+    else j2_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
   } else {
     unsigned parity = 0;
     activeset_env(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);

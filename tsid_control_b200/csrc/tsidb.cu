@@ -187,7 +187,7 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
   CK(cudaFuncSetAttribute(tsidb_prepare_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaFuncSetAttribute(tsidb_prepare_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaFuncSetAttribute(tsidb_activeset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_as));
-  const size_t smem_g = (size_t)TSIDB_G_WARPS * SG_IMAGE * sizeof(double);
+  const size_t smem_g = (size_t)TSIDB_G_WARPS * (SG_IMAGE + 2) * sizeof(double);
   CK(cudaFuncSetAttribute(tsidb_j2_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   CK(cudaFuncSetAttribute(tsidb_j2_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   CK(cudaMalloc(&h->counter, 4 * sizeof(int32_t)));
@@ -286,7 +286,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st) {
     const int warps = TSIDB_G_WARPS;
     int blocks = (n + warps - 1) / warps;
     if (blocks > h->sm_count) blocks = h->sm_count;
-    const size_t smem = (size_t)warps * SG_IMAGE * sizeof(double);
+    const size_t smem = (size_t)warps * (SG_IMAGE + 2) * sizeof(double);
     if (h->dc.nv == 26) tsidb_j2_kernel<26><<<blocks, 32 * warps, smem, st>>>(a);
     else tsidb_j2_kernel<24><<<blocks, 32 * warps, smem, st>>>(a);
     CK(cudaGetLastError());

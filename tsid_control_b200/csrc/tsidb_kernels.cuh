@@ -275,25 +275,23 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, double* sm, int lane) {
     acc[16] = P[0]; acc[17] = P[1]; acc[18] = P[2]; acc[19] = Lo[0]; acc[20] = Lo[1]; acc[21] = Lo[2];
     acc[22] = fl[0]; acc[23] = fl[1]; acc[24] = fl[2]; acc[25] = fa[0]; acc[26] = fa[1]; acc[27] = fa[2];
   }
-  /* bottom-up subtree sums through shared memory (scratch in the J2 region) */
+  /* bottom-up subtree sums through shared memory (scratch in the J2 region).  Lanes <-> the 28 components:
+   * a body's index is larger than its parent's (Pinocchio's depth-first order), so ONE sweep from the last
+   * body to the first leaves every subtree sum in place; each lane only ever touches its own component, so
+   * the sweep needs no synchronisation. */
   double* sc = sm + SM_oJ2;
   if (act) {
 #pragma unroll
-    for (int k = 0; k < 28; k++) sc[b * 28 + k] = acc[k];
+    for (int k = 0; k < 28; k++) sc[b * 29 + k] = acc[k];
   }
   __syncwarp();
-  for (int L = C.maxdepth; L >= 1; L--) {
-    for (int rk = 0; rk < C.maxsib[L]; rk++) {
-      if (dep == L && C.sibrank[b] == rk) {
-#pragma unroll
-        for (int k = 0; k < 28; k++) sc[par * 28 + k] += sc[b * 28 + k];
-      }
-      __syncwarp();
-    }
+  if (lane < 28) {
+    for (int c = nb - 1; c >= 1; c--) sc[C.parent[c] * 29 + lane] += sc[c * 29 + lane];
   }
+  __syncwarp();
   if (act) {
 #pragma unroll
-    for (int k = 0; k < 28; k++) acc[k] = sc[b * 28 + k];
+    for (int k = 0; k < 28; k++) acc[k] = sc[b * 29 + k];
   }
   __syncwarp();
   /* totals and the base placement, broadcast from lane 0 */
@@ -598,7 +596,11 @@ TSIDB_DEV void k2_assemble(const DevConst& C, double* sm, const TickArgs& a, int
 #pragma unroll
       for (int r = 0; r < 3; r++) ja[r] = Ag[r * TSIDB_NVX + j];
     }
-    for (int i = 0; i < nv; i++) {
+    /* H is symmetric: lane j computes the entries (i, j) for the nv/2 + 1 rows i = j, j+1, ... (cyclic) and
+     * stores each one on both sides of the diagonal; every unordered pair is covered */
+    for (int t = 0; t <= nv / 2; t++) {
+      int i = j + t;
+      if (i >= nv) i -= nv;
       double sf = 0.0, scm = 0.0, sam = 0.0;
 #pragma unroll
       for (int r = 0; r < 12; r++) sf += JF[r * TSIDB_NVX + i] * jf[r];
@@ -612,6 +614,7 @@ TSIDB_DEV void k2_assemble(const DevConst& C, double* sm, const TickArgs& a, int
       }
       if (i == j) hij += (i >= 6 ? C.w_post : 0.0) + C.hreg;
       H[i * SM_LDM + j] = hij;
+      H[j * SM_LDM + i] = hij;
     }
     double gf = 0.0, gc = 0.0, ga = 0.0;
 #pragma unroll
@@ -849,8 +852,9 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
       const int lo = top ? i : ncm;          /* first dv row of the span */
       __syncwarp();
       if (lane == i) {
+        double2* c2 = reinterpret_cast<double2*>(colp);
 #pragma unroll
-        for (int k = 0; k < N; k++) colp[k] = b[k];
+        for (int k = 0; k < N; k += 2) c2[k >> 1] = make_double2(b[k], b[k + 1]);
       }
       __syncwarp();
       double part = 0.0;
@@ -903,9 +907,11 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
     } else if (lane < neq) {
       rhs = -sm[SM_oNle + lane - ncm];
     }
+    if (lane < neq) Rd[lane] = 1.0 / Rd[lane];
+    __syncwarp();
     double accv = rhs;
     for (int i = 0; i < neq; i++) {
-      const double wi = shfl(accv, i) / Rd[i];
+      const double wi = shfl(accv, i) * Rd[i];
       if (lane == i) accv = wi;
       else if (lane > i && lane < neq) accv -= R1[i * SM_LDB + lane] * wi;
     }
@@ -956,11 +962,13 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
  * lock-step, G register-blocked with no cross-lane traffic, A balancing the data-dependent iteration counts
  * (1..40) dynamically.                                                                                     */
 #define SG_LDV (TSIDB_NVX + 24)           /* reflector stride written by F (JE_VT rows)      */
-#define SG_oL 0                           /* L      26 x 27                             702 */
-#define SG_oILD (SG_oL + 702)             /* 1/L_ii                                      26 */
+#define SG_LDL 28                         /* row stride of L in the factor image (even: 16-byte reads)    */
+#define SG_oL 0                           /* L      26 x 28                             728 */
+#define SG_oILD (SG_oL + 728)             /* 1/L_ii                                      26 */
 #define SG_oTAU (SG_oILD + 26)            /* Householder tau                             18 */
 #define SG_oVT (SG_oTAU + 18)             /* reflectors [18][50]                        900 */
-#define SG_IMAGE (SG_oVT + 900)           /* doubles handed over per env               1646 */
+#define SG_IMAGE (SG_oVT + 900)           /* doubles handed over per env               1672 */
+#define SG_LPART SG_oTAU                  /* [0, SG_LPART): factor part, [SG_LPART, SG_IMAGE): reflector part */
 #define TSIDB_G_WARPS 16
 #define SA_LDJA 20                        /* JFa row stride                                  */
 #define SA_LDJ 34                         /* J2 row stride: even (16-byte row accesses), conflict-free by rows and by columns */
@@ -1577,7 +1585,12 @@ TSIDB_DEV void prepare_env(const DevConst& C, double* sm, const TickArgs& a, int
   if (lane == 0) { img[SA_oSc] = c1c2; img[SA_oSc + 1] = R_norm; img[SA_oSc + 2] = (double)err; img[SA_oSc + 3] = (double)mask; }
   /* factor image (layout SG_*): L, 1/diag, tau are contiguous in the factor region, the reflectors in the scratch */
   double* fimg = a.ws2 + (size_t)slot * SG_IMAGE;
-  for (int k = lane; k < SG_oVT; k += 32) fimg[k] = sm[SM_oU + k];
+  for (int k = lane; k < nv * SG_LDL; k += 32) {
+    const int r = k / SG_LDL, c = k % SG_LDL;
+    fimg[SG_oL + k] = (c <= r) ? sm[SM_oU + UE_L + r * SM_LDM + c] : 0.0;
+  }
+  if (lane < nv) fimg[SG_oILD + lane] = sm[SM_oU + UE_ILD + lane];
+  if (lane < 18) fimg[SG_oTAU + lane] = sm[SM_oU + UE_TAU + lane];
   for (int k = lane; k < 18 * SG_LDV; k += 32) fimg[SG_oVT + k] = sm[SM_oJ2 + JE_VT + k];
   __syncwarp();
 }
@@ -1588,12 +1601,44 @@ TSIDB_DEV void prepare_env(const DevConst& C, double* sm, const TickArgs& a, int
  * after which the force rows are final and leave through the constant Lf^-T; then the contact-motion ones
  * (rows i..nv-1) and the back substitution with L on the dv rows.  Operands shared by the warp (reflector and
  * factor entries) are broadcast reads from shared memory. */
+/* software pipeline of the J2 kernel: the factor image of the NEXT slot is requested (two bulk asynchronous
+ * copies, one mbarrier each) as soon as the part of the buffer it lands in is dead for the current slot — the
+ * reflector part before the back substitution starts, the factor part when the env is done. */
+struct G2Pipe {
+  double* bars;         /* [0]: reflector part, [1]: factor part */
+  const double* next;   /* factor image of the next slot, or null */
+  unsigned pv, pl;      /* phase parities */
+};
+TSIDB_DEV void g2_wait_v(G2Pipe& P) {
+#ifndef TSIDB_EMU
+  mbar_wait(P.bars, P.pv);
+#endif
+  P.pv ^= 1u;
+}
+TSIDB_DEV void g2_wait_l(G2Pipe& P) {
+#ifndef TSIDB_EMU
+  mbar_wait(P.bars + 1, P.pl);
+#endif
+  P.pl ^= 1u;
+}
+/* called by all lanes after a __syncwarp that retires every read of that part */
+TSIDB_DEV void g2_request_v(const G2Pipe& P, double* sg, int lane) {
+#ifndef TSIDB_EMU
+  if (lane == 0 && P.next) bulk_load(sg + SG_LPART, P.next + SG_LPART, (SG_IMAGE - SG_LPART) * sizeof(double), P.bars);
+#endif
+}
+TSIDB_DEV void g2_request_l(const G2Pipe& P, double* sg, int lane) {
+#ifndef TSIDB_EMU
+  if (lane == 0 && P.next) bulk_load(sg, P.next, SG_LPART * sizeof(double), P.bars + 1);
+#endif
+}
+
 template <int NV, int NC>
-TSIDB_DEV void j2_columns(const DevConst& C, const double* sg, double* img, int lane) {
+TSIDB_DEV void j2_columns(const DevConst& C, double* sg, double* img, int lane, G2Pipe& P) {
   constexpr int NS = NV + 24;
   constexpr int N = NV + 12 * NC, NEQ = 6 + 6 * NC, NCM = 6 * NC, M = N - NEQ;
-  if (lane >= M) return;
-  const double* L = sg + SG_oL;
+  const bool work = lane < M;
+  const double2* L2 = reinterpret_cast<const double2*>(sg + SG_oL);
   const double* ild = sg + SG_oILD;
   const double* tauq = sg + SG_oTAU;
   const double* Vt = sg + SG_oVT;
@@ -1605,75 +1650,102 @@ TSIDB_DEV void j2_columns(const DevConst& C, const double* sg, double* img, int 
     const int col = (NC == 0) ? k - 6 : ((k < NV) ? k - NCM : ((k >= NV + 6) ? (NV - NCM) + (k - NV - 6) : -1));
     q[k] = (col >= 0 && col == lane) ? 1.0 : 0.0;
   }
+  g2_wait_v(P);
+  if (work) {
 #pragma unroll
-  for (int i = NEQ - 1; i >= 0; i--) {
-    const bool top = (i < NCM) || NC == 0;
-    const int head = top ? i : NV + (i - NCM);
-    const int lo = top ? i + 1 : NCM;            /* dv rows lo..NV-1 */
-    const int flo = top ? N : head + 1;          /* force rows flo..N-1 */
-    const double* v = Vt + i * NS;
-    /* the head row is still zero here (no reflector applied so far touches it) and v[head] = 1 */
-    double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+    for (int i = NEQ - 1; i >= 0; i--) {
+      const bool top = (i < NCM) || NC == 0;
+      const int head = top ? i : NV + (i - NCM);
+      const int lo = top ? i + 1 : NCM;            /* dv rows lo..NV-1 */
+      const int flo = top ? N : head + 1;          /* force rows flo..N-1 */
+      const double2* v2 = reinterpret_cast<const double2*>(Vt + i * NS);
+      /* the head row is still zero here (no reflector applied so far touches it) and v[head] = 1;
+       * reflector entries come in pairs (16-byte broadcast reads) */
+      double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
 #pragma unroll
-    for (int k = lo; k < NV; k++) {
-      if ((k & 3) == 0) w0 += v[k] * q[k];
-      else if ((k & 3) == 1) w1 += v[k] * q[k];
-      else if ((k & 3) == 2) w2 += v[k] * q[k];
-      else w3 += v[k] * q[k];
-    }
+      for (int kk = (lo & ~1); kk < NV; kk += 2) {
+        const double2 p = v2[kk >> 1];
+        if (kk >= lo) { if (kk & 2) w2 += p.x * q[kk]; else w0 += p.x * q[kk]; }
+        if (kk & 2) w3 += p.y * q[kk + 1]; else w1 += p.y * q[kk + 1];
+      }
 #pragma unroll
-    for (int k = flo; k < N; k++) {
-      if ((k & 3) == 0) w0 += v[k] * q[k];
-      else if ((k & 3) == 1) w1 += v[k] * q[k];
-      else if ((k & 3) == 2) w2 += v[k] * q[k];
-      else w3 += v[k] * q[k];
-    }
-    const double w = tauq[i] * ((w0 + w1) + (w2 + w3));
-    q[head] = -w;
+      for (int kk = (flo & ~1); kk < N; kk += 2) {
+        const double2 p = v2[kk >> 1];
+        if (kk >= flo) { if (kk & 2) w2 += p.x * q[kk]; else w0 += p.x * q[kk]; }
+        if (kk & 2) w3 += p.y * q[kk + 1]; else w1 += p.y * q[kk + 1];
+      }
+      const double w = tauq[i] * ((w0 + w1) + (w2 + w3));
+      q[head] = -w;
 #pragma unroll
-    for (int k = lo; k < NV; k++) q[k] -= w * v[k];
+      for (int kk = (lo & ~1); kk < NV; kk += 2) {
+        const double2 p = v2[kk >> 1];
+        if (kk >= lo) q[kk] -= w * p.x;
+        q[kk + 1] -= w * p.y;
+      }
 #pragma unroll
-    for (int k = flo; k < N; k++) q[k] -= w * v[k];
-    if (i == NCM) {
-      /* force rows are final: J2_f = Lf^-T q_f, stored right away */
+      for (int kk = (flo & ~1); kk < N; kk += 2) {
+        const double2 p = v2[kk >> 1];
+        if (kk >= flo) q[kk] -= w * p.x;
+        q[kk + 1] -= w * p.y;
+      }
+      if (i == NCM) {
+        /* force rows are final: J2_f = Lf^-T q_f, stored right away */
 #pragma unroll
-      for (int s = 0; s < NC; s++) {
+        for (int s = 0; s < NC; s++) {
 #pragma unroll
-        for (int r = 0; r < 12; r++) {
-          double acc = 0.0;
+          for (int r = 0; r < 12; r++) {
+            double acc = 0.0;
 #pragma unroll
-          for (int k = r; k < 12; k++) acc += C.Lfinv[k][r] * q[NV + 12 * s + k];
-          img[SA_oJ2 + (NV + 12 * s + r) * SA_LDJ + lane] = acc;
+            for (int k = r; k < 12; k++) acc += C.Lfinv[k][r] * q[NV + 12 * s + k];
+            img[SA_oJ2 + (NV + 12 * s + r) * SA_LDJ + lane] = acc;
+          }
         }
       }
     }
   }
+  __syncwarp();
+  g2_request_v(P, sg, lane);
+  g2_wait_l(P);
+  if (work) {
 #pragma unroll
-  for (int k = NV - 1; k >= 0; k--) {
-    q[k] *= ild[k];
+    for (int k = NV - 1; k >= 0; k--) {
+      q[k] *= ild[k];
 #pragma unroll
-    for (int i = 0; i < k; i++) q[i] -= L[k * SM_LDM + i] * q[k];
+      for (int ii = 0; ii < k; ii += 2) {
+        const double2 p = L2[(k * SG_LDL + ii) >> 1];
+        q[ii] -= p.x * q[k];
+        if (ii + 1 < k) q[ii + 1] -= p.y * q[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; k++) img[SA_oJ2 + k * SA_LDJ + lane] = q[k];
   }
-#pragma unroll
-  for (int k = 0; k < NV; k++) img[SA_oJ2 + k * SA_LDJ + lane] = q[k];
+  __syncwarp();
+  g2_request_l(P, sg, lane);
 }
 
 template <int NV>
-TSIDB_DEV void j2_env(const DevConst& C, double* sg, const TickArgs& a, int slot, int lane) {
+TSIDB_DEV void j2_env(const DevConst& C, double* sg, const TickArgs& a, int slot, int lane, G2Pipe& P) {
   double* img = a.ws + (size_t)slot * SA_IMAGE;
   const int err = (int)img[SA_oSc + 2], mask = (int)img[SA_oSc + 3];
-  if (err != ST_OPTIMAL) return; /* the active-set kernel reports the status and never reads J2 */
-  {
-    const double2* src = reinterpret_cast<const double2*>(a.ws2 + (size_t)slot * SG_IMAGE);
-    double2* dst = reinterpret_cast<double2*>(sg);
-    for (int k = lane; k < SG_IMAGE / 2; k += 32) dst[k] = __ldcs(src + k);
+#ifdef TSIDB_EMU
+  for (int k = lane; k < SG_IMAGE; k += 32) sg[k] = a.ws2[(size_t)slot * SG_IMAGE + k];
+  __syncwarp();
+#endif
+  if (err != ST_OPTIMAL) {
+    /* the active-set kernel reports the status and never reads J2; keep the pipeline moving */
+    g2_wait_v(P);
+    __syncwarp();
+    g2_request_v(P, sg, lane);
+    g2_wait_l(P);
+    __syncwarp();
+    g2_request_l(P, sg, lane);
+    return;
   }
-  __syncwarp();
   const int nc = (mask & 1) + ((mask >> 1) & 1);
-  if (nc == 2) j2_columns<NV, 2>(C, sg, img, lane);
-  else if (nc == 1) j2_columns<NV, 1>(C, sg, img, lane);
-  else j2_columns<NV, 0>(C, sg, img, lane);
-  __syncwarp();
+  if (nc == 2) j2_columns<NV, 2>(C, sg, img, lane, P);
+  else if (nc == 1) j2_columns<NV, 1>(C, sg, img, lane, P);
+  else j2_columns<NV, 0>(C, sg, img, lane, P);
 }
 
 /* ================================================================= kernel A: active set + decode of one env */
@@ -1798,10 +1870,23 @@ tsidb_j2_kernel(const TickArgs a) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* sg = smem + wid * SG_IMAGE;
   const DevConst& C = g_const[a.slot];
+  G2Pipe P;
+  P.bars = smem + TSIDB_G_WARPS * SG_IMAGE + 2 * wid;
+  P.pv = P.pl = 0;
   /* every column costs the same within a contact class and the slots are class-sorted: a static stride
    * spreads each class evenly over the SMs */
-  for (int slot = blockIdx.x * TSIDB_G_WARPS + wid; slot < a.n_envs; slot += gridDim.x * TSIDB_G_WARPS)
-    j2_env<NV>(C, sg, a, slot, lane);
+  const int stride = gridDim.x * TSIDB_G_WARPS;
+  int slot = blockIdx.x * TSIDB_G_WARPS + wid;
+  if (slot >= a.n_envs) return;
+  if (lane == 0) { mbar_init(P.bars, 1); mbar_init(P.bars + 1, 1); }
+  __syncwarp();
+  P.next = a.ws2 + (size_t)slot * SG_IMAGE;
+  g2_request_v(P, sg, lane);
+  g2_request_l(P, sg, lane);
+  for (; slot < a.n_envs; slot += stride) {
+    P.next = (slot + stride < a.n_envs) ? a.ws2 + (size_t)(slot + stride) * SG_IMAGE : nullptr;
+    j2_env<NV>(C, sg, a, slot, lane, P);
+  }
 }
 
 __global__ void __launch_bounds__(32 * TSIDB_AS_WARPS, 1)
