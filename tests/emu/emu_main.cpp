@@ -14,9 +14,13 @@ static Job g_job;
 
 static void lane_entry(int lane) {
   if (g_job.stage == 0) {
-    if (g_job.C->nv == 26) prepare_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
-    else prepare_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
+    if (g_job.C->nv == 26) dynamics_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
+    else dynamics_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
   } else if (g_job.stage == 1) {
+    unsigned parity = 0;
+    if (g_job.C->nv == 26) eliminate_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, parity);
+    else eliminate_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, parity);
+  } else if (g_job.stage == 2) {
     G2Pipe P;
     P.bars = nullptr; P.next = nullptr; P.pv = P.pl = 0;
     if (g_job.C->nv == 26) j2_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
@@ -80,16 +84,18 @@ extern "C" int emu_tick(const TickArgs* a_in, double* sm_out) {
   emu::Warp& W = emu::W;
   if (!W.stacks) W.stacks = (char*)malloc(32 * STK);
   TickArgs a = *a_in;
-  const int smn = SM_PER_ENV > SA_PER_ENV ? SM_PER_ENV : SA_PER_ENV;
+  const int smn = SA_PER_ENV > SE_PER_ENV ? SA_PER_ENV : SE_PER_ENV;
   double* sm = (double*)calloc(smn, sizeof(double));
   double* ws = (double*)calloc((size_t)a.n_envs * SA_IMAGE, sizeof(double));
   double* ws2 = (double*)calloc((size_t)a.n_envs * SG_IMAGE, sizeof(double));
   a.ws = ws;
   a.ws2 = ws2;
+  double* ws3 = (double*)calloc((size_t)a.n_envs * SE_IMAGE, sizeof(double));
+  a.ws3 = ws3;
   a.perm = nullptr;
   int rc = 0;
   for (int env = 0; env < a.n_envs && rc == 0; env++) {
-    for (int stage = 0; stage < (a.kin_only ? 1 : 3) && rc == 0; stage++) {
+    for (int stage = 0; stage < (a.kin_only ? 1 : 4) && rc == 0; stage++) {
       for (int k = 0; k < smn; k++) sm[k] = NAN; /* poison: catches reads of unwritten smem */
       g_job = Job{&g_const[0], sm, &a, env, stage};
       rc = run_warp(env);
@@ -99,6 +105,7 @@ extern "C" int emu_tick(const TickArgs* a_in, double* sm_out) {
   free(sm);
   free(ws);
   free(ws2);
+  free(ws3);
   return rc;
 }
-extern "C" int emu_sm_per_env() { return SM_PER_ENV > SA_PER_ENV ? SM_PER_ENV : SA_PER_ENV; }
+extern "C" int emu_sm_per_env() { return SA_PER_ENV > SE_PER_ENV ? SA_PER_ENV : SE_PER_ENV; }

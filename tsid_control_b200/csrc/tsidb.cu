@@ -31,6 +31,7 @@ struct tsidb_handle {
   int32_t* counter;      /* device: [0] work counter of the active-set kernel, [1..3] class counts */
   double* ws;            /* device: solver images, SA_IMAGE doubles per slot */
   double* ws2;           /* device: factor images, SG_IMAGE doubles per slot */
+  double* ws3;           /* device: assembly images, SE_IMAGE doubles per slot */
   int32_t* perm;         /* device: slot -> env */
   int32_t* cls_pos;      /* device: per-env (class, position) */
   int64_t launches;
@@ -184,8 +185,11 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
     g_err = "tsidb_create: device offers less opt-in shared memory per block than the active-set kernel needs";
     return -2;
   }
-  CK(cudaFuncSetAttribute(tsidb_prepare_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(tsidb_prepare_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(tsidb_dynamics_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(tsidb_dynamics_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem_e = (size_t)TSIDB_E_WARPS * SE_PER_ENV * sizeof(double);
+  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
   CK(cudaFuncSetAttribute(tsidb_activeset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_as));
   const size_t smem_g = (size_t)TSIDB_G_WARPS * (SG_IMAGE + 2) * sizeof(double);
   CK(cudaFuncSetAttribute(tsidb_j2_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
@@ -193,6 +197,7 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
   CK(cudaMalloc(&h->counter, 4 * sizeof(int32_t)));
   CK(cudaMalloc(&h->ws, (size_t)max_envs * SA_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->ws2, (size_t)max_envs * SG_IMAGE * sizeof(double)));
+  CK(cudaMalloc(&h->ws3, (size_t)max_envs * SE_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->perm, (size_t)max_envs * sizeof(int32_t)));
   CK(cudaMalloc(&h->cls_pos, (size_t)max_envs * sizeof(int32_t)));
   if (upload_const(h) != 0) return -2;
@@ -217,7 +222,7 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
 extern "C" void tsidb_destroy(tsidb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaFree(h->counter); cudaFree(h->ws); cudaFree(h->ws2); cudaFree(h->perm); cudaFree(h->cls_pos);
+  cudaFree(h->counter); cudaFree(h->ws); cudaFree(h->ws2); cudaFree(h->ws3); cudaFree(h->perm); cudaFree(h->cls_pos);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFree(h->d_in); cudaFree(h->d_out);
   cudaFreeHost(h->h_mask); cudaFree(h->d_mask);
   cudaFreeHost(h->h_int); cudaFree(h->d_int);
@@ -259,6 +264,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st) {
   a.slot = h->slot;
   a.ws = h->ws;
   a.ws2 = h->ws2;
+  a.ws3 = h->ws3;
   a.perm = nullptr;
   const int n = a.n_envs;
   if (!a.kin_only) {
@@ -277,8 +283,18 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st) {
     int blocks = (n + warps - 1) / warps;
     if (blocks > h->sm_count) blocks = h->sm_count; /* persistent: one CTA per SM */
     const size_t smem = (size_t)warps * SM_PER_ENV * sizeof(double);
-    if (h->dc.nv == 26) tsidb_prepare_kernel<26><<<blocks, 32 * warps, smem, st>>>(a);
-    else tsidb_prepare_kernel<24><<<blocks, 32 * warps, smem, st>>>(a);
+    if (h->dc.nv == 26) tsidb_dynamics_kernel<26><<<blocks, 32 * warps, smem, st>>>(a);
+    else tsidb_dynamics_kernel<24><<<blocks, 32 * warps, smem, st>>>(a);
+    CK(cudaGetLastError());
+    h->launches += 1;
+  }
+  if (!a.kin_only) {
+    const int warps = TSIDB_E_WARPS;
+    int blocks = (n + warps - 1) / warps;
+    if (blocks > h->sm_count) blocks = h->sm_count;
+    const size_t smem = (size_t)warps * SE_PER_ENV * sizeof(double);
+    if (h->dc.nv == 26) tsidb_eliminate_kernel<26><<<blocks, 32 * warps, smem, st>>>(a);
+    else tsidb_eliminate_kernel<24><<<blocks, 32 * warps, smem, st>>>(a);
     CK(cudaGetLastError());
     h->launches += 1;
   }

@@ -8,7 +8,8 @@
 #define TSIDB_NVX 26   /* largest nv this build keeps in shared memory (robot/v1)          */
 #define TSIDB_NX 50    /* nv + 24                                                          */
 #define TSIDB_MRED 32  /* n - nEq = na + 6*nc <= 32: one lane per reduced coordinate       */
-#define TSIDB_WARPS_PER_BLOCK 8
+#define TSIDB_WARPS_PER_BLOCK 12  /* dynamics kernel */
+#define TSIDB_E_WARPS 8            /* elimination kernel */
 #define TSIDB_MAX_SLOTS 6
 
 struct DevConst {
@@ -44,10 +45,9 @@ struct DevConst {
   double ref_com[9], ref_foot[2][24], ref_contact[2][12], ref_posture[23];
 };
 
-/* shared-memory layout of one env (doubles) */
+/* shared-memory layout of one env in the dynamics kernel (doubles) */
 #define SM_LDM 27
 #define SM_LDB 19
-#define SM_LDJ 33
 #define SM_oM 0                         /* M        26 x 27                       702 */
 #define SM_oJF (SM_oM + 702)            /* JF       2 x 6 x 26                    312 */
 #define SM_oJcom (SM_oJF + 312)         /* Jcom     3 x 26                         78 */
@@ -56,10 +56,9 @@ struct DevConst {
 #define SM_oBv (SM_oNle + 26)           /* task vectors                            64 */
 #define SM_oFr (SM_oBv + 64)            /* frames and CoM                          64 */
 #define SM_oQV (SM_oFr + 64)            /* q (32) and v (32)                       64 */
-#define SM_oX (SM_oQV + 64)             /* x        50                             50 */
-#define SM_oJ2 (SM_oX + 50)             /* elimination scratch (JE_*)            1406 */
-#define SM_oU (SM_oJ2 + 1406)           /* factor region (UE_*)                   764 */
-#define SM_PER_ENV (SM_oU + 764)        /*                                       3608 */
+#define SM_oH (SM_oQV + 64)             /* dv block of the Hessian 26 x 27; subtree-sum scratch of K1   702 */
+#define SM_oGv (SM_oH + 702)            /* gradient                                50 */
+#define SM_PER_ENV (SM_oGv + 50)        /*                                       2140 */
 /* task vectors inside oBv */
 #define BV_MOT 0   /* 2 x 6 contact motion rhs, by foot */
 #define BV_FOOT 12 /* 2 x 6 foot task rhs               */
@@ -72,17 +71,26 @@ struct DevConst {
 #define FR_AF 36   /* 2 x 6 */
 #define FR_COM 48  /* com 3, vcom 3, acom 3 */
 #define FR_L 57    /* angular momentum about the CoM 3, its drift 3 */
-/* factor region of the prepare kernel (equality elimination) */
-#define UE_L 0                    /* H -> L  26 x 27              702 */
-#define UE_ILD (UE_L + 702)       /* 1/L_ii                        26 */
-#define UE_TAU (UE_ILD + 26)      /* Householder tau               18 */
-#define UE_RD (UE_TAU + 18)       /* diagonal of R1 (beta)         18 */
-/* elimination scratch of the prepare kernel */
-#define JE_VT 0                   /* dense reflectors [18][N]     900 */
-#define JE_R1 (JE_VT + 900)       /* R1 [18][SM_LDB]              342 */
-#define JE_G (JE_R1 + 342)        /* gradient / Q^T w_unc / w_hat  50 */
-#define JE_COL (JE_G + 50)        /* published column              50 */
-#define JE_W0 (JE_COL + 50)       /* w0                            64 */
+/* shared-memory layout of one env in the elimination kernel.  [0, SE_IMAGE) is the assembly image written by
+ * the dynamics kernel (one bulk copy); the Hessian block is factored in place. */
+#define SE_oH 0                     /* H -> L  26 x 27                         702 */
+#define SE_oG (SE_oH + 702)         /* gradient / Q^T w_unc / w_hat             50 */
+#define SE_oMu (SE_oG + 50)         /* base rows of M, 6 x 27                  162 */
+#define SE_oJF (SE_oMu + 162)       /* JF 2 x 6 x 26                           312 */
+#define SE_oNle (SE_oJF + 312)      /* base nle                                  8 */
+#define SE_oBm (SE_oNle + 8)        /* contact-motion rhs 2 x 6                 12 */
+#define SE_oSc (SE_oBm + 12)        /* contact mask, pad                         2 */
+#define SE_IMAGE (SE_oSc + 2)       /* doubles handed over per env            1248 */
+#define SE_oILD (SE_IMAGE)          /* 1/L_ii                                   26 */
+#define SE_oTAU (SE_oILD + 26)      /* Householder tau                          18 */
+#define SE_oRD (SE_oTAU + 18)       /* diagonal of R1 (beta), then 1/beta       18 */
+#define SE_oVT (SE_oRD + 18)        /* dense reflectors [18][50]               900 */
+#define SE_oR1 (SE_oVT + 900)       /* R1 [18][SM_LDB]                         342 */
+#define SE_oCOL (SE_oR1 + 342)      /* published column                         50 */
+#define SE_oW0 (SE_oCOL + 50)       /* w0                                       64 */
+#define SE_oX (SE_oW0 + 64)         /* x0                                       50 */
+#define SE_oBar (SE_oX + 50)        /* mbarrier of the image load                2 */
+#define SE_PER_ENV (SE_oBar + 2)    /*                                        2718 */
 /* work arrays of the active-set kernel */
 #define UF_R 0                    /* R packed by columns: col j at j(j+1)/2       528 */
 #define UF_IRD (UF_R + 528)       /* 1/R_jj                        32 */
@@ -116,7 +124,8 @@ struct TickArgs {
   double* o_wrench;
   int32_t* counter;   /* dynamic work counter of the active-set kernel */
   double* ws;         /* hand-off images of the active-set kernel, SA_IMAGE doubles per slot */
-  double* ws2;        /* hand-off images prepare -> J2 kernel, SG_IMAGE doubles per slot */
+  double* ws2;        /* factor images elimination -> J2 kernel, SG_IMAGE doubles per slot */
+  double* ws3;        /* assembly images dynamics -> elimination kernel, SE_IMAGE doubles per slot */
   const int32_t* perm; /* slot -> env (class sort), null = identity */
   int32_t kin_only;   /* stop after the kinematics (tsidb_kinematics) */
   int32_t slot;       /* constant-memory slot of the handle */

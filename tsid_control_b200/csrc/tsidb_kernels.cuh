@@ -279,7 +279,7 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, double* sm, int lane) {
    * a body's index is larger than its parent's (Pinocchio's depth-first order), so ONE sweep from the last
    * body to the first leaves every subtree sum in place; each lane only ever touches its own component, so
    * the sweep needs no synchronisation. */
-  double* sc = sm + SM_oJ2;
+  double* sc = sm + SM_oH;
   if (act) {
 #pragma unroll
     for (int k = 0; k < 28; k++) sc[b * 29 + k] = acc[k];
@@ -529,7 +529,7 @@ TSIDB_DEV void se3_rhs(const double* fr, int f, const double* kp, const double* 
   }
 }
 
-/* Task right-hand sides -> sm[oBv]; Hessian dv block -> UE_L (to be factored in place);
+/* Task right-hand sides -> sm[oBv]; Hessian dv block -> SM_oH (factored by the elimination kernel);
  * gradient -> column nEq of B (it rides through the QR as an extra column). */
 TSIDB_DEV void k2_assemble(const DevConst& C, double* sm, const TickArgs& a, int env, int lane, int mask, int neq, int n) {
   const int nv = C.nv, na = C.na;
@@ -583,8 +583,8 @@ TSIDB_DEV void k2_assemble(const DevConst& C, double* sm, const TickArgs& a, int
   const double* JF = sm + SM_oJF;
   const double* Jcom = sm + SM_oJcom;
   const double* Ag = sm + SM_oAg;
-  double* H = sm + SM_oU + UE_L;
-  double* gv = sm + SM_oJ2 + JE_G;
+  double* H = sm + SM_oH;
+  double* gv = sm + SM_oGv;
   const int j = lane;
   if (j < nv) {
     double jf[12], jc[3], ja[3] = {0, 0, 0};
@@ -724,9 +724,10 @@ TSIDB_DEV void store_R1(double* R1, const double (&b)[N], int lane) {
   for (int k = 0; k < NEQ; k++) R1[k * SM_LDB + lane] = b[head_row<NV, NCM>(k)];
 }
 
-/* The equality elimination.  In: H (dv block) in U+UE_L, gradient in JE_G, M/JF/bv from K1/K2.
- * Out: x = x0 (the equality-constrained minimiser), the Cholesky factor L (U+UE_L, UE_ILD) and the Householder
- * reflectors of B = L^-1 CE^T (JE_VT, UE_TAU) from which the J2 kernel builds the null-space basis, the c1*c2
+/* The equality elimination.  In: the assembly image (SE_*: H dv block, gradient, base rows of M, JF, base nle,
+ * contact-motion rhs).  Out: x = x0 (the equality-constrained minimiser), the Cholesky factor L (in place of H,
+ * SE_oILD) and the Householder reflectors of B = L^-1 CE^T (SE_oVT, SE_oTAU) from which the J2 kernel builds
+ * the null-space basis, the c1*c2
  * product and R_norm; returns 0 or an HQP error status.
  *
  * Column order of B: the 6*nc contact-motion rows first, then the 6 base-dynamics rows.  Any order yields the
@@ -737,21 +738,19 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
                            double& c1c2, double& R_norm_out) {
   constexpr int N = NV + 24;
   const int ncm = 6 * nc;
-  double* U = sm + SM_oU;
-  double* L = U + UE_L;
-  double* ild = U + UE_ILD;
-  double* tauq = U + UE_TAU;
-  double* Rd = U + UE_RD;
-  double* JE = sm + SM_oJ2;
-  double* Vt = JE + JE_VT;   /* [neq][N] dense reflectors */
-  double* R1 = JE + JE_R1;   /* [18][SM_LDB] */
-  double* gv = JE + JE_G;    /* gradient, later Q^T w_unc / w_hat */
-  double* colp = JE + JE_COL;
-  double* w0v = JE + JE_W0;
-  double* x = sm + SM_oX;
-  const double* Mm = sm + SM_oM;
-  const double* JF = sm + SM_oJF;
-  const double* bv = sm + SM_oBv;
+  double* L = sm + SE_oH;
+  double* ild = sm + SE_oILD;
+  double* tauq = sm + SE_oTAU;
+  double* Rd = sm + SE_oRD;
+  double* Vt = sm + SE_oVT;   /* [neq][N] dense reflectors */
+  double* R1 = sm + SE_oR1;   /* [18][SM_LDB] */
+  double* gv = sm + SE_oG;    /* gradient, later Q^T w_unc / w_hat */
+  double* colp = sm + SE_oCOL;
+  double* w0v = sm + SE_oW0;
+  double* x = sm + SE_oX;
+  const double* Mm = sm + SE_oMu;
+  const double* JF = sm + SE_oJF;
+  const double* bmot = sm + SE_oBm;
   const int f0 = (mask & 1) ? 0 : 1; /* foot of force block 0 */
 
   int err = ST_OPTIMAL; /* an error status is carried to the end: every warp must reach every PHASE_SYNC */
@@ -903,9 +902,9 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
     if (lane < ncm) {
       const int s = lane / 6, r = lane % 6;
       const int f = (s == 0) ? f0 : 1;
-      rhs = bv[BV_MOT + 6 * f + r];
+      rhs = bmot[6 * f + r];
     } else if (lane < neq) {
-      rhs = -sm[SM_oNle + lane - ncm];
+      rhs = -sm[SE_oNle + lane - ncm];
     }
     if (lane < neq) Rd[lane] = 1.0 / Rd[lane];
     __syncwarp();
@@ -961,7 +960,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
  * buys is that every stage runs at the occupancy and the thread mapping that suits it: F in CTA-wide phase
  * lock-step, G register-blocked with no cross-lane traffic, A balancing the data-dependent iteration counts
  * (1..40) dynamically.                                                                                     */
-#define SG_LDV (TSIDB_NVX + 24)           /* reflector stride written by F (JE_VT rows)      */
+#define SG_LDV (TSIDB_NVX + 24)           /* reflector stride written by the elimination kernel      */
 #define SG_LDL 28                         /* row stride of L in the factor image (even: 16-byte reads)    */
 #define SG_oL 0                           /* L      26 x 28                             728 */
 #define SG_oILD (SG_oL + 728)             /* 1/L_ii                                      26 */
@@ -1542,9 +1541,9 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
   return status;
 }
 
-/* ================================================================= kernel F: one env up to the hand-off */
+/* ================================================================= kernel D: dynamics + assembly of one env */
 template <int NV>
-TSIDB_DEV void prepare_env(const DevConst& C, double* sm, const TickArgs& a, int env, int slot, int lane) {
+TSIDB_DEV void dynamics_env(const DevConst& C, double* sm, const TickArgs& a, int env, int slot, int lane) {
   const int nv = C.nv, na = C.na, nq = C.nq;
   PHASE_SYNC();
   /* stage q, v */
@@ -1568,9 +1567,7 @@ TSIDB_DEV void prepare_env(const DevConst& C, double* sm, const TickArgs& a, int
   const int n = nv + 12 * nc, neq = 6 + 6 * nc;
   PHASE_SYNC();
   k2_assemble(C, sm, a, env, lane, mask, neq, n);
-  double c1c2 = 0.0, R_norm = 1.0;
-  const int err = k3_eliminate<NV>(C, sm, lane, mask, nc, n, neq, c1c2, R_norm);
-  /* solver image (layout SA_*; J2 is filled in by kernel G) */
+  /* solver image (layout SA_*): the parts that do not depend on the elimination */
   double* img = a.ws + (size_t)slot * SA_IMAGE;
   for (int k = lane; k < na * SA_LDM; k += 32) {
     const int r = k / SA_LDM, c = k % SA_LDM;
@@ -1581,17 +1578,49 @@ TSIDB_DEV void prepare_env(const DevConst& C, double* sm, const TickArgs& a, int
     img[SA_oJFa + k] = (r < na) ? sm[SM_oJF + q * TSIDB_NVX + 6 + r] : 0.0;
   }
   if (lane < na) { img[SA_oNle + lane] = sm[SM_oNle + 6 + lane]; img[SA_oVj + lane] = sm[SM_oQV + 32 + 6 + lane]; }
-  for (int k = lane; k < TSIDB_NX; k += 32) img[SA_oX + k] = (k < n) ? sm[SM_oX + k] : 0.0;
-  if (lane == 0) { img[SA_oSc] = c1c2; img[SA_oSc + 1] = R_norm; img[SA_oSc + 2] = (double)err; img[SA_oSc + 3] = (double)mask; }
-  /* factor image (layout SG_*): L, 1/diag, tau are contiguous in the factor region, the reflectors in the scratch */
+  if (lane == 0) img[SA_oSc + 3] = (double)mask;
+  /* assembly image (layout SE_*) for the elimination kernel */
+  double* eimg = a.ws3 + (size_t)slot * SE_IMAGE;
+  for (int k = lane; k < 702; k += 32) eimg[SE_oH + k] = sm[SM_oH + k];
+  for (int k = lane; k < TSIDB_NX; k += 32) eimg[SE_oG + k] = sm[SM_oGv + k];
+  for (int k = lane; k < 162; k += 32) eimg[SE_oMu + k] = sm[SM_oM + k];
+  for (int k = lane; k < 312; k += 32) eimg[SE_oJF + k] = sm[SM_oJF + k];
+  if (lane < 8) eimg[SE_oNle + lane] = (lane < 6) ? sm[SM_oNle + lane] : 0.0;
+  if (lane < 12) eimg[SE_oBm + lane] = sm[SM_oBv + BV_MOT + lane];
+  if (lane < 2) eimg[SE_oSc + lane] = (lane == 0) ? (double)mask : 0.0;
+  __syncwarp();
+}
+
+/* ================================================================= kernel E: equality elimination of one env */
+template <int NV>
+TSIDB_DEV void eliminate_env(const DevConst& C, double* sm, const TickArgs& a, int slot, int lane, unsigned& parity) {
+  const int nv = C.nv;
+  __syncwarp(); /* every lane is done with the previous env's shared memory */
+#ifndef TSIDB_EMU
+  if (lane == 0) bulk_load(sm, a.ws3 + (size_t)slot * SE_IMAGE, SE_IMAGE * sizeof(double), sm + SE_oBar);
+  mbar_wait(sm + SE_oBar, parity);
+  parity ^= 1u;
+#else
+  for (int k = lane; k < SE_IMAGE; k += 32) sm[k] = a.ws3[(size_t)slot * SE_IMAGE + k];
+#endif
+  __syncwarp();
+  const int mask = (int)sm[SE_oSc];
+  const int nc = (mask & 1) + ((mask >> 1) & 1);
+  const int n = nv + 12 * nc, neq = 6 + 6 * nc;
+  double c1c2 = 0.0, R_norm = 1.0;
+  const int err = k3_eliminate<NV>(C, sm, lane, mask, nc, n, neq, c1c2, R_norm);
+  double* img = a.ws + (size_t)slot * SA_IMAGE;
+  for (int k = lane; k < TSIDB_NX; k += 32) img[SA_oX + k] = (k < n) ? sm[SE_oX + k] : 0.0;
+  if (lane == 0) { img[SA_oSc] = c1c2; img[SA_oSc + 1] = R_norm; img[SA_oSc + 2] = (double)err; }
+  /* factor image (layout SG_*) for the J2 kernel */
   double* fimg = a.ws2 + (size_t)slot * SG_IMAGE;
   for (int k = lane; k < nv * SG_LDL; k += 32) {
     const int r = k / SG_LDL, c = k % SG_LDL;
-    fimg[SG_oL + k] = (c <= r) ? sm[SM_oU + UE_L + r * SM_LDM + c] : 0.0;
+    fimg[SG_oL + k] = (c <= r) ? sm[SE_oH + r * SM_LDM + c] : 0.0;
   }
-  if (lane < nv) fimg[SG_oILD + lane] = sm[SM_oU + UE_ILD + lane];
-  if (lane < 18) fimg[SG_oTAU + lane] = sm[SM_oU + UE_TAU + lane];
-  for (int k = lane; k < 18 * SG_LDV; k += 32) fimg[SG_oVT + k] = sm[SM_oJ2 + JE_VT + k];
+  if (lane < nv) fimg[SG_oILD + lane] = sm[SE_oILD + lane];
+  if (lane < 18) fimg[SG_oTAU + lane] = sm[SE_oTAU + lane];
+  for (int k = lane; k < 18 * SG_LDV; k += 32) fimg[SG_oVT + k] = sm[SE_oVT + k];
   __syncwarp();
 }
 
@@ -1845,21 +1874,40 @@ __global__ void tsidb_permute_kernel(int n_envs, const int32_t* cls_pos, const i
 
 template <int NV>
 __global__ void __launch_bounds__(32 * TSIDB_WARPS_PER_BLOCK, 1)
-tsidb_prepare_kernel(const TickArgs a) {
+tsidb_dynamics_kernel(const TickArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* sm = smem + wid * SM_PER_ENV;
   const DevConst& C = g_const[a.slot];
-  /* rounds: in every round the CTA's warps take TSIDB_WARPS_PER_BLOCK consecutive slots and move through the
-   * phases together (PHASE_SYNC).  A warp without a slot of its own in the last round repeats the last slot
-   * (it must reach the barriers); it stores the same values again. */
+  /* rounds: in every round the CTA's warps take consecutive slots and move through the phases together
+   * (PHASE_SYNC).  A warp without a slot of its own in the last round repeats the last slot (it must reach
+   * the barriers); it stores the same values again. */
   const int per_round = gridDim.x * TSIDB_WARPS_PER_BLOCK;
   const int rounds = (a.n_envs + per_round - 1) / per_round;
   for (int r = 0; r < rounds; r++) {
     int slot = (r * gridDim.x + blockIdx.x) * TSIDB_WARPS_PER_BLOCK + wid;
     if (slot >= a.n_envs) slot = a.n_envs - 1;
     const int env = a.perm ? a.perm[slot] : slot;
-    prepare_env<NV>(C, sm, a, env, slot, lane);
+    dynamics_env<NV>(C, sm, a, env, slot, lane);
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(32 * TSIDB_E_WARPS, 1)
+tsidb_eliminate_kernel(const TickArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* sm = smem + wid * SE_PER_ENV;
+  const DevConst& C = g_const[a.slot];
+  if (lane == 0) mbar_init(sm + SE_oBar, 1);
+  __syncwarp();
+  unsigned parity = 0;
+  const int per_round = gridDim.x * TSIDB_E_WARPS;
+  const int rounds = (a.n_envs + per_round - 1) / per_round;
+  for (int r = 0; r < rounds; r++) {
+    int slot = (r * gridDim.x + blockIdx.x) * TSIDB_E_WARPS + wid;
+    if (slot >= a.n_envs) slot = a.n_envs - 1;
+    eliminate_env<NV>(C, sm, a, slot, lane, parity);
   }
 }
 
