@@ -40,15 +40,19 @@ WORKLOAD = "robot/v1 LIPM walking (BASELINE configs[2]): 65536 envs/GPU, 20% DS 
 
 
 # ----------------------------------------------------------------------------------------------
-def algorithmic_flops(mask: np.ndarray, iters: np.ndarray) -> float:
-    """F/tick = base(config) + per_iter(config) * it (1 FMA = 2 flop); it = active-set
-    iterations that attempted a constraint change = iterations - 1 (the last pass only checks feasibility).
-    DS 0.50 M + 0.020 M it, SS 0.22 M + 0.012 M it, flight from the same formula (n = 26, m_e = 6)."""
+def algorithmic_flops(mask: np.ndarray, iters: np.ndarray) -> dict:
+    """SURVEY.md §8(d): F/tick = F_dyn + F_asm + F_fact(n) + equality phase + per_iter * it (1 FMA = 2 flop);
+    it = active-set iterations that attempted a constraint change = iterations - 1 (the last pass only checks
+    feasibility).  DS 0.50 M + 0.020 M it, SS 0.22 M + 0.012 M it, flight from the same formula (n = 26,
+    m_e = 6).  Split by the kernel that does the work: dynamics+assembly 28 k (F_dyn 20 k + F_asm 8 k), the
+    factorisation and equality phase (elimination + null-space-basis kernels), the iterations (active set)."""
     nc = (mask & 1) + ((mask >> 1) & 1)
     base = np.where(nc == 2, 0.50e6, np.where(nc == 1, 0.22e6, 0.075e6))
     per = np.where(nc == 2, 0.020e6, np.where(nc == 1, 0.012e6, 0.0075e6))
     it = np.maximum(iters.astype(np.float64) - 1.0, 0.0)
-    return float((base + per * it).sum())
+    dyn = 28e3 * len(mask)
+    return {"dynamics": float(dyn), "eliminate+j2": float(base.sum() - dyn), "activeset": float((per * it).sum()),
+            "tick": float((base + per * it).sum())}
 
 
 HBM_BYTES_PER_TICK = 1832.0  # SURVEY.md §8(d): 1240 B in + 592 B out (v1, double support)
@@ -231,26 +235,56 @@ def main() -> None:
     iters_np = out.iters.cpu().numpy()
     status_np = out.status.cpu().numpy()
     flops = algorithmic_flops(mask, iters_np)
-    kernel_ms = statistics.mean(ms)  # one launch per step: the fused tick kernel
-    ach_tf = flops / (kernel_ms * 1e-3) / 1e12
+    step_ms = statistics.mean(ms)
+    # per-kernel durations: CUDA events recorded by the library between its launches, on the launching stream,
+    # in separate (untimed) steps with the same L2 flush so the events do not perturb `value`
+    eng.set_timing(True)
+    per_kernel = {}
+    reps = max(3, min(args.steps, 10))
+    for _ in range(reps):
+        flush.zero_()
+        step()
+        for k, t in eng.last_tick_ms().items():
+            per_kernel.setdefault(k, []).append(t)
+    eng.set_timing(False)
+    kms = {k: statistics.mean(v) for k, v in per_kernel.items()}
+    groups = {"dynamics": kms["dynamics"], "eliminate+j2": kms["eliminate"] + kms["j2"], "activeset": kms["activeset"]}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+    except Exception:
+        pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_ach = HBM_BYTES_PER_TICK * n / (kernel_ms * 1e-3) / 1e9
+    hbm_ach = HBM_BYTES_PER_TICK * n / (step_ms * 1e-3) / 1e9
+    kernels = []
+    for g, t in groups.items():
+        tf = flops[g] / (t * 1e-3) / 1e12
+        kernels.append({"kernel": g, "ms": t, "algorithmic_flops_per_launch": flops[g], "achieved": tf,
+                        "frac": tf / fp64_peak if fp64_peak else None, "traffic": traffic.get(g)})
+    dom = max(kernels, key=lambda k: k["ms"])
+    tick_tf = flops["tick"] / (step_ms * 1e-3) / 1e12
 
     # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the call) ----
+    # inputs live in pinned host memory (the contract's "from pinned host memory"), results land in pinned
+    # host memory; the library cuts the batch into chunks so the copies run under the kernels
     e2e_steps = max(3, min(args.steps, 10))
+    hq, hv, hmask = eng.pin(q), eng.pin(v), eng.pin(mask)
+    hrefs = {k: eng.pin(a) for k, a in refs.items()}
+    hout = eng.host_buffers(n, pinned=True)
     for _ in range(2):
-        eng.compute_host(q, v, mask, refs)
+        eng.compute_host(hq, hv, hmask, hrefs, out=hout)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ho = eng.compute_host(q, v, mask, refs)
+        ho = eng.compute_host(hq, hv, hmask, hrefs, out=hout)
     t_e2e = time.perf_counter() - t0
+    assert np.array_equal(ho["status"], status_np) and np.array_equal(ho["iters"], iters_np), "e2e path disagrees with the device path"
     if world > 1:
         t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -288,14 +322,22 @@ def main() -> None:
                    "timing": "CUDA events per step on the launching stream, flush outside the events, max over ranks",
                    "collective": "all_gather of int32[N_local,2] diagnostics per step" if world > 1 else "none (1 GPU)"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "api": "tsidb_compute_host via TsidEngine.compute_host (pinned staging inside the library)"},
+                "api": "tsidb_compute_host via TsidEngine.compute_host: pinned host buffers in and out, 4 chunks over 3 streams (copies overlap the kernels)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
-                     "traffic": None, "kernel": "tsidb_tick_kernel", "kernel_ms": kernel_ms,
-                     "peak_source": "measured on this GPU by tsidb_fp64_peak (dependent-free DFMA chains); MEASURED_PEAKS.json has no FP64 entry",
-                     "algorithmic_flops_per_launch": flops,
+        "roofline": {"bound": "fp64", "achieved": dom["achieved"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": dom["frac"],
+                     "traffic": dom["traffic"], "kernel": dom["kernel"], "kernel_ms": dom["ms"],
+                     "algorithmic_flops_per_launch": dom["algorithmic_flops_per_launch"],
+                     "peak_source": "measured on this GPU by tsidb_fp64_peak (dependent-free DFMA chains); MEASURED_PEAKS.json has no FP64 "
+                                    "entry; the path is FP64-bound, not HBM- or tensor-bound (SURVEY.md §8d)",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture in profiles/ "
+                                       "(profiles/dram_traffic.json)" if traffic else None,
+                     "tick": {"achieved": tick_tf, "frac": tick_tf / fp64_peak if fp64_peak else None, "ms": step_ms,
+                              "algorithmic_flops_per_step": flops["tick"],
+                              "launches": "class sort (2) + dynamics + eliminate + j2 + activeset"},
+                     "kernels": kernels, "kernel_ms_all": kms,
                      "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                             "algorithmic_bytes_per_tick": HBM_BYTES_PER_TICK,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
         "solver": {"mean_iters": float(iters_np.mean()), "max_iters": int(iters_np.max()), "status_optimal_frac": float((status_np == 0).mean())},
         "tick_latency_1env_us_p50": lat,

@@ -204,6 +204,14 @@ int tsidb_fp64_peak(int device, double* tflops_out);
 /* counters: kernel launches issued by this handle since creation */
 int64_t tsidb_launch_count(const tsidb_handle* h);
 
+/* Instrumentation for bench.py (the reference has no counterpart; its only timer is the unused
+ * start_time of ref:main.py:54,113).  With timing on, every tick records CUDA events between its
+ * kernels on the launching stream; tsidb_last_tick_ms waits for the last tick and returns the
+ * durations of {class sort, dynamics+assembly, equality elimination, null-space basis,
+ * active set+decode} in milliseconds.                                                            */
+int tsidb_set_timing(tsidb_handle* h, int on);
+int tsidb_last_tick_ms(tsidb_handle* h, float* ms5);
+
 #ifdef __cplusplus
 }
 #endif

@@ -237,6 +237,29 @@ def test_soa_layout_and_host_call_agree_with_device_call():
     assert np.array_equal(h["active_set"].astype(np.int64), base["active_set"])
 
 
+@pytest.mark.parametrize("n,pinned", [(4100, False), (4100, True), (16500, True)])
+def test_chunked_host_call_agrees_with_device_call(n, pinned):
+    """tsidb_compute_host cuts the batch into 2 (n >= 2048) or 4 (n >= 16384) chunks on rotating streams; pinned
+    caller buffers are DMA'd directly, pageable ones go through the staging copy.  Both must reproduce the
+    single-launch device call bit for bit, including a ragged last chunk and per-env references."""
+    s = setup("v1")
+    ctrl = _controller("v1", n)
+    e = ctrl.engine
+    q, v = synth.random_states(s["q0"], n, 12)
+    mask, refs = synth.walking_batch(s["refs"], n, 12, 0.3, 0.2, 0.2, 0.5, float(s["refs"]["com"][2]))
+    base = _run(ctrl, q, v, mask, refs)
+    if pinned:
+        hq, hv, hm = e.pin(q), e.pin(v), e.pin(mask)
+        hr = {k: e.pin(a) for k, a in refs.items()}
+        out = e.host_buffers(n, pinned=True)
+        h = e.compute_host(hq, hv, hm, hr, out=out)
+    else:
+        h = e.compute_host(q, v, mask, refs)
+    for k in ("tau", "ddq", "f", "status", "iters"):
+        assert np.array_equal(h[k], base[k]), k
+    assert np.array_equal(h["active_set"].astype(np.int64), base["active_set"])
+
+
 def test_integrate_matches_oracle():
     s = setup("v1")
     n = 64

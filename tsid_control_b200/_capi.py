@@ -224,6 +224,10 @@ def load_library() -> C.CDLL:
     lib.tsidb_fp64_peak.restype = ip
     lib.tsidb_launch_count.argtypes = [vp]
     lib.tsidb_launch_count.restype = C.c_int64
+    lib.tsidb_set_timing.argtypes = [vp, ip]
+    lib.tsidb_set_timing.restype = ip
+    lib.tsidb_last_tick_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.tsidb_last_tick_ms.restype = ip
     _LIB = lib
     return lib
 
@@ -237,5 +241,5 @@ def check(rc: int, what: str) -> None:
 EXPORTED_SYMBOLS = [
     "tsidb_create", "tsidb_destroy", "tsidb_last_error", "tsidb_sizes", "tsidb_set_default_refs",
     "tsidb_compute", "tsidb_compute_host", "tsidb_integrate", "tsidb_kinematics", "tsidb_ci_row",
-    "tsidb_fp64_peak", "tsidb_launch_count",
+    "tsidb_fp64_peak", "tsidb_launch_count", "tsidb_set_timing", "tsidb_last_tick_ms",
 ]

@@ -25,6 +25,9 @@ static bool g_slot_used[8][TSIDB_MAX_SLOTS]; /* per device */
     }                                                                                        \
   } while (0)
 
+#define TSIDB_HOST_STREAMS 3   /* tsidb_compute_host: chunks rotate over these streams (copy/compute overlap) */
+#define TSIDB_MAX_CHUNKS 8     /* independent work counters / workspace windows */
+
 struct tsidb_handle {
   int device, slot, max_envs, sm_count;
   DevConst dc;
@@ -35,13 +38,15 @@ struct tsidb_handle {
   int32_t* perm;         /* device: slot -> env */
   int32_t* cls_pos;      /* device: per-env (class, position) */
   int64_t launches;
+  int timing;            /* tsidb_set_timing: record events between the tick's kernels */
+  cudaEvent_t ev[6];     /* start, after class sort, dynamics, elimination, J2, active set */
   /* staging for tsidb_compute_host */
   double *h_in, *h_out;  /* pinned */
   double *d_in, *d_out;  /* device */
   uint8_t *h_mask, *d_mask;
   int32_t *h_int, *d_int;    /* status, iters */
   uint64_t *h_act, *d_act;
-  cudaStream_t stream;
+  cudaStream_t stream[TSIDB_HOST_STREAMS];
 };
 
 /* ------------------------------------------------------------------ small kernels */
@@ -194,7 +199,7 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
   const size_t smem_g = (size_t)TSIDB_G_WARPS * (SG_IMAGE + 2) * sizeof(double);
   CK(cudaFuncSetAttribute(tsidb_j2_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   CK(cudaFuncSetAttribute(tsidb_j2_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  CK(cudaMalloc(&h->counter, 4 * sizeof(int32_t)));
+  CK(cudaMalloc(&h->counter, 4 * TSIDB_MAX_CHUNKS * sizeof(int32_t)));
   CK(cudaMalloc(&h->ws, (size_t)max_envs * SA_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->ws2, (size_t)max_envs * SG_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->ws3, (size_t)max_envs * SE_IMAGE * sizeof(double)));
@@ -214,7 +219,7 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
   CK(cudaMalloc(&h->d_int, 2 * sizeof(int32_t) * max_envs));
   CK(cudaMallocHost(&h->h_act, 3 * sizeof(uint64_t) * max_envs));
   CK(cudaMalloc(&h->d_act, 3 * sizeof(uint64_t) * max_envs));
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < TSIDB_HOST_STREAMS; i++) CK(cudaStreamCreateWithFlags(&h->stream[i], cudaStreamNonBlocking));
   *out = h;
   return 0;
 }
@@ -227,7 +232,10 @@ extern "C" void tsidb_destroy(tsidb_handle* h) {
   cudaFreeHost(h->h_mask); cudaFree(h->d_mask);
   cudaFreeHost(h->h_int); cudaFree(h->d_int);
   cudaFreeHost(h->h_act); cudaFree(h->d_act);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  for (int i = 0; i < TSIDB_HOST_STREAMS; i++)
+    if (h->stream[i]) cudaStreamDestroy(h->stream[i]);
+  for (int i = 0; i < 6; i++)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   {
     std::lock_guard<std::mutex> lk(g_slot_mu);
     if (h->slot >= 0) g_slot_used[h->device][h->slot] = false;
@@ -257,27 +265,35 @@ extern "C" int tsidb_set_default_refs(tsidb_handle* h, const double* com9, const
   return upload_const(h);
 }
 
-static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st) {
+/* One tick over a.n_envs envs on stream st.  `base` / `chunk` select a window of the workspaces and a work
+ * counter of its own, so that chunks of one host call can be in flight on different streams. */
+static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base = 0, int chunk = 0) {
   CK(cudaSetDevice(h->device));
-  if (a.n_envs > h->max_envs) { g_err = "n_envs exceeds the handle's max_envs (workspace size)"; return -1; }
-  a.counter = h->counter;
+  if (base + a.n_envs > h->max_envs) { g_err = "n_envs exceeds the handle's max_envs (workspace size)"; return -1; }
+  int32_t* counter = h->counter + 4 * chunk;
+  int32_t* perm = h->perm + base;
+  int32_t* cls_pos = h->cls_pos + base;
+  a.counter = counter;
   a.slot = h->slot;
-  a.ws = h->ws;
-  a.ws2 = h->ws2;
-  a.ws3 = h->ws3;
+  a.ws = h->ws + (size_t)base * SA_IMAGE;
+  a.ws2 = h->ws2 + (size_t)base * SG_IMAGE;
+  a.ws3 = h->ws3 + (size_t)base * SE_IMAGE;
   a.perm = nullptr;
   const int n = a.n_envs;
+  const bool timed = h->timing && !a.kin_only && chunk == 0 && base == 0;
+  if (timed) CK(cudaEventRecord(h->ev[0], st));
   if (!a.kin_only) {
-    CK(cudaMemsetAsync(h->counter, 0, 4 * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(counter, 0, 4 * sizeof(int32_t), st));
     if (a.mask) {
       /* class sort (double support, single support, flight) -> slot order */
       const int th = 256;
-      tsidb_classify_kernel<<<(n + th - 1) / th, th, 0, st>>>(n, a.mask, h->cls_pos, h->counter + 1);
-      tsidb_permute_kernel<<<(n + th - 1) / th, th, 0, st>>>(n, h->cls_pos, h->counter + 1, h->perm);
-      a.perm = h->perm;
+      tsidb_classify_kernel<<<(n + th - 1) / th, th, 0, st>>>(n, a.mask, cls_pos, counter + 1);
+      tsidb_permute_kernel<<<(n + th - 1) / th, th, 0, st>>>(n, cls_pos, counter + 1, perm);
+      a.perm = perm;
       h->launches += 2;
     }
   }
+  if (timed) CK(cudaEventRecord(h->ev[1], st));
   {
     const int warps = TSIDB_WARPS_PER_BLOCK;
     int blocks = (n + warps - 1) / warps;
@@ -288,6 +304,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st) {
     CK(cudaGetLastError());
     h->launches += 1;
   }
+  if (timed) CK(cudaEventRecord(h->ev[2], st));
   if (!a.kin_only) {
     const int warps = TSIDB_E_WARPS;
     int blocks = (n + warps - 1) / warps;
@@ -298,6 +315,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st) {
     CK(cudaGetLastError());
     h->launches += 1;
   }
+  if (timed) CK(cudaEventRecord(h->ev[3], st));
   if (!a.kin_only) {
     const int warps = TSIDB_G_WARPS;
     int blocks = (n + warps - 1) / warps;
@@ -308,6 +326,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st) {
     CK(cudaGetLastError());
     h->launches += 1;
   }
+  if (timed) CK(cudaEventRecord(h->ev[4], st));
   if (!a.kin_only) {
     const int warps = TSIDB_AS_WARPS;
     int blocks = (n + warps - 1) / warps;
@@ -317,6 +336,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st) {
     CK(cudaGetLastError());
     h->launches += 1;
   }
+  if (timed) CK(cudaEventRecord(h->ev[5], st));
   return 0;
 }
 
@@ -351,6 +371,16 @@ extern "C" int tsidb_kinematics(tsidb_handle* h, int n_envs, int layout, const d
   return launch_tick(h, a, (cudaStream_t)cuda_stream);
 }
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+/* The host-buffer tick.  The batch is cut into up to 4 chunks that rotate over 3 streams, so the H2D copy of
+ * chunk k+1 and the D2H copy of chunk k-1 run under the kernels of chunk k.  A caller buffer that is pinned
+ * (cudaHostAlloc / cudaHostRegister / torch pin_memory) is the DMA source or target itself; a pageable one
+ * goes through the handle's pinned staging, chunk by chunk. */
 extern "C" int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, const double* v, const uint8_t* contact_mask,
                                   const tsidb_refs* refs, double* tau, double* ddq, double* f, int32_t* status,
                                   int32_t* iters, uint64_t* active_set) {
@@ -359,42 +389,78 @@ extern "C" int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, 
   CK(cudaSetDevice(h->device));
   const int na = h->dc.na, nv = h->dc.nv, nq = h->dc.nq;
   const size_t N = (size_t)n_envs;
-  /* pack into pinned staging: [q | v | com | foot_lf | foot_rf | contact_lf | contact_rf | posture] */
-  struct Seg { const double* src; int nd; } segs[8] = {
-      {q, nq}, {v, nv}, {refs ? refs->com : nullptr, 9}, {refs ? refs->foot_lf : nullptr, 24},
-      {refs ? refs->foot_rf : nullptr, 24}, {refs ? refs->contact_lf : nullptr, 12},
-      {refs ? refs->contact_rf : nullptr, 12}, {refs ? refs->posture : nullptr, na}};
+  /* device / staging layout: [q | v | com | foot_lf | foot_rf | contact_lf | contact_rf | posture], each [N][nd] */
+  struct Seg { const double* src; int nd; bool pinned; } segs[8] = {
+      {q, nq, false}, {v, nv, false}, {refs ? refs->com : nullptr, 9, false}, {refs ? refs->foot_lf : nullptr, 24, false},
+      {refs ? refs->foot_rf : nullptr, 24, false}, {refs ? refs->contact_lf : nullptr, 12, false},
+      {refs ? refs->contact_rf : nullptr, 12, false}, {refs ? refs->posture : nullptr, na, false}};
   size_t off[9];
   off[0] = 0;
-  for (int s = 0; s < 8; s++) off[s + 1] = off[s] + (segs[s].src ? N * segs[s].nd : 0);
-  for (int s = 0; s < 8; s++)
-    if (segs[s].src) memcpy(h->h_in + off[s], segs[s].src, N * segs[s].nd * sizeof(double));
-  if (contact_mask) memcpy(h->h_mask, contact_mask, N);
-  cudaStream_t st = h->stream;
-  CK(cudaMemcpyAsync(h->d_in, h->h_in, off[8] * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (contact_mask) CK(cudaMemcpyAsync(h->d_mask, h->h_mask, N, cudaMemcpyHostToDevice, st));
-  TickArgs a;
-  memset(&a, 0, sizeof a);
-  a.n_envs = n_envs; a.layout = 0;
-  auto dptr = [&](int s) -> const double* { return segs[s].src ? h->d_in + off[s] : nullptr; };
-  a.q = dptr(0); a.v = dptr(1); a.r_com = dptr(2); a.r_foot[0] = dptr(3); a.r_foot[1] = dptr(4);
-  a.r_contact[0] = dptr(5); a.r_contact[1] = dptr(6); a.r_posture = dptr(7);
-  a.mask = contact_mask ? h->d_mask : nullptr;
-  a.tau = h->d_out; a.ddq = h->d_out + N * na; a.f = h->d_out + N * (na + nv);
-  a.status = h->d_int; a.iters = h->d_int + N;
-  a.active = active_set ? h->d_act : nullptr;
-  int rc = launch_tick(h, a, st);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(h->h_out, h->d_out, N * (na + nv + 24) * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(h->h_int, h->d_int, 2 * N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  if (active_set) CK(cudaMemcpyAsync(h->h_act, h->d_act, 3 * N * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  memcpy(tau, h->h_out, N * na * sizeof(double));
-  memcpy(ddq, h->h_out + N * na, N * nv * sizeof(double));
-  memcpy(f, h->h_out + N * (na + nv), N * 24 * sizeof(double));
-  memcpy(status, h->h_int, N * sizeof(int32_t));
-  memcpy(iters, h->h_int + N, N * sizeof(int32_t));
-  if (active_set) memcpy(active_set, h->h_act, 3 * N * sizeof(uint64_t));
+  for (int s = 0; s < 8; s++) {
+    off[s + 1] = off[s] + (segs[s].src ? N * segs[s].nd : 0);
+    if (segs[s].src) segs[s].pinned = is_pinned(segs[s].src);
+  }
+  const bool mask_pinned = contact_mask && is_pinned(contact_mask);
+  const bool out_pinned[3] = {is_pinned(tau), is_pinned(ddq), is_pinned(f)};
+  const bool st_pinned = is_pinned(status), it_pinned = is_pinned(iters);
+  const bool act_pinned = active_set && is_pinned(active_set);
+  double* d_tau = h->d_out;
+  double* d_ddq = h->d_out + N * na;
+  double* d_f = h->d_out + N * (na + nv);
+  double* s_tau = h->h_out;
+  double* s_ddq = h->h_out + N * na;
+  double* s_f = h->h_out + N * (na + nv);
+
+  int nch = n_envs >= 16384 ? 4 : (n_envs >= 2048 ? 2 : 1);
+  const int cs = ((n_envs + nch - 1) / nch + 7) & ~7;
+  nch = (n_envs + cs - 1) / cs;
+  for (int c = 0; c < nch; c++) {
+    cudaStream_t st = h->stream[c % TSIDB_HOST_STREAMS];
+    const size_t o = (size_t)c * cs;
+    const int m = (int)((N - o < (size_t)cs) ? N - o : (size_t)cs);
+    for (int s = 0; s < 8; s++) {
+      if (!segs[s].src) continue;
+      const size_t cnt = (size_t)m * segs[s].nd, eo = off[s] + o * segs[s].nd;
+      const double* src = segs[s].src + o * segs[s].nd;
+      if (!segs[s].pinned) { memcpy(h->h_in + eo, src, cnt * sizeof(double)); src = h->h_in + eo; }
+      CK(cudaMemcpyAsync(h->d_in + eo, src, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (contact_mask) {
+      const uint8_t* src = contact_mask + o;
+      if (!mask_pinned) { memcpy(h->h_mask + o, src, m); src = h->h_mask + o; }
+      CK(cudaMemcpyAsync(h->d_mask + o, src, m, cudaMemcpyHostToDevice, st));
+    }
+    TickArgs a;
+    memset(&a, 0, sizeof a);
+    a.n_envs = m; a.layout = 0;
+    auto dptr = [&](int s) -> const double* { return segs[s].src ? h->d_in + off[s] + o * segs[s].nd : nullptr; };
+    a.q = dptr(0); a.v = dptr(1); a.r_com = dptr(2); a.r_foot[0] = dptr(3); a.r_foot[1] = dptr(4);
+    a.r_contact[0] = dptr(5); a.r_contact[1] = dptr(6); a.r_posture = dptr(7);
+    a.mask = contact_mask ? h->d_mask + o : nullptr;
+    a.tau = d_tau + o * na; a.ddq = d_ddq + o * nv; a.f = d_f + o * 24;
+    a.status = h->d_int + o; a.iters = h->d_int + N + o;
+    a.active = active_set ? h->d_act + 3 * o : nullptr; /* [3][m] block of this chunk */
+    int rc = launch_tick(h, a, st, (int)o, c);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_pinned[0] ? tau + o * na : s_tau + o * na, a.tau, (size_t)m * na * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_pinned[1] ? ddq + o * nv : s_ddq + o * nv, a.ddq, (size_t)m * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_pinned[2] ? f + o * 24 : s_f + o * 24, a.f, (size_t)m * 24 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(st_pinned ? status + o : h->h_int + o, a.status, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(it_pinned ? iters + o : h->h_int + N + o, a.iters, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (active_set) {
+      for (int w = 0; w < 3; w++) {
+        uint64_t* dst = act_pinned ? active_set + (size_t)w * N + o : h->h_act + (size_t)w * N + o;
+        CK(cudaMemcpyAsync(dst, h->d_act + 3 * o + (size_t)w * m, (size_t)m * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      }
+    }
+  }
+  for (int i = 0; i < TSIDB_HOST_STREAMS && i < nch; i++) CK(cudaStreamSynchronize(h->stream[i]));
+  if (!out_pinned[0]) memcpy(tau, s_tau, N * na * sizeof(double));
+  if (!out_pinned[1]) memcpy(ddq, s_ddq, N * nv * sizeof(double));
+  if (!out_pinned[2]) memcpy(f, s_f, N * 24 * sizeof(double));
+  if (!st_pinned) memcpy(status, h->h_int, N * sizeof(int32_t));
+  if (!it_pinned) memcpy(iters, h->h_int + N, N * sizeof(int32_t));
+  if (active_set && !act_pinned) memcpy(active_set, h->h_act, 3 * N * sizeof(uint64_t));
   return 0;
 }
 
@@ -421,6 +487,24 @@ extern "C" int tsidb_ci_row(const tsidb_handle* h, int block, int side, int i) {
 }
 
 extern "C" int64_t tsidb_launch_count(const tsidb_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int tsidb_set_timing(tsidb_handle* h, int on) {
+  if (!h) { g_err = "tsidb_set_timing: null handle"; return -1; }
+  CK(cudaSetDevice(h->device));
+  if (on && !h->ev[0])
+    for (int i = 0; i < 6; i++) CK(cudaEventCreate(&h->ev[i]));
+  h->timing = on ? 1 : 0;
+  return 0;
+}
+
+extern "C" int tsidb_last_tick_ms(tsidb_handle* h, float* ms5) {
+  if (!h || !ms5) { g_err = "tsidb_last_tick_ms: null argument"; return -1; }
+  if (!h->timing || !h->ev[0]) { g_err = "tsidb_last_tick_ms: timing is off (tsidb_set_timing)"; return -1; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize(h->ev[5]));
+  for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&ms5[i], h->ev[i], h->ev[i + 1]));
+  return 0;
+}
 
 extern "C" int tsidb_fp64_peak(int device, double* tflops_out) {
   if (!tflops_out) { g_err = "tsidb_fp64_peak: null argument"; return -1; }

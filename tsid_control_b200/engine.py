@@ -119,9 +119,34 @@ class TsidEngine:
             C.byref(a) if aux else None, self._stream()), "tsidb_compute")
         return TickOutput(**{k: o[k] for k in TickOutput.__slots__})
 
+    def host_buffers(self, n: int, pinned: bool = True) -> Dict[str, np.ndarray]:
+        """Output buffers for :meth:`compute_host`.  Pinned buffers (the default) are DMA targets themselves;
+        pageable ones go through the library's staging copy."""
+        shapes = {"tau": ((n, self.na), torch.float64), "ddq": ((n, self.nv), torch.float64), "f": ((n, 24), torch.float64),
+                  "status": ((n,), torch.int32), "iters": ((n,), torch.int32), "active_set": ((3, n), torch.int64)}
+        out = {}
+        self._pinned_keep = getattr(self, "_pinned_keep", [])
+        for k, (shp, dt) in shapes.items():
+            t = torch.empty(shp, dtype=dt, pin_memory=pinned)
+            self._pinned_keep.append(t)
+            a = t.numpy()
+            out[k] = a.view(np.uint64) if k == "active_set" else a
+        return out
+
+    @staticmethod
+    def pin(a: np.ndarray) -> np.ndarray:
+        """A pinned copy of a host array (so that compute_host can DMA straight from it)."""
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        TsidEngine._pins.append(t)  # the numpy view does not own the pinned allocation
+        return t.numpy()
+
+    _pins: list = []
+
     def compute_host(self, q: np.ndarray, v: np.ndarray, contact_mask: Optional[np.ndarray] = None,
-                     refs: Optional[Dict[str, np.ndarray]] = None, want_active: bool = True) -> Dict[str, np.ndarray]:
-        """The same tick with HOST numpy buffers in and out (H2D, kernels, D2H inside the call)."""
+                     refs: Optional[Dict[str, np.ndarray]] = None, want_active: bool = True,
+                     out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+        """The same tick with HOST numpy buffers in and out (H2D, kernels, D2H inside the call, chunked so that
+        the copies overlap the kernels).  `out` = buffers from :meth:`host_buffers` to avoid per-call allocation."""
         q = np.ascontiguousarray(q, dtype=np.float64)
         v = np.ascontiguousarray(v, dtype=np.float64)
         n = q.shape[0]
@@ -140,9 +165,10 @@ class TsidEngine:
         m = None
         if contact_mask is not None:
             m = np.ascontiguousarray(contact_mask, dtype=np.uint8)
-        out = {"tau": np.empty((n, self.na)), "ddq": np.empty((n, self.nv)), "f": np.empty((n, 24)),
-               "status": np.empty(n, np.int32), "iters": np.empty(n, np.int32),
-               "active_set": np.empty((3, n), np.uint64)}
+        if out is None:
+            out = self.host_buffers(n, pinned=False)
+        elif out["tau"].shape[0] != n:
+            raise ValueError("out: buffers were allocated for a different batch size")
         check(self.lib.tsidb_compute_host(
             self.h, n, q.ctypes.data, v.ctypes.data, m.ctypes.data if m is not None else None, C.byref(r),
             out["tau"].ctypes.data, out["ddq"].ctypes.data, out["f"].ctypes.data, out["status"].ctypes.data,
@@ -176,6 +202,17 @@ class TsidEngine:
 
     def launch_count(self) -> int:
         return int(self.lib.tsidb_launch_count(self.h))
+
+    KERNEL_NAMES = ("class_sort", "dynamics", "eliminate", "j2", "activeset")
+
+    def set_timing(self, on: bool) -> None:
+        check(self.lib.tsidb_set_timing(self.h, int(on)), "tsidb_set_timing")
+
+    def last_tick_ms(self) -> Dict[str, float]:
+        """CUDA-event durations of the kernels of the last tick (needs set_timing(True))."""
+        ms = (C.c_float * 5)()
+        check(self.lib.tsidb_last_tick_ms(self.h, ms), "tsidb_last_tick_ms")
+        return {k: float(ms[i]) for i, k in enumerate(self.KERNEL_NAMES)}
 
 
 def fp64_peak_tflops(device: int = 0) -> float:
