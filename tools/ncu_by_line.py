@@ -30,7 +30,8 @@ def phase_table(src):
         (r"^TSIDB_DEV int as_solve", "K3 AS setup"), (r"for \(;;\) \{ /\* l1 \*/", "K3 AS l1: s, psi"),
         (r"for \(;;\) \{ /\* l2 \*/", "K3 AS l2: pick"), (r"for \(;;\) \{ /\* l2a \*/", "K3 AS l2a: d,z,r,steps"),
         (r"if \(t == t2\) \{", "K3 AS add (Householder)"), (r"partial step: drop the blocking", "K3 AS partial-step drop"),
-        (r"^TSIDB_DEV void prepare_env", "F io + hand-off store"), (r"^TSIDB_DEV void activeset_env", "A load + decode"),
+        (r"^TSIDB_DEV void dynamics_env", "D io + image stores"), (r"^TSIDB_DEV void eliminate_env", "E io + image stores"),
+        (r"^struct G2Pipe", "G pipeline"), (r"^TSIDB_DEV int warp_argmin", "K3 argmin"), (r"^TSIDB_DEV unsigned smem_u32", "TMA helpers"), (r"^TSIDB_DEV void activeset_env", "A load + decode"),
         (r"^TSIDB_DEV void j2_columns", "G columns"), (r"^TSIDB_DEV void j2_env", "G load"),
         (r"^TSIDB_DEV void wrench_of", "K3 wrench_of"), (r"^TSIDB_DEV double eval_one", "K3 eval_one"), (r"^TSIDB_DEV void actuation_normal", "K3 actuation_normal"),
         (r"w0 = Q w_hat: reflectors in reverse", "E w0"), (r"x0 = L\^-T w0: force rows", "E x0"), (r"^__global__ void tsidb_classify", "kernel loops"),
