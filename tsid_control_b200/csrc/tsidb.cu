@@ -193,8 +193,13 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
   CK(cudaFuncSetAttribute(tsidb_dynamics_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaFuncSetAttribute(tsidb_dynamics_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t smem_e = (size_t)TSIDB_E_WARPS * SE_PER_ENV * sizeof(double);
-  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+  const size_t smem_el = (size_t)TSIDB_E_WARPS_LIGHT * SE_PER_ENV * sizeof(double);
+  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<26, 2, TSIDB_E_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<24, 2, TSIDB_E_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<26, 1, TSIDB_E_WARPS_LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_el));
+  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<24, 1, TSIDB_E_WARPS_LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_el));
+  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<26, 0, TSIDB_E_WARPS_LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_el));
+  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<24, 0, TSIDB_E_WARPS_LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_el));
   CK(cudaFuncSetAttribute(tsidb_activeset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_as));
   const size_t smem_g = (size_t)TSIDB_G_WARPS * (SG_IMAGE + 2) * sizeof(double);
   CK(cudaFuncSetAttribute(tsidb_j2_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
@@ -306,14 +311,26 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   }
   if (timed) CK(cudaEventRecord(h->ev[2], st));
   if (!a.kin_only) {
-    const int warps = TSIDB_E_WARPS;
-    int blocks = (n + warps - 1) / warps;
-    if (blocks > h->sm_count) blocks = h->sm_count;
-    const size_t smem = (size_t)warps * SE_PER_ENV * sizeof(double);
-    if (h->dc.nv == 26) tsidb_eliminate_kernel<26><<<blocks, 32 * warps, smem, st>>>(a);
-    else tsidb_eliminate_kernel<24><<<blocks, 32 * warps, smem, st>>>(a);
+    /* one launch per contact class; the class sizes are only known on the device, so every class gets a full
+     * persistent grid and the CTAs of an empty class return at once.  Without a mask all envs are double support. */
+    const int blocks = h->sm_count;
+    const size_t smem = (size_t)TSIDB_E_WARPS * SE_PER_ENV * sizeof(double);
+    const size_t smem_l = (size_t)TSIDB_E_WARPS_LIGHT * SE_PER_ENV * sizeof(double);
+    if (h->dc.nv == 26) {
+      tsidb_eliminate_kernel<26, 2, TSIDB_E_WARPS><<<blocks, 32 * TSIDB_E_WARPS, smem, st>>>(a);
+      if (a.perm) {
+        tsidb_eliminate_kernel<26, 1, TSIDB_E_WARPS_LIGHT><<<blocks, 32 * TSIDB_E_WARPS_LIGHT, smem_l, st>>>(a);
+        tsidb_eliminate_kernel<26, 0, TSIDB_E_WARPS_LIGHT><<<blocks, 32 * TSIDB_E_WARPS_LIGHT, smem_l, st>>>(a);
+      }
+    } else {
+      tsidb_eliminate_kernel<24, 2, TSIDB_E_WARPS><<<blocks, 32 * TSIDB_E_WARPS, smem, st>>>(a);
+      if (a.perm) {
+        tsidb_eliminate_kernel<24, 1, TSIDB_E_WARPS_LIGHT><<<blocks, 32 * TSIDB_E_WARPS_LIGHT, smem_l, st>>>(a);
+        tsidb_eliminate_kernel<24, 0, TSIDB_E_WARPS_LIGHT><<<blocks, 32 * TSIDB_E_WARPS_LIGHT, smem_l, st>>>(a);
+      }
+    }
     CK(cudaGetLastError());
-    h->launches += 1;
+    h->launches += a.perm ? 3 : 1;
   }
   if (timed) CK(cudaEventRecord(h->ev[3], st));
   if (!a.kin_only) {

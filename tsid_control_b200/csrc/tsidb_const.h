@@ -9,8 +9,10 @@
 #define TSIDB_NX 50    /* nv + 24                                                          */
 #define TSIDB_MRED 32  /* n - nEq = na + 6*nc <= 32: one lane per reduced coordinate       */
 #define TSIDB_WARPS_PER_BLOCK 12  /* dynamics kernel */
-#define TSIDB_E_WARPS 8            /* elimination kernel */
+#define TSIDB_E_WARPS 8            /* elimination kernel, double support */
+#define TSIDB_E_WARPS_LIGHT 8      /* elimination kernel, single support and flight */
 #define TSIDB_MAX_SLOTS 6
+#define SG_LDV (TSIDB_NVX + 24)  /* row stride of the Householder reflectors (elimination kernel -> J2 kernel) */
 
 struct DevConst {
   int32_t nb, na, nv, nq;

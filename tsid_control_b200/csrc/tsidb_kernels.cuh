@@ -641,37 +641,9 @@ TSIDB_DEV void k2_assemble(const DevConst& C, double* sm, const TickArgs& a, int
  * register-array indices are compile-time constants (fully unrolled loops), the operands shared by the
  * warp (factor entries, Householder vectors) are broadcast reads from shared memory. */
 
-/* q <- L^-T q for the dv block (axpy form: the updates of one step are independent), then the constant
- * force blocks q_f <- Lf^-T q_f */
-template <int NV>
-TSIDB_DEV void backsub_LT(double (&q)[NV + 24], const double* L, const double* ild, const DevConst& C, int nc) {
-#pragma unroll
-  for (int k = NV - 1; k >= 0; k--) {
-    SCHED_FENCE(); /* keep the compiler from hoisting the factor loads of later steps (register pressure) */
-    q[k] *= ild[k];
-#pragma unroll
-    for (int i = 0; i < k; i++) q[i] -= L[k * SM_LDM + i] * q[k];
-  }
-#pragma unroll
-  for (int s = 0; s < 2; s++) {
-    if (s < nc) {
-      double t[12];
-#pragma unroll
-      for (int i = 0; i < 12; i++) t[i] = q[NV + 12 * s + i];
-#pragma unroll
-      for (int i = 0; i < 12; i++) {
-        double acc = 0.0;
-#pragma unroll
-        for (int k = i; k < 12; k++) acc += C.Lfinv[k][i] * t[k];
-        q[NV + 12 * s + i] = acc;
-      }
-    }
-  }
-}
-
 /* b <- L^-1 b (dv block, axpy form) and b_f <- Lf^-1 b_f */
-template <int NV>
-TSIDB_DEV void fwdsub_L(double (&b)[NV + 24], const double* L, const double* ild, const DevConst& C, int nc) {
+template <int NV, int NC>
+TSIDB_DEV void fwdsub_L(double (&b)[NV + 12 * NC], const double* L, const double* ild, const DevConst& C) {
 #pragma unroll
   for (int k = 0; k < NV; k++) {
     SCHED_FENCE();
@@ -680,8 +652,8 @@ TSIDB_DEV void fwdsub_L(double (&b)[NV + 24], const double* L, const double* ild
     for (int i = k + 1; i < NV; i++) b[i] -= L[i * SM_LDM + k] * b[k];
   }
 #pragma unroll
-  for (int s = 0; s < 2; s++) {
-    if (s < nc) {
+  for (int s = 0; s < NC; s++) {
+    {
       double t[12];
 #pragma unroll
       for (int i = 0; i < 12; i++) t[i] = b[NV + 12 * s + i];
@@ -733,11 +705,11 @@ TSIDB_DEV void store_R1(double* R1, const double (&b)[N], int lane) {
  * Column order of B: the 6*nc contact-motion rows first, then the 6 base-dynamics rows.  Any order yields the
  * same null space, x0 and projector; this one keeps the first 6*nc reflectors inside the dv rows (a contact-motion
  * row has no force entries), which halves their cost here and in the J2 kernel. */
-template <int NV>
-TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, int nc, int n, int neq,
-                           double& c1c2, double& R_norm_out) {
-  constexpr int N = NV + 24;
-  const int ncm = 6 * nc;
+template <int NV, int NC>
+TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, double& c1c2, double& R_norm_out) {
+  constexpr int N = NV + 12 * NC;   /* n: the contact class fixes every size at compile time */
+  constexpr int nc = NC, ncm = 6 * NC, neq = 6 + 6 * NC, n = N;
+  constexpr int LDV = SG_LDV;       /* reflector row stride (the J2 kernel reads the same layout) */
   double* L = sm + SE_oH;
   double* ild = sm + SE_oILD;
   double* tauq = sm + SE_oTAU;
@@ -812,8 +784,8 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
 #pragma unroll
       for (int k = 0; k < NV; k++) b[k] = Mm[u * SM_LDM + k];
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
-        if (s < nc) {
+      for (int s = 0; s < NC; s++) {
+        {
           const int f = (s == 0) ? f0 : 1;
           double jf[6];
 #pragma unroll
@@ -831,15 +803,14 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
 #pragma unroll
       for (int k = 0; k < N; k++) b[k] = gv[k];
     }
-    fwdsub_L<NV>(b, L, ild, C, nc);
+    fwdsub_L<NV, NC>(b, L, ild, C);
     if (e == neq) {
 #pragma unroll
       for (int k = 0; k < N; k++) b[k] = -b[k]; /* w_unc = -L^-1 g */
     }
     PHASE_SYNC();
-    for (int i = 0; i < 18; i++) {
+    for (int i = 0; i < neq; i++) {
       PHASE_SYNC();
-      if (i >= neq) continue;
       /* Reflector i < ncm (contact motion): head row i, span = dv rows i..NV-1.  Reflector i >= ncm (base
        * dynamics): head = force row NV + (i - ncm), span = dv rows ncm..NV-1 and the force rows from the head
        * on.  The base-dynamics columns carry their largest entries in the force rows (scaled by Lf^-1), so
@@ -870,24 +841,22 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
       R_norm = fmax(R_norm, fabs(beta));
       const double tau = (beta - alpha) / beta;
       const double scal = 1.0 / (alpha - beta);
-      for (int k = lane; k < N; k += 32) {
+      for (int k = lane; k < LDV; k += 32) {
         const bool in_span = k < n && ((k >= lo && k < NV) || (!top && k > head));
-        Vt[i * N + k] = (k == head) ? 1.0 : (in_span ? colp[k] * scal : 0.0);
+        Vt[i * LDV + k] = (k == head) ? 1.0 : (in_span ? colp[k] * scal : 0.0);
       }
       if (lane == 0) { tauq[i] = tau; Rd[i] = beta; }
       __syncwarp();
       if (lane > i && lane <= neq) {
-        if (top) reflect<N, NV>(b, Vt + i * N, tau);
-        else reflect<N, N>(b, Vt + i * N, tau);
+        if (top) reflect<N, NV>(b, Vt + i * LDV, tau);
+        else reflect<N, N>(b, Vt + i * LDV, tau);
       }
     }
     __syncwarp();
     /* R1 (strictly upper part; the diagonal is Rd) and the carried column */
     if (lane <= neq) {
       /* R1[k][j] = entry of column j at the head row of reflector k */
-      if (nc == 2) store_R1<N, NV, 12, 18>(R1, b, lane);
-      else if (nc == 1) store_R1<N, NV, 6, 12>(R1, b, lane);
-      else store_R1<N, NV, 0, 6>(R1, b, lane);
+      store_R1<N, NV, ncm, neq>(R1, b, lane);
     }
     if (lane == neq) {
 #pragma unroll
@@ -922,8 +891,8 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
   double y0 = (lane < n) ? gv[lane] : 0.0;
   double y1 = (lane + 32 < n) ? gv[lane + 32] : 0.0;
   for (int i = neq - 1; i >= 0; i--) {
-    const double v0 = Vt[i * N + lane];
-    const double v1 = (lane + 32 < N) ? Vt[i * N + lane + 32] : 0.0;
+    const double v0 = Vt[i * LDV + lane];
+    const double v1 = (lane + 32 < N) ? Vt[i * LDV + lane + 32] : 0.0;
     const double w = tauq[i] * warp_sum(v0 * y0 + v1 * y1);
     y0 -= w * v0;
     y1 -= w * v1;
@@ -960,7 +929,6 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, in
  * buys is that every stage runs at the occupancy and the thread mapping that suits it: F in CTA-wide phase
  * lock-step, G register-blocked with no cross-lane traffic, A balancing the data-dependent iteration counts
  * (1..40) dynamically.                                                                                     */
-#define SG_LDV (TSIDB_NVX + 24)           /* reflector stride written by the elimination kernel      */
 #define SG_LDL 28                         /* row stride of L in the factor image (even: 16-byte reads)    */
 #define SG_oL 0                           /* L      26 x 28                             728 */
 #define SG_oILD (SG_oL + 728)             /* 1/L_ii                                      26 */
@@ -1592,7 +1560,7 @@ TSIDB_DEV void dynamics_env(const DevConst& C, double* sm, const TickArgs& a, in
 }
 
 /* ================================================================= kernel E: equality elimination of one env */
-template <int NV>
+template <int NV, int NC>
 TSIDB_DEV void eliminate_env(const DevConst& C, double* sm, const TickArgs& a, int slot, int lane, unsigned& parity) {
   const int nv = C.nv;
   __syncwarp(); /* every lane is done with the previous env's shared memory */
@@ -1604,11 +1572,10 @@ TSIDB_DEV void eliminate_env(const DevConst& C, double* sm, const TickArgs& a, i
   for (int k = lane; k < SE_IMAGE; k += 32) sm[k] = a.ws3[(size_t)slot * SE_IMAGE + k];
 #endif
   __syncwarp();
-  const int mask = (int)sm[SE_oSc];
-  const int nc = (mask & 1) + ((mask >> 1) & 1);
-  const int n = nv + 12 * nc, neq = 6 + 6 * nc;
+  const int mask = (int)sm[SE_oSc]; /* its contact count is NC: the slots are class-sorted */
+  constexpr int n = NV + 12 * NC;
   double c1c2 = 0.0, R_norm = 1.0;
-  const int err = k3_eliminate<NV>(C, sm, lane, mask, nc, n, neq, c1c2, R_norm);
+  const int err = k3_eliminate<NV, NC>(C, sm, lane, mask, c1c2, R_norm);
   double* img = a.ws + (size_t)slot * SA_IMAGE;
   for (int k = lane; k < TSIDB_NX; k += 32) img[SA_oX + k] = (k < n) ? sm[SE_oX + k] : 0.0;
   if (lane == 0) { img[SA_oSc] = c1c2; img[SA_oSc + 1] = R_norm; img[SA_oSc + 2] = (double)err; }
@@ -1664,7 +1631,7 @@ TSIDB_DEV void g2_request_l(const G2Pipe& P, double* sg, int lane) {
 
 template <int NV, int NC>
 TSIDB_DEV void j2_columns(const DevConst& C, double* sg, double* img, int lane, G2Pipe& P) {
-  constexpr int NS = NV + 24;
+  constexpr int NS = SG_LDV;
   constexpr int N = NV + 12 * NC, NEQ = 6 + 6 * NC, NCM = 6 * NC, M = N - NEQ;
   const bool work = lane < M;
   const double2* L2 = reinterpret_cast<const double2*>(sg + SG_oL);
@@ -1892,22 +1859,37 @@ tsidb_dynamics_kernel(const TickArgs a) {
   }
 }
 
-template <int NV>
-__global__ void __launch_bounds__(32 * TSIDB_E_WARPS, 1)
+/* slot range of contact class NC (2: double support, 1: single support, 0: flight) in the class-sorted slot
+ * order; without a contact mask every env is in double support */
+template <int NC>
+TSIDB_DEV void class_range(const TickArgs& a, int& start, int& count) {
+  if (!a.perm) { start = 0; count = (NC == 2) ? a.n_envs : 0; return; }
+  const int c0 = a.counter[1], c1 = a.counter[2], c2 = a.counter[3];
+  start = (NC == 2) ? 0 : ((NC == 1) ? c0 : c0 + c1);
+  count = (NC == 2) ? c0 : ((NC == 1) ? c1 : c2);
+}
+
+/* one launch per contact class: every size of the elimination is a compile-time constant, the warps of a CTA
+ * have identical trip counts (phase lock-step), and the lighter classes fit more warps per SM */
+template <int NV, int NC, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1)
 tsidb_eliminate_kernel(const TickArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* sm = smem + wid * SE_PER_ENV;
   const DevConst& C = g_const[a.slot];
+  int start, count;
+  class_range<NC>(a, start, count);
+  if (count <= 0) return;
   if (lane == 0) mbar_init(sm + SE_oBar, 1);
   __syncwarp();
   unsigned parity = 0;
-  const int per_round = gridDim.x * TSIDB_E_WARPS;
-  const int rounds = (a.n_envs + per_round - 1) / per_round;
+  const int per_round = gridDim.x * WARPS;
+  const int rounds = (count + per_round - 1) / per_round;
   for (int r = 0; r < rounds; r++) {
-    int slot = (r * gridDim.x + blockIdx.x) * TSIDB_E_WARPS + wid;
-    if (slot >= a.n_envs) slot = a.n_envs - 1;
-    eliminate_env<NV>(C, sm, a, slot, lane, parity);
+    int k = (r * gridDim.x + blockIdx.x) * WARPS + wid;
+    if (k >= count) k = count - 1;
+    eliminate_env<NV, NC>(C, sm, a, start + k, lane, parity);
   }
 }
 
