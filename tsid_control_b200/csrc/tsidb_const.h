@@ -11,6 +11,12 @@
 #define TSIDB_WARPS_PER_BLOCK 12  /* dynamics kernel */
 #define TSIDB_E_WARPS 8            /* elimination kernel, double support */
 #define TSIDB_E_WARPS_LIGHT 8      /* elimination kernel, single support and flight */
+/* CTA-wide phase lock-step (all warps of a CTA run the same phase at the same time, so one instruction-cache
+ * line serves all of them).  It paid off for the fused 215 KB kernel of the first generation; with one kernel
+ * per stage the code fits the instruction cache and free-running warps hide each other's latencies better
+ * (measured: elimination 1.82 -> 1.63 ms, dynamics 1.24 -> 1.17 ms), so both are off. */
+#define TSIDB_LOCK_D 0
+#define TSIDB_LOCK_E 0
 #define TSIDB_MAX_SLOTS 6
 #define SG_LDV (TSIDB_NVX + 24)  /* row stride of the Householder reflectors (elimination kernel -> J2 kernel) */
 

@@ -45,9 +45,11 @@ __constant__ DevConst g_const[TSIDB_MAX_SLOTS];
  * time, so an instruction-cache line fetched by one warp serves all of them (the kernel is fetch-bound
  * otherwise: profiles/ r1b).  A no-op in the single-warp host emulation. */
 #ifdef TSIDB_EMU
-#define PHASE_SYNC() ((void)0)
+#define PHASE_SYNC_D() ((void)0)
+#define PHASE_SYNC_E() ((void)0)
 #else
-#define PHASE_SYNC() __syncthreads()
+#define PHASE_SYNC_D() do { if (TSIDB_LOCK_D) __syncthreads(); } while (0)
+#define PHASE_SYNC_E() do { if (TSIDB_LOCK_E) __syncthreads(); } while (0)
 #endif
 #define TS_EPS 2.220446049250313e-16
 #define TS_INF 1.7976931348623157e308
@@ -672,18 +674,29 @@ TSIDB_DEV void fwdsub_L(double (&b)[NV + 12 * NC], const double* L, const double
  * rows K.. of v are zero by construction and are not visited */
 template <int N, int K>
 TSIDB_DEV void reflect(double (&c)[N], const double* v, double tau) {
+  static_assert((K & 1) == 0, "rows come in pairs");
+  /* the reflector is read as 16-byte pairs (broadcast): half the shared-memory instructions */
+  const double2* v2 = reinterpret_cast<const double2*>(v);
   double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
 #pragma unroll
-  for (int k = 0; k + 1 < K; k += 4) {
-    w0 += v[k] * c[k];
-    w1 += v[k + 1] * c[k + 1];
-    if (k + 2 < K) w2 += v[k + 2] * c[k + 2];
-    if (k + 3 < K) w3 += v[k + 3] * c[k + 3];
+  for (int k = 0; k < K; k += 4) {
+    const double2 p = v2[k >> 1];
+    w0 += p.x * c[k];
+    w1 += p.y * c[k + 1];
+    if (k + 2 < K) {
+      const double2 q = v2[(k >> 1) + 1];
+      w2 += q.x * c[k + 2];
+      w3 += q.y * c[k + 3];
+    }
   }
   const double w = tau * ((w0 + w1) + (w2 + w3));
   SCHED_FENCE(); /* reload v for the update instead of keeping 50 more values live (spills otherwise) */
 #pragma unroll
-  for (int k = 0; k < K; k++) c[k] -= w * v[k];
+  for (int k = 0; k < K; k += 2) {
+    const double2 p = v2[k >> 1];
+    c[k] -= w * p.x;
+    c[k + 1] -= w * p.y;
+  }
 }
 
 /* head row of reflector k for a class with NCM contact-motion equalities (see k3_eliminate) */
@@ -725,8 +738,8 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, do
   const double* bmot = sm + SE_oBm;
   const int f0 = (mask & 1) ? 0 : 1; /* foot of force block 0 */
 
-  int err = ST_OPTIMAL; /* an error status is carried to the end: every warp must reach every PHASE_SYNC */
-  PHASE_SYNC();
+  int err = ST_OPTIMAL; /* an error status is carried to the end: every warp must reach every PHASE_SYNC_E */
+  PHASE_SYNC_E();
   /* ---- Cholesky of the dv block: lane i keeps row i; c1 = trace(H), c2 = trace(L^-T) ---- */
   double c1, c2;
   {
@@ -764,7 +777,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, do
   }
   c1c2 = c1 * c2;
 
-  PHASE_SYNC();
+  PHASE_SYNC_E();
   /* ---- B = L^-1 [CE^T | g]: lane e keeps column e; Householder QR; the last column becomes Q^T w_unc ---- */
   double R_norm = 1.0;
   {
@@ -808,9 +821,9 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, do
 #pragma unroll
       for (int k = 0; k < N; k++) b[k] = -b[k]; /* w_unc = -L^-1 g */
     }
-    PHASE_SYNC();
+    PHASE_SYNC_E();
     for (int i = 0; i < neq; i++) {
-      PHASE_SYNC();
+      PHASE_SYNC_E();
       /* Reflector i < ncm (contact motion): head row i, span = dv rows i..NV-1.  Reflector i >= ncm (base
        * dynamics): head = force row NV + (i - ncm), span = dv rows ncm..NV-1 and the force rows from the head
        * on.  The base-dynamics columns carry their largest entries in the force rows (scaled by Lf^-1), so
@@ -864,7 +877,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, do
     }
     __syncwarp();
   }
-  PHASE_SYNC();
+  PHASE_SYNC_E();
   /* ---- w_hat[0:neq] = R1^-T rhs (forward substitution, lane <-> equation); rhs = -ce0 ---- */
   {
     double rhs = 0.0;
@@ -1513,7 +1526,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
 template <int NV>
 TSIDB_DEV void dynamics_env(const DevConst& C, double* sm, const TickArgs& a, int env, int slot, int lane) {
   const int nv = C.nv, na = C.na, nq = C.nq;
-  PHASE_SYNC();
+  PHASE_SYNC_D();
   /* stage q, v */
   if (lane < nq) sm[SM_oQV + lane] = ldin(a.q, a, env, lane, nq);
   if (lane < nv) sm[SM_oQV + 32 + lane] = a.v ? ldin(a.v, a, env, lane, nv) : 0.0;
@@ -1533,7 +1546,7 @@ TSIDB_DEV void dynamics_env(const DevConst& C, double* sm, const TickArgs& a, in
   const int mask = a.mask ? (a.mask[env] & 3) : 3;
   const int nc = (mask & 1) + ((mask >> 1) & 1);
   const int n = nv + 12 * nc, neq = 6 + 6 * nc;
-  PHASE_SYNC();
+  PHASE_SYNC_D();
   k2_assemble(C, sm, a, env, lane, mask, neq, n);
   /* solver image (layout SA_*): the parts that do not depend on the elimination */
   double* img = a.ws + (size_t)slot * SA_IMAGE;
