@@ -1277,6 +1277,23 @@ TSIDB_DEVNI void qp_delete(const ASCtx& S, int n, int& iq, int qq, int lane) {
   __syncwarp();
 }
 
+/* this lane's most violated row among the rows it owns that are neither active nor excluded; ties to the lowest
+ * reference row index */
+TSIDB_DEV void pick_local(const DevConst& C, const double (&sl)[6], unsigned actbits, unsigned exclbits, int na, int lane,
+                          double& best, int& bcid, int& bbit) {
+  best = 0.0;
+  bcid = -1;
+  bbit = 1 << 30;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    if (!((actbits >> k) & 1u) && !((exclbits >> k) & 1u) && sl[k] < 0.0) {
+      const int cid = cid_of(na, lane, k);
+      const int bit = cid_bit(C, cid);
+      if (sl[k] < best || (sl[k] == best && bit < bbit)) { best = sl[k]; bcid = cid; bbit = bit; }
+    }
+  }
+}
+
 /* Active-set iterations on the reduced basis [eiquadprog-fast solve_quadprog, after the equality phase]. */
 TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, int lane, int mask, int nc, int n, int neq,
                        double c1c2, double R_norm, int& iters_out, uint64_t* act_words) {
@@ -1318,26 +1335,26 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
 #pragma unroll
     for (int k = 0; k < 6; k++) part += (sl[k] < 0.0) ? sl[k] : 0.0;
     exclbits = 0;
+    /* the violation sum (termination test) and the first pivot search are independent reductions: issue both
+     * before branching on the sum so that their latencies overlap */
+    double best;
+    int bcid, bbit;
+    pick_local(C, sl, actbits, exclbits, na, lane, best, bcid, bbit);
+    int src = warp_argmin(best, bcid >= 0, bbit);
     double psi = warp_sum(part);
     if (fabs(psi) <= psi_thresh) { status = ST_OPTIMAL; break; }
     /* save x, u, A */
     for (int k = lane; k < n; k += 32) xo[k] = x[k];
     if (lane < iq) { uo[lane] = u[lane]; Ao[lane] = A[lane]; }
     __syncwarp();
-    bool done = false, restart_l1 = false;
+    bool done = false, restart_l1 = false, first_pick = true;
     for (;;) { /* l2 */
       /* most violated row, lowest reference index on ties */
-      double best = 0.0;
-      int bcid = -1, bbit = 1 << 30;
-#pragma unroll
-      for (int k = 0; k < 6; k++) {
-        if (!((actbits >> k) & 1u) && !((exclbits >> k) & 1u) && sl[k] < 0.0) {
-          const int cid = cid_of(na, lane, k);
-          const int bit = cid_bit(C, cid);
-          if (sl[k] < best || (sl[k] == best && bit < bbit)) { best = sl[k]; bcid = cid; bbit = bit; }
-        }
+      if (!first_pick) {
+        pick_local(C, sl, actbits, exclbits, na, lane, best, bcid, bbit);
+        src = warp_argmin(best, bcid >= 0, bbit);
       }
-      const int src = warp_argmin(best, bcid >= 0, bbit);
+      first_pick = false;
       if (src < 0) { status = ST_OPTIMAL; done = true; break; }
       const int ip = __shfl_sync(FULL, bcid, src);
       double s_ip = shfl(best, src);
@@ -1359,21 +1376,20 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
         /* z = J2[:, iq:] d[iq:] (lanes over rows, 16-byte reads of the row and of d); zero if no free
          * direction is left */
         double z0 = 0.0, z1 = 0.0;
+        const bool h0 = lane < n, h1 = lane + 32 < n; /* this lane's two rows (an absent row reads row 0) */
+        const double2* Jr0 = reinterpret_cast<const double2*>(J2 + (h0 ? lane : 0) * SA_LDJ);
+        const double2* Jr1 = reinterpret_cast<const double2*>(J2 + (h1 ? lane + 32 : 0) * SA_LDJ);
         if (iq < m) {
           const int c0 = iq >> 1, c1 = (m + 1) >> 1;
           const double2* d2 = reinterpret_cast<const double2*>(dd);
-          if (lane < n) {
-            const double2* Jr = reinterpret_cast<const double2*>(J2 + lane * SA_LDJ);
-            double a0 = 0.0, a1 = 0.0;
-            for (int c = c0; c < c1; c++) { const double2 jv = Jr[c], dv = d2[c]; a0 += jv.x * dv.x; a1 += jv.y * dv.y; }
-            z0 = a0 + a1;
+          double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0; /* both rows in one loop: four independent chains */
+          for (int c = c0; c < c1; c++) {
+            const double2 j0 = Jr0[c], j1 = Jr1[c], dv = d2[c];
+            a0 += j0.x * dv.x; a1 += j0.y * dv.y;
+            b0 += j1.x * dv.x; b1 += j1.y * dv.y;
           }
-          if (lane + 32 < n) {
-            const double2* Jr = reinterpret_cast<const double2*>(J2 + (lane + 32) * SA_LDJ);
-            double a0 = 0.0, a1 = 0.0;
-            for (int c = c0; c < c1; c++) { const double2 jv = Jr[c], dv = d2[c]; a0 += jv.x * dv.x; a1 += jv.y * dv.y; }
-            z1 = a0 + a1;
-          }
+          z0 = h0 ? a0 + a1 : 0.0;
+          z1 = h1 ? b0 + b1 : 0.0;
         }
         /* r = R^-1 d[0:iq] (back substitution, lane <-> row) */
         {
@@ -1439,29 +1455,21 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
               /* v_c = d_c * scal (c > iq), v_iq = 1;  w_k = sum_c J2[k][c] v_c = (z_k - beta J2[k][iq]) * scal;
                * J2[k][c] -= tau w_k v_c: lanes over rows, 16-byte read-modify-write of the row */
               vv[lane] = (lane < iq || lane >= m) ? 0.0 : ((lane == iq) ? 1.0 : dl * scal);
-              const double w0 = (lane < n) ? tauh * (z0 - beta * J2[lane * SA_LDJ + iq]) * scal : 0.0;
-              const double w1 = (lane + 32 < n) ? tauh * (z1 - beta * J2[(lane + 32) * SA_LDJ + iq]) * scal : 0.0;
+              const double w0 = h0 ? tauh * (z0 - beta * J2[lane * SA_LDJ + iq]) * scal : 0.0;
+              const double w1 = h1 ? tauh * (z1 - beta * J2[(lane + 32) * SA_LDJ + iq]) * scal : 0.0;
               __syncwarp();
               {
                 const int c0 = iq >> 1, c1 = (m + 1) >> 1;
                 const double2* v2 = reinterpret_cast<const double2*>(vv);
-                if (lane < n) {
-                  double2* Jr = reinterpret_cast<double2*>(J2 + lane * SA_LDJ);
-                  for (int c = c0; c < c1; c++) {
-                    double2 jv = Jr[c];
-                    const double2 vc = v2[c];
-                    jv.x -= w0 * vc.x; jv.y -= w0 * vc.y;
-                    Jr[c] = jv;
-                  }
-                }
-                if (lane + 32 < n) {
-                  double2* Jr = reinterpret_cast<double2*>(J2 + (lane + 32) * SA_LDJ);
-                  for (int c = c0; c < c1; c++) {
-                    double2 jv = Jr[c];
-                    const double2 vc = v2[c];
-                    jv.x -= w1 * vc.x; jv.y -= w1 * vc.y;
-                    Jr[c] = jv;
-                  }
+                double2* W0 = const_cast<double2*>(Jr0);
+                double2* W1 = const_cast<double2*>(Jr1);
+                for (int c = c0; c < c1; c++) {
+                  const double2 vc = v2[c];
+                  double2 j0 = Jr0[c], j1 = Jr1[c];
+                  j0.x -= w0 * vc.x; j0.y -= w0 * vc.y;
+                  j1.x -= w1 * vc.x; j1.y -= w1 * vc.y;
+                  if (h0) W0[c] = j0;
+                  if (h1) W1[c] = j1;
                 }
               }
               /* new column of R: [d[0:iq]; beta] */
