@@ -189,6 +189,41 @@ int tsidb_integrate(tsidb_handle* h, int n_envs, int layout, double* q, double* 
 int tsidb_kinematics(tsidb_handle* h, int n_envs, int layout, const double* q,
                      const double* v, const tsidb_aux_out* aux, void* cuda_stream);
 
+/* ---- gait phase machine and closed-loop rollout on the device --------------------------------
+ * What the reference intends around update_tasks (ref:ctrl/WalkController.py:189-206; the call is commented out
+ * at ref:main.py:117) and never finishes (ref:ctrl/Walk_Planner.py:14-32 does not run): per-env gait phase,
+ * contact switching with the legacy semantics (ref:legacy/biped.py:168-212), swing-foot references with the
+ * FootTrajectory shape (ref:ctrl/Foot_Trajectory.py:8-19), CoM reference by LIPM Euler steps
+ * (ref:ctrl/LIPM.py:44-47).  State and references live in library-owned device arrays; see
+ * tsid_control_b200/csrc/tsidb_gait.cuh for the exact rules and tests/gait_ref.py for their numpy restatement. */
+typedef struct tsidb_gait_conf {
+  double dt;             /* conf.dt            ref:ctrl/conf.py:21 */
+  double step_duration;  /* conf.step_duration ref:ctrl/conf.py:27 (duration of one swing) */
+  double step_length;    /* conf.step_length   ref:ctrl/conf.py:26 */
+  double step_height;    /* conf.step_height   ref:ctrl/conf.py:24 */
+  double com_height;     /* LIPM h0            ref:ctrl/LIPM.py:6,15 */
+} tsidb_gait_conf;
+
+/* (re)start the gait of n_envs envs from the default references: phase0 [N] in [0,1) and vcmd [N][2] are DEVICE
+ * pointers (NULL = 0).  Asynchronous on cuda_stream except for one small synchronising upload. */
+int tsidb_gait_reset(tsidb_handle* h, int n_envs, const tsidb_gait_conf* conf, const double* phase0,
+                     const double* vcmd, void* cuda_stream);
+/* device pointers of the gait's references / contact mask / phase / failure counters (any out pointer may be NULL);
+ * valid until tsidb_destroy.  refs_out->posture is NULL (the default posture reference applies). */
+int tsidb_gait_state(tsidb_handle* h, tsidb_refs* refs_out, const uint8_t** mask_out, const double** phase_out,
+                     const int32_t** fails_out);
+/* advance the phase machine by one tick given the sole placements the tick measured (tsidb_aux_out.foot_*,
+ * [N][12] row-major device arrays) and its status (may be NULL). */
+int tsidb_gait_step(tsidb_handle* h, int n_envs, const double* foot_lf_now, const double* foot_rf_now,
+                    const int32_t* status, void* cuda_stream);
+/* n_steps x { tick with the gait's references and mask -> integrate_dv -> gait step } with no host round trip:
+ * the batched, closed-loop form of ref:main.py:110-128.  q, v ([N][nq], [N][nv], DEVICE, row-major) are
+ * advanced in place; tau/ddq/f/status/iters hold the last step's outputs.  use_graph != 0 captures the step in
+ * a CUDA graph and replays it (launch-bound small batches).  Returns after the last step has been enqueued
+ * (use_graph: after it has finished). */
+int tsidb_rollout(tsidb_handle* h, int n_envs, int n_steps, double* q, double* v, double* tau, double* ddq,
+                  double* f, int32_t* status, int32_t* iters, int use_graph, void* cuda_stream);
+
 /* canonical one-sided inequality row numbering used by active_set:
  *   block 0: LF force rows (17), block 1: RF force rows (17),
  *   block 2: actuation rows (na), block 3: joint-bound rows (nv)

@@ -6,6 +6,7 @@
 #include "../../tsid_control_b200/csrc/tsidb_host_const.h"
 static DevConst g_const[TSIDB_MAX_SLOTS];
 #include "../../tsid_control_b200/csrc/tsidb_kernels.cuh"
+#include "../../tsid_control_b200/csrc/tsidb_gait.cuh"
 
 namespace emu { Warp W; }
 
@@ -118,3 +119,17 @@ extern "C" int emu_tick(const TickArgs* a_in, double* sm_out) {
   return rc;
 }
 extern "C" int emu_sm_per_env() { return SA_PER_ENV > SE_PER_ENV ? SA_PER_ENV : SE_PER_ENV; }
+
+/* the gait phase machine of tsidb_gait.cuh, one env after the other: reset when defaults81 is given, else one step */
+extern "C" int emu_gait(int n, const double* gconf6, double* phi, uint8_t* mask, double* vcmd, double* lipm, double* origin,
+                        double* com, double* foot_lf, double* foot_rf, double* contact_lf, double* contact_rf, int32_t* fails,
+                        const double* defaults81, const double* phase0, const double* vcmd0, const double* foot_now_lf,
+                        const double* foot_now_rf, const int32_t* status) {
+  GaitConf G{gconf6[0], gconf6[1], gconf6[2], gconf6[3], gconf6[4], gconf6[5]};
+  GaitState S{phi, mask, vcmd, lipm, origin, com, {foot_lf, foot_rf}, {contact_lf, contact_rf}, fails};
+  for (int e = 0; e < n; e++) {
+    if (defaults81) gait_reset_env(G, S, defaults81, defaults81 + 9, defaults81 + 33, defaults81 + 57, defaults81 + 69, phase0, vcmd0, e);
+    else gait_step_env(G, S, foot_now_lf, foot_now_rf, status, e);
+  }
+  return 0;
+}

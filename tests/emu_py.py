@@ -31,7 +31,7 @@ class TickArgs(C.Structure):
 def build_emu() -> str:
     so = os.path.join(EMU_DIR, "libtsidb_emu.so")
     srcs = [os.path.join(EMU_DIR, "emu_main.cpp"), os.path.join(EMU_DIR, "emu_cuda.h")] + [
-        os.path.join(SRC_DIR, f) for f in ("tsidb_kernels.cuh", "tsidb_const.h", "tsidb_host_const.h")]
+        os.path.join(SRC_DIR, f) for f in ("tsidb_kernels.cuh", "tsidb_gait.cuh", "tsidb_const.h", "tsidb_host_const.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
                         "-o", so, os.path.join(EMU_DIR, "emu_main.cpp")], check=True)
@@ -103,3 +103,35 @@ def active_bits(words) -> list:
             if (val >> b) & 1:
                 bits.append(64 * w + b)
     return bits
+
+
+class EmuGait:
+    """Host build of the device gait phase machine (tsidb_gait.cuh via tests/emu): same state arrays as the
+    library keeps on the device."""
+
+    def __init__(self, n, dt, step_duration, step_length, step_height, com_height, defaults, phase0=None, vcmd=None):
+        self.lib = C.CDLL(build_emu())
+        self.n = n
+        self.g = np.array([dt, step_duration, step_length, step_height, 9.80665 / com_height, defaults["com"][2]], np.float64)
+        z = lambda *s: np.zeros(s, np.float64)
+        self.phi, self.mask, self.vcmd, self.lipm, self.origin = z(n), np.zeros(n, np.uint8), z(n, 2), z(n, 4), z(n, 24)
+        self.com, self.foot, self.contact = z(n, 9), [z(n, 24), z(n, 24)], [z(n, 12), z(n, 12)]
+        self.fails = np.zeros(n, np.int32)
+        d = np.concatenate([defaults["com"], defaults["foot_lf"], defaults["foot_rf"], defaults["contact_lf"], defaults["contact_rf"]]).astype(np.float64)
+        p0 = None if phase0 is None else np.ascontiguousarray(phase0, np.float64)
+        vc = None if vcmd is None else np.ascontiguousarray(vcmd, np.float64)
+        self._call(d, p0, vc, None, None, None)
+
+    def _call(self, d, p0, vc, fl, fr, st):
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        self.lib.emu_gait.argtypes = [C.c_int] + [C.c_void_p] * 18
+        rc = self.lib.emu_gait(self.n, ptr(self.g), ptr(self.phi), ptr(self.mask), ptr(self.vcmd), ptr(self.lipm), ptr(self.origin),
+                               ptr(self.com), ptr(self.foot[0]), ptr(self.foot[1]), ptr(self.contact[0]), ptr(self.contact[1]),
+                               ptr(self.fails), ptr(d), ptr(p0), ptr(vc), ptr(fl), ptr(fr), ptr(st))
+        assert rc == 0
+
+    def step(self, foot_now_lf, foot_now_rf, status=None):
+        fl = np.ascontiguousarray(foot_now_lf, np.float64)
+        fr = np.ascontiguousarray(foot_now_rf, np.float64)
+        st = None if status is None else np.ascontiguousarray(status, np.int32)
+        self._call(None, None, None, fl, fr, st)

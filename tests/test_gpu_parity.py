@@ -260,6 +260,53 @@ def test_chunked_host_call_agrees_with_device_call(n, pinned):
     assert np.array_equal(h["active_set"].astype(np.int64), base["active_set"])
 
 
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_device_rollout_matches_host_driven_loop(use_graph):
+    """tsidb_rollout (tick -> integrate -> gait step, no host round trip, optionally one CUDA graph replayed) against
+    the same loop driven from the host with the numpy gait restatement (tests/gait_ref.py)."""
+    from gait_ref import GaitRef
+
+    s = setup("v1")
+    n, steps = 96, 40
+    ctrl = _controller("v1", n)
+    e = ctrl.engine
+    dev = e.device
+    conf = s["conf"]
+    rng = np.random.Generator(np.random.PCG64(31))
+    q, v = synth.random_states(s["q0"], n, 15)
+    v *= 0.2
+    phase0 = rng.uniform(0, 1, n)
+    vcmd = np.c_[rng.uniform(-0.3, 0.3, n), rng.uniform(-0.1, 0.1, n)]
+    h0 = float(ctrl.default_refs["com"][2])
+    gait = dict(dt=conf.dt, step_duration=conf.step_duration, step_length=conf.step_length, step_height=conf.step_height, com_height=h0)
+    # device
+    e.gait_reset(n, phase0=torch.as_tensor(phase0, device=dev), vcmd=torch.as_tensor(vcmd, device=dev), **gait)
+    qd, vd = torch.as_tensor(q, device=dev).clone(), torch.as_tensor(v, device=dev).clone()
+    out = e.rollout(qd, vd, steps, use_graph=use_graph)
+    torch.cuda.synchronize()
+    gs = {k: t.cpu().numpy().copy() for k, t in e.gait_state().items()}
+    # host-driven
+    g = GaitRef(n, defaults=ctrl.default_refs, phase0=phase0, vcmd=vcmd, **gait)
+    qh, vh = torch.as_tensor(q, device=dev).clone(), torch.as_tensor(v, device=dev).clone()
+    post = torch.as_tensor(np.tile(ctrl.default_refs["posture"], (n, 1)), device=dev)
+    for _ in range(steps):
+        refs = {k: torch.as_tensor(np.ascontiguousarray(a), device=dev) for k, a in g.refs().items()}
+        refs["posture"] = post
+        o = e.compute(qh, vh, torch.as_tensor(g.mask, device=dev), refs, aux=True)
+        e.integrate(qh, vh, o.ddq, conf.dt)
+        g.step(o.foot_lf.cpu().numpy(), o.foot_rf.cpu().numpy(), o.status.cpu().numpy())
+    torch.cuda.synchronize()
+    assert np.array_equal(gs["mask"], g.mask) and np.array_equal(gs["fails"], g.fails)
+    assert len(set(int(m) for m in g.mask)) == 3  # all three contact classes are present
+    ok = g.fails == 0
+    assert ok.mean() > 0.9
+    assert np.abs(qd.cpu().numpy()[ok] - qh.cpu().numpy()[ok]).max() < 1e-8
+    assert np.abs(vd.cpu().numpy()[ok] - vh.cpu().numpy()[ok]).max() < 1e-6
+    for k in ("com", "foot_lf", "foot_rf", "contact_lf", "contact_rf"):
+        assert np.abs(gs[k][ok] - g.refs()[k][ok]).max() < 1e-8, k
+    assert np.abs(out.tau.cpu().numpy()[ok] - o.tau.cpu().numpy()[ok]).max() < 1e-5
+
+
 def test_integrate_matches_oracle():
     s = setup("v1")
     n = 64

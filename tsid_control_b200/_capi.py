@@ -84,6 +84,11 @@ class TsidbRefs(C.Structure):
     ]
 
 
+class TsidbGaitConf(C.Structure):
+    _fields_ = [("dt", C.c_double), ("step_duration", C.c_double), ("step_length", C.c_double),
+                ("step_height", C.c_double), ("com_height", C.c_double)]
+
+
 class TsidbAuxOut(C.Structure):
     _fields_ = [
         ("com", C.c_void_p),
@@ -228,6 +233,14 @@ def load_library() -> C.CDLL:
     lib.tsidb_set_timing.restype = ip
     lib.tsidb_last_tick_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.tsidb_last_tick_ms.restype = ip
+    lib.tsidb_gait_reset.argtypes = [vp, ip, C.POINTER(TsidbGaitConf), vp, vp, vp]
+    lib.tsidb_gait_reset.restype = ip
+    lib.tsidb_gait_state.argtypes = [vp, C.POINTER(TsidbRefs), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.tsidb_gait_state.restype = ip
+    lib.tsidb_gait_step.argtypes = [vp, ip, vp, vp, vp, vp]
+    lib.tsidb_gait_step.restype = ip
+    lib.tsidb_rollout.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp, ip, vp]
+    lib.tsidb_rollout.restype = ip
     _LIB = lib
     return lib
 
@@ -242,4 +255,5 @@ EXPORTED_SYMBOLS = [
     "tsidb_create", "tsidb_destroy", "tsidb_last_error", "tsidb_sizes", "tsidb_set_default_refs",
     "tsidb_compute", "tsidb_compute_host", "tsidb_integrate", "tsidb_kinematics", "tsidb_ci_row",
     "tsidb_fp64_peak", "tsidb_launch_count", "tsidb_set_timing", "tsidb_last_tick_ms",
+    "tsidb_gait_reset", "tsidb_gait_state", "tsidb_gait_step", "tsidb_rollout",
 ]

@@ -84,6 +84,23 @@ class BatchedController:
         out = self._tick(q, v)
         return out.tau, out.ddq, out.f
 
+    def rollout(self, q: torch.Tensor, v: torch.Tensor, n_steps: int, phase0: Optional[torch.Tensor] = None,
+                vcmd: Optional[torch.Tensor] = None, restart: bool = False, use_graph: bool = True):
+        """Closed-loop batched form of the reference's loop (ref:main.py:110-128) with the walking references it
+        never wires in (ref:main.py:117): n_steps x {tick, integrate_dv, gait phase machine} on the device, no host
+        round trip.  q [N,nq] and v [N,nv] are advanced in place; returns (tau, ddq, f_contact) of the last step.
+        The gait is (re)started from the controller's default references on the first call or with restart=True,
+        with per-env phase0 [N] in [0,1) and velocity command vcmd [N,2]; gait parameters come from conf
+        (dt, step_duration, step_length, step_height; LIPM height = reference CoM height)."""
+        if restart or not getattr(self, "_gait_started", False):
+            c = self.conf
+            self.engine.gait_reset(self.n_envs, float(c.dt), float(getattr(c, "step_duration", 0.5)),
+                                   float(getattr(c, "step_length", 0.1)), float(getattr(c, "step_height", 0.05)),
+                                   float(self.default_refs["com"][2]), phase0, vcmd)
+            self._gait_started = True
+        self.last = self.engine.rollout(q, v, n_steps, use_graph=use_graph)
+        return self.last.tau, self.last.ddq, self.last.f
+
     # ------------------------------------------------------------------ references
     def _set_task_reference(self, key: str, sample) -> None:
         if key == "am":

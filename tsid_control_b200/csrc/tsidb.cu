@@ -11,6 +11,7 @@
 #include "../../include/tsidb.h"
 #include "tsidb_host_const.h"
 #include "tsidb_kernels.cuh"
+#include "tsidb_gait.cuh"
 
 static thread_local std::string g_err;
 static std::mutex g_slot_mu;
@@ -47,6 +48,12 @@ struct tsidb_handle {
   int32_t *h_int, *d_int;    /* status, iters */
   uint64_t *h_act, *d_act;
   cudaStream_t stream[TSIDB_HOST_STREAMS];
+  /* gait phase machine (tsidb_gait_*): state and references, allocated at the first tsidb_gait_reset */
+  GaitConf gconf;
+  GaitState gait;
+  double* g_foot_now[2];   /* sole placements measured by the last tick of a rollout, [N][12] */
+  double* g_defaults;      /* device copy of the default references: com 9, feet 2x24, contacts 2x12 */
+  int gait_ready;
 };
 
 /* ------------------------------------------------------------------ small kernels */
@@ -241,6 +248,12 @@ extern "C" void tsidb_destroy(tsidb_handle* h) {
     if (h->stream[i]) cudaStreamDestroy(h->stream[i]);
   for (int i = 0; i < 6; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->gait_ready) {
+    cudaFree(h->gait.phi); cudaFree(h->gait.mask); cudaFree(h->gait.vcmd); cudaFree(h->gait.lipm); cudaFree(h->gait.origin);
+    cudaFree(h->gait.com); cudaFree(h->gait.foot[0]); cudaFree(h->gait.foot[1]); cudaFree(h->gait.contact[0]);
+    cudaFree(h->gait.contact[1]); cudaFree(h->gait.fails); cudaFree(h->g_foot_now[0]); cudaFree(h->g_foot_now[1]);
+    cudaFree(h->g_defaults);
+  }
   {
     std::lock_guard<std::mutex> lk(g_slot_mu);
     if (h->slot >= 0) g_slot_used[h->device][h->slot] = false;
@@ -491,6 +504,145 @@ extern "C" int tsidb_integrate(tsidb_handle* h, int n_envs, int layout, double* 
       n_envs, layout, h->dc.na, q, v, dv, dt);
   CK(cudaGetLastError());
   h->launches += 1;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ gait phase machine and closed-loop rollout */
+static int gait_alloc(tsidb_handle* h) {
+  if (h->gait_ready) return 0;
+  const size_t N = (size_t)h->max_envs;
+  CK(cudaMalloc(&h->gait.phi, N * sizeof(double)));
+  CK(cudaMalloc(&h->gait.mask, N));
+  CK(cudaMalloc(&h->gait.vcmd, 2 * N * sizeof(double)));
+  CK(cudaMalloc(&h->gait.lipm, 4 * N * sizeof(double)));
+  CK(cudaMalloc(&h->gait.origin, 24 * N * sizeof(double)));
+  CK(cudaMalloc(&h->gait.com, 9 * N * sizeof(double)));
+  for (int f = 0; f < 2; f++) {
+    CK(cudaMalloc(&h->gait.foot[f], 24 * N * sizeof(double)));
+    CK(cudaMalloc(&h->gait.contact[f], 12 * N * sizeof(double)));
+    CK(cudaMalloc(&h->g_foot_now[f], 12 * N * sizeof(double)));
+  }
+  CK(cudaMalloc(&h->gait.fails, N * sizeof(int32_t)));
+  CK(cudaMalloc(&h->g_defaults, 81 * sizeof(double)));
+  h->gait_ready = 1;
+  return 0;
+}
+
+extern "C" int tsidb_gait_reset(tsidb_handle* h, int n_envs, const tsidb_gait_conf* gc, const double* phase0, const double* vcmd,
+                                void* cuda_stream) {
+  if (!h || !gc) { g_err = "tsidb_gait_reset: null argument"; return -1; }
+  if (n_envs <= 0 || n_envs > h->max_envs) { g_err = "tsidb_gait_reset: n_envs exceeds the handle's max_envs"; return -1; }
+  if (!(gc->dt > 0) || !(gc->step_duration > 0) || !(gc->com_height > 0)) { g_err = "tsidb_gait_reset: dt, step_duration and com_height must be positive"; return -1; }
+  CK(cudaSetDevice(h->device));
+  if (gait_alloc(h)) return -2;
+  h->gconf.dt = gc->dt; h->gconf.step_duration = gc->step_duration; h->gconf.step_length = gc->step_length;
+  h->gconf.step_height = gc->step_height; h->gconf.w2 = 9.80665 / gc->com_height; /* ref:ctrl/LIPM.py:15 */
+  h->gconf.com_z = h->dc.ref_com[2];
+  double d[81];
+  memcpy(d, h->dc.ref_com, 9 * sizeof(double));
+  memcpy(d + 9, h->dc.ref_foot[0], 24 * sizeof(double));
+  memcpy(d + 33, h->dc.ref_foot[1], 24 * sizeof(double));
+  memcpy(d + 57, h->dc.ref_contact[0], 12 * sizeof(double));
+  memcpy(d + 69, h->dc.ref_contact[1], 12 * sizeof(double));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CK(cudaMemcpyAsync(h->g_defaults, d, sizeof d, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st)); /* d is a stack buffer */
+  const int th = 128;
+  tsidb_gait_reset_kernel<<<(n_envs + th - 1) / th, th, 0, st>>>(n_envs, h->gconf, h->gait, h->g_defaults, phase0, vcmd);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+extern "C" int tsidb_gait_state(tsidb_handle* h, tsidb_refs* refs_out, const uint8_t** mask_out, const double** phase_out,
+                                const int32_t** fails_out) {
+  if (!h || !h->gait_ready) { g_err = "tsidb_gait_state: call tsidb_gait_reset first"; return -1; }
+  if (refs_out) {
+    refs_out->com = h->gait.com; refs_out->foot_lf = h->gait.foot[0]; refs_out->foot_rf = h->gait.foot[1];
+    refs_out->contact_lf = h->gait.contact[0]; refs_out->contact_rf = h->gait.contact[1]; refs_out->posture = nullptr;
+  }
+  if (mask_out) *mask_out = h->gait.mask;
+  if (phase_out) *phase_out = h->gait.phi;
+  if (fails_out) *fails_out = h->gait.fails;
+  return 0;
+}
+
+extern "C" int tsidb_gait_step(tsidb_handle* h, int n_envs, const double* foot_lf_now, const double* foot_rf_now,
+                               const int32_t* status, void* cuda_stream) {
+  if (!h || !h->gait_ready) { g_err = "tsidb_gait_step: call tsidb_gait_reset first"; return -1; }
+  if (!foot_lf_now || !foot_rf_now) { g_err = "tsidb_gait_step: null foot placements"; return -1; }
+  if (n_envs <= 0 || n_envs > h->max_envs) { g_err = "tsidb_gait_step: bad n_envs"; return -1; }
+  CK(cudaSetDevice(h->device));
+  const int th = 128;
+  tsidb_gait_step_kernel<<<(n_envs + th - 1) / th, th, 0, (cudaStream_t)cuda_stream>>>(n_envs, h->gconf, h->gait, foot_lf_now,
+                                                                                         foot_rf_now, status);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+/* one closed-loop step on stream st: tick with the gait's references -> integrate -> phase machine */
+static int rollout_step(tsidb_handle* h, int n, double* q, double* v, double* tau, double* ddq, double* f, int32_t* status,
+                        int32_t* iters, cudaStream_t st) {
+  TickArgs a;
+  memset(&a, 0, sizeof a);
+  a.n_envs = n; a.layout = 0; a.q = q; a.v = v; a.mask = h->gait.mask;
+  a.r_com = h->gait.com; a.r_foot[0] = h->gait.foot[0]; a.r_foot[1] = h->gait.foot[1];
+  a.r_contact[0] = h->gait.contact[0]; a.r_contact[1] = h->gait.contact[1];
+  a.tau = tau; a.ddq = ddq; a.f = f; a.status = status; a.iters = iters;
+  a.o_foot[0] = h->g_foot_now[0]; a.o_foot[1] = h->g_foot_now[1];
+  int rc = launch_tick(h, a, st);
+  if (rc) return rc;
+  const int th = 128;
+  tsidb_integrate_kernel<<<(n + th - 1) / th, th, 0, st>>>(n, 0, h->dc.na, q, v, ddq, h->gconf.dt);
+  tsidb_gait_step_kernel<<<(n + th - 1) / th, th, 0, st>>>(n, h->gconf, h->gait, h->g_foot_now[0], h->g_foot_now[1], status);
+  CK(cudaGetLastError());
+  h->launches += 2;
+  return 0;
+}
+
+extern "C" int tsidb_rollout(tsidb_handle* h, int n_envs, int n_steps, double* q, double* v, double* tau, double* ddq, double* f,
+                             int32_t* status, int32_t* iters, int use_graph, void* cuda_stream) {
+  if (!h || !q || !v || !tau || !ddq || !f || !status || !iters) { g_err = "tsidb_rollout: null argument"; return -1; }
+  if (!h->gait_ready) { g_err = "tsidb_rollout: call tsidb_gait_reset first"; return -1; }
+  if (n_envs <= 0 || n_envs > h->max_envs || n_steps < 0) { g_err = "tsidb_rollout: bad n_envs / n_steps"; return -1; }
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (!use_graph || n_steps < 2) {
+    for (int k = 0; k < n_steps; k++) {
+      int rc = rollout_step(h, n_envs, q, v, tau, ddq, f, status, iters, st);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  /* the step is the same every time (all state lives in device memory): capture it once, replay it */
+  cudaStream_t cap = st;
+  bool own = false;
+  if (!cap) { CK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking)); own = true; } /* the legacy stream cannot be captured */
+  const int timing = h->timing;
+  h->timing = 0;
+  const int64_t l0 = h->launches;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  CK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+  int rc = rollout_step(h, n_envs, q, v, tau, ddq, f, status, iters, cap);
+  cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+  h->timing = timing;
+  if (rc || ce != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    if (own) cudaStreamDestroy(cap);
+    if (!rc) { g_err = std::string("tsidb_rollout: stream capture failed: ") + cudaGetErrorString(ce); rc = -2; }
+    return rc;
+  }
+  const int64_t per_step = h->launches - l0;
+  CK(cudaGraphInstantiate(&exec, graph, 0));
+  for (int k = 0; k < n_steps; k++) CK(cudaGraphLaunch(exec, cap));
+  h->launches = l0 + per_step * n_steps;
+  if (own) CK(cudaStreamSynchronize(cap));
+  else { /* exec must outlive its launches */ CK(cudaStreamSynchronize(cap)); }
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  if (own) cudaStreamDestroy(cap);
   return 0;
 }
 

@@ -1,0 +1,141 @@
+/* tsidb_gait.cuh — per-env gait phase machine and reference generator on the device (one thread per env).
+ *
+ * The reference keeps this logic on the host and never wires it into its loop (`update_tasks` is commented
+ * out at ref:main.py:117); the pieces it is made of are restated here so that closed-loop batched rollouts
+ * need no host round trip:
+ *   - contact switching with the legacy semantics: on lift-off the foot-task reference becomes the current
+ *     foot placement, on touch-down the contact reference becomes the current placement
+ *     (ref:legacy/biped.py:168-212; the WalkController versions at ref:ctrl/WalkController.py:215-253 raise);
+ *   - swing foot: x linear in time, z the parabola through (0,0), (T/2,h), (T,0) — the 2-knot and 3-knot
+ *     CubicSplines of ref:ctrl/Foot_Trajectory.py:8-19 with rise_ratio 0.5 — with first and second derivatives
+ *     as velocity and acceleration references;
+ *   - CoM: one semi-implicit Euler step of the linear inverted pendulum per tick,
+ *     acc = (zmp - pos) w^2; vel += acc dt; pos += vel dt  (ref:ctrl/LIPM.py:44-47, w^2 = 9.80665/h0 at :15),
+ *     with the ZMP at the centre of the support (both contact references in double support, the stance one
+ *     in single support);
+ *   - gait cycle as in the benchmark workload: phase in [0,1): [0,0.2) double support,
+ *     [0.2,0.6) left foot in contact / right foot swinging, [0.6,1) right in contact / left swinging; one
+ *     swing lasts step_duration, so the phase advances by 0.4 dt / step_duration per tick.
+ * tests/gait_ref.py is the numpy restatement these functions are checked against.
+ * Compiles for the host under tests/emu (TSIDB_EMU). */
+#ifndef TSIDB_GAIT_CUH_
+#define TSIDB_GAIT_CUH_
+#include <stdint.h>
+
+#ifndef TSIDB_DEV
+#define TSIDB_DEV __device__ __forceinline__
+#endif
+
+struct GaitConf {
+  double dt, step_duration, step_length, step_height, w2, com_z;
+};
+
+/* device arrays, [N][k] row-major */
+struct GaitState {
+  double* phi;        /* [N]       gait phase                                   */
+  uint8_t* mask;      /* [N]       contact mask of the tick about to run        */
+  double* vcmd;       /* [N][2]    velocity command                             */
+  double* lipm;       /* [N][4]    pendulum position xy, velocity xy            */
+  double* origin;     /* [N][2][12] placement of each foot at its last lift-off */
+  double* com;        /* [N][9]    references handed to the tick ...            */
+  double* foot[2];    /* [N][24]                                                */
+  double* contact[2]; /* [N][12]                                                */
+  int32_t* fails;     /* [N]       ticks whose QP did not reach status 0        */
+};
+
+TSIDB_DEV int gait_mask_of(double phi) { return phi < 0.2 ? 3 : (phi < 0.6 ? 1 : 2); }
+
+/* state of env e at reset: standing references, pendulum at the standing CoM moving with the command */
+TSIDB_DEV void gait_reset_env(const GaitConf& G, const GaitState& S, const double* com9, const double* foot_lf24,
+                              const double* foot_rf24, const double* contact_lf12, const double* contact_rf12,
+                              const double* phase0, const double* vcmd, int e) {
+  const double phi = phase0 ? phase0[e] : 0.0;
+  S.phi[e] = phi;
+  S.mask[e] = (uint8_t)gait_mask_of(phi);
+  const double vx = vcmd ? vcmd[2 * e] : 0.0, vy = vcmd ? vcmd[2 * e + 1] : 0.0;
+  S.vcmd[2 * e] = vx; S.vcmd[2 * e + 1] = vy;
+  S.lipm[4 * e] = com9[0]; S.lipm[4 * e + 1] = com9[1]; S.lipm[4 * e + 2] = vx; S.lipm[4 * e + 3] = vy;
+  for (int k = 0; k < 9; k++) S.com[9 * e + k] = com9[k];
+  S.com[9 * e + 3] = vx; S.com[9 * e + 4] = vy;
+  for (int k = 0; k < 24; k++) { S.foot[0][24 * e + k] = foot_lf24[k]; S.foot[1][24 * e + k] = foot_rf24[k]; }
+  for (int k = 0; k < 12; k++) {
+    S.contact[0][12 * e + k] = contact_lf12[k]; S.contact[1][12 * e + k] = contact_rf12[k];
+    S.origin[24 * e + k] = foot_lf24[k]; S.origin[24 * e + 12 + k] = foot_rf24[k];
+  }
+  if (S.fails) S.fails[e] = 0;
+}
+
+/* one tick of the phase machine for env e; foot_now[f] = placements (p, R column-major) measured by the tick
+ * that just ran, status = its QP status (may be null) */
+TSIDB_DEV void gait_step_env(const GaitConf& G, const GaitState& S, const double* foot_now_lf, const double* foot_now_rf,
+                             const int32_t* status, int e) {
+  double phi = S.phi[e] + 0.4 * G.dt / G.step_duration;
+  if (phi >= 1.0) phi -= 1.0;
+  const int old = S.mask[e];
+  const int nm = gait_mask_of(phi);
+  const double T = G.step_duration, h = G.step_height;
+  const double L = (S.vcmd[2 * e] >= 0.0) ? G.step_length : -G.step_length;
+#pragma unroll
+  for (int f = 0; f < 2; f++) {
+    const int bit = 1 << f;
+    const double* now = (f == 0 ? foot_now_lf : foot_now_rf) + 12 * (size_t)e;
+    double* org = S.origin + 24 * (size_t)e + 12 * f;
+    double* fr = S.foot[f] + 24 * (size_t)e;
+    double* cr = S.contact[f] + 12 * (size_t)e;
+    if ((old & bit) && !(nm & bit)) {
+      /* lift-off [Biped.remove*FootContact]: the swing starts from where the foot is */
+      for (int k = 0; k < 12; k++) org[k] = now[k];
+    }
+    if (!(old & bit) && (nm & bit)) {
+      /* touch-down [Biped.add*FootContact]: contact (and foot task) reference := current placement */
+      for (int k = 0; k < 12; k++) { cr[k] = now[k]; fr[k] = now[k]; }
+      for (int k = 12; k < 24; k++) fr[k] = 0.0;
+    }
+    if (!(nm & bit)) {
+      /* swinging [FootTrajectory]: right foot swings in [0.2,0.6), left foot in [0.6,1) */
+      const double s = (phi - (f == 1 ? 0.2 : 0.6)) / 0.4;
+      fr[0] = org[0] + L * s;
+      fr[1] = org[1];
+      fr[2] = org[2] + 4.0 * h * s * (1.0 - s);
+      for (int k = 3; k < 12; k++) fr[k] = org[k];
+      for (int k = 12; k < 24; k++) fr[k] = 0.0;
+      fr[12] = L / T;
+      fr[14] = 4.0 * h * (1.0 - 2.0 * s) / T;
+      fr[20] = -8.0 * h / (T * T);
+    }
+  }
+  /* LIPM step towards the centre of the support */
+  const double* cl = S.contact[0] + 12 * (size_t)e;
+  const double* cr_ = S.contact[1] + 12 * (size_t)e;
+  double zx, zy;
+  if (nm == 3) { zx = 0.5 * (cl[0] + cr_[0]); zy = 0.5 * (cl[1] + cr_[1]); }
+  else if (nm == 1) { zx = cl[0]; zy = cl[1]; }
+  else { zx = cr_[0]; zy = cr_[1]; }
+  double* lp = S.lipm + 4 * (size_t)e;
+  const double ax = (zx - lp[0]) * G.w2, ay = (zy - lp[1]) * G.w2;
+  lp[2] += ax * G.dt; lp[3] += ay * G.dt;
+  lp[0] += lp[2] * G.dt; lp[1] += lp[3] * G.dt;
+  double* c = S.com + 9 * (size_t)e;
+  c[0] = lp[0]; c[1] = lp[1]; c[2] = G.com_z;
+  c[3] = lp[2]; c[4] = lp[3]; c[5] = 0.0;
+  c[6] = ax; c[7] = ay; c[8] = 0.0;
+  S.phi[e] = phi;
+  S.mask[e] = (uint8_t)nm;
+  if (S.fails && status && status[e] != 0) S.fails[e] += 1;
+}
+
+#ifndef TSIDB_EMU
+__global__ void tsidb_gait_reset_kernel(int n, GaitConf G, GaitState S, const double* defaults /* 9+24+24+12+12 */,
+                                        const double* phase0, const double* vcmd) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  gait_reset_env(G, S, defaults, defaults + 9, defaults + 33, defaults + 57, defaults + 69, phase0, vcmd, e);
+}
+__global__ void tsidb_gait_step_kernel(int n, GaitConf G, GaitState S, const double* foot_now_lf, const double* foot_now_rf,
+                                       const int32_t* status) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  gait_step_env(G, S, foot_now_lf, foot_now_rf, status, e);
+}
+#endif
+#endif

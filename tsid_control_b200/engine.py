@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._capi import TsidbAuxOut, TsidbRefs, check, conf_to_c, load_library, model_to_c
+from ._capi import TsidbAuxOut, TsidbGaitConf, TsidbRefs, check, conf_to_c, load_library, model_to_c
 from .model_compiler import CompiledModel
 
 REF_KEYS = ("com", "foot_lf", "foot_rf", "contact_lf", "contact_rf", "posture")
@@ -196,6 +196,62 @@ class TsidEngine:
         self._chk(dv, n, self.nv, "dv")
         check(self.lib.tsidb_integrate(self.h, n, 0, q.data_ptr(), v.data_ptr(), dv.data_ptr(), float(dt), self._stream()),
               "tsidb_integrate")
+
+    # ------------------------------------------------------------------ gait phase machine / closed-loop rollout
+    def gait_reset(self, n: int, dt: float, step_duration: float, step_length: float, step_height: float, com_height: float,
+                   phase0: Optional[torch.Tensor] = None, vcmd: Optional[torch.Tensor] = None) -> None:
+        """(Re)start the device gait of n envs from the default references (tsidb_gait_reset).  phase0 [n] in
+        [0,1) and vcmd [n,2] are CUDA fp64 tensors (None = zeros)."""
+        gc = TsidbGaitConf(float(dt), float(step_duration), float(step_length), float(step_height), float(com_height))
+        if phase0 is not None:
+            self._chk(phase0.reshape(n, 1), n, 1, "phase0")
+        if vcmd is not None:
+            self._chk(vcmd, n, 2, "vcmd")
+        self._gait_n = n
+        check(self.lib.tsidb_gait_reset(self.h, n, C.byref(gc), phase0.data_ptr() if phase0 is not None else None,
+                                        vcmd.data_ptr() if vcmd is not None else None, self._stream()), "tsidb_gait_reset")
+
+    def _view(self, ptr: int, shape, dtype: torch.dtype) -> torch.Tensor:
+        """A torch view of a library-owned device array (no copy)."""
+        np_dt = {torch.float64: "<f8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": tuple(shape), "typestr": np_dt, "data": (int(ptr), False), "version": 2}
+
+        return torch.as_tensor(_Arr(), device=self.device)
+
+    def gait_state(self) -> Dict[str, torch.Tensor]:
+        """Views of the gait's device state: references (com, foot_lf, foot_rf, contact_lf, contact_rf), mask,
+        phase and the per-env count of failed ticks."""
+        n = self._gait_n
+        r = TsidbRefs()
+        m, ph, fl = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(self.lib.tsidb_gait_state(self.h, C.byref(r), C.byref(m), C.byref(ph), C.byref(fl)), "tsidb_gait_state")
+        out = {k: self._view(getattr(r, k), (n, nd), torch.float64)
+               for k, nd in (("com", 9), ("foot_lf", 24), ("foot_rf", 24), ("contact_lf", 12), ("contact_rf", 12))}
+        out["mask"] = self._view(m.value, (n,), torch.uint8)
+        out["phase"] = self._view(ph.value, (n,), torch.float64)
+        out["fails"] = self._view(fl.value, (n,), torch.int32)
+        return out
+
+    def gait_step(self, foot_lf_now: torch.Tensor, foot_rf_now: torch.Tensor, status: Optional[torch.Tensor] = None) -> None:
+        n = self._gait_n
+        self._chk(foot_lf_now, n, 12, "foot_lf_now")
+        self._chk(foot_rf_now, n, 12, "foot_rf_now")
+        check(self.lib.tsidb_gait_step(self.h, n, foot_lf_now.data_ptr(), foot_rf_now.data_ptr(),
+                                       status.data_ptr() if status is not None else None, self._stream()), "tsidb_gait_step")
+
+    def rollout(self, q: torch.Tensor, v: torch.Tensor, n_steps: int, use_graph: bool = True) -> TickOutput:
+        """n_steps closed-loop ticks on the device (tick -> integrate_dv -> gait step), q and v advanced in place;
+        returns the last step's outputs.  Needs gait_reset first."""
+        n = q.shape[0]
+        self._chk(q, n, self.nq, "q")
+        self._chk(v, n, self.nv, "v")
+        o = self._outputs(n, False)
+        check(self.lib.tsidb_rollout(self.h, n, int(n_steps), q.data_ptr(), v.data_ptr(), o["tau"].data_ptr(), o["ddq"].data_ptr(),
+                                     o["f"].data_ptr(), o["status"].data_ptr(), o["iters"].data_ptr(), int(use_graph),
+                                     self._stream()), "tsidb_rollout")
+        return TickOutput(**{k: o[k] for k in TickOutput.__slots__})
 
     def ci_row(self, block: int, side: int, i: int) -> int:
         return int(self.lib.tsidb_ci_row(self.h, block, side, i))
