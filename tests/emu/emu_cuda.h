@@ -17,6 +17,7 @@
 #define TSIDB_EMU 1
 #define TSIDB_DEV static inline
 #define TSIDB_DEVNI static
+#define TSIDB_HD
 
 namespace emu {
 struct Warp {

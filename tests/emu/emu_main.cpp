@@ -37,7 +37,17 @@ static void lane_entry(int lane) {
     else j2_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
   } else {
     unsigned parity = 0;
-    activeset_env(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
+    const int m = g_job.a->mask ? (((const uint8_t*)g_job.a->mask)[g_job.env] & 3) : 3;
+    const int nc = (m & 1) + ((m >> 1) & 1);
+    if (g_job.C->nv == 26) {
+      if (nc == 2) activeset_env<26, 2>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
+      else if (nc == 1) activeset_env<26, 1>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
+      else activeset_env<26, 0>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
+    } else {
+      if (nc == 2) activeset_env<24, 2>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
+      else if (nc == 1) activeset_env<24, 1>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
+      else activeset_env<24, 0>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
+    }
   }
   emu::W.done[lane] = true;
   swapcontext(&emu::W.ctx[lane], &emu::W.sched);
@@ -94,7 +104,7 @@ extern "C" int emu_tick(const TickArgs* a_in, double* sm_out) {
   emu::Warp& W = emu::W;
   if (!W.stacks) W.stacks = (char*)malloc(32 * STK);
   TickArgs a = *a_in;
-  const int smn = SA_PER_ENV > SE_PER_ENV ? SA_PER_ENV : SE_PER_ENV;
+  const int smn = a_layout(TSIDB_NVX, 2).per_env > SE_PER_ENV ? a_layout(TSIDB_NVX, 2).per_env : SE_PER_ENV;
   double* sm = (double*)calloc(smn, sizeof(double));
   double* ws = (double*)calloc((size_t)a.n_envs * SA_IMAGE, sizeof(double));
   double* ws2 = (double*)calloc((size_t)a.n_envs * SG_IMAGE, sizeof(double));
@@ -111,14 +121,14 @@ extern "C" int emu_tick(const TickArgs* a_in, double* sm_out) {
       rc = run_warp(env);
     }
   }
-  if (sm_out) memcpy(sm_out, sm, SA_PER_ENV * sizeof(double));
+  if (sm_out) memcpy(sm_out, sm, smn * sizeof(double));
   free(sm);
   free(ws);
   free(ws2);
   free(ws3);
   return rc;
 }
-extern "C" int emu_sm_per_env() { return SA_PER_ENV > SE_PER_ENV ? SA_PER_ENV : SE_PER_ENV; }
+extern "C" int emu_sm_per_env() { return a_layout(TSIDB_NVX, 2).per_env > SE_PER_ENV ? a_layout(TSIDB_NVX, 2).per_env : SE_PER_ENV; }
 
 /* the gait phase machine of tsidb_gait.cuh, one env after the other: reset when defaults81 is given, else one step */
 extern "C" int emu_gait(int n, const double* gconf6, double* phi, uint8_t* mask, double* vcmd, double* lipm, double* origin,

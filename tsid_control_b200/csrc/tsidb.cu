@@ -32,7 +32,7 @@ static bool g_slot_used[8][TSIDB_MAX_SLOTS]; /* per device */
 struct tsidb_handle {
   int device, slot, max_envs, sm_count;
   DevConst dc;
-  int32_t* counter;      /* device: [0] work counter of the active-set kernel, [1..3] class counts */
+  int32_t* counter;      /* device, 8 per chunk: [0],[4],[5] work counters of the active-set kernels, [1..3] class sizes */
   double* ws;            /* device: solver images, SA_IMAGE doubles per slot */
   double* ws2;           /* device: factor images, SG_IMAGE doubles per slot */
   double* ws3;           /* device: assembly images, SE_IMAGE doubles per slot */
@@ -192,11 +192,19 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
     g_err = "tsidb_create: this build instantiates the tick kernels for nv = 26 (robot/v1) and nv = 24 (robot/v0)";
     return -1;
   }
-  const size_t smem_as = (size_t)TSIDB_AS_WARPS * SA_PER_ENV * sizeof(double);
-  if ((size_t)prop.sharedMemPerBlockOptin < smem_as) {
-    g_err = "tsidb_create: device offers less opt-in shared memory per block than the active-set kernel needs";
-    return -2;
+  {
+    const size_t need = (size_t)TSIDB_AS_WARPS_DS * a_layout(TSIDB_NVX, 2).per_env * sizeof(double);
+    if ((size_t)prop.sharedMemPerBlockOptin < need) {
+      g_err = "tsidb_create: device offers less opt-in shared memory per block than the active-set kernel needs";
+      return -2;
+    }
   }
+#define TSIDB_AS_ATTR(NV, NC, W)                                                                                         \
+  CK(cudaFuncSetAttribute(tsidb_activeset_kernel<NV, NC, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
+                          (int)((size_t)W * a_layout(NV, NC).per_env * sizeof(double))))
+  TSIDB_AS_ATTR(26, 2, TSIDB_AS_WARPS_DS); TSIDB_AS_ATTR(26, 1, TSIDB_AS_WARPS_SS); TSIDB_AS_ATTR(26, 0, TSIDB_AS_WARPS_FL);
+  TSIDB_AS_ATTR(24, 2, TSIDB_AS_WARPS_DS); TSIDB_AS_ATTR(24, 1, TSIDB_AS_WARPS_SS); TSIDB_AS_ATTR(24, 0, TSIDB_AS_WARPS_FL);
+#undef TSIDB_AS_ATTR
   CK(cudaFuncSetAttribute(tsidb_dynamics_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaFuncSetAttribute(tsidb_dynamics_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t smem_e = (size_t)TSIDB_E_WARPS * SE_PER_ENV * sizeof(double);
@@ -207,11 +215,10 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
   CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<24, 1, TSIDB_E_WARPS_LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_el));
   CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<26, 0, TSIDB_E_WARPS_LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_el));
   CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<24, 0, TSIDB_E_WARPS_LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_el));
-  CK(cudaFuncSetAttribute(tsidb_activeset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_as));
   const size_t smem_g = (size_t)TSIDB_G_WARPS * (SG_IMAGE + 2) * sizeof(double);
   CK(cudaFuncSetAttribute(tsidb_j2_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   CK(cudaFuncSetAttribute(tsidb_j2_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  CK(cudaMalloc(&h->counter, 4 * TSIDB_MAX_CHUNKS * sizeof(int32_t)));
+  CK(cudaMalloc(&h->counter, 8 * TSIDB_MAX_CHUNKS * sizeof(int32_t)));
   CK(cudaMalloc(&h->ws, (size_t)max_envs * SA_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->ws2, (size_t)max_envs * SG_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->ws3, (size_t)max_envs * SE_IMAGE * sizeof(double)));
@@ -288,7 +295,7 @@ extern "C" int tsidb_set_default_refs(tsidb_handle* h, const double* com9, const
 static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base = 0, int chunk = 0) {
   CK(cudaSetDevice(h->device));
   if (base + a.n_envs > h->max_envs) { g_err = "n_envs exceeds the handle's max_envs (workspace size)"; return -1; }
-  int32_t* counter = h->counter + 4 * chunk;
+  int32_t* counter = h->counter + 8 * chunk; /* [0],[4],[5]: work counters per class, [1..3]: class sizes */
   int32_t* perm = h->perm + base;
   int32_t* cls_pos = h->cls_pos + base;
   a.counter = counter;
@@ -301,7 +308,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   const bool timed = h->timing && !a.kin_only && chunk == 0 && base == 0;
   if (timed) CK(cudaEventRecord(h->ev[0], st));
   if (!a.kin_only) {
-    CK(cudaMemsetAsync(counter, 0, 4 * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(counter, 0, 8 * sizeof(int32_t), st));
     if (a.mask) {
       /* class sort (double support, single support, flight) -> slot order */
       const int th = 256;
@@ -358,13 +365,20 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   }
   if (timed) CK(cudaEventRecord(h->ev[4], st));
   if (!a.kin_only) {
-    const int warps = TSIDB_AS_WARPS;
-    int blocks = (n + warps - 1) / warps;
-    if (blocks > h->sm_count) blocks = h->sm_count;
-    const size_t smem = (size_t)warps * SA_PER_ENV * sizeof(double);
-    tsidb_activeset_kernel<<<blocks, 32 * warps, smem, st>>>(a);
+    /* one launch per contact class, as for the elimination */
+    const int blocks = h->sm_count;
+#define TSIDB_AS_LAUNCH(NV, NC, W)                                                                                       \
+  tsidb_activeset_kernel<NV, NC, W><<<blocks, 32 * W, (size_t)W * a_layout(NV, NC).per_env * sizeof(double), st>>>(a)
+    if (h->dc.nv == 26) {
+      TSIDB_AS_LAUNCH(26, 2, TSIDB_AS_WARPS_DS);
+      if (a.perm) { TSIDB_AS_LAUNCH(26, 1, TSIDB_AS_WARPS_SS); TSIDB_AS_LAUNCH(26, 0, TSIDB_AS_WARPS_FL); }
+    } else {
+      TSIDB_AS_LAUNCH(24, 2, TSIDB_AS_WARPS_DS);
+      if (a.perm) { TSIDB_AS_LAUNCH(24, 1, TSIDB_AS_WARPS_SS); TSIDB_AS_LAUNCH(24, 0, TSIDB_AS_WARPS_FL); }
+    }
+#undef TSIDB_AS_LAUNCH
     CK(cudaGetLastError());
-    h->launches += 1;
+    h->launches += a.perm ? 3 : 1;
   }
   if (timed) CK(cudaEventRecord(h->ev[5], st));
   return 0;

@@ -99,19 +99,6 @@ struct DevConst {
 #define SE_oX (SE_oW0 + 64)         /* x0                                       50 */
 #define SE_oBar (SE_oX + 50)        /* mbarrier of the image load                2 */
 #define SE_PER_ENV (SE_oBar + 2)    /*                                        2718 */
-/* work arrays of the active-set kernel */
-#define UF_R 0                    /* R packed by columns: col j at j(j+1)/2       528 */
-#define UF_IRD (UF_R + 528)       /* 1/R_jj                        32 */
-#define UF_NP (UF_IRD + 32)       /* constraint normal             50 */
-#define UF_D (UF_NP + 50)         /* d (free columns), padded      34 */
-#define UF_RR (UF_D + 34)         /* r                             32 */
-#define UF_VV (UF_RR + 32)        /* Householder vector, padded    34 */
-#define UF_U (UF_VV + 34)         /* u                             34 */
-#define UF_UO (UF_U + 34)         /* u_old                         34 */
-#define UF_XO (UF_UO + 34)        /* x_old                         50 */
-#define UF_A (UF_XO + 50)         /* A, A_old as int32: 2 x 34 ints = 34 doubles */
-#define UF_END (UF_A + 34)
-
 struct TickArgs {
   int32_t n_envs, layout, pad_;
   const double* q;

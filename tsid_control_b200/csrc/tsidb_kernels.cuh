@@ -35,6 +35,7 @@
 #ifndef TSIDB_EMU
 #include <cuda_runtime.h>
 #define TSIDB_DEV __device__ __forceinline__
+#define TSIDB_HD __host__ __device__
 #define TSIDB_DEVNI __device__ __noinline__
 __constant__ DevConst g_const[TSIDB_MAX_SLOTS];
 #endif
@@ -951,21 +952,58 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, do
 #define SG_LPART SG_oTAU                  /* [0, SG_LPART): factor part, [SG_LPART, SG_IMAGE): reflector part */
 #define TSIDB_G_WARPS 12
 #define SA_LDJA 20                        /* JFa row stride                                  */
-#define SA_LDJ 34                         /* J2 row stride: even (16-byte row accesses), conflict-free by rows and by columns */
 #define SA_LDM 30                         /* M_a row stride: even, 16-byte lane-strided reads are conflict-free           */
-#define SA_oJ2 0                          /* J2   50 x 34                              1700 */
-#define SA_oMa (SA_oJ2 + 1700)            /* M_a  na x 30 (rows 6.. of M)               600 */
-#define SA_oJFa (SA_oMa + 600)            /* JF columns 6.., 12 x 20                     240 */
-#define SA_oNle (SA_oJFa + 240)           /* nle_a                                        20 */
-#define SA_oVj (SA_oNle + 20)             /* joint velocities                             20 */
-#define SA_oX (SA_oVj + 20)               /* x                                            50 */
-#define SA_oSc (SA_oX + 50)               /* c1*c2, R_norm, error status, contact mask     4 */
-#define SA_IMAGE (SA_oSc + 4)             /* doubles handed over per env                2634 */
-#define SA_oWr (SA_IMAGE)                 /* wrenches                                     12 */
-#define SA_oU (SA_oWr + 12)               /* active-set work arrays (UF_*)                   */
-#define SA_oBar (SA_oU + UF_END)          /* mbarrier of the image load                    2 */
-#define SA_PER_ENV (SA_oBar + 2)
-#define TSIDB_AS_WARPS 8
+/* Solver image / active-set shared-memory layout of one env, per contact class (nc = 2, 1, 0).  The first
+ * `image` doubles are what the producer kernels write to HBM and what one bulk copy brings in; the work arrays
+ * follow.  J2's row stride ldj is even (16-byte row accesses) with ldj/2 odd, which keeps both the row-wise
+ * 16-byte accesses (lane <-> row) and the column-wise 8-byte ones (lane <-> column) free of bank conflicts.
+ * The status block comes first so that it sits at the same place for every class. */
+struct ALayout {
+  int n, m, ldj;
+  int oSc, oJ2, oMa, oJFa, oNle, oVj, oX, image;
+  int oWr, oR, oIRD, oNP, oD, oRR, oVV, oU, oUO, oXO, oA, oBar, per_env;
+};
+TSIDB_HD constexpr int even_up(int x) { return (x + 1) & ~1; }
+TSIDB_HD constexpr ALayout a_layout(int nv, int nc) {
+  ALayout L{};
+  const int na = nv - 6;
+  L.n = nv + 12 * nc;
+  L.m = na + 6 * nc;
+  L.ldj = ((((L.m + 2) / 2) & 1) != 0) ? L.m + 2 : L.m + 4;
+  L.oSc = 0;                              /* c1*c2, R_norm, error status, contact mask */
+  L.oJ2 = 4;                              /* J2  n x ldj                               */
+  L.oMa = L.oJ2 + L.n * L.ldj;            /* M_a na x SA_LDM (rows 6.. of M)           */
+  L.oJFa = L.oMa + na * SA_LDM;           /* JF columns 6.., 12 x SA_LDJA              */
+  L.oNle = L.oJFa + 12 * SA_LDJA;         /* nle_a                                     */
+  L.oVj = L.oNle + even_up(na);           /* joint velocities                          */
+  L.oX = L.oVj + even_up(na);             /* x                                         */
+  L.image = L.oX + even_up(L.n);
+  L.oWr = L.image;                        /* wrenches 12                               */
+  L.oR = L.oWr + 12;                      /* R packed by columns: col j at j(j+1)/2    */
+  L.oIRD = L.oR + even_up(L.m * (L.m + 1) / 2);  /* 1/R_jj                             */
+  L.oNP = L.oIRD + L.m;                   /* dense constraint normal                   */
+  L.oD = L.oNP + even_up(L.n);            /* d (free columns), zero padded to m + 2    */
+  L.oRR = L.oD + L.m + 2;                 /* r                                         */
+  L.oVV = L.oRR + L.m;                    /* Householder vector, zero padded to m + 2  */
+  L.oU = L.oVV + L.m + 2;                 /* u                                         */
+  L.oUO = L.oU + L.m + 2;                 /* u_old                                     */
+  L.oXO = L.oUO + L.m + 2;                /* x_old                                     */
+  L.oA = L.oXO + even_up(L.n);            /* A, A_old as int32: 2 x (m + 2) ints       */
+  L.oBar = L.oA + L.m + 2;                /* mbarrier of the image load                */
+  L.per_env = L.oBar + 2;
+  return L;
+}
+/* the same numbers as enumerators (pure compile-time constants in device code) */
+template <int NV, int NC>
+struct AL {
+  enum : int { n = a_layout(NV, NC).n, m = a_layout(NV, NC).m, ldj = a_layout(NV, NC).ldj, oSc = a_layout(NV, NC).oSc, oJ2 = a_layout(NV, NC).oJ2, oMa = a_layout(NV, NC).oMa, oJFa = a_layout(NV, NC).oJFa, oNle = a_layout(NV, NC).oNle, oVj = a_layout(NV, NC).oVj, oX = a_layout(NV, NC).oX, image = a_layout(NV, NC).image, oWr = a_layout(NV, NC).oWr, oR = a_layout(NV, NC).oR, oIRD = a_layout(NV, NC).oIRD, oNP = a_layout(NV, NC).oNP, oD = a_layout(NV, NC).oD, oRR = a_layout(NV, NC).oRR, oVV = a_layout(NV, NC).oVV, oU = a_layout(NV, NC).oU, oUO = a_layout(NV, NC).oUO, oXO = a_layout(NV, NC).oXO, oA = a_layout(NV, NC).oA, oBar = a_layout(NV, NC).oBar, per_env = a_layout(NV, NC).per_env };
+};
+#define SA_IMAGE (a_layout(TSIDB_NVX, 2).image)   /* slot stride of the solver images in HBM (largest class) */
+#define SA_oSc 0
+/* warps per CTA of the active-set kernel per contact class (shared memory: 28 / 21.6 / 15.5 KB per env) */
+#define TSIDB_AS_WARPS_DS 8
+#define TSIDB_AS_WARPS_SS 10
+#define TSIDB_AS_WARPS_FL 12
 
 /* ---- bulk asynchronous copy global -> shared (TMA, 1-D) completed through an mbarrier ---- */
 #ifndef TSIDB_EMU
@@ -1024,6 +1062,7 @@ struct LaneConst {
 };
 
 struct ASCtx {
+  int ldj;            /* row stride of J2 */
   double* J2;
   const double* Ma;
   const double* JFa;
@@ -1031,7 +1070,9 @@ struct ASCtx {
   const double* vj;
   double* x;
   double* wr;
-  double* U;
+  double *Rp, *ird, *np, *dd, *rr, *vv, *u, *uo, *xo;
+  int* A;             /* working set, then its saved copy at A + m + 2 */
+  int aoff;           /* m + 2 */
 };
 
 /* x index of foot f's first force variable */
@@ -1155,29 +1196,29 @@ TSIDB_DEV double row_dot_col(const DevConst& C, const ASCtx& S, int cid, int mas
   if (cid < 32) {
     const int f = cid >> 4, c = (cid & 15) >> 2, k = cid & 3;
     const int r0 = fvar0(nv, mask, f) + 3 * c;
-    return -(C.fric[k][0] * Jc[r0 * SA_LDJ] + C.fric[k][1] * Jc[(r0 + 1) * SA_LDJ] + C.fric[k][2] * Jc[(r0 + 2) * SA_LDJ]);
+    return -(C.fric[k][0] * Jc[r0 * S.ldj] + C.fric[k][1] * Jc[(r0 + 1) * S.ldj] + C.fric[k][2] * Jc[(r0 + 2) * S.ldj]);
   }
   if (cid < 36) {
     const int f = (cid - 32) >> 1, side = (cid - 32) & 1;
     const int r0 = fvar0(nv, mask, f);
     double t = 0.0;
 #pragma unroll
-    for (int o = 0; o < 12; o++) t += C.nrm[o % 3] * Jc[(r0 + o) * SA_LDJ];
+    for (int o = 0; o < 12; o++) t += C.nrm[o % 3] * Jc[(r0 + o) * S.ldj];
     return side ? -t : t;
   }
   if (cid >= 36 + 2 * na) {
     const int k = cid - 36 - 2 * na, side = k >= na ? 1 : 0, i = k - side * na;
-    const double t = Jc[(6 + i) * SA_LDJ];
+    const double t = Jc[(6 + i) * S.ldj];
     return side ? -t : t;
   }
   /* actuation row r: n = +-[M_a(r,:) | -Jc(:,6+r)^T]; every lane reads the normal from np */
   double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
   int k = 0;
   for (; k + 3 < n; k += 4) {
-    d0 += np[k] * Jc[k * SA_LDJ]; d1 += np[k + 1] * Jc[(k + 1) * SA_LDJ];
-    d2 += np[k + 2] * Jc[(k + 2) * SA_LDJ]; d3 += np[k + 3] * Jc[(k + 3) * SA_LDJ];
+    d0 += np[k] * Jc[k * S.ldj]; d1 += np[k + 1] * Jc[(k + 1) * S.ldj];
+    d2 += np[k + 2] * Jc[(k + 2) * S.ldj]; d3 += np[k + 3] * Jc[(k + 3) * S.ldj];
   }
-  for (; k < n; k++) d0 += np[k] * Jc[k * SA_LDJ];
+  for (; k < n; k++) d0 += np[k] * Jc[k * S.ldj];
   return (d0 + d1) + (d2 + d3);
 }
 /* dense normal of an actuation row into np[0..n) (all lanes cooperate) */
@@ -1218,10 +1259,9 @@ TSIDB_DEV void wrench_of(const DevConst& C, const LaneConst& K, const double* x,
  * the columns of R, restore R to upper-triangular with Givens rotations of rows (j, j+1) and apply the
  * same rotations to columns j, j+1 of J2.  [eiquadprog-fast delete_constraint] */
 TSIDB_DEVNI void qp_delete(const ASCtx& S, int n, int& iq, int qq, int lane) {
-  double* U = S.U;
-  double* Rp = U + UF_R;
-  double* u = U + UF_U;
-  int* A = (int*)(U + UF_A);
+  double* Rp = S.Rp;
+  double* u = S.u;
+  int* A = S.A;
   double* J2 = S.J2;
   __syncwarp(); /* every lane has finished reading A/u/R of the current working set */
   /* shift columns qq+1..iq-1 one to the left; a column keeps its length, so column c (length c+1 in
@@ -1266,14 +1306,14 @@ TSIDB_DEVNI void qp_delete(const ASCtx& S, int n, int& iq, int qq, int lane) {
     }
     /* columns j, j+1 of J2: lanes over rows */
     for (int k = lane; k < n; k += 32) {
-      double t1 = J2[k * SA_LDJ + j], t2 = J2[k * SA_LDJ + j + 1];
+      double t1 = J2[k * S.ldj + j], t2 = J2[k * S.ldj + j + 1];
       double n1 = t1 * cc + t2 * ss;
-      J2[k * SA_LDJ + j] = n1;
-      J2[k * SA_LDJ + j + 1] = xny * (n1 + t1) - t2;
+      J2[k * S.ldj + j] = n1;
+      J2[k * S.ldj + j + 1] = xny * (n1 + t1) - t2;
     }
     __syncwarp();
   }
-  if (lane < iq) U[UF_IRD + lane] = 1.0 / Rp[lane * (lane + 1) / 2 + lane];
+  if (lane < iq) S.ird[lane] = 1.0 / Rp[lane * (lane + 1) / 2 + lane];
   __syncwarp();
 }
 
@@ -1299,24 +1339,23 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
                        double c1c2, double R_norm, int& iters_out, uint64_t* act_words) {
   const int na = C.na;
   const int m = n - neq; /* reduced dimension, <= 32 */
-  double* U = S.U;
   double* J2 = S.J2;
   double* x = S.x;
   double* wr = S.wr;
-  double* Rp = U + UF_R;
-  double* ird = U + UF_IRD;
-  double* np = U + UF_NP;
-  double* dd = U + UF_D;   /* d with the entries of the active columns zeroed, zero padded to 34 */
-  double* rr = U + UF_RR;
-  double* vv = U + UF_VV;  /* Householder vector over the columns, zero below iq, zero padded to 34 */
-  double* u = U + UF_U;
-  double* uo = U + UF_UO;
-  double* xo = U + UF_XO;
-  int* A = (int*)(U + UF_A);
-  int* Ao = A + 34;
+  double* Rp = S.Rp;
+  double* ird = S.ird;
+  double* np = S.np;
+  double* dd = S.dd;   /* d with the entries of the active columns zeroed, zero padded to m + 2 */
+  double* rr = S.rr;
+  double* vv = S.vv;   /* Householder vector over the columns, zero below iq, zero padded to m + 2 */
+  double* u = S.u;
+  double* uo = S.uo;
+  double* xo = S.xo;
+  int* A = S.A;
+  int* Ao = A + S.aoff;
   iters_out = 0;
   act_words[0] = act_words[1] = act_words[2] = 0;
-  if (lane < 2) { dd[32 + lane] = 0.0; vv[32 + lane] = 0.0; }
+  if (lane < 2) { dd[m + lane] = 0.0; vv[m + lane] = 0.0; }
 
   const int nin_ref = C.nin_ref_fixed + 34 * nc;
   const double psi_thresh = (double)nin_ref * TS_EPS * c1c2 * 100.0;
@@ -1371,14 +1410,14 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
         /* d = J2^T n_ip (lane <-> column) */
         double dl = 0.0;
         if (lane < m) dl = row_dot_col(C, S, ip, mask, n, lane, np);
-        dd[lane] = (lane >= iq && lane < m) ? dl : 0.0;
+        if (lane < m) dd[lane] = (lane >= iq) ? dl : 0.0;
         __syncwarp();
         /* z = J2[:, iq:] d[iq:] (lanes over rows, 16-byte reads of the row and of d); zero if no free
          * direction is left */
         double z0 = 0.0, z1 = 0.0;
         const bool h0 = lane < n, h1 = lane + 32 < n; /* this lane's two rows (an absent row reads row 0) */
-        const double2* Jr0 = reinterpret_cast<const double2*>(J2 + (h0 ? lane : 0) * SA_LDJ);
-        const double2* Jr1 = reinterpret_cast<const double2*>(J2 + (h1 ? lane + 32 : 0) * SA_LDJ);
+        const double2* Jr0 = reinterpret_cast<const double2*>(J2 + (h0 ? lane : 0) * S.ldj);
+        const double2* Jr1 = reinterpret_cast<const double2*>(J2 + (h1 ? lane + 32 : 0) * S.ldj);
         if (iq < m) {
           const int c0 = iq >> 1, c1 = (m + 1) >> 1;
           const double2* d2 = reinterpret_cast<const double2*>(dd);
@@ -1454,9 +1493,9 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
               const double scal = 1.0 / (d0 - beta);
               /* v_c = d_c * scal (c > iq), v_iq = 1;  w_k = sum_c J2[k][c] v_c = (z_k - beta J2[k][iq]) * scal;
                * J2[k][c] -= tau w_k v_c: lanes over rows, 16-byte read-modify-write of the row */
-              vv[lane] = (lane < iq || lane >= m) ? 0.0 : ((lane == iq) ? 1.0 : dl * scal);
-              const double w0 = h0 ? tauh * (z0 - beta * J2[lane * SA_LDJ + iq]) * scal : 0.0;
-              const double w1 = h1 ? tauh * (z1 - beta * J2[(lane + 32) * SA_LDJ + iq]) * scal : 0.0;
+              if (lane < m) vv[lane] = (lane < iq) ? 0.0 : ((lane == iq) ? 1.0 : dl * scal);
+              const double w0 = h0 ? tauh * (z0 - beta * J2[lane * S.ldj + iq]) * scal : 0.0;
+              const double w1 = h1 ? tauh * (z1 - beta * J2[(lane + 32) * S.ldj + iq]) * scal : 0.0;
               __syncwarp();
               {
                 const int c0 = iq >> 1, c1 = (m + 1) >> 1;
@@ -1556,17 +1595,18 @@ TSIDB_DEV void dynamics_env(const DevConst& C, double* sm, const TickArgs& a, in
   const int n = nv + 12 * nc, neq = 6 + 6 * nc;
   PHASE_SYNC_D();
   k2_assemble(C, sm, a, env, lane, mask, neq, n);
-  /* solver image (layout SA_*): the parts that do not depend on the elimination */
+  /* solver image (layout a_layout(nv, nc)): the parts that do not depend on the elimination */
+  const ALayout LA = a_layout(nv, nc);
   double* img = a.ws + (size_t)slot * SA_IMAGE;
   for (int k = lane; k < na * SA_LDM; k += 32) {
     const int r = k / SA_LDM, c = k % SA_LDM;
-    img[SA_oMa + k] = (c < nv) ? sm[SM_oM + (6 + r) * SM_LDM + c] : 0.0;
+    img[LA.oMa + k] = (c < nv) ? sm[SM_oM + (6 + r) * SM_LDM + c] : 0.0;
   }
   for (int k = lane; k < 12 * SA_LDJA; k += 32) {
     const int q = k / SA_LDJA, r = k % SA_LDJA;
-    img[SA_oJFa + k] = (r < na) ? sm[SM_oJF + q * TSIDB_NVX + 6 + r] : 0.0;
+    img[LA.oJFa + k] = (r < na) ? sm[SM_oJF + q * TSIDB_NVX + 6 + r] : 0.0;
   }
-  if (lane < na) { img[SA_oNle + lane] = sm[SM_oNle + 6 + lane]; img[SA_oVj + lane] = sm[SM_oQV + 32 + 6 + lane]; }
+  if (lane < na) { img[LA.oNle + lane] = sm[SM_oNle + 6 + lane]; img[LA.oVj + lane] = sm[SM_oQV + 32 + 6 + lane]; }
   if (lane == 0) img[SA_oSc + 3] = (double)mask;
   /* assembly image (layout SE_*) for the elimination kernel */
   double* eimg = a.ws3 + (size_t)slot * SE_IMAGE;
@@ -1597,8 +1637,9 @@ TSIDB_DEV void eliminate_env(const DevConst& C, double* sm, const TickArgs& a, i
   constexpr int n = NV + 12 * NC;
   double c1c2 = 0.0, R_norm = 1.0;
   const int err = k3_eliminate<NV, NC>(C, sm, lane, mask, c1c2, R_norm);
+  typedef AL<NV, NC> LA;
   double* img = a.ws + (size_t)slot * SA_IMAGE;
-  for (int k = lane; k < TSIDB_NX; k += 32) img[SA_oX + k] = (k < n) ? sm[SE_oX + k] : 0.0;
+  for (int k = lane; k < even_up(n); k += 32) img[LA::oX + k] = (k < n) ? sm[SE_oX + k] : 0.0;
   if (lane == 0) { img[SA_oSc] = c1c2; img[SA_oSc + 1] = R_norm; img[SA_oSc + 2] = (double)err; }
   /* factor image (layout SG_*) for the J2 kernel */
   double* fimg = a.ws2 + (size_t)slot * SG_IMAGE;
@@ -1654,6 +1695,7 @@ template <int NV, int NC>
 TSIDB_DEV void j2_columns(const DevConst& C, double* sg, double* img, int lane, G2Pipe& P) {
   constexpr int NS = SG_LDV;
   constexpr int N = NV + 12 * NC, NEQ = 6 + 6 * NC, NCM = 6 * NC, M = N - NEQ;
+  typedef AL<NV, NC> LA;
   const bool work = lane < M;
   const double2* L2 = reinterpret_cast<const double2*>(sg + SG_oL);
   const double* ild = sg + SG_oILD;
@@ -1714,7 +1756,7 @@ TSIDB_DEV void j2_columns(const DevConst& C, double* sg, double* img, int lane, 
             double acc = 0.0;
 #pragma unroll
             for (int k = r; k < 12; k++) acc += C.Lfinv[k][r] * q[NV + 12 * s + k];
-            img[SA_oJ2 + (NV + 12 * s + r) * SA_LDJ + lane] = acc;
+            img[LA::oJ2 + (NV + 12 * s + r) * LA::ldj + lane] = acc;
           }
         }
       }
@@ -1735,7 +1777,7 @@ TSIDB_DEV void j2_columns(const DevConst& C, double* sg, double* img, int lane, 
       }
     }
 #pragma unroll
-    for (int k = 0; k < NV; k++) img[SA_oJ2 + k * SA_LDJ + lane] = q[k];
+    for (int k = 0; k < NV; k++) img[LA::oJ2 + k * LA::ldj + lane] = q[k];
   }
   __syncwarp();
   g2_request_l(P, sg, lane);
@@ -1766,31 +1808,35 @@ TSIDB_DEV void j2_env(const DevConst& C, double* sg, const TickArgs& a, int slot
 }
 
 /* ================================================================= kernel A: active set + decode of one env */
+template <int NV, int NC>
 TSIDB_DEV void activeset_env(const DevConst& C, double* sm, const TickArgs& a, int env, int slot, int lane, unsigned& parity) {
-  const int nv = C.nv, na = C.na;
+  typedef AL<NV, NC> LA;
+  constexpr int nv = NV, na = NV - 6;
   __syncwarp(); /* every lane is done with the previous env's shared memory */
 #ifndef TSIDB_EMU
   /* the 21 KB solver image arrives as ONE bulk asynchronous copy (TMA); the warp waits on its mbarrier */
-  if (lane == 0) bulk_load(sm, a.ws + (size_t)slot * SA_IMAGE, SA_IMAGE * sizeof(double), sm + SA_oBar);
+  if (lane == 0) bulk_load(sm, a.ws + (size_t)slot * SA_IMAGE, LA::image * sizeof(double), sm + LA::oBar);
   /* per-lane constants while the copy is in flight */
 #else
-  for (int k = lane; k < SA_IMAGE; k += 32) sm[k] = a.ws[(size_t)slot * SA_IMAGE + k];
+  for (int k = lane; k < LA::image; k += 32) sm[k] = a.ws[(size_t)slot * SA_IMAGE + k];
 #endif
   LaneConst K;
 #pragma unroll
   for (int j = 0; j < 12; j++) K.Trow[j] = C.T[lane % 6][j];
 #ifndef TSIDB_EMU
-  mbar_wait(sm + SA_oBar, parity);
+  mbar_wait(sm + LA::oBar, parity);
   parity ^= 1u;
 #endif
   __syncwarp();
   ASCtx S;
-  S.J2 = sm + SA_oJ2; S.Ma = sm + SA_oMa; S.JFa = sm + SA_oJFa; S.nle_a = sm + SA_oNle; S.vj = sm + SA_oVj;
-  S.x = sm + SA_oX; S.wr = sm + SA_oWr; S.U = sm + SA_oU;
+  S.ldj = LA::ldj; S.aoff = LA::m + 2;
+  S.J2 = sm + LA::oJ2; S.Ma = sm + LA::oMa; S.JFa = sm + LA::oJFa; S.nle_a = sm + LA::oNle; S.vj = sm + LA::oVj;
+  S.x = sm + LA::oX; S.wr = sm + LA::oWr;
+  S.Rp = sm + LA::oR; S.ird = sm + LA::oIRD; S.np = sm + LA::oNP; S.dd = sm + LA::oD; S.rr = sm + LA::oRR; S.vv = sm + LA::oVV;
+  S.u = sm + LA::oU; S.uo = sm + LA::oUO; S.xo = sm + LA::oXO; S.A = (int*)(sm + LA::oA);
   const double c1c2 = sm[SA_oSc], R_norm = sm[SA_oSc + 1];
-  const int err = (int)sm[SA_oSc + 2], mask = (int)sm[SA_oSc + 3];
-  const int nc = (mask & 1) + ((mask >> 1) & 1);
-  const int n = nv + 12 * nc, neq = 6 + 6 * nc;
+  const int err = (int)sm[SA_oSc + 2], mask = (int)sm[SA_oSc + 3]; /* its contact count is NC (class-sorted slots) */
+  constexpr int nc = NC, n = LA::n, neq = 6 + 6 * NC;
   K.lb = K.ub = 0.0;
   if (lane < na && C.use_jb) {
     /* [tsid TaskJointBounds] (v_min - v)/dt <= dv <= (v_max - v)/dt, clipped to +-1e10 */
@@ -1940,22 +1986,32 @@ tsidb_j2_kernel(const TickArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(32 * TSIDB_AS_WARPS, 1)
+/* one launch per contact class (sizes, strides and the shared-memory layout are compile-time; the lighter
+ * classes fit more warps per SM); each class pulls its slots from a work counter of its own because the
+ * iteration counts vary from 1 to ~40 */
+template <int NV, int NC, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1)
 tsidb_activeset_kernel(const TickArgs a) {
   extern __shared__ double smem[];
+  typedef AL<NV, NC> LA;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double* sm = smem + wid * SA_PER_ENV;
+  double* sm = smem + wid * LA::per_env;
   const DevConst& C = g_const[a.slot];
-  if (lane == 0) mbar_init(sm + SA_oBar, 1);
+  int start, count;
+  class_range<NC>(a, start, count);
+  if (count <= 0) return;
+  int* counter = a.counter + ((NC == 2) ? 0 : ((NC == 1) ? 4 : 5));
+  if (lane == 0) mbar_init(sm + LA::oBar, 1);
   __syncwarp();
   unsigned parity = 0;
   for (;;) {
-    int slot = 0;
-    if (lane == 0) slot = atomicAdd(a.counter, 1);
-    slot = __shfl_sync(FULL, slot, 0);
-    if (slot >= a.n_envs) break;
+    int k = 0;
+    if (lane == 0) k = atomicAdd(counter, 1);
+    k = __shfl_sync(FULL, k, 0);
+    if (k >= count) break;
+    const int slot = start + k;
     const int env = a.perm ? a.perm[slot] : slot;
-    activeset_env(C, sm, a, env, slot, lane, parity);
+    activeset_env<NV, NC>(C, sm, a, env, slot, lane, parity);
   }
 }
 #endif
