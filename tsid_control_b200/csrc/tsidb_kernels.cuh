@@ -1021,6 +1021,14 @@ TSIDB_DEV void bulk_load(void* dst, const void* src, unsigned bytes, void* bar) 
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+/* bulk asynchronous store shared -> global (issued by ONE lane after a __syncwarp that makes the warp's
+ * shared-memory writes visible); bulk_store_commit closes the group, bulk_store_wait_read returns when the
+ * stores of all committed groups have finished READING shared memory (the source may then be overwritten) */
+TSIDB_DEV void bulk_store(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+TSIDB_DEV void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+TSIDB_DEV void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 TSIDB_DEV void mbar_wait(void* bar, unsigned parity) {
   unsigned ok = 0;
   const unsigned addr = smem_u32(bar);
@@ -1574,6 +1582,10 @@ template <int NV>
 TSIDB_DEV void dynamics_env(const DevConst& C, double* sm, const TickArgs& a, int env, int slot, int lane) {
   const int nv = C.nv, na = C.na, nq = C.nq;
   PHASE_SYNC_D();
+#ifndef TSIDB_EMU
+  if (lane == 0) bulk_store_wait_read(); /* the previous env's image stores are done with this warp's shared memory */
+  __syncwarp();
+#endif
   /* stage q, v */
   if (lane < nq) sm[SM_oQV + lane] = ldin(a.q, a, env, lane, nq);
   if (lane < nv) sm[SM_oQV + 32 + lane] = a.v ? ldin(a.v, a, env, lane, nv) : 0.0;
@@ -1610,10 +1622,23 @@ TSIDB_DEV void dynamics_env(const DevConst& C, double* sm, const TickArgs& a, in
   if (lane == 0) img[SA_oSc + 3] = (double)mask;
   /* assembly image (layout SE_*) for the elimination kernel */
   double* eimg = a.ws3 + (size_t)slot * SE_IMAGE;
+#ifndef TSIDB_EMU
+  /* the three contiguous pieces (H | g, base rows of M, JF) leave as bulk asynchronous stores (TMA); the next env
+   * of this warp waits for them to have read shared memory before it overwrites it */
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    bulk_store(eimg + SE_oH, sm + SM_oH, (702 + TSIDB_NX) * sizeof(double)); /* SM_oGv follows SM_oH, SE_oG follows SE_oH */
+    bulk_store(eimg + SE_oMu, sm + SM_oM, 162 * sizeof(double));
+    bulk_store(eimg + SE_oJF, sm + SM_oJF, 312 * sizeof(double));
+    bulk_store_commit();
+  }
+#else
   for (int k = lane; k < 702; k += 32) eimg[SE_oH + k] = sm[SM_oH + k];
   for (int k = lane; k < TSIDB_NX; k += 32) eimg[SE_oG + k] = sm[SM_oGv + k];
   for (int k = lane; k < 162; k += 32) eimg[SE_oMu + k] = sm[SM_oM + k];
   for (int k = lane; k < 312; k += 32) eimg[SE_oJF + k] = sm[SM_oJF + k];
+#endif
   if (lane < 8) eimg[SE_oNle + lane] = (lane < 6) ? sm[SM_oNle + lane] : 0.0;
   if (lane < 12) eimg[SE_oBm + lane] = sm[SM_oBv + BV_MOT + lane];
   if (lane < 2) eimg[SE_oSc + lane] = (lane == 0) ? (double)mask : 0.0;
@@ -1892,11 +1917,22 @@ TSIDB_DEV void activeset_env(const DevConst& C, double* sm, const TickArgs& a, i
  * kernel F have equal trip counts and kernel A starts with the longest jobs. */
 __global__ void tsidb_classify_kernel(int n_envs, const uint8_t* mask, int32_t* cls_pos, int32_t* counts) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= n_envs) return;
-  const int m = mask ? (mask[env] & 3) : 3;
-  const int cls = 2 - ((m & 1) + ((m >> 1) & 1)); /* 0: DS, 1: SS, 2: flight */
-  const int pos = atomicAdd(&counts[cls], 1);
-  cls_pos[env] = (cls << 28) | pos;
+  const int lane = threadIdx.x & 31;
+  int cls = -1;
+  if (env < n_envs) {
+    const int m = mask ? (mask[env] & 3) : 3;
+    cls = 2 - ((m & 1) + ((m >> 1) & 1)); /* 0: DS, 1: SS, 2: flight */
+  }
+  /* warp-aggregated: one atomic per warp and class instead of one per env */
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const unsigned peers = __ballot_sync(FULL, cls == c);
+    if (!peers) continue;
+    int base = 0;
+    if (lane == __ffs(peers) - 1) base = atomicAdd(&counts[c], __popc(peers));
+    base = __shfl_sync(FULL, base, __ffs(peers) - 1);
+    if (cls == c) cls_pos[env] = (c << 28) | (base + __popc(peers & ((1u << lane) - 1u)));
+  }
 }
 __global__ void tsidb_permute_kernel(int n_envs, const int32_t* cls_pos, const int32_t* counts, int32_t* perm) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1924,6 +1960,7 @@ tsidb_dynamics_kernel(const TickArgs a) {
     const int env = a.perm ? a.perm[slot] : slot;
     dynamics_env<NV>(C, sm, a, env, slot, lane);
   }
+  if (lane == 0) bulk_store_wait_read(); /* shared memory must outlive the bulk stores that read it */
 }
 
 /* slot range of contact class NC (2: double support, 1: single support, 0: flight) in the class-sorted slot
