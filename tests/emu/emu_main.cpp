@@ -11,24 +11,26 @@ static DevConst g_const[TSIDB_MAX_SLOTS];
 namespace emu { Warp W; }
 
 struct Job { const DevConst* C; double* sm; const TickArgs* a; int env; int stage; };
+static double g_mdl[MDL_SIZE];   /* the CTA-shared copies the kernels keep in shared memory */
+static double g_lfinv[144];
 static Job g_job;
 
 static void lane_entry(int lane) {
   if (g_job.stage == 0) {
-    if (g_job.C->nv == 26) dynamics_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
-    else dynamics_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
+    if (g_job.C->nv == 26) dynamics_env<26>(*g_job.C, g_mdl, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
+    else dynamics_env<24>(*g_job.C, g_mdl, g_job.sm, *g_job.a, g_job.env, g_job.env, lane);
   } else if (g_job.stage == 1) {
     unsigned parity = 0;
     const int m = g_job.a->mask ? (((const uint8_t*)g_job.a->mask)[g_job.env] & 3) : 3;
     const int nc = (m & 1) + ((m >> 1) & 1);
     if (g_job.C->nv == 26) {
-      if (nc == 2) eliminate_env<26, 2>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, parity);
-      else if (nc == 1) eliminate_env<26, 1>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, parity);
-      else eliminate_env<26, 0>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, parity);
+      if (nc == 2) eliminate_env<26, 2>(*g_job.C, g_lfinv, g_job.sm, *g_job.a, g_job.env, lane, parity);
+      else if (nc == 1) eliminate_env<26, 1>(*g_job.C, g_lfinv, g_job.sm, *g_job.a, g_job.env, lane, parity);
+      else eliminate_env<26, 0>(*g_job.C, g_lfinv, g_job.sm, *g_job.a, g_job.env, lane, parity);
     } else {
-      if (nc == 2) eliminate_env<24, 2>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, parity);
-      else if (nc == 1) eliminate_env<24, 1>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, parity);
-      else eliminate_env<24, 0>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, parity);
+      if (nc == 2) eliminate_env<24, 2>(*g_job.C, g_lfinv, g_job.sm, *g_job.a, g_job.env, lane, parity);
+      else if (nc == 1) eliminate_env<24, 1>(*g_job.C, g_lfinv, g_job.sm, *g_job.a, g_job.env, lane, parity);
+      else eliminate_env<24, 0>(*g_job.C, g_lfinv, g_job.sm, *g_job.a, g_job.env, lane, parity);
     }
   } else if (g_job.stage == 2) {
     G2Pipe P;
@@ -104,6 +106,8 @@ extern "C" int emu_tick(const TickArgs* a_in, double* sm_out) {
   emu::Warp& W = emu::W;
   if (!W.stacks) W.stacks = (char*)malloc(32 * STK);
   TickArgs a = *a_in;
+  stage_model(g_const[0], g_mdl, 0, 1);
+  for (int k = 0; k < 144; k++) g_lfinv[k] = g_const[0].Lfinv[k / 12][k % 12];
   const int smn = a_layout(TSIDB_NVX, 2).per_env > SE_PER_ENV ? a_layout(TSIDB_NVX, 2).per_env : SE_PER_ENV;
   double* sm = (double*)calloc(smn, sizeof(double));
   double* ws = (double*)calloc((size_t)a.n_envs * SA_IMAGE, sizeof(double));

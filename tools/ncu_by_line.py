@@ -70,7 +70,8 @@ def main():
         if re.match(r"\s*/\*[0-9a-f]{4,}\*/", l):
             lines_of.append(cur)
     filt = os.environ.get("NCU_KERNEL_FILTER")
-    cmd = ["ncu", "-i", rep, "--page", "source", "--csv"] + (["-k", "regex:" + filt] if filt else [])
+    kid = os.environ.get("NCU_KERNEL_ID")  # n-th result of the report (1-based): template instantiations share a base name
+    cmd = ["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-id", f":::{kid}"] if kid else (["-k", "regex:" + filt] if filt else []))
     out = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[1]

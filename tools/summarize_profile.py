@@ -22,9 +22,15 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
-GROUP = {"dynamics": "dynamics", "eliminate": "eliminate+j2", "j2": "eliminate+j2", "activeset": "activeset"}
-MANGLED = {"dynamics": "_Z21tsidb_dynamics_kernelILi26EEv8TickArgs", "eliminate": "_Z22tsidb_eliminate_kernelILi26EEv8TickArgs",
-           "j2": "_Z15tsidb_j2_kernelILi26EEv8TickArgs", "activeset": "_Z22tsidb_activeset_kernel8TickArgs"}
+# short name -> (traffic group of bench.py, regex selecting the launch in the report, mangled name in the cubin)
+KERNELS = {
+    "dynamics": ("dynamics", r"tsidb_dynamics_kernel<26>", "_Z21tsidb_dynamics_kernelILi26EEv8TickArgs"),
+    "eliminate_ds": ("eliminate+j2", r"tsidb_eliminate_kernel<26, 2", "_Z22tsidb_eliminate_kernelILi26ELi2ELi8EEv8TickArgs"),
+    "eliminate_ss": ("eliminate+j2", r"tsidb_eliminate_kernel<26, 1", "_Z22tsidb_eliminate_kernelILi26ELi1ELi8EEv8TickArgs"),
+    "j2": ("eliminate+j2", r"tsidb_j2_kernel<26>", "_Z15tsidb_j2_kernelILi26EEv8TickArgs"),
+    "activeset_ds": ("activeset", r"tsidb_activeset_kernel<26, 2", "_Z22tsidb_activeset_kernelILi26ELi2ELi8EEv8TickArgs"),
+    "activeset_ss": ("activeset", r"tsidb_activeset_kernel<26, 1", "_Z22tsidb_activeset_kernelILi26ELi1ELi10EEv8TickArgs"),
+}
 
 
 def main():
@@ -33,8 +39,13 @@ def main():
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     out = [f"{tag}: ncu --set full --clock-control none, one launch of each tick kernel inside `python bench.py --steps 2 --warmup 3` "
-           "(robot/v1 walking, 65536 envs); per-launch times under ncu are serialised and cold-cache, use them for shares only\n"]
+           "(robot/v1 walking, 65536 envs: 13 107 double support, 52 429 single support); per-launch times under ncu are serialised and cold-cache, use them for shares only\n"]
     traffic = defaultdict(float)
+    result_id = {}
+    for idx, r in enumerate(rows[2:]):
+        for k, (_, rx, _m) in KERNELS.items():
+            if rx in r[hdr.index("Kernel Name")] and k not in result_id:
+                result_id[k] = idx + 1
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
         out.append(f"Kernel {name}")
@@ -42,15 +53,17 @@ def main():
             if k in hdr:
                 i = hdr.index(k)
                 out.append(f"  {k:90s} {r[i]} {units[i]}")
-        short = next((s for s in MANGLED if f"tsidb_{s}" in name), None)
+        short = next((k for k, (_, rx, _m) in KERNELS.items() if rx in name), None)
         if short:
             rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-            traffic[GROUP[short]] += float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]]
+            traffic[KERNELS[short][0]] += float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]]
         out.append("")
     so = os.path.join(ROOT, "tsid_control_b200", "csrc", "libtsidb.so")
-    for short, mangled in MANGLED.items():
-        env = dict(os.environ, NCU_KERNEL_FILTER=f"tsidb_{short}")
+    for short, (_g, rx, mangled) in KERNELS.items():
+        if short not in result_id:
+            continue
+        env = dict(os.environ, NCU_KERNEL_ID=str(result_id[short]))
         t = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), rep, so, mangled], capture_output=True, text=True, env=env)
         out.append(f"---- {short}: warp-state samples and executed instructions by source phase (tools/ncu_by_line.py)")
         out.append(t.stdout if t.returncode == 0 else t.stderr[-400:])

@@ -183,7 +183,7 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
-  const size_t smem = (size_t)TSIDB_WARPS_PER_BLOCK * SM_PER_ENV * sizeof(double);
+  const size_t smem = ((size_t)TSIDB_WARPS_PER_BLOCK * SM_PER_ENV + MDL_SIZE) * sizeof(double);
   if ((size_t)prop.sharedMemPerBlockOptin < smem) {
     g_err = "tsidb_create: device offers less opt-in shared memory per block than the kernel needs";
     return -2;
@@ -207,8 +207,8 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
 #undef TSIDB_AS_ATTR
   CK(cudaFuncSetAttribute(tsidb_dynamics_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaFuncSetAttribute(tsidb_dynamics_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const size_t smem_e = (size_t)TSIDB_E_WARPS * SE_PER_ENV * sizeof(double);
-  const size_t smem_el = (size_t)TSIDB_E_WARPS_LIGHT * SE_PER_ENV * sizeof(double);
+  const size_t smem_e = ((size_t)TSIDB_E_WARPS * SE_PER_ENV + 144) * sizeof(double);
+  const size_t smem_el = ((size_t)TSIDB_E_WARPS_LIGHT * SE_PER_ENV + 144) * sizeof(double);
   CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<26, 2, TSIDB_E_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
   CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<24, 2, TSIDB_E_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
   CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<26, 1, TSIDB_E_WARPS_LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_el));
@@ -323,7 +323,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
     const int warps = TSIDB_WARPS_PER_BLOCK;
     int blocks = (n + warps - 1) / warps;
     if (blocks > h->sm_count) blocks = h->sm_count; /* persistent: one CTA per SM */
-    const size_t smem = (size_t)warps * SM_PER_ENV * sizeof(double);
+    const size_t smem = ((size_t)warps * SM_PER_ENV + MDL_SIZE) * sizeof(double);
     if (h->dc.nv == 26) tsidb_dynamics_kernel<26><<<blocks, 32 * warps, smem, st>>>(a);
     else tsidb_dynamics_kernel<24><<<blocks, 32 * warps, smem, st>>>(a);
     CK(cudaGetLastError());
@@ -334,8 +334,8 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
     /* one launch per contact class; the class sizes are only known on the device, so every class gets a full
      * persistent grid and the CTAs of an empty class return at once.  Without a mask all envs are double support. */
     const int blocks = h->sm_count;
-    const size_t smem = (size_t)TSIDB_E_WARPS * SE_PER_ENV * sizeof(double);
-    const size_t smem_l = (size_t)TSIDB_E_WARPS_LIGHT * SE_PER_ENV * sizeof(double);
+    const size_t smem = ((size_t)TSIDB_E_WARPS * SE_PER_ENV + 144) * sizeof(double);
+    const size_t smem_l = ((size_t)TSIDB_E_WARPS_LIGHT * SE_PER_ENV + 144) * sizeof(double);
     if (h->dc.nv == 26) {
       tsidb_eliminate_kernel<26, 2, TSIDB_E_WARPS><<<blocks, 32 * TSIDB_E_WARPS, smem, st>>>(a);
       if (a.perm) {

@@ -151,7 +151,35 @@ TSIDB_DEV void log6_dev(const double* R, const double* p, double* out) {
 /* lane <-> body.  Everything is expressed in WORLD coordinates (Plücker vectors taken at the
  * world origin), which makes the per-body work independent once the placements are known;
  * only the placement/velocity chain (top-down) and the subtree sums (bottom-up) walk the tree. */
-TSIDB_DEV void k1_dynamics(const DevConst& C, double* sm, int lane) {
+/* per-body model constants staged in shared memory, one copy per CTA: a lane reads the constants of ITS body, and
+ * lane-dependent addresses into __constant__ memory are served one address at a time */
+#define MDL_STRIDE 25   /* jR 9, jp 3, mass 1, com 3, inertia 9; odd: conflict-free lane <-> body reads */
+#define MDL_oJR 0
+#define MDL_oJP 9
+#define MDL_oMASS 12
+#define MDL_oCOM 13
+#define MDL_oI 16
+#define MDL_oPOST (TSIDB_MAX_BODIES_K * MDL_STRIDE)   /* kp_post 23, kd_post 23, ref_posture 23 */
+#define TSIDB_MAX_BODIES_K 24
+#define MDL_SIZE (MDL_oPOST + 70)
+TSIDB_DEV void stage_model(const DevConst& C, double* mdl, int tid, int nthreads) {
+  for (int k = tid; k < TSIDB_MAX_BODIES_K * MDL_STRIDE; k += nthreads) {
+    const int b = k / MDL_STRIDE, j = k % MDL_STRIDE;
+    double v;
+    if (j < 9) v = C.jR[b][j];
+    else if (j < 12) v = C.jp[b][j - 9];
+    else if (j < 13) v = C.mass[b];
+    else if (j < 16) v = C.com[b][j - 13];
+    else v = C.inertia[b][j - 16];
+    mdl[k] = v;
+  }
+  for (int k = tid; k < 69; k += nthreads) {
+    const int j = k % 23;
+    mdl[MDL_oPOST + k] = (k < 23) ? C.kp_post[j] : ((k < 46) ? C.kd_post[j] : C.ref_posture[j]);
+  }
+}
+
+TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int lane) {
   const int nb = C.nb, nv = C.nv;
   const bool act = lane < nb;
   const int b = act ? lane : 0;
@@ -183,7 +211,7 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, double* sm, int lane) {
     qd = act ? vs[5 + b] : 0.0;
     double sa, ca;
     sincos(ang, &sa, &ca);
-    const double* jR = C.jR[b];
+    const double* jR = mdl + b * MDL_STRIDE + MDL_oJR;
 #pragma unroll
     for (int r = 0; r < 3; r++) {
       double c0 = jR[3 * r], c1 = jR[3 * r + 1];
@@ -191,7 +219,7 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, double* sm, int lane) {
       Rl[3 * r + 1] = c1 * ca - c0 * sa;
       Rl[3 * r + 2] = jR[3 * r + 2];
     }
-    pl[0] = C.jp[b][0]; pl[1] = C.jp[b][1]; pl[2] = C.jp[b][2];
+    pl[0] = mdl[b * MDL_STRIDE + MDL_oJP]; pl[1] = mdl[b * MDL_STRIDE + MDL_oJP + 1]; pl[2] = mdl[b * MDL_STRIDE + MDL_oJP + 2];
 #pragma unroll
     for (int k = 0; k < 9; k++) R[k] = Rl[k];
 #pragma unroll
@@ -232,12 +260,12 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, double* sm, int lane) {
   /* per-body inertial quantities, world coordinates, reference point = world origin */
   double acc[28];
   {
-    double m = act ? C.mass[b] : 0.0;
-    double cl[3] = {C.com[b][0], C.com[b][1], C.com[b][2]}, cw[3];
+    double m = act ? mdl[b * MDL_STRIDE + MDL_oMASS] : 0.0;
+    double cl[3] = {mdl[b * MDL_STRIDE + MDL_oCOM], mdl[b * MDL_STRIDE + MDL_oCOM + 1], mdl[b * MDL_STRIDE + MDL_oCOM + 2]}, cw[3];
     mv3(R, cl, cw);
     cw[0] += p[0]; cw[1] += p[1]; cw[2] += p[2];
     double RI[9], Iw[9];
-    mm3(R, C.inertia[b], RI);
+    mm3(R, mdl + b * MDL_STRIDE + MDL_oI, RI);
     /* Iw = RI * R^T */
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -534,7 +562,7 @@ TSIDB_DEV void se3_rhs(const double* fr, int f, const double* kp, const double* 
 
 /* Task right-hand sides -> sm[oBv]; Hessian dv block -> SM_oH (factored by the elimination kernel);
  * gradient -> column nEq of B (it rides through the QR as an extra column). */
-TSIDB_DEV void k2_assemble(const DevConst& C, double* sm, const TickArgs& a, int env, int lane, int mask, int neq, int n) {
+TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, const TickArgs& a, int env, int lane, int mask, int neq, int n) {
   const int nv = C.nv, na = C.na;
   double* bv = sm + SM_oBv;
   const double* fr = sm + SM_oFr;
@@ -577,8 +605,8 @@ TSIDB_DEV void k2_assemble(const DevConst& C, double* sm, const TickArgs& a, int
   }
   /* tsid::TaskJointPosture */
   if (lane < na) {
-    double rp = a.r_posture ? ldin(a.r_posture, a, env, lane, na) : C.ref_posture[lane];
-    bv[BV_POST + lane] = -C.kp_post[lane] * (qs[7 + lane] - rp) - C.kd_post[lane] * vs[6 + lane];
+    double rp = a.r_posture ? ldin(a.r_posture, a, env, lane, na) : mdl[MDL_oPOST + 46 + lane];
+    bv[BV_POST + lane] = -mdl[MDL_oPOST + lane] * (qs[7 + lane] - rp) - mdl[MDL_oPOST + 23 + lane] * vs[6 + lane];
   }
   __syncwarp();
   /* H_dv = w_foot (JF0^T JF0 + JF1^T JF1) + w_com Jcom^T Jcom + w_post S^T S (+ w_am Ag^T Ag) + hreg I
@@ -720,7 +748,7 @@ TSIDB_DEV void store_R1(double* R1, const double (&b)[N], int lane) {
  * same null space, x0 and projector; this one keeps the first 6*nc reflectors inside the dv rows (a contact-motion
  * row has no force entries), which halves their cost here and in the J2 kernel. */
 template <int NV, int NC>
-TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, double& c1c2, double& R_norm_out) {
+TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm, int lane, int mask, double& c1c2, double& R_norm_out) {
   constexpr int N = NV + 12 * NC;   /* n: the contact class fixes every size at compile time */
   constexpr int nc = NC, ncm = 6 * NC, neq = 6 + 6 * NC, n = N;
   constexpr int LDV = SG_LDV;       /* reflector row stride (the J2 kernel reads the same layout) */
@@ -919,7 +947,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, double* sm, int lane, int mask, do
   if (lane < 12 * nc) {
     const int s = lane / 12, i = lane % 12;
     double acc = 0.0;
-    for (int k = i; k < 12; k++) acc += C.Lfinv[k][i] * w0v[NV + 12 * s + k];
+    for (int k = i; k < 12; k++) acc += lfinv_sm[k * 12 + i] * w0v[NV + 12 * s + k];
     x[NV + lane] = acc;
   }
   for (int k = NV - 1; k >= 0; k--) {
@@ -1066,6 +1094,7 @@ TSIDB_DEV int warp_argmin(double val, bool valid, int tiebreak) {
 /* per-lane constants of one env, kept in registers across the iterations */
 struct LaneConst {
   double lb, ub;     /* joint-bound row `lane`: lb <= dv_j <= ub */
+  double tmin, tmax; /* actuation row `lane`: tmin <= tau <= tmax */
   double Trow[12];   /* row lane%6 of the force generator */
 };
 
@@ -1153,8 +1182,8 @@ TSIDB_DEV void eval_rows(const DevConst& C, const ASCtx& S, const LaneConst& K, 
       double t = (t0 + t1) + (t2 + t3);
 #pragma unroll
       for (int q = 0; q < 12; q++) t -= S.JFa[q * SA_LDJA + lane] * S.wr[q];
-      s[2] = t - C.tau_min[lane];
-      s[3] = C.tau_max[lane] - t;
+      s[2] = t - K.tmin;
+      s[3] = K.tmax - t;
     }
     if (C.use_jb) {
       s[4] = x[6 + lane] - K.lb;
@@ -1579,7 +1608,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
 
 /* ================================================================= kernel D: dynamics + assembly of one env */
 template <int NV>
-TSIDB_DEV void dynamics_env(const DevConst& C, double* sm, const TickArgs& a, int env, int slot, int lane) {
+TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, const TickArgs& a, int env, int slot, int lane) {
   const int nv = C.nv, na = C.na, nq = C.nq;
   PHASE_SYNC_D();
 #ifndef TSIDB_EMU
@@ -1590,7 +1619,7 @@ TSIDB_DEV void dynamics_env(const DevConst& C, double* sm, const TickArgs& a, in
   if (lane < nq) sm[SM_oQV + lane] = ldin(a.q, a, env, lane, nq);
   if (lane < nv) sm[SM_oQV + 32 + lane] = a.v ? ldin(a.v, a, env, lane, nv) : 0.0;
   __syncwarp();
-  k1_dynamics(C, sm, lane);
+  k1_dynamics(C, mdl, sm, lane);
   const double* fr = sm + SM_oFr;
   if (a.o_com && lane < 9) a.o_com[eidx(a, env, lane, 9)] = fr[FR_COM + lane];
 #pragma unroll
@@ -1606,7 +1635,7 @@ TSIDB_DEV void dynamics_env(const DevConst& C, double* sm, const TickArgs& a, in
   const int nc = (mask & 1) + ((mask >> 1) & 1);
   const int n = nv + 12 * nc, neq = 6 + 6 * nc;
   PHASE_SYNC_D();
-  k2_assemble(C, sm, a, env, lane, mask, neq, n);
+  k2_assemble(C, mdl, sm, a, env, lane, mask, neq, n);
   /* solver image (layout a_layout(nv, nc)): the parts that do not depend on the elimination */
   const ALayout LA = a_layout(nv, nc);
   double* img = a.ws + (size_t)slot * SA_IMAGE;
@@ -1647,7 +1676,7 @@ TSIDB_DEV void dynamics_env(const DevConst& C, double* sm, const TickArgs& a, in
 
 /* ================================================================= kernel E: equality elimination of one env */
 template <int NV, int NC>
-TSIDB_DEV void eliminate_env(const DevConst& C, double* sm, const TickArgs& a, int slot, int lane, unsigned& parity) {
+TSIDB_DEV void eliminate_env(const DevConst& C, const double* lfinv_sm, double* sm, const TickArgs& a, int slot, int lane, unsigned& parity) {
   const int nv = C.nv;
   __syncwarp(); /* every lane is done with the previous env's shared memory */
 #ifndef TSIDB_EMU
@@ -1661,7 +1690,7 @@ TSIDB_DEV void eliminate_env(const DevConst& C, double* sm, const TickArgs& a, i
   const int mask = (int)sm[SE_oSc]; /* its contact count is NC: the slots are class-sorted */
   constexpr int n = NV + 12 * NC;
   double c1c2 = 0.0, R_norm = 1.0;
-  const int err = k3_eliminate<NV, NC>(C, sm, lane, mask, c1c2, R_norm);
+  const int err = k3_eliminate<NV, NC>(C, lfinv_sm, sm, lane, mask, c1c2, R_norm);
   typedef AL<NV, NC> LA;
   double* img = a.ws + (size_t)slot * SA_IMAGE;
   for (int k = lane; k < even_up(n); k += 32) img[LA::oX + k] = (k < n) ? sm[SE_oX + k] : 0.0;
@@ -1863,6 +1892,8 @@ TSIDB_DEV void activeset_env(const DevConst& C, double* sm, const TickArgs& a, i
   const int err = (int)sm[SA_oSc + 2], mask = (int)sm[SA_oSc + 3]; /* its contact count is NC (class-sorted slots) */
   constexpr int nc = NC, n = LA::n, neq = 6 + 6 * NC;
   K.lb = K.ub = 0.0;
+  K.tmin = (lane < na) ? C.tau_min[lane] : 0.0;
+  K.tmax = (lane < na) ? C.tau_max[lane] : 0.0;
   if (lane < na && C.use_jb) {
     /* [tsid TaskJointBounds] (v_min - v)/dt <= dv <= (v_max - v)/dt, clipped to +-1e10 */
     const double vj = S.vj[lane];
@@ -1949,6 +1980,9 @@ tsidb_dynamics_kernel(const TickArgs a) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* sm = smem + wid * SM_PER_ENV;
   const DevConst& C = g_const[a.slot];
+  double* mdl = smem + TSIDB_WARPS_PER_BLOCK * SM_PER_ENV;
+  stage_model(C, mdl, threadIdx.x, blockDim.x);
+  __syncthreads();
   /* rounds: in every round the CTA's warps take consecutive slots and move through the phases together
    * (PHASE_SYNC).  A warp without a slot of its own in the last round repeats the last slot (it must reach
    * the barriers); it stores the same values again. */
@@ -1958,7 +1992,7 @@ tsidb_dynamics_kernel(const TickArgs a) {
     int slot = (r * gridDim.x + blockIdx.x) * TSIDB_WARPS_PER_BLOCK + wid;
     if (slot >= a.n_envs) slot = a.n_envs - 1;
     const int env = a.perm ? a.perm[slot] : slot;
-    dynamics_env<NV>(C, sm, a, env, slot, lane);
+    dynamics_env<NV>(C, mdl, sm, a, env, slot, lane);
   }
   if (lane == 0) bulk_store_wait_read(); /* shared memory must outlive the bulk stores that read it */
 }
@@ -1985,6 +2019,10 @@ tsidb_eliminate_kernel(const TickArgs a) {
   int start, count;
   class_range<NC>(a, start, count);
   if (count <= 0) return;
+  /* CTA-shared copy of the constant Lf^-1 (read with lane-dependent indices) */
+  double* lfinv_sm = smem + WARPS * SE_PER_ENV;
+  for (int k = threadIdx.x; k < 144; k += blockDim.x) lfinv_sm[k] = C.Lfinv[k / 12][k % 12];
+  __syncthreads();
   if (lane == 0) mbar_init(sm + SE_oBar, 1);
   __syncwarp();
   unsigned parity = 0;
@@ -1993,7 +2031,7 @@ tsidb_eliminate_kernel(const TickArgs a) {
   for (int r = 0; r < rounds; r++) {
     int k = (r * gridDim.x + blockIdx.x) * WARPS + wid;
     if (k >= count) k = count - 1;
-    eliminate_env<NV, NC>(C, sm, a, start + k, lane, parity);
+    eliminate_env<NV, NC>(C, lfinv_sm, sm, a, start + k, lane, parity);
   }
 }
 
