@@ -39,16 +39,18 @@ static void lane_entry(int lane) {
     else j2_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
   } else {
     unsigned parity = 0;
+    LaneConst K;
+    lane_const_init(*g_job.C, K, lane);
     const int m = g_job.a->mask ? (((const uint8_t*)g_job.a->mask)[g_job.env] & 3) : 3;
     const int nc = (m & 1) + ((m >> 1) & 1);
     if (g_job.C->nv == 26) {
-      if (nc == 2) activeset_env<26, 2>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
-      else if (nc == 1) activeset_env<26, 1>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
-      else activeset_env<26, 0>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
+      if (nc == 2) activeset_env<26, 2>(*g_job.C, K, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
+      else if (nc == 1) activeset_env<26, 1>(*g_job.C, K, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
+      else activeset_env<26, 0>(*g_job.C, K, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
     } else {
-      if (nc == 2) activeset_env<24, 2>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
-      else if (nc == 1) activeset_env<24, 1>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
-      else activeset_env<24, 0>(*g_job.C, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
+      if (nc == 2) activeset_env<24, 2>(*g_job.C, K, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
+      else if (nc == 1) activeset_env<24, 1>(*g_job.C, K, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
+      else activeset_env<24, 0>(*g_job.C, K, g_job.sm, *g_job.a, g_job.env, g_job.env, lane, parity);
     }
   }
   emu::W.done[lane] = true;

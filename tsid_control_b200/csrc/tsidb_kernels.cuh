@@ -153,12 +153,14 @@ TSIDB_DEV void log6_dev(const double* R, const double* p, double* out) {
  * only the placement/velocity chain (top-down) and the subtree sums (bottom-up) walk the tree. */
 /* per-body model constants staged in shared memory, one copy per CTA: a lane reads the constants of ITS body, and
  * lane-dependent addresses into __constant__ memory are served one address at a time */
-#define MDL_STRIDE 25   /* jR 9, jp 3, mass 1, com 3, inertia 9; odd: conflict-free lane <-> body reads */
+#define MDL_STRIDE 27   /* jR 9, jp 3, mass 1, com 3, inertia 9, parent, depth; odd: conflict-free lane <-> body reads */
 #define MDL_oJR 0
 #define MDL_oJP 9
 #define MDL_oMASS 12
 #define MDL_oCOM 13
 #define MDL_oI 16
+#define MDL_oPAR 25
+#define MDL_oDEP 26
 #define MDL_oPOST (TSIDB_MAX_BODIES_K * MDL_STRIDE)   /* kp_post 23, kd_post 23, ref_posture 23 */
 #define TSIDB_MAX_BODIES_K 24
 #define MDL_SIZE (MDL_oPOST + 70)
@@ -170,7 +172,9 @@ TSIDB_DEV void stage_model(const DevConst& C, double* mdl, int tid, int nthreads
     else if (j < 12) v = C.jp[b][j - 9];
     else if (j < 13) v = C.mass[b];
     else if (j < 16) v = C.com[b][j - 13];
-    else v = C.inertia[b][j - 16];
+    else if (j < 25) v = C.inertia[b][j - 16];
+    else if (j < 26) v = (double)C.parent[b];
+    else v = (double)C.depth[b];
     mdl[k] = v;
   }
   for (int k = tid; k < 69; k += nthreads) {
@@ -179,12 +183,13 @@ TSIDB_DEV void stage_model(const DevConst& C, double* mdl, int tid, int nthreads
   }
 }
 
+template <int NV>
 TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int lane) {
-  const int nb = C.nb, nv = C.nv;
+  constexpr int nb = NV - 5, nv = NV; /* bodies = floating base + NV - 6 revolute joints */
   const bool act = lane < nb;
   const int b = act ? lane : 0;
-  const int par = act && lane > 0 ? C.parent[b] : 0;
-  const int dep = act ? C.depth[b] : -1;
+  const int par = act && lane > 0 ? (int)mdl[b * MDL_STRIDE + MDL_oPAR] : 0;
+  const int dep = act ? (int)mdl[b * MDL_STRIDE + MDL_oDEP] : -1;
   const double* qs = sm + SM_oQV;
   const double* vs = sm + SM_oQV + 32;
 
@@ -391,11 +396,12 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int
       double sjl[3], sja[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) { sjl[k] = shfl(Sl_[k], j); sja[k] = shfl(Sa_[k], j); }
+      const int pj = __shfl_sync(FULL, par, j); /* parent of body j: lane j holds it (no lane-indexed constant read) */
       if (j > 0) {
         double val = dot3(sjl, Fl) + dot3(sja, Fa);
         Mm[(5 + j) * SM_LDM + 5 + b] = val;
         Mm[(5 + b) * SM_LDM + 5 + j] = val;
-        j = C.parent[j];
+        j = pj;
       }
     }
   }
@@ -562,8 +568,9 @@ TSIDB_DEV void se3_rhs(const double* fr, int f, const double* kp, const double* 
 
 /* Task right-hand sides -> sm[oBv]; Hessian dv block -> SM_oH (factored by the elimination kernel);
  * gradient -> column nEq of B (it rides through the QR as an extra column). */
+template <int NV>
 TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, const TickArgs& a, int env, int lane, int mask, int neq, int n) {
-  const int nv = C.nv, na = C.na;
+  constexpr int nv = NV, na = NV - 6;
   double* bv = sm + SM_oBv;
   const double* fr = sm + SM_oFr;
   const double* qs = sm + SM_oQV;
@@ -1095,10 +1102,13 @@ TSIDB_DEV int warp_argmin(double val, bool valid, int tiebreak) {
 struct LaneConst {
   double lb, ub;     /* joint-bound row `lane`: lb <= dv_j <= ub */
   double tmin, tmax; /* actuation row `lane`: tmin <= tau <= tmax */
+  double vmin, vmax; /* joint velocity limits of joint `lane` */
+  double fric[3];    /* friction pyramid row lane % 4 */
   double Trow[12];   /* row lane%6 of the force generator */
 };
 
 struct ASCtx {
+  int na, nv;         /* compile-time in the per-class kernels (constant-propagated through the inlined solver) */
   int ldj;            /* row stride of J2 */
   double* J2;
   const double* Ma;
@@ -1134,8 +1144,7 @@ TSIDB_DEV void cid_owner(int na, int cid, int& lane, int& slot) {
   else { const int k = cid - 36; slot = 2 + k / na; lane = k - (slot - 2) * na; }
 }
 /* bit index in the 192-bit active-set word = row numbering of tsidb_ci_row() */
-TSIDB_DEV int cid_bit(const DevConst& C, int cid) {
-  const int na = C.na, nv = C.nv;
+TSIDB_DEV int cid_bit(int na, int nv, int cid) {
   if (cid < 32) return 34 * (cid >> 4) + 17 + (cid & 15);
   if (cid < 36) return 34 * ((cid - 32) >> 1) + (((cid - 32) & 1) ? 33 : 16);
   if (cid < 36 + 2 * na) { int k = cid - 36; return 68 + k; }
@@ -1144,17 +1153,32 @@ TSIDB_DEV int cid_bit(const DevConst& C, int cid) {
   return 68 + 2 * na + side * nv + 6 + i;
 }
 
+/* the part of LaneConst that depends on the lane only: read once per kernel (lane-indexed reads of __constant__
+ * memory are served one address at a time) */
+TSIDB_DEV void lane_const_init(const DevConst& C, LaneConst& K, int lane) {
+  const int na = C.na;
+#pragma unroll
+  for (int j = 0; j < 12; j++) K.Trow[j] = C.T[lane % 6][j];
+#pragma unroll
+  for (int j = 0; j < 3; j++) K.fric[j] = C.fric[lane & 3][j];
+  K.tmin = (lane < na) ? C.tau_min[lane] : 0.0;
+  K.tmax = (lane < na) ? C.tau_max[lane] : 0.0;
+  K.vmin = (lane < na) ? C.v_min[lane] : 0.0;
+  K.vmax = (lane < na) ? C.v_max[lane] : 0.0;
+  K.lb = K.ub = 0.0;
+}
+
 /* s = CI x + ci0 for the rows this lane owns; invalid rows get +inf */
 TSIDB_DEV void eval_rows(const DevConst& C, const ASCtx& S, const LaneConst& K, int lane, int mask, double (&s)[6]) {
-  const int na = C.na, nv = C.nv;
+  const int na = S.na, nv = S.nv;
   const double* x = S.x;
 #pragma unroll
   for (int k = 0; k < 6; k++) s[k] = TS_INF;
   {
-    const int f = lane >> 4, c = (lane & 15) >> 2, k = lane & 3;
+    const int f = lane >> 4, c = (lane & 15) >> 2;
     if ((mask >> f) & 1) {
       const double* ff = x + fvar0(nv, mask, f) + 3 * c;
-      s[0] = -(C.fric[k][0] * ff[0] + C.fric[k][1] * ff[1] + C.fric[k][2] * ff[2]);
+      s[0] = -(K.fric[0] * ff[0] + K.fric[1] * ff[1] + K.fric[2] * ff[2]);
     }
   }
   if (lane < 4) {
@@ -1193,7 +1217,7 @@ TSIDB_DEV void eval_rows(const DevConst& C, const ASCtx& S, const LaneConst& K, 
 }
 /* s of one row (after a partial step) — lane-uniform call, every lane computes the same value */
 TSIDB_DEV double eval_one(const DevConst& C, const ASCtx& S, int cid, int mask) {
-  const int na = C.na, nv = C.nv;
+  const int na = S.na, nv = S.nv;
   const double* x = S.x;
   if (cid < 32) {
     const int f = cid >> 4, c = (cid & 15) >> 2, k = cid & 3;
@@ -1228,7 +1252,7 @@ TSIDB_DEV double eval_one(const DevConst& C, const ASCtx& S, int cid, int mask) 
 /* d_c = n_cid^T J2[:, c] for this lane's column c, using the sparsity of the row: 3 entries for a pyramid
  * row, 12 for a normal-force row, 1 for a joint bound; actuation rows are dense (normal built in np). */
 TSIDB_DEV double row_dot_col(const DevConst& C, const ASCtx& S, int cid, int mask, int n, int lane, double* np) {
-  const int na = C.na, nv = C.nv;
+  const int na = S.na, nv = S.nv;
   const double* Jc = S.J2 + lane;
   if (cid < 32) {
     const int f = cid >> 4, c = (cid & 15) >> 2, k = cid & 3;
@@ -1260,7 +1284,7 @@ TSIDB_DEV double row_dot_col(const DevConst& C, const ASCtx& S, int cid, int mas
 }
 /* dense normal of an actuation row into np[0..n) (all lanes cooperate) */
 TSIDB_DEV void actuation_normal(const DevConst& C, const ASCtx& S, int cid, int mask, int n, double* np, int lane) {
-  const int na = C.na, nv = C.nv;
+  const int na = S.na, nv = S.nv;
   const int q = cid - 36, side = q >= na ? 1 : 0, r = q - side * na;
   for (int k = lane; k < n; k += 32) {
     double val;
@@ -1279,12 +1303,12 @@ TSIDB_DEV void actuation_normal(const DevConst& C, const ASCtx& S, int cid, int 
 }
 
 /* wrench T f of both feet -> wr[12] (zero for a foot not in contact); lanes 0..11 */
-TSIDB_DEV void wrench_of(const DevConst& C, const LaneConst& K, const double* x, int mask, double* wr, int lane) {
+TSIDB_DEV void wrench_of(int nv, const LaneConst& K, const double* x, int mask, double* wr, int lane) {
   if (lane < 12) {
     const int f = lane / 6;
     double s = 0.0;
     if ((mask >> f) & 1) {
-      const double* ff = x + fvar0(C.nv, mask, f);
+      const double* ff = x + fvar0(nv, mask, f);
 #pragma unroll
       for (int j = 0; j < 12; j++) s += K.Trow[j] * ff[j];
     }
@@ -1356,7 +1380,7 @@ TSIDB_DEVNI void qp_delete(const ASCtx& S, int n, int& iq, int qq, int lane) {
 
 /* this lane's most violated row among the rows it owns that are neither active nor excluded; ties to the lowest
  * reference row index */
-TSIDB_DEV void pick_local(const DevConst& C, const double (&sl)[6], unsigned actbits, unsigned exclbits, int na, int lane,
+TSIDB_DEV void pick_local(const double (&sl)[6], unsigned actbits, unsigned exclbits, int na, int nv, int lane,
                           double& best, int& bcid, int& bbit) {
   best = 0.0;
   bcid = -1;
@@ -1365,7 +1389,7 @@ TSIDB_DEV void pick_local(const DevConst& C, const double (&sl)[6], unsigned act
   for (int k = 0; k < 6; k++) {
     if (!((actbits >> k) & 1u) && !((exclbits >> k) & 1u) && sl[k] < 0.0) {
       const int cid = cid_of(na, lane, k);
-      const int bit = cid_bit(C, cid);
+      const int bit = cid_bit(na, nv, cid);
       if (sl[k] < best || (sl[k] == best && bit < bbit)) { best = sl[k]; bcid = cid; bbit = bit; }
     }
   }
@@ -1374,7 +1398,7 @@ TSIDB_DEV void pick_local(const DevConst& C, const double (&sl)[6], unsigned act
 /* Active-set iterations on the reduced basis [eiquadprog-fast solve_quadprog, after the equality phase]. */
 TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, int lane, int mask, int nc, int n, int neq,
                        double c1c2, double R_norm, int& iters_out, uint64_t* act_words) {
-  const int na = C.na;
+  const int na = S.na, nv = S.nv;
   const int m = n - neq; /* reduced dimension, <= 32 */
   double* J2 = S.J2;
   double* x = S.x;
@@ -1403,7 +1427,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
   for (;;) { /* l1 */
     iter++;
     if (iter >= C.max_iter) { status = ST_MAX_ITER; break; }
-    wrench_of(C, K, x, mask, wr, lane);
+    wrench_of(S.nv, K, x, mask, wr, lane);
     __syncwarp();
     double sl[6];
     eval_rows(C, S, K, lane, mask, sl);
@@ -1415,7 +1439,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
      * before branching on the sum so that their latencies overlap */
     double best;
     int bcid, bbit;
-    pick_local(C, sl, actbits, exclbits, na, lane, best, bcid, bbit);
+    pick_local(sl, actbits, exclbits, na, nv, lane, best, bcid, bbit);
     int src = warp_argmin(best, bcid >= 0, bbit);
     double psi = warp_sum(part);
     if (fabs(psi) <= psi_thresh) { status = ST_OPTIMAL; break; }
@@ -1427,7 +1451,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
     for (;;) { /* l2 */
       /* most violated row, lowest reference index on ties */
       if (!first_pick) {
-        pick_local(C, sl, actbits, exclbits, na, lane, best, bcid, bbit);
+        pick_local(sl, actbits, exclbits, na, nv, lane, best, bcid, bbit);
         src = warp_argmin(best, bcid >= 0, bbit);
       }
       first_pick = false;
@@ -1438,7 +1462,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
       cid_owner(na, ip, ip_lane, ip_slot);
       const bool dense_row = (ip >= 36 && ip < 36 + 2 * na);
 #ifdef TSIDB_EMU_TRACE
-      if (lane == 0) printf("[emu] iter %d pick bit %d s=%.17g iq=%d\n", iter, cid_bit(C, ip), s_ip, iq);
+      if (lane == 0) printf("[emu] iter %d pick bit %d s=%.17g iq=%d\n", iter, cid_bit(na, nv, ip), s_ip, iq);
 #endif
       if (dense_row) actuation_normal(C, S, ip, mask, n, np, lane);
       if (lane == 0) { u[iq] = 0.0; A[iq] = ip; }
@@ -1584,7 +1608,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
           if (lane == ol) actbits &= ~(1u << os);
         }
         qp_delete(S, n, iq, lpos, lane);
-        wrench_of(C, K, x, mask, wr, lane);
+        wrench_of(S.nv, K, x, mask, wr, lane);
         __syncwarp();
         s_ip = eval_one(C, S, ip, mask);
       } /* l2a */
@@ -1596,7 +1620,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
   if (status == ST_OPTIMAL || status == ST_MAX_ITER) {
     uint64_t w0 = 0, w1 = 0, w2 = 0;
     for (int i = 0; i < iq; i++) {
-      const int bit = cid_bit(C, A[i]);
+      const int bit = cid_bit(na, nv, A[i]);
       if (bit < 64) w0 |= 1ull << bit;
       else if (bit < 128) w1 |= 1ull << (bit - 64);
       else w2 |= 1ull << (bit - 128);
@@ -1609,7 +1633,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
 /* ================================================================= kernel D: dynamics + assembly of one env */
 template <int NV>
 TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, const TickArgs& a, int env, int slot, int lane) {
-  const int nv = C.nv, na = C.na, nq = C.nq;
+  constexpr int nv = NV, na = NV - 6, nq = NV + 1;
   PHASE_SYNC_D();
 #ifndef TSIDB_EMU
   if (lane == 0) bulk_store_wait_read(); /* the previous env's image stores are done with this warp's shared memory */
@@ -1619,7 +1643,7 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
   if (lane < nq) sm[SM_oQV + lane] = ldin(a.q, a, env, lane, nq);
   if (lane < nv) sm[SM_oQV + 32 + lane] = a.v ? ldin(a.v, a, env, lane, nv) : 0.0;
   __syncwarp();
-  k1_dynamics(C, mdl, sm, lane);
+  k1_dynamics<NV>(C, mdl, sm, lane);
   const double* fr = sm + SM_oFr;
   if (a.o_com && lane < 9) a.o_com[eidx(a, env, lane, 9)] = fr[FR_COM + lane];
 #pragma unroll
@@ -1635,7 +1659,7 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
   const int nc = (mask & 1) + ((mask >> 1) & 1);
   const int n = nv + 12 * nc, neq = 6 + 6 * nc;
   PHASE_SYNC_D();
-  k2_assemble(C, mdl, sm, a, env, lane, mask, neq, n);
+  k2_assemble<NV>(C, mdl, sm, a, env, lane, mask, neq, n);
   /* solver image (layout a_layout(nv, nc)): the parts that do not depend on the elimination */
   const ALayout LA = a_layout(nv, nc);
   double* img = a.ws + (size_t)slot * SA_IMAGE;
@@ -1863,27 +1887,23 @@ TSIDB_DEV void j2_env(const DevConst& C, double* sg, const TickArgs& a, int slot
 
 /* ================================================================= kernel A: active set + decode of one env */
 template <int NV, int NC>
-TSIDB_DEV void activeset_env(const DevConst& C, double* sm, const TickArgs& a, int env, int slot, int lane, unsigned& parity) {
+TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const TickArgs& a, int env, int slot, int lane, unsigned& parity) {
   typedef AL<NV, NC> LA;
   constexpr int nv = NV, na = NV - 6;
   __syncwarp(); /* every lane is done with the previous env's shared memory */
 #ifndef TSIDB_EMU
   /* the 21 KB solver image arrives as ONE bulk asynchronous copy (TMA); the warp waits on its mbarrier */
   if (lane == 0) bulk_load(sm, a.ws + (size_t)slot * SA_IMAGE, LA::image * sizeof(double), sm + LA::oBar);
-  /* per-lane constants while the copy is in flight */
 #else
   for (int k = lane; k < LA::image; k += 32) sm[k] = a.ws[(size_t)slot * SA_IMAGE + k];
 #endif
-  LaneConst K;
-#pragma unroll
-  for (int j = 0; j < 12; j++) K.Trow[j] = C.T[lane % 6][j];
 #ifndef TSIDB_EMU
   mbar_wait(sm + LA::oBar, parity);
   parity ^= 1u;
 #endif
   __syncwarp();
   ASCtx S;
-  S.ldj = LA::ldj; S.aoff = LA::m + 2;
+  S.na = na; S.nv = nv; S.ldj = LA::ldj; S.aoff = LA::m + 2;
   S.J2 = sm + LA::oJ2; S.Ma = sm + LA::oMa; S.JFa = sm + LA::oJFa; S.nle_a = sm + LA::oNle; S.vj = sm + LA::oVj;
   S.x = sm + LA::oX; S.wr = sm + LA::oWr;
   S.Rp = sm + LA::oR; S.ird = sm + LA::oIRD; S.np = sm + LA::oNP; S.dd = sm + LA::oD; S.rr = sm + LA::oRR; S.vv = sm + LA::oVV;
@@ -1892,13 +1912,11 @@ TSIDB_DEV void activeset_env(const DevConst& C, double* sm, const TickArgs& a, i
   const int err = (int)sm[SA_oSc + 2], mask = (int)sm[SA_oSc + 3]; /* its contact count is NC (class-sorted slots) */
   constexpr int nc = NC, n = LA::n, neq = 6 + 6 * NC;
   K.lb = K.ub = 0.0;
-  K.tmin = (lane < na) ? C.tau_min[lane] : 0.0;
-  K.tmax = (lane < na) ? C.tau_max[lane] : 0.0;
   if (lane < na && C.use_jb) {
     /* [tsid TaskJointBounds] (v_min - v)/dt <= dv <= (v_max - v)/dt, clipped to +-1e10 */
     const double vj = S.vj[lane];
-    K.ub = fmin((C.v_max[lane] - vj) / C.jb_dt, 1e10);
-    K.lb = fmax((C.v_min[lane] - vj) / C.jb_dt, -1e10);
+    K.ub = fmin((K.vmax - vj) / C.jb_dt, 1e10);
+    K.lb = fmax((K.vmin - vj) / C.jb_dt, -1e10);
   }
   int iters = 0;
   uint64_t words[3] = {0, 0, 0};
@@ -1907,7 +1925,7 @@ TSIDB_DEV void activeset_env(const DevConst& C, double* sm, const TickArgs& a, i
   const bool ok = (status == ST_OPTIMAL || status == ST_MAX_ITER);
   const double* x = S.x;
   double* wr = S.wr;
-  if (ok) wrench_of(C, K, x, mask, wr, lane);
+  if (ok) wrench_of(nv, K, x, mask, wr, lane);
   __syncwarp();
   /* decode: dv = x[:nv], f = x[nv:], tau = h_a + M_a dv - J_a^T f  (ref:main.py:126-127) */
   if (lane < nv) a.ddq[eidx(a, env, lane, nv)] = ok ? x[lane] : 0.0;
@@ -2078,6 +2096,8 @@ tsidb_activeset_kernel(const TickArgs a) {
   int* counter = a.counter + ((NC == 2) ? 0 : ((NC == 1) ? 4 : 5));
   if (lane == 0) mbar_init(sm + LA::oBar, 1);
   __syncwarp();
+  LaneConst K;
+  lane_const_init(C, K, lane);
   unsigned parity = 0;
   for (;;) {
     int k = 0;
@@ -2086,7 +2106,7 @@ tsidb_activeset_kernel(const TickArgs a) {
     if (k >= count) break;
     const int slot = start + k;
     const int env = a.perm ? a.perm[slot] : slot;
-    activeset_env<NV, NC>(C, sm, a, env, slot, lane, parity);
+    activeset_env<NV, NC>(C, K, sm, a, env, slot, lane, parity);
   }
 }
 #endif
