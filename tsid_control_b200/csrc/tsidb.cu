@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -456,6 +457,10 @@ extern "C" int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, 
   double* s_f = h->h_out + N * (na + nv);
 
   int nch = n_envs >= 16384 ? 4 : (n_envs >= 2048 ? 2 : 1);
+  if (const char* e = getenv("TSIDB_HOST_CHUNKS")) { /* tuning knob */
+    const int v = atoi(e);
+    if (v >= 1 && v <= TSIDB_MAX_CHUNKS) nch = v;
+  }
   const int cs = ((n_envs + nch - 1) / nch + 7) & ~7;
   nch = (n_envs + cs - 1) / cs;
   for (int c = 0; c < nch; c++) {
