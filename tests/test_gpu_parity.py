@@ -413,3 +413,55 @@ def test_full_size_properties_batch65536():
     c = _run(ctrl, q[perm], v[perm], mask[perm], {k: r[perm] for k, r in refs.items()})
     for k in ("tau", "ddq", "f", "status", "iters"):
         assert np.array_equal(a[k][perm], c[k]), k
+
+
+def test_legacy_walking_batch16384_config4():
+    """BASELINE.json configs[3] at its quoted size: legacy OP3 model (robot/v0 + op3_conf), 16384 envs with per-env
+    contact phases (single/double support) and walking references (step 0.1 x 0.1275 x 0.05 m, 0.7 s,
+    ref:legacy/op3_conf.py:9-12): feasibility of every solution, and parity with the oracle on a 256-env sample."""
+    s = setup("v0")
+    n = 16384
+    ctrl = _controller("v0", n)
+    q, v = synth.random_states(s["q0"], n, 4)
+    mask, refs = synth.walking_batch(s["refs"], n, 4, 0.1, 0.1275, 0.05, 0.7, float(s["refs"]["com"][2]))
+    a = _run(ctrl, q, v, mask, refs)
+    ok = a["status"] == 0
+    assert ok.mean() > 0.99
+    f = a["f"][ok].reshape(-1, 8, 3)
+    assert (np.abs(f[:, :, 0]) <= 0.5 * f[:, :, 2] + 1e-5).all() and (np.abs(f[:, :, 1]) <= 0.5 * f[:, :, 2] + 1e-5).all()
+    fz = f[:, :, 2].reshape(-1, 2, 4).sum(-1)
+    on = np.stack([(mask[ok] & 1) != 0, (mask[ok] & 2) != 0], axis=1)
+    assert (fz[on] >= -1e-6).all() and (fz[~on] == 0).all()  # fMin = 0 in the legacy conf
+    idx = np.arange(0, n, n // 256)
+    ref = s["oracle"].batch(q[idx], v[idx], mask[idx], {k: r[idx] for k, r in refs.items()}, n_threads=8)
+    assert np.array_equal(a["status"][idx], ref["status"])
+    good = ref["status"] == 0
+    assert _err(a["ddq"][idx][good], ref["dv"][good]) < 5e-8 and _err(a["tau"][idx][good], ref["tau"][good]) < 5e-7
+
+
+def test_mixed_models_two_handles_config5():
+    """BASELINE.json configs[4]: robot/v0 and robot/v1 envs side by side (contiguous by model, one handle per model
+    on the same device, each with its own constant-memory slot and workspaces): interleaved ticks give what each
+    model gives alone."""
+    n = 3000
+    c1, c0 = _controller("v1", n), _controller("v0", n)
+    s1, s0 = setup("v1"), setup("v0")
+    q1, v1 = synth.random_states(s1["q0"], n, 9)
+    q0, v0 = synth.random_states(s0["q0"], n, 9)
+    m1, r1 = synth.walking_batch(s1["refs"], n, 9, 0.3, 0.2, 0.2, 0.5, float(s1["refs"]["com"][2]))
+    m0, r0 = synth.walking_batch(s0["refs"], n, 9, 0.1, 0.1275, 0.05, 0.7, float(s0["refs"]["com"][2]))
+    solo1, solo0 = _run(c1, q1, v1, m1, r1), _run(c0, q0, v0, m0, r0)
+    # interleaved, no synchronisation in between
+    dev = c1.device
+    c1.contact_mask, c0.contact_mask = torch.as_tensor(m1, device=dev), torch.as_tensor(m0, device=dev)
+    c1.refs = {k: torch.as_tensor(np.ascontiguousarray(a), device=dev) for k, a in r1.items()}
+    c0.refs = {k: torch.as_tensor(np.ascontiguousarray(a), device=dev) for k, a in r0.items()}
+    t = [torch.as_tensor(x, device=dev) for x in (q1, v1, q0, v0)]
+    for _ in range(3):
+        o1 = c1._tick(t[0], t[1])
+        o0 = c0._tick(t[2], t[3])
+    torch.cuda.synchronize()
+    for k in ("tau", "ddq", "f", "status", "iters"):
+        assert np.array_equal(getattr(o1, k).cpu().numpy(), solo1[k]), k
+        assert np.array_equal(getattr(o0, k).cpu().numpy(), solo0[k]), k
+    assert solo1["tau"].shape[1] == 20 and solo0["tau"].shape[1] == 18
