@@ -224,6 +224,13 @@ int tsidb_gait_step(tsidb_handle* h, int n_envs, const double* foot_lf_now, cons
 int tsidb_rollout(tsidb_handle* h, int n_envs, int n_steps, double* q, double* v, double* tau, double* ddq,
                   double* f, int32_t* status, int32_t* iters, int use_graph, void* cuda_stream);
 
+/* per-env diagnostics from a tick's auxiliary outputs (all [N][k] row-major DEVICE arrays; any output may be NULL):
+ *   cop [3]            controller.get_cop(sol)              ref:ctrl/WalkController.py:255-289
+ *   capture_point [3]  Biped.compute_capture_point(com, dcom, w)  ref:legacy/biped.py:224-227 (omega = w)
+ *   support [4]        Biped.compute_support_polygon()      ref:legacy/biped.py:229-234 (lf.xy, rf.xy)      */
+int tsidb_diagnostics(tsidb_handle* h, int n_envs, const tsidb_aux_out* aux, const uint8_t* contact_mask,
+                      double omega, double* cop, double* capture_point, double* support, void* cuda_stream);
+
 /* canonical one-sided inequality row numbering used by active_set:
  *   block 0: LF force rows (17), block 1: RF force rows (17),
  *   block 2: actuation rows (na), block 3: joint-bound rows (nv)

@@ -465,3 +465,35 @@ def test_mixed_models_two_handles_config5():
         assert np.array_equal(getattr(o1, k).cpu().numpy(), solo1[k]), k
         assert np.array_equal(getattr(o0, k).cpu().numpy(), solo0[k]), k
     assert solo1["tau"].shape[1] == 20 and solo0["tau"].shape[1] == 18
+
+
+def test_device_diagnostics_match_the_reference_formulas():
+    """tsidb_diagnostics against the formulas of ref:ctrl/WalkController.py:255-289 (CoP, evaluated here in numpy per env
+    exactly as the reference writes them) and ref:legacy/biped.py:224-234 (capture point, support polygon)."""
+    s = setup("v1")
+    n = 500
+    ctrl = _controller("v1", n)
+    q, v = synth.random_states(s["q0"], n, 17)
+    mask = np.array([3, 3, 1, 2, 3] * (n // 5), np.uint8)
+    out = _run(ctrl, q, v, mask)
+    w = float(np.sqrt(9.80665 / s["refs"]["com"][2]))
+    d = ctrl.engine.diagnostics(ctrl.last, ctrl.contact_mask, w)
+    torch.cuda.synchronize()
+    cop, cp, sup = (d[k].cpu().numpy() for k in ("cop", "capture_point", "support"))
+    for i in range(n):
+        num, den = np.zeros(2), 0.0
+        for f, key in ((0, "foot_lf"), (1, "foot_rf")):
+            if not (mask[i] >> f) & 1:
+                continue
+            wr = out["wrench"][i, 6 * f:6 * f + 6]
+            loc = np.array([wr[4] / wr[2], wr[3] / wr[2], 0.0]) if wr[2] > 1e-3 else np.zeros(3)
+            p, R = out[key][i, :3], out[key][i, 3:].reshape(3, 3).T
+            num += (R @ loc + p)[:2] * wr[2]
+            den += wr[2]
+        exp = np.r_[num / den, 0.0] if den != 0 else np.zeros(3)
+        assert np.abs(cop[i] - exp).max() < 1e-12
+        c = out["com"][i]
+        assert np.abs(cp[i] - np.r_[c[:2] + c[3:5] / w, 0.0]).max() < 1e-13
+        assert np.array_equal(sup[i], np.r_[out["foot_lf"][i, :2], out["foot_rf"][i, :2]])
+    # the host-side batched CoP (torch) agrees too
+    assert np.abs(ctrl.cop_batch().cpu().numpy() - cop).max() < 1e-12

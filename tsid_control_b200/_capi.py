@@ -241,6 +241,8 @@ def load_library() -> C.CDLL:
     lib.tsidb_gait_step.restype = ip
     lib.tsidb_rollout.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp, ip, vp]
     lib.tsidb_rollout.restype = ip
+    lib.tsidb_diagnostics.argtypes = [vp, ip, C.POINTER(TsidbAuxOut), vp, C.c_double, vp, vp, vp, vp]
+    lib.tsidb_diagnostics.restype = ip
     _LIB = lib
     return lib
 
@@ -255,5 +257,5 @@ EXPORTED_SYMBOLS = [
     "tsidb_create", "tsidb_destroy", "tsidb_last_error", "tsidb_sizes", "tsidb_set_default_refs",
     "tsidb_compute", "tsidb_compute_host", "tsidb_integrate", "tsidb_kinematics", "tsidb_ci_row",
     "tsidb_fp64_peak", "tsidb_launch_count", "tsidb_set_timing", "tsidb_last_tick_ms",
-    "tsidb_gait_reset", "tsidb_gait_state", "tsidb_gait_step", "tsidb_rollout",
+    "tsidb_gait_reset", "tsidb_gait_state", "tsidb_gait_step", "tsidb_rollout", "tsidb_diagnostics",
 ]

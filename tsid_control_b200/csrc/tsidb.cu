@@ -665,6 +665,22 @@ extern "C" int tsidb_rollout(tsidb_handle* h, int n_envs, int n_steps, double* q
   return 0;
 }
 
+extern "C" int tsidb_diagnostics(tsidb_handle* h, int n_envs, const tsidb_aux_out* aux, const uint8_t* contact_mask, double omega,
+                                 double* cop, double* capture_point, double* support, void* cuda_stream) {
+  if (!h || !aux || !aux->com || !aux->foot_lf || !aux->foot_rf || !aux->wrench) {
+    g_err = "tsidb_diagnostics: needs the four auxiliary outputs of a tick (com, foot_lf, foot_rf, wrench)";
+    return -1;
+  }
+  if (n_envs <= 0 || !(omega > 0)) { g_err = "tsidb_diagnostics: bad n_envs / omega"; return -1; }
+  CK(cudaSetDevice(h->device));
+  const int th = 128;
+  tsidb_diagnostics_kernel<<<(n_envs + th - 1) / th, th, 0, (cudaStream_t)cuda_stream>>>(
+      n_envs, aux->com, aux->foot_lf, aux->foot_rf, aux->wrench, contact_mask, omega, cop, capture_point, support);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
 extern "C" int tsidb_ci_row(const tsidb_handle* h, int block, int side, int i) {
   if (!h || block < 0 || block > 3 || side < 0 || side > 1 || i < 0) return -1;
   const int na = h->dc.na, nv = h->dc.nv;

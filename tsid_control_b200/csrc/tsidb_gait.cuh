@@ -124,7 +124,54 @@ TSIDB_DEV void gait_step_env(const GaitConf& G, const GaitState& S, const double
   if (S.fails && status && status[e] != 0) S.fails[e] += 1;
 }
 
+/* per-env diagnostics of one tick from its auxiliary outputs:
+ *   cop[3]   centre of pressure, ref:ctrl/WalkController.py:255-289: per foot in contact with f_z > 1e-3 the local
+ *            CoP (w[4]/w[2], w[3]/w[2], 0) from the wrench w = T f, mapped to the world by the sole placement,
+ *            then the f_z-weighted mean over the feet in contact.  (The reference returns None unless both feet
+ *            are in contact because it reads f_rf unconditionally; a single contact gives that foot's CoP here,
+ *            no contact gives zeros.)
+ *   cp[3]    capture point com + vcom / w with z = 0, ref:legacy/biped.py:224-227
+ *   poly[4]  support "polygon" (lf.xy, rf.xy) of ref:legacy/biped.py:229-234 */
+TSIDB_DEV void diagnostics_env(const double* com9, const double* foot_lf12, const double* foot_rf12, const double* wrench12,
+                               const uint8_t* mask, double w, double* cop, double* cp, double* poly, int e) {
+  const int m = mask ? (mask[e] & 3) : 3;
+  double nx = 0.0, ny = 0.0, den = 0.0;
+#pragma unroll
+  for (int f = 0; f < 2; f++) {
+    const double* W = wrench12 + 12 * (size_t)e + 6 * f;
+    const double* P = (f == 0 ? foot_lf12 : foot_rf12) + 12 * (size_t)e; /* p, R column-major */
+    const double fz = W[2];
+    double lx = 0.0, ly = 0.0;
+    if (fz > 1e-3) { lx = W[4] / fz; ly = W[3] / fz; }
+    /* world = R (lx, ly, 0) + p; R column-major: R[r][c] = P[3 + 3 c + r] */
+    const double wx = P[3] * lx + P[6] * ly + P[0];
+    const double wy = P[4] * lx + P[7] * ly + P[1];
+    if ((m >> f) & 1) { nx += wx * fz; ny += wy * fz; den += fz; }
+  }
+  if (cop) {
+    cop[3 * (size_t)e] = den != 0.0 ? nx / den : 0.0;
+    cop[3 * (size_t)e + 1] = den != 0.0 ? ny / den : 0.0;
+    cop[3 * (size_t)e + 2] = 0.0;
+  }
+  if (cp) {
+    const double* c = com9 + 9 * (size_t)e;
+    cp[3 * (size_t)e] = c[0] + c[3] / w;
+    cp[3 * (size_t)e + 1] = c[1] + c[4] / w;
+    cp[3 * (size_t)e + 2] = 0.0;
+  }
+  if (poly) {
+    poly[4 * (size_t)e] = foot_lf12[12 * (size_t)e]; poly[4 * (size_t)e + 1] = foot_lf12[12 * (size_t)e + 1];
+    poly[4 * (size_t)e + 2] = foot_rf12[12 * (size_t)e]; poly[4 * (size_t)e + 3] = foot_rf12[12 * (size_t)e + 1];
+  }
+}
+
 #ifndef TSIDB_EMU
+__global__ void tsidb_diagnostics_kernel(int n, const double* com9, const double* foot_lf12, const double* foot_rf12,
+                                         const double* wrench12, const uint8_t* mask, double w, double* cop, double* cp, double* poly) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  diagnostics_env(com9, foot_lf12, foot_rf12, wrench12, mask, w, cop, cp, poly, e);
+}
 __global__ void tsidb_gait_reset_kernel(int n, GaitConf G, GaitState S, const double* defaults /* 9+24+24+12+12 */,
                                         const double* phase0, const double* vcmd) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;

@@ -253,6 +253,21 @@ class TsidEngine:
                                      self._stream()), "tsidb_rollout")
         return TickOutput(**{k: o[k] for k in TickOutput.__slots__})
 
+    def diagnostics(self, out: TickOutput, contact_mask: Optional[torch.Tensor], omega: float) -> Dict[str, torch.Tensor]:
+        """CoP [N,3], capture point [N,3] and support (lf.xy, rf.xy) [N,4] of a tick computed with aux=True
+        (tsidb_diagnostics; ref:ctrl/WalkController.py:255-289, ref:legacy/biped.py:224-234)."""
+        if out.wrench is None or out.com is None:
+            raise RuntimeError("diagnostics needs a tick computed with aux outputs")
+        n = out.com.shape[0]
+        f64 = dict(dtype=torch.float64, device=self.device)
+        res = {"cop": torch.empty((n, 3), **f64), "capture_point": torch.empty((n, 3), **f64), "support": torch.empty((n, 4), **f64)}
+        a = TsidbAuxOut()
+        a.com, a.foot_lf, a.foot_rf, a.wrench = out.com.data_ptr(), out.foot_lf.data_ptr(), out.foot_rf.data_ptr(), out.wrench.data_ptr()
+        check(self.lib.tsidb_diagnostics(self.h, n, C.byref(a), contact_mask.data_ptr() if contact_mask is not None else None,
+                                         float(omega), res["cop"].data_ptr(), res["capture_point"].data_ptr(),
+                                         res["support"].data_ptr(), self._stream()), "tsidb_diagnostics")
+        return res
+
     def ci_row(self, block: int, side: int, i: int) -> int:
         return int(self.lib.tsidb_ci_row(self.h, block, side, i))
 
