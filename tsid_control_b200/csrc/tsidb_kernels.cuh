@@ -985,7 +985,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
 #define SG_oVT (SG_oTAU + 18)             /* reflectors [18][50]                        900 */
 #define SG_IMAGE (SG_oVT + 900)           /* doubles handed over per env               1672 */
 #define SG_LPART SG_oTAU                  /* [0, SG_LPART): factor part, [SG_LPART, SG_IMAGE): reflector part */
-#define TSIDB_G_WARPS 12
+#define TSIDB_G_WARPS 8
 #define SA_LDJA 20                        /* JFa row stride                                  */
 #define SA_LDM 30                         /* M_a row stride: even, 16-byte lane-strided reads are conflict-free           */
 /* Solver image / active-set shared-memory layout of one env, per contact class (nc = 2, 1, 0).  The first
