@@ -708,30 +708,52 @@ TSIDB_DEV void fwdsub_L(double (&b)[NV + 12 * NC], const double* L, const double
 
 /* c[0:K) <- (I - tau v v^T) c[0:K) with the dense reflector v (explicit zeros above its head, 1 at the head);
  * rows K.. of v are zero by construction and are not visited */
-template <int N, int K>
+template <int N, int K, bool RELOAD>
 TSIDB_DEV void reflect(double (&c)[N], const double* v, double tau) {
   static_assert((K & 1) == 0, "rows come in pairs");
   /* the reflector is read as 16-byte pairs (broadcast): half the shared-memory instructions */
   const double2* v2 = reinterpret_cast<const double2*>(v);
   double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+  if (RELOAD) {
 #pragma unroll
-  for (int k = 0; k < K; k += 4) {
-    const double2 p = v2[k >> 1];
-    w0 += p.x * c[k];
-    w1 += p.y * c[k + 1];
-    if (k + 2 < K) {
-      const double2 q = v2[(k >> 1) + 1];
-      w2 += q.x * c[k + 2];
-      w3 += q.y * c[k + 3];
+    for (int k = 0; k < K; k += 4) {
+      const double2 p = v2[k >> 1];
+      w0 += p.x * c[k];
+      w1 += p.y * c[k + 1];
+      if (k + 2 < K) {
+        const double2 q = v2[(k >> 1) + 1];
+        w2 += q.x * c[k + 2];
+        w3 += q.y * c[k + 3];
+      }
     }
-  }
-  const double w = tau * ((w0 + w1) + (w2 + w3));
-  SCHED_FENCE(); /* reload v for the update instead of keeping 50 more values live (spills otherwise) */
+    const double w = tau * ((w0 + w1) + (w2 + w3));
+    SCHED_FENCE(); /* reload v for the update instead of keeping 50 more values live (spills otherwise) */
 #pragma unroll
-  for (int k = 0; k < K; k += 2) {
-    const double2 p = v2[k >> 1];
-    c[k] -= w * p.x;
-    c[k + 1] -= w * p.y;
+    for (int k = 0; k < K; k += 2) {
+      const double2 p = v2[k >> 1];
+      c[k] -= w * p.x;
+      c[k + 1] -= w * p.y;
+    }
+  } else {
+    /* the lighter classes have the registers to keep the reflector between the two passes */
+    double2 p[K / 2];
+#pragma unroll
+    for (int k = 0; k < K / 2; k++) p[k] = v2[k];
+#pragma unroll
+    for (int k = 0; k < K; k += 4) {
+      w0 += p[k >> 1].x * c[k];
+      w1 += p[k >> 1].y * c[k + 1];
+      if (k + 2 < K) {
+        w2 += p[(k >> 1) + 1].x * c[k + 2];
+        w3 += p[(k >> 1) + 1].y * c[k + 3];
+      }
+    }
+    const double w = tau * ((w0 + w1) + (w2 + w3));
+#pragma unroll
+    for (int k = 0; k < K; k += 2) {
+      c[k] -= w * p[k >> 1].x;
+      c[k + 1] -= w * p[k >> 1].y;
+    }
   }
 }
 
@@ -897,8 +919,8 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
       if (lane == 0) { tauq[i] = tau; Rd[i] = beta; }
       __syncwarp();
       if (lane > i && lane <= neq) {
-        if (top) reflect<N, NV>(b, Vt + i * LDV, tau);
-        else reflect<N, N>(b, Vt + i * LDV, tau);
+        if (top) reflect<N, NV, (NC == 2)>(b, Vt + i * LDV, tau);
+        else reflect<N, N, (NC == 2)>(b, Vt + i * LDV, tau);
       }
     }
     __syncwarp();
