@@ -1225,9 +1225,14 @@ TSIDB_DEV void eval_rows(const DevConst& C, const ASCtx& S, const LaneConst& K, 
         t0 += m0.x * x0.x; t1 += m0.y * x0.y; t2 += m1.x * x1.x; t3 += m1.y * x1.y;
       }
       for (; j < nv / 2; j++) { const double2 m0 = Mr[j], x0 = x2[j]; t0 += m0.x * x0.x; t1 += m0.y * x0.y; }
-      double t = (t0 + t1) + (t2 + t3);
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0;
 #pragma unroll
-      for (int q = 0; q < 12; q++) t -= S.JFa[q * SA_LDJA + lane] * S.wr[q];
+      for (int q = 0; q < 12; q += 3) {
+        u0 += S.JFa[q * SA_LDJA + lane] * S.wr[q];
+        u1 += S.JFa[(q + 1) * SA_LDJA + lane] * S.wr[q + 1];
+        u2 += S.JFa[(q + 2) * SA_LDJA + lane] * S.wr[q + 2];
+      }
+      const double t = ((t0 + t1) + (t2 + t3)) - ((u0 + u1) + u2);
       s[2] = t - K.tmin;
       s[3] = K.tmax - t;
     }
@@ -1331,8 +1336,11 @@ TSIDB_DEV void wrench_of(int nv, const LaneConst& K, const double* x, int mask, 
     double s = 0.0;
     if ((mask >> f) & 1) {
       const double* ff = x + fvar0(nv, mask, f);
+      /* three independent chains (the solver is bound by dependent fp64 latency, not by throughput) */
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
-      for (int j = 0; j < 12; j++) s += K.Trow[j] * ff[j];
+      for (int j = 0; j < 12; j += 3) { s0 += K.Trow[j] * ff[j]; s1 += K.Trow[j + 1] * ff[j + 1]; s2 += K.Trow[j + 2] * ff[j + 2]; }
+      s = (s0 + s1) + s2;
     }
     wr[lane] = s;
   }
@@ -1504,14 +1512,24 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
         if (iq < m) {
           const int c0 = iq >> 1, c1 = (m + 1) >> 1;
           const double2* d2 = reinterpret_cast<const double2*>(dd);
-          double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0; /* both rows in one loop: four independent chains */
-          for (int c = c0; c < c1; c++) {
+          /* both rows in one loop, column pairs alternating between two accumulator sets: eight independent chains */
+          double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, a2 = 0.0, a3 = 0.0, b2 = 0.0, b3 = 0.0;
+          int c = c0;
+          for (; c + 1 < c1; c += 2) {
+            const double2 j0 = Jr0[c], j1 = Jr1[c], dv = d2[c];
+            const double2 k0 = Jr0[c + 1], k1 = Jr1[c + 1], ev = d2[c + 1];
+            a0 += j0.x * dv.x; a1 += j0.y * dv.y;
+            b0 += j1.x * dv.x; b1 += j1.y * dv.y;
+            a2 += k0.x * ev.x; a3 += k0.y * ev.y;
+            b2 += k1.x * ev.x; b3 += k1.y * ev.y;
+          }
+          if (c < c1) {
             const double2 j0 = Jr0[c], j1 = Jr1[c], dv = d2[c];
             a0 += j0.x * dv.x; a1 += j0.y * dv.y;
             b0 += j1.x * dv.x; b1 += j1.y * dv.y;
           }
-          z0 = h0 ? a0 + a1 : 0.0;
-          z1 = h1 ? b0 + b1 : 0.0;
+          z0 = h0 ? (a0 + a1) + (a2 + a3) : 0.0;
+          z1 = h1 ? (b0 + b1) + (b2 + b3) : 0.0;
         }
         /* r = R^-1 d[0:iq] (back substitution, lane <-> row) */
         {
@@ -1572,13 +1590,14 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
             const double beta = (d0 >= 0.0) ? -nrm : nrm;
             degenerate = !(fabs(beta) > TS_EPS * R_norm);
             if (!degenerate) {
-              const double tauh = (beta - d0) / beta;
-              const double scal = 1.0 / (d0 - beta);
-              /* v_c = d_c * scal (c > iq), v_iq = 1;  w_k = sum_c J2[k][c] v_c = (z_k - beta J2[k][iq]) * scal;
-               * J2[k][c] -= tau w_k v_c: lanes over rows, 16-byte read-modify-write of the row */
-              if (lane < m) vv[lane] = (lane < iq) ? 0.0 : ((lane == iq) ? 1.0 : dl * scal);
-              const double w0 = h0 ? tauh * (z0 - beta * J2[lane * S.ldj + iq]) * scal : 0.0;
-              const double w1 = h1 ? tauh * (z1 - beta * J2[(lane + 32) * S.ldj + iq]) * scal : 0.0;
+              /* Householder H = I - tau v v^T with v = (1, d_c / (d0 - beta)), tau = (beta - d0) / beta.  With
+               * u = (d0 - beta, d_c) (unscaled) and rho = 1 / (beta (d0 - beta)):
+               *   J2[k][c] -= tau (sum_c' J2[k][c'] v_c') v_c  =  J2[k][c] + rho (z_k - beta J2[k][iq]) u_c
+               * (sum_c' J2[k][c'] d_c' = z_k): one reciprocal on the critical path instead of two divisions */
+              const double rho = 1.0 / (beta * (d0 - beta));
+              if (lane < m) vv[lane] = (lane < iq) ? 0.0 : ((lane == iq) ? d0 - beta : dl);
+              const double w0 = h0 ? -rho * (z0 - beta * J2[lane * S.ldj + iq]) : 0.0;
+              const double w1 = h1 ? -rho * (z1 - beta * J2[(lane + 32) * S.ldj + iq]) : 0.0;
               __syncwarp();
               {
                 const int c0 = iq >> 1, c1 = (m + 1) >> 1;
