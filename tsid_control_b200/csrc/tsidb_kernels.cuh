@@ -910,12 +910,15 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
       /* dependent equality row [eiquadprog add_constraint: |d(iq)| <= eps * R_norm] */
       if (fabs(beta) <= TS_EPS * R_norm && err == ST_OPTIMAL) err = ST_ERROR;
       R_norm = fmax(R_norm, fabs(beta));
-      const double tau = (beta - alpha) / beta;
-      const double scal = 1.0 / (alpha - beta);
-      for (int k = lane; k < LDV; k += 32) {
-        const bool in_span = k < n && ((k >= lo && k < NV) || (!top && k > head));
-        Vt[i * LDV + k] = (k == head) ? 1.0 : (in_span ? colp[k] * scal : 0.0);
+      /* UNSCALED Householder vector u = x - beta e_head, H = I - kappa u u^T with kappa = -1 / (beta u_head):
+       * the vector can be published as soon as beta is known, and the one reciprocal (instead of two divisions)
+       * overlaps with the dot products of the reflection */
+      const double uh = alpha - beta;
+      for (int k = lane; k < N; k += 32) {
+        const bool in_span = (k >= lo && k < NV) || (!top && k > head);
+        Vt[i * LDV + k] = (k == head) ? uh : (in_span ? colp[k] : 0.0);
       }
+      const double tau = -1.0 / (beta * uh);
       if (lane == 0) { tauq[i] = tau; Rd[i] = beta; }
       __syncwarp();
       if (lane > i && lane <= neq) {
@@ -962,7 +965,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
   double y0 = (lane < n) ? gv[lane] : 0.0;
   double y1 = (lane + 32 < n) ? gv[lane + 32] : 0.0;
   for (int i = neq - 1; i >= 0; i--) {
-    const double v0 = Vt[i * LDV + lane];
+    const double v0 = (lane < N) ? Vt[i * LDV + lane] : 0.0; /* a reflector row holds N entries */
     const double v1 = (lane + 32 < N) ? Vt[i * LDV + lane + 32] : 0.0;
     const double w = tauq[i] * warp_sum(v0 * y0 + v1 * y1);
     y0 -= w * v0;
@@ -1837,8 +1840,8 @@ TSIDB_DEV void j2_columns(const DevConst& C, double* sg, double* img, int lane, 
       const int lo = top ? i + 1 : NCM;            /* dv rows lo..NV-1 */
       const int flo = top ? N : head + 1;          /* force rows flo..N-1 */
       const double2* v2 = reinterpret_cast<const double2*>(Vt + i * NS);
-      /* the head row is still zero here (no reflector applied so far touches it) and v[head] = 1;
-       * reflector entries come in pairs (16-byte broadcast reads) */
+      /* the head row is still zero here (no reflector applied so far touches it); the reflectors are unscaled
+       * (H = I - kappa u u^T, u_head = alpha - beta); entries come in pairs (16-byte broadcast reads) */
       double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
 #pragma unroll
       for (int kk = (lo & ~1); kk < NV; kk += 2) {
@@ -1853,7 +1856,7 @@ TSIDB_DEV void j2_columns(const DevConst& C, double* sg, double* img, int lane, 
         if (kk & 2) w3 += p.y * q[kk + 1]; else w1 += p.y * q[kk + 1];
       }
       const double w = tauq[i] * ((w0 + w1) + (w2 + w3));
-      q[head] = -w;
+      q[head] = -w * Vt[i * NS + head];
 #pragma unroll
       for (int kk = (lo & ~1); kk < NV; kk += 2) {
         const double2 p = v2[kk >> 1];
