@@ -952,6 +952,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
     if (lane < neq) Rd[lane] = 1.0 / Rd[lane];
     __syncwarp();
     double accv = rhs;
+#pragma unroll
     for (int i = 0; i < neq; i++) {
       const double wi = shfl(accv, i) * Rd[i];
       if (lane == i) accv = wi;
@@ -964,6 +965,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
   /* ---- w0 = Q w_hat: reflectors in reverse, lanes over rows ---- */
   double y0 = (lane < n) ? gv[lane] : 0.0;
   double y1 = (lane + 32 < n) ? gv[lane + 32] : 0.0;
+#pragma unroll
   for (int i = neq - 1; i >= 0; i--) {
     const double v0 = (lane < N) ? Vt[i * LDV + lane] : 0.0; /* a reflector row holds N entries */
     const double v1 = (lane + 32 < N) ? Vt[i * LDV + lane + 32] : 0.0;
@@ -982,7 +984,8 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
     for (int k = i; k < 12; k++) acc += lfinv_sm[k * 12 + i] * w0v[NV + 12 * s + k];
     x[NV + lane] = acc;
   }
-  for (int k = NV - 1; k >= 0; k--) {
+#pragma unroll
+  for (int k = NV - 1; k >= 0; k--) { /* unrolled: the loads are hoisted, the chain per step is shuffle + multiply + FMA */
     const double xk = shfl(y0, k) * ild[k];
     if (lane == k) y0 = xk;
     else if (lane < k) y0 -= L[k * SM_LDM + lane] * xk;
