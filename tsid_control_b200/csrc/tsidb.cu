@@ -456,17 +456,28 @@ extern "C" int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, 
   double* s_ddq = h->h_out + N * na;
   double* s_f = h->h_out + N * (na + nv);
 
+  /* chunk boundaries: the first chunk's H2D copy and the last chunk's D2H copy cannot overlap with kernels, so for
+   * large batches those two chunks are small (1/8 of the batch each) and the middle ones large (3/8 each) */
   int nch = n_envs >= 16384 ? 4 : (n_envs >= 2048 ? 2 : 1);
-  if (const char* e = getenv("TSIDB_HOST_CHUNKS")) { /* tuning knob */
+  bool tapered = nch == 4;
+  if (const char* e = getenv("TSIDB_HOST_CHUNKS")) { /* tuning knob: equal chunks */
     const int v = atoi(e);
-    if (v >= 1 && v <= TSIDB_MAX_CHUNKS) nch = v;
+    if (v >= 1 && v <= TSIDB_MAX_CHUNKS) { nch = v; tapered = false; }
   }
-  const int cs = ((n_envs + nch - 1) / nch + 7) & ~7;
-  nch = (n_envs + cs - 1) / cs;
+  size_t bound[TSIDB_MAX_CHUNKS + 1];
+  bound[0] = 0;
+  if (tapered) {
+    const size_t e8 = (N / 8 + 7) & ~(size_t)7;
+    bound[1] = e8; bound[2] = (N / 2 + 7) & ~(size_t)7; bound[3] = N - e8; bound[4] = N;
+  } else {
+    const size_t cs = ((N + nch - 1) / nch + 7) & ~(size_t)7;
+    nch = (int)((N + cs - 1) / cs);
+    for (int c = 1; c <= nch; c++) bound[c] = (c * cs < N) ? c * cs : N;
+  }
   for (int c = 0; c < nch; c++) {
     cudaStream_t st = h->stream[c % TSIDB_HOST_STREAMS];
-    const size_t o = (size_t)c * cs;
-    const int m = (int)((N - o < (size_t)cs) ? N - o : (size_t)cs);
+    const size_t o = bound[c];
+    const int m = (int)(bound[c + 1] - bound[c]);
     for (int s = 0; s < 8; s++) {
       if (!segs[s].src) continue;
       const size_t cnt = (size_t)m * segs[s].nd, eo = off[s] + o * segs[s].nd;
