@@ -648,7 +648,17 @@ extern "C" int tsidb_rollout(tsidb_handle* h, int n_envs, int n_steps, double* q
   /* the step is the same every time (all state lives in device memory): capture it once, replay it */
   cudaStream_t cap = st;
   bool own = false;
-  if (!cap) { CK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking)); own = true; } /* the legacy stream cannot be captured */
+  if (!cap) {
+    /* the legacy default stream cannot be captured: replay on a stream of our own, ordered after the work the
+     * caller has already queued on the default stream (and synchronised before returning, below) */
+    CK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    own = true;
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev, st));
+    CK(cudaStreamWaitEvent(cap, ev, 0));
+    CK(cudaEventDestroy(ev));
+  }
   const int timing = h->timing;
   h->timing = 0;
   const int64_t l0 = h->launches;
