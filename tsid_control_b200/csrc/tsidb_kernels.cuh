@@ -115,6 +115,8 @@ TSIDB_DEV void log6_dev(const double* R, const double* p, double* out) {
   else th = acos((tr - 1.0) / 2.0);
   double w[3];
   const double prec3 = 1.220703125e-4;
+  double st, ct; /* one sincos for every use below (the SE3 logs sit on the critical path of the assembly) */
+  sincos(th, &st, &ct);
   if (th >= PI - 1e-2) {
     double cphi = -(tr - 1.0) / 2.0;
     double beta = th * th / (1.0 + cphi);
@@ -123,7 +125,7 @@ TSIDB_DEV void log6_dev(const double* R, const double* p, double* out) {
     w[1] = (R[2] > R[6] ? 1.0 : -1.0) * (t1 > 0 ? sqrt(t1) : 0.0);
     w[2] = (R[3] > R[1] ? 1.0 : -1.0) * (t2 > 0 ? sqrt(t2) : 0.0);
   } else {
-    double t = ((th > prec3) ? th / sin(th) : 1.0) / 2.0;
+    double t = ((th > prec3) ? th / st : 1.0) / 2.0;
     w[0] = t * (R[7] - R[5]);
     w[1] = t * (R[2] - R[6]);
     w[2] = t * (R[3] - R[1]);
@@ -133,7 +135,6 @@ TSIDB_DEV void log6_dev(const double* R, const double* p, double* out) {
     alpha = 1.0 - t2 / 12.0 - t2 * t2 / 720.0;
     beta = 1.0 / 12.0 + t2 / 720.0;
   } else {
-    double st = sin(th), ct = cos(th);
     alpha = th * st / (2.0 * (1.0 - ct));
     beta = 1.0 / t2 - st / (2.0 * th * (1.0 - ct));
   }
@@ -636,12 +637,20 @@ TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, con
     }
     /* H is symmetric: lane j computes the entries (i, j) for the nv/2 + 1 rows i = j, j+1, ... (cyclic) and
      * stores each one on both sides of the diagonal; every unordered pair is covered */
+#pragma unroll 2
     for (int t = 0; t <= nv / 2; t++) {
       int i = j + t;
       if (i >= nv) i -= nv;
-      double sf = 0.0, scm = 0.0, sam = 0.0;
+      /* four independent chains for the 12 foot rows (dependent fp64 latency, not throughput, is the limit) */
+      double sf0 = 0.0, sf1 = 0.0, sf2 = 0.0, sf3 = 0.0, scm = 0.0, sam = 0.0;
 #pragma unroll
-      for (int r = 0; r < 12; r++) sf += JF[r * TSIDB_NVX + i] * jf[r];
+      for (int r = 0; r < 12; r += 4) {
+        sf0 += JF[r * TSIDB_NVX + i] * jf[r];
+        sf1 += JF[(r + 1) * TSIDB_NVX + i] * jf[r + 1];
+        sf2 += JF[(r + 2) * TSIDB_NVX + i] * jf[r + 2];
+        sf3 += JF[(r + 3) * TSIDB_NVX + i] * jf[r + 3];
+      }
+      const double sf = (sf0 + sf1) + (sf2 + sf3);
 #pragma unroll
       for (int r = 0; r < 3; r++) scm += Jcom[r * TSIDB_NVX + i] * jc[r];
       double hij = C.w_foot * sf + C.w_com * scm;
@@ -1685,6 +1694,19 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
 #ifndef TSIDB_EMU
   if (lane == 0) bulk_store_wait_read(); /* the previous env's image stores are done with this warp's shared memory */
   __syncwarp();
+#endif
+#ifndef TSIDB_EMU
+  /* the per-env references are read after K1: pull their lines into L2 now (row-major layout: contiguous per env) */
+  if (!a.layout && !a.kin_only) {
+    const char* pf = nullptr;
+    if (lane < 2 && a.r_foot[lane]) pf = (const char*)(a.r_foot[lane] + (size_t)env * 24);
+    else if (lane < 4 && lane >= 2 && a.r_foot[lane - 2]) pf = (const char*)(a.r_foot[lane - 2] + (size_t)env * 24) + 128;
+    else if (lane < 6 && lane >= 4 && a.r_contact[lane - 4]) pf = (const char*)(a.r_contact[lane - 4] + (size_t)env * 12);
+    else if (lane == 6 && a.r_com) pf = (const char*)(a.r_com + (size_t)env * 9);
+    else if (lane == 7 && a.r_posture) pf = (const char*)(a.r_posture + (size_t)env * na);
+    else if (lane == 8 && a.r_posture) pf = (const char*)(a.r_posture + (size_t)env * na) + 128;
+    if (pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+  }
 #endif
   /* stage q, v */
   if (lane < nq) sm[SM_oQV + lane] = ldin(a.q, a, env, lane, nq);
