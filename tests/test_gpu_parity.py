@@ -497,3 +497,51 @@ def test_device_diagnostics_match_the_reference_formulas():
         assert np.array_equal(sup[i], np.r_[out["foot_lf"][i, :2], out["foot_rf"][i, :2]])
     # the host-side batched CoP (torch) agrees too
     assert np.abs(ctrl.cop_batch().cpu().numpy() - cop).max() < 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 7, 33, 1185])
+def test_ragged_batch_sizes(n):
+    """Batch sizes that do not fill a warp round, a CTA or the persistent grid (148 x 8 + 1): every env still gets
+    its own answer, equal to the oracle's."""
+    s = setup("v1")
+    ctrl = _controller("v1", n)
+    q, v = synth.random_states(s["q0"], n, 40 + n)
+    mask = np.array([3, 1, 2, 0, 3, 2, 1][:7] * (n // 7 + 1), np.uint8)[:n]
+    out = _run(ctrl, q, v, mask)
+    idx = np.unique(np.r_[np.arange(min(n, 16)), np.arange(max(0, n - 16), n)])
+    ref = s["oracle"].batch(q[idx], v[idx], mask[idx], s["refs"], n_threads=4)
+    assert np.array_equal(out["status"][idx], ref["status"])
+    ok = ref["status"] == 0
+    assert _err(out["tau"][idx][ok], ref["tau"][ok]) < 5e-8 and _err(out["ddq"][idx][ok], ref["dv"][ok]) < 5e-8
+    assert np.array_equal(out["iters"][idx][ok] > 0, np.ones(ok.sum(), bool))
+
+
+def test_api_misuse_is_reported_not_executed():
+    """Error behaviour of the boundary: negative return + message, no launch (ref: the tsid binding raises on bad
+    sizes; per-env solver failures are NOT errors, they are status values — test_infeasible_envs_...)."""
+    import ctypes as C
+
+    from tsid_control_b200._capi import TsidbError, TsidbRefs
+
+    s = setup("v1")
+    n = 8
+    ctrl = _controller("v1", n)
+    e = ctrl.engine
+    q, v = synth.random_states(s["q0"], 2 * n, 3)
+    dev = e.device
+    with pytest.raises(TsidbError, match="max_envs"):
+        e.compute(torch.as_tensor(q, device=dev), torch.as_tensor(v, device=dev))          # batch larger than the handle
+    with pytest.raises((TypeError, ValueError)):
+        e.compute(torch.as_tensor(q[:n, :-1].copy(), device=dev), torch.as_tensor(v[:n], device=dev))  # wrong nq
+    with pytest.raises((TypeError, ValueError)):
+        e.compute(torch.as_tensor(q[:n], device=dev).float(), torch.as_tensor(v[:n], device=dev))      # wrong dtype
+    r = TsidbRefs()
+    rc = e.lib.tsidb_compute(e.h, n, 7, 0, 0, None, C.byref(r), 0, 0, 0, 0, 0, None, None, None)     # null pointers, bad layout
+    assert rc < 0 and e.lib.tsidb_last_error()
+    assert e.lib.tsidb_compute_host(e.h, 0, 0, 0, None, None, 0, 0, 0, 0, 0, None) < 0
+    with pytest.raises(TsidbError, match="gait_reset"):
+        e._gait_n = n
+        e.rollout(torch.as_tensor(q[:n], device=dev), torch.as_tensor(v[:n], device=dev), 2)
+    # the handle still works afterwards
+    out = _run(ctrl, q[:n], v[:n], np.full(n, 3, np.uint8))
+    assert (out["status"] == 0).all()
