@@ -1,31 +1,31 @@
 /* tsidb_kernels.cuh — device code of the batched TSID tick for sm_100a.
  *
- * One warp solves one robot instance ("env"); a persistent CTA of
- * TSIDB_WARPS_PER_BLOCK warps per SM pulls env indices from a global counter.
- * All arithmetic is fp64.  The env's whole working set (mass matrix, Jacobians,
- * factor, null-space basis, active-set factor: SM_PER_ENV doubles = 37.8 KB) stays in
- * shared memory from the first load of q to the last store of tau; HBM sees only
- * the algorithmic inputs and outputs (1.8 KB per tick).
+ * One warp solves one robot instance ("env"); all arithmetic is fp64.  The tick is a pipeline of persistent
+ * kernels (one CTA per SM), each with the thread mapping, register budget and warp count that suit its stage;
+ * an env's state moves from stage to stage as an "image" in HBM that the consumer pulls into shared memory
+ * with one bulk asynchronous copy (TMA).  DESIGN.md §4 has the table with sizes and measured times.
  *
- * Phases (reference function each one replaces):
- *   K1 dynamics   lane <-> body.  World-frame FK, velocities, zero-acceleration drift,
- *                 composite inertias and forces accumulated up the tree, then M (CRBA),
- *                 nle (RNEA), frame Jacobians, CoM/Jcom, centroidal angular rows.
- *                 [tsid::RobotWrapper::computeAllTerms inside computeProblemData, ref:main.py:119]
- *   K2 assembly   task right-hand sides (SE3 log, PD laws), the dv block of the Hessian
- *                 (the force blocks are constant and pre-factored on the host), gradient.
- *                 [task.compute() + SolverHQuadProgFast H/g build, ref:main.py:119,121]
- *   K3 QP         Goldfarb-Idnani dual active set, same pivot rules as eiquadprog-fast
- *                 (most violated row, lowest index on ties; min ratio drop).  The 6+6nc
- *                 equalities are always active, so they are eliminated once by a
- *                 Householder QR of L^-1 CE^T (lane <-> column) instead of 18 Givens
- *                 sweeps; the iterations then run on the n x (n-nEq) null-space basis
- *                 J2 = L^-T Q2, whose column count na+6nc is <= 32: one lane per column.
- *                 [SolverHQuadProgFast::solve -> EiquadprogFast::solve_quadprog, ref:main.py:121]
- *   K4 decode     dv, f, tau = h_a + M_a dv - J_a^T f.   [ref:main.py:126-127]
+ *   kernel D  tsidb_dynamics_kernel        (reference function each phase replaces)
+ *     K1 dynamics   lane <-> body.  World-frame FK, velocities, zero-acceleration drift, composite inertias and
+ *                   forces accumulated up the tree, then M (CRBA), nle (RNEA), frame Jacobians, CoM/Jcom,
+ *                   centroidal angular rows.
+ *                   [tsid::RobotWrapper::computeAllTerms inside computeProblemData, ref:main.py:119]
+ *     K2 assembly   task right-hand sides (SE3 log, PD laws), the dv block of the Hessian (the force blocks are
+ *                   constant and pre-factored on the host), gradient.
+ *                   [task.compute() + SolverHQuadProgFast H/g build, ref:main.py:119,121]
+ *   kernels E, G, A  the QP: Goldfarb-Idnani dual active set with the pivot rules of eiquadprog-fast (most
+ *                   violated row, lowest index on ties; min ratio drop)
+ *                   [SolverHQuadProgFast::solve -> EiquadprogFast::solve_quadprog, ref:main.py:121]
+ *     E  tsidb_eliminate_kernel   the 6+6nc equalities are always active, so they are eliminated once: Cholesky of
+ *                   H, Householder QR of L^-1 CE^T (lane <-> column), x0 — instead of 18 Givens sweeps.
+ *     G  tsidb_j2_kernel          the n x (n-nEq) null-space basis J2 = L^-T Q2 (na+6nc <= 32 columns), one thread
+ *                   per column.
+ *     A  tsidb_activeset_kernel   the iterations on J2 (one lane per column / per row), then
+ *        decode     dv, f, tau = h_a + M_a dv - J_a^T f.   [ref:main.py:126-127]
+ *   E and A are instantiated and launched per contact class (nc = 2, 1, 0): every size is a compile-time constant.
  *
- * The file also compiles for the host under tests/emu (lock-step warp emulator) so that
- * the kernel logic can be exercised without a GPU; TSIDB_EMU selects that build.
+ * The file also compiles for the host under tests/emu (lock-step warp emulator that poisons shared memory with
+ * NaN) so that the kernel logic can be exercised without a GPU; TSIDB_EMU selects that build.
  */
 #ifndef TSIDB_KERNELS_CUH_
 #define TSIDB_KERNELS_CUH_
@@ -42,9 +42,9 @@ __constant__ DevConst g_const[TSIDB_MAX_SLOTS];
 
 #define FULL 0xffffffffu
 #define SCHED_FENCE() asm volatile("" ::: "memory")
-/* CTA-wide phase alignment: the warps of a CTA work on different envs but run the same phase at the same
- * time, so an instruction-cache line fetched by one warp serves all of them (the kernel is fetch-bound
- * otherwise: profiles/ r1b).  A no-op in the single-warp host emulation. */
+/* Optional CTA-wide phase alignment (TSIDB_LOCK_D / TSIDB_LOCK_E in tsidb_const.h, both off): the warps of a CTA
+ * work on different envs but run the same phase at the same time, so an instruction-cache line fetched by one
+ * warp serves all of them.  A no-op in the single-warp host emulation. */
 #ifdef TSIDB_EMU
 #define PHASE_SYNC_D() ((void)0)
 #define PHASE_SYNC_E() ((void)0)
@@ -66,11 +66,6 @@ TSIDB_DEV double shfl(double x, int src) { return __shfl_sync(FULL, x, src); }
 TSIDB_DEV double warp_sum(double x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
-  return x;
-}
-TSIDB_DEV double warp_max(double x) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(FULL, x, o));
   return x;
 }
 TSIDB_DEV void cross3(const double* a, const double* b, double* o) {
