@@ -33,7 +33,7 @@ static bool g_slot_used[8][TSIDB_MAX_SLOTS]; /* per device */
 struct tsidb_handle {
   int device, slot, max_envs, sm_count;
   DevConst dc;
-  int32_t* counter;      /* device, 8 per chunk: [0],[4],[5] work counters of the active-set kernels, [1..3] class sizes */
+  int32_t* counter;      /* device, 12 per chunk: work counters of the active-set ([0],[4],[5]) and elimination ([8..10]) kernels, [1..3] class sizes */
   double* ws;            /* device: solver images, SA_IMAGE doubles per slot */
   double* ws2;           /* device: factor images, SG_IMAGE doubles per slot */
   double* ws3;           /* device: assembly images, SE_IMAGE doubles per slot */
@@ -219,7 +219,7 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
   const size_t smem_g = (size_t)TSIDB_G_WARPS * (SG_IMAGE + 2) * sizeof(double);
   CK(cudaFuncSetAttribute(tsidb_j2_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   CK(cudaFuncSetAttribute(tsidb_j2_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  CK(cudaMalloc(&h->counter, 8 * TSIDB_MAX_CHUNKS * sizeof(int32_t)));
+  CK(cudaMalloc(&h->counter, 12 * TSIDB_MAX_CHUNKS * sizeof(int32_t)));
   CK(cudaMalloc(&h->ws, (size_t)max_envs * SA_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->ws2, (size_t)max_envs * SG_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->ws3, (size_t)max_envs * SE_IMAGE * sizeof(double)));
@@ -296,7 +296,7 @@ extern "C" int tsidb_set_default_refs(tsidb_handle* h, const double* com9, const
 static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base = 0, int chunk = 0) {
   CK(cudaSetDevice(h->device));
   if (base + a.n_envs > h->max_envs) { g_err = "n_envs exceeds the handle's max_envs (workspace size)"; return -1; }
-  int32_t* counter = h->counter + 8 * chunk; /* [0],[4],[5]: work counters per class, [1..3]: class sizes */
+  int32_t* counter = h->counter + 12 * chunk; /* [0],[4],[5]: active-set work counters per class, [1..3]: class sizes, [8..10]: elimination work counters */
   int32_t* perm = h->perm + base;
   int32_t* cls_pos = h->cls_pos + base;
   a.counter = counter;
@@ -309,7 +309,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   const bool timed = h->timing && !a.kin_only && chunk == 0 && base == 0;
   if (timed) CK(cudaEventRecord(h->ev[0], st));
   if (!a.kin_only) {
-    CK(cudaMemsetAsync(counter, 0, 8 * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(counter, 0, 12 * sizeof(int32_t), st));
     if (a.mask) {
       /* class sort (double support, single support, flight) -> slot order */
       const int th = 256;

@@ -2108,6 +2108,8 @@ tsidb_eliminate_kernel(const TickArgs a) {
   if (lane == 0) mbar_init(sm + SE_oBar, 1);
   __syncwarp();
   unsigned parity = 0;
+#if TSIDB_LOCK_E
+  /* phase lock-step needs every warp of the CTA in every round: static rounds, idle warps repeat the last slot */
   const int per_round = gridDim.x * WARPS;
   const int rounds = (count + per_round - 1) / per_round;
   for (int r = 0; r < rounds; r++) {
@@ -2115,6 +2117,17 @@ tsidb_eliminate_kernel(const TickArgs a) {
     if (k >= count) k = count - 1;
     eliminate_env<NV, NC>(C, lfinv_sm, sm, a, start + k, lane, parity);
   }
+#else
+  /* free-running warps pull slots from a work counter of the class */
+  int* counter = a.counter + 8 + NC;
+  for (;;) {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(counter, 1);
+    k = __shfl_sync(FULL, k, 0);
+    if (k >= count) break;
+    eliminate_env<NV, NC>(C, lfinv_sm, sm, a, start + k, lane, parity);
+  }
+#endif
 }
 
 template <int NV>
