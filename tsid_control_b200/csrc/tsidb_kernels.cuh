@@ -1019,10 +1019,10 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
 #define SG_LPART SG_oTAU                  /* [0, SG_LPART): factor part, [SG_LPART, SG_IMAGE): reflector part */
 #define TSIDB_G_WARPS 8
 #define SA_LDJA 20                        /* JFa row stride                                  */
-#define SA_LDM 30                         /* M_a row stride: even, 16-byte lane-strided reads are conflict-free           */
+#define SA_LDM 26                         /* M_a row stride: even with SA_LDM/2 odd, 16-byte lane-strided reads are conflict-free */
 /* Solver image / active-set shared-memory layout of one env, per contact class (nc = 2, 1, 0).  The first
  * `image` doubles are what the producer kernels write to HBM and what one bulk copy brings in; the work arrays
- * follow.  J2's row stride ldj is even (16-byte row accesses) with ldj/2 odd, which keeps both the row-wise
+ * follow.  J2's row stride ldj (m or m + 2) is even (16-byte row accesses) with ldj/2 odd, which keeps both the row-wise
  * 16-byte accesses (lane <-> row) and the column-wise 8-byte ones (lane <-> column) free of bank conflicts.
  * The status block comes first so that it sits at the same place for every class. */
 struct ALayout {
@@ -1036,12 +1036,12 @@ TSIDB_HD constexpr ALayout a_layout(int nv, int nc) {
   const int na = nv - 6;
   L.n = nv + 12 * nc;
   L.m = na + 6 * nc;
-  L.ldj = ((((L.m + 2) / 2) & 1) != 0) ? L.m + 2 : L.m + 4;
+  L.ldj = (((L.m / 2) & 1) != 0) ? L.m : L.m + 2;
   L.oSc = 0;                              /* c1*c2, R_norm, error status, contact mask */
   L.oJ2 = 4;                              /* J2  n x ldj                               */
   L.oMa = L.oJ2 + L.n * L.ldj;            /* M_a na x SA_LDM (rows 6.. of M)           */
-  L.oJFa = L.oMa + na * SA_LDM;           /* JF columns 6.., 12 x SA_LDJA              */
-  L.oNle = L.oJFa + 12 * SA_LDJA;         /* nle_a                                     */
+  L.oJFa = L.oMa + na * SA_LDM;           /* JF columns 6.. of the feet in contact, in force-block order: 6 nc x SA_LDJA */
+  L.oNle = L.oJFa + 6 * nc * SA_LDJA;     /* nle_a                                     */
   L.oVj = L.oNle + even_up(na);           /* joint velocities                          */
   L.oX = L.oVj + even_up(na);             /* x                                         */
   L.image = L.oX + even_up(L.n);
@@ -1067,9 +1067,10 @@ struct AL {
 };
 #define SA_IMAGE (a_layout(TSIDB_NVX, 2).image)   /* slot stride of the solver images in HBM (largest class) */
 #define SA_oSc 0
-/* warps per CTA of the active-set kernel per contact class (shared memory: 28 / 21.6 / 15.5 KB per env) */
+/* warps per CTA of the active-set kernel per contact class (shared memory: 27.4 / 18.7 / 12.6 KB per env);
+ * multiples of 4 keep the four schedulers of an SM evenly loaded */
 #define TSIDB_AS_WARPS_DS 8
-#define TSIDB_AS_WARPS_SS 10
+#define TSIDB_AS_WARPS_SS 12
 #define TSIDB_AS_WARPS_FL 12
 
 /* ---- bulk asynchronous copy global -> shared (TMA, 1-D) completed through an mbarrier ---- */
@@ -1144,7 +1145,9 @@ struct ASCtx {
   int ldj;            /* row stride of J2 */
   double* J2;
   const double* Ma;
-  const double* JFa;
+  const double* JFa;  /* rows of the feet in contact, in force-block order */
+  int nfr;            /* 6 * (feet in contact) rows of JFa */
+  int wro;            /* wrench of force block 0 starts at wr[wro] (wr is per foot: LF 0..5, RF 6..11) */
   const double* nle_a;
   const double* vj;
   double* x;
@@ -1236,11 +1239,14 @@ TSIDB_DEV void eval_rows(const DevConst& C, const ASCtx& S, const LaneConst& K, 
       }
       for (; j < nv / 2; j++) { const double2 m0 = Mr[j], x0 = x2[j]; t0 += m0.x * x0.x; t1 += m0.y * x0.y; }
       double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+      const double* wb = S.wr + S.wro;
 #pragma unroll
       for (int q = 0; q < 12; q += 3) {
-        u0 += S.JFa[q * SA_LDJA + lane] * S.wr[q];
-        u1 += S.JFa[(q + 1) * SA_LDJA + lane] * S.wr[q + 1];
-        u2 += S.JFa[(q + 2) * SA_LDJA + lane] * S.wr[q + 2];
+        if (q < S.nfr) {
+          u0 += S.JFa[q * SA_LDJA + lane] * wb[q];
+          u1 += S.JFa[(q + 1) * SA_LDJA + lane] * wb[q + 1];
+          u2 += S.JFa[(q + 2) * SA_LDJA + lane] * wb[q + 2];
+        }
       }
       const double t = ((t0 + t1) + (t2 + t3)) - ((u0 + u1) + u2);
       s[2] = t - K.tmin;
@@ -1275,7 +1281,8 @@ TSIDB_DEV double eval_one(const DevConst& C, const ASCtx& S, int cid, int mask) 
     double t = S.nle_a[r];
     for (int j = 0; j < nv; j++) t += Mr[j] * x[j];
 #pragma unroll
-    for (int q = 0; q < 12; q++) t -= S.JFa[q * SA_LDJA + r] * S.wr[q];
+    for (int q = 0; q < 12; q++)
+      if (q < S.nfr) t -= S.JFa[q * SA_LDJA + r] * S.wr[S.wro + q];
     return side ? (C.tau_max[r] - t) : (t - C.tau_min[r]);
   }
   {
@@ -1328,11 +1335,10 @@ TSIDB_DEV void actuation_normal(const DevConst& C, const ASCtx& S, int cid, int 
     if (k < nv) val = S.Ma[r * SA_LDM + k];
     else {
       const int o = k - nv;
-      const int f = (mask == 3) ? (o / 12) : ((mask & 1) ? 0 : 1);
-      const int j = o % 12;
+      const int blk = o / 12, j = o % 12; /* force block = row block of JFa */
       double t = 0.0;
 #pragma unroll
-      for (int kk = 0; kk < 6; kk++) t += C.T[kk][j] * S.JFa[(f * 6 + kk) * SA_LDJA + r];
+      for (int kk = 0; kk < 6; kk++) t += C.T[kk][j] * S.JFa[(blk * 6 + kk) * SA_LDJA + r];
       val = -t;
     }
     np[k] = side ? -val : val;
@@ -1731,9 +1737,11 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
     const int r = k / SA_LDM, c = k % SA_LDM;
     img[LA.oMa + k] = (c < nv) ? sm[SM_oM + (6 + r) * SM_LDM + c] : 0.0;
   }
-  for (int k = lane; k < 12 * SA_LDJA; k += 32) {
+  for (int k = lane; k < 6 * nc * SA_LDJA; k += 32) {
+    /* rows of the feet in contact, in force-block order (block 0 = LF if it is in contact, else RF) */
     const int q = k / SA_LDJA, r = k % SA_LDJA;
-    img[LA.oJFa + k] = (r < na) ? sm[SM_oJF + q * TSIDB_NVX + 6 + r] : 0.0;
+    const int f = (q < 6) ? ((mask & 1) ? 0 : 1) : 1;
+    img[LA.oJFa + k] = (r < na) ? sm[SM_oJF + (f * 6 + q % 6) * TSIDB_NVX + 6 + r] : 0.0;
   }
   if (lane < na) { img[LA.oNle + lane] = sm[SM_oNle + 6 + lane]; img[LA.oVj + lane] = sm[SM_oQV + 32 + 6 + lane]; }
   if (lane == 0) img[SA_oSc + 3] = (double)mask;
@@ -1967,7 +1975,7 @@ TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const 
 #endif
   __syncwarp();
   ASCtx S;
-  S.na = na; S.nv = nv; S.ldj = LA::ldj; S.aoff = LA::m + 2;
+  S.na = na; S.nv = nv; S.ldj = LA::ldj; S.aoff = LA::m + 2; S.nfr = 6 * NC;
   S.J2 = sm + LA::oJ2; S.Ma = sm + LA::oMa; S.JFa = sm + LA::oJFa; S.nle_a = sm + LA::oNle; S.vj = sm + LA::oVj;
   S.x = sm + LA::oX; S.wr = sm + LA::oWr;
   S.Rp = sm + LA::oR; S.ird = sm + LA::oIRD; S.np = sm + LA::oNP; S.dd = sm + LA::oD; S.rr = sm + LA::oRR; S.vv = sm + LA::oVV;
@@ -1975,6 +1983,7 @@ TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const 
   const double c1c2 = sm[SA_oSc], R_norm = sm[SA_oSc + 1];
   const int err = (int)sm[SA_oSc + 2], mask = (int)sm[SA_oSc + 3]; /* its contact count is NC (class-sorted slots) */
   constexpr int nc = NC, n = LA::n, neq = 6 + 6 * NC;
+  S.wro = (NC == 1 && !(mask & 1)) ? 6 : 0;
   K.lb = K.ub = 0.0;
   if (lane < na && C.use_jb) {
     /* [tsid TaskJointBounds] (v_min - v)/dt <= dv <= (v_max - v)/dt, clipped to +-1e10 */
@@ -2007,7 +2016,7 @@ TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const 
       for (int j = 0; j < nv; j += 2) { s0 += Mr[j] * x[j]; s1 += (j + 1 < nv) ? Mr[j + 1] * x[j + 1] : 0.0; }
       double s = s0 + s1;
 #pragma unroll
-      for (int q = 0; q < 12; q++) s -= S.JFa[q * SA_LDJA + lane] * wr[q];
+      for (int q = 0; q < 6 * NC; q++) s -= S.JFa[q * SA_LDJA + lane] * wr[S.wro + q];
       val = s;
     }
     a.tau[eidx(a, env, lane, na)] = val;
