@@ -110,7 +110,7 @@ extern "C" int emu_tick(const TickArgs* a_in, double* sm_out) {
   TickArgs a = *a_in;
   stage_model(g_const[0], g_mdl, 0, 1);
   for (int k = 0; k < 144; k++) g_lfinv[k] = g_const[0].Lfinv[k / 12][k % 12];
-  const int smn = a_layout(TSIDB_NVX, 2).per_env > SE_PER_ENV ? a_layout(TSIDB_NVX, 2).per_env : SE_PER_ENV;
+  const int smn = a_layout(TSIDB_NVX, 2).per_env > e_per_env(TSIDB_NVX, 2) ? a_layout(TSIDB_NVX, 2).per_env : e_per_env(TSIDB_NVX, 2);
   double* sm = (double*)calloc(smn, sizeof(double));
   double* ws = (double*)calloc((size_t)a.n_envs * SA_IMAGE, sizeof(double));
   double* ws2 = (double*)calloc((size_t)a.n_envs * SG_IMAGE, sizeof(double));
@@ -134,7 +134,7 @@ extern "C" int emu_tick(const TickArgs* a_in, double* sm_out) {
   free(ws3);
   return rc;
 }
-extern "C" int emu_sm_per_env() { return a_layout(TSIDB_NVX, 2).per_env > SE_PER_ENV ? a_layout(TSIDB_NVX, 2).per_env : SE_PER_ENV; }
+extern "C" int emu_sm_per_env() { return a_layout(TSIDB_NVX, 2).per_env > e_per_env(TSIDB_NVX, 2) ? a_layout(TSIDB_NVX, 2).per_env : e_per_env(TSIDB_NVX, 2); }
 
 /* the gait phase machine of tsidb_gait.cuh, one env after the other: reset when defaults81 is given, else one step */
 extern "C" int emu_gait(int n, const double* gconf6, double* phi, uint8_t* mask, double* vcmd, double* lipm, double* origin,

@@ -208,14 +208,12 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
 #undef TSIDB_AS_ATTR
   CK(cudaFuncSetAttribute(tsidb_dynamics_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaFuncSetAttribute(tsidb_dynamics_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const size_t smem_e = ((size_t)TSIDB_E_WARPS * SE_PER_ENV + 144) * sizeof(double);
-  const size_t smem_el = ((size_t)TSIDB_E_WARPS_LIGHT * SE_PER_ENV + 144) * sizeof(double);
-  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<26, 2, TSIDB_E_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<24, 2, TSIDB_E_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<26, 1, TSIDB_E_WARPS_LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_el));
-  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<24, 1, TSIDB_E_WARPS_LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_el));
-  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<26, 0, TSIDB_E_WARPS_LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_el));
-  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<24, 0, TSIDB_E_WARPS_LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_el));
+#define TSIDB_E_SMEM(NV, NC, W) (((size_t)(W) * e_per_env(NV, NC) + 144) * sizeof(double))
+#define TSIDB_E_ATTR(NV, NC, W) \
+  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<NV, NC, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSIDB_E_SMEM(NV, NC, W)))
+  TSIDB_E_ATTR(26, 2, TSIDB_E_WARPS); TSIDB_E_ATTR(26, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_ATTR(26, 0, TSIDB_E_WARPS_LIGHT);
+  TSIDB_E_ATTR(24, 2, TSIDB_E_WARPS); TSIDB_E_ATTR(24, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_ATTR(24, 0, TSIDB_E_WARPS_LIGHT);
+#undef TSIDB_E_ATTR
   const size_t smem_g = (size_t)TSIDB_G_WARPS * (SG_IMAGE + 2) * sizeof(double);
   CK(cudaFuncSetAttribute(tsidb_j2_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   CK(cudaFuncSetAttribute(tsidb_j2_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
@@ -335,21 +333,15 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
     /* one launch per contact class; the class sizes are only known on the device, so every class gets a full
      * persistent grid and the CTAs of an empty class return at once.  Without a mask all envs are double support. */
     const int blocks = h->sm_count;
-    const size_t smem = ((size_t)TSIDB_E_WARPS * SE_PER_ENV + 144) * sizeof(double);
-    const size_t smem_l = ((size_t)TSIDB_E_WARPS_LIGHT * SE_PER_ENV + 144) * sizeof(double);
+#define TSIDB_E_LAUNCH(NV, NC, W) tsidb_eliminate_kernel<NV, NC, W><<<blocks, 32 * (W), TSIDB_E_SMEM(NV, NC, W), st>>>(a)
     if (h->dc.nv == 26) {
-      tsidb_eliminate_kernel<26, 2, TSIDB_E_WARPS><<<blocks, 32 * TSIDB_E_WARPS, smem, st>>>(a);
-      if (a.perm) {
-        tsidb_eliminate_kernel<26, 1, TSIDB_E_WARPS_LIGHT><<<blocks, 32 * TSIDB_E_WARPS_LIGHT, smem_l, st>>>(a);
-        tsidb_eliminate_kernel<26, 0, TSIDB_E_WARPS_LIGHT><<<blocks, 32 * TSIDB_E_WARPS_LIGHT, smem_l, st>>>(a);
-      }
+      TSIDB_E_LAUNCH(26, 2, TSIDB_E_WARPS);
+      if (a.perm) { TSIDB_E_LAUNCH(26, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_LAUNCH(26, 0, TSIDB_E_WARPS_LIGHT); }
     } else {
-      tsidb_eliminate_kernel<24, 2, TSIDB_E_WARPS><<<blocks, 32 * TSIDB_E_WARPS, smem, st>>>(a);
-      if (a.perm) {
-        tsidb_eliminate_kernel<24, 1, TSIDB_E_WARPS_LIGHT><<<blocks, 32 * TSIDB_E_WARPS_LIGHT, smem_l, st>>>(a);
-        tsidb_eliminate_kernel<24, 0, TSIDB_E_WARPS_LIGHT><<<blocks, 32 * TSIDB_E_WARPS_LIGHT, smem_l, st>>>(a);
-      }
+      TSIDB_E_LAUNCH(24, 2, TSIDB_E_WARPS);
+      if (a.perm) { TSIDB_E_LAUNCH(24, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_LAUNCH(24, 0, TSIDB_E_WARPS_LIGHT); }
     }
+#undef TSIDB_E_LAUNCH
     CK(cudaGetLastError());
     h->launches += a.perm ? 3 : 1;
   }

@@ -10,7 +10,7 @@
 #define TSIDB_MRED 32  /* n - nEq = na + 6*nc <= 32: one lane per reduced coordinate       */
 #define TSIDB_WARPS_PER_BLOCK 12  /* dynamics kernel */
 #define TSIDB_E_WARPS 8            /* elimination kernel, double support */
-#define TSIDB_E_WARPS_LIGHT 8      /* elimination kernel, single support and flight */
+#define TSIDB_E_WARPS_LIGHT 12     /* elimination kernel, single support and flight */
 /* CTA-wide phase lock-step (all warps of a CTA run the same phase at the same time, so one instruction-cache
  * line serves all of them).  It paid off for the fused 215 KB kernel of the first generation; with one kernel
  * per stage the code fits the instruction cache and free-running warps hide each other's latencies better
@@ -89,16 +89,7 @@ struct DevConst {
 #define SE_oBm (SE_oNle + 8)        /* contact-motion rhs 2 x 6                 12 */
 #define SE_oSc (SE_oBm + 12)        /* contact mask, pad                         2 */
 #define SE_IMAGE (SE_oSc + 2)       /* doubles handed over per env            1248 */
-#define SE_oILD (SE_IMAGE)          /* 1/L_ii                                   26 */
-#define SE_oTAU (SE_oILD + 26)      /* Householder tau                          18 */
-#define SE_oRD (SE_oTAU + 18)       /* diagonal of R1 (beta), then 1/beta       18 */
-#define SE_oVT (SE_oRD + 18)        /* dense reflectors [18][50]               900 */
-#define SE_oR1 (SE_oVT + 900)       /* R1 [18][SM_LDB]                         342 */
-#define SE_oCOL (SE_oR1 + 342)      /* published column                         50 */
-#define SE_oW0 (SE_oCOL + 50)       /* w0                                       64 */
-#define SE_oX (SE_oW0 + 64)         /* x0                                       50 */
-#define SE_oBar (SE_oX + 50)        /* mbarrier of the image load                2 */
-#define SE_PER_ENV (SE_oBar + 2)    /*                                        2718 */
+
 struct TickArgs {
   int32_t n_envs, layout, pad_;
   const double* q;

@@ -771,9 +771,33 @@ TSIDB_DEV void store_R1(double* R1, const double (&b)[N], int lane) {
   for (int k = 0; k < NEQ; k++) R1[k * SM_LDB + lane] = b[head_row<NV, NCM>(k)];
 }
 
+/* shared-memory layout of one env in the elimination kernel per contact class: the assembly image (SE_*, the same
+ * for every class) followed by class-sized work arrays; the reflector rows have the class's own stride N */
+TSIDB_HD constexpr int e_per_env(int nv, int nc) {
+  const int n = nv + 12 * nc, neq = 6 + 6 * nc;
+  return SE_IMAGE + 26 + 18 + 18 + neq * n + neq * SM_LDB + n + 64 + n + 2;
+}
+template <int NV, int NC>
+struct EL {
+  enum : int {
+    N = NV + 12 * NC, NEQ = 6 + 6 * NC,
+    oILD = SE_IMAGE,          /* 1/L_ii                           26 */
+    oTAU = oILD + 26,         /* Householder coefficients         18 */
+    oRD = oTAU + 18,          /* diagonal of R1, then its inverse 18 */
+    oVT = oRD + 18,           /* reflectors [NEQ][N]                 */
+    oR1 = oVT + NEQ * N,      /* R1 [NEQ][SM_LDB]                    */
+    oCOL = oR1 + NEQ * SM_LDB, /* published column                 N */
+    oW0 = oCOL + N,           /* w0                               64 */
+    oX = oW0 + 64,            /* x0                                N */
+    oBar = oX + N,            /* mbarrier of the image load        2 */
+    per_env = oBar + 2
+  };
+  static_assert(per_env == e_per_env(NV, NC) && (oVT % 2) == 0 && (oCOL % 2) == 0, "layout");
+};
+
 /* The equality elimination.  In: the assembly image (SE_*: H dv block, gradient, base rows of M, JF, base nle,
  * contact-motion rhs).  Out: x = x0 (the equality-constrained minimiser), the Cholesky factor L (in place of H,
- * SE_oILD) and the Householder reflectors of B = L^-1 CE^T (SE_oVT, SE_oTAU) from which the J2 kernel builds
+ * EL::oILD) and the Householder reflectors of B = L^-1 CE^T (EL::oVT, EL::oTAU) from which the J2 kernel builds
  * the null-space basis, the c1*c2
  * product and R_norm; returns 0 or an HQP error status.
  *
@@ -784,17 +808,18 @@ template <int NV, int NC>
 TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm, int lane, int mask, double& c1c2, double& R_norm_out) {
   constexpr int N = NV + 12 * NC;   /* n: the contact class fixes every size at compile time */
   constexpr int nc = NC, ncm = 6 * NC, neq = 6 + 6 * NC, n = N;
-  constexpr int LDV = SG_LDV;       /* reflector row stride (the J2 kernel reads the same layout) */
+  typedef EL<NV, NC> LE;
+  constexpr int LDV = N;            /* reflector row stride in shared memory (SG_LDV in the factor image) */
   double* L = sm + SE_oH;
-  double* ild = sm + SE_oILD;
-  double* tauq = sm + SE_oTAU;
-  double* Rd = sm + SE_oRD;
-  double* Vt = sm + SE_oVT;   /* [neq][N] dense reflectors */
-  double* R1 = sm + SE_oR1;   /* [18][SM_LDB] */
+  double* ild = sm + LE::oILD;
+  double* tauq = sm + LE::oTAU;
+  double* Rd = sm + LE::oRD;
+  double* Vt = sm + LE::oVT;   /* [neq][N] dense reflectors */
+  double* R1 = sm + LE::oR1;   /* [18][SM_LDB] */
   double* gv = sm + SE_oG;    /* gradient, later Q^T w_unc / w_hat */
-  double* colp = sm + SE_oCOL;
-  double* w0v = sm + SE_oW0;
-  double* x = sm + SE_oX;
+  double* colp = sm + LE::oCOL;
+  double* w0v = sm + LE::oW0;
+  double* x = sm + LE::oX;
   const double* Mm = sm + SE_oMu;
   const double* JF = sm + SE_oJF;
   const double* bmot = sm + SE_oBm;
@@ -1773,11 +1798,12 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
 /* ================================================================= kernel E: equality elimination of one env */
 template <int NV, int NC>
 TSIDB_DEV void eliminate_env(const DevConst& C, const double* lfinv_sm, double* sm, const TickArgs& a, int slot, int lane, unsigned& parity) {
-  const int nv = C.nv;
+  constexpr int nv = NV;
+  typedef EL<NV, NC> LE;
   __syncwarp(); /* every lane is done with the previous env's shared memory */
 #ifndef TSIDB_EMU
-  if (lane == 0) bulk_load(sm, a.ws3 + (size_t)slot * SE_IMAGE, SE_IMAGE * sizeof(double), sm + SE_oBar);
-  mbar_wait(sm + SE_oBar, parity);
+  if (lane == 0) bulk_load(sm, a.ws3 + (size_t)slot * SE_IMAGE, SE_IMAGE * sizeof(double), sm + LE::oBar);
+  mbar_wait(sm + LE::oBar, parity);
   parity ^= 1u;
 #else
   for (int k = lane; k < SE_IMAGE; k += 32) sm[k] = a.ws3[(size_t)slot * SE_IMAGE + k];
@@ -1789,7 +1815,7 @@ TSIDB_DEV void eliminate_env(const DevConst& C, const double* lfinv_sm, double* 
   const int err = k3_eliminate<NV, NC>(C, lfinv_sm, sm, lane, mask, c1c2, R_norm);
   typedef AL<NV, NC> LA;
   double* img = a.ws + (size_t)slot * SA_IMAGE;
-  for (int k = lane; k < even_up(n); k += 32) img[LA::oX + k] = (k < n) ? sm[SE_oX + k] : 0.0;
+  for (int k = lane; k < even_up(n); k += 32) img[LA::oX + k] = (k < n) ? sm[LE::oX + k] : 0.0;
   if (lane == 0) { img[SA_oSc] = c1c2; img[SA_oSc + 1] = R_norm; img[SA_oSc + 2] = (double)err; }
   /* factor image (layout SG_*) for the J2 kernel */
   double* fimg = a.ws2 + (size_t)slot * SG_IMAGE;
@@ -1797,9 +1823,12 @@ TSIDB_DEV void eliminate_env(const DevConst& C, const double* lfinv_sm, double* 
     const int r = k / SG_LDL, c = k % SG_LDL;
     fimg[SG_oL + k] = (c <= r) ? sm[SE_oH + r * SM_LDM + c] : 0.0;
   }
-  if (lane < nv) fimg[SG_oILD + lane] = sm[SE_oILD + lane];
-  if (lane < 18) fimg[SG_oTAU + lane] = sm[SE_oTAU + lane];
-  for (int k = lane; k < 18 * SG_LDV; k += 32) fimg[SG_oVT + k] = sm[SE_oVT + k];
+  if (lane < nv) fimg[SG_oILD + lane] = sm[LE::oILD + lane];
+  if (lane < LE::NEQ) fimg[SG_oTAU + lane] = sm[LE::oTAU + lane];
+  for (int k = lane; k < LE::NEQ * LE::N; k += 32) {
+    const int i = k / LE::N, j = k % LE::N; /* restride the reflector rows: N in shared memory, SG_LDV in the image */
+    fimg[SG_oVT + i * SG_LDV + j] = sm[LE::oVT + k];
+  }
   __syncwarp();
 }
 
@@ -2105,16 +2134,17 @@ __global__ void __launch_bounds__(32 * WARPS, 1)
 tsidb_eliminate_kernel(const TickArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double* sm = smem + wid * SE_PER_ENV;
+  typedef EL<NV, NC> LE;
+  double* sm = smem + wid * LE::per_env;
   const DevConst& C = g_const[a.slot];
   int start, count;
   class_range<NC>(a, start, count);
   if (count <= 0) return;
   /* CTA-shared copy of the constant Lf^-1 (read with lane-dependent indices) */
-  double* lfinv_sm = smem + WARPS * SE_PER_ENV;
+  double* lfinv_sm = smem + WARPS * LE::per_env;
   for (int k = threadIdx.x; k < 144; k += blockDim.x) lfinv_sm[k] = C.Lfinv[k / 12][k % 12];
   __syncthreads();
-  if (lane == 0) mbar_init(sm + SE_oBar, 1);
+  if (lane == 0) mbar_init(sm + LE::oBar, 1);
   __syncwarp();
   unsigned parity = 0;
 #if TSIDB_LOCK_E
