@@ -8,7 +8,7 @@
 #define TSIDB_NVX 26   /* largest nv this build keeps in shared memory (robot/v1)          */
 #define TSIDB_NX 50    /* nv + 24                                                          */
 #define TSIDB_MRED 32  /* n - nEq = na + 6*nc <= 32: one lane per reduced coordinate       */
-#define TSIDB_WARPS_PER_BLOCK 12  /* dynamics kernel */
+#define TSIDB_WARPS_PER_BLOCK 16  /* dynamics kernel */
 #define TSIDB_E_WARPS 8            /* elimination kernel, double support */
 #define TSIDB_E_WARPS_LIGHT 12     /* elimination kernel, single support and flight */
 /* CTA-wide phase lock-step (all warps of a CTA run the same phase at the same time, so one instruction-cache
@@ -56,17 +56,18 @@ struct DevConst {
 /* shared-memory layout of one env in the dynamics kernel (doubles) */
 #define SM_LDM 27
 #define SM_LDB 19
-#define SM_oM 0                         /* M        26 x 27                       702 */
-#define SM_oJF (SM_oM + 702)            /* JF       2 x 6 x 26                    312 */
+#define SM_oM 0                         /* region 0, reused in time: subtree-sum scratch of K1 (609) -> M 26 x 27 -> dv
+                                           block of the Hessian 26 x 27                                        702 */
+#define SM_oH SM_oM
+#define SM_oGv (SM_oM + 702)            /* gradient (follows H: one bulk store)    50 */
+#define SM_oJF (SM_oGv + 50)            /* JF       2 x 6 x 26                    312 */
 #define SM_oJcom (SM_oJF + 312)         /* Jcom     3 x 26                         78 */
 #define SM_oAg (SM_oJcom + 78)          /* Ag_ang   3 x 26                         78 */
 #define SM_oNle (SM_oAg + 78)           /* nle      26                             26 */
 #define SM_oBv (SM_oNle + 26)           /* task vectors                            64 */
 #define SM_oFr (SM_oBv + 64)            /* frames and CoM                          64 */
 #define SM_oQV (SM_oFr + 64)            /* q (32) and v (32)                       64 */
-#define SM_oH (SM_oQV + 64)             /* dv block of the Hessian 26 x 27; subtree-sum scratch of K1   702 */
-#define SM_oGv (SM_oH + 702)            /* gradient                                50 */
-#define SM_PER_ENV (SM_oGv + 50)        /*                                       2140 */
+#define SM_PER_ENV (SM_oQV + 64)        /*                                       1438 */
 /* task vectors inside oBv */
 #define BV_MOT 0   /* 2 x 6 contact motion rhs, by foot */
 #define BV_FOOT 12 /* 2 x 6 foot task rhs               */

@@ -1753,15 +1753,20 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
   const int mask = a.mask ? (a.mask[env] & 3) : 3;
   const int nc = (mask & 1) + ((mask >> 1) & 1);
   const int n = nv + 12 * nc, neq = 6 + 6 * nc;
-  PHASE_SYNC_D();
-  k2_assemble<NV>(C, mdl, sm, a, env, lane, mask, neq, n);
-  /* solver image (layout a_layout(nv, nc)): the parts that do not depend on the elimination */
+  /* M shares its shared-memory region with the Hessian block that K2 is about to write: the rows of M that the
+   * later stages need leave for their images now */
   const ALayout LA = a_layout(nv, nc);
   double* img = a.ws + (size_t)slot * SA_IMAGE;
+  double* eimg = a.ws3 + (size_t)slot * SE_IMAGE;
   for (int k = lane; k < na * SA_LDM; k += 32) {
     const int r = k / SA_LDM, c = k % SA_LDM;
     img[LA.oMa + k] = (c < nv) ? sm[SM_oM + (6 + r) * SM_LDM + c] : 0.0;
   }
+  for (int k = lane; k < 162; k += 32) eimg[SE_oMu + k] = sm[SM_oM + k];
+  __syncwarp();
+  PHASE_SYNC_D();
+  k2_assemble<NV>(C, mdl, sm, a, env, lane, mask, neq, n);
+  /* solver image (layout a_layout(nv, nc)): the parts that do not depend on the elimination */
   for (int k = lane; k < 6 * nc * SA_LDJA; k += 32) {
     /* rows of the feet in contact, in force-block order (block 0 = LF if it is in contact, else RF) */
     const int q = k / SA_LDJA, r = k % SA_LDJA;
@@ -1771,22 +1776,19 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
   if (lane < na) { img[LA.oNle + lane] = sm[SM_oNle + 6 + lane]; img[LA.oVj + lane] = sm[SM_oQV + 32 + 6 + lane]; }
   if (lane == 0) img[SA_oSc + 3] = (double)mask;
   /* assembly image (layout SE_*) for the elimination kernel */
-  double* eimg = a.ws3 + (size_t)slot * SE_IMAGE;
 #ifndef TSIDB_EMU
-  /* the three contiguous pieces (H | g, base rows of M, JF) leave as bulk asynchronous stores (TMA); the next env
+  /* the two contiguous pieces (H | g, JF) leave as bulk asynchronous stores (TMA); the next env
    * of this warp waits for them to have read shared memory before it overwrites it */
   __syncwarp();
   if (lane == 0) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     bulk_store(eimg + SE_oH, sm + SM_oH, (702 + TSIDB_NX) * sizeof(double)); /* SM_oGv follows SM_oH, SE_oG follows SE_oH */
-    bulk_store(eimg + SE_oMu, sm + SM_oM, 162 * sizeof(double));
     bulk_store(eimg + SE_oJF, sm + SM_oJF, 312 * sizeof(double));
     bulk_store_commit();
   }
 #else
   for (int k = lane; k < 702; k += 32) eimg[SE_oH + k] = sm[SM_oH + k];
   for (int k = lane; k < TSIDB_NX; k += 32) eimg[SE_oG + k] = sm[SM_oGv + k];
-  for (int k = lane; k < 162; k += 32) eimg[SE_oMu + k] = sm[SM_oM + k];
   for (int k = lane; k < 312; k += 32) eimg[SE_oJF + k] = sm[SM_oJF + k];
 #endif
   if (lane < 8) eimg[SE_oNle + lane] = (lane < 6) ? sm[SM_oNle + lane] : 0.0;
