@@ -775,17 +775,19 @@ TSIDB_DEV void store_R1(double* R1, const double (&b)[N], int lane) {
  * for every class) followed by class-sized work arrays; the reflector rows have the class's own stride N */
 TSIDB_HD constexpr int e_per_env(int nv, int nc) {
   const int n = nv + 12 * nc, neq = 6 + 6 * nc;
-  return SE_IMAGE + 26 + 18 + 18 + neq * n + neq * SM_LDB + n + 64 + n + 2;
+  const int vt_own = (neq * n <= 162 + 312) ? 0 : neq * n; /* the reflectors of the light classes reuse the M_u | JF part of the image */
+  return SE_IMAGE + 26 + 18 + 18 + vt_own + neq * SM_LDB + n + 64 + n + 2;
 }
 template <int NV, int NC>
 struct EL {
   enum : int {
     N = NV + 12 * NC, NEQ = 6 + 6 * NC,
+    VT_ALIAS = (NEQ * N <= 162 + 312) ? 1 : 0, /* M_u and JF are dead once B is built; the reflectors are written after that */
     oILD = SE_IMAGE,          /* 1/L_ii                           26 */
     oTAU = oILD + 26,         /* Householder coefficients         18 */
     oRD = oTAU + 18,          /* diagonal of R1, then its inverse 18 */
-    oVT = oRD + 18,           /* reflectors [NEQ][N]                 */
-    oR1 = oVT + NEQ * N,      /* R1 [NEQ][SM_LDB]                    */
+    oVT = VT_ALIAS ? SE_oMu : oRD + 18,                 /* reflectors [NEQ][N] */
+    oR1 = VT_ALIAS ? oRD + 18 : oRD + 18 + NEQ * N,     /* R1 [NEQ][SM_LDB]    */
     oCOL = oR1 + NEQ * SM_LDB, /* published column                 N */
     oW0 = oCOL + N,           /* w0                               64 */
     oX = oW0 + 64,            /* x0                                N */
