@@ -74,3 +74,39 @@ def test_emulated_kinematics_only():
         r = s["oracle"].tick(q[i], v[i], 3, s["refs"])
         assert np.abs(out["com"][i] - r["com"]).max() < 1e-12
         assert np.abs(out["foot_rf"][i] - r["foot"][1]).max() < 1e-13
+
+
+def test_emulated_kernel_with_active_torque_bounds():
+    """Torque limits tight enough that actuation rows enter the working set: exercises the dense-row path and the
+    slack lower bound that lets the solver skip actuation rows it can prove satisfied."""
+    import copy
+    import ctypes as C
+
+    from oracle_py import Oracle
+
+    s = setup("v1")
+    cc = copy.deepcopy(s["cc"]) if False else type(s["cc"]).from_buffer_copy(bytes(s["cc"]))
+    for i in range(20):
+        cc.tau_max[i] = 0.6
+        cc.tau_min[i] = -0.6
+    orc = Oracle(s["cm"], cc, "liboracle.so")
+    emu = Emu(s["cm"], cc, s["refs"])
+    n = 20
+    q, v = synth.random_states(s["q0"], n, 33)
+    v *= 0.3
+    mask = np.array([3, 1, 2, 3] * 5, np.uint8)
+    out = emu.tick(q, v, mask)
+    hit = 0
+    for i in range(n):
+        r = orc.tick(q[i], v[i], int(mask[i]), s["refs"])
+        assert out["status"][i] == r["status"]
+        if r["status"] != 0:
+            continue
+        assert _err(out["tau"][i], r["tau"]) < 5e-7 and _err(out["ddq"][i], r["dv"]) < 5e-7
+        rows = orc.ci_rows(int(mask[i]))
+        ra = set(rows[k] for k in r["active"])
+        rb = set(bits_to_rows(orc.na, orc.nv, active_bits(out["active"][:, i])))
+        assert canonical_active(ra) == canonical_active(rb)
+        hit += any(blk == 2 for blk, _, _ in ra)
+        assert (np.abs(out["tau"][i]) <= 0.6 + 1e-7).all()
+    assert hit >= 5  # torque rows are really active in this batch
