@@ -459,7 +459,9 @@ extern "C" int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, 
   size_t bound[TSIDB_MAX_CHUNKS + 1];
   bound[0] = 0;
   if (tapered) {
-    const size_t e8 = (N / 8 + 7) & ~(size_t)7;
+    int den = 8;
+    if (const char* e = getenv("TSIDB_HOST_TAPER")) { const int v = atoi(e); if (v >= 3 && v <= 64) den = v; } /* tuning knob */
+    const size_t e8 = (N / den + 7) & ~(size_t)7;
     bound[1] = e8; bound[2] = (N / 2 + 7) & ~(size_t)7; bound[3] = N - e8; bound[4] = N;
   } else {
     const size_t cs = ((N + nch - 1) / nch + 7) & ~(size_t)7;
