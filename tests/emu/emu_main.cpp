@@ -35,8 +35,17 @@ static void lane_entry(int lane) {
   } else if (g_job.stage == 2) {
     G2Pipe P;
     P.bars = nullptr; P.next = nullptr; P.pv = P.pl = 0;
-    if (g_job.C->nv == 26) j2_env<26>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
-    else j2_env<24>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
+    const int m = g_job.a->mask ? (((const uint8_t*)g_job.a->mask)[g_job.env] & 3) : 3;
+    const int nc = (m & 1) + ((m >> 1) & 1);
+    if (g_job.C->nv == 26) {
+      if (nc == 2) j2_env<26, 2>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
+      else if (nc == 1) j2_env<26, 1>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
+      else j2_env<26, 0>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
+    } else {
+      if (nc == 2) j2_env<24, 2>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
+      else if (nc == 1) j2_env<24, 1>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
+      else j2_env<24, 0>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
+    }
   } else {
     unsigned parity = 0;
     LaneConst K;

@@ -49,6 +49,11 @@ struct tsidb_handle {
   int32_t *h_int, *d_int;    /* status, iters */
   uint64_t *h_act, *d_act;
   cudaStream_t stream[TSIDB_HOST_STREAMS];
+  /* the three contact-class chains E -> G -> A of a tick are independent: double support stays on the tick's own
+   * stream, single support and flight run on side streams (per chunk in flight), forked and joined with events */
+  cudaStream_t side[TSIDB_MAX_CHUNKS][2];
+  cudaEvent_t ev_fork[TSIDB_MAX_CHUNKS], ev_join[TSIDB_MAX_CHUNKS][2];
+  int class_streams;     /* 0: every kernel on the tick's stream (also whenever per-kernel timing is on) */
   /* gait phase machine (tsidb_gait_*): state and references, allocated at the first tsidb_gait_reset */
   GaitConf gconf;
   GaitState gait;
@@ -215,8 +220,12 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
   TSIDB_E_ATTR(24, 2, TSIDB_E_WARPS); TSIDB_E_ATTR(24, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_ATTR(24, 0, TSIDB_E_WARPS_LIGHT);
 #undef TSIDB_E_ATTR
   const size_t smem_g = (size_t)TSIDB_G_WARPS * (SG_IMAGE + 2) * sizeof(double);
-  CK(cudaFuncSetAttribute(tsidb_j2_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  CK(cudaFuncSetAttribute(tsidb_j2_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  CK((cudaFuncSetAttribute(tsidb_j2_kernel<26, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)));
+  CK((cudaFuncSetAttribute(tsidb_j2_kernel<26, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)));
+  CK((cudaFuncSetAttribute(tsidb_j2_kernel<26, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)));
+  CK((cudaFuncSetAttribute(tsidb_j2_kernel<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)));
+  CK((cudaFuncSetAttribute(tsidb_j2_kernel<24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)));
+  CK((cudaFuncSetAttribute(tsidb_j2_kernel<24, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)));
   CK(cudaMalloc(&h->counter, 12 * TSIDB_MAX_CHUNKS * sizeof(int32_t)));
   CK(cudaMalloc(&h->ws, (size_t)max_envs * SA_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->ws2, (size_t)max_envs * SG_IMAGE * sizeof(double)));
@@ -238,6 +247,15 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
   CK(cudaMallocHost(&h->h_act, 3 * sizeof(uint64_t) * max_envs));
   CK(cudaMalloc(&h->d_act, 3 * sizeof(uint64_t) * max_envs));
   for (int i = 0; i < TSIDB_HOST_STREAMS; i++) CK(cudaStreamCreateWithFlags(&h->stream[i], cudaStreamNonBlocking));
+  for (int c = 0; c < TSIDB_MAX_CHUNKS; c++) {
+    CK(cudaEventCreateWithFlags(&h->ev_fork[c], cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+      CK(cudaStreamCreateWithFlags(&h->side[c][i], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&h->ev_join[c][i], cudaEventDisableTiming));
+    }
+  }
+  h->class_streams = 1;
+  if (const char* e = getenv("TSIDB_CLASS_STREAMS")) h->class_streams = atoi(e) != 0; /* tuning knob */
   *out = h;
   return 0;
 }
@@ -252,6 +270,13 @@ extern "C" void tsidb_destroy(tsidb_handle* h) {
   cudaFreeHost(h->h_act); cudaFree(h->d_act);
   for (int i = 0; i < TSIDB_HOST_STREAMS; i++)
     if (h->stream[i]) cudaStreamDestroy(h->stream[i]);
+  for (int c = 0; c < TSIDB_MAX_CHUNKS; c++) {
+    if (h->ev_fork[c]) cudaEventDestroy(h->ev_fork[c]);
+    for (int i = 0; i < 2; i++) {
+      if (h->side[c][i]) cudaStreamDestroy(h->side[c][i]);
+      if (h->ev_join[c][i]) cudaEventDestroy(h->ev_join[c][i]);
+    }
+  }
   for (int i = 0; i < 6; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->gait_ready) {
@@ -330,48 +355,63 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   }
   if (timed) CK(cudaEventRecord(h->ev[2], st));
   if (!a.kin_only) {
-    /* one launch per contact class; the class sizes are only known on the device, so every class gets a full
-     * persistent grid and the CTAs of an empty class return at once.  Without a mask all envs are double support. */
+    /* One launch per kernel and contact class (NC = 2 double support, 1 single support, 0 flight): every size is a
+     * compile-time constant and the lighter classes fit more warps per SM.  The class sizes are only known on the
+     * device, so every class gets a full persistent grid and the CTAs of an empty class return at once.  Without
+     * a mask all envs are double support.  The chains E -> G -> A of the classes do not depend on each other: with
+     * class streams on, single support and flight run on side streams, so that the SMs a kernel's last CTAs leave
+     * idle are picked up by the next ready kernel of another class.  Per-kernel timing keeps everything on one
+     * stream, stage by stage. */
     const int blocks = h->sm_count;
-#define TSIDB_E_LAUNCH(NV, NC, W) tsidb_eliminate_kernel<NV, NC, W><<<blocks, 32 * (W), TSIDB_E_SMEM(NV, NC, W), st>>>(a)
-    if (h->dc.nv == 26) {
-      TSIDB_E_LAUNCH(26, 2, TSIDB_E_WARPS);
-      if (a.perm) { TSIDB_E_LAUNCH(26, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_LAUNCH(26, 0, TSIDB_E_WARPS_LIGHT); }
+    const int nv26 = h->dc.nv == 26;
+    const size_t smem_g = (size_t)TSIDB_G_WARPS * (SG_IMAGE + 2) * sizeof(double);
+#define TSIDB_E_LAUNCH(NV, NC, W, S) tsidb_eliminate_kernel<NV, NC, W><<<blocks, 32 * (W), TSIDB_E_SMEM(NV, NC, W), S>>>(a)
+#define TSIDB_G_LAUNCH(NV, NC, S) tsidb_j2_kernel<NV, NC><<<blocks, 32 * TSIDB_G_WARPS, smem_g, S>>>(a)
+#define TSIDB_AS_LAUNCH(NV, NC, W, S)                                                                                    \
+  tsidb_activeset_kernel<NV, NC, W><<<blocks, 32 * W, (size_t)W * a_layout(NV, NC).per_env * sizeof(double), S>>>(a)
+    auto launch_e = [&](int nc, cudaStream_t s) {
+      if (nv26) { if (nc == 2) TSIDB_E_LAUNCH(26, 2, TSIDB_E_WARPS, s); else if (nc == 1) TSIDB_E_LAUNCH(26, 1, TSIDB_E_WARPS_LIGHT, s); else TSIDB_E_LAUNCH(26, 0, TSIDB_E_WARPS_LIGHT, s); }
+      else { if (nc == 2) TSIDB_E_LAUNCH(24, 2, TSIDB_E_WARPS, s); else if (nc == 1) TSIDB_E_LAUNCH(24, 1, TSIDB_E_WARPS_LIGHT, s); else TSIDB_E_LAUNCH(24, 0, TSIDB_E_WARPS_LIGHT, s); }
+    };
+    auto launch_g = [&](int nc, cudaStream_t s) {
+      if (nv26) { if (nc == 2) TSIDB_G_LAUNCH(26, 2, s); else if (nc == 1) TSIDB_G_LAUNCH(26, 1, s); else TSIDB_G_LAUNCH(26, 0, s); }
+      else { if (nc == 2) TSIDB_G_LAUNCH(24, 2, s); else if (nc == 1) TSIDB_G_LAUNCH(24, 1, s); else TSIDB_G_LAUNCH(24, 0, s); }
+    };
+    auto launch_a = [&](int nc, cudaStream_t s) {
+      if (nv26) { if (nc == 2) TSIDB_AS_LAUNCH(26, 2, TSIDB_AS_WARPS_DS, s); else if (nc == 1) TSIDB_AS_LAUNCH(26, 1, TSIDB_AS_WARPS_SS, s); else TSIDB_AS_LAUNCH(26, 0, TSIDB_AS_WARPS_FL, s); }
+      else { if (nc == 2) TSIDB_AS_LAUNCH(24, 2, TSIDB_AS_WARPS_DS, s); else if (nc == 1) TSIDB_AS_LAUNCH(24, 1, TSIDB_AS_WARPS_SS, s); else TSIDB_AS_LAUNCH(24, 0, TSIDB_AS_WARPS_FL, s); }
+    };
+    const int ncls = a.perm ? 3 : 1;
+    if (h->class_streams && !timed && ncls == 3) {
+      CK(cudaEventRecord(h->ev_fork[chunk], st));
+      for (int c = 0; c < 3; c++) {
+        const int nc = 2 - c;
+        cudaStream_t s = c == 0 ? st : h->side[chunk][c - 1];
+        if (c > 0) CK(cudaStreamWaitEvent(s, h->ev_fork[chunk], 0));
+        launch_e(nc, s); launch_g(nc, s); launch_a(nc, s);
+        CK(cudaGetLastError());
+        if (c > 0) {
+          CK(cudaEventRecord(h->ev_join[chunk][c - 1], s));
+          CK(cudaStreamWaitEvent(st, h->ev_join[chunk][c - 1], 0));
+        }
+      }
     } else {
-      TSIDB_E_LAUNCH(24, 2, TSIDB_E_WARPS);
-      if (a.perm) { TSIDB_E_LAUNCH(24, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_LAUNCH(24, 0, TSIDB_E_WARPS_LIGHT); }
+      for (int c = 0; c < ncls; c++) launch_e(2 - c, st);
+      CK(cudaGetLastError());
+      if (timed) CK(cudaEventRecord(h->ev[3], st));
+      for (int c = 0; c < ncls; c++) launch_g(2 - c, st);
+      CK(cudaGetLastError());
+      if (timed) CK(cudaEventRecord(h->ev[4], st));
+      for (int c = 0; c < ncls; c++) launch_a(2 - c, st);
+      CK(cudaGetLastError());
     }
+    h->launches += 3 * ncls;
 #undef TSIDB_E_LAUNCH
-    CK(cudaGetLastError());
-    h->launches += a.perm ? 3 : 1;
-  }
-  if (timed) CK(cudaEventRecord(h->ev[3], st));
-  if (!a.kin_only) {
-    const int warps = TSIDB_G_WARPS;
-    int blocks = (n + warps - 1) / warps;
-    if (blocks > h->sm_count) blocks = h->sm_count;
-    const size_t smem = (size_t)warps * (SG_IMAGE + 2) * sizeof(double);
-    if (h->dc.nv == 26) tsidb_j2_kernel<26><<<blocks, 32 * warps, smem, st>>>(a);
-    else tsidb_j2_kernel<24><<<blocks, 32 * warps, smem, st>>>(a);
-    CK(cudaGetLastError());
-    h->launches += 1;
-  }
-  if (timed) CK(cudaEventRecord(h->ev[4], st));
-  if (!a.kin_only) {
-    /* one launch per contact class, as for the elimination */
-    const int blocks = h->sm_count;
-#define TSIDB_AS_LAUNCH(NV, NC, W)                                                                                       \
-  tsidb_activeset_kernel<NV, NC, W><<<blocks, 32 * W, (size_t)W * a_layout(NV, NC).per_env * sizeof(double), st>>>(a)
-    if (h->dc.nv == 26) {
-      TSIDB_AS_LAUNCH(26, 2, TSIDB_AS_WARPS_DS);
-      if (a.perm) { TSIDB_AS_LAUNCH(26, 1, TSIDB_AS_WARPS_SS); TSIDB_AS_LAUNCH(26, 0, TSIDB_AS_WARPS_FL); }
-    } else {
-      TSIDB_AS_LAUNCH(24, 2, TSIDB_AS_WARPS_DS);
-      if (a.perm) { TSIDB_AS_LAUNCH(24, 1, TSIDB_AS_WARPS_SS); TSIDB_AS_LAUNCH(24, 0, TSIDB_AS_WARPS_FL); }
-    }
+#undef TSIDB_G_LAUNCH
 #undef TSIDB_AS_LAUNCH
-    CK(cudaGetLastError());
-    h->launches += a.perm ? 3 : 1;
+  } else if (timed) {
+    CK(cudaEventRecord(h->ev[3], st));
+    CK(cudaEventRecord(h->ev[4], st));
   }
   if (timed) CK(cudaEventRecord(h->ev[5], st));
   return 0;

@@ -1042,7 +1042,8 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
 #define SG_oILD (SG_oL + 728)             /* 1/L_ii                                      26 */
 #define SG_oTAU (SG_oILD + 26)            /* Householder tau                             18 */
 #define SG_oVT (SG_oTAU + 18)             /* reflectors [18][50]                        900 */
-#define SG_IMAGE (SG_oVT + 900)           /* doubles handed over per env               1672 */
+#define SG_oERR (SG_oVT + 900)            /* status of the elimination (arrives with the reflector part)  2 */
+#define SG_IMAGE (SG_oERR + 2)            /* doubles handed over per env               1674 */
 #define SG_LPART SG_oTAU                  /* [0, SG_LPART): factor part, [SG_LPART, SG_IMAGE): reflector part */
 #define TSIDB_G_WARPS 8
 #define SA_LDJA 20                        /* JFa row stride                                  */
@@ -1829,6 +1830,7 @@ TSIDB_DEV void eliminate_env(const DevConst& C, const double* lfinv_sm, double* 
   }
   if (lane < nv) fimg[SG_oILD + lane] = sm[LE::oILD + lane];
   if (lane < LE::NEQ) fimg[SG_oTAU + lane] = sm[LE::oTAU + lane];
+  if (lane == 0) fimg[SG_oERR] = (double)err;
   for (int k = lane; k < LE::NEQ * LE::N; k += 32) {
     const int i = k / LE::N, j = k % LE::N; /* restride the reflector rows: N in shared memory, SG_LDV in the image */
     fimg[SG_oVT + i * SG_LDV + j] = sm[LE::oVT + k];
@@ -1892,7 +1894,6 @@ TSIDB_DEV void j2_columns(const DevConst& C, double* sg, double* img, int lane, 
     const int col = (NC == 0) ? k - 6 : ((k < NV) ? k - NCM : ((k >= NV + 6) ? (NV - NCM) + (k - NV - 6) : -1));
     q[k] = (col >= 0 && col == lane) ? 1.0 : 0.0;
   }
-  g2_wait_v(P);
   if (work) {
 #pragma unroll
     for (int i = NEQ - 1; i >= 0; i--) {
@@ -1966,17 +1967,18 @@ TSIDB_DEV void j2_columns(const DevConst& C, double* sg, double* img, int lane, 
   g2_request_l(P, sg, lane);
 }
 
-template <int NV>
+template <int NV, int NC>
 TSIDB_DEV void j2_env(const DevConst& C, double* sg, const TickArgs& a, int slot, int lane, G2Pipe& P) {
   double* img = a.ws + (size_t)slot * SA_IMAGE;
-  const int err = (int)img[SA_oSc + 2], mask = (int)img[SA_oSc + 3];
 #ifdef TSIDB_EMU
   for (int k = lane; k < SG_IMAGE; k += 32) sg[k] = a.ws2[(size_t)slot * SG_IMAGE + k];
   __syncwarp();
 #endif
+  /* the status of the elimination travels in the reflector part of the factor image: no dependent global read */
+  g2_wait_v(P);
+  const int err = (int)sg[SG_oERR];
   if (err != ST_OPTIMAL) {
     /* the active-set kernel reports the status and never reads J2; keep the pipeline moving */
-    g2_wait_v(P);
     __syncwarp();
     g2_request_v(P, sg, lane);
     g2_wait_l(P);
@@ -1984,10 +1986,7 @@ TSIDB_DEV void j2_env(const DevConst& C, double* sg, const TickArgs& a, int slot
     g2_request_l(P, sg, lane);
     return;
   }
-  const int nc = (mask & 1) + ((mask >> 1) & 1);
-  if (nc == 2) j2_columns<NV, 2>(C, sg, img, lane, P);
-  else if (nc == 1) j2_columns<NV, 1>(C, sg, img, lane, P);
-  else j2_columns<NV, 0>(C, sg, img, lane, P);
+  j2_columns<NV, NC>(C, sg, img, lane, P);
 }
 
 /* ================================================================= kernel A: active set + decode of one env */
@@ -2173,29 +2172,32 @@ tsidb_eliminate_kernel(const TickArgs a) {
 #endif
 }
 
-template <int NV>
+/* one launch per contact class, like the elimination and the active set: the three class chains E -> G -> A are
+ * independent of each other and run on streams of their own */
+template <int NV, int NC>
 __global__ void __launch_bounds__(32 * TSIDB_G_WARPS, 1)
 tsidb_j2_kernel(const TickArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* sg = smem + wid * SG_IMAGE;
   const DevConst& C = g_const[a.slot];
+  int start, count;
+  class_range<NC>(a, start, count);
   G2Pipe P;
   P.bars = smem + TSIDB_G_WARPS * SG_IMAGE + 2 * wid;
   P.pv = P.pl = 0;
-  /* every column costs the same within a contact class and the slots are class-sorted: a static stride
-   * spreads each class evenly over the SMs */
+  /* every column costs the same within a contact class: a static stride spreads the class evenly over the SMs */
   const int stride = gridDim.x * TSIDB_G_WARPS;
-  int slot = blockIdx.x * TSIDB_G_WARPS + wid;
-  if (slot >= a.n_envs) return;
+  int k = blockIdx.x * TSIDB_G_WARPS + wid;
+  if (k >= count) return;
   if (lane == 0) { mbar_init(P.bars, 1); mbar_init(P.bars + 1, 1); }
   __syncwarp();
-  P.next = a.ws2 + (size_t)slot * SG_IMAGE;
+  P.next = a.ws2 + (size_t)(start + k) * SG_IMAGE;
   g2_request_v(P, sg, lane);
   g2_request_l(P, sg, lane);
-  for (; slot < a.n_envs; slot += stride) {
-    P.next = (slot + stride < a.n_envs) ? a.ws2 + (size_t)(slot + stride) * SG_IMAGE : nullptr;
-    j2_env<NV>(C, sg, a, slot, lane, P);
+  for (; k < count; k += stride) {
+    P.next = (k + stride < count) ? a.ws2 + (size_t)(start + k + stride) * SG_IMAGE : nullptr;
+    j2_env<NV, NC>(C, sg, a, start + k, lane, P);
   }
 }
 
