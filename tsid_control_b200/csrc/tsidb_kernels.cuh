@@ -1125,6 +1125,10 @@ TSIDB_DEV void bulk_store(void* dst, const void* src, unsigned bytes) {
 }
 TSIDB_DEV void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 TSIDB_DEV void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+/* pull a region into L2 ahead of the bulk load that will fetch it (bytes: multiple of 16) */
+TSIDB_DEV void bulk_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 TSIDB_DEV void mbar_wait(void* bar, unsigned parity) {
   unsigned ok = 0;
   const unsigned addr = smem_u32(bar);
@@ -1577,11 +1581,16 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
         }
         /* r = R^-1 d[0:iq] (back substitution, lane <-> row) */
         {
-          double accv = (lane < iq) ? dl : 0.0;
-          for (int i = iq - 1; i >= 0; i--) {
-            double ri = shfl(accv, i) * ird[i];
-            if (lane == i) accv = ri;
-            else if (lane < i) accv -= Rp[i * (i + 1) / 2 + lane] * ri;
+          /* row l scaled by 1/R_ll up front, so that a step of the chain is one shuffle and one FMA; the scaled
+           * coefficient of the next step is formed while the current one waits for its shuffle */
+          const double irl = (lane < iq) ? ird[lane] : 0.0;
+          double accv = dl * irl;
+          double coef = (lane < iq - 1) ? Rp[(iq - 1) * iq / 2 + lane] * irl : 0.0;
+          for (int i = iq - 1; i > 0; i--) {
+            const double ri = shfl(accv, i);
+            const double cnext = (lane < i - 1) ? Rp[(i - 1) * i / 2 + lane] * irl : 0.0;
+            accv -= coef * ri; /* coef is zero for the lanes >= i */
+            coef = cnext;
           }
           if (lane < iq) rr[lane] = accv;
         }
@@ -1648,7 +1657,20 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
                 const double2* v2 = reinterpret_cast<const double2*>(vv);
                 double2* W0 = const_cast<double2*>(Jr0);
                 double2* W1 = const_cast<double2*>(Jr1);
-                for (int c = c0; c < c1; c++) {
+                /* two column pairs per trip, all loads ahead of the stores (the rows alias the store targets, so
+                 * the compiler cannot move them itself) */
+                int c = c0;
+                for (; c + 1 < c1; c += 2) {
+                  const double2 vc = v2[c], vd = v2[c + 1];
+                  double2 j0 = Jr0[c], j1 = Jr1[c], k0 = Jr0[c + 1], k1 = Jr1[c + 1];
+                  j0.x -= w0 * vc.x; j0.y -= w0 * vc.y;
+                  j1.x -= w1 * vc.x; j1.y -= w1 * vc.y;
+                  k0.x -= w0 * vd.x; k0.y -= w0 * vd.y;
+                  k1.x -= w1 * vd.x; k1.y -= w1 * vd.y;
+                  if (h0) { W0[c] = j0; W0[c + 1] = k0; }
+                  if (h1) { W1[c] = j1; W1[c + 1] = k1; }
+                }
+                if (c < c1) {
                   const double2 vc = v2[c];
                   double2 j0 = Jr0[c], j1 = Jr1[c];
                   j0.x -= w0 * vc.x; j0.y -= w0 * vc.y;
@@ -1659,7 +1681,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
               }
               /* new column of R: [d[0:iq]; beta] */
               if (lane < iq) Rp[iq * (iq + 1) / 2 + lane] = dl;
-              if (lane == 0) { Rp[iq * (iq + 1) / 2 + iq] = beta; ird[iq] = 1.0 / beta; }
+              if (lane == 0) { Rp[iq * (iq + 1) / 2 + iq] = beta; ird[iq] = rho * (d0 - beta); }
               R_norm = fmax(R_norm, fabs(beta));
               if (lane == ip_lane) actbits |= 1u << ip_slot;
               iq++;
@@ -2162,12 +2184,16 @@ tsidb_eliminate_kernel(const TickArgs a) {
 #else
   /* free-running warps pull slots from a work counter of the class */
   int* counter = a.counter + 8 + NC;
-  for (;;) {
-    int k = 0;
-    if (lane == 0) k = atomicAdd(counter, 1);
-    k = __shfl_sync(FULL, k, 0);
-    if (k >= count) break;
+  int k = 0;
+  if (lane == 0) k = atomicAdd(counter, 1);
+  k = __shfl_sync(FULL, k, 0);
+  while (k < count) {
+    int kn = 0;
+    if (lane == 0) kn = atomicAdd(counter, 1);
+    kn = __shfl_sync(FULL, kn, 0);
+    if (kn < count && lane == 0) bulk_prefetch_l2(a.ws3 + (size_t)(start + kn) * SE_IMAGE, SE_IMAGE * sizeof(double));
     eliminate_env<NV, NC>(C, lfinv_sm, sm, a, start + k, lane, parity);
+    k = kn;
   }
 #endif
 }
@@ -2221,14 +2247,24 @@ tsidb_activeset_kernel(const TickArgs a) {
   LaneConst K;
   lane_const_init(C, K, lane);
   unsigned parity = 0;
-  for (;;) {
-    int k = 0;
-    if (lane == 0) k = atomicAdd(counter, 1);
-    k = __shfl_sync(FULL, k, 0);
-    if (k >= count) break;
-    const int slot = start + k;
-    const int env = a.perm ? a.perm[slot] : slot;
-    activeset_env<NV, NC>(C, K, sm, a, env, slot, lane, parity);
+  /* the warp draws its next slot before it works on the current one, so that the next solver image can be pulled
+   * into L2 and its env index read while the current env is being solved */
+  int k = 0;
+  if (lane == 0) k = atomicAdd(counter, 1);
+  k = __shfl_sync(FULL, k, 0);
+  int env = (k < count) ? (a.perm ? a.perm[start + k] : start + k) : 0;
+  while (k < count) {
+    int kn = 0;
+    if (lane == 0) kn = atomicAdd(counter, 1);
+    kn = __shfl_sync(FULL, kn, 0);
+    int envn = 0;
+    if (kn < count) {
+      if (lane == 0) bulk_prefetch_l2(a.ws + (size_t)(start + kn) * SA_IMAGE, LA::image * sizeof(double));
+      envn = a.perm ? a.perm[start + kn] : start + kn;
+    }
+    activeset_env<NV, NC>(C, K, sm, a, env, start + k, lane, parity);
+    k = kn;
+    env = envn;
   }
 }
 #endif
