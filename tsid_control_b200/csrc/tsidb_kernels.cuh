@@ -980,14 +980,13 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
     } else if (lane < neq) {
       rhs = -sm[SE_oNle + lane - ncm];
     }
-    if (lane < neq) Rd[lane] = 1.0 / Rd[lane];
-    __syncwarp();
-    double accv = rhs;
+    /* equation `lane` scaled by 1 / R_ll up front: a step of the chain is one shuffle and one FMA */
+    const double ird = (lane < neq) ? 1.0 / Rd[lane] : 0.0;
+    double accv = rhs * ird;
 #pragma unroll
-    for (int i = 0; i < neq; i++) {
-      const double wi = shfl(accv, i) * Rd[i];
-      if (lane == i) accv = wi;
-      else if (lane > i && lane < neq) accv -= R1[i * SM_LDB + lane] * wi;
+    for (int i = 0; i < neq - 1; i++) {
+      const double wi = shfl(accv, i);
+      if (lane > i && lane < neq) accv -= (R1[i * SM_LDB + lane] * ird) * wi;
     }
     __syncwarp();
     if (lane < neq) gv[(lane < ncm || nc == 0) ? lane : NV + (lane - ncm)] = accv; /* head row of reflector `lane` */
@@ -1016,10 +1015,16 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
     x[NV + lane] = acc;
   }
 #pragma unroll
-  for (int k = NV - 1; k >= 0; k--) { /* unrolled: the loads are hoisted, the chain per step is shuffle + multiply + FMA */
-    const double xk = shfl(y0, k) * ild[k];
-    if (lane == k) y0 = xk;
-    else if (lane < k) y0 -= L[k * SM_LDM + lane] * xk;
+  {
+    /* row `lane` scaled by 1 / L_ll up front; unrolled, so the scaled coefficients are formed off the chain and a
+     * step is one shuffle and one FMA */
+    const double il = (lane < NV) ? ild[lane] : 0.0;
+    y0 *= il;
+#pragma unroll
+    for (int k = NV - 1; k > 0; k--) {
+      const double xk = shfl(y0, k);
+      if (lane < k) y0 -= (L[k * SM_LDM + lane] * il) * xk;
+    }
   }
   if (lane < NV) x[lane] = y0;
   __syncwarp();
@@ -1397,11 +1402,9 @@ TSIDB_DEV void wrench_of(int nv, const LaneConst& K, const double* x, int mask, 
 /* Remove the active constraint at position qq (0-based among the active inequalities): shift A, u and
  * the columns of R, restore R to upper-triangular with Givens rotations of rows (j, j+1) and apply the
  * same rotations to columns j, j+1 of J2.  [eiquadprog-fast delete_constraint] */
-TSIDB_DEVNI void qp_delete(const ASCtx& S, int n, int& iq, int qq, int lane) {
-  double* Rp = S.Rp;
-  double* u = S.u;
-  int* A = S.A;
-  double* J2 = S.J2;
+/* every operand by value: the function is not inlined (two call sites), and a context struct passed by reference
+ * would live in local memory */
+TSIDB_DEVNI int qp_delete(double* Rp, double* u, int* A, double* J2, double* ird, int ldj, int n, int iq, int qq, int lane) {
   __syncwarp(); /* every lane has finished reading A/u/R of the current working set */
   /* shift columns qq+1..iq-1 one to the left; a column keeps its length, so column c (length c+1 in
    * packed storage) moves into slot c-1 (capacity c): element c sits on the sub-diagonal and is carried
@@ -1445,15 +1448,16 @@ TSIDB_DEVNI void qp_delete(const ASCtx& S, int n, int& iq, int qq, int lane) {
     }
     /* columns j, j+1 of J2: lanes over rows */
     for (int k = lane; k < n; k += 32) {
-      double t1 = J2[k * S.ldj + j], t2 = J2[k * S.ldj + j + 1];
+      double t1 = J2[k * ldj + j], t2 = J2[k * ldj + j + 1];
       double n1 = t1 * cc + t2 * ss;
-      J2[k * S.ldj + j] = n1;
-      J2[k * S.ldj + j + 1] = xny * (n1 + t1) - t2;
+      J2[k * ldj + j] = n1;
+      J2[k * ldj + j + 1] = xny * (n1 + t1) - t2;
     }
     __syncwarp();
   }
-  if (lane < iq) S.ird[lane] = 1.0 / Rp[lane * (lane + 1) / 2 + lane];
+  if (lane < iq) ird[lane] = 1.0 / Rp[lane * (lane + 1) / 2 + lane];
   __syncwarp();
+  return iq;
 }
 
 /* this lane's most violated row among the rows it owns that are neither active nor excluded; ties to the lowest
@@ -1601,7 +1605,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
           double rk = rr[lane];
           if (rk > 0.0) { t1 = u[lane] / rk; t1_valid = true; }
         }
-        const int lpos = warp_argmin(t1, t1_valid, lane);
+        const int lpos = (__ballot_sync(FULL, t1_valid) != 0u) ? warp_argmin(t1, t1_valid, lane) : -1;
         t1 = (lpos >= 0) ? shfl(t1, lpos) : TS_INF;
         /* full step t2 = -s_ip / z.n_ip, with z.n_ip = |d[iq:]|^2 (z = J2 d2, d2 = J2^T n) */
         const double zz = warp_sum(z0 * z0 + z1 * z1);
@@ -1623,7 +1627,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
             cid_owner(na, A[lpos], ol, os);
             if (lane == ol) actbits &= ~(1u << os);
           }
-          qp_delete(S, n, iq, lpos, lane);
+          iq = qp_delete(Rp, u, A, J2, ird, S.ldj, n, iq, lpos, lane);
           continue;
         }
         /* step in primal and dual space */
@@ -1714,7 +1718,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
           cid_owner(na, A[lpos], ol, os);
           if (lane == ol) actbits &= ~(1u << os);
         }
-        qp_delete(S, n, iq, lpos, lane);
+        iq = qp_delete(Rp, u, A, J2, ird, S.ldj, n, iq, lpos, lane);
         wrench_of(S.nv, K, x, mask, wr, lane);
         __syncwarp();
         s_ip = eval_one(C, S, ip, mask);
