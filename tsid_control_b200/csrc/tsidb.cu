@@ -33,7 +33,7 @@ static bool g_slot_used[8][TSIDB_MAX_SLOTS]; /* per device */
 struct tsidb_handle {
   int device, slot, max_envs, sm_count;
   DevConst dc;
-  int32_t* counter;      /* device, 12 per chunk: work counters of the active-set ([0],[4],[5]) and elimination ([8..10]) kernels, [1..3] class sizes */
+  int32_t* counter;      /* device, 16 per chunk: work counters of the active-set ([0],[4],[5]), elimination ([8..10]) and basis ([12..14]) kernels, [1..3] class sizes */
   double* ws;            /* device: solver images, SA_IMAGE doubles per slot */
   double* ws2;           /* device: factor images, SG_IMAGE doubles per slot */
   double* ws3;           /* device: assembly images, SE_IMAGE doubles per slot */
@@ -198,35 +198,40 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
     g_err = "tsidb_create: this build instantiates the tick kernels for nv = 26 (robot/v1) and nv = 24 (robot/v0)";
     return -1;
   }
-  {
-    const size_t need = (size_t)TSIDB_AS_WARPS_DS * a_layout(TSIDB_NVX, 2).per_env * sizeof(double);
-    if ((size_t)prop.sharedMemPerBlockOptin < need) {
-      g_err = "tsidb_create: device offers less opt-in shared memory per block than the active-set kernel needs";
-      return -2;
-    }
-  }
-#define TSIDB_AS_ATTR(NV, NC, W)                                                                                         \
-  CK(cudaFuncSetAttribute(tsidb_activeset_kernel<NV, NC, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
-                          (int)((size_t)W * a_layout(NV, NC).per_env * sizeof(double))))
+  /* Every CTA of the elimination, basis and active-set kernels is one warp; WARPS of them are to be resident per SM
+   * (1 KB of shared memory is reserved per CTA on top of its own), so every kernel asks for the largest
+   * shared-memory carve-out. */
+  const size_t per_sm = (size_t)prop.sharedMemPerMultiprocessor, rsv = (size_t)prop.reservedSharedMemPerBlock;
+#define TSIDB_ATTR(KERNEL, BYTES, RESIDENT, WHAT)                                                                        \
+  do {                                                                                                                   \
+    if ((size_t)(RESIDENT) * ((size_t)(BYTES) + rsv) > per_sm) {                                                         \
+      g_err = std::string("tsidb_create: an SM does not hold the planned number of resident CTAs of the ") + WHAT;       \
+      return -2;                                                                                                         \
+    }                                                                                                                    \
+    CK((cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES))));                       \
+    CK((cudaFuncSetAttribute(KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared))); \
+  } while (0)
+#define TSIDB_AS_SMEM(NV, NC) ((size_t)TSIDB_A_CTA_WARPS * a_layout(NV, NC).per_env * sizeof(double))
+#define TSIDB_AS_ATTR(NV, NC, W) TSIDB_ATTR((tsidb_activeset_kernel<NV, NC, W>), TSIDB_AS_SMEM(NV, NC), (W) / TSIDB_A_CTA_WARPS, "active-set kernel")
   TSIDB_AS_ATTR(26, 2, TSIDB_AS_WARPS_DS); TSIDB_AS_ATTR(26, 1, TSIDB_AS_WARPS_SS); TSIDB_AS_ATTR(26, 0, TSIDB_AS_WARPS_FL);
   TSIDB_AS_ATTR(24, 2, TSIDB_AS_WARPS_DS); TSIDB_AS_ATTR(24, 1, TSIDB_AS_WARPS_SS); TSIDB_AS_ATTR(24, 0, TSIDB_AS_WARPS_FL);
 #undef TSIDB_AS_ATTR
-  CK(cudaFuncSetAttribute(tsidb_dynamics_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(tsidb_dynamics_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#define TSIDB_E_SMEM(NV, NC, W) (((size_t)(W) * e_per_env(NV, NC) + 144) * sizeof(double))
-#define TSIDB_E_ATTR(NV, NC, W) \
-  CK(cudaFuncSetAttribute(tsidb_eliminate_kernel<NV, NC, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSIDB_E_SMEM(NV, NC, W)))
+  TSIDB_ATTR(tsidb_dynamics_kernel<26>, smem, TSIDB_D_CTAS_PER_SM, "dynamics kernel");
+  TSIDB_ATTR(tsidb_dynamics_kernel<24>, smem, TSIDB_D_CTAS_PER_SM, "dynamics kernel");
+#define TSIDB_E_SMEM(NV, NC) (((size_t)TSIDB_E_CTA_WARPS * e_per_env(NV, NC) + 144) * sizeof(double))
+#define TSIDB_E_ATTR(NV, NC, W) TSIDB_ATTR((tsidb_eliminate_kernel<NV, NC, W>), TSIDB_E_SMEM(NV, NC), (W) / TSIDB_E_CTA_WARPS, "elimination kernel")
   TSIDB_E_ATTR(26, 2, TSIDB_E_WARPS); TSIDB_E_ATTR(26, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_ATTR(26, 0, TSIDB_E_WARPS_LIGHT);
   TSIDB_E_ATTR(24, 2, TSIDB_E_WARPS); TSIDB_E_ATTR(24, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_ATTR(24, 0, TSIDB_E_WARPS_LIGHT);
 #undef TSIDB_E_ATTR
-  const size_t smem_g = (size_t)TSIDB_G_WARPS * (SG_IMAGE + 2) * sizeof(double);
-  CK((cudaFuncSetAttribute(tsidb_j2_kernel<26, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)));
-  CK((cudaFuncSetAttribute(tsidb_j2_kernel<26, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)));
-  CK((cudaFuncSetAttribute(tsidb_j2_kernel<26, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)));
-  CK((cudaFuncSetAttribute(tsidb_j2_kernel<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)));
-  CK((cudaFuncSetAttribute(tsidb_j2_kernel<24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)));
-  CK((cudaFuncSetAttribute(tsidb_j2_kernel<24, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)));
-  CK(cudaMalloc(&h->counter, 12 * TSIDB_MAX_CHUNKS * sizeof(int32_t)));
+  const size_t smem_g = (size_t)TSIDB_G_CTA_WARPS * (SG_IMAGE + 2) * sizeof(double);
+  TSIDB_ATTR((tsidb_j2_kernel<26, 2>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel");
+  TSIDB_ATTR((tsidb_j2_kernel<26, 1>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel");
+  TSIDB_ATTR((tsidb_j2_kernel<26, 0>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel");
+  TSIDB_ATTR((tsidb_j2_kernel<24, 2>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel");
+  TSIDB_ATTR((tsidb_j2_kernel<24, 1>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel");
+  TSIDB_ATTR((tsidb_j2_kernel<24, 0>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel");
+#undef TSIDB_ATTR
+  CK(cudaMalloc(&h->counter, 16 * TSIDB_MAX_CHUNKS * sizeof(int32_t)));
   CK(cudaMalloc(&h->ws, (size_t)max_envs * SA_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->ws2, (size_t)max_envs * SG_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->ws3, (size_t)max_envs * SE_IMAGE * sizeof(double)));
@@ -319,7 +324,7 @@ extern "C" int tsidb_set_default_refs(tsidb_handle* h, const double* com9, const
 static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base = 0, int chunk = 0) {
   CK(cudaSetDevice(h->device));
   if (base + a.n_envs > h->max_envs) { g_err = "n_envs exceeds the handle's max_envs (workspace size)"; return -1; }
-  int32_t* counter = h->counter + 12 * chunk; /* [0],[4],[5]: active-set work counters per class, [1..3]: class sizes, [8..10]: elimination work counters */
+  int32_t* counter = h->counter + 16 * chunk; /* [0],[4],[5]: active-set work counters per class, [1..3]: class sizes, [8..10]: elimination, [12..14]: basis work counters */
   int32_t* perm = h->perm + base;
   int32_t* cls_pos = h->cls_pos + base;
   a.counter = counter;
@@ -332,7 +337,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   const bool timed = h->timing && !a.kin_only && chunk == 0 && base == 0;
   if (timed) CK(cudaEventRecord(h->ev[0], st));
   if (!a.kin_only) {
-    CK(cudaMemsetAsync(counter, 0, 12 * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(counter, 0, 16 * sizeof(int32_t), st));
     if (a.mask) {
       /* class sort (double support, single support, flight) -> slot order */
       const int th = 256;
@@ -346,7 +351,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   {
     const int warps = TSIDB_WARPS_PER_BLOCK;
     int blocks = (n + warps - 1) / warps;
-    if (blocks > h->sm_count) blocks = h->sm_count; /* persistent: one CTA per SM */
+    if (blocks > TSIDB_D_CTAS_PER_SM * h->sm_count) blocks = TSIDB_D_CTAS_PER_SM * h->sm_count; /* persistent */
     const size_t smem = ((size_t)warps * SM_PER_ENV + MDL_SIZE) * sizeof(double);
     if (h->dc.nv == 26) tsidb_dynamics_kernel<26><<<blocks, 32 * warps, smem, st>>>(a);
     else tsidb_dynamics_kernel<24><<<blocks, 32 * warps, smem, st>>>(a);
@@ -362,13 +367,20 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
      * class streams on, single support and flight run on side streams, so that the SMs a kernel's last CTAs leave
      * idle are picked up by the next ready kernel of another class.  Per-kernel timing keeps everything on one
      * stream, stage by stage. */
-    const int blocks = h->sm_count;
+    /* grids: as many CTAs as an SM holds of the kernel, times the SMs (never more warps than envs) */
+    const int sms = h->sm_count;
+    auto grid = [&](int resident_warps, int cta_warps) {
+      const long g = (long)(resident_warps / cta_warps) * sms, need = (n + cta_warps - 1) / cta_warps;
+      return (int)(g < need ? g : need);
+    };
     const int nv26 = h->dc.nv == 26;
-    const size_t smem_g = (size_t)TSIDB_G_WARPS * (SG_IMAGE + 2) * sizeof(double);
-#define TSIDB_E_LAUNCH(NV, NC, W, S) tsidb_eliminate_kernel<NV, NC, W><<<blocks, 32 * (W), TSIDB_E_SMEM(NV, NC, W), S>>>(a)
-#define TSIDB_G_LAUNCH(NV, NC, S) tsidb_j2_kernel<NV, NC><<<blocks, 32 * TSIDB_G_WARPS, smem_g, S>>>(a)
-#define TSIDB_AS_LAUNCH(NV, NC, W, S)                                                                                    \
-  tsidb_activeset_kernel<NV, NC, W><<<blocks, 32 * W, (size_t)W * a_layout(NV, NC).per_env * sizeof(double), S>>>(a)
+    const size_t smem_g = (size_t)TSIDB_G_CTA_WARPS * (SG_IMAGE + 2) * sizeof(double);
+#define TSIDB_E_LAUNCH(NV, NC, W, S) \
+  tsidb_eliminate_kernel<NV, NC, W><<<grid(W, TSIDB_E_CTA_WARPS), 32 * TSIDB_E_CTA_WARPS, TSIDB_E_SMEM(NV, NC), S>>>(a)
+#define TSIDB_G_LAUNCH(NV, NC, S) \
+  tsidb_j2_kernel<NV, NC><<<grid(TSIDB_G_WARPS, TSIDB_G_CTA_WARPS), 32 * TSIDB_G_CTA_WARPS, smem_g, S>>>(a)
+#define TSIDB_AS_LAUNCH(NV, NC, W, S) \
+  tsidb_activeset_kernel<NV, NC, W><<<grid(W, TSIDB_A_CTA_WARPS), 32 * TSIDB_A_CTA_WARPS, TSIDB_AS_SMEM(NV, NC), S>>>(a)
     auto launch_e = [&](int nc, cudaStream_t s) {
       if (nv26) { if (nc == 2) TSIDB_E_LAUNCH(26, 2, TSIDB_E_WARPS, s); else if (nc == 1) TSIDB_E_LAUNCH(26, 1, TSIDB_E_WARPS_LIGHT, s); else TSIDB_E_LAUNCH(26, 0, TSIDB_E_WARPS_LIGHT, s); }
       else { if (nc == 2) TSIDB_E_LAUNCH(24, 2, TSIDB_E_WARPS, s); else if (nc == 1) TSIDB_E_LAUNCH(24, 1, TSIDB_E_WARPS_LIGHT, s); else TSIDB_E_LAUNCH(24, 0, TSIDB_E_WARPS_LIGHT, s); }
@@ -508,9 +520,16 @@ extern "C" int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, 
     nch = (int)((N + cs - 1) / cs);
     for (int c = 1; c <= nch; c++) bound[c] = (c * cs < N) ? c * cs : N;
   }
+  /* TSIDB_HOST_TRACE=1: event time stamps per chunk (copies in, kernels, copies out) printed to stderr */
+  const bool trace = getenv("TSIDB_HOST_TRACE") != nullptr;
+  cudaEvent_t tev[TSIDB_MAX_CHUNKS][4];
+  if (trace)
+    for (int c = 0; c < nch; c++)
+      for (int i = 0; i < 4; i++) CK(cudaEventCreate(&tev[c][i]));
   for (int c = 0; c < nch; c++) {
     cudaStream_t st = h->stream[c % TSIDB_HOST_STREAMS];
     const size_t o = bound[c];
+    if (trace) CK(cudaEventRecord(tev[c][0], st));
     const int m = (int)(bound[c + 1] - bound[c]);
     for (int s = 0; s < 8; s++) {
       if (!segs[s].src) continue;
@@ -534,8 +553,10 @@ extern "C" int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, 
     a.tau = d_tau + o * na; a.ddq = d_ddq + o * nv; a.f = d_f + o * 24;
     a.status = h->d_int + o; a.iters = h->d_int + N + o;
     a.active = active_set ? h->d_act + 3 * o : nullptr; /* [3][m] block of this chunk */
+    if (trace) CK(cudaEventRecord(tev[c][1], st));
     int rc = launch_tick(h, a, st, (int)o, c);
     if (rc) return rc;
+    if (trace) CK(cudaEventRecord(tev[c][2], st));
     CK(cudaMemcpyAsync(out_pinned[0] ? tau + o * na : s_tau + o * na, a.tau, (size_t)m * na * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_pinned[1] ? ddq + o * nv : s_ddq + o * nv, a.ddq, (size_t)m * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_pinned[2] ? f + o * 24 : s_f + o * 24, a.f, (size_t)m * 24 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -547,8 +568,19 @@ extern "C" int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, 
         CK(cudaMemcpyAsync(dst, h->d_act + 3 * o + (size_t)w * m, (size_t)m * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
       }
     }
+    if (trace) CK(cudaEventRecord(tev[c][3], st));
   }
   for (int i = 0; i < TSIDB_HOST_STREAMS && i < nch; i++) CK(cudaStreamSynchronize(h->stream[i]));
+  if (trace) {
+    for (int c = 0; c < nch; c++) {
+      float t[4];
+      for (int i = 0; i < 4; i++) { CK(cudaEventElapsedTime(&t[i], tev[0][0], tev[c][i])); }
+      fprintf(stderr, "[tsidb host trace] chunk %d (%d envs): enqueued %.3f  inputs on device %.3f  kernels done %.3f  outputs on host %.3f ms\n",
+              c, (int)(bound[c + 1] - bound[c]), t[0], t[1], t[2], t[3]);
+    }
+    for (int c = 0; c < nch; c++)
+      for (int i = 0; i < 4; i++) cudaEventDestroy(tev[c][i]);
+  }
   if (!out_pinned[0]) memcpy(tau, s_tau, N * na * sizeof(double));
   if (!out_pinned[1]) memcpy(ddq, s_ddq, N * nv * sizeof(double));
   if (!out_pinned[2]) memcpy(f, s_f, N * 24 * sizeof(double));

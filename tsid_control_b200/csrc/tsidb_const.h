@@ -8,9 +8,15 @@
 #define TSIDB_NVX 26   /* largest nv this build keeps in shared memory (robot/v1)          */
 #define TSIDB_NX 50    /* nv + 24                                                          */
 #define TSIDB_MRED 32  /* n - nEq = na + 6*nc <= 32: one lane per reduced coordinate       */
-#define TSIDB_WARPS_PER_BLOCK 16  /* dynamics kernel */
-#define TSIDB_E_WARPS 8            /* elimination kernel, double support */
+#define TSIDB_WARPS_PER_BLOCK 16   /* dynamics kernel: warps per CTA (they share the staged model constants) */
+#define TSIDB_D_CTAS_PER_SM 1     /* dynamics kernel: resident CTAs per SM (16 warps)                       */
+#define TSIDB_E_WARPS 8            /* elimination kernel, double support: one-warp CTAs resident per SM */
 #define TSIDB_E_WARPS_LIGHT 12     /* elimination kernel, single support and flight */
+/* warps per CTA of the per-class kernels (the resident warps per SM above are split into CTAs of this width; a
+ * narrow CTA returns its shared memory and registers as soon as its warps run out of work) */
+#define TSIDB_E_CTA_WARPS 1
+#define TSIDB_G_CTA_WARPS 1
+#define TSIDB_A_CTA_WARPS 4
 /* CTA-wide phase lock-step (all warps of a CTA run the same phase at the same time, so one instruction-cache
  * line serves all of them).  It paid off for the fused 215 KB kernel of the first generation; with one kernel
  * per stage the code fits the instruction cache and free-running warps hide each other's latencies better

@@ -1075,17 +1075,19 @@ TSIDB_HD constexpr ALayout a_layout(int nv, int nc) {
   L.oMa = L.oJ2 + L.n * L.ldj;            /* M_a na x SA_LDM (rows 6.. of M)           */
   L.oJFa = L.oMa + na * SA_LDM;           /* JF columns 6.. of the feet in contact, in force-block order: 6 nc x SA_LDJA */
   L.oNle = L.oJFa + 6 * nc * SA_LDJA;     /* nle_a                                     */
-  L.oVj = L.oNle + even_up(na);           /* joint velocities                          */
-  L.oX = L.oVj + even_up(na);             /* x                                         */
-  L.image = L.oX + even_up(L.n);
-  L.oWr = L.image;                        /* wrenches 12                               */
+  L.oX = L.oNle + even_up(na);            /* x                                         */
+  L.oVj = L.oX + even_up(L.n);            /* joint velocities: only read when the env is loaded (joint-bound limits
+                                           * into registers), so the work arrays start on top of them */
+  L.image = L.oVj + even_up(na);
+  L.oWr = L.oVj;                          /* wrenches 12                               */
   L.oR = L.oWr + 12;                      /* R packed by columns: col j at j(j+1)/2    */
   L.oIRD = L.oR + even_up(L.m * (L.m + 1) / 2);  /* 1/R_jj                             */
-  L.oNP = L.oIRD + L.m;                   /* dense constraint normal                   */
+  L.oNP = L.oIRD + L.m;                   /* dense constraint normal (n >= m + 2)      */
+  L.oVV = L.oNP;                          /* Householder vector, zero padded to m + 2: built after the last use of
+                                           * the dense normal of the same pick, so it shares its place */
   L.oD = L.oNP + even_up(L.n);            /* d (free columns), zero padded to m + 2    */
   L.oRR = L.oD + L.m + 2;                 /* r                                         */
-  L.oVV = L.oRR + L.m;                    /* Householder vector, zero padded to m + 2  */
-  L.oU = L.oVV + L.m + 2;                 /* u                                         */
+  L.oU = L.oRR + L.m;                 /* u                                         */
   L.oUO = L.oU + L.m + 2;                 /* u_old                                     */
   L.oXO = L.oUO + L.m + 2;                /* x_old                                     */
   L.oA = L.oXO + even_up(L.n);            /* A, A_old as int32: 2 x (m + 2) ints       */
@@ -1296,7 +1298,7 @@ TSIDB_DEV void eval_rows(const DevConst& C, const ASCtx& S, const LaneConst& K, 
   }
 }
 /* s of one row (after a partial step) — lane-uniform call, every lane computes the same value */
-TSIDB_DEV double eval_one(const DevConst& C, const ASCtx& S, int cid, int mask) {
+TSIDB_DEV double eval_one(const DevConst& C, const ASCtx& S, const LaneConst& K, int cid, int mask) {
   const int na = S.na, nv = S.nv;
   const double* x = S.x;
   if (cid < 32) {
@@ -1324,9 +1326,9 @@ TSIDB_DEV double eval_one(const DevConst& C, const ASCtx& S, int cid, int mask) 
   }
   {
     const int k = cid - 36 - 2 * na, side = k >= na ? 1 : 0, i = k - side * na;
-    const double vj = S.vj[i];
-    if (side) return fmin((C.v_max[i] - vj) / C.jb_dt, 1e10) - x[6 + i];
-    return x[6 + i] - fmax((C.v_min[i] - vj) / C.jb_dt, -1e10);
+    /* the limits of joint i live in lane i's registers (the call is warp-uniform) */
+    const double lim = shfl(side ? K.ub : K.lb, i);
+    return side ? lim - x[6 + i] : x[6 + i] - lim;
   }
 }
 
@@ -1653,6 +1655,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
                * (sum_c' J2[k][c'] d_c' = z_k): one reciprocal on the critical path instead of two divisions */
               const double rho = 1.0 / (beta * (d0 - beta));
               if (lane < m) vv[lane] = (lane < iq) ? 0.0 : ((lane == iq) ? d0 - beta : dl);
+              if (lane < 2) vv[m + lane] = 0.0; /* the padding shares its place with the dense normal */
               const double w0 = h0 ? -rho * (z0 - beta * J2[lane * S.ldj + iq]) : 0.0;
               const double w1 = h1 ? -rho * (z1 - beta * J2[(lane + 32) * S.ldj + iq]) : 0.0;
               __syncwarp();
@@ -1721,7 +1724,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
         iq = qp_delete(Rp, u, A, J2, ird, S.ldj, n, iq, lpos, lane);
         wrench_of(S.nv, K, x, mask, wr, lane);
         __syncwarp();
-        s_ip = eval_one(C, S, ip, mask);
+        s_ip = eval_one(C, S, K, ip, mask);
       } /* l2a */
       if (done || restart_l1) break;
     } /* l2 */
@@ -2049,6 +2052,7 @@ TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const 
     K.ub = fmin((K.vmax - vj) / C.jb_dt, 1e10);
     K.lb = fmax((K.vmin - vj) / C.jb_dt, -1e10);
   }
+  __syncwarp(); /* the joint velocities are dead from here on: the work arrays take their place */
   int iters = 0;
   uint64_t words[3] = {0, 0, 0};
   int status = err;
@@ -2123,7 +2127,7 @@ __global__ void tsidb_permute_kernel(int n_envs, const int32_t* cls_pos, const i
 }
 
 template <int NV>
-__global__ void __launch_bounds__(32 * TSIDB_WARPS_PER_BLOCK, 1)
+__global__ void __launch_bounds__(32 * TSIDB_WARPS_PER_BLOCK, TSIDB_D_CTAS_PER_SM)
 tsidb_dynamics_kernel(const TickArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -2156,11 +2160,15 @@ TSIDB_DEV void class_range(const TickArgs& a, int& start, int& count) {
   count = (NC == 2) ? c0 : ((NC == 1) ? c1 : c2);
 }
 
-/* one launch per contact class: every size of the elimination is a compile-time constant, the warps of a CTA
- * have identical trip counts (phase lock-step), and the lighter classes fit more warps per SM */
+/* One launch per contact class: every size of the elimination is a compile-time constant and the lighter classes
+ * fit more warps per SM.  A CTA is ONE warp (WARPS of them resident per SM) that pulls slots from the work counter
+ * of its class and exits when the class is drained: its shared memory and registers are free at once for the
+ * CTAs of whichever kernel is ready next (another class, the next stage, the next chunk of a host call), so a
+ * kernel's tail does not idle the SM. */
 template <int NV, int NC, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, 1)
+__global__ void __launch_bounds__(32 * TSIDB_E_CTA_WARPS, WARPS / TSIDB_E_CTA_WARPS)
 tsidb_eliminate_kernel(const TickArgs a) {
+  static_assert(WARPS % TSIDB_E_CTA_WARPS == 0, "CTA width divides the resident warps");
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   typedef EL<NV, NC> LE;
@@ -2169,28 +2177,18 @@ tsidb_eliminate_kernel(const TickArgs a) {
   int start, count;
   class_range<NC>(a, start, count);
   if (count <= 0) return;
-  /* CTA-shared copy of the constant Lf^-1 (read with lane-dependent indices) */
-  double* lfinv_sm = smem + WARPS * LE::per_env;
-  for (int k = threadIdx.x; k < 144; k += blockDim.x) lfinv_sm[k] = C.Lfinv[k / 12][k % 12];
+  /* the CTA's copy of the constant Lf^-1 (read with lane-dependent indices) */
+  double* lfinv_sm = smem + TSIDB_E_CTA_WARPS * LE::per_env;
+  for (int i = threadIdx.x; i < 144; i += blockDim.x) lfinv_sm[i] = C.Lfinv[i / 12][i % 12];
   __syncthreads();
-  if (lane == 0) mbar_init(sm + LE::oBar, 1);
-  __syncwarp();
-  unsigned parity = 0;
-#if TSIDB_LOCK_E
-  /* phase lock-step needs every warp of the CTA in every round: static rounds, idle warps repeat the last slot */
-  const int per_round = gridDim.x * WARPS;
-  const int rounds = (count + per_round - 1) / per_round;
-  for (int r = 0; r < rounds; r++) {
-    int k = (r * gridDim.x + blockIdx.x) * WARPS + wid;
-    if (k >= count) k = count - 1;
-    eliminate_env<NV, NC>(C, lfinv_sm, sm, a, start + k, lane, parity);
-  }
-#else
-  /* free-running warps pull slots from a work counter of the class */
   int* counter = a.counter + 8 + NC;
   int k = 0;
   if (lane == 0) k = atomicAdd(counter, 1);
   k = __shfl_sync(FULL, k, 0);
+  if (k >= count) return;
+  if (lane == 0) mbar_init(sm + LE::oBar, 1);
+  __syncwarp();
+  unsigned parity = 0;
   while (k < count) {
     int kn = 0;
     if (lane == 0) kn = atomicAdd(counter, 1);
@@ -2199,44 +2197,51 @@ tsidb_eliminate_kernel(const TickArgs a) {
     eliminate_env<NV, NC>(C, lfinv_sm, sm, a, start + k, lane, parity);
     k = kn;
   }
-#endif
 }
 
 /* one launch per contact class, like the elimination and the active set: the three class chains E -> G -> A are
- * independent of each other and run on streams of their own */
+ * independent of each other and run on streams of their own.  One-warp CTAs on a work counter, as above; the warp
+ * draws its next slot before it works on the current one (the pipeline prefetches the next factor image). */
 template <int NV, int NC>
-__global__ void __launch_bounds__(32 * TSIDB_G_WARPS, 1)
+__global__ void __launch_bounds__(32 * TSIDB_G_CTA_WARPS, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS)
 tsidb_j2_kernel(const TickArgs a) {
+  static_assert(TSIDB_G_WARPS % TSIDB_G_CTA_WARPS == 0, "CTA width divides the resident warps");
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double* sg = smem + wid * SG_IMAGE;
+  double* sg = smem + wid * (SG_IMAGE + 2);
   const DevConst& C = g_const[a.slot];
   int start, count;
   class_range<NC>(a, start, count);
-  G2Pipe P;
-  P.bars = smem + TSIDB_G_WARPS * SG_IMAGE + 2 * wid;
-  P.pv = P.pl = 0;
-  /* every column costs the same within a contact class: a static stride spreads the class evenly over the SMs */
-  const int stride = gridDim.x * TSIDB_G_WARPS;
-  int k = blockIdx.x * TSIDB_G_WARPS + wid;
+  int* counter = a.counter + 12 + NC;
+  int k = 0;
+  if (lane == 0) k = atomicAdd(counter, 1);
+  k = __shfl_sync(FULL, k, 0);
   if (k >= count) return;
+  G2Pipe P;
+  P.bars = sg + SG_IMAGE;
+  P.pv = P.pl = 0;
   if (lane == 0) { mbar_init(P.bars, 1); mbar_init(P.bars + 1, 1); }
   __syncwarp();
   P.next = a.ws2 + (size_t)(start + k) * SG_IMAGE;
   g2_request_v(P, sg, lane);
   g2_request_l(P, sg, lane);
-  for (; k < count; k += stride) {
-    P.next = (k + stride < count) ? a.ws2 + (size_t)(start + k + stride) * SG_IMAGE : nullptr;
+  while (k < count) {
+    int kn = 0;
+    if (lane == 0) kn = atomicAdd(counter, 1);
+    kn = __shfl_sync(FULL, kn, 0);
+    P.next = (kn < count) ? a.ws2 + (size_t)(start + kn) * SG_IMAGE : nullptr;
     j2_env<NV, NC>(C, sg, a, start + k, lane, P);
+    k = kn;
   }
 }
 
 /* one launch per contact class (sizes, strides and the shared-memory layout are compile-time; the lighter
- * classes fit more warps per SM); each class pulls its slots from a work counter of its own because the
- * iteration counts vary from 1 to ~40 */
+ * classes fit more warps per SM); one-warp CTAs, each class pulls its slots from a work counter of its own because
+ * the iteration counts vary from 1 to ~40 */
 template <int NV, int NC, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, 1)
+__global__ void __launch_bounds__(32 * TSIDB_A_CTA_WARPS, WARPS / TSIDB_A_CTA_WARPS)
 tsidb_activeset_kernel(const TickArgs a) {
+  static_assert(WARPS % TSIDB_A_CTA_WARPS == 0, "CTA width divides the resident warps");
   extern __shared__ double smem[];
   typedef AL<NV, NC> LA;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -2244,19 +2249,19 @@ tsidb_activeset_kernel(const TickArgs a) {
   const DevConst& C = g_const[a.slot];
   int start, count;
   class_range<NC>(a, start, count);
-  if (count <= 0) return;
   int* counter = a.counter + ((NC == 2) ? 0 : ((NC == 1) ? 4 : 5));
-  if (lane == 0) mbar_init(sm + LA::oBar, 1);
-  __syncwarp();
-  LaneConst K;
-  lane_const_init(C, K, lane);
-  unsigned parity = 0;
   /* the warp draws its next slot before it works on the current one, so that the next solver image can be pulled
    * into L2 and its env index read while the current env is being solved */
   int k = 0;
   if (lane == 0) k = atomicAdd(counter, 1);
   k = __shfl_sync(FULL, k, 0);
-  int env = (k < count) ? (a.perm ? a.perm[start + k] : start + k) : 0;
+  if (k >= count) return;
+  if (lane == 0) mbar_init(sm + LA::oBar, 1);
+  __syncwarp();
+  LaneConst K;
+  lane_const_init(C, K, lane);
+  unsigned parity = 0;
+  int env = a.perm ? a.perm[start + k] : start + k;
   while (k < count) {
     int kn = 0;
     if (lane == 0) kn = atomicAdd(counter, 1);
