@@ -202,34 +202,37 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
    * (1 KB of shared memory is reserved per CTA on top of its own), so every kernel asks for the largest
    * shared-memory carve-out. */
   const size_t per_sm = (size_t)prop.sharedMemPerMultiprocessor, rsv = (size_t)prop.reservedSharedMemPerBlock;
-#define TSIDB_ATTR(KERNEL, BYTES, RESIDENT, WHAT)                                                                        \
+#define TSIDB_ATTR(KERNEL, BYTES, RESIDENT, WHAT, CARVEOUT)                                                                       \
   do {                                                                                                                   \
     if ((size_t)(RESIDENT) * ((size_t)(BYTES) + rsv) > per_sm) {                                                         \
       g_err = std::string("tsidb_create: an SM does not hold the planned number of resident CTAs of the ") + WHAT;       \
       return -2;                                                                                                         \
     }                                                                                                                    \
     CK((cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES))));                       \
-    CK((cudaFuncSetAttribute(KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared))); \
+    CK((cudaFuncSetAttribute(KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout, (int)(CARVEOUT))));                  \
   } while (0)
-#define TSIDB_AS_SMEM(NV, NC) ((size_t)TSIDB_A_CTA_WARPS * a_layout(NV, NC).per_env * sizeof(double))
-#define TSIDB_AS_ATTR(NV, NC, W) TSIDB_ATTR((tsidb_activeset_kernel<NV, NC, W>), TSIDB_AS_SMEM(NV, NC), (W) / TSIDB_A_CTA_WARPS, "active-set kernel")
+#define TSIDB_AS_SMEM(NV, NC) ((size_t)TSIDB_A_CTA_WARPS(NC) * a_layout(NV, NC).per_env * sizeof(double))
+#define TSIDB_AS_ATTR(NV, NC, W) TSIDB_ATTR((tsidb_activeset_kernel<NV, NC, W>), TSIDB_AS_SMEM(NV, NC), (W) / TSIDB_A_CTA_WARPS(NC), "active-set kernel", cudaSharedmemCarveoutMaxShared)
   TSIDB_AS_ATTR(26, 2, TSIDB_AS_WARPS_DS); TSIDB_AS_ATTR(26, 1, TSIDB_AS_WARPS_SS); TSIDB_AS_ATTR(26, 0, TSIDB_AS_WARPS_FL);
   TSIDB_AS_ATTR(24, 2, TSIDB_AS_WARPS_DS); TSIDB_AS_ATTR(24, 1, TSIDB_AS_WARPS_SS); TSIDB_AS_ATTR(24, 0, TSIDB_AS_WARPS_FL);
 #undef TSIDB_AS_ATTR
-  TSIDB_ATTR(tsidb_dynamics_kernel<26>, smem, TSIDB_D_CTAS_PER_SM, "dynamics kernel");
-  TSIDB_ATTR(tsidb_dynamics_kernel<24>, smem, TSIDB_D_CTAS_PER_SM, "dynamics kernel");
+  /* the dynamics kernel runs alone at the head of the tick and has global loads and a few spills: it asks only for
+   * the carve-out it needs (the next configuration up), which leaves it a larger L1 */
+  const int d_carve = (int)((100 * TSIDB_D_CTAS_PER_SM * (smem + rsv) + per_sm - 1) / per_sm);
+  TSIDB_ATTR(tsidb_dynamics_kernel<26>, smem, TSIDB_D_CTAS_PER_SM, "dynamics kernel", d_carve);
+  TSIDB_ATTR(tsidb_dynamics_kernel<24>, smem, TSIDB_D_CTAS_PER_SM, "dynamics kernel", d_carve);
 #define TSIDB_E_SMEM(NV, NC) (((size_t)TSIDB_E_CTA_WARPS * e_per_env(NV, NC) + 144) * sizeof(double))
-#define TSIDB_E_ATTR(NV, NC, W) TSIDB_ATTR((tsidb_eliminate_kernel<NV, NC, W>), TSIDB_E_SMEM(NV, NC), (W) / TSIDB_E_CTA_WARPS, "elimination kernel")
+#define TSIDB_E_ATTR(NV, NC, W) TSIDB_ATTR((tsidb_eliminate_kernel<NV, NC, W>), TSIDB_E_SMEM(NV, NC), (W) / TSIDB_E_CTA_WARPS, "elimination kernel", cudaSharedmemCarveoutMaxShared)
   TSIDB_E_ATTR(26, 2, TSIDB_E_WARPS); TSIDB_E_ATTR(26, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_ATTR(26, 0, TSIDB_E_WARPS_LIGHT);
   TSIDB_E_ATTR(24, 2, TSIDB_E_WARPS); TSIDB_E_ATTR(24, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_ATTR(24, 0, TSIDB_E_WARPS_LIGHT);
 #undef TSIDB_E_ATTR
   const size_t smem_g = (size_t)TSIDB_G_CTA_WARPS * (SG_IMAGE + 2) * sizeof(double);
-  TSIDB_ATTR((tsidb_j2_kernel<26, 2>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel");
-  TSIDB_ATTR((tsidb_j2_kernel<26, 1>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel");
-  TSIDB_ATTR((tsidb_j2_kernel<26, 0>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel");
-  TSIDB_ATTR((tsidb_j2_kernel<24, 2>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel");
-  TSIDB_ATTR((tsidb_j2_kernel<24, 1>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel");
-  TSIDB_ATTR((tsidb_j2_kernel<24, 0>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel");
+  TSIDB_ATTR((tsidb_j2_kernel<26, 2>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel", cudaSharedmemCarveoutMaxShared);
+  TSIDB_ATTR((tsidb_j2_kernel<26, 1>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel", cudaSharedmemCarveoutMaxShared);
+  TSIDB_ATTR((tsidb_j2_kernel<26, 0>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel", cudaSharedmemCarveoutMaxShared);
+  TSIDB_ATTR((tsidb_j2_kernel<24, 2>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel", cudaSharedmemCarveoutMaxShared);
+  TSIDB_ATTR((tsidb_j2_kernel<24, 1>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel", cudaSharedmemCarveoutMaxShared);
+  TSIDB_ATTR((tsidb_j2_kernel<24, 0>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel", cudaSharedmemCarveoutMaxShared);
 #undef TSIDB_ATTR
   CK(cudaMalloc(&h->counter, 16 * TSIDB_MAX_CHUNKS * sizeof(int32_t)));
   CK(cudaMalloc(&h->ws, (size_t)max_envs * SA_IMAGE * sizeof(double)));
@@ -380,7 +383,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
 #define TSIDB_G_LAUNCH(NV, NC, S) \
   tsidb_j2_kernel<NV, NC><<<grid(TSIDB_G_WARPS, TSIDB_G_CTA_WARPS), 32 * TSIDB_G_CTA_WARPS, smem_g, S>>>(a)
 #define TSIDB_AS_LAUNCH(NV, NC, W, S) \
-  tsidb_activeset_kernel<NV, NC, W><<<grid(W, TSIDB_A_CTA_WARPS), 32 * TSIDB_A_CTA_WARPS, TSIDB_AS_SMEM(NV, NC), S>>>(a)
+  tsidb_activeset_kernel<NV, NC, W><<<grid(W, TSIDB_A_CTA_WARPS(NC)), 32 * TSIDB_A_CTA_WARPS(NC), TSIDB_AS_SMEM(NV, NC), S>>>(a)
     auto launch_e = [&](int nc, cudaStream_t s) {
       if (nv26) { if (nc == 2) TSIDB_E_LAUNCH(26, 2, TSIDB_E_WARPS, s); else if (nc == 1) TSIDB_E_LAUNCH(26, 1, TSIDB_E_WARPS_LIGHT, s); else TSIDB_E_LAUNCH(26, 0, TSIDB_E_WARPS_LIGHT, s); }
       else { if (nc == 2) TSIDB_E_LAUNCH(24, 2, TSIDB_E_WARPS, s); else if (nc == 1) TSIDB_E_LAUNCH(24, 1, TSIDB_E_WARPS_LIGHT, s); else TSIDB_E_LAUNCH(24, 0, TSIDB_E_WARPS_LIGHT, s); }

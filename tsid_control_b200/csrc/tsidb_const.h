@@ -16,7 +16,9 @@
  * narrow CTA returns its shared memory and registers as soon as its warps run out of work) */
 #define TSIDB_E_CTA_WARPS 1
 #define TSIDB_G_CTA_WARPS 1
-#define TSIDB_A_CTA_WARPS 4
+#define TSIDB_A_CTA_WARPS_DS 4
+#define TSIDB_A_CTA_WARPS_SS 4
+#define TSIDB_A_CTA_WARPS(NC) ((NC) == 2 ? TSIDB_A_CTA_WARPS_DS : TSIDB_A_CTA_WARPS_SS)
 /* CTA-wide phase lock-step (all warps of a CTA run the same phase at the same time, so one instruction-cache
  * line serves all of them).  It paid off for the fused 215 KB kernel of the first generation; with one kernel
  * per stage the code fits the instruction cache and free-running warps hide each other's latencies better

@@ -2239,9 +2239,9 @@ tsidb_j2_kernel(const TickArgs a) {
  * classes fit more warps per SM); one-warp CTAs, each class pulls its slots from a work counter of its own because
  * the iteration counts vary from 1 to ~40 */
 template <int NV, int NC, int WARPS>
-__global__ void __launch_bounds__(32 * TSIDB_A_CTA_WARPS, WARPS / TSIDB_A_CTA_WARPS)
+__global__ void __launch_bounds__(32 * TSIDB_A_CTA_WARPS(NC), WARPS / TSIDB_A_CTA_WARPS(NC))
 tsidb_activeset_kernel(const TickArgs a) {
-  static_assert(WARPS % TSIDB_A_CTA_WARPS == 0, "CTA width divides the resident warps");
+  static_assert(WARPS % TSIDB_A_CTA_WARPS(NC) == 0, "CTA width divides the resident warps");
   extern __shared__ double smem[];
   typedef AL<NV, NC> LA;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
