@@ -545,3 +545,29 @@ def test_api_misuse_is_reported_not_executed():
     # the handle still works afterwards
     out = _run(ctrl, q[:n], v[:n], np.full(n, 3, np.uint8))
     assert (out["status"] == 0).all()
+
+
+def test_class_chains_on_streams_equal_the_single_stream_tick(monkeypatch):
+    """The three contact-class chains E -> G -> A run on forked streams by default; TSIDB_CLASS_STREAMS=0 (read when
+    the handle is created) keeps every kernel on the caller's stream.  Both orders of execution give bit-identical
+    results on a mixed batch, also when ticks follow each other without a synchronisation in between."""
+    s = setup("v1")
+    n = 3000
+    q, v = synth.random_states(s["q0"], n, 77)
+    mask, refs = synth.walking_batch(s["refs"], n, 77, 0.3, 0.2, 0.2, 0.5, float(s["refs"]["com"][2]))
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TSIDB_CLASS_STREAMS", flag)
+        ctrl = _controller("v1", n)
+        dev = ctrl.device
+        ctrl.contact_mask = torch.as_tensor(mask, device=dev)
+        ctrl.refs = {k: torch.as_tensor(np.ascontiguousarray(a), device=dev) for k, a in refs.items()}
+        qd, vd = torch.as_tensor(q, device=dev), torch.as_tensor(v, device=dev)
+        for _ in range(3):  # back to back: the next tick's class sort must wait for the side streams of this one
+            ctrl._tick(qd, vd, aux=True)
+        torch.cuda.synchronize()
+        o = ctrl.last
+        outs.append({k: getattr(o, k).cpu().numpy() for k in o.__slots__})
+    for k in ("tau", "ddq", "f", "status", "iters", "active_set"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    assert (outs[0]["status"] == 0).mean() > 0.99
