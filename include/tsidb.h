@@ -22,6 +22,17 @@
  * constants and its workspace.  One handle per device; a handle is not
  * re-entrant.  Device entry points are asynchronous on `cuda_stream`.
  * There is no CPU fallback: every entry point fails (<0) without a CUDA device.
+ *
+ * Streams: a tick is enqueued on `cuda_stream`; internally the three contact-class
+ * kernel chains (double support / single support / flight) are forked onto side
+ * streams of the handle with events and joined back before the call returns, so the
+ * caller sees ordinary stream order (also inside CUDA-graph capture).
+ *
+ * Environment knobs (diagnostics and tuning, not needed in normal use):
+ *   TSIDB_CLASS_STREAMS=0   read by tsidb_create: keep every kernel of a tick on the caller's stream
+ *   TSIDB_HOST_CHUNKS=k     read by tsidb_compute_host: k equal chunks instead of the tapered 1/8,3/8,3/8,1/8 split
+ *   TSIDB_HOST_TAPER=d      read by tsidb_compute_host: first/last chunk = 1/d of the batch
+ *   TSIDB_HOST_TRACE=1      read by tsidb_compute_host: event time stamps per chunk on stderr
  */
 #ifndef TSIDB_H_
 #define TSIDB_H_
