@@ -99,6 +99,18 @@ TSIDB_DEV size_t eidx(const TickArgs& a, int env, int dof, int ndof) {
   return a.layout ? ((size_t)dof * a.n_envs + env) : ((size_t)env * ndof + dof);
 }
 TSIDB_DEV double ldin(const double* p, const TickArgs& a, int env, int dof, int ndof) { return p[eidx(a, env, dof, ndof)]; }
+/* the same element through a base pointer and a stride formed once per env and array */
+struct EnvRow {
+  const double* p;
+  size_t st;
+};
+TSIDB_DEV double env_at(const EnvRow& r, int dof) { return r.p[(size_t)dof * r.st]; }
+TSIDB_DEV EnvRow env_row(const double* p, const TickArgs& a, int env, int ndof) {
+  EnvRow r;
+  r.p = p + (a.layout ? (size_t)env : (size_t)env * ndof);
+  r.st = a.layout ? (size_t)a.n_envs : (size_t)1;
+  return r;
+}
 
 /* pinocchio log3 (2.x) + log6: M = (R row-major, p) -> [lin; ang] */
 TSIDB_DEV void log6_dev(const double* R, const double* p, double* out) {
@@ -578,16 +590,18 @@ TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, con
     double ref[24];
     if (is_contact) {
       const double* src = a.r_contact[f];
+      const EnvRow row = env_row(src, a, env, 12);
 #pragma unroll
-      for (int k = 0; k < 12; k++) ref[k] = src ? ldin(src, a, env, k, 12) : C.ref_contact[f][k];
+      for (int k = 0; k < 12; k++) ref[k] = src ? env_at(row, k) : C.ref_contact[f][k];
       double b6[6];
       se3_rhs(fr, f, C.kp_contact, C.kd_contact, ref, nullptr, nullptr, b6);
 #pragma unroll
       for (int k = 0; k < 6; k++) bv[BV_MOT + 6 * f + k] = b6[k];
     } else {
       const double* src = a.r_foot[f];
+      const EnvRow row = env_row(src, a, env, 24);
 #pragma unroll
-      for (int k = 0; k < 24; k++) ref[k] = src ? ldin(src, a, env, k, 24) : C.ref_foot[f][k];
+      for (int k = 0; k < 24; k++) ref[k] = src ? env_at(row, k) : C.ref_foot[f][k];
       double b6[6];
       se3_rhs(fr, f, C.kp_foot, C.kd_foot, ref, ref + 12, ref + 18, b6);
 #pragma unroll
@@ -596,9 +610,10 @@ TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, con
   } else if (lane < 7) {
     /* tsid::TaskComEquality */
     const int r = lane - 4;
-    double rp = a.r_com ? ldin(a.r_com, a, env, r, 9) : C.ref_com[r];
-    double rv = a.r_com ? ldin(a.r_com, a, env, 3 + r, 9) : C.ref_com[3 + r];
-    double ra = a.r_com ? ldin(a.r_com, a, env, 6 + r, 9) : C.ref_com[6 + r];
+    const EnvRow row = env_row(a.r_com, a, env, 9);
+    double rp = a.r_com ? env_at(row, r) : C.ref_com[r];
+    double rv = a.r_com ? env_at(row, 3 + r) : C.ref_com[3 + r];
+    double ra = a.r_com ? env_at(row, 6 + r) : C.ref_com[6 + r];
     double ades = -C.kp_com[r] * (fr[FR_COM + r] - rp) - C.kd_com[r] * (fr[FR_COM + 3 + r] - rv) + ra;
     bv[BV_COM + r] = ades - fr[FR_COM + 6 + r];
   } else if (lane < 10) {
@@ -1787,25 +1802,37 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
   const int n = nv + 12 * nc, neq = 6 + 6 * nc;
   /* M shares its shared-memory region with the Hessian block that K2 is about to write: the rows of M that the
    * later stages need leave for their images now */
-  const ALayout LA = a_layout(nv, nc);
+  /* offsets of the class's solver-image layout (compile-time per class; the class of the env is data) */
+  const int oMa_c = (nc == 2) ? AL<NV, 2>::oMa : ((nc == 1) ? AL<NV, 1>::oMa : AL<NV, 0>::oMa);
+  const int oJFa_c = (nc == 2) ? AL<NV, 2>::oJFa : ((nc == 1) ? AL<NV, 1>::oJFa : AL<NV, 0>::oJFa);
+  const int oNle_c = (nc == 2) ? AL<NV, 2>::oNle : ((nc == 1) ? AL<NV, 1>::oNle : AL<NV, 0>::oNle);
+  const int oVj_c = (nc == 2) ? AL<NV, 2>::oVj : ((nc == 1) ? AL<NV, 1>::oVj : AL<NV, 0>::oVj);
   double* img = a.ws + (size_t)slot * SA_IMAGE;
   double* eimg = a.ws3 + (size_t)slot * SE_IMAGE;
-  for (int k = lane; k < na * SA_LDM; k += 32) {
-    const int r = k / SA_LDM, c = k % SA_LDM;
-    img[LA.oMa + k] = (c < nv) ? sm[SM_oM + (6 + r) * SM_LDM + c] : 0.0;
+  /* M_a row by row (lanes over the columns): no index arithmetic per element */
+  if (lane < SA_LDM) {
+    double* dst = img + oMa_c + lane;
+    const double* srcm = sm + SM_oM + 6 * SM_LDM + lane;
+#pragma unroll
+    for (int r = 0; r < na; r++) dst[r * SA_LDM] = (lane < nv) ? srcm[r * SM_LDM] : 0.0;
   }
   for (int k = lane; k < 162; k += 32) eimg[SE_oMu + k] = sm[SM_oM + k];
   __syncwarp();
   PHASE_SYNC_D();
   k2_assemble<NV>(C, mdl, sm, a, env, lane, mask, neq, n);
   /* solver image (layout a_layout(nv, nc)): the parts that do not depend on the elimination */
-  for (int k = lane; k < 6 * nc * SA_LDJA; k += 32) {
-    /* rows of the feet in contact, in force-block order (block 0 = LF if it is in contact, else RF) */
-    const int q = k / SA_LDJA, r = k % SA_LDJA;
-    const int f = (q < 6) ? ((mask & 1) ? 0 : 1) : 1;
-    img[LA.oJFa + k] = (r < na) ? sm[SM_oJF + (f * 6 + q % 6) * TSIDB_NVX + 6 + r] : 0.0;
+  /* rows of the feet in contact, in force-block order (block 0 = LF if it is in contact, else RF), row by row */
+  if (lane < SA_LDJA) {
+    const int f0 = (mask & 1) ? 0 : 1;
+#pragma unroll
+    for (int q = 0; q < 12; q++) {
+      if (q < 6 * nc) {
+        const int f = (q < 6) ? f0 : 1;
+        img[oJFa_c + q * SA_LDJA + lane] = (lane < na) ? sm[SM_oJF + (f * 6 + q % 6) * TSIDB_NVX + 6 + lane] : 0.0;
+      }
+    }
   }
-  if (lane < na) { img[LA.oNle + lane] = sm[SM_oNle + 6 + lane]; img[LA.oVj + lane] = sm[SM_oQV + 32 + 6 + lane]; }
+  if (lane < na) { img[oNle_c + lane] = sm[SM_oNle + 6 + lane]; img[oVj_c + lane] = sm[SM_oQV + 32 + 6 + lane]; }
   if (lane == 0) img[SA_oSc + 3] = (double)mask;
   /* assembly image (layout SE_*) for the elimination kernel */
 #ifndef TSIDB_EMU
@@ -1853,16 +1880,21 @@ TSIDB_DEV void eliminate_env(const DevConst& C, const double* lfinv_sm, double* 
   if (lane == 0) { img[SA_oSc] = c1c2; img[SA_oSc + 1] = R_norm; img[SA_oSc + 2] = (double)err; }
   /* factor image (layout SG_*) for the J2 kernel */
   double* fimg = a.ws2 + (size_t)slot * SG_IMAGE;
-  for (int k = lane; k < nv * SG_LDL; k += 32) {
-    const int r = k / SG_LDL, c = k % SG_LDL;
-    fimg[SG_oL + k] = (c <= r) ? sm[SE_oH + r * SM_LDM + c] : 0.0;
+  /* L row by row (lanes over the columns, zeros above the diagonal): no index arithmetic per element */
+  if (lane < SG_LDL) {
+    double* dst = fimg + SG_oL + lane;
+    const double* srcl = sm + SE_oH + (lane < SM_LDM ? lane : 0);
+#pragma unroll
+    for (int r = 0; r < nv; r++) dst[r * SG_LDL] = (lane <= r) ? srcl[r * SM_LDM] : 0.0;
   }
   if (lane < nv) fimg[SG_oILD + lane] = sm[LE::oILD + lane];
   if (lane < LE::NEQ) fimg[SG_oTAU + lane] = sm[LE::oTAU + lane];
   if (lane == 0) fimg[SG_oERR] = (double)err;
-  for (int k = lane; k < LE::NEQ * LE::N; k += 32) {
-    const int i = k / LE::N, j = k % LE::N; /* restride the reflector rows: N in shared memory, SG_LDV in the image */
-    fimg[SG_oVT + i * SG_LDV + j] = sm[LE::oVT + k];
+  /* restride the reflector rows: N in shared memory, SG_LDV in the image */
+#pragma unroll
+  for (int i = 0; i < LE::NEQ; i++) {
+    if (lane < LE::N) fimg[SG_oVT + i * SG_LDV + lane] = sm[LE::oVT + i * LE::N + lane];
+    if (lane + 32 < LE::N) fimg[SG_oVT + i * SG_LDV + lane + 32] = sm[LE::oVT + i * LE::N + lane + 32];
   }
   __syncwarp();
 }
