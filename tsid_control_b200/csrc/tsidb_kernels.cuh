@@ -238,32 +238,80 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int
 #pragma unroll
     for (int k = 0; k < 3; k++) { p[k] = pl[k]; Vl[k] = 0; Va[k] = 0; }
   }
-  /* top-down: placements, velocities, drift accelerations */
-  for (int L = 1; L <= C.maxdepth; L++) {
-    double Rp[9], pp[3], Vlp[3], Vap[3], Alp[3], Aap[3];
+  /* Top-down by POINTER JUMPING instead of one tree level at a time: every body composes its transform with its
+   * current ancestor's and then points to that ancestor's ancestor, so ceil(log2(depth)) rounds reach the root
+   * (3 instead of 6 for the humanoids here); the twists and the drift accelerations are sums along the path to the
+   * root in world coordinates and are accumulated the same way.  anc = -1: the quantity is already a world one. */
+  int rounds = 0;
+  while ((1 << rounds) < C.maxdepth) rounds++;
+  const int par0 = (act && lane > 0) ? par : -1;
+  {
+    int anc = par0;
+    for (int rd = 0; rd < rounds; rd++) {
+      const int src = anc < 0 ? 0 : anc;
+      double Rp[9], pp[3];
 #pragma unroll
-    for (int k = 0; k < 9; k++) Rp[k] = shfl(R[k], par);
+      for (int k = 0; k < 9; k++) Rp[k] = shfl(R[k], src);
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      pp[k] = shfl(p[k], par); Vlp[k] = shfl(Vl[k], par); Vap[k] = shfl(Va[k], par);
-      Alp[k] = shfl(Al[k], par); Aap[k] = shfl(Aa[k], par);
+      for (int k = 0; k < 3; k++) pp[k] = shfl(p[k], src);
+      const int anc2 = __shfl_sync(FULL, anc, src);
+      if (anc >= 0) {
+        double Rn[9], pn[3];
+        mm3(Rp, R, Rn);
+        mv3(Rp, p, pn);
+#pragma unroll
+        for (int k = 0; k < 9; k++) R[k] = Rn[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) p[k] = pn[k] + pp[k];
+        anc = anc2;
+      }
     }
-    if (dep == L) {
-      mm3(Rp, Rl, R);
-      mv3(Rp, pl, p);
-      p[0] += pp[0]; p[1] += pp[1]; p[2] += pp[2];
-      double a[3] = {R[2], R[5], R[8]}, sl[3];
-      cross3(p, a, sl);
-      double Sl[3] = {sl[0] * qd, sl[1] * qd, sl[2] * qd}, Sa[3] = {a[0] * qd, a[1] * qd, a[2] * qd};
+  }
+  /* own twist S qd of the body's joint (the base keeps its twist): V = sum over the path to the root */
+  double Sql[3] = {0, 0, 0}, Sqa[3] = {0, 0, 0};
+  if (lane > 0) {
+    double a[3] = {R[2], R[5], R[8]}, sl[3];
+    cross3(p, a, sl);
 #pragma unroll
-      for (int k = 0; k < 3; k++) { Vl[k] = Vlp[k] + Sl[k]; Va[k] = Vap[k] + Sa[k]; }
-      /* A = A_parent + V x (S qd)   (motion cross product) */
-      double c1[3], c2[3], c3[3];
-      cross3(Vl, Sa, c1);
-      cross3(Va, Sl, c2);
-      cross3(Va, Sa, c3);
+    for (int k = 0; k < 3; k++) { Sql[k] = sl[k] * qd; Sqa[k] = a[k] * qd; Vl[k] = Sql[k]; Va[k] = Sqa[k]; }
+  }
+  {
+    int anc = par0;
+    for (int rd = 0; rd < rounds; rd++) {
+      const int src = anc < 0 ? 0 : anc;
+      double Vlp[3], Vap[3];
 #pragma unroll
-      for (int k = 0; k < 3; k++) { Al[k] = Alp[k] + c1[k] + c2[k]; Aa[k] = Aap[k] + c3[k]; }
+      for (int k = 0; k < 3; k++) { Vlp[k] = shfl(Vl[k], src); Vap[k] = shfl(Va[k], src); }
+      const int anc2 = __shfl_sync(FULL, anc, src);
+      if (anc >= 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { Vl[k] += Vlp[k]; Va[k] += Vap[k]; }
+        anc = anc2;
+      }
+    }
+  }
+  /* own drift term V x (S qd) (motion cross product; zero for the base): A = sum over the path to the root */
+  if (lane > 0) {
+    double c1[3], c2[3], c3[3];
+    cross3(Vl, Sqa, c1);
+    cross3(Va, Sql, c2);
+    cross3(Va, Sqa, c3);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { Al[k] = c1[k] + c2[k]; Aa[k] = c3[k]; }
+  }
+  {
+    int anc = par0;
+    for (int rd = 0; rd < rounds; rd++) {
+      const int src = anc < 0 ? 0 : anc;
+      double Alp[3], Aap[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { Alp[k] = shfl(Al[k], src); Aap[k] = shfl(Aa[k], src); }
+      const int anc2 = __shfl_sync(FULL, anc, src);
+      if (anc >= 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { Al[k] += Alp[k]; Aa[k] += Aap[k]; }
+        anc = anc2;
+      }
     }
   }
   /* motion subspace of the body's joint (revolute z): S = (p x a, a) */
