@@ -122,8 +122,10 @@ TSIDB_DEV void log6_dev(const double* R, const double* p, double* out) {
   else th = acos((tr - 1.0) / 2.0);
   double w[3];
   const double prec3 = 1.220703125e-4;
-  double st, ct; /* one sincos for every use below (the SE3 logs sit on the critical path of the assembly) */
-  sincos(th, &st, &ct);
+  /* cos(th) is the argument of the acos and sin(th) = sqrt((1 - c)(1 + c)) on [0, pi]: no sincos on the critical
+   * path of the assembly (1 - c is exact near c = 1, where the product form keeps full relative accuracy) */
+  const double ct = (tr >= 3.0) ? 1.0 : ((tr <= -1.0) ? -1.0 : (tr - 1.0) / 2.0);
+  const double st = sqrt(fmax((1.0 - ct) * (1.0 + ct), 0.0));
   if (th >= PI - 1e-2) {
     double cphi = -(tr - 1.0) / 2.0;
     double beta = th * th / (1.0 + cphi);
