@@ -1242,9 +1242,7 @@ struct LaneConst {
   double vmin, vmax; /* joint velocity limits of joint `lane` */
   double fric[3];    /* friction pyramid row lane % 4 */
   double Trow[12];   /* row lane%6 of the force generator */
-  unsigned bits_lo, bits_hi; /* reference row index (cid_bit, < 256) of the lane's six candidate rows, one byte each */
 };
-TSIDB_DEV int lane_bit(const LaneConst& K, int k) { return (int)(((k < 4) ? (K.bits_lo >> (8 * k)) : (K.bits_hi >> (8 * (k - 4)))) & 0xffu); }
 
 struct ASCtx {
   int na, nv;         /* compile-time in the per-class kernels (constant-propagated through the inlined solver) */
@@ -1307,15 +1305,6 @@ TSIDB_DEV void lane_const_init(const DevConst& C, LaneConst& K, int lane) {
   K.vmin = (lane < na) ? C.v_min[lane] : 0.0;
   K.vmax = (lane < na) ? C.v_max[lane] : 0.0;
   K.lb = K.ub = 0.0;
-  K.bits_lo = K.bits_hi = 0u;
-#pragma unroll
-  for (int k = 0; k < 6; k++) {
-    /* rows the lane does not own get a harmless in-range value; they are never candidates (s = +inf) */
-    const bool owns = (k == 0) || (k == 1 && lane < 4) || (k >= 2 && lane < na);
-    const unsigned b = owns ? (unsigned)cid_bit(na, C.nv, cid_of(na, lane, k)) : 0u;
-    if (k < 4) K.bits_lo |= (b & 0xffu) << (8 * k);
-    else K.bits_hi |= (b & 0xffu) << (8 * (k - 4));
-  }
 }
 
 /* s = CI x + ci0 for the rows this lane owns; invalid rows get +inf */
@@ -1540,20 +1529,19 @@ TSIDB_DEVNI int qp_delete(double* Rp, double* u, int* A, double* J2, double* ird
 
 /* this lane's most violated row among the rows it owns that are neither active nor excluded; ties to the lowest
  * reference row index */
-TSIDB_DEV void pick_local(const double (&sl)[6], const LaneConst& K, unsigned actbits, unsigned exclbits, int na, int lane,
+TSIDB_DEV void pick_local(const double (&sl)[6], unsigned actbits, unsigned exclbits, int na, int nv, int lane,
                           double& best, int& bcid, int& bbit) {
   best = 0.0;
+  bcid = -1;
   bbit = 1 << 30;
-  int bk = -1;
-  const unsigned skip = actbits | exclbits;
 #pragma unroll
   for (int k = 0; k < 6; k++) {
-    if (!((skip >> k) & 1u) && sl[k] < 0.0) {
-      const int bit = lane_bit(K, k); /* reference row index: a per-lane constant */
-      if (sl[k] < best || (sl[k] == best && bit < bbit)) { best = sl[k]; bk = k; bbit = bit; }
+    if (!((actbits >> k) & 1u) && !((exclbits >> k) & 1u) && sl[k] < 0.0) {
+      const int cid = cid_of(na, lane, k);
+      const int bit = cid_bit(na, nv, cid);
+      if (sl[k] < best || (sl[k] == best && bit < bbit)) { best = sl[k]; bcid = cid; bbit = bit; }
     }
   }
-  bcid = (bk >= 0) ? cid_of(na, lane, bk) : -1;
 }
 
 /* Active-set iterations on the reduced basis [eiquadprog-fast solve_quadprog, after the equality phase]. */
@@ -1600,7 +1588,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
      * before branching on the sum so that their latencies overlap */
     double best;
     int bcid, bbit;
-    pick_local(sl, K, actbits, exclbits, na, lane, best, bcid, bbit);
+    pick_local(sl, actbits, exclbits, na, nv, lane, best, bcid, bbit);
     int src = warp_argmin(best, bcid >= 0, bbit);
     double psi = warp_sum(part);
     if (fabs(psi) <= psi_thresh) { status = ST_OPTIMAL; break; }
@@ -1612,7 +1600,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
     for (;;) { /* l2 */
       /* most violated row, lowest reference index on ties */
       if (!first_pick) {
-        pick_local(sl, K, actbits, exclbits, na, lane, best, bcid, bbit);
+        pick_local(sl, actbits, exclbits, na, nv, lane, best, bcid, bbit);
         src = warp_argmin(best, bcid >= 0, bbit);
       }
       first_pick = false;
