@@ -241,11 +241,11 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int
     for (int k = 0; k < 3; k++) { p[k] = pl[k]; Vl[k] = 0; Va[k] = 0; }
   }
   /* Top-down by POINTER JUMPING instead of one tree level at a time: every body composes its transform with its
-   * current ancestor's and then points to that ancestor's ancestor, so ceil(log2(depth)) rounds reach the root
-   * (3 instead of 6 for the humanoids here); the twists and the drift accelerations are sums along the path to the
+   * current ancestor's and then points to that ancestor's ancestor: after r rounds a transform spans 2^r joints, so
+   * ceil(log2(depth + 1)) rounds reach the world frame (3 instead of 6 for the humanoids here); the twists and the drift accelerations are sums along the path to the
    * root in world coordinates and are accumulated the same way.  anc = -1: the quantity is already a world one. */
   int rounds = 0;
-  while ((1 << rounds) < C.maxdepth) rounds++;
+  while ((1 << rounds) <= C.maxdepth) rounds++;
   const int par0 = (act && lane > 0) ? par : -1;
   {
     int anc = par0;
