@@ -1,12 +1,14 @@
 /* tsidb_kernels.cuh — device code of the batched TSID tick for sm_100a.
  *
  * One warp solves one robot instance ("env"); all arithmetic is fp64.  The tick is a pipeline of persistent
- * kernels (one CTA per SM), each with the thread mapping, register budget and warp count that suit its stage;
- * an env's state moves from stage to stage as an "image" in HBM that the consumer pulls into shared memory
- * with one bulk asynchronous copy (TMA).  DESIGN.md §4 has the table with sizes and measured times.
+ * kernels, each with the thread mapping, register budget, CTA width and resident warp count that suit its stage
+ * (dynamics: one 16-warp CTA per SM; elimination and basis: 8-12 one-warp CTAs per SM on a work counter; active
+ * set: 4-warp CTAs); an env's state moves from stage to stage as an "image" in HBM that the consumer pulls into
+ * shared memory with one bulk asynchronous copy (TMA).  DESIGN.md §4 has the table with sizes and measured times.
  *
  *   kernel D  tsidb_dynamics_kernel        (reference function each phase replaces)
- *     K1 dynamics   lane <-> body.  World-frame FK, velocities, zero-acceleration drift, composite inertias and
+ *     K1 dynamics   lane <-> body.  World-frame FK, velocities, zero-acceleration drift (pointer jumping over the
+ *                   kinematic tree: log2(depth) rounds of shuffles), composite inertias and
  *                   forces accumulated up the tree, then M (CRBA), nle (RNEA), frame Jacobians, CoM/Jcom,
  *                   centroidal angular rows.
  *                   [tsid::RobotWrapper::computeAllTerms inside computeProblemData, ref:main.py:119]
@@ -22,7 +24,8 @@
  *                   per column.
  *     A  tsidb_activeset_kernel   the iterations on J2 (one lane per column / per row), then
  *        decode     dv, f, tau = h_a + M_a dv - J_a^T f.   [ref:main.py:126-127]
- *   E and A are instantiated and launched per contact class (nc = 2, 1, 0): every size is a compile-time constant.
+ *   E, G and A are instantiated and launched per contact class (nc = 2, 1, 0): every size is a compile-time
+ *   constant; the host runs the three class chains E -> G -> A on forked streams (tsidb.cu, launch_tick).
  *
  * The file also compiles for the host under tests/emu (lock-step warp emulator that poisons shared memory with
  * NaN) so that the kernel logic can be exercised without a GPU; TSIDB_EMU selects that build.
