@@ -8,6 +8,7 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/bench_${tag}.log 2> gpurun_ou
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_${tag}.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_${tag}.log 2>&1; echo "ncu launches rc=$?"
 if [ "$2" = "full" ]; then
-  ncu --set full --clock-control none --import-source on -k regex:"tsidb_(prepare|j2|activeset)" -s 9 -c 3 -o gpurun_out/prof_${tag} -f \
+  # one launch of each tick kernel (dynamics + 3 classes x elimination, basis, active set) of the second warm-up tick
+  ncu --set full --clock-control none --import-source on -k regex:"tsidb_(dynamics|eliminate|j2|activeset)" -s 10 -c 10 -o gpurun_out/prof_${tag} -f \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${tag}.log 2>&1; echo "ncu full rc=$?"
 fi
