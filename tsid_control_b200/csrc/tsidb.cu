@@ -218,7 +218,8 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
 #undef TSIDB_AS_ATTR
   /* the dynamics kernel runs alone at the head of the tick and has global loads and a few spills: it asks only for
    * the carve-out it needs (the next configuration up), which leaves it a larger L1 */
-  const int d_carve = (int)((100 * TSIDB_D_CTAS_PER_SM * (smem + rsv) + per_sm - 1) / per_sm);
+  int d_carve = (int)((100 * TSIDB_D_CTAS_PER_SM * (smem + rsv) + per_sm - 1) / per_sm);
+  if (const char* e = getenv("TSIDB_D_CARVEOUT")) { const int v = atoi(e); if (v >= d_carve && v <= 100) d_carve = v; } /* tuning knob */
   TSIDB_ATTR(tsidb_dynamics_kernel<26>, smem, TSIDB_D_CTAS_PER_SM, "dynamics kernel", d_carve);
   TSIDB_ATTR(tsidb_dynamics_kernel<24>, smem, TSIDB_D_CTAS_PER_SM, "dynamics kernel", d_carve);
 #define TSIDB_E_SMEM(NV, NC) (((size_t)TSIDB_E_CTA_WARPS * e_per_env(NV, NC) + 144) * sizeof(double))
