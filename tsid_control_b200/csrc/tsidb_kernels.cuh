@@ -529,14 +529,13 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int
 #pragma unroll
   for (int f = 0; f < 2; f++) {
     const int fb = C.foot_body[f];
-    double Rb[9], pb[3], Vbl[3], Vba[3], Abl[3], Aba[3];
+    /* every lane needs the placement of the foot's body (Jacobian columns); its twist and drift acceleration are
+     * only needed for the frame's own velocity terms, which the body's lane forms from its registers */
+    double Rb[9], pb[3];
 #pragma unroll
     for (int k = 0; k < 9; k++) Rb[k] = shfl(R[k], fb);
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      pb[k] = shfl(p[k], fb); Vbl[k] = shfl(Vl[k], fb); Vba[k] = shfl(Va[k], fb);
-      Abl[k] = shfl(Al[k], fb); Aba[k] = shfl(Aa[k], fb);
-    }
+    for (int k = 0; k < 3; k++) pb[k] = shfl(p[k], fb);
     double Rf[9], pf[3], t[3];
     mm3(Rb, C.fR[f], Rf);
     mv3(Rb, C.fp[f], pf);
@@ -570,15 +569,15 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int
         JF[(f * 6 + 3 + r) * TSIDB_NVX + lane] = la[r];
       }
     }
-    if (lane == 0) {
+    if (lane == fb) {
       double vl[3], va[3], al[3], aa[3];
-      mtv3(Rf, Vba, va);
-      cross3(pf, Vba, t);
-      double d[3] = {Vbl[0] - t[0], Vbl[1] - t[1], Vbl[2] - t[2]};
+      mtv3(Rf, Va, va);
+      cross3(pf, Va, t);
+      double d[3] = {Vl[0] - t[0], Vl[1] - t[1], Vl[2] - t[2]};
       mtv3(Rf, d, vl);
-      mtv3(Rf, Aba, aa);
-      cross3(pf, Aba, t);
-      double e[3] = {Abl[0] - t[0], Abl[1] - t[1], Abl[2] - t[2]};
+      mtv3(Rf, Aa, aa);
+      cross3(pf, Aa, t);
+      double e[3] = {Al[0] - t[0], Al[1] - t[1], Al[2] - t[2]};
       mtv3(Rf, e, al);
       cross3(va, vl, t);
 #pragma unroll
