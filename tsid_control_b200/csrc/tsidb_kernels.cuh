@@ -828,6 +828,8 @@ TSIDB_DEV void reflect(double (&c)[N], const double* v, double tau) {
   }
 }
 
+template <bool B>
+struct BoolTag { static constexpr bool value = B; };
 /* head row of reflector k for a class with NCM contact-motion equalities (see k3_eliminate) */
 template <int NV, int NCM>
 TSIDB_DEV constexpr int head_row(int k) { return (k < NCM || NCM == 0) ? k : NV + (k - NCM); }
@@ -978,17 +980,17 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
       for (int k = 0; k < N; k++) b[k] = -b[k]; /* w_unc = -L^-1 g */
     }
     PHASE_SYNC_E();
-    for (int i = 0; i < neq; i++) {
+    /* Reflector i < ncm (contact motion): head row i, span = dv rows i..NV-1.  Reflector i >= ncm (base
+     * dynamics): head = force row NV + (i - ncm), span = dv rows ncm..NV-1 and the force rows from the head
+     * on.  The base-dynamics columns carry their largest entries in the force rows (scaled by Lf^-1), so
+     * pivoting on those keeps the factorisation row-wise stable; with the head on a small dv row the
+     * result is 40x further from the 80-bit truth (measured).  Without contacts there are no
+     * force rows: head i, span i..NV-1.  The two kinds run in loops of their own (the kind is a compile-time
+     * constant of the step: a contact-motion reflector lives in the rows below 32, one trip per lane). */
+    auto qr_step = [&](const int i, auto top_tag) {
+      constexpr bool top = decltype(top_tag)::value;
       PHASE_SYNC_E();
-      /* Reflector i < ncm (contact motion): head row i, span = dv rows i..NV-1.  Reflector i >= ncm (base
-       * dynamics): head = force row NV + (i - ncm), span = dv rows ncm..NV-1 and the force rows from the head
-       * on.  The base-dynamics columns carry their largest entries in the force rows (scaled by Lf^-1), so
-       * pivoting on those keeps the factorisation row-wise stable; with the head on a small dv row the
-       * result is 40x further from the 80-bit truth (measured).  Without contacts there are no
-       * force rows: head i, span i..NV-1. */
-      const bool top = i < ncm || nc == 0;
       const int head = top ? i : NV + (i - ncm);
-      const int lo = top ? i : ncm;          /* first dv row of the span */
       __syncwarp();
       if (lane == i) {
         double2* c2 = reinterpret_cast<double2*>(colp);
@@ -997,9 +999,13 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
       }
       __syncwarp();
       double part = 0.0;
-      for (int k = lane; k < n; k += 32) {
-        const bool in_span = (k >= lo && k < NV) || (!top && k > head);
-        if (in_span && k != head) { const double t = colp[k]; part += t * t; }
+      if (top) {
+        if (lane > i && lane < NV) { const double t = colp[lane]; part = t * t; }
+      } else {
+        for (int k = lane; k < n; k += 32) {
+          const bool in_span = (k >= ncm && k < NV) || k > head;
+          if (in_span) { const double t = colp[k]; part += t * t; }
+        }
       }
       const double sigma = warp_sum(part);
       const double alpha = colp[head];
@@ -1012,9 +1018,14 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
        * the vector can be published as soon as beta is known, and the one reciprocal (instead of two divisions)
        * overlaps with the dot products of the reflection */
       const double uh = alpha - beta;
-      for (int k = lane; k < N; k += 32) {
-        const bool in_span = (k >= lo && k < NV) || (!top && k > head);
-        Vt[i * LDV + k] = (k == head) ? uh : (in_span ? colp[k] : 0.0);
+      if (top) {
+        Vt[i * LDV + lane] = (lane == i) ? uh : ((lane > i && lane < NV) ? colp[lane] : 0.0);
+        if (lane + 32 < N) Vt[i * LDV + lane + 32] = 0.0;
+      } else {
+        for (int k = lane; k < N; k += 32) {
+          const bool in_span = (k >= ncm && k < NV) || k > head;
+          Vt[i * LDV + k] = (k == head) ? uh : (in_span ? colp[k] : 0.0);
+        }
       }
       const double tau = -1.0 / (beta * uh);
       if (lane == 0) { tauq[i] = tau; Rd[i] = beta; }
@@ -1023,7 +1034,10 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
         if (top) reflect<N, NV, (NC == 2)>(b, Vt + i * LDV, tau);
         else reflect<N, N, (NC == 2)>(b, Vt + i * LDV, tau);
       }
-    }
+    };
+    constexpr int n_top = (nc == 0) ? neq : ncm;
+    for (int i = 0; i < n_top; i++) qr_step(i, BoolTag<true>());
+    for (int i = n_top; i < neq; i++) qr_step(i, BoolTag<false>());
     __syncwarp();
     /* R1 (strictly upper part; the diagonal is Rd) and the carried column */
     if (lane <= neq) {
