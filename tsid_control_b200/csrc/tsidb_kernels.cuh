@@ -777,17 +777,17 @@ TSIDB_DEV void fwdsub_L(double (&b)[NV + 12 * NC], const double* L, const double
   }
 }
 
-/* c[0:K) <- (I - tau v v^T) c[0:K) with the dense reflector v (explicit zeros above its head, 1 at the head);
- * rows K.. of v are zero by construction and are not visited */
-template <int N, int K, bool RELOAD>
+/* c[K0:K) <- (I - tau v v^T) c[K0:K) with the dense reflector v (explicit zeros above its head, the unscaled head
+ * entry at the head); rows below K0 and from K on are zero in v by construction and are not visited */
+template <int N, int K0, int K, bool RELOAD>
 TSIDB_DEV void reflect(double (&c)[N], const double* v, double tau) {
-  static_assert((K & 1) == 0, "rows come in pairs");
+  static_assert((K & 1) == 0 && (K0 & 1) == 0, "rows come in pairs");
   /* the reflector is read as 16-byte pairs (broadcast): half the shared-memory instructions */
   const double2* v2 = reinterpret_cast<const double2*>(v);
   double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
   if (RELOAD) {
 #pragma unroll
-    for (int k = 0; k < K; k += 4) {
+    for (int k = K0; k < K; k += 4) {
       const double2 p = v2[k >> 1];
       w0 += p.x * c[k];
       w1 += p.y * c[k + 1];
@@ -800,30 +800,30 @@ TSIDB_DEV void reflect(double (&c)[N], const double* v, double tau) {
     const double w = tau * ((w0 + w1) + (w2 + w3));
     SCHED_FENCE(); /* reload v for the update instead of keeping 50 more values live (spills otherwise) */
 #pragma unroll
-    for (int k = 0; k < K; k += 2) {
+    for (int k = K0; k < K; k += 2) {
       const double2 p = v2[k >> 1];
       c[k] -= w * p.x;
       c[k + 1] -= w * p.y;
     }
   } else {
     /* the lighter classes have the registers to keep the reflector between the two passes */
-    double2 p[K / 2];
+    double2 p[(K - K0) / 2];
 #pragma unroll
-    for (int k = 0; k < K / 2; k++) p[k] = v2[k];
+    for (int k = 0; k < (K - K0) / 2; k++) p[k] = v2[(K0 >> 1) + k];
 #pragma unroll
-    for (int k = 0; k < K; k += 4) {
-      w0 += p[k >> 1].x * c[k];
-      w1 += p[k >> 1].y * c[k + 1];
-      if (k + 2 < K) {
-        w2 += p[(k >> 1) + 1].x * c[k + 2];
-        w3 += p[(k >> 1) + 1].y * c[k + 3];
+    for (int k = 0; k < K - K0; k += 4) {
+      w0 += p[k >> 1].x * c[K0 + k];
+      w1 += p[k >> 1].y * c[K0 + k + 1];
+      if (k + 2 < K - K0) {
+        w2 += p[(k >> 1) + 1].x * c[K0 + k + 2];
+        w3 += p[(k >> 1) + 1].y * c[K0 + k + 3];
       }
     }
     const double w = tau * ((w0 + w1) + (w2 + w3));
 #pragma unroll
-    for (int k = 0; k < K; k += 2) {
-      c[k] -= w * p[k >> 1].x;
-      c[k + 1] -= w * p[k >> 1].y;
+    for (int k = 0; k < K - K0; k += 2) {
+      c[K0 + k] -= w * p[k >> 1].x;
+      c[K0 + k + 1] -= w * p[k >> 1].y;
     }
   }
 }
@@ -1031,8 +1031,8 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
       if (lane == 0) { tauq[i] = tau; Rd[i] = beta; }
       __syncwarp();
       if (lane > i && lane <= neq) {
-        if (top) reflect<N, NV, (NC == 2)>(b, Vt + i * LDV, tau);
-        else reflect<N, N, (NC == 2)>(b, Vt + i * LDV, tau);
+        if (top) reflect<N, 0, NV, (NC == 2)>(b, Vt + i * LDV, tau);
+        else reflect<N, ncm, N, (NC == 2)>(b, Vt + i * LDV, tau); /* a base-dynamics reflector is zero in the dv rows above ncm */
       }
     };
     constexpr int n_top = (nc == 0) ? neq : ncm;
