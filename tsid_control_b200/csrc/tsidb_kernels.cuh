@@ -1079,7 +1079,8 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
 #pragma unroll
   for (int i = neq - 1; i >= 0; i--) {
     const double v0 = (lane < N) ? Vt[i * LDV + lane] : 0.0; /* a reflector row holds N entries */
-    const double v1 = (lane + 32 < N) ? Vt[i * LDV + lane + 32] : 0.0;
+    /* a contact-motion reflector (i < ncm, or any reflector without contacts) is zero in the rows from 32 on */
+    const double v1 = (i >= ((nc == 0) ? neq : ncm) && lane + 32 < N) ? Vt[i * LDV + lane + 32] : 0.0;
     const double w = tauq[i] * warp_sum(v0 * y0 + v1 * y1);
     y0 -= w * v0;
     y1 -= w * v1;
@@ -1091,9 +1092,13 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
   __syncwarp();
   if (lane < 12 * nc) {
     const int s = lane / 12, i = lane % 12;
-    double acc = 0.0;
-    for (int k = i; k < 12; k++) acc += lfinv_sm[k * 12 + i] * w0v[NV + 12 * s + k];
-    x[NV + lane] = acc;
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; k += 2) { /* Lf^-1 is lower triangular: entries above the diagonal are stored as zeros */
+      acc0 += lfinv_sm[k * 12 + i] * w0v[NV + 12 * s + k];
+      acc1 += lfinv_sm[(k + 1) * 12 + i] * w0v[NV + 12 * s + k + 1];
+    }
+    x[NV + lane] = acc0 + acc1;
   }
 #pragma unroll
   {
