@@ -993,9 +993,10 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
       const int head = top ? i : NV + (i - ncm);
       __syncwarp();
       if (lane == i) {
+        /* only the rows a reflector of this kind can span are published */
         double2* c2 = reinterpret_cast<double2*>(colp);
 #pragma unroll
-        for (int k = 0; k < N; k += 2) c2[k >> 1] = make_double2(b[k], b[k + 1]);
+        for (int k = (top ? 0 : ncm); k < (top ? NV : N); k += 2) c2[k >> 1] = make_double2(b[k], b[k + 1]);
       }
       __syncwarp();
       double part = 0.0;
