@@ -1,5 +1,13 @@
-import os, sys
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+"""Print the per-chunk time line of tsidb_compute_host (TSIDB_HOST_TRACE=1): when the inputs of a chunk are on the device,
+when its kernels end and when its outputs are back on the host, for the default split and two equal splits.
+
+usage (GPU box): python tools/host_trace.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
 import __graft_entry__ as ge
 ge.build()
