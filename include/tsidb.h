@@ -261,7 +261,9 @@ int64_t tsidb_launch_count(const tsidb_handle* h);
  * start_time of ref:main.py:54,113).  With timing on, every tick records CUDA events between its
  * kernels on the launching stream; tsidb_last_tick_ms waits for the last tick and returns the
  * durations of {class sort, dynamics+assembly, equality elimination, null-space basis,
- * active set+decode} in milliseconds.                                                            */
+ * active set+decode} in milliseconds.  A timed tick runs stage by stage on the launching stream
+ * (the contact-class chains are not forked onto side streams), so the five durations add up to
+ * slightly more than an untimed tick takes.                                                      */
 int tsidb_set_timing(tsidb_handle* h, int on);
 int tsidb_last_tick_ms(tsidb_handle* h, float* ms5);
 
