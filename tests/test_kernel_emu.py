@@ -110,3 +110,21 @@ def test_emulated_kernel_with_active_torque_bounds():
         hit += any(blk == 2 for blk, _, _ in ra)
         assert (np.abs(out["tau"][i]) <= 0.6 + 1e-7).all()
     assert hit >= 5  # torque rows are really active in this batch
+
+
+@pytest.mark.parametrize("overrides", [(("v_max_scaling", 0.09),), (("tau_max_scaling", 0.08), ("v_max_scaling", 0.1))])
+def test_emulated_kernel_with_active_joint_velocity_bounds(overrides):
+    """Joint-velocity limits of 0.9 / 1.0 rad/s (the synthetic joint rates are U(-1, 1)): TaskJointBounds rows
+    (ref:ctrl/WalkController.py:178-184) end in the working set; the GPU tests' parity rules on the emulated kernels."""
+    from common import assert_parity, compare_outputs
+
+    s = setup("v1", overrides=overrides)
+    emu = Emu(s["cm"], s["cc"], s["refs"])
+    n = 48
+    q, v = synth.random_states(s["q0"], n, 33)
+    mask, refs = synth.walking_batch(s["refs"], n, 33, 0.3, 0.2, 0.2, 0.5, float(s["refs"]["com"][2]))
+    out = emu.tick(q, v, mask, refs)
+    out["active_set"] = out["active"]
+    res, ref = compare_outputs("v1", q, v, mask, refs, out, overrides=overrides)
+    assert_parity(res, "v1")
+    assert res["envs_with_active_force_lf_rf_torque_jointvel_rows"][3] >= 8

@@ -81,7 +81,9 @@ class BatchedController:
         contact); per-env solver status / iterations / active set are in ``self.last``."""
         if q.shape[0] != self.n_envs:
             raise ValueError(f"compute: controller was built for {self.n_envs} envs, got {q.shape[0]}")
-        out = self._tick(q, v)
+        # aux outputs on: CoM and sole placements of this tick are what the reference reads from formulation.data()
+        # after the solve (ref:main.py:135-142) and what update_tasks / set_contact_phase need at a contact switch
+        out = self._tick(q, v, aux=True)
         return out.tau, out.ddq, out.f
 
     def rollout(self, q: torch.Tensor, v: torch.Tensor, n_steps: int, phase0: Optional[torch.Tensor] = None,

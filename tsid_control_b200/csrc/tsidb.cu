@@ -1,6 +1,7 @@
 /* tsidb.cu — host side of libtsidb.so: the C ABI of include/tsidb.h over the sm_100a kernels
  * of tsidb_kernels.cuh.  No torch types, no CPU fallback: every entry point needs a CUDA device. */
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> /* header-only: ranges cost nothing unless a profiler is attached */
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -60,6 +61,9 @@ struct tsidb_handle {
   double* g_foot_now[2];   /* sole placements measured by the last tick of a rollout, [N][12] */
   double* g_defaults;      /* device copy of the default references: com 9, feet 2x24, contacts 2x12 */
   int gait_ready;
+  int gait_n;              /* envs initialised by the last tsidb_gait_reset */
+  /* small-batch ticks replayed from a captured CUDA graph (tsidb_compute, n_envs <= TSIDB_GRAPH_MAX_ENVS) */
+  struct TickGraph* tgraph;
 };
 
 /* ------------------------------------------------------------------ small kernels */
@@ -164,40 +168,11 @@ static int upload_const(tsidb_handle* h) {
   return 0;
 }
 
-extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, int max_envs, int device, tsidb_handle** out) {
-  if (!model || !conf || !out || max_envs <= 0) { g_err = "tsidb_create: bad argument"; return -1; }
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    g_err = "tsidb_create: no CUDA device (there is no CPU fallback for the TSID tick)";
-    return -3;
-  }
-  if (device < 0 || device >= ndev || device >= 8) { g_err = "tsidb_create: bad device index"; return -1; }
-  tsidb_handle* h = new tsidb_handle();
-  memset((void*)h, 0, sizeof *h);
-  std::string err;
-  if (!tsidb_fill_devconst(model, conf, &h->dc, &err)) { g_err = "tsidb_create: " + err; delete h; return -1; }
-  h->device = device;
-  h->max_envs = max_envs;
-  h->slot = -1;
-  {
-    std::lock_guard<std::mutex> lk(g_slot_mu);
-    for (int s = 0; s < TSIDB_MAX_SLOTS; s++)
-      if (!g_slot_used[device][s]) { g_slot_used[device][s] = true; h->slot = s; break; }
-  }
-  if (h->slot < 0) { g_err = "tsidb_create: all constant-memory slots of this device are in use"; delete h; return -1; }
-  CK(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
+/* everything of tsidb_create that can fail after the handle exists; on any failure the caller destroys the handle
+ * (tsidb_destroy tolerates members that were never created), which also returns the constant-memory slot */
+static int create_impl(tsidb_handle* h, const cudaDeviceProp& prop, int max_envs, int device) {
   h->sm_count = prop.multiProcessorCount;
   const size_t smem = ((size_t)TSIDB_WARPS_PER_BLOCK * SM_PER_ENV + MDL_SIZE) * sizeof(double);
-  if ((size_t)prop.sharedMemPerBlockOptin < smem) {
-    g_err = "tsidb_create: device offers less opt-in shared memory per block than the kernel needs";
-    return -2;
-  }
-  if (h->dc.nv != 26 && h->dc.nv != 24) {
-    g_err = "tsidb_create: this build instantiates the tick kernels for nv = 26 (robot/v1) and nv = 24 (robot/v0)";
-    return -1;
-  }
   /* Every CTA of the elimination, basis and active-set kernels is one warp; WARPS of them are to be resident per SM
    * (1 KB of shared memory is reserved per CTA on top of its own), so every kernel asks for the largest
    * shared-memory carve-out. */
@@ -265,6 +240,54 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
   }
   h->class_streams = 1;
   if (const char* e = getenv("TSIDB_CLASS_STREAMS")) h->class_streams = atoi(e) != 0; /* tuning knob */
+  return 0;
+}
+
+extern "C" void tsidb_destroy(tsidb_handle* h);
+
+extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, int max_envs, int device, tsidb_handle** out) {
+  if (!model || !conf || !out || max_envs <= 0) { g_err = "tsidb_create: bad argument"; return -1; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_err = "tsidb_create: no CUDA device (there is no CPU fallback for the TSID tick)";
+    return -3;
+  }
+  if (device < 0 || device >= ndev || device >= 8) { g_err = "tsidb_create: bad device index"; return -1; }
+  /* everything that can be checked without owning anything comes first */
+  DevConst dc;
+  std::string err;
+  if (!tsidb_fill_devconst(model, conf, &dc, &err)) { g_err = "tsidb_create: " + err; return -1; }
+  if (dc.nv != 26 && dc.nv != 24) {
+    g_err = "tsidb_create: this build instantiates the tick kernels for nv = 26 (robot/v1) and nv = 24 (robot/v0)";
+    return -1;
+  }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if ((size_t)prop.sharedMemPerBlockOptin < ((size_t)TSIDB_WARPS_PER_BLOCK * SM_PER_ENV + MDL_SIZE) * sizeof(double)) {
+    g_err = "tsidb_create: device offers less opt-in shared memory per block than the kernel needs";
+    return -2;
+  }
+  tsidb_handle* h = new tsidb_handle();
+  memset((void*)h, 0, sizeof *h);
+  h->dc = dc;
+  h->device = device;
+  h->max_envs = max_envs;
+  h->slot = -1;
+  {
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    for (int s = 0; s < TSIDB_MAX_SLOTS; s++)
+      if (!g_slot_used[device][s]) { g_slot_used[device][s] = true; h->slot = s; break; }
+  }
+  if (h->slot < 0) { g_err = "tsidb_create: all constant-memory slots of this device are in use"; delete h; return -1; }
+  const int rc = create_impl(h, prop, max_envs, device);
+  if (rc != 0) {
+    const std::string keep = g_err; /* tsidb_destroy must not hide the cause */
+    tsidb_destroy(h);               /* frees whatever was allocated so far and returns the slot */
+    cudaGetLastError();
+    g_err = keep;
+    return rc;
+  }
   *out = h;
   return 0;
 }
@@ -340,7 +363,10 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   const int n = a.n_envs;
   const bool timed = h->timing && !a.kin_only && chunk == 0 && base == 0;
   if (timed) CK(cudaEventRecord(h->ev[0], st));
+  struct NvtxRange { explicit NvtxRange(const char* n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } };
+  NvtxRange r_tick("tsidb:tick");
   if (!a.kin_only) {
+    NvtxRange r("tsidb:class_sort");
     CK(cudaMemsetAsync(counter, 0, 16 * sizeof(int32_t), st));
     if (a.mask) {
       /* class sort (double support, single support, flight) -> slot order */
@@ -353,6 +379,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   }
   if (timed) CK(cudaEventRecord(h->ev[1], st));
   {
+    NvtxRange r("tsidb:dynamics");
     const int warps = TSIDB_WARPS_PER_BLOCK;
     int blocks = (n + warps - 1) / warps;
     if (blocks > TSIDB_D_CTAS_PER_SM * h->sm_count) blocks = TSIDB_D_CTAS_PER_SM * h->sm_count; /* persistent */
@@ -398,6 +425,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
       else { if (nc == 2) TSIDB_AS_LAUNCH(24, 2, TSIDB_AS_WARPS_DS, s); else if (nc == 1) TSIDB_AS_LAUNCH(24, 1, TSIDB_AS_WARPS_SS, s); else TSIDB_AS_LAUNCH(24, 0, TSIDB_AS_WARPS_FL, s); }
     };
     const int ncls = a.perm ? 3 : 1;
+    NvtxRange r("tsidb:eliminate+basis+activeset");
     if (h->class_streams && !timed && ncls == 3) {
       CK(cudaEventRecord(h->ev_fork[chunk], st));
       for (int c = 0; c < 3; c++) {
@@ -651,6 +679,7 @@ extern "C" int tsidb_gait_reset(tsidb_handle* h, int n_envs, const tsidb_gait_co
   tsidb_gait_reset_kernel<<<(n_envs + th - 1) / th, th, 0, st>>>(n_envs, h->gconf, h->gait, h->g_defaults, phase0, vcmd);
   CK(cudaGetLastError());
   h->launches += 1;
+  h->gait_n = n_envs;
   return 0;
 }
 
@@ -706,6 +735,7 @@ extern "C" int tsidb_rollout(tsidb_handle* h, int n_envs, int n_steps, double* q
   if (!h || !q || !v || !tau || !ddq || !f || !status || !iters) { g_err = "tsidb_rollout: null argument"; return -1; }
   if (!h->gait_ready) { g_err = "tsidb_rollout: call tsidb_gait_reset first"; return -1; }
   if (n_envs <= 0 || n_envs > h->max_envs || n_steps < 0) { g_err = "tsidb_rollout: bad n_envs / n_steps"; return -1; }
+  if (n_envs > h->gait_n) { g_err = "tsidb_rollout: n_envs exceeds the envs initialised by the last tsidb_gait_reset"; return -1; }
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   if (!use_graph || n_steps < 2) {
@@ -745,14 +775,14 @@ extern "C" int tsidb_rollout(tsidb_handle* h, int n_envs, int n_steps, double* q
     return rc;
   }
   const int64_t per_step = h->launches - l0;
-  CK(cudaGraphInstantiate(&exec, graph, 0));
-  for (int k = 0; k < n_steps; k++) CK(cudaGraphLaunch(exec, cap));
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  for (int k = 0; k < n_steps && ce == cudaSuccess; k++) ce = cudaGraphLaunch(exec, cap);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(cap); /* exec must outlive its launches */
   h->launches = l0 + per_step * n_steps;
-  if (own) CK(cudaStreamSynchronize(cap));
-  else { /* exec must outlive its launches */ CK(cudaStreamSynchronize(cap)); }
-  cudaGraphExecDestroy(exec);
+  if (exec) cudaGraphExecDestroy(exec);
   cudaGraphDestroy(graph);
   if (own) cudaStreamDestroy(cap);
+  if (ce != cudaSuccess) { g_err = std::string("tsidb_rollout: graph replay failed: ") + cudaGetErrorString(ce); return -2; }
   return 0;
 }
 

@@ -81,8 +81,18 @@ class TsidEngine:
                 "com": torch.empty((n, 9), **f64), "foot_lf": torch.empty((n, 12), **f64),
                 "foot_rf": torch.empty((n, 12), **f64), "wrench": torch.empty((n, 12), **f64),
             }
-            self._out_cache = {n: o}  # keep one size resident
+            # a few sizes stay resident (a single-robot kinematics()/solve() call between two batched ticks must
+            # not evict the batch's buffers); the least recently created goes first
+            while len(self._out_cache) >= 4:
+                self._out_cache.pop(next(iter(self._out_cache)))
+            self._out_cache[n] = o
         return o
+
+    def _tick_output(self, o: dict, aux: bool, want_active: bool) -> TickOutput:
+        """Fields the call did not write are None (never a stale or uninitialised buffer)."""
+        keys = ["tau", "ddq", "f", "status", "iters"] + (["active_set"] if want_active else []) + \
+               (["com", "foot_lf", "foot_rf", "wrench"] if aux else [])
+        return TickOutput(**{k: o[k] for k in keys})
 
     # ------------------------------------------------------------------ API
     def set_default_refs(self, refs: Dict[str, np.ndarray]) -> None:
@@ -96,6 +106,10 @@ class TsidEngine:
 
     def compute(self, q: torch.Tensor, v: torch.Tensor, contact_mask: Optional[torch.Tensor] = None,
                 refs: Optional[Dict[str, torch.Tensor]] = None, aux: bool = False, want_active: bool = True) -> TickOutput:
+        """One batched tick.  The returned tensors are the engine's cached output buffers for this batch size: the
+        NEXT compute()/rollout()/kinematics() call with the same size overwrites them in place (clone what must
+        survive).  aux=False leaves com/foot_lf/foot_rf/wrench None, want_active=False leaves active_set None.
+        All calls on one engine must be ordered on one CUDA stream (the handle has one set of workspaces)."""
         n = q.shape[0]
         self._chk(q, n, self.nq, "q")
         self._chk(v, n, self.nv, "v")
@@ -117,7 +131,7 @@ class TsidEngine:
             C.byref(r), o["tau"].data_ptr(), o["ddq"].data_ptr(), o["f"].data_ptr(), o["status"].data_ptr(),
             o["iters"].data_ptr(), o["active_set"].data_ptr() if want_active else None,
             C.byref(a) if aux else None, self._stream()), "tsidb_compute")
-        return TickOutput(**{k: o[k] for k in TickOutput.__slots__})
+        return self._tick_output(o, aux, want_active)
 
     def host_buffers(self, n: int, pinned: bool = True) -> Dict[str, np.ndarray]:
         """Output buffers for :meth:`compute_host`.  Pinned buffers (the default) are DMA targets themselves;
@@ -243,7 +257,8 @@ class TsidEngine:
 
     def rollout(self, q: torch.Tensor, v: torch.Tensor, n_steps: int, use_graph: bool = True) -> TickOutput:
         """n_steps closed-loop ticks on the device (tick -> integrate_dv -> gait step), q and v advanced in place;
-        returns the last step's outputs.  Needs gait_reset first."""
+        returns the last step's outputs (tau, ddq, f, status, iters; the engine's cached buffers, overwritten by the
+        next call of the same batch size).  Needs gait_reset first."""
         n = q.shape[0]
         self._chk(q, n, self.nq, "q")
         self._chk(v, n, self.nv, "v")
@@ -251,7 +266,7 @@ class TsidEngine:
         check(self.lib.tsidb_rollout(self.h, n, int(n_steps), q.data_ptr(), v.data_ptr(), o["tau"].data_ptr(), o["ddq"].data_ptr(),
                                      o["f"].data_ptr(), o["status"].data_ptr(), o["iters"].data_ptr(), int(use_graph),
                                      self._stream()), "tsidb_rollout")
-        return TickOutput(**{k: o[k] for k in TickOutput.__slots__})
+        return self._tick_output(o, False, False)
 
     def diagnostics(self, out: TickOutput, contact_mask: Optional[torch.Tensor], omega: float) -> Dict[str, torch.Tensor]:
         """CoP [N,3], capture point [N,3] and support (lf.xy, rf.xy) [N,4] of a tick computed with aux=True
