@@ -154,6 +154,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="envs per GPU (the metric is quoted at 65536)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end and latency legs (the line then has no e2e)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -271,7 +272,7 @@ def main() -> None:
     # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the call) ----
     # inputs live in pinned host memory (the contract's "from pinned host memory"), results land in pinned
     # host memory; the library cuts the batch into chunks so the copies run under the kernels
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 10)) if not args.no_e2e else 1
     hq, hv, hmask = eng.pin(q), eng.pin(v), eng.pin(mask)
     hrefs = {k: eng.pin(a) for k, a in refs.items()}
     hout = eng.host_buffers(n, pinned=True)
@@ -299,7 +300,7 @@ def main() -> None:
 
     # ---- single-env tick latency (the reference's own operating point: one robot per call) ----
     lat = None
-    if rank == 0:
+    if rank == 0 and not args.no_e2e:
         q1, v1 = qd[:1].contiguous(), vd[:1].contiguous()
         ts = []
         m1 = ctrl.contact_mask[:1].contiguous()

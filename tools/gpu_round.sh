@@ -1,0 +1,24 @@
+#!/bin/bash
+# One GPU-box session: GPU tests, the bench line, the launch list and a full ncu capture of one tick.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh r5a [tests|notests] [ncu|noncu]'
+# Everything lands in gpurun_out/ (the only directory that travels back).
+TAG=${1:-rX}; TESTS=${2:-tests}; NCU=${3:-ncu}
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build_$TAG.log 2>&1 || { echo "build failed"; tail -20 gpurun_out/build_$TAG.log; exit 1; }
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi_$TAG.log 2>&1
+nproc >> gpurun_out/smi_$TAG.log
+if [ "$TESTS" = "tests" ]; then
+  timeout 1200 python -m pytest tests -q -m gpu -s > gpurun_out/pytest_$TAG.log 2>&1
+  echo "pytest rc=$?"; tail -15 gpurun_out/pytest_$TAG.log
+fi
+timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.log 2> gpurun_out/bench_$TAG.err
+echo "bench rc=$?"; tail -c 1500 gpurun_out/bench_$TAG.log
+if [ "$NCU" = "ncu" ]; then
+  timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/plain_$TAG.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tsidb_(activeset|eliminate|j2|dynamics)_kernel' \
+      --launch-skip 33 --launch-count 10 -f -o gpurun_out/prof_$TAG python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_$TAG.log 2>&1
+  echo "ncu rc=$?"; tail -3 gpurun_out/ncu_$TAG.log
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 20 --launch-count 60 --csv \
+      --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu2_$TAG.log 2>&1
+fi
+exit 0
