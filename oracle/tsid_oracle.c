@@ -290,6 +290,16 @@ typedef struct {
   real JF[2][6 * NVMAX]; /* LOCAL frame Jacobian, row-major 6 x nv */
 } dyn_t;
 
+/* ---- switches for the [UPSTREAM] details recalled with the least certainty.  Default 0 = the
+ * restatement's reading of tsid / pinocchio / eiquadprog.  tests/test_assumptions.py flips them one at a time to
+ * measure how much each assumption moves the answer.  Test infrastructure only. */
+int g_assume[ORACLE_A_COUNT];
+int oracle_set_assumption(int which, int alt) {
+  if (which < 0 || which >= ORACLE_A_COUNT) return -1;
+  g_assume[which] = alt;
+  return 0;
+}
+
 static void load_inertia(const tsidb_model* m, int i, sinertia* Y) {
   Y->m = m->mass[i];
   for (int k = 0; k < 3; k++) Y->c[k] = m->com[i][k];
@@ -523,7 +533,8 @@ static void ot_dynamics(const tsidb_model* m, const double* q, const double* v, 
     se3_actinv_motion(&pl, &d->a[b], &d->aF[s]);
     real wxv[3];
     cross3(d->vF[s].ang, d->vF[s].lin, wxv);
-    for (int k = 0; k < 3; k++) d->aF[s].lin[k] += wxv[k];
+    if (!g_assume[ORACLE_A_SPATIAL_FRAME_ACC]) /* A11.6: frameClassicAcceleration = spatial + w x v */
+      for (int k = 0; k < 3; k++) d->aF[s].lin[k] += wxv[k];
     memset(d->JF[s], 0, sizeof d->JF[s]);
     for (int j = b; j >= 0; j = m->parent[j]) {
       for (int k = 0; k < ndof(j); k++) {
@@ -546,6 +557,7 @@ typedef struct {
   real H[NMAX * NMAX], g[NMAX];
   real CE[NEQMAX * NMAX], ce0[NEQMAX];
   real CI[NINMAX * NMAX], ci0[NINMAX];
+  int ci_canon[NINMAX];  /* stacked CI row -> block-wise numbering (identity unless ORACLE_A_CI_INTERLEAVED) */
 } qp_t;
 
 static void se3_from_vec12(const double* r, se3* M) {
@@ -560,9 +572,15 @@ static void se3_task(const dyn_t* d, int foot, const double* kp, const double* k
                      const double* vref, const double* aref, real* b6) {
   se3 Mref, err;
   se3_from_vec12(ref12, &Mref);
-  se3_inv_mul(&d->oMf[foot], &Mref, &err); /* errorInSE3: log6(oMi^-1 * Mref) */
   sv pe;
-  log6_(&err, &pe);
+  if (!g_assume[ORACLE_A_LOG6_OLD_SIGN]) {
+    se3_inv_mul(&d->oMf[foot], &Mref, &err); /* errorInSE3: log6(oMi^-1 * Mref) */
+    log6_(&err, &pe);
+  } else { /* A11.7, the older tsid convention: a_des = -Kp log6(Mref^-1 oMi) + ... */
+    se3_inv_mul(&Mref, &d->oMf[foot], &err);
+    log6_(&err, &pe);
+    for (int k = 0; k < 3; k++) { pe.lin[k] = -pe.lin[k]; pe.ang[k] = -pe.ang[k]; }
+  }
   sv vr, ar, vrl, arl;
   memset(&vr, 0, sizeof vr);
   memset(&ar, 0, sizeof ar);
@@ -634,12 +652,18 @@ static void add_cost(qp_t* P, real w, const real* A, const real* b, int rows) {
 static void add_ineq(qp_t* P, const real* A, const real* lb, const real* ub, int rows) {
   const int n = P->n;
   for (int r = 0; r < rows; r++) {
+    /* A11.4: block-wise (all lower sides of the constraint, then all upper sides) or interleaved (lb_r, ub_r, ...);
+     * ci_canon maps a stacked row back to the block-wise numbering every comparison uses */
+    const int lo = g_assume[ORACLE_A_CI_INTERLEAVED] ? P->nin + 2 * r : P->nin + r;
+    const int hi = g_assume[ORACLE_A_CI_INTERLEAVED] ? P->nin + 2 * r + 1 : P->nin + rows + r;
     for (int j = 0; j < n; j++) {
-      P->CI[(P->nin + r) * n + j] = A[r * n + j];
-      P->CI[(P->nin + rows + r) * n + j] = -A[r * n + j];
+      P->CI[lo * n + j] = A[r * n + j];
+      P->CI[hi * n + j] = -A[r * n + j];
     }
-    P->ci0[P->nin + r] = -lb[r];
-    P->ci0[P->nin + rows + r] = ub[r];
+    P->ci0[lo] = -lb[r];
+    P->ci0[hi] = ub[r];
+    P->ci_canon[lo] = P->nin + r;
+    P->ci_canon[hi] = P->nin + rows + r;
   }
   P->nin += 2 * rows;
 }
@@ -734,11 +758,16 @@ static void ot_assemble(const tsidb_model* m, const tsidb_conf* c, const oracle_
       int foot = task == ORACLE_T_FORCEREG_LF ? 0 : 1;
       int s = P->slot_of_foot[foot];
       if (s < 0) continue;
-      for (int r = 0; r < 6; r++) {
-        for (int j = 0; j < 12; j++) A[r * n + nv + 12 * s + j] = (real)c->force_reg_weights[r] * T[r * 12 + j];
-        b[r] = 0; /* A * fRef, fRef = 0 */
+      if (!g_assume[ORACLE_A_FORCEREG_12x12]) {
+        for (int r = 0; r < 6; r++) {
+          for (int j = 0; j < 12; j++) A[r * n + nv + 12 * s + j] = (real)c->force_reg_weights[r] * T[r * 12 + j];
+          b[r] = 0; /* A * fRef, fRef = 0 */
+        }
+        add_cost(P, c->w_force_reg, A, b, 6);
+      } else { /* A11.1 alternative: the regularisation acts on the 12 corner-force components themselves */
+        for (int r = 0; r < 12; r++) { A[r * n + nv + 12 * s + r] = 1; b[r] = 0; }
+        add_cost(P, c->w_force_reg, A, b, 12);
       }
-      add_cost(P, c->w_force_reg, A, b, 6);
     } else if (task == ORACLE_T_FOOT_LF || task == ORACLE_T_FOOT_RF) {
       int foot = task == ORACLE_T_FOOT_LF ? 0 : 1;
       real b6[6];
@@ -1081,7 +1110,7 @@ int oracle_tick(const tsidb_model* m, const tsidb_conf* c, const oracle_problem*
   if (st == EQ_OPTIMAL || st == EQ_MAX_ITER) {
     for (int i = 0; i < n; i++) out->x[i] = (double)x[i];
     for (int i = 0; i < q; i++) out->lambda[i] = (double)u[i];
-    for (int i = P->neq; i < q; i++) out->active[out->n_active++] = A[i];
+    for (int i = P->neq; i < q; i++) out->active[out->n_active++] = P->ci_canon[A[i]];
     /* decodeSolution: dv = x[:nv], f = x[nv:], tau = h_a + M_a dv - J_a^T f */
     for (int i = 0; i < nv; i++) out->dv[i] = (double)x[i];
     for (int s = 0; s < nc; s++)

@@ -61,6 +61,18 @@ int oracle_tick_batch(const tsidb_model* m, const tsidb_conf* c, const oracle_pr
 int oracle_integrate(const tsidb_model* m, double* q, double* v, const double* dv, double dt);
 int oracle_real_bytes(void);
 
+/* the upstream details this restatement is least sure of, switchable one at a time (default 0 = the
+ * restatement's reading) so that tests/test_assumptions.py can measure how much each one moves the answer.  The
+ * joint-bounds time step (dt vs 2 dt) and the Hessian regulariser are plain tsidb_conf fields and need no switch. */
+enum {
+  ORACLE_A_FORCEREG_12x12 = 0,   /* A11.1: force regularisation on the 12 corner-force components, not on diag(w) T f (6x12) */
+  ORACLE_A_CI_INTERLEAVED = 1,   /* A11.4: two-sided rows stacked (lb_i, ub_i) pairwise instead of block-wise */
+  ORACLE_A_SPATIAL_FRAME_ACC = 2,/* A11.6: frame drift = spatial acceleration, without the w x v of frameClassicAcceleration */
+  ORACLE_A_LOG6_OLD_SIGN = 3,    /* A11.7: a_des = -Kp log6(Mref^-1 M) (older tsid) instead of +Kp log6(M^-1 Mref) */
+  ORACLE_A_COUNT = 4
+};
+int oracle_set_assumption(int which, int alt);
+
 #ifdef __cplusplus
 }
 #endif
