@@ -53,6 +53,7 @@ template <class T> inline T exchange(T x, int src) {
 
 template <class T> inline T __shfl_sync(unsigned, T x, int src) { return emu::exchange(x, src); }
 template <class T> inline T __shfl_xor_sync(unsigned, T x, int m) { return emu::exchange(x, emu::W.cur ^ m); }
+template <class T> inline T __shfl_down_sync(unsigned, T x, int d) { return emu::exchange(x, emu::W.cur + d > 31 ? emu::W.cur : emu::W.cur + d); }
 inline void __syncwarp() { emu::barrier(); }
 inline unsigned __reduce_min_sync(unsigned, unsigned v) {
   unsigned m = v;

@@ -32,20 +32,6 @@ static void lane_entry(int lane) {
       else if (nc == 1) eliminate_env<24, 1>(*g_job.C, g_lfinv, g_job.sm, *g_job.a, g_job.env, lane, parity);
       else eliminate_env<24, 0>(*g_job.C, g_lfinv, g_job.sm, *g_job.a, g_job.env, lane, parity);
     }
-  } else if (g_job.stage == 2) {
-    G2Pipe P;
-    P.bars = nullptr; P.next = nullptr; P.pv = P.pl = 0;
-    const int m = g_job.a->mask ? (((const uint8_t*)g_job.a->mask)[g_job.env] & 3) : 3;
-    const int nc = (m & 1) + ((m >> 1) & 1);
-    if (g_job.C->nv == 26) {
-      if (nc == 2) j2_env<26, 2>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
-      else if (nc == 1) j2_env<26, 1>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
-      else j2_env<26, 0>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
-    } else {
-      if (nc == 2) j2_env<24, 2>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
-      else if (nc == 1) j2_env<24, 1>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
-      else j2_env<24, 0>(*g_job.C, g_job.sm, *g_job.a, g_job.env, lane, P);
-    }
   } else {
     unsigned parity = 0;
     LaneConst K;
@@ -122,15 +108,13 @@ extern "C" int emu_tick(const TickArgs* a_in, double* sm_out) {
   const int smn = a_layout(TSIDB_NVX, 2).per_env > e_per_env(TSIDB_NVX, 2) ? a_layout(TSIDB_NVX, 2).per_env : e_per_env(TSIDB_NVX, 2);
   double* sm = (double*)calloc(smn, sizeof(double));
   double* ws = (double*)calloc((size_t)a.n_envs * SA_IMAGE, sizeof(double));
-  double* ws2 = (double*)calloc((size_t)a.n_envs * SG_IMAGE, sizeof(double));
   a.ws = ws;
-  a.ws2 = ws2;
   double* ws3 = (double*)calloc((size_t)a.n_envs * SE_IMAGE, sizeof(double));
   a.ws3 = ws3;
   a.perm = nullptr;
   int rc = 0;
   for (int env = 0; env < a.n_envs && rc == 0; env++) {
-    for (int stage = 0; stage < (a.kin_only ? 1 : 4) && rc == 0; stage++) {
+    for (int stage = 0; stage < (a.kin_only ? 1 : 3) && rc == 0; stage++) {
       for (int k = 0; k < smn; k++) sm[k] = NAN; /* poison: catches reads of unwritten smem */
       g_job = Job{&g_const[0], sm, &a, env, stage};
       rc = run_warp(env);
@@ -139,7 +123,6 @@ extern "C" int emu_tick(const TickArgs* a_in, double* sm_out) {
   if (sm_out) memcpy(sm_out, sm, smn * sizeof(double));
   free(sm);
   free(ws);
-  free(ws2);
   free(ws3);
   return rc;
 }

@@ -36,7 +36,6 @@ struct tsidb_handle {
   DevConst dc;
   int32_t* counter;      /* device, 16 per chunk: work counters of the active-set ([0],[4],[5]), elimination ([8..10]) and basis ([12..14]) kernels, [1..3] class sizes */
   double* ws;            /* device: solver images, SA_IMAGE doubles per slot */
-  double* ws2;           /* device: factor images, SG_IMAGE doubles per slot */
   double* ws3;           /* device: assembly images, SE_IMAGE doubles per slot */
   int32_t* perm;         /* device: slot -> env */
   int32_t* cls_pos;      /* device: per-env (class, position) */
@@ -202,17 +201,9 @@ static int create_impl(tsidb_handle* h, const cudaDeviceProp& prop, int max_envs
   TSIDB_E_ATTR(26, 2, TSIDB_E_WARPS); TSIDB_E_ATTR(26, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_ATTR(26, 0, TSIDB_E_WARPS_LIGHT);
   TSIDB_E_ATTR(24, 2, TSIDB_E_WARPS); TSIDB_E_ATTR(24, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_ATTR(24, 0, TSIDB_E_WARPS_LIGHT);
 #undef TSIDB_E_ATTR
-  const size_t smem_g = (size_t)TSIDB_G_CTA_WARPS * (SG_IMAGE + 2) * sizeof(double);
-  TSIDB_ATTR((tsidb_j2_kernel<26, 2>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel", cudaSharedmemCarveoutMaxShared);
-  TSIDB_ATTR((tsidb_j2_kernel<26, 1>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel", cudaSharedmemCarveoutMaxShared);
-  TSIDB_ATTR((tsidb_j2_kernel<26, 0>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel", cudaSharedmemCarveoutMaxShared);
-  TSIDB_ATTR((tsidb_j2_kernel<24, 2>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel", cudaSharedmemCarveoutMaxShared);
-  TSIDB_ATTR((tsidb_j2_kernel<24, 1>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel", cudaSharedmemCarveoutMaxShared);
-  TSIDB_ATTR((tsidb_j2_kernel<24, 0>), smem_g, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS, "basis kernel", cudaSharedmemCarveoutMaxShared);
 #undef TSIDB_ATTR
   CK(cudaMalloc(&h->counter, 16 * TSIDB_MAX_CHUNKS * sizeof(int32_t)));
   CK(cudaMalloc(&h->ws, (size_t)max_envs * SA_IMAGE * sizeof(double)));
-  CK(cudaMalloc(&h->ws2, (size_t)max_envs * SG_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->ws3, (size_t)max_envs * SE_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->perm, (size_t)max_envs * sizeof(int32_t)));
   CK(cudaMalloc(&h->cls_pos, (size_t)max_envs * sizeof(int32_t)));
@@ -295,7 +286,7 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
 extern "C" void tsidb_destroy(tsidb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaFree(h->counter); cudaFree(h->ws); cudaFree(h->ws2); cudaFree(h->ws3); cudaFree(h->perm); cudaFree(h->cls_pos);
+  cudaFree(h->counter); cudaFree(h->ws); cudaFree(h->ws3); cudaFree(h->perm); cudaFree(h->cls_pos);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFree(h->d_in); cudaFree(h->d_out);
   cudaFreeHost(h->h_mask); cudaFree(h->d_mask);
   cudaFreeHost(h->h_int); cudaFree(h->d_int);
@@ -357,7 +348,6 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   a.counter = counter;
   a.slot = h->slot;
   a.ws = h->ws + (size_t)base * SA_IMAGE;
-  a.ws2 = h->ws2 + (size_t)base * SG_IMAGE;
   a.ws3 = h->ws3 + (size_t)base * SE_IMAGE;
   a.perm = nullptr;
   const int n = a.n_envs;
@@ -405,20 +395,13 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
       return (int)(g < need ? g : need);
     };
     const int nv26 = h->dc.nv == 26;
-    const size_t smem_g = (size_t)TSIDB_G_CTA_WARPS * (SG_IMAGE + 2) * sizeof(double);
 #define TSIDB_E_LAUNCH(NV, NC, W, S) \
   tsidb_eliminate_kernel<NV, NC, W><<<grid(W, TSIDB_E_CTA_WARPS), 32 * TSIDB_E_CTA_WARPS, TSIDB_E_SMEM(NV, NC), S>>>(a)
-#define TSIDB_G_LAUNCH(NV, NC, S) \
-  tsidb_j2_kernel<NV, NC><<<grid(TSIDB_G_WARPS, TSIDB_G_CTA_WARPS), 32 * TSIDB_G_CTA_WARPS, smem_g, S>>>(a)
 #define TSIDB_AS_LAUNCH(NV, NC, W, S) \
   tsidb_activeset_kernel<NV, NC, W><<<grid(W, TSIDB_A_CTA_WARPS(NC)), 32 * TSIDB_A_CTA_WARPS(NC), TSIDB_AS_SMEM(NV, NC), S>>>(a)
     auto launch_e = [&](int nc, cudaStream_t s) {
       if (nv26) { if (nc == 2) TSIDB_E_LAUNCH(26, 2, TSIDB_E_WARPS, s); else if (nc == 1) TSIDB_E_LAUNCH(26, 1, TSIDB_E_WARPS_LIGHT, s); else TSIDB_E_LAUNCH(26, 0, TSIDB_E_WARPS_LIGHT, s); }
       else { if (nc == 2) TSIDB_E_LAUNCH(24, 2, TSIDB_E_WARPS, s); else if (nc == 1) TSIDB_E_LAUNCH(24, 1, TSIDB_E_WARPS_LIGHT, s); else TSIDB_E_LAUNCH(24, 0, TSIDB_E_WARPS_LIGHT, s); }
-    };
-    auto launch_g = [&](int nc, cudaStream_t s) {
-      if (nv26) { if (nc == 2) TSIDB_G_LAUNCH(26, 2, s); else if (nc == 1) TSIDB_G_LAUNCH(26, 1, s); else TSIDB_G_LAUNCH(26, 0, s); }
-      else { if (nc == 2) TSIDB_G_LAUNCH(24, 2, s); else if (nc == 1) TSIDB_G_LAUNCH(24, 1, s); else TSIDB_G_LAUNCH(24, 0, s); }
     };
     auto launch_a = [&](int nc, cudaStream_t s) {
       if (nv26) { if (nc == 2) TSIDB_AS_LAUNCH(26, 2, TSIDB_AS_WARPS_DS, s); else if (nc == 1) TSIDB_AS_LAUNCH(26, 1, TSIDB_AS_WARPS_SS, s); else TSIDB_AS_LAUNCH(26, 0, TSIDB_AS_WARPS_FL, s); }
@@ -432,7 +415,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
         const int nc = 2 - c;
         cudaStream_t s = c == 0 ? st : h->side[chunk][c - 1];
         if (c > 0) CK(cudaStreamWaitEvent(s, h->ev_fork[chunk], 0));
-        launch_e(nc, s); launch_g(nc, s); launch_a(nc, s);
+        launch_e(nc, s); launch_a(nc, s);
         CK(cudaGetLastError());
         if (c > 0) {
           CK(cudaEventRecord(h->ev_join[chunk][c - 1], s));
@@ -443,15 +426,12 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
       for (int c = 0; c < ncls; c++) launch_e(2 - c, st);
       CK(cudaGetLastError());
       if (timed) CK(cudaEventRecord(h->ev[3], st));
-      for (int c = 0; c < ncls; c++) launch_g(2 - c, st);
-      CK(cudaGetLastError());
-      if (timed) CK(cudaEventRecord(h->ev[4], st));
+      if (timed) CK(cudaEventRecord(h->ev[4], st)); /* the basis is built inside the elimination kernel: stage 4 is empty */
       for (int c = 0; c < ncls; c++) launch_a(2 - c, st);
       CK(cudaGetLastError());
     }
-    h->launches += 3 * ncls;
+    h->launches += 2 * ncls;
 #undef TSIDB_E_LAUNCH
-#undef TSIDB_G_LAUNCH
 #undef TSIDB_AS_LAUNCH
   } else if (timed) {
     CK(cudaEventRecord(h->ev[3], st));

@@ -15,7 +15,6 @@
 /* warps per CTA of the per-class kernels (the resident warps per SM above are split into CTAs of this width; a
  * narrow CTA returns its shared memory and registers as soon as its warps run out of work) */
 #define TSIDB_E_CTA_WARPS 1
-#define TSIDB_G_CTA_WARPS 1
 #define TSIDB_A_CTA_WARPS_DS 4
 #define TSIDB_A_CTA_WARPS_SS 4
 #define TSIDB_A_CTA_WARPS(NC) ((NC) == 2 ? TSIDB_A_CTA_WARPS_DS : TSIDB_A_CTA_WARPS_SS)
@@ -26,7 +25,6 @@
 #define TSIDB_LOCK_D 0
 #define TSIDB_LOCK_E 0
 #define TSIDB_MAX_SLOTS 6
-#define SG_LDV (TSIDB_NVX + 24)  /* row stride of the Householder reflectors (elimination kernel -> J2 kernel) */
 
 struct DevConst {
   int32_t nb, na, nv, nq;
@@ -119,7 +117,6 @@ struct TickArgs {
   double* o_wrench;
   int32_t* counter;   /* dynamic work counter of the active-set kernel */
   double* ws;         /* hand-off images of the active-set kernel, SA_IMAGE doubles per slot */
-  double* ws2;        /* factor images elimination -> J2 kernel, SG_IMAGE doubles per slot */
   double* ws3;        /* assembly images dynamics -> elimination kernel, SE_IMAGE doubles per slot */
   const int32_t* perm; /* slot -> env (class sort), null = identity */
   int32_t kin_only;   /* stop after the kinematics (tsidb_kinematics) */

@@ -15,17 +15,17 @@
  *     K2 assembly   task right-hand sides (SE3 log, PD laws), the dv block of the Hessian (the force blocks are
  *                   constant and pre-factored on the host), gradient.
  *                   [task.compute() + SolverHQuadProgFast H/g build, ref:main.py:119,121]
- *   kernels E, G, A  the QP: Goldfarb-Idnani dual active set with the pivot rules of eiquadprog-fast (most
+ *   kernels E, A  the QP: Goldfarb-Idnani dual active set with the pivot rules of eiquadprog-fast (most
  *                   violated row, lowest index on ties; min ratio drop)
  *                   [SolverHQuadProgFast::solve -> EiquadprogFast::solve_quadprog, ref:main.py:121]
  *     E  tsidb_eliminate_kernel   the 6+6nc equalities are always active, so they are eliminated once: Cholesky of
- *                   H, Householder QR of L^-1 CE^T (lane <-> column), x0 — instead of 18 Givens sweeps.
- *     G  tsidb_j2_kernel          the n x (n-nEq) null-space basis J2 = L^-T Q2 (na+6nc <= 32 columns), one thread
- *                   per column.
+ *                   H, Householder QR of L^-1 CE^T (lane <-> column), x0 — instead of 18 Givens sweeps; then the
+ *                   n x (n-nEq) null-space basis J2 = L^-T Q2 (na+6nc <= 32 columns), one thread per column,
+ *                   straight from the factor in shared memory.
  *     A  tsidb_activeset_kernel   the iterations on J2 (one lane per column / per row), then
  *        decode     dv, f, tau = h_a + M_a dv - J_a^T f.   [ref:main.py:126-127]
- *   E, G and A are instantiated and launched per contact class (nc = 2, 1, 0): every size is a compile-time
- *   constant; the host runs the three class chains E -> G -> A on forked streams (tsidb.cu, launch_tick).
+ *   E and A are instantiated and launched per contact class (nc = 2, 1, 0): every size is a compile-time
+ *   constant; the host runs the three class chains E -> A on forked streams (tsidb.cu, launch_tick).
  *
  * The file also compiles for the host under tests/emu (lock-step warp emulator that poisons shared memory with
  * NaN) so that the kernel logic can be exercised without a GPU; TSIDB_EMU selects that build.
@@ -880,7 +880,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
   constexpr int N = NV + 12 * NC;   /* n: the contact class fixes every size at compile time */
   constexpr int nc = NC, ncm = 6 * NC, neq = 6 + 6 * NC, n = N;
   typedef EL<NV, NC> LE;
-  constexpr int LDV = N;            /* reflector row stride in shared memory (SG_LDV in the factor image) */
+  constexpr int LDV = N;            /* reflector row stride in shared memory */
   double* L = sm + SE_oH;
   double* ild = sm + LE::oILD;
   double* tauq = sm + LE::oTAU;
@@ -1120,24 +1120,11 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
 }
 
 /* ================================================================= hand-off between the kernels */
-/* Kernel F (tsidb_prepare_kernel: K1 dynamics, K2 assembly, equality elimination) leaves two images per env in
- * global workspaces: the factor image (SG_*: Cholesky factor + Householder reflectors) for kernel G
- * (tsidb_j2_kernel: null-space basis J2 = L^-T Q2, one thread per column at 16 warps per SM), and the solver
- * image (SA_*) for kernel A (tsidb_activeset_kernel: active-set iterations + decode), which pulls images from a
- * work counter.  The solver image is kernel A's shared-memory layout, so its load is one linear copy.
- * Cost: 13 KB + 20 KB written and read per tick, a few % of the tick time at the measured HBM rate; what it
- * buys is that every stage runs at the occupancy and the thread mapping that suits it: F in CTA-wide phase
- * lock-step, G register-blocked with no cross-lane traffic, A balancing the data-dependent iteration counts
- * (1..40) dynamically.                                                                                     */
-#define SG_LDL 28                         /* row stride of L in the factor image (even: 16-byte reads)    */
-#define SG_oL 0                           /* L      26 x 28                             728 */
-#define SG_oILD (SG_oL + 728)             /* 1/L_ii                                      26 */
-#define SG_oTAU (SG_oILD + 26)            /* Householder tau                             18 */
-#define SG_oVT (SG_oTAU + 18)             /* reflectors [18][50]                        900 */
-#define SG_oERR (SG_oVT + 900)            /* status of the elimination (arrives with the reflector part)  2 */
-#define SG_IMAGE (SG_oERR + 2)            /* doubles handed over per env               1674 */
-#define SG_LPART SG_oTAU                  /* [0, SG_LPART): factor part, [SG_LPART, SG_IMAGE): reflector part */
-#define TSIDB_G_WARPS 8
+/* The dynamics kernel leaves the assembly image (SE_*) for the elimination kernel, and both of them fill the
+ * solver image (SA_*) that the active-set kernel pulls from a work counter with one linear bulk copy (the image is
+ * that kernel's shared-memory layout).  What the hand-off buys is that every stage runs at the occupancy and the
+ * thread mapping that suit it, and that the active set balances its data-dependent iteration counts (1..40)
+ * dynamically. */
 #define SA_LDJA 20                        /* JFa row stride                                  */
 #define SA_LDM 26                         /* M_a row stride: even with SA_LDM/2 odd, 16-byte lane-strided reads are conflict-free */
 /* Solver image / active-set shared-memory layout of one env, per contact class (nc = 2, 1, 0).  The first
@@ -1148,7 +1135,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
 struct ALayout {
   int n, m, ldj;
   int oSc, oJ2, oMa, oJFa, oNle, oVj, oX, image;
-  int oWr, oR, oIRD, oNP, oD, oRR, oVV, oU, oUO, oXO, oA, oBar, per_env;
+  int oWr, oR, oNP, oD, oBar, per_env;
 };
 TSIDB_HD constexpr int even_up(int x) { return (x + 1) & ~1; }
 TSIDB_HD constexpr ALayout a_layout(int nv, int nc) {
@@ -1168,24 +1155,17 @@ TSIDB_HD constexpr ALayout a_layout(int nv, int nc) {
   L.image = L.oVj + even_up(na);
   L.oWr = L.oVj;                          /* wrenches 12                               */
   L.oR = L.oWr + 12;                      /* R packed by columns: col j at j(j+1)/2    */
-  L.oIRD = L.oR + even_up(L.m * (L.m + 1) / 2);  /* 1/R_jj                             */
-  L.oNP = L.oIRD + L.m;                   /* dense constraint normal (n >= m + 2)      */
-  L.oVV = L.oNP;                          /* Householder vector, zero padded to m + 2: built after the last use of
-                                           * the dense normal of the same pick, so it shares its place */
-  L.oD = L.oNP + even_up(L.n);            /* d (free columns), zero padded to m + 2    */
-  L.oRR = L.oD + L.m + 2;                 /* r                                         */
-  L.oU = L.oRR + L.m;                 /* u                                         */
-  L.oUO = L.oU + L.m + 2;                 /* u_old                                     */
-  L.oXO = L.oUO + L.m + 2;                /* x_old                                     */
-  L.oA = L.oXO + even_up(L.n);            /* A, A_old as int32: 2 x (m + 2) ints       */
-  L.oBar = L.oA + L.m + 2;                /* mbarrier of the image load                */
+  L.oNP = L.oR + even_up(L.m * (L.m + 1) / 2);  /* dense constraint normal (actuation rows) */
+  L.oD = L.oNP + even_up(L.n);            /* d (free columns), zero padded to m + 2; doubles as the Householder vector */
+  L.oBar = L.oD + L.m + 2;                /* mbarrier of the image load                */
   L.per_env = L.oBar + 2;
+  if (L.per_env < L.image + 2) L.per_env = L.image + 2;
   return L;
 }
 /* the same numbers as enumerators (pure compile-time constants in device code) */
 template <int NV, int NC>
 struct AL {
-  enum : int { n = a_layout(NV, NC).n, m = a_layout(NV, NC).m, ldj = a_layout(NV, NC).ldj, oSc = a_layout(NV, NC).oSc, oJ2 = a_layout(NV, NC).oJ2, oMa = a_layout(NV, NC).oMa, oJFa = a_layout(NV, NC).oJFa, oNle = a_layout(NV, NC).oNle, oVj = a_layout(NV, NC).oVj, oX = a_layout(NV, NC).oX, image = a_layout(NV, NC).image, oWr = a_layout(NV, NC).oWr, oR = a_layout(NV, NC).oR, oIRD = a_layout(NV, NC).oIRD, oNP = a_layout(NV, NC).oNP, oD = a_layout(NV, NC).oD, oRR = a_layout(NV, NC).oRR, oVV = a_layout(NV, NC).oVV, oU = a_layout(NV, NC).oU, oUO = a_layout(NV, NC).oUO, oXO = a_layout(NV, NC).oXO, oA = a_layout(NV, NC).oA, oBar = a_layout(NV, NC).oBar, per_env = a_layout(NV, NC).per_env };
+  enum : int { n = a_layout(NV, NC).n, m = a_layout(NV, NC).m, ldj = a_layout(NV, NC).ldj, oSc = a_layout(NV, NC).oSc, oJ2 = a_layout(NV, NC).oJ2, oMa = a_layout(NV, NC).oMa, oJFa = a_layout(NV, NC).oJFa, oNle = a_layout(NV, NC).oNle, oVj = a_layout(NV, NC).oVj, oX = a_layout(NV, NC).oX, image = a_layout(NV, NC).image, oWr = a_layout(NV, NC).oWr, oR = a_layout(NV, NC).oR, oNP = a_layout(NV, NC).oNP, oD = a_layout(NV, NC).oD, oBar = a_layout(NV, NC).oBar, per_env = a_layout(NV, NC).per_env };
 };
 #define SA_IMAGE (a_layout(TSIDB_NVX, 2).image)   /* slot stride of the solver images in HBM (largest class) */
 #define SA_oSc 0
@@ -1241,22 +1221,6 @@ TSIDB_DEV unsigned long long sortable(double v) {
   memcpy(&b, &v, 8);
   return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
-/* lane holding the smallest `val` among the lanes with `valid`, ties to the smallest `tiebreak` (unique per
- * lane); -1 if no lane is valid.  Three REDUX instead of a 5-level shuffle tree on (double, int, int). */
-TSIDB_DEV int warp_argmin(double val, bool valid, int tiebreak) {
-  const unsigned long long key = sortable(val);
-  const unsigned hi = valid ? (unsigned)(key >> 32) : 0xffffffffu;
-  const unsigned mhi = __reduce_min_sync(FULL, hi);
-  const bool v1 = valid && hi == mhi;
-  const unsigned lo = v1 ? (unsigned)key : 0xffffffffu;
-  const unsigned mlo = __reduce_min_sync(FULL, lo);
-  const bool v2 = v1 && lo == mlo;
-  const unsigned tb = v2 ? (unsigned)tiebreak : 0xffffffffu;
-  const unsigned mtb = __reduce_min_sync(FULL, tb);
-  const unsigned win = __ballot_sync(FULL, v2 && tb == mtb);
-  return win ? (__ffs(win) - 1) : -1;
-}
-
 /* per-lane constants of one env, kept in registers across the iterations */
 struct LaneConst {
   double lb, ub;     /* joint-bound row `lane`: lb <= dv_j <= ub */
@@ -1278,9 +1242,7 @@ struct ASCtx {
   const double* vj;
   double* x;
   double* wr;
-  double *Rp, *ird, *np, *dd, *rr, *vv, *u, *uo, *xo;
-  int* A;             /* working set, then its saved copy at A + m + 2 */
-  int aoff;           /* m + 2 */
+  double *Rp, *np, *dd;
 };
 
 /* x index of foot f's first force variable */
@@ -1488,109 +1450,64 @@ TSIDB_DEV void wrench_of(int nv, const LaneConst& K, const double* x, int mask, 
   }
 }
 
-/* Remove the active constraint at position qq (0-based among the active inequalities): shift A, u and
- * the columns of R, restore R to upper-triangular with Givens rotations of rows (j, j+1) and apply the
- * same rotations to columns j, j+1 of J2.  [eiquadprog-fast delete_constraint] */
-/* every operand by value: the function is not inlined (two call sites), and a context struct passed by reference
- * would live in local memory */
-TSIDB_DEVNI int qp_delete(double* Rp, double* u, int* A, double* J2, double* ird, int ldj, int n, int iq, int qq, int lane) {
-  __syncwarp(); /* every lane has finished reading A/u/R of the current working set */
-  /* shift columns qq+1..iq-1 one to the left; a column keeps its length, so column c (length c+1 in
-   * packed storage) moves into slot c-1 (capacity c): element c sits on the sub-diagonal and is carried
-   * in `sub` until the rotation that annihilates it. */
-  double sub = 0.0; /* lane c holds sub-diagonal entry R[c+1][c] of the shifted matrix (c >= qq) */
-  for (int c = qq; c < iq - 1; c++) {
-    double v0 = (lane <= c + 1) ? Rp[(c + 1) * (c + 2) / 2 + lane] : 0.0;
-    __syncwarp();
-    if (lane <= c) Rp[c * (c + 1) / 2 + lane] = v0;
-    double sd = shfl(v0, c + 1);
-    if (lane == c) sub = sd;
-    if (lane == 0) { A[c] = A[c + 1]; u[c] = u[c + 1]; }
-    __syncwarp();
-  }
-  if (lane == 0) { A[iq - 1] = A[iq]; u[iq - 1] = u[iq]; A[iq] = 0; u[iq] = 0.0; }
-  iq--;
-  __syncwarp();
-  for (int j = qq; j < iq; j++) {
-    double cc = Rp[j * (j + 1) / 2 + j];
-    double ss = shfl(sub, j);
-    /* eiquadprog distance() */
-    double a1 = fabs(cc), b1 = fabs(ss), h;
-    if (a1 > b1) { double t = b1 / a1; h = a1 * sqrt(1.0 + t * t); }
-    else if (b1 > a1) { double t = a1 / b1; h = b1 * sqrt(1.0 + t * t); }
-    else h = a1 * sqrt(2.0);
-    if (h == 0.0) continue;
-    cc = cc / h; ss = ss / h;
-    double dj = h;
-    if (cc < 0.0) { dj = -h; cc = -cc; ss = -ss; }
-    const double xny = ss / (1.0 + cc);
-    __syncwarp();
-    if (lane == j) Rp[j * (j + 1) / 2 + j] = dj;
-    /* rows j, j+1 of columns k > j: lane k owns column k (k >= j+1: both rows are regular stored entries) */
-    if (lane > j && lane < iq) {
-      double t1 = Rp[lane * (lane + 1) / 2 + j];
-      double t2 = Rp[lane * (lane + 1) / 2 + j + 1];
-      double n1 = t1 * cc + t2 * ss;
-      double n2 = xny * (t1 + n1) - t2;
-      Rp[lane * (lane + 1) / 2 + j] = n1;
-      Rp[lane * (lane + 1) / 2 + j + 1] = n2;
-    }
-    /* columns j, j+1 of J2: lanes over rows */
-    for (int k = lane; k < n; k += 32) {
-      double t1 = J2[k * ldj + j], t2 = J2[k * ldj + j + 1];
-      double n1 = t1 * cc + t2 * ss;
-      J2[k * ldj + j] = n1;
-      J2[k * ldj + j + 1] = xny * (n1 + t1) - t2;
-    }
-    __syncwarp();
-  }
-  if (lane < iq) ird[lane] = 1.0 / Rp[lane * (lane + 1) / 2 + lane];
-  __syncwarp();
-  return iq;
+/* ---- Active-set iterations on the reduced basis [eiquadprog-fast solve_quadprog, after the equality phase] ----
+ * The working set's state lives in registers (round 1 kept u, A, r, 1/R_jj, the saved copies and the Householder
+ * vector in shared memory: every scalar update was "lane 0 writes, __syncwarp, everybody reads"; -1.7 KB of shared
+ * memory per env and a third of the instructions per iteration).  Lane l owns position l of the working set — its
+ * multiplier u_l, constraint id A_l, r_l = (R^-1 d)_l and 1/R_ll live in lane l's registers, like the two rows of x
+ * the lane owns; the pending constraint's multiplier is a warp-uniform scalar (the reference's u[iq]); the saved copies
+ * for the degenerate-add restore are register moves.  The two one-sided rows of an actuation or joint-bound pair
+ * (lb <= . <= ub) cannot be violated together, so each pair is ONE candidate (the more negative side): four
+ * candidates per lane instead of six, with the rows' reference indices (tie-break keys) precomputed per lane.  The
+ * arg-min takes one REDUX on the high words and only falls back to the 64-bit + tie-break path when two lanes
+ * share the high word.  The Householder vector is d itself with its head replaced.  All pivot rules are unchanged
+ * (most violated row, lowest reference index on ties; min-ratio drop, lowest position on ties; degenerate add ->
+ * exclude and restore) [eiquadprog-fast solve_quadprog after the equality phase]. */
+TSIDB_DEV int warp_argmin_fast(double val, bool valid, int tiebreak) {
+  const unsigned long long key = sortable(val);
+  const unsigned hi = valid ? (unsigned)(key >> 32) : 0xffffffffu;
+  const unsigned mhi = __reduce_min_sync(FULL, hi);
+  const bool v1 = valid && hi == mhi;
+  const unsigned b1 = __ballot_sync(FULL, v1);
+  if (b1 == 0u) return -1;
+  if ((b1 & (b1 - 1u)) == 0u) return __ffs(b1) - 1; /* a single lane holds the smallest high word */
+  const unsigned lo = v1 ? (unsigned)key : 0xffffffffu;
+  const unsigned mlo = __reduce_min_sync(FULL, lo);
+  const bool v2 = v1 && lo == mlo;
+  const unsigned tb = v2 ? (unsigned)tiebreak : 0xffffffffu;
+  const unsigned mtb = __reduce_min_sync(FULL, tb);
+  const unsigned win = __ballot_sync(FULL, v2 && tb == mtb);
+  return win ? (__ffs(win) - 1) : -1;
 }
 
-/* this lane's most violated row among the rows it owns that are neither active nor excluded; ties to the lowest
- * reference row index */
-TSIDB_DEV void pick_local(const double (&sl)[6], unsigned actbits, unsigned exclbits, int na, int nv, int lane,
-                          double& best, int& bcid, int& bbit) {
-  best = 0.0;
-  bcid = -1;
-  bbit = 1 << 30;
-#pragma unroll
-  for (int k = 0; k < 6; k++) {
-    if (!((actbits >> k) & 1u) && !((exclbits >> k) & 1u) && sl[k] < 0.0) {
-      const int cid = cid_of(na, lane, k);
-      const int bit = cid_bit(na, nv, cid);
-      if (sl[k] < best || (sl[k] == best && bit < bbit)) { best = sl[k]; bcid = cid; bbit = bit; }
-    }
-  }
-}
-
-/* Active-set iterations on the reduced basis [eiquadprog-fast solve_quadprog, after the equality phase]. */
-TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, int lane, int mask, int nc, int n, int neq,
-                       double c1c2, double R_norm, int& iters_out, uint64_t* act_words) {
-  const int na = S.na, nv = S.nv;
-  const int m = n - neq; /* reduced dimension, <= 32 */
+template <int NV, int NC>
+TSIDB_DEV int as_solve2(const DevConst& C, const ASCtx& S, const LaneConst& K, int lane, int mask, double c1c2, double R_norm,
+                        int& iters_out, uint64_t* act_words) {
+  typedef AL<NV, NC> LA;
+  constexpr int nv = NV, na = NV - 6, n = LA::n, m = LA::m, ldj = LA::ldj;
   double* J2 = S.J2;
   double* x = S.x;
   double* wr = S.wr;
   double* Rp = S.Rp;
-  double* ird = S.ird;
   double* np = S.np;
-  double* dd = S.dd;   /* d with the entries of the active columns zeroed, zero padded to m + 2 */
-  double* rr = S.rr;
-  double* vv = S.vv;   /* Householder vector over the columns, zero below iq, zero padded to m + 2 */
-  double* u = S.u;
-  double* uo = S.uo;
-  double* xo = S.xo;
-  int* A = S.A;
-  int* Ao = A + S.aoff;
+  double* dd = S.dd;   /* d with the entries of the active columns zeroed, zero padded to m + 2; doubles as the Householder vector */
   iters_out = 0;
   act_words[0] = act_words[1] = act_words[2] = 0;
-  if (lane < 2) { dd[m + lane] = 0.0; vv[m + lane] = 0.0; }
+  if (lane < 2) dd[m + lane] = 0.0;
 
-  const int nin_ref = C.nin_ref_fixed + 34 * nc;
+  const int nin_ref = C.nin_ref_fixed + 34 * NC;
   const double psi_thresh = (double)nin_ref * TS_EPS * c1c2 * 100.0;
+  /* reference row indices (tie-break keys) of the rows this lane owns */
+  const int bit_f = 34 * (lane >> 4) + 17 + (lane & 15);
+  const int bit_n = 34 * ((lane & 3) >> 1) + ((lane & 1) ? 33 : 16);
+  const int bit_a = 68 + lane;                 /* lower side; upper side + na */
+  const int bit_j = 68 + 2 * na + 6 + lane;    /* lower side; upper side + nv */
+  const bool has0 = lane < n, has1 = lane + 32 < n;
+  /* state in registers: this lane's rows of x, position `lane` of the working set */
+  double xr0 = has0 ? x[lane] : 0.0, xr1 = has1 ? x[lane + 32] : 0.0;
+  double xo0 = xr0, xo1 = xr1;
+  double ur = 0.0, uo = 0.0, irl = 0.0;
+  int Ar = 0, Ao = 0;
   int iq = 0, iter = 0, status = ST_OPTIMAL;
   unsigned actbits = 0;  /* bit k: the row of slot k owned by this lane is in the working set */
   unsigned exclbits = 0;
@@ -1598,65 +1515,125 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
   for (;;) { /* l1 */
     iter++;
     if (iter >= C.max_iter) { status = ST_MAX_ITER; break; }
-    wrench_of(S.nv, K, x, mask, wr, lane);
+    wrench_of(nv, K, x, mask, wr, lane);
     __syncwarp();
-    double sl[6];
-    eval_rows(C, S, K, lane, mask, sl);
-    double part = 0.0;
+    /* s = CI x + ci0 for the rows this lane owns, one candidate per two-sided pair */
+    double c0 = TS_INF, c1 = TS_INF, c2 = TS_INF, c3 = TS_INF;
+    int side2 = 0, side3 = 0;
+    {
+      const int f = lane >> 4, c = (lane & 15) >> 2;
+      if ((mask >> f) & 1) {
+        const double* ff = x + fvar0(nv, mask, f) + 3 * c;
+        c0 = -(K.fric[0] * ff[0] + K.fric[1] * ff[1] + K.fric[2] * ff[2]);
+      }
+    }
+    if (lane < 4) {
+      const int f = lane >> 1, side = lane & 1;
+      if ((mask >> f) & 1) {
+        const double* ff = x + fvar0(nv, mask, f);
+        double t = 0.0;
 #pragma unroll
-    for (int k = 0; k < 6; k++) part += (sl[k] < 0.0) ? sl[k] : 0.0;
+        for (int c = 0; c < 4; c++) t += C.nrm[0] * ff[3 * c] + C.nrm[1] * ff[3 * c + 1] + C.nrm[2] * ff[3 * c + 2];
+        c1 = side ? (C.fmax - t) : (t - C.fmin);
+      }
+    }
+    if (lane < na) {
+      if (C.use_tb) {
+        const double2* Mr = reinterpret_cast<const double2*>(S.Ma + lane * SA_LDM);
+        const double2* x2 = reinterpret_cast<const double2*>(x);
+        double t0 = S.nle_a[lane], t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+        for (int j = 0; j + 1 < nv / 2; j += 2) {
+          const double2 m0 = Mr[j], m1 = Mr[j + 1], x0 = x2[j], x1 = x2[j + 1];
+          t0 += m0.x * x0.x; t1 += m0.y * x0.y; t2 += m1.x * x1.x; t3 += m1.y * x1.y;
+        }
+        if ((nv / 2) & 1) { const double2 m0 = Mr[nv / 2 - 1], x0 = x2[nv / 2 - 1]; t0 += m0.x * x0.x; t1 += m0.y * x0.y; }
+        double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+        const double* wb = wr + S.wro;
+#pragma unroll
+        for (int q = 0; q < 6 * NC; q += 3) {
+          u0 += S.JFa[q * SA_LDJA + lane] * wb[q];
+          u1 += S.JFa[(q + 1) * SA_LDJA + lane] * wb[q + 1];
+          u2 += S.JFa[(q + 2) * SA_LDJA + lane] * wb[q + 2];
+        }
+        const double t = ((t0 + t1) + (t2 + t3)) - ((u0 + u1) + u2);
+        const double slo = t - K.tmin, sup = K.tmax - t;
+        side2 = sup < slo;
+        c2 = side2 ? sup : slo;
+      }
+      if (C.use_jb) {
+        const double xv = x[6 + lane];
+        const double slo = xv - K.lb, sup = K.ub - xv;
+        side3 = sup < slo;
+        c3 = side3 ? sup : slo;
+      }
+    }
+    /* violation sum: the other side of a pair is positive and adds nothing */
+    double part = (c0 < 0.0) ? c0 : 0.0;
+    part += (c1 < 0.0) ? c1 : 0.0;
+    part += (c2 < 0.0) ? c2 : 0.0;
+    part += (c3 < 0.0) ? c3 : 0.0;
     exclbits = 0;
-    /* the violation sum (termination test) and the first pivot search are independent reductions: issue both
-     * before branching on the sum so that their latencies overlap */
     double best;
-    int bcid, bbit;
-    pick_local(sl, actbits, exclbits, na, nv, lane, best, bcid, bbit);
-    int src = warp_argmin(best, bcid >= 0, bbit);
-    double psi = warp_sum(part);
+    int bslot, bbit;
+    auto pick = [&]() {
+      best = 0.0; bslot = -1; bbit = 1 << 30;
+      const unsigned blocked = actbits | exclbits;
+      auto consider = [&](double val, int slot, int bit) {
+        if (val < 0.0 && !((blocked >> slot) & 1u) && (val < best || (val == best && bit < bbit))) { best = val; bslot = slot; bbit = bit; }
+      };
+      consider(c0, 0, bit_f);
+      consider(c1, 1, bit_n);
+      consider(c2, 2 + side2, bit_a + side2 * na);
+      consider(c3, 4 + side3, bit_j + side3 * nv);
+    };
+    pick();
+    int src = warp_argmin_fast(best, bslot >= 0, bbit);
+    const double psi = warp_sum(part);
     if (fabs(psi) <= psi_thresh) { status = ST_OPTIMAL; break; }
-    /* save x, u, A */
-    for (int k = lane; k < n; k += 32) xo[k] = x[k];
-    if (lane < iq) { uo[lane] = u[lane]; Ao[lane] = A[lane]; }
-    __syncwarp();
+    /* save x, u, A: register moves */
+    xo0 = xr0; xo1 = xr1; uo = ur; Ao = Ar;
     bool done = false, restart_l1 = false, first_pick = true;
     for (;;) { /* l2 */
-      /* most violated row, lowest reference index on ties */
       if (!first_pick) {
-        pick_local(sl, actbits, exclbits, na, nv, lane, best, bcid, bbit);
-        src = warp_argmin(best, bcid >= 0, bbit);
+        pick();
+        src = warp_argmin_fast(best, bslot >= 0, bbit);
       }
       first_pick = false;
       if (src < 0) { status = ST_OPTIMAL; done = true; break; }
-      const int ip = __shfl_sync(FULL, bcid, src);
+      const int ip_slot = __shfl_sync(FULL, bslot, src); /* the owner of the picked row is the lane that proposed it */
+      const int ip = cid_of(na, src, ip_slot);
       double s_ip = shfl(best, src);
-      int ip_lane, ip_slot;
-      cid_owner(na, ip, ip_lane, ip_slot);
-      const bool dense_row = (ip >= 36 && ip < 36 + 2 * na);
+      const bool dense_row = (ip_slot == 2 || ip_slot == 3);
 #ifdef TSIDB_EMU_TRACE
       if (lane == 0) printf("[emu] iter %d pick bit %d s=%.17g iq=%d\n", iter, cid_bit(na, nv, ip), s_ip, iq);
 #endif
-      if (dense_row) actuation_normal(C, S, ip, mask, n, np, lane);
-      if (lane == 0) { u[iq] = 0.0; A[iq] = ip; }
-      __syncwarp();
+      if (dense_row) { actuation_normal(C, S, ip, mask, n, np, lane); __syncwarp(); }
+      double up = 0.0; /* multiplier of the pending constraint (the reference's u[iq]) */
       for (;;) { /* l2a */
         /* d = J2^T n_ip (lane <-> column) */
         double dl = 0.0;
         if (lane < m) dl = row_dot_col(C, S, ip, mask, n, lane, np);
         if (lane < m) dd[lane] = (lane >= iq) ? dl : 0.0;
         __syncwarp();
-        /* z = J2[:, iq:] d[iq:] (lanes over rows, 16-byte reads of the row and of d); zero if no free
-         * direction is left */
+        /* z = J2[:, iq:] d[iq:] (lanes over rows, 16-byte reads of the row and of d); zero if no free direction is left */
         double z0 = 0.0, z1 = 0.0;
-        const bool h0 = lane < n, h1 = lane + 32 < n; /* this lane's two rows (an absent row reads row 0) */
-        const double2* Jr0 = reinterpret_cast<const double2*>(J2 + (h0 ? lane : 0) * S.ldj);
-        const double2* Jr1 = reinterpret_cast<const double2*>(J2 + (h1 ? lane + 32 : 0) * S.ldj);
+        const double2* Jr0 = reinterpret_cast<const double2*>(J2 + (has0 ? lane : 0) * ldj);
+        const double2* Jr1 = reinterpret_cast<const double2*>(J2 + (has1 ? lane + 32 : 0) * ldj);
         if (iq < m) {
-          const int c0 = iq >> 1, c1 = (m + 1) >> 1;
+          const int cb = iq >> 1;
+          constexpr int ce = (m + 1) >> 1;
           const double2* d2 = reinterpret_cast<const double2*>(dd);
-          /* both rows in one loop, column pairs alternating between two accumulator sets: eight independent chains */
           double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, a2 = 0.0, a3 = 0.0, b2 = 0.0, b3 = 0.0;
-          int c = c0;
-          for (; c + 1 < c1; c += 2) {
+          int c = cb;
+          if ((ce - c) & 1) {
+            const double2 j0 = Jr0[c], j1 = Jr1[c], dv = d2[c];
+            a0 += j0.x * dv.x; a1 += j0.y * dv.y;
+            b0 += j1.x * dv.x; b1 += j1.y * dv.y;
+            c++;
+          }
+#pragma unroll 2
+          for (; c < ce; c += 2) {
             const double2 j0 = Jr0[c], j1 = Jr1[c], dv = d2[c];
             const double2 k0 = Jr0[c + 1], k1 = Jr1[c + 1], ev = d2[c + 1];
             a0 += j0.x * dv.x; a1 += j0.y * dv.y;
@@ -1664,137 +1641,116 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
             a2 += k0.x * ev.x; a3 += k0.y * ev.y;
             b2 += k1.x * ev.x; b3 += k1.y * ev.y;
           }
-          if (c < c1) {
-            const double2 j0 = Jr0[c], j1 = Jr1[c], dv = d2[c];
-            a0 += j0.x * dv.x; a1 += j0.y * dv.y;
-            b0 += j1.x * dv.x; b1 += j1.y * dv.y;
-          }
-          z0 = h0 ? (a0 + a1) + (a2 + a3) : 0.0;
-          z1 = h1 ? (b0 + b1) + (b2 + b3) : 0.0;
+          z0 = has0 ? (a0 + a1) + (a2 + a3) : 0.0;
+          z1 = has1 ? (b0 + b1) + (b2 + b3) : 0.0;
         }
-        /* r = R^-1 d[0:iq] (back substitution, lane <-> row) */
+        /* r = R^-1 d[0:iq] (back substitution, lane <-> row; row l scaled by 1/R_ll, so a step of the chain is one
+         * shuffle and one FMA; the column pointer walks down the packed storage) */
+        double rl;
         {
-          /* row l scaled by 1/R_ll up front, so that a step of the chain is one shuffle and one FMA; the scaled
-           * coefficient of the next step is formed while the current one waits for its shuffle */
-          const double irl = (lane < iq) ? ird[lane] : 0.0;
-          double accv = dl * irl;
-          double coef = (lane < iq - 1) ? Rp[(iq - 1) * iq / 2 + lane] * irl : 0.0;
+          double accv = dl * irl; /* irl is zero for the lanes >= iq */
+          const double* col = Rp + (iq - 1) * iq / 2 + lane;
           for (int i = iq - 1; i > 0; i--) {
             const double ri = shfl(accv, i);
-            const double cnext = (lane < i - 1) ? Rp[(i - 1) * i / 2 + lane] * irl : 0.0;
-            accv -= coef * ri; /* coef is zero for the lanes >= i */
-            coef = cnext;
+            if (lane < i) accv -= (col[0] * irl) * ri;
+            col -= i;
           }
-          if (lane < iq) rr[lane] = accv;
+          rl = accv;
         }
-        /* partial step t1 = min u_k / r_k over r_k > 0, first index on ties */
+        /* partial step t1 = min u_k / r_k over r_k > 0, first position on ties */
         double t1 = TS_INF;
-        bool t1_valid = false;
-        if (lane < iq) {
-          double rk = rr[lane];
-          if (rk > 0.0) { t1 = u[lane] / rk; t1_valid = true; }
-        }
-        const int lpos = (__ballot_sync(FULL, t1_valid) != 0u) ? warp_argmin(t1, t1_valid, lane) : -1;
+        const bool t1_valid = lane < iq && rl > 0.0;
+        if (t1_valid) t1 = ur / rl;
+        const int lpos = (__ballot_sync(FULL, t1_valid) != 0u) ? warp_argmin_fast(t1, t1_valid, lane) : -1;
         t1 = (lpos >= 0) ? shfl(t1, lpos) : TS_INF;
         /* full step t2 = -s_ip / z.n_ip, with z.n_ip = |d[iq:]|^2 (z = J2 d2, d2 = J2^T n) */
         const double zz = warp_sum(z0 * z0 + z1 * z1);
         const double d2sum = warp_sum((lane >= iq && lane < m) ? dl * dl : 0.0);
-        double t2 = (fabs(zz) > TS_EPS) ? (-s_ip / d2sum) : TS_INF;
-        double t = fmin(t1, t2);
+        const double t2 = (fabs(zz) > TS_EPS) ? (-s_ip / d2sum) : TS_INF;
+        const double t = fmin(t1, t2);
 #ifdef TSIDB_EMU_TRACE
         if (lane == 0) printf("[emu]   t1=%.17g (pos %d) t2=%.17g zz=%.6g znp=%.6g\n", t1, lpos, t2, zz, d2sum);
 #endif
         if (t >= TS_INF) { status = ST_INFEASIBLE; done = true; break; } /* eiquadprog UNBOUNDED -> HQP INFEASIBLE */
-        __syncwarp();
-        if (t2 >= TS_INF) {
-          /* dual step only: drop the blocking constraint */
-          if (lane < iq) u[lane] -= t * rr[lane];
-          if (lane == 0) u[iq] += t;
-          __syncwarp();
-          {
-            int ol, os;
-            cid_owner(na, A[lpos], ol, os);
-            if (lane == ol) actbits &= ~(1u << os);
-          }
-          iq = qp_delete(Rp, u, A, J2, ird, S.ldj, n, iq, lpos, lane);
-          continue;
+        /* step in dual space, and in primal space unless no direction is left */
+        if (lane < iq) ur -= t * rl;
+        up += t;
+        if (t2 < TS_INF) {
+          xr0 += t * z0;
+          xr1 += t * z1;
+          if (has0) x[lane] = xr0;
+          if (has1) x[lane + 32] = xr1;
         }
-        /* step in primal and dual space */
-        if (lane < n) x[lane] += t * z0;
-        if (lane + 32 < n) x[lane + 32] += t * z1;
-        if (lane < iq) u[lane] -= t * rr[lane];
-        if (lane == 0) u[iq] += t;
-        __syncwarp();
-        if (t == t2) {
+        if (t2 < TS_INF && t == t2) {
           /* full step: add ip.  Householder on the free columns iq..m-1 maps d[iq:] to beta e_iq; the
            * row sums needed for the update are z and column iq (already known). */
-          const double nrm = sqrt(d2sum);
-          const double d0 = shfl(dl, iq < 32 ? iq : 31);
-          bool degenerate;
-          if (iq >= m) degenerate = true; /* no free direction: |d(iq)| = 0 */
-          else {
+          bool degenerate = true; /* iq >= m: no free direction, |d(iq)| = 0 */
+          if (iq < m) {
+            const double nrm = sqrt(d2sum);
+            const double d0 = shfl(dl, iq);
             const double beta = (d0 >= 0.0) ? -nrm : nrm;
             degenerate = !(fabs(beta) > TS_EPS * R_norm);
             if (!degenerate) {
-              /* Householder H = I - tau v v^T with v = (1, d_c / (d0 - beta)), tau = (beta - d0) / beta.  With
-               * u = (d0 - beta, d_c) (unscaled) and rho = 1 / (beta (d0 - beta)):
-               *   J2[k][c] -= tau (sum_c' J2[k][c'] v_c') v_c  =  J2[k][c] + rho (z_k - beta J2[k][iq]) u_c
-               * (sum_c' J2[k][c'] d_c' = z_k): one reciprocal on the critical path instead of two divisions */
+              /* H = I - tau v v^T with the unscaled vector u = (d0 - beta, d_c) and rho = 1 / (beta (d0 - beta)):
+               *   J2[k][c] += rho (z_k - beta J2[k][iq]) u_c   (sum_c' J2[k][c'] d_c' = z_k)
+               * u is dd with its head replaced: one store, no second vector */
               const double rho = 1.0 / (beta * (d0 - beta));
-              if (lane < m) vv[lane] = (lane < iq) ? 0.0 : ((lane == iq) ? d0 - beta : dl);
-              if (lane < 2) vv[m + lane] = 0.0; /* the padding shares its place with the dense normal */
-              const double w0 = h0 ? -rho * (z0 - beta * J2[lane * S.ldj + iq]) : 0.0;
-              const double w1 = h1 ? -rho * (z1 - beta * J2[(lane + 32) * S.ldj + iq]) : 0.0;
+              if (lane == iq) dd[iq] = d0 - beta;
+              const double w0 = has0 ? -rho * (z0 - beta * J2[lane * ldj + iq]) : 0.0;
+              const double w1 = has1 ? -rho * (z1 - beta * J2[(lane + 32) * ldj + iq]) : 0.0;
               __syncwarp();
               {
-                const int c0 = iq >> 1, c1 = (m + 1) >> 1;
-                const double2* v2 = reinterpret_cast<const double2*>(vv);
+                const int cb = iq >> 1;
+                constexpr int ce = (m + 1) >> 1;
+                const double2* v2 = reinterpret_cast<const double2*>(dd);
                 double2* W0 = const_cast<double2*>(Jr0);
                 double2* W1 = const_cast<double2*>(Jr1);
-                /* two column pairs per trip, all loads ahead of the stores (the rows alias the store targets, so
-                 * the compiler cannot move them itself) */
-                int c = c0;
-                for (; c + 1 < c1; c += 2) {
+                int c = cb;
+                if ((ce - c) & 1) {
+                  const double2 vc = v2[c];
+                  double2 j0 = Jr0[c], j1 = Jr1[c];
+                  j0.x -= w0 * vc.x; j0.y -= w0 * vc.y;
+                  j1.x -= w1 * vc.x; j1.y -= w1 * vc.y;
+                  if (has0) W0[c] = j0;
+                  if (has1) W1[c] = j1;
+                  c++;
+                }
+#pragma unroll 2
+                for (; c < ce; c += 2) {
                   const double2 vc = v2[c], vd = v2[c + 1];
                   double2 j0 = Jr0[c], j1 = Jr1[c], k0 = Jr0[c + 1], k1 = Jr1[c + 1];
                   j0.x -= w0 * vc.x; j0.y -= w0 * vc.y;
                   j1.x -= w1 * vc.x; j1.y -= w1 * vc.y;
                   k0.x -= w0 * vd.x; k0.y -= w0 * vd.y;
                   k1.x -= w1 * vd.x; k1.y -= w1 * vd.y;
-                  if (h0) { W0[c] = j0; W0[c + 1] = k0; }
-                  if (h1) { W1[c] = j1; W1[c + 1] = k1; }
-                }
-                if (c < c1) {
-                  const double2 vc = v2[c];
-                  double2 j0 = Jr0[c], j1 = Jr1[c];
-                  j0.x -= w0 * vc.x; j0.y -= w0 * vc.y;
-                  j1.x -= w1 * vc.x; j1.y -= w1 * vc.y;
-                  if (h0) W0[c] = j0;
-                  if (h1) W1[c] = j1;
+                  if (has0) { W0[c] = j0; W0[c + 1] = k0; }
+                  if (has1) { W1[c] = j1; W1[c + 1] = k1; }
                 }
               }
-              /* new column of R: [d[0:iq]; beta] */
+              /* new column of R: [d[0:iq]; beta]; position iq of the working set */
               if (lane < iq) Rp[iq * (iq + 1) / 2 + lane] = dl;
-              if (lane == 0) { Rp[iq * (iq + 1) / 2 + iq] = beta; ird[iq] = rho * (d0 - beta); }
+              if (lane == iq) { Rp[iq * (iq + 1) / 2 + iq] = beta; irl = rho * (d0 - beta); ur = up; Ar = ip; }
               R_norm = fmax(R_norm, fabs(beta));
-              if (lane == ip_lane) actbits |= 1u << ip_slot;
+              if (lane == src) actbits |= 1u << ip_slot;
               iq++;
               __syncwarp();
             }
           }
 #ifdef TSIDB_EMU_TRACE
-          if (lane == 0) printf("[emu]   add -> %s nrm=%.6g Rnorm=%.6g\n", degenerate ? "DEGENERATE" : "ok", nrm, R_norm);
+          if (lane == 0) printf("[emu]   add -> %s Rnorm=%.6g\n", degenerate ? "DEGENERATE" : "ok", R_norm);
 #endif
           if (degenerate) {
             /* eiquadprog: exclude ip, restore the saved x, u, A for the first iq entries, retry l2 */
-            if (lane == ip_lane) exclbits |= 1u << ip_slot;
+            if (lane == src) exclbits |= 1u << ip_slot;
             actbits = 0;
-            if (lane < iq) { A[lane] = Ao[lane]; u[lane] = uo[lane]; }
-            for (int k = lane; k < n; k += 32) x[k] = xo[k];
+            if (lane < iq) { Ar = Ao; ur = uo; }
+            xr0 = xo0; xr1 = xo1;
+            if (has0) x[lane] = xr0;
+            if (has1) x[lane + 32] = xr1;
             __syncwarp();
             for (int i = 0; i < iq; i++) {
               int ol, os;
-              cid_owner(na, A[i], ol, os);
+              cid_owner(na, __shfl_sync(FULL, Ar, i), ol, os);
               if (lane == ol) actbits |= 1u << os;
             }
             break; /* back to l2 with the same s */
@@ -1802,16 +1758,84 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
           restart_l1 = true;
           break;
         }
-        /* partial step: drop the blocking constraint, recompute s(ip), try again */
+        /* dual-only step or partial step: drop the blocking constraint at position lpos
+         * [eiquadprog-fast delete_constraint]: shift A, u and the columns of R, restore R to upper triangular with
+         * Givens rotations of rows (j, j+1) and apply them to columns j, j+1 of J2 */
         {
           int ol, os;
-          cid_owner(na, A[lpos], ol, os);
+          cid_owner(na, __shfl_sync(FULL, Ar, lpos), ol, os);
           if (lane == ol) actbits &= ~(1u << os);
         }
-        iq = qp_delete(Rp, u, A, J2, ird, S.ldj, n, iq, lpos, lane);
-        wrench_of(S.nv, K, x, mask, wr, lane);
-        __syncwarp();
-        s_ip = eval_one(C, S, K, ip, mask);
+        {
+          const int qq = lpos;
+          __syncwarp(); /* every lane has finished reading R of the current working set */
+          /* a column keeps its length when it moves one slot to the left: column c + 1 (length c + 2) goes into slot c
+           * (capacity c + 1); its last element sits on the sub-diagonal and is carried in `sub` until the rotation
+           * that annihilates it */
+          double sub = 0.0;
+          for (int c = qq; c < iq - 1; c++) {
+            const double v0 = (lane <= c + 1) ? Rp[(c + 1) * (c + 2) / 2 + lane] : 0.0;
+            __syncwarp();
+            if (lane <= c) Rp[c * (c + 1) / 2 + lane] = v0;
+            const double sd = shfl(v0, c + 1);
+            if (lane == c) sub = sd;
+            __syncwarp();
+          }
+          {
+            const int An = __shfl_down_sync(FULL, Ar, 1);
+            const double un = __shfl_down_sync(FULL, ur, 1);
+            if (lane >= qq && lane < iq - 1) { Ar = An; ur = un; }
+            if (lane == iq - 1) { Ar = 0; ur = 0.0; }
+          }
+          iq--;
+          for (int j = qq; j < iq; j++) {
+            double cc = Rp[j * (j + 1) / 2 + j];
+            double ss = shfl(sub, j);
+            /* eiquadprog distance() */
+            const double a1 = fabs(cc), b1 = fabs(ss);
+            double h;
+            if (a1 > b1) { const double tq = b1 / a1; h = a1 * sqrt(1.0 + tq * tq); }
+            else if (b1 > a1) { const double tq = a1 / b1; h = b1 * sqrt(1.0 + tq * tq); }
+            else h = a1 * sqrt(2.0);
+            if (h == 0.0) continue;
+            cc = cc / h; ss = ss / h;
+            double dj = h;
+            if (cc < 0.0) { dj = -h; cc = -cc; ss = -ss; }
+            const double xny = ss / (1.0 + cc);
+            __syncwarp();
+            if (lane == j) Rp[j * (j + 1) / 2 + j] = dj;
+            /* rows j, j+1 of columns k > j: lane k owns column k (both rows are regular stored entries) */
+            if (lane > j && lane < iq) {
+              const double q1 = Rp[lane * (lane + 1) / 2 + j];
+              const double q2 = Rp[lane * (lane + 1) / 2 + j + 1];
+              const double n1 = q1 * cc + q2 * ss;
+              Rp[lane * (lane + 1) / 2 + j] = n1;
+              Rp[lane * (lane + 1) / 2 + j + 1] = xny * (q1 + n1) - q2;
+            }
+            /* columns j, j+1 of J2: lanes over rows */
+            if (has0) {
+              const double q1 = J2[lane * ldj + j], q2 = J2[lane * ldj + j + 1];
+              const double n1 = q1 * cc + q2 * ss;
+              J2[lane * ldj + j] = n1;
+              J2[lane * ldj + j + 1] = xny * (n1 + q1) - q2;
+            }
+            if (has1) {
+              const double q1 = J2[(lane + 32) * ldj + j], q2 = J2[(lane + 32) * ldj + j + 1];
+              const double n1 = q1 * cc + q2 * ss;
+              J2[(lane + 32) * ldj + j] = n1;
+              J2[(lane + 32) * ldj + j + 1] = xny * (n1 + q1) - q2;
+            }
+            __syncwarp();
+          }
+          irl = (lane < iq) ? 1.0 / Rp[lane * (lane + 1) / 2 + lane] : 0.0;
+          __syncwarp();
+        }
+        if (t2 < TS_INF) {
+          /* partial step: recompute s(ip) at the new x and try again */
+          wrench_of(nv, K, x, mask, wr, lane);
+          __syncwarp();
+          s_ip = eval_one(C, S, K, ip, mask);
+        }
       } /* l2a */
       if (done || restart_l1) break;
     } /* l2 */
@@ -1821,7 +1845,7 @@ TSIDB_DEV int as_solve(const DevConst& C, const ASCtx& S, const LaneConst& K, in
   if (status == ST_OPTIMAL || status == ST_MAX_ITER) {
     uint64_t w0 = 0, w1 = 0, w2 = 0;
     for (int i = 0; i < iq; i++) {
-      const int bit = cid_bit(na, nv, A[i]);
+      const int bit = cid_bit(na, nv, __shfl_sync(FULL, Ar, i));
       if (bit < 64) w0 |= 1ull << bit;
       else if (bit < 128) w1 |= 1ull << (bit - 64);
       else w2 |= 1ull << (bit - 128);
@@ -1930,6 +1954,9 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
 
 /* ================================================================= kernel E: equality elimination of one env */
 template <int NV, int NC>
+TSIDB_DEV void j2_from_factor(const DevConst& C, const double* L, const double* ild, const double* tauq, const double* Vt,
+                              double* img, int lane);
+template <int NV, int NC>
 TSIDB_DEV void eliminate_env(const DevConst& C, const double* lfinv_sm, double* sm, const TickArgs& a, int slot, int lane, unsigned& parity) {
   constexpr int nv = NV;
   typedef EL<NV, NC> LE;
@@ -1950,75 +1977,27 @@ TSIDB_DEV void eliminate_env(const DevConst& C, const double* lfinv_sm, double* 
   double* img = a.ws + (size_t)slot * SA_IMAGE;
   for (int k = lane; k < even_up(n); k += 32) img[LA::oX + k] = (k < n) ? sm[LE::oX + k] : 0.0;
   if (lane == 0) { img[SA_oSc] = c1c2; img[SA_oSc + 1] = R_norm; img[SA_oSc + 2] = (double)err; }
-  /* factor image (layout SG_*) for the J2 kernel */
-  double* fimg = a.ws2 + (size_t)slot * SG_IMAGE;
-  /* L row by row (lanes over the columns, zeros above the diagonal): no index arithmetic per element */
-  if (lane < SG_LDL) {
-    double* dst = fimg + SG_oL + lane;
-    const double* srcl = sm + SE_oH + (lane < SM_LDM ? lane : 0);
-#pragma unroll
-    for (int r = 0; r < nv; r++) dst[r * SG_LDL] = (lane <= r) ? srcl[r * SM_LDM] : 0.0;
-  }
-  if (lane < nv) fimg[SG_oILD + lane] = sm[LE::oILD + lane];
-  if (lane < LE::NEQ) fimg[SG_oTAU + lane] = sm[LE::oTAU + lane];
-  if (lane == 0) fimg[SG_oERR] = (double)err;
-  /* restride the reflector rows: N in shared memory, SG_LDV in the image */
-#pragma unroll
-  for (int i = 0; i < LE::NEQ; i++) {
-    if (lane < LE::N) fimg[SG_oVT + i * SG_LDV + lane] = sm[LE::oVT + i * LE::N + lane];
-    if (lane + 32 < LE::N) fimg[SG_oVT + i * SG_LDV + lane + 32] = sm[LE::oVT + i * LE::N + lane + 32];
-  }
+  /* the null-space basis goes straight from the factor in shared memory to the solver image */
+  __syncwarp();
+  if (err == ST_OPTIMAL) j2_from_factor<NV, NC>(C, sm + SE_oH, sm + LE::oILD, sm + LE::oTAU, sm + LE::oVT, img, lane);
   __syncwarp();
 }
 
-/* ================================================================= kernel G: the null-space basis of one env */
+/* ================================================================= null-space basis of one env (tail of kernel E) */
 /* J2[:, c] = L^-T Q [0; e_c], one lane per column c < m = n - neq, the column in registers, every index a
  * compile-time constant.  The reflectors are applied in reverse: the base-dynamics ones (rows i..n-1) first,
  * after which the force rows are final and leave through the constant Lf^-T; then the contact-motion ones
  * (rows i..nv-1) and the back substitution with L on the dv rows.  Operands shared by the warp (reflector and
- * factor entries) are broadcast reads from shared memory. */
-/* software pipeline of the J2 kernel: the factor image of the NEXT slot is requested (two bulk asynchronous
- * copies, one mbarrier each) as soon as the part of the buffer it lands in is dead for the current slot — the
- * reflector part before the back substitution starts, the factor part when the env is done. */
-struct G2Pipe {
-  double* bars;         /* [0]: reflector part, [1]: factor part */
-  const double* next;   /* factor image of the next slot, or null */
-  unsigned pv, pl;      /* phase parities */
-};
-TSIDB_DEV void g2_wait_v(G2Pipe& P) {
-#ifndef TSIDB_EMU
-  mbar_wait(P.bars, P.pv);
-#endif
-  P.pv ^= 1u;
-}
-TSIDB_DEV void g2_wait_l(G2Pipe& P) {
-#ifndef TSIDB_EMU
-  mbar_wait(P.bars + 1, P.pl);
-#endif
-  P.pl ^= 1u;
-}
-/* called by all lanes after a __syncwarp that retires every read of that part */
-TSIDB_DEV void g2_request_v(const G2Pipe& P, double* sg, int lane) {
-#ifndef TSIDB_EMU
-  if (lane == 0 && P.next) bulk_load(sg + SG_LPART, P.next + SG_LPART, (SG_IMAGE - SG_LPART) * sizeof(double), P.bars);
-#endif
-}
-TSIDB_DEV void g2_request_l(const G2Pipe& P, double* sg, int lane) {
-#ifndef TSIDB_EMU
-  if (lane == 0 && P.next) bulk_load(sg, P.next, SG_LPART * sizeof(double), P.bars + 1);
-#endif
-}
-
+ * factor entries) are broadcast reads of the elimination's own shared memory: the factor never travels through
+ * HBM (round 1 ran this as a kernel of its own behind a 13 KB factor image per env; that image and its round
+ * trip — 1.8 GB per 65536-env tick, 94 % of the HBM rate inside the single-support launch — are gone). */
 template <int NV, int NC>
-TSIDB_DEV void j2_columns(const DevConst& C, double* sg, double* img, int lane, G2Pipe& P) {
-  constexpr int NS = SG_LDV;
+TSIDB_DEV void j2_from_factor(const DevConst& C, const double* L, const double* ild, const double* tauq, const double* Vt,
+                              double* img, int lane) {
   constexpr int N = NV + 12 * NC, NEQ = 6 + 6 * NC, NCM = 6 * NC, M = N - NEQ;
+  constexpr int NS = N; /* reflector row stride in the elimination's shared memory (EL::oVT) */
   typedef AL<NV, NC> LA;
-  const bool work = lane < M;
-  const double2* L2 = reinterpret_cast<const double2*>(sg + SG_oL);
-  const double* ild = sg + SG_oILD;
-  const double* tauq = sg + SG_oTAU;
-  const double* Vt = sg + SG_oVT;
+  if (lane >= M) return;
   /* column c starts as the unit vector of the c-th row that is not a reflector head: dv rows NCM..NV-1, then
    * the force rows NV+6.. (without contacts: rows 6..NV-1) */
   double q[N];
@@ -2027,99 +2006,65 @@ TSIDB_DEV void j2_columns(const DevConst& C, double* sg, double* img, int lane, 
     const int col = (NC == 0) ? k - 6 : ((k < NV) ? k - NCM : ((k >= NV + 6) ? (NV - NCM) + (k - NV - 6) : -1));
     q[k] = (col >= 0 && col == lane) ? 1.0 : 0.0;
   }
-  if (work) {
 #pragma unroll
-    for (int i = NEQ - 1; i >= 0; i--) {
-      const bool top = (i < NCM) || NC == 0;
-      const int head = top ? i : NV + (i - NCM);
-      const int lo = top ? i + 1 : NCM;            /* dv rows lo..NV-1 */
-      const int flo = top ? N : head + 1;          /* force rows flo..N-1 */
-      const double2* v2 = reinterpret_cast<const double2*>(Vt + i * NS);
-      /* the head row is still zero here (no reflector applied so far touches it); the reflectors are unscaled
-       * (H = I - kappa u u^T, u_head = alpha - beta); entries come in pairs (16-byte broadcast reads) */
-      double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+  for (int i = NEQ - 1; i >= 0; i--) {
+    const bool top = (i < NCM) || NC == 0;
+    const int head = top ? i : NV + (i - NCM);
+    const int lo = top ? i + 1 : NCM;            /* dv rows lo..NV-1 */
+    const int flo = top ? N : head + 1;          /* force rows flo..N-1 */
+    const double2* v2 = reinterpret_cast<const double2*>(Vt + i * NS);
+    /* the head row is still zero here (no reflector applied so far touches it); the reflectors are unscaled
+     * (H = I - kappa u u^T, u_head = alpha - beta); entries come in pairs (16-byte broadcast reads) */
+    double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
 #pragma unroll
-      for (int kk = (lo & ~1); kk < NV; kk += 2) {
-        const double2 p = v2[kk >> 1];
-        if (kk >= lo) { if (kk & 2) w2 += p.x * q[kk]; else w0 += p.x * q[kk]; }
-        if (kk & 2) w3 += p.y * q[kk + 1]; else w1 += p.y * q[kk + 1];
-      }
+    for (int kk = (lo & ~1); kk < NV; kk += 2) {
+      const double2 p = v2[kk >> 1];
+      if (kk >= lo) { if (kk & 2) w2 += p.x * q[kk]; else w0 += p.x * q[kk]; }
+      if (kk & 2) w3 += p.y * q[kk + 1]; else w1 += p.y * q[kk + 1];
+    }
 #pragma unroll
-      for (int kk = (flo & ~1); kk < N; kk += 2) {
-        const double2 p = v2[kk >> 1];
-        if (kk >= flo) { if (kk & 2) w2 += p.x * q[kk]; else w0 += p.x * q[kk]; }
-        if (kk & 2) w3 += p.y * q[kk + 1]; else w1 += p.y * q[kk + 1];
-      }
-      const double w = tauq[i] * ((w0 + w1) + (w2 + w3));
-      q[head] = -w * Vt[i * NS + head];
+    for (int kk = (flo & ~1); kk < N; kk += 2) {
+      const double2 p = v2[kk >> 1];
+      if (kk >= flo) { if (kk & 2) w2 += p.x * q[kk]; else w0 += p.x * q[kk]; }
+      if (kk & 2) w3 += p.y * q[kk + 1]; else w1 += p.y * q[kk + 1];
+    }
+    const double w = tauq[i] * ((w0 + w1) + (w2 + w3));
+    q[head] = -w * Vt[i * NS + head];
 #pragma unroll
-      for (int kk = (lo & ~1); kk < NV; kk += 2) {
-        const double2 p = v2[kk >> 1];
-        if (kk >= lo) q[kk] -= w * p.x;
-        q[kk + 1] -= w * p.y;
-      }
+    for (int kk = (lo & ~1); kk < NV; kk += 2) {
+      const double2 p = v2[kk >> 1];
+      if (kk >= lo) q[kk] -= w * p.x;
+      q[kk + 1] -= w * p.y;
+    }
 #pragma unroll
-      for (int kk = (flo & ~1); kk < N; kk += 2) {
-        const double2 p = v2[kk >> 1];
-        if (kk >= flo) q[kk] -= w * p.x;
-        q[kk + 1] -= w * p.y;
-      }
-      if (i == NCM) {
-        /* force rows are final: J2_f = Lf^-T q_f, stored right away */
+    for (int kk = (flo & ~1); kk < N; kk += 2) {
+      const double2 p = v2[kk >> 1];
+      if (kk >= flo) q[kk] -= w * p.x;
+      q[kk + 1] -= w * p.y;
+    }
+    if (i == NCM) {
+      /* force rows are final: J2_f = Lf^-T q_f, stored right away */
 #pragma unroll
-        for (int s = 0; s < NC; s++) {
+      for (int s = 0; s < NC; s++) {
 #pragma unroll
-          for (int r = 0; r < 12; r++) {
-            double acc = 0.0;
+        for (int r = 0; r < 12; r++) {
+          double acc = 0.0;
 #pragma unroll
-            for (int k = r; k < 12; k++) acc += C.Lfinv[k][r] * q[NV + 12 * s + k];
-            img[LA::oJ2 + (NV + 12 * s + r) * LA::ldj + lane] = acc;
-          }
+          for (int k = r; k < 12; k++) acc += C.Lfinv[k][r] * q[NV + 12 * s + k];
+          img[LA::oJ2 + (NV + 12 * s + r) * LA::ldj + lane] = acc;
         }
       }
     }
   }
-  __syncwarp();
-  g2_request_v(P, sg, lane);
-  g2_wait_l(P);
-  if (work) {
+  /* dv rows: q <- L^-T q (column-oriented back substitution; row k of L is a broadcast read) */
 #pragma unroll
-    for (int k = NV - 1; k >= 0; k--) {
-      q[k] *= ild[k];
+  for (int k = NV - 1; k >= 0; k--) {
+    q[k] *= ild[k];
 #pragma unroll
-      for (int ii = 0; ii < k; ii += 2) {
-        const double2 p = L2[(k * SG_LDL + ii) >> 1];
-        q[ii] -= p.x * q[k];
-        if (ii + 1 < k) q[ii + 1] -= p.y * q[k];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < NV; k++) img[LA::oJ2 + k * LA::ldj + lane] = q[k];
+    for (int ii = 0; ii < k; ii++) q[ii] -= L[k * SM_LDM + ii] * q[k];
   }
-  __syncwarp();
-  g2_request_l(P, sg, lane);
-}
-
-template <int NV, int NC>
-TSIDB_DEV void j2_env(const DevConst& C, double* sg, const TickArgs& a, int slot, int lane, G2Pipe& P) {
-  double* img = a.ws + (size_t)slot * SA_IMAGE;
-#ifdef TSIDB_EMU
-  for (int k = lane; k < SG_IMAGE; k += 32) sg[k] = a.ws2[(size_t)slot * SG_IMAGE + k];
-  __syncwarp();
-#endif
-  /* the status of the elimination travels in the reflector part of the factor image: no dependent global read */
-  g2_wait_v(P);
-  const int err = (int)sg[SG_oERR];
-  if (err != ST_OPTIMAL) {
-    /* the active-set kernel reports the status and never reads J2; keep the pipeline moving */
-    __syncwarp();
-    g2_request_v(P, sg, lane);
-    g2_wait_l(P);
-    __syncwarp();
-    g2_request_l(P, sg, lane);
-    return;
-  }
-  j2_columns<NV, NC>(C, sg, img, lane, P);
+#pragma unroll
+  for (int k = 0; k < NV; k++) img[LA::oJ2 + k * LA::ldj + lane] = q[k];
 }
 
 /* ================================================================= kernel A: active set + decode of one env */
@@ -2140,11 +2085,10 @@ TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const 
 #endif
   __syncwarp();
   ASCtx S;
-  S.na = na; S.nv = nv; S.ldj = LA::ldj; S.aoff = LA::m + 2; S.nfr = 6 * NC;
+  S.na = na; S.nv = nv; S.ldj = LA::ldj; S.nfr = 6 * NC;
   S.J2 = sm + LA::oJ2; S.Ma = sm + LA::oMa; S.JFa = sm + LA::oJFa; S.nle_a = sm + LA::oNle; S.vj = sm + LA::oVj;
   S.x = sm + LA::oX; S.wr = sm + LA::oWr;
-  S.Rp = sm + LA::oR; S.ird = sm + LA::oIRD; S.np = sm + LA::oNP; S.dd = sm + LA::oD; S.rr = sm + LA::oRR; S.vv = sm + LA::oVV;
-  S.u = sm + LA::oU; S.uo = sm + LA::oUO; S.xo = sm + LA::oXO; S.A = (int*)(sm + LA::oA);
+  S.Rp = sm + LA::oR; S.np = sm + LA::oNP; S.dd = sm + LA::oD;
   const double c1c2 = sm[SA_oSc], R_norm = sm[SA_oSc + 1];
   const int err = (int)sm[SA_oSc + 2], mask = (int)sm[SA_oSc + 3]; /* its contact count is NC (class-sorted slots) */
   constexpr int nc = NC, n = LA::n, neq = 6 + 6 * NC;
@@ -2160,7 +2104,7 @@ TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const 
   int iters = 0;
   uint64_t words[3] = {0, 0, 0};
   int status = err;
-  if (err == ST_OPTIMAL) status = as_solve(C, S, K, lane, mask, nc, n, neq, c1c2, R_norm, iters, words);
+  if (err == ST_OPTIMAL) status = as_solve2<NV, NC>(C, S, K, lane, mask, c1c2, R_norm, iters, words);
   const bool ok = (status == ST_OPTIMAL || status == ST_MAX_ITER);
   const double* x = S.x;
   double* wr = S.wr;
@@ -2299,42 +2243,6 @@ tsidb_eliminate_kernel(const TickArgs a) {
     kn = __shfl_sync(FULL, kn, 0);
     if (kn < count && lane == 0) bulk_prefetch_l2(a.ws3 + (size_t)(start + kn) * SE_IMAGE, SE_IMAGE * sizeof(double));
     eliminate_env<NV, NC>(C, lfinv_sm, sm, a, start + k, lane, parity);
-    k = kn;
-  }
-}
-
-/* one launch per contact class, like the elimination and the active set: the three class chains E -> G -> A are
- * independent of each other and run on streams of their own.  One-warp CTAs on a work counter, as above; the warp
- * draws its next slot before it works on the current one (the pipeline prefetches the next factor image). */
-template <int NV, int NC>
-__global__ void __launch_bounds__(32 * TSIDB_G_CTA_WARPS, TSIDB_G_WARPS / TSIDB_G_CTA_WARPS)
-tsidb_j2_kernel(const TickArgs a) {
-  static_assert(TSIDB_G_WARPS % TSIDB_G_CTA_WARPS == 0, "CTA width divides the resident warps");
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double* sg = smem + wid * (SG_IMAGE + 2);
-  const DevConst& C = g_const[a.slot];
-  int start, count;
-  class_range<NC>(a, start, count);
-  int* counter = a.counter + 12 + NC;
-  int k = 0;
-  if (lane == 0) k = atomicAdd(counter, 1);
-  k = __shfl_sync(FULL, k, 0);
-  if (k >= count) return;
-  G2Pipe P;
-  P.bars = sg + SG_IMAGE;
-  P.pv = P.pl = 0;
-  if (lane == 0) { mbar_init(P.bars, 1); mbar_init(P.bars + 1, 1); }
-  __syncwarp();
-  P.next = a.ws2 + (size_t)(start + k) * SG_IMAGE;
-  g2_request_v(P, sg, lane);
-  g2_request_l(P, sg, lane);
-  while (k < count) {
-    int kn = 0;
-    if (lane == 0) kn = atomicAdd(counter, 1);
-    kn = __shfl_sync(FULL, kn, 0);
-    P.next = (kn < count) ? a.ws2 + (size_t)(start + kn) * SG_IMAGE : nullptr;
-    j2_env<NV, NC>(C, sg, a, start + k, lane, P);
     k = kn;
   }
 }
