@@ -15,8 +15,8 @@ timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.log 2>
 echo "bench rc=$?"; tail -c 1500 gpurun_out/bench_$TAG.log
 if [ "$NCU" = "ncu" ]; then
   timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/plain_$TAG.log 2>&1 &&
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tsidb_(activeset|eliminate|j2|dynamics)_kernel' \
-      --launch-skip 33 --launch-count 10 -f -o gpurun_out/prof_$TAG python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_$TAG.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tsidb_(activeset|eliminate|dynamics)_kernel' \
+      --launch-skip 24 --launch-count 7 -f -o gpurun_out/prof_$TAG python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_$TAG.log 2>&1
   echo "ncu rc=$?"; tail -3 gpurun_out/ncu_$TAG.log
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 20 --launch-count 60 --csv \
       --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu2_$TAG.log 2>&1
