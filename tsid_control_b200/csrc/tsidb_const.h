@@ -73,7 +73,13 @@ struct DevConst {
 #define SM_oBv (SM_oNle + 26)           /* task vectors                            64 */
 #define SM_oFr (SM_oBv + 64)            /* frames and CoM                          64 */
 #define SM_oQV (SM_oFr + 64)            /* q (32) and v (32)                       64 */
-#define SM_PER_ENV (SM_oQV + 64)        /*                                       1438 */
+#define SM_oRef (SM_oQV + 64)           /* this env's references, staged by asynchronous copies at the start of the env:
+                                           com 9 (+1), foot LF 24, foot RF 24, contact LF 12, contact RF 12, posture 24   106 */
+#define RF_COM 0
+#define RF_FOOT 10   /* + 24 f */
+#define RF_CONTACT 58 /* + 12 f */
+#define RF_POST 82
+#define SM_PER_ENV (SM_oRef + 106)      /*                                       1544 */
 /* task vectors inside oBv */
 #define BV_MOT 0   /* 2 x 6 contact motion rhs, by foot */
 #define BV_FOOT 12 /* 2 x 6 foot task rhs               */

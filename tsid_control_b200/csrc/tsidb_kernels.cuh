@@ -635,26 +635,19 @@ TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, con
   const double* fr = sm + SM_oFr;
   const double* qs = sm + SM_oQV;
   const double* vs = sm + SM_oQV + 32;
-  /* lanes 0..3: the four SE3 laws (contact LF, contact RF, foot LF, foot RF) */
+  /* lanes 0..3: the four SE3 laws (contact LF, contact RF, foot LF, foot RF); the references were staged in shared
+   * memory by asynchronous copies issued before K1 (stage_refs) */
+  const double* rf = sm + SM_oRef;
   if (lane < 4) {
     const int f = lane & 1;
     const bool is_contact = lane < 2;
-    double ref[24];
+    double b6[6];
     if (is_contact) {
-      const double* src = a.r_contact[f];
-      const EnvRow row = env_row(src, a, env, 12);
-#pragma unroll
-      for (int k = 0; k < 12; k++) ref[k] = src ? env_at(row, k) : C.ref_contact[f][k];
-      double b6[6];
-      se3_rhs(fr, f, C.kp_contact, C.kd_contact, ref, nullptr, nullptr, b6);
+      se3_rhs(fr, f, C.kp_contact, C.kd_contact, rf + RF_CONTACT + 12 * f, nullptr, nullptr, b6);
 #pragma unroll
       for (int k = 0; k < 6; k++) bv[BV_MOT + 6 * f + k] = b6[k];
     } else {
-      const double* src = a.r_foot[f];
-      const EnvRow row = env_row(src, a, env, 24);
-#pragma unroll
-      for (int k = 0; k < 24; k++) ref[k] = src ? env_at(row, k) : C.ref_foot[f][k];
-      double b6[6];
+      const double* ref = rf + RF_FOOT + 24 * f;
       se3_rhs(fr, f, C.kp_foot, C.kd_foot, ref, ref + 12, ref + 18, b6);
 #pragma unroll
       for (int k = 0; k < 6; k++) bv[BV_FOOT + 6 * f + k] = b6[k];
@@ -662,10 +655,7 @@ TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, con
   } else if (lane < 7) {
     /* tsid::TaskComEquality */
     const int r = lane - 4;
-    const EnvRow row = env_row(a.r_com, a, env, 9);
-    double rp = a.r_com ? env_at(row, r) : C.ref_com[r];
-    double rv = a.r_com ? env_at(row, 3 + r) : C.ref_com[3 + r];
-    double ra = a.r_com ? env_at(row, 6 + r) : C.ref_com[6 + r];
+    const double rp = rf[RF_COM + r], rv = rf[RF_COM + 3 + r], ra = rf[RF_COM + 6 + r];
     double ades = -C.kp_com[r] * (fr[FR_COM + r] - rp) - C.kd_com[r] * (fr[FR_COM + 3 + r] - rv) + ra;
     bv[BV_COM + r] = ades - fr[FR_COM + 6 + r];
   } else if (lane < 10) {
@@ -675,7 +665,7 @@ TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, con
   }
   /* tsid::TaskJointPosture */
   if (lane < na) {
-    double rp = a.r_posture ? ldin(a.r_posture, a, env, lane, na) : mdl[MDL_oPOST + 46 + lane];
+    const double rp = rf[RF_POST + lane];
     bv[BV_POST + lane] = -mdl[MDL_oPOST + lane] * (qs[7 + lane] - rp) - mdl[MDL_oPOST + 23 + lane] * vs[6 + lane];
   }
   __syncwarp();
@@ -876,7 +866,7 @@ struct EL {
  * same null space, x0 and projector; this one keeps the first 6*nc reflectors inside the dv rows (a contact-motion
  * row has no force entries), which halves their cost here and in the J2 kernel. */
 template <int NV, int NC>
-TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm, int lane, int mask, double& c1c2, double& R_norm_out) {
+TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm, int lane, int mask, double& c1c2, double& c1_out, double& R_norm_out) {
   constexpr int N = NV + 12 * NC;   /* n: the contact class fixes every size at compile time */
   constexpr int nc = NC, ncm = 6 * NC, neq = 6 + 6 * NC, n = N;
   typedef EL<NV, NC> LE;
@@ -934,6 +924,7 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
     c2 = c2p + nc * C.Lfinv_trace;
   }
   c1c2 = c1 * c2;
+  c1_out = c1;
 
   PHASE_SYNC_E();
   /* ---- B = L^-1 [CE^T | g]: lane e keeps column e; Householder QR; the last column becomes Q^T w_unc ---- */
@@ -1256,14 +1247,16 @@ TSIDB_DEV int fvar0(int nv, int mask, int f) { return nv + ((f == 1 && (mask & 1
  * The never-active sides of the reference's two-sided blocks (friction lower side at -1e10, the six
  * base rows of the joint-bounds block at +-1e10) are not enumerated: they can neither be violated
  * nor change the violation sum.
- * Lane ownership: lane l evaluates "slot" 0: cid l (friction), 1: cid 32+l (l < 4), 2/3: actuation row l
- * lower/upper, 4/5: joint-bound row l lower/upper (l < na). */
+ * Lane ownership: lane l evaluates "slot" 0: cid l (friction), 1: cid 32+(l-12) (lanes 12..15: they form the normal
+ * force in the same pass in which lanes 0..11 form the wrenches), 2/3: actuation row l lower/upper, 4/5: joint-bound
+ * row l lower/upper (l < na). */
+#define NRM_LANE0 12
 TSIDB_DEV int cid_of(int na, int lane, int slot) {
-  return slot == 0 ? lane : (slot == 1 ? 32 + lane : 36 + (slot - 2) * na + lane);
+  return slot == 0 ? lane : (slot == 1 ? 32 + lane - NRM_LANE0 : 36 + (slot - 2) * na + lane);
 }
 TSIDB_DEV void cid_owner(int na, int cid, int& lane, int& slot) {
   if (cid < 32) { lane = cid; slot = 0; }
-  else if (cid < 36) { lane = cid - 32; slot = 1; }
+  else if (cid < 36) { lane = cid - 32 + NRM_LANE0; slot = 1; }
   else { const int k = cid - 36; slot = 2 + k / na; lane = k - (slot - 2) * na; }
 }
 /* bit index in the 192-bit active-set word = row numbering of tsidb_ci_row() */
@@ -1280,8 +1273,9 @@ TSIDB_DEV int cid_bit(int na, int nv, int cid) {
  * memory are served one address at a time) */
 TSIDB_DEV void lane_const_init(const DevConst& C, LaneConst& K, int lane) {
   const int na = C.na;
+  /* lanes 0..11: row lane % 6 of the force generator; lanes 12..15: the normal-force row [n n n n] */
 #pragma unroll
-  for (int j = 0; j < 12; j++) K.Trow[j] = C.T[lane % 6][j];
+  for (int j = 0; j < 12; j++) K.Trow[j] = (lane >= NRM_LANE0 && lane < NRM_LANE0 + 4) ? C.nrm[j % 3] : C.T[lane % 6][j];
 #pragma unroll
   for (int j = 0; j < 3; j++) K.fric[j] = C.fric[lane & 3][j];
   K.tmin = (lane < na) ? C.tau_min[lane] : 0.0;
@@ -1433,11 +1427,12 @@ TSIDB_DEV void actuation_normal(const DevConst& C, const ASCtx& S, int cid, int 
   }
 }
 
-/* wrench T f of both feet -> wr[12] (zero for a foot not in contact); lanes 0..11 */
-TSIDB_DEV void wrench_of(int nv, const LaneConst& K, const double* x, int mask, double* wr, int lane) {
-  if (lane < 12) {
-    const int f = lane / 6;
-    double s = 0.0;
+/* wrench T f of both feet -> wr[12] (zero for a foot not in contact), lanes 0..11; in the same pass lanes 12..15 form
+ * the total normal force of foot (lane - 12) / 2 (K.Trow holds [n n n n] there).  Returns the lane's own sum. */
+TSIDB_DEV double wrench_of(int nv, const LaneConst& K, const double* x, int mask, double* wr, int lane) {
+  double s = 0.0;
+  if (lane < NRM_LANE0 + 4) {
+    const int f = (lane < NRM_LANE0) ? lane / 6 : (lane - NRM_LANE0) >> 1;
     if ((mask >> f) & 1) {
       const double* ff = x + fvar0(nv, mask, f);
       /* three independent chains (the solver is bound by dependent fp64 latency, not by throughput) */
@@ -1446,8 +1441,9 @@ TSIDB_DEV void wrench_of(int nv, const LaneConst& K, const double* x, int mask, 
       for (int j = 0; j < 12; j += 3) { s0 += K.Trow[j] * ff[j]; s1 += K.Trow[j + 1] * ff[j + 1]; s2 += K.Trow[j + 2] * ff[j + 2]; }
       s = (s0 + s1) + s2;
     }
-    wr[lane] = s;
+    if (lane < NRM_LANE0) wr[lane] = s;
   }
+  return s;
 }
 
 /* ---- Active-set iterations on the reduced basis [eiquadprog-fast solve_quadprog, after the equality phase] ----
@@ -1481,8 +1477,8 @@ TSIDB_DEV int warp_argmin_fast(double val, bool valid, int tiebreak) {
 }
 
 template <int NV, int NC>
-TSIDB_DEV int as_solve2(const DevConst& C, const ASCtx& S, const LaneConst& K, int lane, int mask, double c1c2, double R_norm,
-                        int& iters_out, uint64_t* act_words) {
+TSIDB_DEV int as_solve2(const DevConst& C, const ASCtx& S, const LaneConst& K, int lane, int mask, double c1c2, double trH,
+                        double R_norm, int& iters_out, uint64_t* act_words) {
   typedef AL<NV, NC> LA;
   constexpr int nv = NV, na = NV - 6, n = LA::n, m = LA::m, ldj = LA::ldj;
   double* J2 = S.J2;
@@ -1499,7 +1495,7 @@ TSIDB_DEV int as_solve2(const DevConst& C, const ASCtx& S, const LaneConst& K, i
   const double psi_thresh = (double)nin_ref * TS_EPS * c1c2 * 100.0;
   /* reference row indices (tie-break keys) of the rows this lane owns */
   const int bit_f = 34 * (lane >> 4) + 17 + (lane & 15);
-  const int bit_n = 34 * ((lane & 3) >> 1) + ((lane & 1) ? 33 : 16);
+  const int bit_n = 34 * ((lane & 3) >> 1) + ((lane & 1) ? 33 : 16); /* lanes 12..15: (lane - 12) = lane & 3 */
   const int bit_a = 68 + lane;                 /* lower side; upper side + na */
   const int bit_j = 68 + 2 * na + 6 + lane;    /* lower side; upper side + nv */
   const bool has0 = lane < n, has1 = lane + 32 < n;
@@ -1515,7 +1511,7 @@ TSIDB_DEV int as_solve2(const DevConst& C, const ASCtx& S, const LaneConst& K, i
   for (;;) { /* l1 */
     iter++;
     if (iter >= C.max_iter) { status = ST_MAX_ITER; break; }
-    wrench_of(nv, K, x, mask, wr, lane);
+    const double nf = wrench_of(nv, K, x, mask, wr, lane);
     __syncwarp();
     /* s = CI x + ci0 for the rows this lane owns, one candidate per two-sided pair */
     double c0 = TS_INF, c1 = TS_INF, c2 = TS_INF, c3 = TS_INF;
@@ -1527,15 +1523,9 @@ TSIDB_DEV int as_solve2(const DevConst& C, const ASCtx& S, const LaneConst& K, i
         c0 = -(K.fric[0] * ff[0] + K.fric[1] * ff[1] + K.fric[2] * ff[2]);
       }
     }
-    if (lane < 4) {
-      const int f = lane >> 1, side = lane & 1;
-      if ((mask >> f) & 1) {
-        const double* ff = x + fvar0(nv, mask, f);
-        double t = 0.0;
-#pragma unroll
-        for (int c = 0; c < 4; c++) t += C.nrm[0] * ff[3 * c] + C.nrm[1] * ff[3 * c + 1] + C.nrm[2] * ff[3 * c + 2];
-        c1 = side ? (C.fmax - t) : (t - C.fmin);
-      }
+    if (lane >= NRM_LANE0 && lane < NRM_LANE0 + 4) {
+      const int f = (lane - NRM_LANE0) >> 1, side = lane & 1;
+      if ((mask >> f) & 1) c1 = side ? (C.fmax - nf) : (nf - C.fmin);
     }
     if (lane < na) {
       if (C.use_tb) {
@@ -1621,26 +1611,24 @@ TSIDB_DEV int as_solve2(const DevConst& C, const ASCtx& S, const LaneConst& K, i
         const double2* Jr0 = reinterpret_cast<const double2*>(J2 + (has0 ? lane : 0) * ldj);
         const double2* Jr1 = reinterpret_cast<const double2*>(J2 + (has1 ? lane + 32 : 0) * ldj);
         if (iq < m) {
+          /* column pairs in static segments of four (every offset an immediate, the loads of a segment issue ahead of
+           * its FMAs); a segment that lies entirely below iq is skipped, the pairs of the first live segment that lie
+           * below iq multiply by the zeros of dd */
           const int cb = iq >> 1;
           constexpr int ce = (m + 1) >> 1;
           const double2* d2 = reinterpret_cast<const double2*>(dd);
           double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, a2 = 0.0, a3 = 0.0, b2 = 0.0, b3 = 0.0;
-          int c = cb;
-          if ((ce - c) & 1) {
-            const double2 j0 = Jr0[c], j1 = Jr1[c], dv = d2[c];
-            a0 += j0.x * dv.x; a1 += j0.y * dv.y;
-            b0 += j1.x * dv.x; b1 += j1.y * dv.y;
-            c++;
-          }
-#pragma unroll 2
-          for (; c < ce; c += 2) {
-            const double2 j0 = Jr0[c], j1 = Jr1[c], dv = d2[c];
-            const double2 k0 = Jr0[c + 1], k1 = Jr1[c + 1], ev = d2[c + 1];
-            a0 += j0.x * dv.x; a1 += j0.y * dv.y;
-            b0 += j1.x * dv.x; b1 += j1.y * dv.y;
-            a2 += k0.x * ev.x; a3 += k0.y * ev.y;
-            b2 += k1.x * ev.x; b3 += k1.y * ev.y;
-          }
+#define TSIDB_ZPAIR(c)                                                                       \
+  if ((c) < ce) {                                                                            \
+    const double2 j0 = Jr0[c], j1 = Jr1[c], dv = d2[c];                                      \
+    if ((c) & 1) { a2 += j0.x * dv.x; a3 += j0.y * dv.y; b2 += j1.x * dv.x; b3 += j1.y * dv.y; } \
+    else { a0 += j0.x * dv.x; a1 += j0.y * dv.y; b0 += j1.x * dv.x; b1 += j1.y * dv.y; }     \
+  }
+#define TSIDB_ZSEG(s) if (cb < 4 * (s) + 4 && 4 * (s) < ce) { TSIDB_ZPAIR(4 * (s)) TSIDB_ZPAIR(4 * (s) + 1) TSIDB_ZPAIR(4 * (s) + 2) TSIDB_ZPAIR(4 * (s) + 3) }
+          TSIDB_ZSEG(0) TSIDB_ZSEG(1) TSIDB_ZSEG(2) TSIDB_ZSEG(3)
+#undef TSIDB_ZSEG
+#undef TSIDB_ZPAIR
+          static_assert(ce <= 16, "four segments of four column pairs");
           z0 = has0 ? (a0 + a1) + (a2 + a3) : 0.0;
           z1 = has1 ? (b0 + b1) + (b2 + b3) : 0.0;
         }
@@ -1664,12 +1652,15 @@ TSIDB_DEV int as_solve2(const DevConst& C, const ASCtx& S, const LaneConst& K, i
         const int lpos = (__ballot_sync(FULL, t1_valid) != 0u) ? warp_argmin_fast(t1, t1_valid, lane) : -1;
         t1 = (lpos >= 0) ? shfl(t1, lpos) : TS_INF;
         /* full step t2 = -s_ip / z.n_ip, with z.n_ip = |d[iq:]|^2 (z = J2 d2, d2 = J2^T n) */
-        const double zz = warp_sum(z0 * z0 + z1 * z1);
+        /* The reference tests |z|^2 > eps.  z = J2 d with J2^T H J2 = I, so |z|^2 >= |d[iq:]|^2 / lambda_max(H) >=
+         * |d[iq:]|^2 / trace(H): when that bound clears eps by a wide margin the sum over z is not needed */
         const double d2sum = warp_sum((lane >= iq && lane < m) ? dl * dl : 0.0);
-        const double t2 = (fabs(zz) > TS_EPS) ? (-s_ip / d2sum) : TS_INF;
+        bool z_nonzero = d2sum > 64.0 * TS_EPS * trH;
+        if (!z_nonzero) z_nonzero = fabs(warp_sum(z0 * z0 + z1 * z1)) > TS_EPS;
+        const double t2 = z_nonzero ? (-s_ip / d2sum) : TS_INF;
         const double t = fmin(t1, t2);
 #ifdef TSIDB_EMU_TRACE
-        if (lane == 0) printf("[emu]   t1=%.17g (pos %d) t2=%.17g zz=%.6g znp=%.6g\n", t1, lpos, t2, zz, d2sum);
+        if (lane == 0) printf("[emu]   t1=%.17g (pos %d) t2=%.17g znp=%.6g\n", t1, lpos, t2, d2sum);
 #endif
         if (t >= TS_INF) { status = ST_INFEASIBLE; done = true; break; } /* eiquadprog UNBOUNDED -> HQP INFEASIBLE */
         /* step in dual space, and in primal space unless no direction is left */
@@ -1705,27 +1696,20 @@ TSIDB_DEV int as_solve2(const DevConst& C, const ASCtx& S, const LaneConst& K, i
                 const double2* v2 = reinterpret_cast<const double2*>(dd);
                 double2* W0 = const_cast<double2*>(Jr0);
                 double2* W1 = const_cast<double2*>(Jr1);
-                int c = cb;
-                if ((ce - c) & 1) {
-                  const double2 vc = v2[c];
-                  double2 j0 = Jr0[c], j1 = Jr1[c];
-                  j0.x -= w0 * vc.x; j0.y -= w0 * vc.y;
-                  j1.x -= w1 * vc.x; j1.y -= w1 * vc.y;
-                  if (has0) W0[c] = j0;
-                  if (has1) W1[c] = j1;
-                  c++;
-                }
-#pragma unroll 2
-                for (; c < ce; c += 2) {
-                  const double2 vc = v2[c], vd = v2[c + 1];
-                  double2 j0 = Jr0[c], j1 = Jr1[c], k0 = Jr0[c + 1], k1 = Jr1[c + 1];
-                  j0.x -= w0 * vc.x; j0.y -= w0 * vc.y;
-                  j1.x -= w1 * vc.x; j1.y -= w1 * vc.y;
-                  k0.x -= w0 * vd.x; k0.y -= w0 * vd.y;
-                  k1.x -= w1 * vd.x; k1.y -= w1 * vd.y;
-                  if (has0) { W0[c] = j0; W0[c + 1] = k0; }
-                  if (has1) { W1[c] = j1; W1[c + 1] = k1; }
-                }
+                /* static segments of four column pairs as in the z pass; all loads of a segment ahead of its stores
+                 * (the rows alias the store targets, so the compiler cannot move them itself) */
+#define TSIDB_HSEG(s)                                                                                          \
+  if (cb < 4 * (s) + 4 && 4 * (s) < ce) {                                                                      \
+    constexpr int c_ = 4 * (s);                                                                                \
+    double2 vq[4], p0[4], p1[4];                                                                               \
+    _Pragma("unroll") for (int k = 0; k < 4; k++) if (c_ + k < ce) { vq[k] = v2[c_ + k]; p0[k] = Jr0[c_ + k]; p1[k] = Jr1[c_ + k]; } \
+    _Pragma("unroll") for (int k = 0; k < 4; k++) if (c_ + k < ce) {                                           \
+      p0[k].x -= w0 * vq[k].x; p0[k].y -= w0 * vq[k].y; p1[k].x -= w1 * vq[k].x; p1[k].y -= w1 * vq[k].y;       \
+    }                                                                                                          \
+    _Pragma("unroll") for (int k = 0; k < 4; k++) if (c_ + k < ce) { if (has0) W0[c_ + k] = p0[k]; if (has1) W1[c_ + k] = p1[k]; } \
+  }
+                TSIDB_HSEG(0) TSIDB_HSEG(1) TSIDB_HSEG(2) TSIDB_HSEG(3)
+#undef TSIDB_HSEG
               }
               /* new column of R: [d[0:iq]; beta]; position iq of the working set */
               if (lane < iq) Rp[iq * (iq + 1) / 2 + lane] = dl;
@@ -1856,6 +1840,41 @@ TSIDB_DEV int as_solve2(const DevConst& C, const ASCtx& S, const LaneConst& K, i
 }
 
 /* ================================================================= kernel D: dynamics + assembly of one env */
+/* This env's references -> shared memory, one element per lane and array, as asynchronous copies (cp.async: no
+ * register, no wait): they are issued before K1 and waited for after it, so the tick never stalls on them.  An
+ * array the caller did not pass (null) takes the handle's default reference. */
+TSIDB_DEV void stage_one(double* dst, const double* src, const TickArgs& a, int env, int k, int nd, const double* dflt) {
+  if (!src) { *dst = dflt[k]; return; } /* lane-indexed read of the constants: default path only */
+#ifndef TSIDB_EMU
+  const double* g = src + eidx(a, env, k, nd);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(g) : "memory");
+#else
+  *dst = src[eidx(a, env, k, nd)];
+#endif
+}
+TSIDB_DEV void stage_refs(const DevConst& C, const double* mdl, double* sm, const TickArgs& a, int env, int lane, int na) {
+  double* rf = sm + SM_oRef;
+  if (lane < 24) {
+    stage_one(rf + RF_FOOT + lane, a.r_foot[0], a, env, lane, 24, C.ref_foot[0]);
+    stage_one(rf + RF_FOOT + 24 + lane, a.r_foot[1], a, env, lane, 24, C.ref_foot[1]);
+  }
+  if (lane < 12) {
+    stage_one(rf + RF_CONTACT + lane, a.r_contact[0], a, env, lane, 12, C.ref_contact[0]);
+    stage_one(rf + RF_CONTACT + 12 + lane, a.r_contact[1], a, env, lane, 12, C.ref_contact[1]);
+  }
+  if (lane < 9) stage_one(rf + RF_COM + lane, a.r_com, a, env, lane, 9, C.ref_com);
+  if (lane < na) stage_one(rf + RF_POST + lane, a.r_posture, a, env, lane, na, mdl + MDL_oPOST + 46);
+#ifndef TSIDB_EMU
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+TSIDB_DEV void stage_refs_wait() {
+#ifndef TSIDB_EMU
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+  __syncwarp();
+}
+
 template <int NV>
 TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, const TickArgs& a, int env, int slot, int lane) {
   constexpr int nv = NV, na = NV - 6, nq = NV + 1;
@@ -1864,22 +1883,10 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
   if (lane == 0) bulk_store_wait_read(); /* the previous env's image stores are done with this warp's shared memory */
   __syncwarp();
 #endif
-#ifndef TSIDB_EMU
-  /* the per-env references are read after K1: pull their lines into L2 now (row-major layout: contiguous per env) */
-  if (!a.layout && !a.kin_only) {
-    const char* pf = nullptr;
-    if (lane < 2 && a.r_foot[lane]) pf = (const char*)(a.r_foot[lane] + (size_t)env * 24);
-    else if (lane < 4 && lane >= 2 && a.r_foot[lane - 2]) pf = (const char*)(a.r_foot[lane - 2] + (size_t)env * 24) + 128;
-    else if (lane < 6 && lane >= 4 && a.r_contact[lane - 4]) pf = (const char*)(a.r_contact[lane - 4] + (size_t)env * 12);
-    else if (lane == 6 && a.r_com) pf = (const char*)(a.r_com + (size_t)env * 9);
-    else if (lane == 7 && a.r_posture) pf = (const char*)(a.r_posture + (size_t)env * na);
-    else if (lane == 8 && a.r_posture) pf = (const char*)(a.r_posture + (size_t)env * na) + 128;
-    if (pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-  }
-#endif
   /* stage q, v */
   if (lane < nq) sm[SM_oQV + lane] = ldin(a.q, a, env, lane, nq);
   if (lane < nv) sm[SM_oQV + 32 + lane] = a.v ? ldin(a.v, a, env, lane, nv) : 0.0;
+  if (!a.kin_only) stage_refs(C, mdl, sm, a, env, lane, na);
   __syncwarp();
   k1_dynamics<NV>(C, mdl, sm, lane);
   const double* fr = sm + SM_oFr;
@@ -1915,6 +1922,7 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
   for (int k = lane; k < 162; k += 32) eimg[SE_oMu + k] = sm[SM_oM + k];
   __syncwarp();
   PHASE_SYNC_D();
+  stage_refs_wait();
   k2_assemble<NV>(C, mdl, sm, a, env, lane, mask, neq, n);
   /* solver image (layout a_layout(nv, nc)): the parts that do not depend on the elimination */
   /* rows of the feet in contact, in force-block order (block 0 = LF if it is in contact, else RF), row by row */
@@ -1929,7 +1937,6 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
     }
   }
   if (lane < na) { img[oNle_c + lane] = sm[SM_oNle + 6 + lane]; img[oVj_c + lane] = sm[SM_oQV + 32 + 6 + lane]; }
-  if (lane == 0) img[SA_oSc + 3] = (double)mask;
   /* assembly image (layout SE_*) for the elimination kernel */
 #ifndef TSIDB_EMU
   /* the two contiguous pieces (H | g, JF) leave as bulk asynchronous stores (TMA); the next env
@@ -1971,12 +1978,13 @@ TSIDB_DEV void eliminate_env(const DevConst& C, const double* lfinv_sm, double* 
   __syncwarp();
   const int mask = (int)sm[SE_oSc]; /* its contact count is NC: the slots are class-sorted */
   constexpr int n = NV + 12 * NC;
-  double c1c2 = 0.0, R_norm = 1.0;
-  const int err = k3_eliminate<NV, NC>(C, lfinv_sm, sm, lane, mask, c1c2, R_norm);
+  double c1c2 = 0.0, c1 = 0.0, R_norm = 1.0;
+  const int err = k3_eliminate<NV, NC>(C, lfinv_sm, sm, lane, mask, c1c2, c1, R_norm);
   typedef AL<NV, NC> LA;
   double* img = a.ws + (size_t)slot * SA_IMAGE;
   for (int k = lane; k < even_up(n); k += 32) img[LA::oX + k] = (k < n) ? sm[LE::oX + k] : 0.0;
-  if (lane == 0) { img[SA_oSc] = c1c2; img[SA_oSc + 1] = R_norm; img[SA_oSc + 2] = (double)err; }
+  /* scalars of the solver image: c1 c2, R_norm, (status, contact mask) packed, trace(H) */
+  if (lane == 0) { img[SA_oSc] = c1c2; img[SA_oSc + 1] = R_norm; img[SA_oSc + 2] = (double)(4 * err + mask); img[SA_oSc + 3] = c1; }
   /* the null-space basis goes straight from the factor in shared memory to the solver image */
   __syncwarp();
   if (err == ST_OPTIMAL) j2_from_factor<NV, NC>(C, sm + SE_oH, sm + LE::oILD, sm + LE::oTAU, sm + LE::oVT, img, lane);
@@ -2089,8 +2097,8 @@ TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const 
   S.J2 = sm + LA::oJ2; S.Ma = sm + LA::oMa; S.JFa = sm + LA::oJFa; S.nle_a = sm + LA::oNle; S.vj = sm + LA::oVj;
   S.x = sm + LA::oX; S.wr = sm + LA::oWr;
   S.Rp = sm + LA::oR; S.np = sm + LA::oNP; S.dd = sm + LA::oD;
-  const double c1c2 = sm[SA_oSc], R_norm = sm[SA_oSc + 1];
-  const int err = (int)sm[SA_oSc + 2], mask = (int)sm[SA_oSc + 3]; /* its contact count is NC (class-sorted slots) */
+  const double c1c2 = sm[SA_oSc], R_norm = sm[SA_oSc + 1], c1 = sm[SA_oSc + 3];
+  const int em = (int)sm[SA_oSc + 2], err = em >> 2, mask = em & 3; /* its contact count is NC (class-sorted slots) */
   constexpr int nc = NC, n = LA::n, neq = 6 + 6 * NC;
   S.wro = (NC == 1 && !(mask & 1)) ? 6 : 0;
   K.lb = K.ub = 0.0;
@@ -2104,7 +2112,7 @@ TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const 
   int iters = 0;
   uint64_t words[3] = {0, 0, 0};
   int status = err;
-  if (err == ST_OPTIMAL) status = as_solve2<NV, NC>(C, S, K, lane, mask, c1c2, R_norm, iters, words);
+  if (err == ST_OPTIMAL) status = as_solve2<NV, NC>(C, S, K, lane, mask, c1c2, c1, R_norm, iters, words);
   const bool ok = (status == ST_OPTIMAL || status == ST_MAX_ITER);
   const double* x = S.x;
   double* wr = S.wr;
