@@ -3,17 +3,22 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+    python bench.py --config {standing4096,walking65536,legacy16384,mixed1M} [--data replay]
 
 One "step" = one TSID tick (computeProblemData + solve + decode, ref:main.py:119-127) of every env of the
-batch.  Workload = BASELINE.json configs[2]: robot/v1 LIPM walking, 65536 envs per GPU with per-env contact
-phases (20 % double support, 40 % / 40 % single support), swing-foot and CoM references and random
-perturbed states (seed 0).  Weak scaling: every rank owns its own 65536 envs; the only
-collective is the all-gather of the per-tick diagnostics.
+batch.  The headline workload (default) is BASELINE.json configs[2]: robot/v1 LIPM walking, 65536 envs per GPU
+with per-env contact phases (20 % double support, 40 % / 40 % single support), swing-foot and CoM references and
+random perturbed states (seed 0).  Weak scaling: every rank owns its own 65536 envs; the only
+collective is the all-gather of the per-tick diagnostics.  --config selects the other BASELINE configs
+(configs[1] standing, configs[3] legacy OP3, configs[4] v0+v1 mixed 1 M envs sharded by env index: strong
+scaling); --data replay times ticks over states RECORDED from a closed-loop device rollout (tick -> integrate ->
+gait phase machine), one recorded step per timed step, instead of independent random states.
 
 Rank 0 prints ONE JSON line.  `value` is measured with inputs resident in HBM, CUDA events around every
 step on the launching stream, an L2 flush between steps (outside the events), max over ranks.  `e2e` is the
-same tick through the host-buffer entry point tsidb_compute_host (pinned staging, H2D, kernels, D2H inside
-the timed region).
+same tick through the host-buffer entry point tsidb_compute_host (pinned host buffers, H2D, kernels, D2H inside
+the timed region); `e2e_device_refs` is the deployment the device gait makes possible: references and contact
+phases stay on the device (tsidb_compute_host_devrefs), only q and v are uploaded per tick.
 """
 from __future__ import annotations
 
@@ -33,25 +38,45 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-BATCH = 65536
 METRIC = "tsid_qp_ticks_per_sec"
 UNIT = "ticks/s"
-WORKLOAD = "robot/v1 LIPM walking (BASELINE configs[2]): 65536 envs/GPU, 20% DS / 40% SS-L / 40% SS-R, seed 0"
+
+# parts: (controller kind, share of the envs) — 'v1' = WalkController + ctrl/conf.py, 'v0' = legacy Biped + op3_conf;
+# n: envs per GPU (weak scaling) or in total (strong scaling)
+CONFIGS = {
+    "standing4096": dict(parts=[("v1", 1.0)], n=4096, mode="standing", scaling="weak",
+                         workload="robot/v1 double-support standing balance (BASELINE configs[1]): 4096 envs/GPU, seed 0"),
+    "walking65536": dict(parts=[("v1", 1.0)], n=65536, mode="walking", scaling="weak",
+                         workload="robot/v1 LIPM walking (BASELINE configs[2]): 65536 envs/GPU, 20% DS / 40% SS-L / 40% SS-R, seed 0"),
+    "legacy16384": dict(parts=[("v0", 1.0)], n=16384, mode="walking", scaling="weak",
+                        workload="legacy OP3 model (robot/v0 + op3_conf) walking (BASELINE configs[3]): 16384 envs/GPU, "
+                                 "single/double-support contact switching, seed 0"),
+    "mixed1M": dict(parts=[("v0", 0.5), ("v1", 0.5)], n=1 << 20, mode="walking", scaling="strong",
+                    workload="robot/v0 + robot/v1 mixed walking (BASELINE configs[4]): 1048576 envs in total, first half v0 "
+                             "(op3_conf), second half v1, contiguous by model, sharded by env index over the GPUs, seed 0"),
+}
+GAIT = {"v1": (0.3, 0.2, 0.2, 0.5), "v0": (0.1, 0.1275, 0.05, 0.7)}  # ref:ctrl/conf.py:24-28, ref:legacy/op3_conf.py:9-12
+CHUNK = 131072  # envs per handle call (workspace 30 KB per env)
 
 
 # ----------------------------------------------------------------------------------------------
-def algorithmic_flops(mask: np.ndarray, iters: np.ndarray) -> dict:
+def algorithmic_flops(kind: str, mask: np.ndarray, iters: np.ndarray) -> dict:
     """SURVEY.md §8(d): F/tick = F_dyn + F_asm + F_fact(n) + equality phase + per_iter * it (1 FMA = 2 flop);
     it = active-set iterations that attempted a constraint change = iterations - 1 (the last pass only checks
-    feasibility).  DS 0.50 M + 0.020 M it, SS 0.22 M + 0.012 M it, flight from the same formula (n = 26,
-    m_e = 6).  Split by the kernel that does the work: dynamics+assembly 28 k (F_dyn 20 k + F_asm 8 k), the
-    factorisation and equality phase (elimination + null-space-basis kernels), the iterations (active set)."""
+    feasibility).  v1: DS 0.50 M + 0.020 M it, SS 0.22 M + 0.012 M it; v0: DS 0.46 M + 0.018 M it, SS 0.20 M +
+    0.011 M it; flight from the same formula (n = nv, m_e = 6).  Split by the kernel that does the work:
+    dynamics+assembly 28 k (F_dyn 20 k + F_asm 8 k), the factorisation and equality phase (elimination kernel,
+    which also builds the null-space basis), the iterations (active-set kernel)."""
     nc = (mask & 1) + ((mask >> 1) & 1)
-    base = np.where(nc == 2, 0.50e6, np.where(nc == 1, 0.22e6, 0.075e6))
-    per = np.where(nc == 2, 0.020e6, np.where(nc == 1, 0.012e6, 0.0075e6))
+    if kind == "v1":
+        base = np.where(nc == 2, 0.50e6, np.where(nc == 1, 0.22e6, 0.075e6))
+        per = np.where(nc == 2, 0.020e6, np.where(nc == 1, 0.012e6, 0.0075e6))
+    else:
+        base = np.where(nc == 2, 0.46e6, np.where(nc == 1, 0.20e6, 0.065e6))
+        per = np.where(nc == 2, 0.018e6, np.where(nc == 1, 0.011e6, 0.0065e6))
     it = np.maximum(iters.astype(np.float64) - 1.0, 0.0)
     dyn = 28e3 * len(mask)
-    return {"dynamics": float(dyn), "eliminate+j2": float(base.sum() - dyn), "activeset": float((per * it).sum()),
+    return {"dynamics": float(dyn), "eliminate": float(base.sum() - dyn), "activeset": float((per * it).sum()),
             "tick": float((base + per * it).sum())}
 
 
@@ -104,46 +129,135 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-def make_workload(n: int, seed: int, q_stand: np.ndarray, refs0: dict):
+def make_workload(kind: str, mode: str, n: int, seed: int, q_stand: np.ndarray, refs0: dict):
     from tsid_control_b200 import synth
 
     q, v = synth.random_states(q_stand, n, seed)
-    mask, refs = synth.walking_batch(refs0, n, seed, 0.3, 0.2, 0.2, 0.5, float(refs0["com"][2]))
+    if mode == "standing":
+        return q, v, np.full(n, 3, np.uint8), {k: np.tile(a, (n, 1)) for k, a in refs0.items()}
+    mask, refs = synth.walking_batch(refs0, n, seed, *GAIT[kind], float(refs0["com"][2]))
     return q, v, mask, refs
 
 
+def shard_parts(cfg: dict, rank: int, world: int):
+    """[(kind, n_envs, seed)] this rank owns.  Weak scaling: the whole config per rank.  Strong scaling (mixed1M): the
+    global env range is cut by contiguous env index (sharding.shard_range); a rank's slice is split by model."""
+    if cfg["scaling"] == "weak":
+        return [(cfg["parts"][0][0], cfg["n"], 1000 * rank)]
+    from tsid_control_b200.sharding import shard_range
+
+    lo, hi = shard_range(cfg["n"], rank, world)
+    out, start = [], 0
+    for kind, frac in cfg["parts"]:
+        end = start + int(round(frac * cfg["n"]))
+        a, b = max(lo, start), min(hi, end)
+        if b > a:
+            out.append((kind, b - a, 7 * a + 1))  # the seed depends on the global offset only
+        start = end
+    return out
+
+
 def run_reference(args) -> None:
-    """The reference algorithm (restated CPU port: oracle/, -O3 AVX2 build) on all host threads."""
+    """The reference algorithm (restated CPU port: oracle/, -O3 AVX2 build) on all host threads, on the SAME config:
+    every step is one tick of the whole per-GPU batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from common import setup
 
-    s = setup("v1", "liboracle_fast.so")
+    cfg = dict(CONFIGS[args.config])
+    if args.batch:
+        cfg["n"] = args.batch
     cores = os.cpu_count() or 1
-    sample = max(256, min(8192, 512 * cores))
-    q, v, mask, refs = make_workload(sample, 0, s["q0"], s["refs"])
-    run = s["oracle"].timed_batch(q, v, mask, refs, cores)
+    runs, total = [], 0
+    for kind, n, seed in shard_parts(cfg, 0, 1):
+        if cfg["scaling"] == "strong":
+            n = min(n, 32768)  # mixed1M: a bounded sample per model (the whole config needs > 10 s per step on a host)
+        s = setup(kind, "liboracle_fast.so")
+        q, v, mask, refs = make_workload(kind, cfg["mode"], n, seed, s["q0"], s["refs"])
+        runs.append(s["oracle"].timed_batch(q, v, mask, refs, cores))
+        total += n
     for _ in range(max(1, args.warmup)):
-        run()
+        for r in runs:
+            r()
     times = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        run()
+        for r in runs:
+            r()
         times.append(time.perf_counter() - t0)
-    val = sample * len(times) / sum(times)
+    val = total * len(times) / sum(times)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": cfg["scaling"],
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_envs_per_step": sample},
+        "config": {"workload": cfg["workload"], "name": args.config, "envs_per_step": total},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} envs of the workload per step, {cores} threads, restated CPU port of "
-                                   "pinocchio+tsid+eiquadprog-fast (oracle/, -O3 x86-64-v3); the reference's own binaries "
-                                   "cannot be installed in this image"},
+                         "sample": f"{total} envs of the workload per step (the whole per-GPU batch), {cores} threads, restated "
+                                   "CPU port of pinocchio+tsid+eiquadprog-fast (oracle/, -O3 x86-64-v3); the reference's own "
+                                   "binaries cannot be installed in this image"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def pin_rank_to_cores(local: int, world: int) -> list:
+    """One slice of the host cores per rank (the ranks of a box share one NUMA node here: topology shows every GPU
+    with the same CPU affinity): the pinned staging buffers are first-touched from the slice that feeds them."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cores) >= world:
+            per = len(cores) // world
+            mine = cores[local * per:(local + 1) * per]
+            os.sched_setaffinity(0, mine)
+            return mine
+        return cores
+    except Exception:
+        return []
+
+
+class Shard:
+    """One (model, env range) of this rank: controller, device-resident inputs, host copies."""
+
+    def __init__(self, kind, n, seed, mode, local, torch):
+        if kind == "v1":
+            from tsid_control_b200.ctrl.conf import RobotConfig
+            from tsid_control_b200.ctrl.WalkController import WalkController
+
+            conf = RobotConfig()
+            conf.device, conf.max_envs = local, min(n, CHUNK)
+            self.ctrl = WalkController(conf, n_envs=1)
+        else:
+            import importlib
+            import types
+
+            from tsid_control_b200.legacy.biped import Biped
+
+            mod = importlib.import_module("tsid_control_b200.legacy.op3_conf")
+            conf = types.SimpleNamespace(**{k: getattr(mod, k) for k in dir(mod) if not k.startswith("_")})
+            conf.device, conf.max_envs = local, min(n, CHUNK)
+            self.ctrl = Biped(conf, n_envs=1)
+        self.kind, self.n, self.eng, self.dev = kind, n, self.ctrl.engine, self.ctrl.device
+        self.q, self.v, self.mask, self.refs = make_workload(kind, mode, n, seed, self.ctrl.q, self.ctrl.default_refs)
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=self.dev)
+        self.qd, self.vd, self.md = t(self.q), t(self.v), t(self.mask)
+        self.rd = {k: t(a) for k, a in self.refs.items()}
+        self.chunks = [(o, min(o + CHUNK, n)) for o in range(0, n, CHUNK)]
+        self.torch = torch
+
+    def set_inputs(self, qd, vd, md, rd):
+        self.qd, self.vd, self.md, self.rd = qd, vd, md, rd
+
+    def tick(self):
+        """One tick of every env of the shard (a handle call per chunk of <= CHUNK envs); returns (status, iters)."""
+        if len(self.chunks) == 1:
+            o = self.eng.compute(self.qd, self.vd, self.md, self.rd, want_active=True)
+            return o.status, o.iters
+        outs = []
+        for lo, hi in self.chunks:
+            o = self.eng.compute(self.qd[lo:hi], self.vd[lo:hi], self.md[lo:hi], {k: r[lo:hi] for k, r in self.rd.items()})
+            outs.append((o.status.clone(), o.iters.clone()))
+        return self.torch.cat([a for a, _ in outs]), self.torch.cat([b for _, b in outs])
 
 
 def main() -> None:
@@ -152,22 +266,29 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="envs per GPU (the metric is quoted at 65536)")
+    ap.add_argument("--config", default="walking65536", choices=sorted(CONFIGS),
+                    help="BASELINE.json config (the metric is quoted on walking65536)")
+    ap.add_argument("--data", default="synthetic", choices=["synthetic", "replay"],
+                    help="replay: states, contact phases and references recorded from a closed-loop device rollout")
+    ap.add_argument("--batch", type=int, default=0, help="override the config's env count (the metric is quoted at the config's own size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end and latency legs (the line then has no e2e)")
+    ap.add_argument("--no-e2e", action="store_true",
+                    help="profiling runs only: skip the end-to-end and latency legs (the line then has no e2e)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    my_cores = pin_rank_to_cores(local, world)  # before CUDA and the pinned allocations exist
 
     import torch
     import torch.distributed as dist
 
     import __graft_entry__ as ge
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the TSID tick has no CPU fallback (use --impl reference for the CPU port)")
     if rank == 0:
@@ -176,30 +297,69 @@ def main() -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
-    from tsid_control_b200.ctrl.conf import RobotConfig
-    from tsid_control_b200.ctrl.WalkController import WalkController
     from tsid_control_b200.engine import fp64_peak_tflops
     from tsid_control_b200.sharding import gather_diagnostics
 
-    n = args.batch
-    conf = RobotConfig()
-    conf.device, conf.max_envs = local, n
-    ctrl = WalkController(conf, n_envs=n)
-    eng = ctrl.engine
-    dev = ctrl.device
-    # every rank owns a different shard of the global env range (seed offset by rank)
-    q, v, mask, refs = make_workload(n, 0 + 1000 * rank, ctrl.q, ctrl.default_refs)
-    qd, vd = torch.as_tensor(q, device=dev), torch.as_tensor(v, device=dev)
-    ctrl.contact_mask = torch.as_tensor(mask, device=dev)
-    ctrl.refs = {k: torch.as_tensor(np.ascontiguousarray(a), device=dev) for k, a in refs.items()}
+    cfg = dict(CONFIGS[args.config])
+    if args.batch:
+        cfg["n"] = args.batch
+    parts = shard_parts(cfg, rank, world)
+    shards = [Shard(kind, n, seed, cfg["mode"], local, torch) for kind, n, seed in parts]
+    dev = shards[0].dev
+    n_local = sum(s.n for s in shards)
+    n_global = cfg["n"] * world if cfg["scaling"] == "weak" else cfg["n"]
+    n_pad = -(-cfg["n"] // world) if cfg["scaling"] == "strong" else cfg["n"]  # equal-length shards for the all-gather
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 256 MiB > 126 MB L2
-    diag_out = torch.empty((world * n, 2), dtype=torch.int32, device=dev) if world > 1 else None
+    diag_out = torch.empty((world * n_pad, 2), dtype=torch.int32, device=dev) if world > 1 else None
+    diag_st = torch.zeros(n_pad, dtype=torch.int32, device=dev)
+    diag_it = torch.zeros(n_pad, dtype=torch.int32, device=dev)
+
+    # ---- replay data: record a closed-loop rollout (tick -> integrate -> gait step on the device), one snapshot per step
+    replay, fails = None, 0
+    if args.data == "replay":
+        if len(shards) != 1 or len(shards[0].chunks) != 1:
+            raise SystemExit("--data replay records one rollout per rank: use a single-model config of at most 131072 envs per GPU")
+        s = shards[0]
+        conf = s.ctrl.conf
+        rng = np.random.Generator(np.random.PCG64(12345 + rank))
+        phase0 = torch.as_tensor(rng.uniform(0, 1, s.n), device=dev)
+        vcmd = torch.as_tensor(np.c_[rng.uniform(-0.3, 0.3, s.n), rng.uniform(-0.1, 0.1, s.n)], device=dev)
+        L, W, Hh, T = GAIT[s.kind]
+        s.eng.gait_reset(s.n, dt=float(conf.dt), step_duration=T, step_length=L, step_height=Hh,
+                         com_height=float(s.ctrl.default_refs["com"][2]), phase0=phase0, vcmd=vcmd)
+        qr, vr = s.qd.clone(), s.vd.clone()
+        vr *= 0.2  # start near rest: the recorded states are what the controller itself produces afterwards
+        post = s.rd["posture"]
+        snaps = []
+        s.eng.rollout(qr, vr, 25, use_graph=True)  # run in
+        for _ in range(max(args.steps, 8)):
+            gs = s.eng.gait_state()
+            snaps.append((qr.clone(), vr.clone(), gs["mask"].clone(),
+                          {"com": gs["com"].clone(), "foot_lf": gs["foot_lf"].clone(), "foot_rf": gs["foot_rf"].clone(),
+                           "contact_lf": gs["contact_lf"].clone(), "contact_rf": gs["contact_rf"].clone(), "posture": post}))
+            s.eng.rollout(qr, vr, 5, use_graph=True)  # 10 ms of closed loop between snapshots
+        torch.cuda.synchronize()
+        replay = snaps
+        fails = int((s.eng.gait_state()["fails"] > 0).sum().item())
+
+    step_no = [0]
 
     def step():
-        out = ctrl._tick(qd, vd)
+        if replay is not None:
+            shards[0].set_inputs(*replay[step_no[0] % len(replay)])
+            step_no[0] += 1
+        off = 0
+        res = []
+        for s in shards:
+            st, it = s.tick()
+            res.append((st, it))
+            if world > 1:
+                diag_st[off:off + s.n] = st
+                diag_it[off:off + s.n] = it
+            off += s.n
         if world > 1:
-            gather_diagnostics(out.status, out.iters, diag_out)
-        return out
+            gather_diagnostics(diag_st, diag_it, diag_out)
+        return res
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -211,44 +371,60 @@ def main() -> None:
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
-    launches0 = eng.launch_count()
+    step_no[0] = 0
+    launches0 = sum(s.eng.launch_count() for s in shards)
     evs = []
+    iters_seen, mask_seen = [], []
     for _ in range(args.steps):
         flush.zero_()  # evict the inputs from L2 (outside the timed events)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = step()
+        res = step()
         e1.record()
         evs.append((e0, e1))
+        if replay is not None:  # the iteration histogram differs from step to step: keep them all (outside the events)
+            iters_seen.append(res[0][1].cpu().numpy().copy())
+            mask_seen.append(shards[0].md.cpu().numpy().copy())
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    launches = eng.launch_count() - launches0
+    launches = sum(s.eng.launch_count() for s in shards) - launches0
     ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = sum(ms)
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    value = world * n * args.steps / (total_ms * 1e-3)
+    value = n_global * args.steps / (total_ms * 1e-3)
 
-    iters_np = out.iters.cpu().numpy()
-    status_np = out.status.cpu().numpy()
-    flops = algorithmic_flops(mask, iters_np)
+    status_np = np.concatenate([st.cpu().numpy() for st, _ in res])
+    iters_np = np.concatenate([it.cpu().numpy() for _, it in res])
+    if replay is not None:
+        fl = [algorithmic_flops(shards[0].kind, m, i) for m, i in zip(mask_seen, iters_seen)]
+        flops = {k: float(np.mean([f[k] for f in fl])) for k in fl[0]}
+    else:
+        fl = [algorithmic_flops(s.kind, s.mask, it.cpu().numpy()) for s, (_, it) in zip(shards, res)]
+        flops = {k: float(sum(f[k] for f in fl)) for k in fl[0]}
     step_ms = statistics.mean(ms)
     # per-kernel durations: CUDA events recorded by the library between its launches, on the launching stream,
     # in separate (untimed) steps with the same L2 flush so the events do not perturb `value`
-    eng.set_timing(True)
-    per_kernel = {}
-    reps = max(3, min(args.steps, 10))
-    for _ in range(reps):
-        flush.zero_()
-        step()
-        for k, t in eng.last_tick_ms().items():
-            per_kernel.setdefault(k, []).append(t)
-    eng.set_timing(False)
-    kms = {k: statistics.mean(v) for k, v in per_kernel.items()}
-    groups = {"dynamics": kms["dynamics"], "eliminate+j2": kms["eliminate"] + kms["j2"], "activeset": kms["activeset"]}
+    kms = {}
+    if all(len(s.chunks) == 1 for s in shards):  # the library keeps the events of a handle's last call only
+        for s in shards:
+            s.eng.set_timing(True)
+        per_kernel = {}
+        for _ in range(max(3, min(args.steps, 10))):
+            flush.zero_()
+            step()
+            acc = {}
+            for s in shards:
+                for k, t in s.eng.last_tick_ms().items():
+                    acc[k] = acc.get(k, 0.0) + t
+            for k, t in acc.items():
+                per_kernel.setdefault(k, []).append(t)
+        for s in shards:
+            s.eng.set_timing(False)
+        kms = {k: statistics.mean(v) for k, v in per_kernel.items()}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -260,58 +436,89 @@ def main() -> None:
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_ach = HBM_BYTES_PER_TICK * n / (step_ms * 1e-3) / 1e9
+    hbm_ach = HBM_BYTES_PER_TICK * n_local / (step_ms * 1e-3) / 1e9
     kernels = []
-    for g, t in groups.items():
-        tf = flops[g] / (t * 1e-3) / 1e12
-        kernels.append({"kernel": g, "ms": t, "algorithmic_flops_per_launch": flops[g], "achieved": tf,
-                        "frac": tf / fp64_peak if fp64_peak else None, "traffic": traffic.get(g)})
-    dom = max(kernels, key=lambda k: k["ms"])
+    if kms:
+        for g in ("dynamics", "eliminate", "activeset"):
+            t = kms[g]
+            tf = flops[g] / (t * 1e-3) / 1e12
+            kernels.append({"kernel": g, "ms": t, "algorithmic_flops_per_launch": flops[g], "achieved": tf,
+                            "frac": tf / fp64_peak if fp64_peak else None,
+                            "traffic": traffic.get(g) if args.config == "walking65536" else None})
+    dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
     tick_tf = flops["tick"] / (step_ms * 1e-3) / 1e12
 
     # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the call) ----
     # inputs live in pinned host memory (the contract's "from pinned host memory"), results land in pinned
     # host memory; the library cuts the batch into chunks so the copies run under the kernels
-    e2e_steps = max(3, min(args.steps, 10)) if not args.no_e2e else 1
-    hq, hv, hmask = eng.pin(q), eng.pin(v), eng.pin(mask)
-    hrefs = {k: eng.pin(a) for k, a in refs.items()}
-    hout = eng.host_buffers(n, pinned=True)
-    for _ in range(2):
-        eng.compute_host(hq, hv, hmask, hrefs, out=hout)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ho = eng.compute_host(hq, hv, hmask, hrefs, out=hout)
-    t_e2e = time.perf_counter() - t0
-    assert np.array_equal(ho["status"], status_np) and np.array_equal(ho["iters"], iters_np), "e2e path disagrees with the device path"
-    if world > 1:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
+    e2e = e2e_dev = None
+    lat = None
+    if not args.no_e2e:
+        e2e_steps = max(3, min(args.steps, 10))
+        host = []
+        for s in shards:
+            for lo, hi in s.chunks:
+                hq, hv, hm = s.eng.pin(s.q[lo:hi]), s.eng.pin(s.v[lo:hi]), s.eng.pin(s.mask[lo:hi])
+                hr = {k: s.eng.pin(a[lo:hi]) for k, a in s.refs.items()}
+                dm = torch.as_tensor(s.mask[lo:hi], device=dev)
+                dr = {k: torch.as_tensor(np.ascontiguousarray(a[lo:hi]), device=dev) for k, a in s.refs.items()}
+                host.append((s, hq, hv, hm, hr, s.eng.host_buffers(hi - lo, pinned=True), dm, dr))
+
+        def e2e_pass(device_refs: bool):
+            outs = []
+            for s, hq, hv, hm, hr, hout, dm, dr in host:
+                if device_refs:
+                    outs.append(s.eng.compute_host_devrefs(hq, hv, dm, dr, out=hout))
+                else:
+                    outs.append(s.eng.compute_host(hq, hv, hm, hr, out=hout))
+            return outs
+
+        results = {}
+        for device_refs in (False, True):
+            for _ in range(2):
+                e2e_pass(device_refs)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                ho = e2e_pass(device_refs)
+            t_e2e = time.perf_counter() - t0
+            if replay is None:
+                assert np.array_equal(np.concatenate([o["status"] for o in ho]), status_np), "e2e path disagrees with the device path"
+                assert np.array_equal(np.concatenate([o["iters"] for o in ho]), iters_np), "e2e path disagrees with the device path"
+            if world > 1:
+                t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                t_e2e = float(t.item())
+            results[device_refs] = n_global * e2e_steps / t_e2e
+        h2d_full = sum(s.n * (8 * (s.eng.nq + s.eng.nv + 9 + 24 + 24 + 12 + 12 + s.eng.na) + 1) for s in shards)
+        h2d_dev = sum(s.n * 8 * (s.eng.nq + s.eng.nv) for s in shards)
+        d2h = sum(s.n * (8 * (s.eng.na + s.eng.nv + 24) + 4 + 4 + 24) for s in shards)
+        e2e = {"value": results[False], "unit": UNIT, "h2d_bytes_per_step": h2d_full, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "api": "tsidb_compute_host via TsidEngine.compute_host: q, v, contact mask and every reference from pinned host buffers, "
+                      "results into pinned host buffers, 4 chunks over 3 streams (copies overlap the kernels)"}
+        e2e_dev = {"value": results[True], "unit": UNIT, "h2d_bytes_per_step": h2d_dev, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                   "api": "tsidb_compute_host_devrefs: q and v from pinned host buffers; references and contact phases resident on the "
+                          "device (the gait state the device phase machine keeps), results into pinned host buffers"}
+
+        # ---- single-env tick latency (the reference's own operating point: one robot per call) ----
+        if rank == 0:
+            s = shards[-1]
+            q1, v1 = s.qd[:1].contiguous(), s.vd[:1].contiguous()
+            ts = []
+            m1 = s.md[:1].contiguous()
+            r1 = {k: t[:1].contiguous() for k, t in s.rd.items()}
+            for i in range(220):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                s.eng.compute(q1, v1, m1, r1)
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            lat = statistics.median(ts[20:]) * 1e6
     # the sampler ran from the start of the timed region to here: the GPU was under the same tick load throughout
     # (timed steps, per-kernel timing steps, end-to-end steps), which gives nvidia-smi time for several samples
     clocks = sampler.stop()
     clocks["window"] = "timed steps + per-kernel timing steps + end-to-end steps"
-    e2e_val = world * n * e2e_steps / t_e2e
-    na, nv, nq = eng.na, eng.nv, eng.nq
-    h2d = n * (8 * (nq + nv + 9 + 24 + 24 + 12 + 12 + na) + 1)
-    d2h = n * (8 * (na + nv + 24) + 4 + 4 + 24)
-
-    # ---- single-env tick latency (the reference's own operating point: one robot per call) ----
-    lat = None
-    if rank == 0 and not args.no_e2e:
-        q1, v1 = qd[:1].contiguous(), vd[:1].contiguous()
-        ts = []
-        m1 = ctrl.contact_mask[:1].contiguous()
-        r1 = {k: t[:1].contiguous() for k, t in ctrl.refs.items()}
-        for i in range(220):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            o1 = eng.compute(q1, v1, m1, r1)
-            torch.cuda.synchronize()
-            ts.append(time.perf_counter() - t0)
-        lat = statistics.median(ts[20:]) * 1e6
 
     if rank != 0:
         if world > 1:
@@ -321,38 +528,48 @@ def main() -> None:
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": total_ms / args.steps, "p50_ms_per_step": statistics.median(ms), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": n, "global_envs": world * n, "l2_flush_between_steps": True,
+        "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f64", "data": args.data,
+        "config": {"workload": cfg["workload"], "name": args.config, "envs_per_gpu": n_local, "global_envs": n_global,
+                   "l2_flush_between_steps": True,
                    "timing": "CUDA events per step on the launching stream, flush outside the events, max over ranks",
-                   "collective": "all_gather of int32[N_local,2] diagnostics per step" if world > 1 else "none (1 GPU)"},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "api": "tsidb_compute_host via TsidEngine.compute_host: pinned host buffers in and out, 4 chunks over 3 streams (copies overlap the kernels)"},
+                   "collective": "all_gather of int32[N_local,2] diagnostics per step" if world > 1 else "none (1 GPU)",
+                   "host_cores_of_rank0": len(my_cores)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "fp64", "achieved": dom["achieved"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": dom["frac"],
-                     "traffic": dom["traffic"], "kernel": dom["kernel"], "kernel_ms": dom["ms"],
-                     "algorithmic_flops_per_launch": dom["algorithmic_flops_per_launch"],
-                     "peak_source": "measured on this GPU by tsidb_fp64_peak (dependent-free DFMA chains); MEASURED_PEAKS.json has no FP64 "
-                                    "entry; the path is FP64-bound, not HBM- or tensor-bound (SURVEY.md §8d)",
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture in profiles/ "
-                                       "(profiles/dram_traffic.json)" if traffic else None,
-                     "tick": {"achieved": tick_tf, "frac": tick_tf / fp64_peak if fp64_peak else None, "ms": step_ms,
-                              "algorithmic_flops_per_step": flops["tick"],
-                              "launches": "class sort (2) + dynamics + eliminate + j2 + activeset"},
-                     "kernels": kernels, "kernel_ms_all": kms,
-                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                             "algorithmic_bytes_per_tick": HBM_BYTES_PER_TICK,
-                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
-        "solver": {"mean_iters": float(iters_np.mean()), "max_iters": int(iters_np.max()), "status_optimal_frac": float((status_np == 0).mean())},
+        "solver": {"mean_iters": float(iters_np.mean()), "max_iters": int(iters_np.max()),
+                   "status_optimal_frac": float((status_np == 0).mean())},
         "tick_latency_1env_us_p50": lat,
     }
+    if replay is not None:
+        line["config"]["replay"] = (f"{len(replay)} snapshots of a closed-loop device rollout (tsidb_rollout: tick -> integrate_dv -> gait "
+                                    f"phase machine), 5 control steps apart after a 25-step run-in; envs that ever failed a tick: {fails}")
+    if e2e:
+        line["e2e"] = e2e
+        line["e2e_device_refs"] = e2e_dev
+    if dom:
+        line["roofline"] = {
+            "bound": "fp64", "achieved": dom["achieved"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": dom["frac"],
+            "traffic": dom["traffic"], "kernel": dom["kernel"], "kernel_ms": dom["ms"],
+            "algorithmic_flops_per_launch": dom["algorithmic_flops_per_launch"],
+            "peak_source": "measured on this GPU by tsidb_fp64_peak (dependent-free DFMA chains); MEASURED_PEAKS.json has no FP64 "
+                           "entry; the path is FP64- and shared-memory-bound, not HBM- or tensor-bound (SURVEY.md §8d, DESIGN.md §4)",
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture in profiles/ "
+                              "(profiles/dram_traffic.json)" if traffic else None,
+            "tick": {"achieved": tick_tf, "frac": tick_tf / fp64_peak if fp64_peak else None, "ms": step_ms,
+                     "algorithmic_flops_per_step": flops["tick"],
+                     "launches": "class sort (2) + dynamics + per contact class: elimination (with the null-space basis) + active set"},
+            "kernels": kernels, "kernel_ms_all": kms,
+            "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                    "algorithmic_bytes_per_tick": HBM_BYTES_PER_TICK,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
     if not args.no_cpu_baseline:
         from common import setup
 
-        s = setup("v1", "liboracle_fast.so")
+        s0 = shards[-1]
+        so = setup(s0.kind, "liboracle_fast.so")
         cores = os.cpu_count() or 1
-        sample = max(256, min(8192, 512 * cores))
-        run = s["oracle"].timed_batch(q[:sample], v[:sample], mask[:sample], {k: a[:sample] for k, a in refs.items()}, cores)
+        sample = min(s0.n, max(256, min(8192, 512 * cores)))
+        run = so["oracle"].timed_batch(s0.q[:sample], s0.v[:sample], s0.mask[:sample], {k: a[:sample] for k, a in s0.refs.items()}, cores)
         run()
         reps, t0 = 0, time.perf_counter()
         while time.perf_counter() - t0 < 10.0 and reps < 50:
@@ -360,7 +577,7 @@ def main() -> None:
             reps += 1
         dt = time.perf_counter() - t0
         # single-thread latency of one tick
-        run1 = s["oracle"].timed_batch(q[:64], v[:64], mask[:64], {k: a[:64] for k, a in refs.items()}, 1)
+        run1 = so["oracle"].timed_batch(s0.q[:64], s0.v[:64], s0.mask[:64], {k: a[:64] for k, a in s0.refs.items()}, 1)
         run1()
         t1 = time.perf_counter()
         run1()

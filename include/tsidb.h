@@ -20,7 +20,11 @@
  *
  * Ownership: the caller owns every buffer; the library owns the model/conf
  * constants and its workspace.  One handle per device; a handle is not
- * re-entrant.  Device entry points are asynchronous on `cuda_stream`.
+ * re-entrant: it has ONE set of workspaces, work counters and side streams, so
+ * all calls on one handle must be ordered with each other on one CUDA stream
+ * (two ticks enqueued on different streams, or a tsidb_compute_host issued while
+ * an earlier asynchronous tsidb_compute is still running, race on them); use one
+ * handle per stream.  Device entry points are asynchronous on `cuda_stream`.
  * There is no CPU fallback: every entry point fails (<0) without a CUDA device.
  *
  * Streams: a tick is enqueued on `cuda_stream`; internally the three contact-class
@@ -188,6 +192,17 @@ int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, const doubl
                        const uint8_t* contact_mask, const tsidb_refs* refs_host,
                        double* tau, double* ddq, double* f, int32_t* status, int32_t* iters,
                        uint64_t* active_set);
+
+/* The same host-buffer tick when the references and the contact phases already live on the DEVICE — the gait state
+ * of tsidb_gait_state(), advanced there by tsidb_gait_step(), or any [N][dof] device arrays of the caller — so that
+ * only q and v (424 B per robot/v1 env instead of 1 233 B) cross PCIe on the way in.  This is the deployment the
+ * reference intends around update_tasks (ref:ctrl/WalkController.py:189-206): the simulator hands over the state,
+ * the walking references are generated next to the solver.  contact_mask_dev and the arrays of refs_dev are device
+ * pointers (null = all feet in contact / handle defaults); q, v and the outputs are host pointers as above. */
+int tsidb_compute_host_devrefs(tsidb_handle* h, int n_envs, const double* q, const double* v,
+                               const uint8_t* contact_mask_dev, const tsidb_refs* refs_dev,
+                               double* tau, double* ddq, double* f, int32_t* status, int32_t* iters,
+                               uint64_t* active_set);
 
 /* controller.integrate_dv(q, v, dv, dt) (ref:ctrl/WalkController.py:291-295,
  * ref:legacy/biped.py:236-240): v_mean = v + dt/2*dv; v += dt*dv;

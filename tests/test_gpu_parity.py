@@ -215,6 +215,13 @@ def test_chunked_host_call_agrees_with_device_call(n, pinned):
     for k in ("tau", "ddq", "f", "status", "iters"):
         assert np.array_equal(h[k], base[k]), k
     assert np.array_equal(h["active_set"].astype(np.int64), base["active_set"])
+    # the same call with the references and contact phases resident on the device: only q and v are uploaded
+    dev = e.device
+    d = e.compute_host_devrefs(q, v, torch.as_tensor(mask, device=dev),
+                               {k: torch.as_tensor(np.ascontiguousarray(a), device=dev) for k, a in refs.items()})
+    for k in ("tau", "ddq", "f", "status", "iters"):
+        assert np.array_equal(d[k], base[k]), k
+    assert np.array_equal(d["active_set"].astype(np.int64), base["active_set"])
 
 
 @pytest.mark.parametrize("use_graph", [True, False])

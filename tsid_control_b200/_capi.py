@@ -219,6 +219,8 @@ def load_library() -> C.CDLL:
     lib.tsidb_compute.restype = ip
     lib.tsidb_compute_host.argtypes = [vp, ip, vp, vp, vp, C.POINTER(TsidbRefs), vp, vp, vp, vp, vp, vp]
     lib.tsidb_compute_host.restype = ip
+    lib.tsidb_compute_host_devrefs.argtypes = [vp, ip, vp, vp, vp, C.POINTER(TsidbRefs), vp, vp, vp, vp, vp, vp]
+    lib.tsidb_compute_host_devrefs.restype = ip
     lib.tsidb_integrate.argtypes = [vp, ip, ip, vp, vp, vp, C.c_double, vp]
     lib.tsidb_integrate.restype = ip
     lib.tsidb_kinematics.argtypes = [vp, ip, ip, vp, vp, C.POINTER(TsidbAuxOut), vp]
@@ -255,7 +257,7 @@ def check(rc: int, what: str) -> None:
 
 EXPORTED_SYMBOLS = [
     "tsidb_create", "tsidb_destroy", "tsidb_last_error", "tsidb_sizes", "tsidb_set_default_refs",
-    "tsidb_compute", "tsidb_compute_host", "tsidb_integrate", "tsidb_kinematics", "tsidb_ci_row",
+    "tsidb_compute", "tsidb_compute_host", "tsidb_compute_host_devrefs", "tsidb_integrate", "tsidb_kinematics", "tsidb_ci_row",
     "tsidb_fp64_peak", "tsidb_launch_count", "tsidb_set_timing", "tsidb_last_tick_ms",
     "tsidb_gait_reset", "tsidb_gait_state", "tsidb_gait_step", "tsidb_rollout", "tsidb_diagnostics",
 ]

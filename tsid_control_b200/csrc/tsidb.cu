@@ -482,9 +482,27 @@ static bool is_pinned(const void* p) {
  * chunk k+1 and the D2H copy of chunk k-1 run under the kernels of chunk k.  A caller buffer that is pinned
  * (cudaHostAlloc / cudaHostRegister / torch pin_memory) is the DMA source or target itself; a pageable one
  * goes through the handle's pinned staging, chunk by chunk. */
+static int compute_host_impl(tsidb_handle* h, int n_envs, const double* q, const double* v, const uint8_t* contact_mask,
+                             const tsidb_refs* refs, bool dev_refs, double* tau, double* ddq, double* f, int32_t* status,
+                             int32_t* iters, uint64_t* active_set);
+
 extern "C" int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, const double* v, const uint8_t* contact_mask,
                                   const tsidb_refs* refs, double* tau, double* ddq, double* f, int32_t* status,
                                   int32_t* iters, uint64_t* active_set) {
+  return compute_host_impl(h, n_envs, q, v, contact_mask, refs, false, tau, ddq, f, status, iters, active_set);
+}
+
+extern "C" int tsidb_compute_host_devrefs(tsidb_handle* h, int n_envs, const double* q, const double* v,
+                                          const uint8_t* contact_mask_dev, const tsidb_refs* refs_dev, double* tau, double* ddq,
+                                          double* f, int32_t* status, int32_t* iters, uint64_t* active_set) {
+  return compute_host_impl(h, n_envs, q, v, contact_mask_dev, refs_dev, true, tau, ddq, f, status, iters, active_set);
+}
+
+/* dev_refs: the contact mask and the reference arrays are device pointers and are used in place (chunk by chunk);
+ * otherwise they are host arrays and travel with q and v */
+static int compute_host_impl(tsidb_handle* h, int n_envs, const double* q, const double* v, const uint8_t* contact_mask,
+                             const tsidb_refs* refs, bool dev_refs, double* tau, double* ddq, double* f, int32_t* status,
+                             int32_t* iters, uint64_t* active_set) {
   if (!h || !q || !v || !tau || !ddq || !f || !status || !iters) { g_err = "tsidb_compute_host: null argument"; return -1; }
   if (n_envs <= 0 || n_envs > h->max_envs) { g_err = "tsidb_compute_host: n_envs exceeds the handle's max_envs"; return -1; }
   CK(cudaSetDevice(h->device));
@@ -497,11 +515,12 @@ extern "C" int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, 
       {refs ? refs->contact_rf : nullptr, 12, false}, {refs ? refs->posture : nullptr, na, false}};
   size_t off[9];
   off[0] = 0;
+  const int n_host_segs = dev_refs ? 2 : 8; /* q and v always come from the host */
   for (int s = 0; s < 8; s++) {
-    off[s + 1] = off[s] + (segs[s].src ? N * segs[s].nd : 0);
-    if (segs[s].src) segs[s].pinned = is_pinned(segs[s].src);
+    off[s + 1] = off[s] + ((segs[s].src && s < n_host_segs) ? N * segs[s].nd : 0);
+    if (segs[s].src && s < n_host_segs) segs[s].pinned = is_pinned(segs[s].src);
   }
-  const bool mask_pinned = contact_mask && is_pinned(contact_mask);
+  const bool mask_pinned = !dev_refs && contact_mask && is_pinned(contact_mask);
   const bool out_pinned[3] = {is_pinned(tau), is_pinned(ddq), is_pinned(f)};
   const bool st_pinned = is_pinned(status), it_pinned = is_pinned(iters);
   const bool act_pinned = active_set && is_pinned(active_set);
@@ -543,14 +562,14 @@ extern "C" int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, 
     const size_t o = bound[c];
     if (trace) CK(cudaEventRecord(tev[c][0], st));
     const int m = (int)(bound[c + 1] - bound[c]);
-    for (int s = 0; s < 8; s++) {
+    for (int s = 0; s < n_host_segs; s++) {
       if (!segs[s].src) continue;
       const size_t cnt = (size_t)m * segs[s].nd, eo = off[s] + o * segs[s].nd;
       const double* src = segs[s].src + o * segs[s].nd;
       if (!segs[s].pinned) { memcpy(h->h_in + eo, src, cnt * sizeof(double)); src = h->h_in + eo; }
       CK(cudaMemcpyAsync(h->d_in + eo, src, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
     }
-    if (contact_mask) {
+    if (contact_mask && !dev_refs) {
       const uint8_t* src = contact_mask + o;
       if (!mask_pinned) { memcpy(h->h_mask + o, src, m); src = h->h_mask + o; }
       CK(cudaMemcpyAsync(h->d_mask + o, src, m, cudaMemcpyHostToDevice, st));
@@ -558,10 +577,13 @@ extern "C" int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, 
     TickArgs a;
     memset(&a, 0, sizeof a);
     a.n_envs = m; a.layout = 0;
-    auto dptr = [&](int s) -> const double* { return segs[s].src ? h->d_in + off[s] + o * segs[s].nd : nullptr; };
+    auto dptr = [&](int s) -> const double* {
+      if (!segs[s].src) return nullptr;
+      return (s < n_host_segs) ? h->d_in + off[s] + o * segs[s].nd : segs[s].src + o * segs[s].nd; /* device array: in place */
+    };
     a.q = dptr(0); a.v = dptr(1); a.r_com = dptr(2); a.r_foot[0] = dptr(3); a.r_foot[1] = dptr(4);
     a.r_contact[0] = dptr(5); a.r_contact[1] = dptr(6); a.r_posture = dptr(7);
-    a.mask = contact_mask ? h->d_mask + o : nullptr;
+    a.mask = contact_mask ? (dev_refs ? contact_mask + o : h->d_mask + o) : nullptr;
     a.tau = d_tau + o * na; a.ddq = d_ddq + o * nv; a.f = d_f + o * 24;
     a.status = h->d_int + o; a.iters = h->d_int + N + o;
     a.active = active_set ? h->d_act + 3 * o : nullptr; /* [3][m] block of this chunk */

@@ -687,33 +687,41 @@ TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, con
 #pragma unroll
       for (int r = 0; r < 3; r++) ja[r] = Ag[r * TSIDB_NVX + j];
     }
-    /* H is symmetric: lane j computes the entries (i, j) for the nv/2 + 1 rows i = j, j+1, ... (cyclic) and
-     * stores each one on both sides of the diagonal; every unordered pair is covered */
-#pragma unroll 2
-    for (int t = 0; t <= nv / 2; t++) {
-      int i = j + t;
-      if (i >= nv) i -= nv;
-      /* four independent chains for the 12 foot rows (dependent fp64 latency, not throughput, is the limit) */
-      double sf0 = 0.0, sf1 = 0.0, sf2 = 0.0, sf3 = 0.0, scm = 0.0, sam = 0.0;
+    /* Lane j keeps column j of the stacked task matrix [JF; Jcom; Ag] in registers and forms H[t][j] for two rows t
+     * at a time: the other factor, column t, is the same for every lane, so it arrives as 16-byte BROADCAST reads (one
+     * shared-memory wavefront each) and a row of H leaves as one contiguous store.  The symmetric half-matrix
+     * scheme of round 1 (rows j+t cyclic) did half the FMAs but read 15 lane-strided values per entry and
+     * scattered its stores at stride 28 (8-way bank conflicts): 2.5x the shared-memory wavefronts of this loop,
+     * in a kernel that runs at two thirds of the shared-memory pipe's rate. */
+    static_assert((NV & 1) == 0 && (TSIDB_NVX & 1) == 0, "rows of H come in pairs");
+#pragma unroll 1
+    for (int t = 0; t < nv; t += 2) {
+      double sa0 = 0.0, sa1 = 0.0, sb0 = 0.0, sb1 = 0.0, ca = 0.0, cb = 0.0, ma = 0.0, mb = 0.0;
 #pragma unroll
-      for (int r = 0; r < 12; r += 4) {
-        sf0 += JF[r * TSIDB_NVX + i] * jf[r];
-        sf1 += JF[(r + 1) * TSIDB_NVX + i] * jf[r + 1];
-        sf2 += JF[(r + 2) * TSIDB_NVX + i] * jf[r + 2];
-        sf3 += JF[(r + 3) * TSIDB_NVX + i] * jf[r + 3];
+      for (int r = 0; r < 12; r += 2) {
+        const double2 p = *reinterpret_cast<const double2*>(JF + r * TSIDB_NVX + t);
+        const double2 q = *reinterpret_cast<const double2*>(JF + (r + 1) * TSIDB_NVX + t);
+        sa0 += p.x * jf[r]; sb0 += p.y * jf[r];
+        sa1 += q.x * jf[r + 1]; sb1 += q.y * jf[r + 1];
       }
-      const double sf = (sf0 + sf1) + (sf2 + sf3);
 #pragma unroll
-      for (int r = 0; r < 3; r++) scm += Jcom[r * TSIDB_NVX + i] * jc[r];
-      double hij = C.w_foot * sf + C.w_com * scm;
+      for (int r = 0; r < 3; r++) {
+        const double2 p = *reinterpret_cast<const double2*>(Jcom + r * TSIDB_NVX + t);
+        ca += p.x * jc[r]; cb += p.y * jc[r];
+      }
+      double ha = C.w_foot * (sa0 + sa1) + C.w_com * ca, hb = C.w_foot * (sb0 + sb1) + C.w_com * cb;
       if (C.use_am) {
 #pragma unroll
-        for (int r = 0; r < 3; r++) sam += Ag[r * TSIDB_NVX + i] * ja[r];
-        hij += C.w_am * sam;
+        for (int r = 0; r < 3; r++) {
+          const double2 p = *reinterpret_cast<const double2*>(Ag + r * TSIDB_NVX + t);
+          ma += p.x * ja[r]; mb += p.y * ja[r];
+        }
+        ha += C.w_am * ma; hb += C.w_am * mb;
       }
-      if (i == j) hij += (i >= 6 ? C.w_post : 0.0) + C.hreg;
-      H[i * SM_LDM + j] = hij;
-      H[j * SM_LDM + i] = hij;
+      if (t == j) ha += (j >= 6 ? C.w_post : 0.0) + C.hreg;
+      if (t + 1 == j) hb += (j >= 6 ? C.w_post : 0.0) + C.hreg;
+      H[t * SM_LDM + j] = ha;
+      H[(t + 1) * SM_LDM + j] = hb;
     }
     double gf = 0.0, gc = 0.0, ga = 0.0;
 #pragma unroll
@@ -2068,8 +2076,19 @@ TSIDB_DEV void j2_from_factor(const DevConst& C, const double* L, const double* 
 #pragma unroll
   for (int k = NV - 1; k >= 0; k--) {
     q[k] *= ild[k];
+    /* row k of L as 16-byte broadcast reads wherever the (odd) row stride leaves a pair aligned */
+    const int i0 = (k * SM_LDM) & 1;
+    if (i0 && k > 0) q[0] -= L[k * SM_LDM] * q[k];
 #pragma unroll
-    for (int ii = 0; ii < k; ii++) q[ii] -= L[k * SM_LDM + ii] * q[k];
+    for (int ii = i0; ii < k; ii += 2) {
+      if (ii + 1 < k) {
+        const double2 p = *reinterpret_cast<const double2*>(L + k * SM_LDM + ii);
+        q[ii] -= p.x * q[k];
+        q[ii + 1] -= p.y * q[k];
+      } else {
+        q[ii] -= L[k * SM_LDM + ii] * q[k];
+      }
+    }
   }
 #pragma unroll
   for (int k = 0; k < NV; k++) img[LA::oJ2 + k * LA::ldj + lane] = q[k];

@@ -189,6 +189,36 @@ class TsidEngine:
             out["iters"].ctypes.data, out["active_set"].ctypes.data if want_active else None), "tsidb_compute_host")
         return out
 
+    def compute_host_devrefs(self, q: np.ndarray, v: np.ndarray, contact_mask: Optional[torch.Tensor] = None,
+                             refs: Optional[Dict[str, torch.Tensor]] = None, want_active: bool = True,
+                             out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+        """compute_host with the references and the contact phases resident on the DEVICE (CUDA tensors, e.g. the
+        views of gait_state()): only q and v cross PCIe on the way in (tsidb_compute_host_devrefs)."""
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        n = q.shape[0]
+        if q.shape != (n, self.nq) or v.shape != (n, self.nv):
+            raise ValueError("q/v: expected [N,nq] / [N,nv]")
+        r = TsidbRefs()
+        if refs:
+            for k, nd in zip(REF_KEYS, (9, 24, 24, 12, 12, self.na)):
+                t = refs.get(k)
+                if t is not None:
+                    setattr(r, k, self._chk(t, n, nd, f"refs[{k}]").data_ptr())
+        if contact_mask is not None:
+            if contact_mask.dtype != torch.uint8 or contact_mask.device != self.device or tuple(contact_mask.shape) != (n,):
+                raise TypeError("contact_mask: expected a uint8 [N] tensor on the engine's device")
+        if out is None:
+            out = self.host_buffers(n, pinned=False)
+        elif out["tau"].shape[0] != n:
+            raise ValueError("out: buffers were allocated for a different batch size")
+        torch.cuda.current_stream(self.device).synchronize()  # the device arrays must be final: the call uses its own streams
+        check(self.lib.tsidb_compute_host_devrefs(
+            self.h, n, q.ctypes.data, v.ctypes.data, contact_mask.data_ptr() if contact_mask is not None else None, C.byref(r),
+            out["tau"].ctypes.data, out["ddq"].ctypes.data, out["f"].ctypes.data, out["status"].ctypes.data,
+            out["iters"].ctypes.data, out["active_set"].ctypes.data if want_active else None), "tsidb_compute_host_devrefs")
+        return out
+
     def kinematics(self, q: torch.Tensor, v: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """(com9, foot_lf12, foot_rf12): robot.com / robot.framePosition without a solve."""
         n = q.shape[0]
