@@ -282,6 +282,21 @@ int64_t tsidb_launch_count(const tsidb_handle* h);
 int tsidb_set_timing(tsidb_handle* h, int on);
 int tsidb_last_tick_ms(tsidb_handle* h, float* ms5);
 
+/* ---- the reference's planners on the device, one thread per env ---------------------------
+ * tsidb_foot_trajectory: FootTrajectory(t = [t0, t1], start, target, step_height, rise_ratio) of
+ * ref:ctrl/Foot_Trajectory.py:6-43 evaluated at t[e] for every env: start4/target4 [N][4] = (x, y, z, yaw),
+ * out16 [N][16] = value, 1st, 2nd and 3rd derivative of (x, y, z, yaw).  (The reference's get_velocity /
+ * get_acceleration return the 2nd and 3rd derivative, :35,:43.)  All arrays are device pointers. */
+int tsidb_foot_trajectory(tsidb_handle* h, int n_envs, double t0, double t1, const double* start4, const double* target4,
+                          double step_height, double rise_ratio, const double* t, double* out16, void* cuda_stream);
+/* tsidb_footstep_plan: FootstepPlanner(step_width, step_length).plan(path, init_supports) of
+ * ref:ctrl/Footstep_Planner.py:92-125 per env: path [N][max_pts][2] with n_pts[e] valid points (null: max_pts for
+ * every env), init8 [N][2][4] the two initial supports (x, y, yaw, side 0 = left / 1 = right), steps
+ * [N][max_steps][4] = (x, y, yaw, side), n_steps[e] = footsteps written (initial supports included; -1: max_steps
+ * too small).  Device pointers. */
+int tsidb_footstep_plan(tsidb_handle* h, int n_envs, const double* path, const int32_t* n_pts, int max_pts, const double* init8,
+                        double step_length, double step_width, double* steps, int32_t* n_steps, int max_steps, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,3 +141,17 @@ extern "C" int emu_gait(int n, const double* gconf6, double* phi, uint8_t* mask,
   }
   return 0;
 }
+
+/* the planners of tsidb_gait.cuh on the host, env after env (same functions the device kernels call) */
+extern "C" int emu_foot_trajectory(int n, double t0, double t1, const double* start4, const double* target4, double h, double rr,
+                                   const double* t, double* out16) {
+  for (int e = 0; e < n; e++) foot_trajectory_eval(t0, t1, start4 + 4 * e, target4 + 4 * e, h, rr, t[e], out16 + 16 * e);
+  return 0;
+}
+extern "C" int emu_footstep_plan(int n, const double* path, const int32_t* n_pts, int max_pts, const double* init8, double L, double W,
+                                 double* steps, int32_t* n_steps, int max_steps) {
+  for (int e = 0; e < n; e++)
+    n_steps[e] = footstep_plan_env(path + 2 * (size_t)max_pts * e, n_pts ? n_pts[e] : max_pts, init8 + 8 * (size_t)e, L, W,
+                                   steps + 4 * (size_t)max_steps * e, max_steps);
+  return 0;
+}

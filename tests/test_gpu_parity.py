@@ -599,3 +599,38 @@ def test_class_chains_on_streams_equal_the_single_stream_tick(monkeypatch):
     for k in ("tau", "ddq", "f", "status", "iters", "active_set"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
     assert (outs[0]["status"] == 0).mean() > 0.99
+
+
+@pytest.mark.parametrize("tag,rr", [("r50", 0.5), ("r10", 0.1)])
+def test_device_foot_trajectory_kernel_against_the_reference_golden(tag, rr):
+    """tsidb_foot_trajectory (CUDA) against the samples of the reference's own scipy CubicSplines
+    (tests/golden/planners.npz, generated by importing ref:ctrl/Foot_Trajectory.py): 3-knot and 4-knot z, linear x/y/yaw."""
+    from test_planners import _device_foot_trajectory
+
+    ctrl = _controller("v1", 1)
+    e, dev = ctrl.engine, ctrl.device
+
+    def run(t0, t1, start, target, h, r, t):
+        out = e.foot_trajectory(t0, t1, torch.as_tensor(start, device=dev), torch.as_tensor(target, device=dev), h, r,
+                                torch.as_tensor(t, device=dev))
+        torch.cuda.synchronize()
+        return out.cpu().numpy().reshape(len(t), 16)
+
+    _device_foot_trajectory(run, tag, rr)
+
+
+def test_device_footstep_plan_kernel_against_the_reference_golden():
+    """tsidb_footstep_plan (CUDA) against the footsteps the reference's FootstepPlanner.plan produces for its own demo path
+    (ref:ctrl/Footstep_Planner.py:127-150) and for a second, curved path — positions, yaw and sides."""
+    from test_planners import _device_footstep_plan
+
+    ctrl = _controller("v1", 1)
+    e, dev = ctrl.engine, ctrl.device
+
+    def run(path, n_pts, init, L, W, max_steps):
+        steps, ns = e.footstep_plan(torch.as_tensor(path, device=dev), torch.as_tensor(init, device=dev), L, W,
+                                    n_pts=torch.as_tensor(n_pts, device=dev), max_steps=max_steps)
+        torch.cuda.synchronize()
+        return steps.cpu().numpy(), ns.cpu().numpy()
+
+    _device_footstep_plan(run)

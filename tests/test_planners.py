@@ -85,3 +85,70 @@ def test_walk_planner_builds_swing_trajectories():
     p1 = first["trajectory"].get_position(0.5)
     assert np.allclose(p0[:2], steps[0].position) and np.allclose(p1[:2], steps[2].position)
     assert abs(float(first["trajectory"].z(0.25)) - 0.2) < 1e-15  # conf.step_height at mid-swing
+
+
+# ---- the same planners as DEVICE code (tsidb_gait.cuh), here through the host build of that header (tests/emu);
+# ---- tests/test_gpu_parity.py runs the CUDA kernels against the same golden vectors
+def _emu_lib():
+    import ctypes as C
+
+    from emu_py import build_emu
+
+    return C.CDLL(build_emu()), C
+
+
+def _device_foot_trajectory(run, tag, rr):
+    ts = G["ft_ts"]
+    n = len(ts)
+    start = np.tile(np.array([0.1, 0.05, 0.0, 0.2]), (n, 1))
+    target = np.tile(np.array([0.4, 0.07, 0.02, -0.1]), (n, 1))
+    out = run(0.0, 0.5, start, target, 0.2, rr, np.ascontiguousarray(ts)).reshape(n, 4, 4)
+    assert np.abs(out[:, 0, :3] - G[f"ft_{tag}_pos"]).max() < 1e-13
+    assert np.abs(out[:, 0, 3] - G[f"ft_{tag}_yaw"]).max() < 1e-14
+    assert np.abs(out[:, 1, :3] - G[f"ft_{tag}_d1"]).max() < 1e-12
+    assert np.abs(out[:, 2, :3] - G[f"ft_{tag}_vel"]).max() < 1e-10   # the reference's "velocity" is the 2nd derivative (:35)
+    assert np.abs(out[:, 3, :3] - G[f"ft_{tag}_acc"]).max() < 1e-8    # and its "acceleration" the 3rd (:43)
+
+
+def _device_footstep_plan(run):
+    paths = [G["fs_demo_path"], G["fs2_path"]]
+    P = max(len(p) for p in paths)
+    path = np.zeros((2, P, 2))
+    for e, p in enumerate(paths):
+        path[e, :len(p)] = p
+    n_pts = np.array([len(p) for p in paths], np.int32)
+    init = np.tile(np.array([[0, 0.1, 0, 0], [0, -0.1, 0, 1]], np.float64), (2, 1, 1))
+    steps, ns = run(path, n_pts, init, 0.3, 0.2, 64)
+    for e, tag in enumerate(("fs_demo", "fs2")):
+        k = int(ns[e])
+        assert k == len(G[f"{tag}_pos"])
+        assert np.abs(steps[e, :k, :2] - G[f"{tag}_pos"]).max() < 1e-14
+        assert np.abs(steps[e, :k, 2] - G[f"{tag}_yaw"]).max() < 1e-14
+        assert steps[e, :k, 3].astype(int).tolist() == G[f"{tag}_side"].tolist()
+
+
+@pytest.mark.parametrize("tag,rr", [("r50", 0.5), ("r10", 0.1)])
+def test_device_foot_trajectory_code_matches_the_reference_splines(tag, rr):
+    lib, C = _emu_lib()
+
+    def run(t0, t1, start, target, h, r, t):
+        out = np.zeros((len(t), 16))
+        lib.emu_foot_trajectory.argtypes = [C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        assert lib.emu_foot_trajectory(len(t), t0, t1, start.ctypes.data, target.ctypes.data, h, r, t.ctypes.data, out.ctypes.data) == 0
+        return out
+
+    _device_foot_trajectory(run, tag, rr)
+
+
+def test_device_footstep_planner_code_matches_the_reference_plan():
+    lib, C = _emu_lib()
+
+    def run(path, n_pts, init, L, W, max_steps):
+        n = path.shape[0]
+        steps, ns = np.zeros((n, max_steps, 4)), np.zeros(n, np.int32)
+        lib.emu_footstep_plan.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int]
+        assert lib.emu_footstep_plan(n, path.ctypes.data, n_pts.ctypes.data, path.shape[1], init.ctypes.data, L, W, steps.ctypes.data,
+                                     ns.ctypes.data, max_steps) == 0
+        return steps, ns
+
+    _device_footstep_plan(run)

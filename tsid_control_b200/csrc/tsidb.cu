@@ -804,6 +804,32 @@ extern "C" int tsidb_diagnostics(tsidb_handle* h, int n_envs, const tsidb_aux_ou
   return 0;
 }
 
+extern "C" int tsidb_foot_trajectory(tsidb_handle* h, int n_envs, double t0, double t1, const double* start4, const double* target4,
+                                     double step_height, double rise_ratio, const double* t, double* out16, void* cuda_stream) {
+  if (!h || !start4 || !target4 || !t || !out16) { g_err = "tsidb_foot_trajectory: null argument"; return -1; }
+  if (n_envs <= 0 || !(t1 > t0) || !(rise_ratio > 0.0) || !(rise_ratio < 1.0)) { g_err = "tsidb_foot_trajectory: bad n_envs / knots / rise_ratio"; return -1; }
+  CK(cudaSetDevice(h->device));
+  const int th = 128;
+  tsidb_foot_trajectory_kernel<<<(n_envs + th - 1) / th, th, 0, (cudaStream_t)cuda_stream>>>(n_envs, t0, t1, start4, target4, step_height,
+                                                                                              rise_ratio, t, out16);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+extern "C" int tsidb_footstep_plan(tsidb_handle* h, int n_envs, const double* path, const int32_t* n_pts, int max_pts, const double* init8,
+                                   double step_length, double step_width, double* steps, int32_t* n_steps, int max_steps, void* cuda_stream) {
+  if (!h || !path || !init8 || !steps || !n_steps) { g_err = "tsidb_footstep_plan: null argument"; return -1; }
+  if (n_envs <= 0 || max_pts < 2 || max_steps < 3 || !(step_length > 0.0)) { g_err = "tsidb_footstep_plan: bad sizes"; return -1; }
+  CK(cudaSetDevice(h->device));
+  const int th = 64;
+  tsidb_footstep_plan_kernel<<<(n_envs + th - 1) / th, th, 0, (cudaStream_t)cuda_stream>>>(n_envs, path, n_pts, max_pts, init8, step_length,
+                                                                                            step_width, steps, n_steps, max_steps);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
 extern "C" int tsidb_ci_row(const tsidb_handle* h, int block, int side, int i) {
   if (!h || block < 0 || block > 3 || side < 0 || side > 1 || i < 0) return -1;
   const int na = h->dc.na, nv = h->dc.nv;

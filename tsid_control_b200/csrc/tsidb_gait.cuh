@@ -124,6 +124,98 @@ TSIDB_DEV void gait_step_env(const GaitConf& G, const GaitState& S, const double
   if (S.fails && status && status[e] != 0) S.fails[e] += 1;
 }
 
+/* ---- the reference's planners, one thread per env -------------------------------------------
+ * Both are pinned to the reference's own Python through tests/golden/planners.npz (generated by importing
+ * ref:ctrl/Foot_Trajectory.py and ref:ctrl/Footstep_Planner.py, tests/golden/make_planner_golden.py). */
+#ifdef TSIDB_EMU
+#define TS_MUL(a, b) ((a) * (b))
+#define TS_ADD(a, b) ((a) + (b))
+#else
+#define TS_MUL(a, b) __dmul_rn(a, b) /* no FMA contraction where a threshold decides (numpy rounds every product) */
+#define TS_ADD(a, b) __dadd_rn(a, b)
+#endif
+
+/* FootTrajectory (ref:ctrl/Foot_Trajectory.py:6-43) at time t: x, y, yaw are 2-knot CubicSplines = straight lines;
+ * z is the spline through (t0, z0), (t0 + T/2, z0 + h), (t1, z1) when rise_ratio == 0.5 and through
+ * (t0, z0), (t0 + r T, z0 + h), (t1 - r T, z1 + h), (t1, z1) otherwise; with scipy's not-a-knot ends a spline through
+ * <= 4 knots is ONE polynomial, evaluated here from Newton divided differences.  start/target = (x, y, z, yaw).
+ * out[16] = value, 1st, 2nd, 3rd derivative of (x, y, z, yaw).  (The reference's get_velocity / get_acceleration
+ * return the 2nd and 3rd derivative, :35,:43; a TSID foot reference needs the 1st and 2nd — all four are here.) */
+TSIDB_DEV void foot_trajectory_eval(double t0, double t1, const double* start, const double* target, double h, double rr,
+                                    double t, double* out) {
+  const double T = t1 - t0, u = t - t0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (k == 2) continue;
+    const double c1 = (target[k] - start[k]) / T;
+    out[k] = start[k] + c1 * u; out[4 + k] = c1; out[8 + k] = 0.0; out[12 + k] = 0.0;
+  }
+  double a0, a1, a2, a3;
+  if (rr != 0.5) {
+    const double u1 = T * rr, u2 = T - T * rr, u3 = T;
+    const double y0 = start[2], y1 = start[2] + h, y2 = target[2] + h, y3 = target[2];
+    const double d01 = (y1 - y0) / u1, d12 = (y2 - y1) / (u2 - u1), d23 = (y3 - y2) / (u3 - u2);
+    const double d012 = (d12 - d01) / u2, d123 = (d23 - d12) / (u3 - u1);
+    const double d0123 = (d123 - d012) / u3;
+    /* c0 + c1 u + c2 u (u - u1) + c3 u (u - u1) (u - u2) in powers of u */
+    a0 = y0; a1 = d01 - d012 * u1 + d0123 * u1 * u2; a2 = d012 - d0123 * (u1 + u2); a3 = d0123;
+  } else {
+    const double u1 = T * rr, u2 = T;
+    const double y0 = start[2], y1 = start[2] + h, y2 = target[2];
+    const double d01 = (y1 - y0) / u1, d12 = (y2 - y1) / (u2 - u1);
+    const double d012 = (d12 - d01) / u2;
+    a0 = y0; a1 = d01 - d012 * u1; a2 = d012; a3 = 0.0;
+  }
+  out[2] = ((a3 * u + a2) * u + a1) * u + a0;
+  out[6] = (3.0 * a3 * u + 2.0 * a2) * u + a1;
+  out[10] = 6.0 * a3 * u + 2.0 * a2;
+  out[14] = 6.0 * a3;
+}
+
+/* FootstepPlanner.add_step (ref:ctrl/Footstep_Planner.py:74-90): out = (x, y, yaw, side) */
+TSIDB_DEV void footstep_add(double dx, double dy, int side, double px, double py, double L, double W, double* out) {
+  const double nrm = sqrt(TS_ADD(TS_MUL(dx, dx), TS_MUL(dy, dy)));
+  const double tx = dx / nrm, ty = dy / nrm;
+  const double sw = W / 2 * (side == 0 ? 1.0 : -1.0);
+  out[0] = TS_ADD(TS_ADD(px, TS_MUL(tx, L / 2)), TS_MUL(-ty, sw));
+  out[1] = TS_ADD(TS_ADD(py, TS_MUL(ty, L / 2)), TS_MUL(tx, sw));
+  out[2] = atan2(dy, dx);
+  out[3] = (double)side;
+}
+/* FootstepPlanner.plan (ref:ctrl/Footstep_Planner.py:92-125) for one env: path [n_pts][2], init [2][4] the two initial
+ * supports (x, y, yaw, side); steps [max_steps][4]; returns the number of footsteps (the initial supports included),
+ * or -1 when max_steps is too small. */
+TSIDB_DEV int footstep_plan_env(const double* path, int n_pts, const double* init, double L, double W, double* steps, int max_steps) {
+  if (max_steps < 2 || n_pts < 2) return -1;
+  for (int k = 0; k < 8; k++) steps[k] = init[k];
+  int ns = 2;
+  int side = (int)init[7];
+  double distance = 0.0, dx = 0.0, dy = 0.0;
+  for (int i = 0; i < n_pts - 1; i++) {
+    dx = path[2 * (i + 1)] - path[2 * i];
+    dy = path[2 * (i + 1) + 1] - path[2 * i + 1];
+    distance = TS_ADD(distance, sqrt(TS_ADD(TS_MUL(dx, dx), TS_MUL(dy, dy))));
+    if (distance >= L) {
+      side = !side;
+      if (ns >= max_steps) return -1;
+      footstep_add(dx, dy, side, path[2 * i], path[2 * i + 1], L, W, steps + 4 * ns);
+      ns++;
+      distance = 0.0;
+    }
+  }
+  side = !side;
+  if (ns >= max_steps) return -1;
+  footstep_add(dx, dy, side, path[2 * (n_pts - 1)], path[2 * (n_pts - 1) + 1], L, W, steps + 4 * ns);
+  ns++;
+  if (distance > 0) {
+    side = !side;
+    if (ns >= max_steps) return -1;
+    footstep_add(dx, dy, side, path[2 * (n_pts - 1)], path[2 * (n_pts - 1) + 1], L, W, steps + 4 * ns);
+    ns++;
+  }
+  return ns;
+}
+
 /* per-env diagnostics of one tick from its auxiliary outputs:
  *   cop[3]   centre of pressure, ref:ctrl/WalkController.py:255-289: per foot in contact with f_z > 1e-3 the local
  *            CoP (w[4]/w[2], w[3]/w[2], 0) from the wrench w = T f, mapped to the world by the sole placement,
@@ -171,6 +263,19 @@ __global__ void tsidb_diagnostics_kernel(int n, const double* com9, const double
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   diagnostics_env(com9, foot_lf12, foot_rf12, wrench12, mask, w, cop, cp, poly, e);
+}
+__global__ void tsidb_foot_trajectory_kernel(int n, double t0, double t1, const double* start4, const double* target4, double h,
+                                            double rr, const double* t, double* out16) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  foot_trajectory_eval(t0, t1, start4 + 4 * (size_t)e, target4 + 4 * (size_t)e, h, rr, t[e], out16 + 16 * (size_t)e);
+}
+__global__ void tsidb_footstep_plan_kernel(int n, const double* path, const int32_t* n_pts, int max_pts, const double* init8,
+                                           double L, double W, double* steps, int32_t* n_steps, int max_steps) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  n_steps[e] = footstep_plan_env(path + 2 * (size_t)max_pts * e, n_pts ? n_pts[e] : max_pts, init8 + 8 * (size_t)e, L, W,
+                                 steps + 4 * (size_t)max_steps * e, max_steps);
 }
 __global__ void tsidb_gait_reset_kernel(int n, GaitConf G, GaitState S, const double* defaults /* 9+24+24+12+12 */,
                                         const double* phase0, const double* vcmd) {

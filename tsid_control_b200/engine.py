@@ -285,6 +285,35 @@ class TsidEngine:
         check(self.lib.tsidb_gait_step(self.h, n, foot_lf_now.data_ptr(), foot_rf_now.data_ptr(),
                                        status.data_ptr() if status is not None else None, self._stream()), "tsidb_gait_step")
 
+    def foot_trajectory(self, t0: float, t1: float, start: torch.Tensor, target: torch.Tensor, step_height: float,
+                        rise_ratio: float, t: torch.Tensor) -> torch.Tensor:
+        """FootTrajectory([t0, t1], start, target, step_height, rise_ratio) of ref:ctrl/Foot_Trajectory.py:6-43 evaluated
+        per env on the device: start/target [N,4] = (x, y, z, yaw), t [N]; returns [N,4,4]: value and the first three
+        derivatives (axis 1) of (x, y, z, yaw) (axis 2)."""
+        n = start.shape[0]
+        self._chk(start, n, 4, "start")
+        self._chk(target, n, 4, "target")
+        self._chk(t.reshape(n, 1), n, 1, "t")
+        out = torch.empty((n, 16), dtype=torch.float64, device=self.device)
+        check(self.lib.tsidb_foot_trajectory(self.h, n, float(t0), float(t1), start.data_ptr(), target.data_ptr(), float(step_height),
+                                             float(rise_ratio), t.data_ptr(), out.data_ptr(), self._stream()), "tsidb_foot_trajectory")
+        return out.reshape(n, 4, 4)
+
+    def footstep_plan(self, path: torch.Tensor, init_supports: torch.Tensor, step_length: float, step_width: float,
+                      n_pts: Optional[torch.Tensor] = None, max_steps: int = 64) -> Tuple[torch.Tensor, torch.Tensor]:
+        """FootstepPlanner(step_width, step_length).plan(path, init_supports) of ref:ctrl/Footstep_Planner.py:92-125 per env
+        on the device: path [N,P,2], init_supports [N,2,4] = (x, y, yaw, side); returns (steps [N,max_steps,4],
+        n_steps [N] int32)."""
+        n, P = path.shape[0], path.shape[1]
+        self._chk(path.reshape(n, 2 * P), n, 2 * P, "path")
+        self._chk(init_supports.reshape(n, 8), n, 8, "init_supports")
+        steps = torch.zeros((n, max_steps, 4), dtype=torch.float64, device=self.device)
+        ns = torch.zeros(n, dtype=torch.int32, device=self.device)
+        check(self.lib.tsidb_footstep_plan(self.h, n, path.data_ptr(), n_pts.data_ptr() if n_pts is not None else None, P,
+                                           init_supports.data_ptr(), float(step_length), float(step_width), steps.data_ptr(),
+                                           ns.data_ptr(), int(max_steps), self._stream()), "tsidb_footstep_plan")
+        return steps, ns
+
     def rollout(self, q: torch.Tensor, v: torch.Tensor, n_steps: int, use_graph: bool = True) -> TickOutput:
         """n_steps closed-loop ticks on the device (tick -> integrate_dv -> gait step), q and v advanced in place;
         returns the last step's outputs (tau, ddq, f, status, iters; the engine's cached buffers, overwritten by the
