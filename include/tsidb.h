@@ -147,6 +147,12 @@ typedef struct tsidb_aux_out {
   double* foot_lf;    /* [12] sole placement (p, R col-major)  robot.framePosition ref:main.py:139 */
   double* foot_rf;    /* [12]                                                     ref:main.py:141 */
   double* wrench;     /* [12] T*f per foot (LF 6, RF 6), the f_lf/f_rf of ref:ctrl/WalkController.py:263,273 */
+  /* sol.lambda [UPSTREAM HQPOutput]: Lagrange multipliers of the inequality rows in the working set, in working-set
+   * order, and the row each one belongs to (tsidb_ci_row numbering, -1 = unused slot); zero / -1 when status != 0.
+   * The multipliers of the always-active equalities are not formed: the equalities are eliminated, not added one
+   * by one (the reference itself never reads sol.lambda). */
+  double* lambda;      /* [32] always row-major [N][32] */
+  int32_t* lambda_row; /* [32] always row-major [N][32] */
 } tsidb_aux_out;
 
 /* ---- lifecycle ------------------------------------------------------------------ */

@@ -224,6 +224,8 @@ def compare_outputs(kind, q, v, mask, refs, out, threads=8, overrides=(), truth=
     res.update(active_set_report(s["oracle"], mask, np.where(ok)[0],
                                  lambda i: bits_to_rows(na, nv, words_to_bits(out["active_set"][:, i])),
                                  ref["active"], out["f"], ref["f"], out["iters"], ref["iters"]))
+    if out.get("lam") is not None:
+        res.update(lambda_report(s["oracle"], mask, np.where(ok)[0], ref, out["lam"], out["lam_row"], na, nv))
     res["mean_iters"] = float(np.mean(out["iters"]))
     blocks = np.zeros(4, np.int64)
     for i in np.where(ok)[0]:
@@ -262,6 +264,30 @@ def assert_parity(res, kind="v1"):
     # force generator (cond ~ 1e8): 1e-7 .. 7e-5 of noise in fp64 depending on the active set (measured for the fp64
     # oracle against its 80-bit build, profiles/parity_r02.json: oracle_f_truth); bar 1e-4
     assert res["f_truth"] <= 1e-4 and res["f"] <= 1e-4 + res["oracle_f_truth"], res
+    if "lambda" in res:  # multipliers of the inequality rows (sol.lambda), envs with identical raw working sets
+        assert res["lambda"] <= 1e-6 and res["lambda_min"] >= -1e-9 and res["lambda_envs_compared"] > 0, res
     assert res["n_unexplained"] == 0, res
     assert res["active_canonical"] == 1.0, res
     assert res["iters_equal_where_exact"] >= 0.95, res
+
+
+def lambda_report(orc, mask, ok_idx, ref, lam_dev, lam_row_dev, na, nv):
+    """sol.lambda: multipliers of the inequality rows in the working set.  For every env whose raw working set equals
+    the oracle's, the multipliers are compared row by row (err = |a-b| / (1e-2 + |b|)); all multipliers must be >= 0
+    (dual feasibility) up to rounding."""
+    worst, n_cmp, min_lam = 0.0, 0, 0.0
+    for i in ok_idx:
+        rows = orc.ci_rows(int(mask[i]))
+        nc = (int(mask[i]) & 1) + ((int(mask[i]) >> 1) & 1)
+        neq = 6 + 6 * nc
+        ra = {rows[k]: ref["lam"][i][neq + j] for j, k in enumerate(ref["active"][i])}
+        used = lam_row_dev[i] >= 0
+        rb = dict(zip(bits_to_rows(na, nv, [int(b) for b in lam_row_dev[i][used]]), lam_dev[i][used]))
+        if rb:
+            min_lam = min(min_lam, min(rb.values()))
+        if set(ra) != set(rb):
+            continue
+        n_cmp += 1
+        for r, a in ra.items():
+            worst = max(worst, abs(rb[r] - a) / (1e-2 + abs(a)))
+    return {"lambda_envs_compared": n_cmp, "lambda": worst, "lambda_min": float(min_lam)}

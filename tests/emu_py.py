@@ -23,7 +23,7 @@ class TickArgs(C.Structure):
         ("r_com", C.c_void_p), ("r_foot", C.c_void_p * 2), ("r_contact", C.c_void_p * 2), ("r_posture", C.c_void_p),
         ("tau", C.c_void_p), ("ddq", C.c_void_p), ("f", C.c_void_p),
         ("status", C.c_void_p), ("iters", C.c_void_p), ("active", C.c_void_p),
-        ("o_com", C.c_void_p), ("o_foot", C.c_void_p * 2), ("o_wrench", C.c_void_p),
+        ("o_com", C.c_void_p), ("o_foot", C.c_void_p * 2), ("o_wrench", C.c_void_p), ("o_lambda", C.c_void_p), ("o_lambda_row", C.c_void_p),
         ("counter", C.c_void_p), ("ws", C.c_void_p), ("ws3", C.c_void_p), ("perm", C.c_void_p), ("kin_only", C.c_int32), ("slot", C.c_int32),
     ]
 
@@ -67,7 +67,7 @@ class Emu:
         out = {"tau": np.zeros(shape(na)), "ddq": np.zeros(shape(nv)), "f": np.zeros(shape(24)),
                "status": np.full(N, -7, np.int32), "iters": np.zeros(N, np.int32), "active": np.zeros((3, N), np.uint64),
                "com": np.zeros(shape(9)), "foot_lf": np.zeros(shape(12)), "foot_rf": np.zeros(shape(12)),
-               "wrench": np.zeros(shape(12))}
+               "wrench": np.zeros(shape(12)), "lambda": np.zeros((N, 32)), "lambda_row": np.full((N, 32), -1, np.int32)}
         a = TickArgs()
         a.n_envs, a.layout, a.kin_only, a.slot = N, layout, int(kin_only), 0
         a.q, a.v, a.mask = qd.ctypes.data, vd.ctypes.data, md.ctypes.data
@@ -83,6 +83,7 @@ class Emu:
         a.status, a.iters, a.active = out["status"].ctypes.data, out["iters"].ctypes.data, out["active"].ctypes.data
         if aux:
             a.o_com, a.o_wrench = out["com"].ctypes.data, out["wrench"].ctypes.data
+            a.o_lambda, a.o_lambda_row = out["lambda"].ctypes.data, out["lambda_row"].ctypes.data
             a.o_foot[0], a.o_foot[1] = out["foot_lf"].ctypes.data, out["foot_rf"].ctypes.data
         sm = np.zeros(self.sm_per_env)
         rc = self.lib.emu_tick(C.byref(a), sm.ctypes.data)

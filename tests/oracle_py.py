@@ -210,6 +210,7 @@ class Oracle:
             "tau": np.array([o["tau"] for o in outs]), "dv": np.array([o["dv"] for o in outs]),
             "f": np.array([o["f"] for o in outs]), "active": [o["active"] for o in outs],
             "com": np.array([o["com"] for o in outs]), "foot": np.array([o["foot"] for o in outs]),
+            "lam": [o["lam"] for o in outs],  # sol.lambda: [equalities (6 + 6 nc); active inequalities in working-set order]
         }
 
     def timed_batch(self, q, v, mask, refs: dict, n_threads: int):

@@ -493,6 +493,11 @@ def test_mixed_models_two_handles_config5():
         assert np.array_equal(getattr(o1, k).cpu().numpy(), solo1[k]), k
         assert np.array_equal(getattr(o0, k).cpu().numpy(), solo0[k]), k
     assert solo1["tau"].shape[1] == 20 and solo0["tau"].shape[1] == 18
+    # and both agree with the oracle (same parity rules as the single-model configs)
+    for kind, qq, vv, mm, rr, solo in (("v1", q1, v1, m1, r1, solo1), ("v0", q0, v0, m0, r0, solo0)):
+        res, _ = compare_outputs(kind, qq, vv, mm, rr, solo, threads=THREADS)
+        parity_log.record(f"test_mixed_models_two_handles_config5[{kind}]", res)
+        assert_parity(res, kind)
 
 
 def test_device_diagnostics_match_the_reference_formulas():

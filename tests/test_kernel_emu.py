@@ -124,7 +124,8 @@ def test_emulated_kernel_with_active_joint_velocity_bounds(overrides):
     q, v = synth.random_states(s["q0"], n, 33)
     mask, refs = synth.walking_batch(s["refs"], n, 33, 0.3, 0.2, 0.2, 0.5, float(s["refs"]["com"][2]))
     out = emu.tick(q, v, mask, refs)
-    out["active_set"] = out["active"]
+    out["active_set"], out["lam"], out["lam_row"] = out["active"], out["lambda"], out["lambda_row"]
     res, ref = compare_outputs("v1", q, v, mask, refs, out, overrides=overrides)
+    assert res["lambda_envs_compared"] >= 30
     assert_parity(res, "v1")
     assert res["envs_with_active_force_lf_rf_torque_jointvel_rows"][3] >= 8

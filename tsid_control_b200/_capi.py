@@ -95,6 +95,8 @@ class TsidbAuxOut(C.Structure):
         ("foot_lf", C.c_void_p),
         ("foot_rf", C.c_void_p),
         ("wrench", C.c_void_p),
+        ("lambda_", C.c_void_p),
+        ("lambda_row", C.c_void_p),
     ]
 
 

@@ -457,7 +457,7 @@ extern "C" int tsidb_compute(tsidb_handle* h, int n_envs, int layout, const doub
     a.r_contact[0] = refs->contact_lf; a.r_contact[1] = refs->contact_rf; a.r_posture = refs->posture;
   }
   a.tau = tau; a.ddq = ddq; a.f = f; a.status = status; a.iters = iters; a.active = active_set;
-  if (aux) { a.o_com = aux->com; a.o_foot[0] = aux->foot_lf; a.o_foot[1] = aux->foot_rf; a.o_wrench = aux->wrench; }
+  if (aux) { a.o_com = aux->com; a.o_foot[0] = aux->foot_lf; a.o_foot[1] = aux->foot_rf; a.o_wrench = aux->wrench; a.o_lambda = aux->lambda; a.o_lambda_row = aux->lambda_row; }
   return launch_tick(h, a, (cudaStream_t)cuda_stream);
 }
 

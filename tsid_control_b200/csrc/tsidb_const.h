@@ -121,6 +121,8 @@ struct TickArgs {
   double* o_com;      /* aux outputs, may be null */
   double* o_foot[2];
   double* o_wrench;
+  double* o_lambda;       /* [N][32] multipliers of the working set, may be null */
+  int32_t* o_lambda_row;  /* [N][32] their rows (tsidb_ci_row numbering), may be null */
   int32_t* counter;   /* dynamic work counter of the active-set kernel */
   double* ws;         /* hand-off images of the active-set kernel, SA_IMAGE doubles per slot */
   double* ws3;        /* assembly images dynamics -> elimination kernel, SE_IMAGE doubles per slot */

@@ -1486,7 +1486,7 @@ TSIDB_DEV int warp_argmin_fast(double val, bool valid, int tiebreak) {
 
 template <int NV, int NC>
 TSIDB_DEV int as_solve2(const DevConst& C, const ASCtx& S, const LaneConst& K, int lane, int mask, double c1c2, double trH,
-                        double R_norm, int& iters_out, uint64_t* act_words) {
+                        double R_norm, int& iters_out, uint64_t* act_words, double& lam_out, int& lam_row_out) {
   typedef AL<NV, NC> LA;
   constexpr int nv = NV, na = NV - 6, n = LA::n, m = LA::m, ldj = LA::ldj;
   double* J2 = S.J2;
@@ -1834,7 +1834,10 @@ TSIDB_DEV int as_solve2(const DevConst& C, const ASCtx& S, const LaneConst& K, i
     if (done) break;
   } /* l1 */
   iters_out = iter;
+  lam_out = 0.0;
+  lam_row_out = -1;
   if (status == ST_OPTIMAL || status == ST_MAX_ITER) {
+    if (lane < iq) { lam_out = ur; lam_row_out = cid_bit(na, nv, Ar); } /* sol.lambda: position `lane` of the working set */
     uint64_t w0 = 0, w1 = 0, w2 = 0;
     for (int i = 0; i < iq; i++) {
       const int bit = cid_bit(na, nv, __shfl_sync(FULL, Ar, i));
@@ -2131,7 +2134,9 @@ TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const 
   int iters = 0;
   uint64_t words[3] = {0, 0, 0};
   int status = err;
-  if (err == ST_OPTIMAL) status = as_solve2<NV, NC>(C, S, K, lane, mask, c1c2, c1, R_norm, iters, words);
+  double lam = 0.0;
+  int lam_row = -1;
+  if (err == ST_OPTIMAL) status = as_solve2<NV, NC>(C, S, K, lane, mask, c1c2, c1, R_norm, iters, words, lam, lam_row);
   const bool ok = (status == ST_OPTIMAL || status == ST_MAX_ITER);
   const double* x = S.x;
   double* wr = S.wr;
@@ -2159,6 +2164,8 @@ TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const 
     a.tau[eidx(a, env, lane, na)] = val;
   }
   if (a.o_wrench && lane < 12) a.o_wrench[eidx(a, env, lane, 12)] = ok ? wr[lane] : 0.0;
+  if (a.o_lambda) a.o_lambda[(size_t)env * 32 + lane] = lam;
+  if (a.o_lambda_row) a.o_lambda_row[(size_t)env * 32 + lane] = lam_row;
   if (lane == 0) {
     a.status[env] = status;
     a.iters[env] = iters;

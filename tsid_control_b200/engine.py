@@ -22,7 +22,7 @@ class TickOutput:
     """Result of one batched tick: what `sol` + the decode calls give in the reference
     (ref:main.py:121-127), for N envs."""
 
-    __slots__ = ("tau", "ddq", "f", "status", "iters", "active_set", "com", "foot_lf", "foot_rf", "wrench")
+    __slots__ = ("tau", "ddq", "f", "status", "iters", "active_set", "com", "foot_lf", "foot_rf", "wrench", "lam", "lam_row")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -80,6 +80,7 @@ class TsidEngine:
                 "active_set": torch.empty((3, n), dtype=torch.int64, device=self.device),
                 "com": torch.empty((n, 9), **f64), "foot_lf": torch.empty((n, 12), **f64),
                 "foot_rf": torch.empty((n, 12), **f64), "wrench": torch.empty((n, 12), **f64),
+                "lam": torch.empty((n, 32), **f64), "lam_row": torch.empty((n, 32), dtype=torch.int32, device=self.device),
             }
             # a few sizes stay resident (a single-robot kinematics()/solve() call between two batched ticks must
             # not evict the batch's buffers); the least recently created goes first
@@ -91,7 +92,7 @@ class TsidEngine:
     def _tick_output(self, o: dict, aux: bool, want_active: bool) -> TickOutput:
         """Fields the call did not write are None (never a stale or uninitialised buffer)."""
         keys = ["tau", "ddq", "f", "status", "iters"] + (["active_set"] if want_active else []) + \
-               (["com", "foot_lf", "foot_rf", "wrench"] if aux else [])
+               (["com", "foot_lf", "foot_rf", "wrench", "lam", "lam_row"] if aux else [])
         return TickOutput(**{k: o[k] for k in keys})
 
     # ------------------------------------------------------------------ API
@@ -126,6 +127,7 @@ class TsidEngine:
         a = TsidbAuxOut()
         if aux:
             a.com, a.foot_lf, a.foot_rf, a.wrench = (o[k].data_ptr() for k in ("com", "foot_lf", "foot_rf", "wrench"))
+            a.lambda_, a.lambda_row = o["lam"].data_ptr(), o["lam_row"].data_ptr()
         check(self.lib.tsidb_compute(
             self.h, n, 0, q.data_ptr(), v.data_ptr(), contact_mask.data_ptr() if contact_mask is not None else None,
             C.byref(r), o["tau"].data_ptr(), o["ddq"].data_ptr(), o["f"].data_ptr(), o["status"].data_ptr(),
