@@ -36,7 +36,7 @@ def test_every_declared_entry_point_is_exported(lib):
 def test_struct_mirrors_match_the_header_layout():
     B, NA = 24, 23
     assert C.sizeof(_capi.TsidbModel) == 8 * ((4 + 4 * B + 7) // 8) + 8 * (9 * B + 3 * B + B + 3 * B + 9 * B) + 8 + 8 * (18 + 6 + 3)
-    assert C.sizeof(_capi.TsidbRefs) == 6 * 8 and C.sizeof(_capi.TsidbAuxOut) == 4 * 8
+    assert C.sizeof(_capi.TsidbRefs) == 6 * 8 and C.sizeof(_capi.TsidbAuxOut) == 6 * 8
     assert C.sizeof(_capi.TsidbGaitConf) == 5 * 8
     fixed = 12 + 3 + 3 + 6 + 6 + 1 + 6 + 1 + 6 + 6 + 1 + 3 + 3 + 1 + 2 * NA + 1 + 3  # doubles up to kp_am
     assert C.sizeof(_capi.TsidbConf) == 8 * (fixed + 1 + 2 * NA + 1 + 2 * NA + 1 + 1 + 1)
