@@ -295,6 +295,14 @@ int tsidb_last_tick_ms(tsidb_handle* h, float* ms5);
  * get_acceleration return the 2nd and 3rd derivative, :35,:43.)  All arrays are device pointers. */
 int tsidb_foot_trajectory(tsidb_handle* h, int n_envs, double t0, double t1, const double* start4, const double* target4,
                           double step_height, double rise_ratio, const double* t, double* out16, void* cuda_stream);
+/* tsidb_gait_set_plan: hand a footstep plan (the output of tsidb_footstep_plan, device pointers; copied) to the gait
+ * phase machine: from then on the swing foot of every gait step goes to the env's next footstep of that side along
+ * FootTrajectory([0, step_duration], start, target, step_height, rise_ratio) — x, y and yaw linear in time, z the 3-
+ * or 4-knot spline — with the first and second derivatives as the velocity / acceleration reference of the foot
+ * task; an exhausted plan sets the foot down where it is.  steps == NULL returns to straight steps along x.  Needs
+ * tsidb_gait_reset first (n_envs <= its n_envs). */
+int tsidb_gait_set_plan(tsidb_handle* h, int n_envs, const double* steps, const int32_t* n_steps, int max_steps,
+                        double rise_ratio, void* cuda_stream);
 /* tsidb_footstep_plan: FootstepPlanner(step_width, step_length).plan(path, init_supports) of
  * ref:ctrl/Footstep_Planner.py:92-125 per env: path [N][max_pts][2] with n_pts[e] valid points (null: max_pts for
  * every env), init8 [N][2][4] the two initial supports (x, y, yaw, side 0 = left / 1 = right), steps

@@ -132,11 +132,15 @@ extern "C" int emu_sm_per_env() { return a_layout(TSIDB_NVX, 2).per_env > e_per_
 extern "C" int emu_gait(int n, const double* gconf6, double* phi, uint8_t* mask, double* vcmd, double* lipm, double* origin,
                         double* com, double* foot_lf, double* foot_rf, double* contact_lf, double* contact_rf, int32_t* fails,
                         const double* defaults81, const double* phase0, const double* vcmd0, const double* foot_now_lf,
-                        const double* foot_now_rf, const int32_t* status) {
-  GaitConf G{gconf6[0], gconf6[1], gconf6[2], gconf6[3], gconf6[4], gconf6[5]};
-  GaitState S{phi, mask, vcmd, lipm, origin, com, {foot_lf, foot_rf}, {contact_lf, contact_rf}, fails};
+                        const double* foot_now_rf, const int32_t* status, const double* steps, const int32_t* n_steps,
+                        int32_t* step_idx, double* swing, int max_steps, double rise_ratio) {
+  GaitConf G{gconf6[0], gconf6[1], gconf6[2], gconf6[3], gconf6[4], gconf6[5], rise_ratio, max_steps, 0};
+  GaitState S{phi, mask, vcmd, lipm, origin, com, {foot_lf, foot_rf}, {contact_lf, contact_rf}, fails, steps, n_steps, step_idx, swing};
   for (int e = 0; e < n; e++) {
-    if (defaults81) gait_reset_env(G, S, defaults81, defaults81 + 9, defaults81 + 33, defaults81 + 57, defaults81 + 69, phase0, vcmd0, e);
+    if (defaults81) {
+      gait_reset_env(G, S, defaults81, defaults81 + 9, defaults81 + 33, defaults81 + 57, defaults81 + 69, phase0, vcmd0, e);
+      if (steps) gait_plan_init_env(G, S, e); /* tsidb_gait_set_plan right after the reset */
+    }
     else gait_step_env(G, S, foot_now_lf, foot_now_rf, status, e);
   }
   return 0;

@@ -110,8 +110,14 @@ class EmuGait:
     """Host build of the device gait phase machine (tsidb_gait.cuh via tests/emu): same state arrays as the
     library keeps on the device."""
 
-    def __init__(self, n, dt, step_duration, step_length, step_height, com_height, defaults, phase0=None, vcmd=None):
+    def __init__(self, n, dt, step_duration, step_length, step_height, com_height, defaults, phase0=None, vcmd=None,
+                 steps=None, n_steps=None, rise_ratio=0.5):
         self.lib = C.CDLL(build_emu())
+        self.steps = None if steps is None else np.ascontiguousarray(steps, np.float64)
+        self.n_steps = None if n_steps is None else np.ascontiguousarray(n_steps, np.int32)
+        self.step_idx = np.full(n, 2, np.int32)
+        self.swing = np.zeros((n, 2, 8))
+        self.rise_ratio = float(rise_ratio)
         self.n = n
         self.g = np.array([dt, step_duration, step_length, step_height, 9.80665 / com_height, defaults["com"][2]], np.float64)
         z = lambda *s: np.zeros(s, np.float64)
@@ -125,10 +131,11 @@ class EmuGait:
 
     def _call(self, d, p0, vc, fl, fr, st):
         ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
-        self.lib.emu_gait.argtypes = [C.c_int] + [C.c_void_p] * 18
+        self.lib.emu_gait.argtypes = [C.c_int] + [C.c_void_p] * 22 + [C.c_int, C.c_double]
         rc = self.lib.emu_gait(self.n, ptr(self.g), ptr(self.phi), ptr(self.mask), ptr(self.vcmd), ptr(self.lipm), ptr(self.origin),
                                ptr(self.com), ptr(self.foot[0]), ptr(self.foot[1]), ptr(self.contact[0]), ptr(self.contact[1]),
-                               ptr(self.fails), ptr(d), ptr(p0), ptr(vc), ptr(fl), ptr(fr), ptr(st))
+                               ptr(self.fails), ptr(d), ptr(p0), ptr(vc), ptr(fl), ptr(fr), ptr(st), ptr(self.steps), ptr(self.n_steps),
+                               ptr(self.step_idx), ptr(self.swing), 0 if self.steps is None else self.steps.shape[1], self.rise_ratio)
         assert rc == 0
 
     def step(self, foot_now_lf, foot_now_rf, status=None):

@@ -14,7 +14,14 @@ def mask_of(phi):
 
 
 class GaitRef:
-    def __init__(self, n, dt, step_duration, step_length, step_height, com_height, defaults, phase0=None, vcmd=None):
+    def __init__(self, n, dt, step_duration, step_length, step_height, com_height, defaults, phase0=None, vcmd=None,
+                 steps=None, n_steps=None, rise_ratio=0.5):
+        """steps [n,S,4] / n_steps [n]: a footstep plan (FootstepPlanner.plan) -> planned mode: every swing is this repo's
+        FootTrajectory (pinned to the reference's scipy splines by tests/golden/planners.npz) from the lift-off placement
+        to the env's next footstep of that side."""
+        self.steps, self.n_steps, self.rr = steps, n_steps, rise_ratio
+        self.step_idx = np.full(n, 2, np.int64)
+        self.swing = [[None, None] for _ in range(n)]
         self.n, self.dt, self.T, self.L, self.h = n, dt, step_duration, step_length, step_height
         self.w2 = 9.80665 / com_height
         self.com_z = float(defaults["com"][2])
@@ -29,6 +36,43 @@ class GaitRef:
         self.contact = [np.tile(defaults["contact_lf"], (n, 1)).astype(np.float64), np.tile(defaults["contact_rf"], (n, 1)).astype(np.float64)]
         self.origin = [self.foot[0][:, :12].copy(), self.foot[1][:, :12].copy()]
         self.fails = np.zeros(n, np.int32)
+        if steps is not None:  # a plan handed over while a foot is in the air: that swing starts from the standing placement
+            for f in (1, 0):
+                up = (self.mask & (1 << f)) == 0
+                self._begin(f, up, self.origin[f])
+
+    def _begin(self, f, lift, now):
+        from tsid_control_b200.ctrl.Foot_Trajectory import FootTrajectory
+
+        for e in np.where(lift)[0]:
+            idx = int(self.step_idx[e])
+            while idx < self.n_steps[e] and int(self.steps[e, idx, 3]) != f:
+                idx += 1
+            yaw = np.arctan2(now[e, 4], now[e, 3])
+            start = np.array([now[e, 0], now[e, 1], now[e, 2], yaw])
+            if idx < self.n_steps[e]:
+                target = np.array([self.steps[e, idx, 0], self.steps[e, idx, 1], now[e, 2], self.steps[e, idx, 2]])
+                idx += 1
+            else:
+                target = start.copy()
+            self.step_idx[e] = idx
+            self.swing[e][f] = (start, FootTrajectory([0.0, self.T], start, target, self.h, self.rr))
+
+    def _planned(self, f, lift, sw, s, now):
+        self._begin(f, lift, now)
+        fr, org = self.foot[f], self.origin[f]
+        for e in np.where(sw)[0]:
+            start, tj = self.swing[e][f]
+            t = s[e] * self.T
+            fr[e, :3] = tj.get_position(t)
+            dy = tj.yaw(t) - start[3]
+            R0 = org[e, 3:12].reshape(3, 3).T  # column-major
+            Rz = np.array([[np.cos(dy), -np.sin(dy), 0], [np.sin(dy), np.cos(dy), 0], [0, 0, 1]])
+            fr[e, 3:12] = (Rz @ R0).T.ravel()
+            fr[e, 12:15] = tj.velocity(t)
+            fr[e, 15:18] = [0.0, 0.0, tj.yaw(t, 1)]
+            fr[e, 18:21] = tj.acceleration(t)
+            fr[e, 21:24] = [0.0, 0.0, tj.yaw(t, 2)]
 
     def refs(self):
         return {"com": self.com, "foot_lf": self.foot[0], "foot_rf": self.foot[1], "contact_lf": self.contact[0],
@@ -51,6 +95,9 @@ class GaitRef:
             sw = (nm & bit) == 0
             s = (phi - (0.2 if f == 1 else 0.6)) / 0.4
             fr, org = self.foot[f], self.origin[f]
+            if self.steps is not None:
+                self._planned(f, lift, sw, s, now)
+                continue
             fr[sw, 0] = org[sw, 0] + L[sw] * s[sw]
             fr[sw, 1] = org[sw, 1]
             fr[sw, 2] = org[sw, 2] + 4.0 * h * s[sw] * (1.0 - s[sw])

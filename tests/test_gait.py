@@ -65,3 +65,59 @@ def test_swing_reference_is_the_reference_foot_trajectory():
         assert np.abs(ref[12:15] - ft.velocity(t)[:3]).max() < 1e-10
         assert np.abs(ref[18:21] - ft.acceleration(t)[:3]).max() < 1e-9
     assert k > 200
+
+
+def _plans(n, rng):
+    """Per-env footstep plans through the HOST planner (pinned to the reference by tests/golden/planners.npz): a curved
+    path per env, the two initial supports at the standing soles."""
+    from tsid_control_b200.ctrl.Footstep_Planner import Footstep, FootstepPlanner
+
+    S = 40
+    steps, ns = np.zeros((n, S, 4)), np.zeros(n, np.int32)
+    for e in range(n):
+        w = rng.uniform(-0.4, 0.4)
+        x = y = th = 0.0
+        path = []
+        for _ in range(50):
+            x += 0.05 * np.cos(th); y += 0.05 * np.sin(th); th += w * 0.1
+            path.append(np.array([x, y]))
+        init = [Footstep(np.array([0, 0.1]), np.array([0, 0, 0]), 0), Footstep(np.array([0, -0.1]), np.array([0, 0, 0]), 1)]
+        fs = FootstepPlanner(step_width=0.2, step_length=0.3).plan(path, init)
+        ns[e] = len(fs)
+        for k, s_ in enumerate(fs):
+            steps[e, k] = [s_.position[0], s_.position[1], s_.orientation[2], int(s_.side)]
+    return steps, ns
+
+
+def test_emulated_planned_gait_follows_the_footstep_plan_with_yaw_and_four_knot_swing():
+    """Planned mode of the device gait (tsidb_gait_set_plan): every swing goes from the lift-off placement to the env's
+    next planned footstep of that side along FootTrajectory with rise_ratio 0.3 (4-knot z spline), x, y and YAW linear,
+    first/second derivatives as velocity/acceleration references — device code (host build) against the numpy
+    restatement built on this repo's FootTrajectory / FootstepPlanner classes (both pinned to the reference's Python)."""
+    s = setup("v1")
+    n = 24
+    rng = np.random.Generator(np.random.PCG64(11))
+    phase0 = rng.uniform(0, 1, n)
+    h0 = float(s["refs"]["com"][2])
+    steps, ns = _plans(n, rng)
+    a = EmuGait(n, com_height=h0, defaults=s["refs"], phase0=phase0, steps=steps, n_steps=ns, rise_ratio=0.3, **GAIT)
+    b = GaitRef(n, com_height=h0, defaults=s["refs"], phase0=phase0, steps=steps, n_steps=ns, rise_ratio=0.3, **GAIT)
+    ticks = int(3 * 0.5 / 0.4 / 0.002)  # three gait cycles: six swings per env
+    yawed = 0.0
+    for k in range(ticks):
+        # the feet "track" their references of the previous tick (what a converged tick would measure)
+        fl, fr = b.foot[0][:, :12].copy(), b.foot[1][:, :12].copy()
+        a.step(fl, fr)
+        b.step(fl, fr)
+        assert np.array_equal(a.mask, b.mask) and np.array_equal(a.step_idx, b.step_idx)
+        for x, y in ((a.foot[0], b.foot[0]), (a.foot[1], b.foot[1]), (a.contact[0], b.contact[0]), (a.contact[1], b.contact[1]), (a.com, b.com)):
+            assert np.abs(x - y).max() < 1e-11
+        yawed = max(yawed, float(np.abs(a.foot[0][:, 17]).max()))
+    assert (a.step_idx > 4).all() and yawed > 0.05  # plans were consumed and the feet turned (yaw-rate references)
+    # at the end of a swing the foot reference sits on the planned footstep
+    e = 0
+    done = steps[e, :a.step_idx[e]]
+    last = {int(sd): done[done[:, 3] == sd][-1] for sd in (0, 1) if (done[2:, 3] == sd).any()}
+    for f, st in last.items():
+        if a.mask[e] & (1 << f):  # foot f is down: its contact reference is where the swing ended
+            assert np.abs(a.contact[f][e, :2] - st[:2]).max() < 0.02

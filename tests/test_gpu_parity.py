@@ -639,3 +639,63 @@ def test_device_footstep_plan_kernel_against_the_reference_golden():
         return steps.cpu().numpy(), ns.cpu().numpy()
 
     _device_footstep_plan(run)
+
+
+def test_device_rollout_along_a_device_made_footstep_plan():
+    """f1 end to end on the device: tsidb_footstep_plan (FootstepPlanner.plan per env) -> tsidb_gait_set_plan -> tsidb_rollout
+    (tick -> integrate -> phase machine whose swing references are FootTrajectory with yaw and a 4-knot z spline), one CUDA
+    graph replayed — against the same loop driven from the host with the numpy restatement (tests/gait_ref.py, built on the
+    host planner classes that tests/golden/planners.npz pins to the reference's own Python)."""
+    from gait_ref import GaitRef
+    from tsid_control_b200.ctrl.Footstep_Planner import Footstep, FootstepPlanner
+
+    s = setup("v1")
+    n, steps_n = 48, 60
+    ctrl = _controller("v1", n)
+    e, dev, conf = ctrl.engine, ctrl.device, s["conf"]
+    rng = np.random.Generator(np.random.PCG64(77))
+    q, v = synth.random_states(s["q0"], n, 19)
+    v *= 0.2
+    phase0 = rng.uniform(0, 1, n)
+    lf, rf = ctrl.default_refs["foot_lf"], ctrl.default_refs["foot_rf"]
+    P = 40
+    path = np.zeros((n, P, 2))
+    for i in range(n):
+        w, x, y, th = rng.uniform(-0.5, 0.5), 0.0, 0.0, 0.0
+        for k in range(P):
+            x += 0.04 * np.cos(th); y += 0.04 * np.sin(th); th += w * 0.1
+            path[i, k] = (x, y)
+    init = np.tile(np.array([[lf[0], lf[1], 0, 0], [rf[0], rf[1], 0, 1]]), (n, 1, 1))
+    h0 = float(ctrl.default_refs["com"][2])
+    gait = dict(dt=conf.dt, step_duration=conf.step_duration, step_length=conf.step_length, step_height=0.05, com_height=h0)
+    e.gait_reset(n, phase0=torch.as_tensor(phase0, device=dev), **gait)
+    steps_d, ns_d = e.footstep_plan(torch.as_tensor(path, device=dev), torch.as_tensor(init, device=dev), 0.1, 2 * abs(lf[1]))
+    e.gait_set_plan(steps_d, ns_d, rise_ratio=0.3)
+    torch.cuda.synchronize()
+    steps_h, ns_h = steps_d.cpu().numpy(), ns_d.cpu().numpy()
+    # the device plan is the host planner's plan (itself pinned to the reference)
+    fs = FootstepPlanner(step_width=2 * abs(lf[1]), step_length=0.1).plan(
+        [p for p in path[0]], [Footstep(init[0, 0, :2], np.array([0, 0, 0.0]), 0), Footstep(init[0, 1, :2], np.array([0, 0, 0.0]), 1)])
+    assert ns_h[0] == len(fs) and np.abs(steps_h[0, :len(fs), :2] - np.array([f.position for f in fs])).max() < 1e-14
+    qd, vd = torch.as_tensor(q, device=dev).clone(), torch.as_tensor(v, device=dev).clone()
+    e.rollout(qd, vd, steps_n, use_graph=True)
+    torch.cuda.synchronize()
+    gs = {k: t.cpu().numpy().copy() for k, t in e.gait_state().items()}
+    # host-driven
+    g = GaitRef(n, defaults=ctrl.default_refs, phase0=phase0, steps=steps_h, n_steps=ns_h, rise_ratio=0.3, **gait)
+    qh, vh = torch.as_tensor(q, device=dev).clone(), torch.as_tensor(v, device=dev).clone()
+    post = torch.as_tensor(np.tile(ctrl.default_refs["posture"], (n, 1)), device=dev)
+    for _ in range(steps_n):
+        refs = {k: torch.as_tensor(np.ascontiguousarray(a), device=dev) for k, a in g.refs().items()}
+        refs["posture"] = post
+        o = e.compute(qh, vh, torch.as_tensor(g.mask, device=dev), refs, aux=True)
+        e.integrate(qh, vh, o.ddq, conf.dt)
+        g.step(o.foot_lf.cpu().numpy(), o.foot_rf.cpu().numpy(), o.status.cpu().numpy())
+    torch.cuda.synchronize()
+    assert np.array_equal(gs["mask"], g.mask) and np.array_equal(gs["fails"], g.fails)
+    ok = g.fails == 0
+    assert ok.mean() > 0.9
+    assert np.abs(qd.cpu().numpy()[ok] - qh.cpu().numpy()[ok]).max() < 1e-8
+    for k in ("com", "foot_lf", "foot_rf", "contact_lf", "contact_rf"):
+        assert np.abs(gs[k][ok] - g.refs()[k][ok]).max() < 1e-8, k
+    assert np.abs(gs["foot_lf"][:, 17]).max() + np.abs(gs["foot_rf"][:, 17]).max() > 0  # yaw-rate references are in play

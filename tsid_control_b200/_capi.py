@@ -243,6 +243,8 @@ def load_library() -> C.CDLL:
     lib.tsidb_foot_trajectory.restype = ip
     lib.tsidb_footstep_plan.argtypes = [vp, ip, vp, vp, ip, vp, C.c_double, C.c_double, vp, vp, ip, vp]
     lib.tsidb_footstep_plan.restype = ip
+    lib.tsidb_gait_set_plan.argtypes = [vp, ip, vp, vp, ip, C.c_double, vp]
+    lib.tsidb_gait_set_plan.restype = ip
     lib.tsidb_gait_state.argtypes = [vp, C.POINTER(TsidbRefs), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.tsidb_gait_state.restype = ip
     lib.tsidb_gait_step.argtypes = [vp, ip, vp, vp, vp, vp]
@@ -266,5 +268,5 @@ EXPORTED_SYMBOLS = [
     "tsidb_compute", "tsidb_compute_host", "tsidb_compute_host_devrefs", "tsidb_integrate", "tsidb_kinematics", "tsidb_ci_row",
     "tsidb_fp64_peak", "tsidb_launch_count", "tsidb_set_timing", "tsidb_last_tick_ms",
     "tsidb_gait_reset", "tsidb_gait_state", "tsidb_gait_step", "tsidb_rollout", "tsidb_diagnostics",
-    "tsidb_foot_trajectory", "tsidb_footstep_plan",
+    "tsidb_foot_trajectory", "tsidb_footstep_plan", "tsidb_gait_set_plan",
 ]

@@ -307,6 +307,7 @@ extern "C" void tsidb_destroy(tsidb_handle* h) {
     cudaFree(h->gait.com); cudaFree(h->gait.foot[0]); cudaFree(h->gait.foot[1]); cudaFree(h->gait.contact[0]);
     cudaFree(h->gait.contact[1]); cudaFree(h->gait.fails); cudaFree(h->g_foot_now[0]); cudaFree(h->g_foot_now[1]);
     cudaFree(h->g_defaults);
+    cudaFree(h->gait.step_idx); cudaFree(h->gait.swing); cudaFree((void*)h->gait.steps); cudaFree((void*)h->gait.n_steps);
   }
   {
     std::lock_guard<std::mutex> lk(g_slot_mu);
@@ -653,6 +654,8 @@ static int gait_alloc(tsidb_handle* h) {
     CK(cudaMalloc(&h->g_foot_now[f], 12 * N * sizeof(double)));
   }
   CK(cudaMalloc(&h->gait.fails, N * sizeof(int32_t)));
+  CK(cudaMalloc(&h->gait.step_idx, N * sizeof(int32_t)));
+  CK(cudaMalloc(&h->gait.swing, 16 * N * sizeof(double)));
   CK(cudaMalloc(&h->g_defaults, 81 * sizeof(double)));
   h->gait_ready = 1;
   return 0;
@@ -668,6 +671,7 @@ extern "C" int tsidb_gait_reset(tsidb_handle* h, int n_envs, const tsidb_gait_co
   h->gconf.dt = gc->dt; h->gconf.step_duration = gc->step_duration; h->gconf.step_length = gc->step_length;
   h->gconf.step_height = gc->step_height; h->gconf.w2 = 9.80665 / gc->com_height; /* ref:ctrl/LIPM.py:15 */
   h->gconf.com_z = h->dc.ref_com[2];
+  if (!h->gait.steps) { h->gconf.rise_ratio = 0.5; h->gconf.max_steps = 0; }
   double d[81];
   memcpy(d, h->dc.ref_com, 9 * sizeof(double));
   memcpy(d + 9, h->dc.ref_foot[0], 24 * sizeof(double));
@@ -682,6 +686,46 @@ extern "C" int tsidb_gait_reset(tsidb_handle* h, int n_envs, const tsidb_gait_co
   CK(cudaGetLastError());
   h->launches += 1;
   h->gait_n = n_envs;
+  return 0;
+}
+
+/* plan = output of tsidb_footstep_plan (or any [N][max_steps][4] footsteps): copied into the handle; the swing foot of
+ * every later gait step goes to the env's next footstep of that side along FootTrajectory(rise_ratio) */
+extern "C" int tsidb_gait_set_plan(tsidb_handle* h, int n_envs, const double* steps, const int32_t* n_steps, int max_steps,
+                                   double rise_ratio, void* cuda_stream) {
+  if (!h || !h->gait_ready) { g_err = "tsidb_gait_set_plan: call tsidb_gait_reset first"; return -1; }
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (!steps) { /* back to straight steps */
+    CK(cudaStreamSynchronize(st));
+    cudaFree((void*)h->gait.steps); cudaFree((void*)h->gait.n_steps);
+    h->gait.steps = nullptr; h->gait.n_steps = nullptr; h->gconf.max_steps = 0;
+    return 0;
+  }
+  if (!n_steps || n_envs <= 0 || n_envs > h->gait_n || max_steps < 3 || !(rise_ratio > 0.0) || !(rise_ratio < 1.0)) {
+    g_err = "tsidb_gait_set_plan: bad n_envs (<= envs of the last tsidb_gait_reset) / max_steps / rise_ratio";
+    return -1;
+  }
+  if (h->gait.steps && h->gconf.max_steps != max_steps) {
+    CK(cudaStreamSynchronize(st));
+    cudaFree((void*)h->gait.steps); cudaFree((void*)h->gait.n_steps);
+    h->gait.steps = nullptr; h->gait.n_steps = nullptr;
+  }
+  if (!h->gait.steps) {
+    double* sp; int32_t* np_;
+    CK(cudaMalloc(&sp, (size_t)h->max_envs * max_steps * 4 * sizeof(double)));
+    CK(cudaMalloc(&np_, (size_t)h->max_envs * sizeof(int32_t)));
+    CK(cudaMemsetAsync(np_, 0, (size_t)h->max_envs * sizeof(int32_t), st));
+    h->gait.steps = sp; h->gait.n_steps = np_;
+  }
+  CK(cudaMemcpyAsync((void*)h->gait.steps, steps, (size_t)n_envs * max_steps * 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync((void*)h->gait.n_steps, n_steps, (size_t)n_envs * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  h->gconf.rise_ratio = rise_ratio;
+  h->gconf.max_steps = max_steps;
+  /* execution starts at footstep 2 (0 and 1 are the initial supports); feet already in the air start their swing */
+  tsidb_gait_plan_init_kernel<<<(n_envs + 127) / 128, 128, 0, st>>>(n_envs, h->gconf, h->gait);
+  CK(cudaGetLastError());
+  h->launches += 1;
   return 0;
 }
 

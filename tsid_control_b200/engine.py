@@ -257,6 +257,19 @@ class TsidEngine:
         check(self.lib.tsidb_gait_reset(self.h, n, C.byref(gc), phase0.data_ptr() if phase0 is not None else None,
                                         vcmd.data_ptr() if vcmd is not None else None, self._stream()), "tsidb_gait_reset")
 
+    def gait_set_plan(self, steps: Optional[torch.Tensor], n_steps: Optional[torch.Tensor] = None, rise_ratio: float = 0.5) -> None:
+        """Footstep plan [N,S,4] (x, y, yaw, side) + n_steps [N] int32 (e.g. from footstep_plan) for the device gait: the
+        swing foot follows FootTrajectory(rise_ratio) to the env's next footstep of its side.  None: straight steps."""
+        if steps is None:
+            check(self.lib.tsidb_gait_set_plan(self.h, 0, None, None, 0, 0.5, self._stream()), "tsidb_gait_set_plan")
+            return
+        n, S = steps.shape[0], steps.shape[1]
+        self._chk(steps.reshape(n, 4 * S), n, 4 * S, "steps")
+        if n_steps.dtype != torch.int32 or tuple(n_steps.shape) != (n,) or n_steps.device != self.device:
+            raise TypeError("n_steps: expected an int32 [N] tensor on the engine's device")
+        check(self.lib.tsidb_gait_set_plan(self.h, n, steps.data_ptr(), n_steps.data_ptr(), S, float(rise_ratio), self._stream()),
+              "tsidb_gait_set_plan")
+
     def _view(self, ptr: int, shape, dtype: torch.dtype) -> torch.Tensor:
         """A torch view of a library-owned device array (no copy)."""
         np_dt = {torch.float64: "<f8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
