@@ -109,6 +109,12 @@ def main():
         top = sorted(st.items(), key=lambda kv: -kv[1])[:3]
         print(f"{name:34s} {100*smp/max(1,tot_s):8.1f} {100*ins/max(1,tot_i):7.1f} {wf/1e6:11.1f}  " +
               ", ".join(f"{k[6:]} {100*v/max(1,smp):.0f}%" for k, v in top))
+    if os.environ.get("NCU_DUMP_LINES"):
+        print("\nall source lines with >= 0.15% of the executed instructions, by line:")
+        for (f, ln), (smp, ins) in sorted(per_line.items()):
+            if ins >= 0.0015 * tot_i:
+                print(f"  {f}:{ln:5d}  inst {ins/1e6:8.2f}M {100*ins/max(1,tot_i):5.1f}%  samples {100*smp/max(1,tot_s):5.1f}%")
+        print(f"  total inst {tot_i/1e6:.1f}M")
     print("\nhottest source lines:")
     for (f, ln), (smp, ins) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:25]:
         print(f"  {f}:{ln:5d}  samples {100*smp/max(1,tot_s):5.1f}%  inst {100*ins/max(1,tot_i):5.1f}%")
