@@ -61,8 +61,7 @@ struct tsidb_handle {
   double* g_defaults;      /* device copy of the default references: com 9, feet 2x24, contacts 2x12 */
   int gait_ready;
   int gait_n;              /* envs initialised by the last tsidb_gait_reset */
-  /* small-batch ticks replayed from a captured CUDA graph (tsidb_compute, n_envs <= TSIDB_GRAPH_MAX_ENVS) */
-  struct TickGraph* tgraph;
+  int small_n;             /* ticks of at most this many envs run as ONE launch (tsidb_tick_small_kernel); TSIDB_SMALL_N */
 };
 
 /* ------------------------------------------------------------------ small kernels */
@@ -196,6 +195,10 @@ static int create_impl(tsidb_handle* h, const cudaDeviceProp& prop, int max_envs
   if (const char* e = getenv("TSIDB_D_CARVEOUT")) { const int v = atoi(e); if (v >= d_carve && v <= 100) d_carve = v; } /* tuning knob */
   TSIDB_ATTR(tsidb_dynamics_kernel<26>, smem, TSIDB_D_CTAS_PER_SM, "dynamics kernel", d_carve);
   TSIDB_ATTR(tsidb_dynamics_kernel<24>, smem, TSIDB_D_CTAS_PER_SM, "dynamics kernel", d_carve);
+  CK((cudaFuncSetAttribute(tsidb_tick_small_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSIDB_SMALL_SMEM_DOUBLES(26) * sizeof(double)))));
+  CK((cudaFuncSetAttribute(tsidb_tick_small_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSIDB_SMALL_SMEM_DOUBLES(24) * sizeof(double)))));
+  h->small_n = 1024;
+  if (const char* e = getenv("TSIDB_SMALL_N")) h->small_n = atoi(e);
 #define TSIDB_E_SMEM(NV, NC) (((size_t)TSIDB_E_CTA_WARPS * e_per_env(NV, NC) + 144) * sizeof(double))
 #define TSIDB_E_ATTR(NV, NC, W) TSIDB_ATTR((tsidb_eliminate_kernel<NV, NC, W>), TSIDB_E_SMEM(NV, NC), (W) / TSIDB_E_CTA_WARPS, "elimination kernel", cudaSharedmemCarveoutMaxShared)
   TSIDB_E_ATTR(26, 2, TSIDB_E_WARPS); TSIDB_E_ATTR(26, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_ATTR(26, 0, TSIDB_E_WARPS_LIGHT);
@@ -356,6 +359,15 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   if (timed) CK(cudaEventRecord(h->ev[0], st));
   struct NvtxRange { explicit NvtxRange(const char* n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } };
   NvtxRange r_tick("tsidb:tick");
+  if (!a.kin_only && !timed && n <= h->small_n) {
+    /* small batch: one launch, one warp per env through all three stages (tsidb_tick_small_kernel) */
+    NvtxRange r("tsidb:tick_small");
+    if (h->dc.nv == 26) tsidb_tick_small_kernel<26><<<n, 32, TSIDB_SMALL_SMEM_DOUBLES(26) * sizeof(double), st>>>(a);
+    else tsidb_tick_small_kernel<24><<<n, 32, TSIDB_SMALL_SMEM_DOUBLES(24) * sizeof(double), st>>>(a);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+  }
   if (!a.kin_only) {
     NvtxRange r("tsidb:class_sort");
     CK(cudaMemsetAsync(counter, 0, 16 * sizeof(int32_t), st));

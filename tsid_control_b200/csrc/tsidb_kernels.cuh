@@ -2322,6 +2322,72 @@ tsidb_activeset_kernel(const TickArgs a) {
     env = envn;
   }
 }
+
+/* ---- Small batches: the whole tick of one env in ONE launch ----
+ * A CTA is one warp and takes one env through the three stages back to back (dynamics + assembly, elimination + basis,
+ * active set + decode), branching on the env's contact class on the device: no class sort, no work counters, no
+ * per-class launches, no launch gaps — a single robot's tick (the reference's operating point, ref:main.py:110-128)
+ * is bound by the dependent chain of its ~30 k instructions, and nine launches plus a memset added a third to that.
+ * The stage functions are the ones the batched kernels call; the hand-off images still travel through global memory
+ * (L2), so between the stages the warp orders its generic-proxy stores and completed bulk stores ahead of the next
+ * stage's bulk (async-proxy) load. */
+TSIDB_DEV void stage_handoff(int lane) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* bulk stores complete, not just read */
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncwarp();
+}
+#define TSIDB_SMALL_SMEM_DOUBLES(NV)                                                                                     \
+  ((a_layout(NV, 2).per_env > e_per_env(NV, 2) + 144 ? a_layout(NV, 2).per_env : e_per_env(NV, 2) + 144) > SM_PER_ENV + MDL_SIZE \
+       ? (a_layout(NV, 2).per_env > e_per_env(NV, 2) + 144 ? a_layout(NV, 2).per_env : e_per_env(NV, 2) + 144)         \
+       : SM_PER_ENV + MDL_SIZE)
+template <int NV>
+__global__ void __launch_bounds__(32, 1) tsidb_tick_small_kernel(const TickArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x;
+  const int env = blockIdx.x; /* slot == env: no class sort */
+  const DevConst& C = g_const[a.slot];
+  double* sm = smem;
+  {
+    double* mdl = smem + SM_PER_ENV;
+    stage_model(C, mdl, lane, 32);
+    __syncwarp();
+    dynamics_env<NV>(C, mdl, sm, a, env, env, lane);
+  }
+  stage_handoff(lane);
+  const int mask = a.mask ? (a.mask[env] & 3) : 3;
+  const int nc = (mask & 1) + ((mask >> 1) & 1);
+  {
+    double* lfinv_sm = smem + e_per_env(NV, 2);
+    for (int i = lane; i < 144; i += 32) lfinv_sm[i] = C.Lfinv[i / 12][i % 12];
+    unsigned parity = 0;
+#define TSIDB_SMALL_E(NC_)                                                                 \
+  {                                                                                          \
+    double* bar = sm + EL<NV, NC_>::oBar;                                                    \
+    if (lane == 0) mbar_init(bar, 1);                                                        \
+    __syncwarp();                                                                            \
+    eliminate_env<NV, NC_>(C, lfinv_sm, sm, a, env, lane, parity);                           \
+    if (lane == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); \
+  }
+    if (nc == 2) TSIDB_SMALL_E(2) else if (nc == 1) TSIDB_SMALL_E(1) else TSIDB_SMALL_E(0)
+#undef TSIDB_SMALL_E
+  }
+  stage_handoff(lane);
+  {
+    LaneConst K;
+    lane_const_init(C, K, lane);
+    unsigned parity = 0;
+#define TSIDB_SMALL_A(NC_)                                                                 \
+  {                                                                                          \
+    double* bar = sm + AL<NV, NC_>::oBar;                                                    \
+    if (lane == 0) mbar_init(bar, 1);                                                        \
+    __syncwarp();                                                                            \
+    activeset_env<NV, NC_>(C, K, sm, a, env, env, lane, parity);                             \
+  }
+    if (nc == 2) TSIDB_SMALL_A(2) else if (nc == 1) TSIDB_SMALL_A(1) else TSIDB_SMALL_A(0)
+#undef TSIDB_SMALL_A
+  }
+}
 #endif
 
 #endif /* TSIDB_KERNELS_CUH_ */
