@@ -451,7 +451,7 @@ def main() -> None:
     # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the call) ----
     # inputs live in pinned host memory (the contract's "from pinned host memory"), results land in pinned
     # host memory; the library cuts the batch into chunks so the copies run under the kernels
-    e2e = e2e_dev = None
+    e2e = e2e_dev = e2e_tau = None
     lat = None
     if not args.no_e2e:
         e2e_steps = max(3, min(args.steps, 10))
@@ -464,17 +464,18 @@ def main() -> None:
                 dr = {k: torch.as_tensor(np.ascontiguousarray(a[lo:hi]), device=dev) for k, a in s.refs.items()}
                 host.append((s, hq, hv, hm, hr, s.eng.host_buffers(hi - lo, pinned=True), dm, dr))
 
-        def e2e_pass(device_refs: bool):
+        def e2e_pass(device_refs):
             outs = []
             for s, hq, hv, hm, hr, hout, dm, dr in host:
                 if device_refs:
-                    outs.append(s.eng.compute_host_devrefs(hq, hv, dm, dr, out=hout))
+                    outs.append(s.eng.compute_host_devrefs(hq, hv, dm, dr, out=hout, tau_only=(device_refs == "tau"),
+                                                           want_active=(device_refs != "tau")))
                 else:
                     outs.append(s.eng.compute_host(hq, hv, hm, hr, out=hout))
             return outs
 
         results = {}
-        for device_refs in (False, True):
+        for device_refs in (False, True, "tau"):
             for _ in range(2):
                 e2e_pass(device_refs)
             if world > 1:
@@ -497,6 +498,10 @@ def main() -> None:
         e2e = {"value": results[False], "unit": UNIT, "h2d_bytes_per_step": h2d_full, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                "api": "tsidb_compute_host via TsidEngine.compute_host: q, v, contact mask and every reference from pinned host buffers, "
                       "results into pinned host buffers, 4 chunks over 3 streams (copies overlap the kernels)"}
+        d2h_tau = sum(s.n * (8 * s.eng.na + 4 + 4) for s in shards)
+        e2e_tau = {"value": results["tau"], "unit": UNIT, "h2d_bytes_per_step": h2d_dev, "d2h_bytes_per_step": d2h_tau, "steps": e2e_steps,
+                   "api": "tsidb_compute_host_devrefs with ddq = f = active_set = NULL: q and v up, tau, status and iters down (what "
+                          "ref:main.py:126 sends to the actuators); references on the device"}
         e2e_dev = {"value": results[True], "unit": UNIT, "h2d_bytes_per_step": h2d_dev, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                    "api": "tsidb_compute_host_devrefs: q and v from pinned host buffers; references and contact phases resident on the "
                           "device (the gait state the device phase machine keeps), results into pinned host buffers"}
@@ -546,6 +551,7 @@ def main() -> None:
     if e2e:
         line["e2e"] = e2e
         line["e2e_device_refs"] = e2e_dev
+        line["e2e_tau_only"] = e2e_tau
     if dom:
         line["roofline"] = {
             "bound": "fp64", "achieved": dom["achieved"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": dom["frac"],

@@ -34,6 +34,8 @@
  *
  * Environment knobs (diagnostics and tuning, not needed in normal use):
  *   TSIDB_CLASS_STREAMS=0   read by tsidb_create: keep every kernel of a tick on the caller's stream
+ *   TSIDB_SMALL_N=n         read by tsidb_create: ticks of at most n envs (default 1024) run as ONE launch, one warp per env
+ *                           through all three stages (no class sort, no per-class launches); 0 = always the batched pipeline
  *   TSIDB_HOST_CHUNKS=k     read by tsidb_compute_host: k equal chunks instead of the tapered 1/8,3/8,3/8,1/8 split
  *   TSIDB_HOST_TAPER=d      read by tsidb_compute_host: first/last chunk = 1/d of the batch
  *   TSIDB_HOST_TRACE=1      read by tsidb_compute_host: event time stamps per chunk on stderr
@@ -193,7 +195,10 @@ int tsidb_compute(tsidb_handle* h, int n_envs, int layout,
 
 /* Same tick with HOST buffers ([N][dof] row-major, contiguous): pinned staging,
  * H2D, kernels, D2H inside the call; returns after the results are in host memory.
- * This is the call the reference-side binding makes.            */
+ * This is the call the reference-side binding makes.
+ * ddq and f may be NULL: a caller that only drives the actuators (ref:main.py:126)
+ * then gets tau, status and iters back and the accelerations and contact forces
+ * stay on the device (168 instead of 592 bytes per env over PCIe).              */
 int tsidb_compute_host(tsidb_handle* h, int n_envs, const double* q, const double* v,
                        const uint8_t* contact_mask, const tsidb_refs* refs_host,
                        double* tau, double* ddq, double* f, int32_t* status, int32_t* iters,

@@ -222,6 +222,41 @@ def test_chunked_host_call_agrees_with_device_call(n, pinned):
     for k in ("tau", "ddq", "f", "status", "iters"):
         assert np.array_equal(d[k], base[k]), k
     assert np.array_equal(d["active_set"].astype(np.int64), base["active_set"])
+    # torque-only call (ddq and f stay on the device): tau, status, iters as before, the other buffers untouched
+    out2 = e.host_buffers(n, pinned=True)
+    out2["ddq"][:] = -7.0
+    out2["f"][:] = -7.0
+    t = e.compute_host(q, v, mask, refs, out=out2, tau_only=True)
+    for k in ("tau", "status", "iters"):
+        assert np.array_equal(t[k], base[k]), k
+    assert (t["ddq"] == -7.0).all() and (t["f"] == -7.0).all()
+
+
+@pytest.mark.parametrize("kind,n", [("v1", 1), ("v1", 97), ("v1", 1024), ("v0", 333)])
+def test_single_launch_small_batch_tick_equals_the_batched_pipeline(kind, n, monkeypatch):
+    """Ticks of at most TSIDB_SMALL_N envs (default 1024) run as one launch (tsidb_tick_small_kernel: one warp per env
+    through dynamics, elimination and active set).  It calls the stage functions of the batched kernels, so every
+    output — tau, ddq, f, status, iters, working sets, multipliers, kinematics — must equal the batched pipeline's bit
+    for bit, on all three contact classes."""
+    s = setup(kind)
+    q, v = synth.random_states(s["q0"], n, 41)
+    step = (0.3, 0.2, 0.2, 0.5) if kind == "v1" else (0.1, 0.1275, 0.05, 0.7)
+    mask, refs = synth.walking_batch(s["refs"], n, 41, *step, float(s["refs"]["com"][2]))
+    if n > 4:
+        mask[3] = 0  # one env in flight
+    outs = []
+    for small in ("1024", "0"):
+        monkeypatch.setenv("TSIDB_SMALL_N", small)  # read by tsidb_create
+        ctrl = _controller(kind, n)
+        launches0 = ctrl.engine.launch_count()
+        outs.append(_run(ctrl, q, v, mask, refs))
+        launches = ctrl.engine.launch_count() - launches0
+        assert launches == (1 if small == "1024" else 9), launches
+    a, b = outs
+    assert (a["status"] == 0).sum() >= 0.9 * n
+    for k in a:
+        if a[k] is not None:
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
 
 
 @pytest.mark.parametrize("use_graph", [True, False])

@@ -86,6 +86,7 @@ def main():
     stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     tot_s = tot_i = 0
     per_line = defaultdict(lambda: [0, 0])
+    exc_line = defaultdict(lambda: [0, 0])  # excessive / total shared wavefronts per source line
     for k, r in enumerate(body[: len(lines_of)]):
         f, ln = lines_of[k]
         smp = int(r[ix["# Samples"]] or 0)
@@ -104,6 +105,8 @@ def main():
                 a[3][c] += v
         tot_s += smp; tot_i += ins
         per_line[(f, ln)][0] += smp; per_line[(f, ln)][1] += ins
+        if "L1 Wavefronts Shared Excessive" in ix:
+            exc_line[(f, ln)][0] += int(r[ix["L1 Wavefronts Shared Excessive"]] or 0); exc_line[(f, ln)][1] += wf
     print(f"{'phase':34s} {'samples%':>8s} {'inst%':>7s} {'smem wf (M)':>11s}  top stalls")
     for name, (smp, ins, wf, st) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         top = sorted(st.items(), key=lambda kv: -kv[1])[:3]
@@ -115,6 +118,12 @@ def main():
             if ins >= 0.0015 * tot_i:
                 print(f"  {f}:{ln:5d}  inst {ins/1e6:8.2f}M {100*ins/max(1,tot_i):5.1f}%  samples {100*smp/max(1,tot_s):5.1f}%")
         print(f"  total inst {tot_i/1e6:.1f}M")
+    if os.environ.get("NCU_DUMP_CONFLICTS"):
+        tot_e = sum(v[0] for v in exc_line.values()); tot_w = sum(v[1] for v in exc_line.values())
+        print(f"\nshared-memory wavefronts {tot_w/1e6:.1f}M, excessive (bank conflicts) {tot_e/1e6:.2f}M = {100*tot_e/max(1,tot_w):.1f}%; lines with the most excessive wavefronts:")
+        for (f, ln), (e, w) in sorted(exc_line.items(), key=lambda kv: -kv[1][0])[:20]:
+            if e:
+                print(f"  {f}:{ln:5d}  excessive {e/1e6:7.2f}M of {w/1e6:7.2f}M")
     print("\nhottest source lines:")
     for (f, ln), (smp, ins) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:25]:
         print(f"  {f}:{ln:5d}  samples {100*smp/max(1,tot_s):5.1f}%  inst {100*ins/max(1,tot_i):5.1f}%")

@@ -516,7 +516,9 @@ extern "C" int tsidb_compute_host_devrefs(tsidb_handle* h, int n_envs, const dou
 static int compute_host_impl(tsidb_handle* h, int n_envs, const double* q, const double* v, const uint8_t* contact_mask,
                              const tsidb_refs* refs, bool dev_refs, double* tau, double* ddq, double* f, int32_t* status,
                              int32_t* iters, uint64_t* active_set) {
-  if (!h || !q || !v || !tau || !ddq || !f || !status || !iters) { g_err = "tsidb_compute_host: null argument"; return -1; }
+  /* ddq and f are optional: a caller that only drives the actuators (ref:main.py:126) passes NULL and the accelerations
+   * and contact forces stay on the device (592 -> 168 bytes per env back over PCIe) */
+  if (!h || !q || !v || !tau || !status || !iters) { g_err = "tsidb_compute_host: null argument"; return -1; }
   if (n_envs <= 0 || n_envs > h->max_envs) { g_err = "tsidb_compute_host: n_envs exceeds the handle's max_envs"; return -1; }
   CK(cudaSetDevice(h->device));
   const int na = h->dc.na, nv = h->dc.nv, nq = h->dc.nq;
@@ -534,7 +536,7 @@ static int compute_host_impl(tsidb_handle* h, int n_envs, const double* q, const
     if (segs[s].src && s < n_host_segs) segs[s].pinned = is_pinned(segs[s].src);
   }
   const bool mask_pinned = !dev_refs && contact_mask && is_pinned(contact_mask);
-  const bool out_pinned[3] = {is_pinned(tau), is_pinned(ddq), is_pinned(f)};
+  const bool out_pinned[3] = {is_pinned(tau), ddq && is_pinned(ddq), f && is_pinned(f)};
   const bool st_pinned = is_pinned(status), it_pinned = is_pinned(iters);
   const bool act_pinned = active_set && is_pinned(active_set);
   double* d_tau = h->d_out;
@@ -605,8 +607,8 @@ static int compute_host_impl(tsidb_handle* h, int n_envs, const double* q, const
     if (rc) return rc;
     if (trace) CK(cudaEventRecord(tev[c][2], st));
     CK(cudaMemcpyAsync(out_pinned[0] ? tau + o * na : s_tau + o * na, a.tau, (size_t)m * na * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out_pinned[1] ? ddq + o * nv : s_ddq + o * nv, a.ddq, (size_t)m * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out_pinned[2] ? f + o * 24 : s_f + o * 24, a.f, (size_t)m * 24 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (ddq) CK(cudaMemcpyAsync(out_pinned[1] ? ddq + o * nv : s_ddq + o * nv, a.ddq, (size_t)m * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (f) CK(cudaMemcpyAsync(out_pinned[2] ? f + o * 24 : s_f + o * 24, a.f, (size_t)m * 24 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(st_pinned ? status + o : h->h_int + o, a.status, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(it_pinned ? iters + o : h->h_int + N + o, a.iters, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (active_set) {
@@ -629,8 +631,8 @@ static int compute_host_impl(tsidb_handle* h, int n_envs, const double* q, const
       for (int i = 0; i < 4; i++) cudaEventDestroy(tev[c][i]);
   }
   if (!out_pinned[0]) memcpy(tau, s_tau, N * na * sizeof(double));
-  if (!out_pinned[1]) memcpy(ddq, s_ddq, N * nv * sizeof(double));
-  if (!out_pinned[2]) memcpy(f, s_f, N * 24 * sizeof(double));
+  if (ddq && !out_pinned[1]) memcpy(ddq, s_ddq, N * nv * sizeof(double));
+  if (f && !out_pinned[2]) memcpy(f, s_f, N * 24 * sizeof(double));
   if (!st_pinned) memcpy(status, h->h_int, N * sizeof(int32_t));
   if (!it_pinned) memcpy(iters, h->h_int + N, N * sizeof(int32_t));
   if (active_set && !act_pinned) memcpy(active_set, h->h_act, 3 * N * sizeof(uint64_t));

@@ -160,9 +160,11 @@ class TsidEngine:
 
     def compute_host(self, q: np.ndarray, v: np.ndarray, contact_mask: Optional[np.ndarray] = None,
                      refs: Optional[Dict[str, np.ndarray]] = None, want_active: bool = True,
-                     out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+                     out: Optional[Dict[str, np.ndarray]] = None, tau_only: bool = False) -> Dict[str, np.ndarray]:
         """The same tick with HOST numpy buffers in and out (H2D, kernels, D2H inside the call, chunked so that
-        the copies overlap the kernels).  `out` = buffers from :meth:`host_buffers` to avoid per-call allocation."""
+        the copies overlap the kernels).  `out` = buffers from :meth:`host_buffers` to avoid per-call allocation.
+        tau_only=True brings back only tau, status and iters (what ref:main.py:126 sends to the actuators): ddq and f
+        stay on the device and out["ddq"], out["f"] are left untouched."""
         q = np.ascontiguousarray(q, dtype=np.float64)
         v = np.ascontiguousarray(v, dtype=np.float64)
         n = q.shape[0]
@@ -187,15 +189,17 @@ class TsidEngine:
             raise ValueError("out: buffers were allocated for a different batch size")
         check(self.lib.tsidb_compute_host(
             self.h, n, q.ctypes.data, v.ctypes.data, m.ctypes.data if m is not None else None, C.byref(r),
-            out["tau"].ctypes.data, out["ddq"].ctypes.data, out["f"].ctypes.data, out["status"].ctypes.data,
-            out["iters"].ctypes.data, out["active_set"].ctypes.data if want_active else None), "tsidb_compute_host")
+            out["tau"].ctypes.data, None if tau_only else out["ddq"].ctypes.data, None if tau_only else out["f"].ctypes.data,
+            out["status"].ctypes.data, out["iters"].ctypes.data, out["active_set"].ctypes.data if want_active else None),
+            "tsidb_compute_host")
         return out
 
     def compute_host_devrefs(self, q: np.ndarray, v: np.ndarray, contact_mask: Optional[torch.Tensor] = None,
                              refs: Optional[Dict[str, torch.Tensor]] = None, want_active: bool = True,
-                             out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+                             out: Optional[Dict[str, np.ndarray]] = None, tau_only: bool = False) -> Dict[str, np.ndarray]:
         """compute_host with the references and the contact phases resident on the DEVICE (CUDA tensors, e.g. the
-        views of gait_state()): only q and v cross PCIe on the way in (tsidb_compute_host_devrefs)."""
+        views of gait_state()): only q and v cross PCIe on the way in (tsidb_compute_host_devrefs); tau_only as in
+        :meth:`compute_host`."""
         q = np.ascontiguousarray(q, dtype=np.float64)
         v = np.ascontiguousarray(v, dtype=np.float64)
         n = q.shape[0]
@@ -217,8 +221,9 @@ class TsidEngine:
         torch.cuda.current_stream(self.device).synchronize()  # the device arrays must be final: the call uses its own streams
         check(self.lib.tsidb_compute_host_devrefs(
             self.h, n, q.ctypes.data, v.ctypes.data, contact_mask.data_ptr() if contact_mask is not None else None, C.byref(r),
-            out["tau"].ctypes.data, out["ddq"].ctypes.data, out["f"].ctypes.data, out["status"].ctypes.data,
-            out["iters"].ctypes.data, out["active_set"].ctypes.data if want_active else None), "tsidb_compute_host_devrefs")
+            out["tau"].ctypes.data, None if tau_only else out["ddq"].ctypes.data, None if tau_only else out["f"].ctypes.data,
+            out["status"].ctypes.data, out["iters"].ctypes.data, out["active_set"].ctypes.data if want_active else None),
+            "tsidb_compute_host_devrefs")
         return out
 
     def kinematics(self, q: torch.Tensor, v: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
