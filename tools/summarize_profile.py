@@ -25,10 +25,10 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 # short name -> (traffic group of bench.py, regex selecting the launch in the report, mangled name in the cubin)
 KERNELS = {
     "dynamics": ("dynamics", r"tsidb_dynamics_kernel<26>", "_Z21tsidb_dynamics_kernelILi26EEv8TickArgs"),
-    "eliminate_ds": ("eliminate+j2", r"tsidb_eliminate_kernel<26, 2", "_Z22tsidb_eliminate_kernelILi26ELi2ELi8EEv8TickArgs"),
-    "eliminate_ss": ("eliminate+j2", r"tsidb_eliminate_kernel<26, 1", "_Z22tsidb_eliminate_kernelILi26ELi1ELi12EEv8TickArgs"),
-    "j2_ds": ("eliminate+j2", r"tsidb_j2_kernel<26, 2>", "_Z15tsidb_j2_kernelILi26ELi2EEv8TickArgs"),
-    "j2_ss": ("eliminate+j2", r"tsidb_j2_kernel<26, 1>", "_Z15tsidb_j2_kernelILi26ELi1EEv8TickArgs"),
+    "eliminate_ds": ("eliminate", r"tsidb_eliminate_kernel<26, 2", "_Z22tsidb_eliminate_kernelILi26ELi2ELi8EEv8TickArgs"),
+    "eliminate_ss": ("eliminate", r"tsidb_eliminate_kernel<26, 1", "_Z22tsidb_eliminate_kernelILi26ELi1ELi12EEv8TickArgs"),
+    "j2_ds": ("eliminate", r"tsidb_j2_kernel<26, 2>", "_Z15tsidb_j2_kernelILi26ELi2EEv8TickArgs"),
+    "j2_ss": ("eliminate", r"tsidb_j2_kernel<26, 1>", "_Z15tsidb_j2_kernelILi26ELi1EEv8TickArgs"),
     "activeset_ds": ("activeset", r"tsidb_activeset_kernel<26, 2", "_Z22tsidb_activeset_kernelILi26ELi2ELi8EEv8TickArgs"),
     "activeset_ss": ("activeset", r"tsidb_activeset_kernel<26, 1", "_Z22tsidb_activeset_kernelILi26ELi1ELi12EEv8TickArgs"),
 }
