@@ -28,12 +28,18 @@ def phase_table(src):
         (r"w_hat\[0:neq\] = R1\^-T", "E w_hat"), (r"w0 = Q w_hat", "E w0"), (r"x0 = L\^-T w0", "E x0"),
         (r"J2\[:, c\] = L\^-T Q", "E J2 columns"),
         (r"^TSIDB_DEV int as_solve", "K3 AS setup"), (r"for \(;;\) \{ /\* l1 \*/", "K3 AS l1: s, psi"),
-        (r"for \(;;\) \{ /\* l2 \*/", "K3 AS l2: pick"), (r"for \(;;\) \{ /\* l2a \*/", "K3 AS l2a: d,z,r,steps"),
-        (r"if \(t == t2\) \{", "K3 AS add (Householder)"), (r"partial step: drop the blocking", "K3 AS partial-step drop"),
+        (r"for \(;;\) \{ /\* l2 \*/", "K3 AS l2: pick"), (r"for \(;;\) \{ /\* l2a \*/", "K3 AS l2a head"),
+        (r"/\* s = CI x \+ ci0 for the rows this lane owns, one", "K3 AS l1: candidates s = CI x + ci0"),
+        (r"violation sum: the other side", "K3 AS l1: pick, psi"),
+        (r"/\* d = J2\^T n_ip", "K3 AS l2a: d = J2^T n"), (r"/\* z = J2\[:, iq:\] d\[iq:\]", "K3 AS l2a: z = J2 d"),
+        (r"/\* r = R\^-1 d\[0:iq\]", "K3 AS l2a: r = R^-1 d"), (r"/\* partial step t1 = min", "K3 AS l2a: t1, t2, step"),
+        (r"/\* full step: add ip", "K3 AS add (Householder update of J2, R column)"), (r"eiquadprog: exclude ip, restore", "K3 AS degenerate restore"),
+        (r"dual-only step or partial step: drop the blocking", "K3 AS drop (shift R, Givens on R and J2)"),
+        (r"/\* partial step: recompute s\(ip\)", "K3 AS partial step: s(ip) again"),
         (r"^TSIDB_DEV void dynamics_env", "D io + image stores"), (r"^TSIDB_DEV void eliminate_env", "E io + image stores"),
         (r"^struct G2Pipe", "G pipeline"), (r"^TSIDB_DEV int warp_argmin", "K3 argmin"), (r"^TSIDB_DEV unsigned smem_u32", "TMA helpers"), (r"^TSIDB_DEV void activeset_env", "A load + decode"),
         (r"^TSIDB_DEV void j2_columns", "G columns"), (r"^TSIDB_DEV void j2_env", "G load"),
-        (r"^TSIDB_DEV void wrench_of", "K3 wrench_of"), (r"^TSIDB_DEV double eval_one", "K3 eval_one"), (r"^TSIDB_DEV void actuation_normal", "K3 actuation_normal"),
+        (r"^TSIDB_DEV (void|double) wrench_of", "K3 wrench_of"), (r"^TSIDB_DEV double eval_one", "K3 eval_one"), (r"^TSIDB_DEV void actuation_normal", "K3 actuation_normal"),
         (r"w0 = Q w_hat: reflectors in reverse", "E w0"), (r"x0 = L\^-T w0: force rows", "E x0"), (r"^__global__ void tsidb_classify", "kernel loops"),
         (r"^TSIDB_DEV void eval_rows", "K3 eval rows"), (r"^TSIDB_DEV double row_dot_col", "K3 row_dot_col"), (r"^TSIDB_DEVNI void qp_delete", "K3 delete_constraint"),
     ]
@@ -107,10 +113,10 @@ def main():
         per_line[(f, ln)][0] += smp; per_line[(f, ln)][1] += ins
         if "L1 Wavefronts Shared Excessive" in ix:
             exc_line[(f, ln)][0] += int(r[ix["L1 Wavefronts Shared Excessive"]] or 0); exc_line[(f, ln)][1] += wf
-    print(f"{'phase':34s} {'samples%':>8s} {'inst%':>7s} {'smem wf (M)':>11s}  top stalls")
+    print(f"{'phase':50s} {'samples%':>8s} {'inst%':>7s} {'smem wf (M)':>11s}  top stalls")
     for name, (smp, ins, wf, st) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         top = sorted(st.items(), key=lambda kv: -kv[1])[:3]
-        print(f"{name:34s} {100*smp/max(1,tot_s):8.1f} {100*ins/max(1,tot_i):7.1f} {wf/1e6:11.1f}  " +
+        print(f"{name:50s} {100*smp/max(1,tot_s):8.1f} {100*ins/max(1,tot_i):7.1f} {wf/1e6:11.1f}  " +
               ", ".join(f"{k[6:]} {100*v/max(1,smp):.0f}%" for k, v in top))
     if os.environ.get("NCU_DUMP_LINES"):
         print("\nall source lines with >= 0.15% of the executed instructions, by line:")
