@@ -23,12 +23,12 @@ def main():
     from tsid_control_b200.ctrl.conf import RobotConfig
     from tsid_control_b200.ctrl.WalkController import WalkController
 
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else bench.BATCH
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
     conf = RobotConfig()
     conf.device, conf.max_envs = 0, n
     ctrl = WalkController(conf, n_envs=n)
     eng = ctrl.engine
-    q, v, mask, refs = bench.make_workload(n, 0, ctrl.q, ctrl.default_refs)
+    q, v, mask, refs = bench.make_workload("v1", "walking", n, 0, ctrl.q, ctrl.default_refs)
     hq, hv, hmask = eng.pin(q), eng.pin(v), eng.pin(mask)
     hrefs = {k: eng.pin(a) for k, a in refs.items()}
     hout = eng.host_buffers(n, pinned=True)
