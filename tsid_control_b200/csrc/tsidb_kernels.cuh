@@ -202,7 +202,6 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int
   const bool act = lane < nb;
   const int b = act ? lane : 0;
   const int par = act && lane > 0 ? (int)mdl[b * MDL_STRIDE + MDL_oPAR] : 0;
-  const int dep = act ? (int)mdl[b * MDL_STRIDE + MDL_oDEP] : -1;
   const double* qs = sm + SM_oQV;
   const double* vs = sm + SM_oQV + 32;
 
@@ -1100,7 +1099,6 @@ TSIDB_DEV int k3_eliminate(const DevConst& C, const double* lfinv_sm, double* sm
     }
     x[NV + lane] = acc0 + acc1;
   }
-#pragma unroll
   {
     /* row `lane` scaled by 1 / L_ll up front; unrolled, so the scaled coefficients are formed off the chain and a
      * step is one shuffle and one FMA */
@@ -1976,7 +1974,6 @@ TSIDB_DEV void j2_from_factor(const DevConst& C, const double* L, const double* 
                               double* img, int lane);
 template <int NV, int NC>
 TSIDB_DEV void eliminate_env(const DevConst& C, const double* lfinv_sm, double* sm, const TickArgs& a, int slot, int lane, unsigned& parity) {
-  constexpr int nv = NV;
   typedef EL<NV, NC> LE;
   __syncwarp(); /* every lane is done with the previous env's shared memory */
 #ifndef TSIDB_EMU
@@ -2121,7 +2118,6 @@ TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const 
   S.Rp = sm + LA::oR; S.np = sm + LA::oNP; S.dd = sm + LA::oD;
   const double c1c2 = sm[SA_oSc], R_norm = sm[SA_oSc + 1], c1 = sm[SA_oSc + 3];
   const int em = (int)sm[SA_oSc + 2], err = em >> 2, mask = em & 3; /* its contact count is NC (class-sorted slots) */
-  constexpr int nc = NC, n = LA::n, neq = 6 + 6 * NC;
   S.wro = (NC == 1 && !(mask & 1)) ? 6 : 0;
   K.lb = K.ub = 0.0;
   if (lane < na && C.use_jb) {
