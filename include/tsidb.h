@@ -215,6 +215,14 @@ int tsidb_compute_host_devrefs(tsidb_handle* h, int n_envs, const double* q, con
                                double* tau, double* ddq, double* f, int32_t* status, int32_t* iters,
                                uint64_t* active_set);
 
+/* Diagnostics for parity tests: the dynamics terms the last tick handed from the dynamics kernel to the solver stages
+ * for ONE env — M [nv][nv], nle [nv], the sole Jacobians JF [2][6][nv] (LOCAL frame, LF then RF), the dv block of the
+ * Hessian H [nv][nv] (lower triangle significant) and the dv part of the gradient g [nv] — what
+ * RobotWrapper::computeAllTerms / the solver's H, g build produce inside ref:main.py:119,121.  Host pointers;
+ * synchronous.  Valid when the last tick ran without a contact mask or with at most TSIDB_SMALL_N envs (no class sort:
+ * slot == env); n_contacts = contacts of that env in that tick. */
+int tsidb_debug_terms(tsidb_handle* h, int env, int n_contacts, double* M, double* nle, double* JF, double* H, double* g);
+
 /* controller.integrate_dv(q, v, dv, dt) (ref:ctrl/WalkController.py:291-295,
  * ref:legacy/biped.py:236-240): v_mean = v + dt/2*dv; v += dt*dv;
  * q = pin.integrate(q, dt*v_mean).  In place on device arrays.                   */

@@ -115,6 +115,38 @@ def test_kinematics_match_oracle():
         assert np.abs(lf[i] - r["foot"][0]).max() < 1e-13 and np.abs(rf[i] - r["foot"][1]).max() < 1e-13
 
 
+@pytest.mark.parametrize("kind", ["v1", "v0"])
+def test_dynamics_terms_match_oracle(kind):
+    """SURVEY.md section 7 step 5 / rows a1-a2: what RobotWrapper::computeAllTerms and the solver's H, g build produce
+    inside computeProblemData / solve (ref:main.py:119,121) — the joint-space inertia M, the non-linear effects h, the
+    LOCAL sole Jacobians, the dv block of the Hessian and of the gradient — read back from the dynamics kernel's
+    hand-off images (tsidb_debug_terms) and compared with the oracle's dump for every env of a small batch."""
+    s = setup(kind)
+    n = 24
+    ctrl = _controller(kind, n)
+    q, v = synth.random_states(s["q0"], n, 17)
+    step = (0.3, 0.2, 0.2, 0.5) if kind == "v1" else (0.1, 0.1275, 0.05, 0.7)
+    mask, refs = synth.walking_batch(s["refs"], n, 17, *step, float(s["refs"]["com"][2]))
+    mask[5] = 0
+    _run(ctrl, q, v, mask, refs)  # n <= TSIDB_SMALL_N: no class sort, slot == env
+    nv = ctrl.engine.nv
+    worst = {}
+    for e in range(n):
+        m = int(mask[e])
+        t = ctrl.engine.debug_terms(e, (m & 1) + (m >> 1))
+        d = s["oracle"].tick(q[e], v[e], m, {k: a[e] for k, a in refs.items()}, dump=True)["dump"]
+        tril = np.tril_indices(nv)
+        pairs = {"M": (t["M"], d["M"]), "nle": (t["nle"], d["nle"]), "H": (t["H"][tril], d["H"][:nv, :nv][tril]),
+                 "g": (t["g"], d["g"][:nv])}
+        for f, bit in ((0, 1), (1, 2)):
+            pairs[f"JF{f}"] = (t["JF"][f], d["JF"][f])
+        for k, (a, b) in pairs.items():
+            worst[k] = max(worst.get(k, 0.0), float(np.max(np.abs(a - b)) / (1e-2 + np.max(np.abs(b)))))
+    print("\ndynamics terms vs oracle (max |a-b| / (1e-2 + max|b|)):", {k: f"{x:.1e}" for k, x in worst.items()})
+    parity_log.record(f"dynamics_terms_{kind}", worst)
+    assert all(x < 1e-10 for x in worst.values()), worst
+
+
 def test_constructor_references_match_reference_semantics():
     s = setup("v1")
     ctrl = _controller("v1", 4)

@@ -253,6 +253,8 @@ def load_library() -> C.CDLL:
     lib.tsidb_rollout.restype = ip
     lib.tsidb_diagnostics.argtypes = [vp, ip, C.POINTER(TsidbAuxOut), vp, C.c_double, vp, vp, vp, vp]
     lib.tsidb_diagnostics.restype = ip
+    lib.tsidb_debug_terms.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp]
+    lib.tsidb_debug_terms.restype = ip
     _LIB = lib
     return lib
 
@@ -268,5 +270,5 @@ EXPORTED_SYMBOLS = [
     "tsidb_compute", "tsidb_compute_host", "tsidb_compute_host_devrefs", "tsidb_integrate", "tsidb_kinematics", "tsidb_ci_row",
     "tsidb_fp64_peak", "tsidb_launch_count", "tsidb_set_timing", "tsidb_last_tick_ms",
     "tsidb_gait_reset", "tsidb_gait_state", "tsidb_gait_step", "tsidb_rollout", "tsidb_diagnostics",
-    "tsidb_foot_trajectory", "tsidb_footstep_plan", "tsidb_gait_set_plan",
+    "tsidb_foot_trajectory", "tsidb_footstep_plan", "tsidb_gait_set_plan", "tsidb_debug_terms",
 ]

@@ -1,6 +1,7 @@
 /* tsidb.cu — host side of libtsidb.so: the C ABI of include/tsidb.h over the sm_100a kernels
  * of tsidb_kernels.cuh.  No torch types, no CPU fallback: every entry point needs a CUDA device. */
 #include <cuda_runtime.h>
+#include <vector>
 #include <nvtx3/nvToolsExt.h> /* header-only: ranges cost nothing unless a profiler is attached */
 #include <stdint.h>
 #include <stdio.h>
@@ -636,6 +637,36 @@ static int compute_host_impl(tsidb_handle* h, int n_envs, const double* q, const
   if (!st_pinned) memcpy(status, h->h_int, N * sizeof(int32_t));
   if (!it_pinned) memcpy(iters, h->h_int + N, N * sizeof(int32_t));
   if (active_set && !act_pinned) memcpy(active_set, h->h_act, 3 * N * sizeof(uint64_t));
+  return 0;
+}
+
+/* The dynamics terms the last tick handed from the dynamics kernel to the solver stages, for ONE env: read back from
+ * the assembly image (Hessian dv block, gradient, base rows of M, sole Jacobians, base nle) and the solve-independent part
+ * of the solver image (rows 6.. of M, nle_a).  Diagnostics for the parity tests (M, h, J against
+ * the oracle), synchronous; valid when the last tick ran without a contact mask or as a small batch (slot == env). */
+extern "C" int tsidb_debug_terms(tsidb_handle* h, int env, int n_contacts, double* M /*[nv][nv]*/, double* nle /*[nv]*/,
+                                 double* JF /*[2][6][nv]*/, double* H /*[nv][nv]*/, double* g /*[nv]*/) {
+  if (!h || !M || !nle || !JF || !H || !g) { g_err = "tsidb_debug_terms: null argument"; return -1; }
+  if (env < 0 || env >= h->max_envs || n_contacts < 0 || n_contacts > 2) { g_err = "tsidb_debug_terms: env or contact count out of range"; return -1; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  const int nv = h->dc.nv, na = h->dc.na;
+  std::vector<double> ea(SE_IMAGE), sa(SA_IMAGE);
+  CK(cudaMemcpy(ea.data(), h->ws3 + (size_t)env * SE_IMAGE, SE_IMAGE * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(sa.data(), h->ws + (size_t)env * SA_IMAGE, SA_IMAGE * sizeof(double), cudaMemcpyDeviceToHost));
+  const ALayout L = a_layout(nv, n_contacts);
+  for (int i = 0; i < nv; i++)
+    for (int j = 0; j < nv; j++) {
+      H[i * nv + j] = ea[SE_oH + i * SM_LDM + j];
+      M[i * nv + j] = (i < 6) ? ea[SE_oMu + i * SM_LDM + j] : sa[L.oMa + (i - 6) * SA_LDM + j];
+    }
+  for (int i = 0; i < nv; i++) {
+    g[i] = ea[SE_oG + i];
+    nle[i] = (i < 6) ? ea[SE_oNle + i] : sa[L.oNle + i - 6];
+  }
+  for (int r = 0; r < 12; r++)
+    for (int j = 0; j < nv; j++) JF[r * nv + j] = ea[SE_oJF + r * TSIDB_NVX + j];
+  (void)na;
   return 0;
 }
 

@@ -365,6 +365,15 @@ class TsidEngine:
     def ci_row(self, block: int, side: int, i: int) -> int:
         return int(self.lib.tsidb_ci_row(self.h, block, side, i))
 
+    def debug_terms(self, env: int, n_contacts: int) -> Dict[str, np.ndarray]:
+        """M, nle, JF (LF, RF sole Jacobians, LOCAL), the dv block of the Hessian and the dv part of the gradient that the
+        dynamics kernel produced for `env` in the last tick (tsidb_debug_terms; parity tests)."""
+        nv = self.nv
+        out = {"M": np.empty((nv, nv)), "nle": np.empty(nv), "JF": np.empty((2, 6, nv)), "H": np.empty((nv, nv)), "g": np.empty(nv)}
+        check(self.lib.tsidb_debug_terms(self.h, env, n_contacts, *(out[k].ctypes.data for k in ("M", "nle", "JF", "H", "g"))),
+              "tsidb_debug_terms")
+        return out
+
     def launch_count(self) -> int:
         return int(self.lib.tsidb_launch_count(self.h))
 
