@@ -12,7 +12,7 @@ def probe():
     from tsid_control_b200.ctrl.WalkController import WalkController
     from tsid_control_b200 import synth
     out = {}
-    for n in (1, 32, 256, 1024, 4096):
+    for n in [int(x) for x in os.environ.get("PROBE_N", "1,32,256,1024,4096").split(",")]:
         conf = RobotConfig(); conf.max_envs = n
         c = WalkController(conf, n_envs=n); e = c.engine
         q, v = synth.random_states(c.q, n, 3)
@@ -37,6 +37,6 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         probe()
     else:
-        for small in ("1024", "0"):
+        for small in os.environ.get("PROBE_SMALL", "1024,0").split(","):
             r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, TSIDB_SMALL_N=small), capture_output=True, text=True)
             print("TSIDB_SMALL_N=" + small, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:])
