@@ -79,7 +79,9 @@ struct DevConst {
 #define RF_FOOT 10   /* + 24 f */
 #define RF_CONTACT 58 /* + 12 f */
 #define RF_POST 82
-#define SM_PER_ENV (SM_oRef + 106)      /*                                       1544 */
+#define SM_oQVn (SM_oRef + 106)         /* q (32) and v (32) of the warp's NEXT env, prefetched by asynchronous copies
+                                           while the current env is computed         64 */
+#define SM_PER_ENV (SM_oQVn + 64)       /*                                       1608 */
 /* task vectors inside oBv */
 #define BV_MOT 0   /* 2 x 6 contact motion rhs, by foot */
 #define BV_FOOT 12 /* 2 x 6 foot task rhs               */

@@ -1884,8 +1884,13 @@ TSIDB_DEV void stage_refs_wait() {
   __syncwarp();
 }
 
+/* `prefetched`: q, v of this env already sit in the warp's next-env buffer (the previous call asked for them);
+ * `env_next` >= 0: ask for that env's q, v now — the copies travel with this env's references (one cp.async group, waited
+ * for after K1), so the next call finds them without waiting on HBM (17.9 % of the kernel's samples were long-scoreboard
+ * stalls, a third of them on these two loads at the head of an env). */
 template <int NV>
-TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, const TickArgs& a, int env, int slot, int lane) {
+TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, const TickArgs& a, int env, int slot, int lane,
+                            bool prefetched = false, int env_next = -1) {
   constexpr int nv = NV, na = NV - 6, nq = NV + 1;
   PHASE_SYNC_D();
 #ifndef TSIDB_EMU
@@ -1893,9 +1898,21 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
   __syncwarp();
 #endif
   /* stage q, v */
-  if (lane < nq) sm[SM_oQV + lane] = ldin(a.q, a, env, lane, nq);
-  if (lane < nv) sm[SM_oQV + 32 + lane] = a.v ? ldin(a.v, a, env, lane, nv) : 0.0;
-  if (!a.kin_only) stage_refs(C, mdl, sm, a, env, lane, na);
+  if (prefetched) {
+    sm[SM_oQV + lane] = sm[SM_oQVn + lane];
+    sm[SM_oQV + 32 + lane] = sm[SM_oQVn + 32 + lane];
+    __syncwarp();
+  } else {
+    if (lane < nq) sm[SM_oQV + lane] = ldin(a.q, a, env, lane, nq);
+    if (lane < nv) sm[SM_oQV + 32 + lane] = a.v ? ldin(a.v, a, env, lane, nv) : 0.0;
+  }
+  if (!a.kin_only) {
+    if (env_next >= 0) {
+      if (lane < nq) stage_one(sm + SM_oQVn + lane, a.q, a, env_next, lane, nq, nullptr);
+      if (lane < nv) { if (a.v) stage_one(sm + SM_oQVn + 32 + lane, a.v, a, env_next, lane, nv, nullptr); else sm[SM_oQVn + 32 + lane] = 0.0; }
+    }
+    stage_refs(C, mdl, sm, a, env, lane, na);
+  }
   __syncwarp();
   k1_dynamics<NV>(C, mdl, sm, lane);
   const double* fr = sm + SM_oFr;
@@ -2219,11 +2236,21 @@ tsidb_dynamics_kernel(const TickArgs a) {
    * the barriers); it stores the same values again. */
   const int per_round = gridDim.x * TSIDB_WARPS_PER_BLOCK;
   const int rounds = (a.n_envs + per_round - 1) / per_round;
+  auto slot_of = [&](int r) {
+    const int s_ = (r * gridDim.x + blockIdx.x) * TSIDB_WARPS_PER_BLOCK + wid;
+    return s_ < a.n_envs ? s_ : a.n_envs - 1;
+  };
+  int slot = slot_of(0);
+  int env = a.perm ? a.perm[slot] : slot;
   for (int r = 0; r < rounds; r++) {
-    int slot = (r * gridDim.x + blockIdx.x) * TSIDB_WARPS_PER_BLOCK + wid;
-    if (slot >= a.n_envs) slot = a.n_envs - 1;
-    const int env = a.perm ? a.perm[slot] : slot;
-    dynamics_env<NV>(C, mdl, sm, a, env, slot, lane);
+    /* the warp's next env: its q, v are prefetched while this one is computed (not in kinematics-only calls, which
+     * stage no references and so have no copy group to ride on) */
+    const bool more = r + 1 < rounds && !a.kin_only;
+    const int slot_n = more ? slot_of(r + 1) : slot;
+    const int env_n = more ? (a.perm ? a.perm[slot_n] : slot_n) : -1;
+    dynamics_env<NV>(C, mdl, sm, a, env, slot, lane, r > 0 && !a.kin_only, env_n);
+    slot = slot_n;
+    env = env_n;
   }
   if (lane == 0) bulk_store_wait_read(); /* shared memory must outlive the bulk stores that read it */
 }
