@@ -38,6 +38,7 @@
  *                           through all three stages (no class sort, no per-class launches); 0 = always the batched pipeline
  *   TSIDB_HOST_CHUNKS=k     read by tsidb_compute_host: k equal chunks instead of the tapered 1/8,3/8,3/8,1/8 split
  *   TSIDB_HOST_TAPER=d      read by tsidb_compute_host: first/last chunk = 1/d of the batch
+ *   TSIDB_HOST_SPLIT=a,b,.. read by tsidb_compute_host: chunk sizes in 64ths of the batch (sum 64), e.g. 8,16,24,16
  *   TSIDB_HOST_TRACE=1      read by tsidb_compute_host: event time stamps per chunk on stderr
  */
 #ifndef TSIDB_H_

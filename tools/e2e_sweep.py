@@ -34,7 +34,7 @@ def main():
     hout = eng.host_buffers(n, pinned=True)
 
     def run(tag, env):
-        for k in ("TSIDB_HOST_CHUNKS", "TSIDB_HOST_TAPER"):
+        for k in ("TSIDB_HOST_CHUNKS", "TSIDB_HOST_TAPER", "TSIDB_HOST_SPLIT"):
             os.environ.pop(k, None)
         os.environ.update(env)
         for _ in range(3):
@@ -49,6 +49,8 @@ def main():
         print(f"{tag:28s} {best * 1e3:7.3f} ms  {n / best / 1e6:7.3f} M ticks/s", flush=True)
 
     run("default", {})
+    for sp in os.environ.get("SWEEP_SPLITS", "8,24,24,8 8,20,28,8 8,18,30,8 6,18,32,8 8,20,26,10 6,16,34,8 6,14,22,16,6 8,18,26,12 4,12,24,18,6 8,16,24,16").split():
+        run(f"split {sp} /64", {"TSIDB_HOST_SPLIT": sp})
     for den in (5, 6, 8, 10, 12, 16, 24, 32):
         run(f"taper 1/{den}", {"TSIDB_HOST_TAPER": str(den)})
     for c in (1, 2, 3, 4, 5, 6, 8):

@@ -557,7 +557,23 @@ static int compute_host_impl(tsidb_handle* h, int n_envs, const double* q, const
   }
   size_t bound[TSIDB_MAX_CHUNKS + 1];
   bound[0] = 0;
-  if (tapered) {
+  int split64[TSIDB_MAX_CHUNKS], nsplit = 0;
+  if (const char* e = getenv("TSIDB_HOST_SPLIT")) { /* tuning knob: chunk sizes in 64ths of the batch, e.g. "8,20,28,8" */
+    int sum = 0;
+    for (const char* p = e; *p && nsplit < TSIDB_MAX_CHUNKS;) {
+      const int v = atoi(p);
+      if (v <= 0) { nsplit = 0; break; }
+      split64[nsplit++] = v; sum += v;
+      while (*p && *p != ',') p++;
+      if (*p == ',') p++;
+    }
+    if (sum != 64) nsplit = 0;
+  }
+  if (nsplit >= 2 && n_envs >= 16384) {
+    nch = nsplit; tapered = false;
+    size_t acc = 0;
+    for (int c = 0; c < nch; c++) { acc += split64[c]; bound[c + 1] = (c + 1 == nch) ? N : ((N * acc / 64 + 7) & ~(size_t)7); }
+  } else if (tapered) {
     int den = 8;
     if (const char* e = getenv("TSIDB_HOST_TAPER")) { const int v = atoi(e); if (v >= 3 && v <= 64) den = v; } /* tuning knob */
     const size_t e8 = (N / den + 7) & ~(size_t)7;
