@@ -693,15 +693,23 @@ TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, con
      * scattered its stores at stride 28 (8-way bank conflicts): 2.5x the shared-memory wavefronts of this loop,
      * in a kernel that runs at two thirds of the shared-memory pipe's rate. */
     static_assert((NV & 1) == 0 && (TSIDB_NVX & 1) == 0, "rows of H come in pairs");
+    /* Columns t, t+1 of a foot's Jacobian are exactly zero unless their joints lie on the chain root -> foot (the base
+     * columns always do): the six rows of a foot are skipped for the column pairs off its chain — the arms' and the head's
+     * pairs take neither foot, a leg's pairs one (the test is warp-uniform: t is the loop variable; adding the skipped
+     * terms would add exact zeros, so the sums are unchanged bit for bit). */
+    const unsigned sup0 = C.foot_support[0], sup1 = C.foot_support[1];
 #pragma unroll 1
     for (int t = 0; t < nv; t += 2) {
       double sa0 = 0.0, sa1 = 0.0, sb0 = 0.0, sb1 = 0.0, ca = 0.0, cb = 0.0, ma = 0.0, mb = 0.0;
+      const bool on0 = t < 6 || ((sup0 >> (t - 5)) & 3u) != 0u, on1 = t < 6 || ((sup1 >> (t - 5)) & 3u) != 0u;
 #pragma unroll
       for (int r = 0; r < 12; r += 2) {
-        const double2 p = *reinterpret_cast<const double2*>(JF + r * TSIDB_NVX + t);
-        const double2 q = *reinterpret_cast<const double2*>(JF + (r + 1) * TSIDB_NVX + t);
-        sa0 += p.x * jf[r]; sb0 += p.y * jf[r];
-        sa1 += q.x * jf[r + 1]; sb1 += q.y * jf[r + 1];
+        if (r < 6 ? on0 : on1) {
+          const double2 p = *reinterpret_cast<const double2*>(JF + r * TSIDB_NVX + t);
+          const double2 q = *reinterpret_cast<const double2*>(JF + (r + 1) * TSIDB_NVX + t);
+          sa0 += p.x * jf[r]; sb0 += p.y * jf[r];
+          sa1 += q.x * jf[r + 1]; sb1 += q.y * jf[r + 1];
+        }
       }
 #pragma unroll
       for (int r = 0; r < 3; r++) {
