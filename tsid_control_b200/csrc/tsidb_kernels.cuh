@@ -638,19 +638,22 @@ TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, con
    * memory by asynchronous copies issued before K1 (stage_refs) */
   const double* rf = sm + SM_oRef;
   if (lane < 4) {
+    /* one pass for all four laws: the contact and the foot-task lanes differ only in their gains, their reference and
+     * in the reference velocity / acceleration (zero for a contact), so they run the same instructions (two divergent
+     * calls did the SE3 logarithm twice) */
     const int f = lane & 1;
     const bool is_contact = lane < 2;
-    double b6[6];
-    if (is_contact) {
-      se3_rhs(fr, f, C.kp_contact, C.kd_contact, rf + RF_CONTACT + 12 * f, nullptr, nullptr, b6);
+    double b6[6], kp[6], kd[6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) bv[BV_MOT + 6 * f + k] = b6[k];
-    } else {
-      const double* ref = rf + RF_FOOT + 24 * f;
-      se3_rhs(fr, f, C.kp_foot, C.kd_foot, ref, ref + 12, ref + 18, b6);
-#pragma unroll
-      for (int k = 0; k < 6; k++) bv[BV_FOOT + 6 * f + k] = b6[k];
+    for (int k = 0; k < 6; k++) {
+      kp[k] = is_contact ? C.kp_contact[k] : C.kp_foot[k];
+      kd[k] = is_contact ? C.kd_contact[k] : C.kd_foot[k];
     }
+    const double* ref = is_contact ? rf + RF_CONTACT + 12 * f : rf + RF_FOOT + 24 * f;
+    se3_rhs(fr, f, kp, kd, ref, is_contact ? nullptr : ref + 12, is_contact ? nullptr : ref + 18, b6);
+    double* dst = bv + (is_contact ? BV_MOT : BV_FOOT) + 6 * f;
+#pragma unroll
+    for (int k = 0; k < 6; k++) dst[k] = b6[k];
   } else if (lane < 7) {
     /* tsid::TaskComEquality */
     const int r = lane - 4;
