@@ -415,21 +415,38 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int
   for (int k = lane; k < 2 * 6 * TSIDB_NVX; k += 32) JF[k] = 0.0;
   __syncwarp();
 
-  /* F = Yc S for the body's own joint; nle, Jcom, Ag columns; M entries along the ancestors */
+  /* Lane roles from here on.  Joint lanes (1..nb-1) own column 5 + b of M, Jcom, Ag, JF.  The six base columns are
+   * formed by the lanes the tree leaves idle — base dof k on lane nb + k — with the base's motion subspace and the
+   * composite inertia of the whole robot, through the SAME instructions as the joint columns (round 1 ran them as a
+   * second, divergent pass on lanes 0..5). */
+  const bool isjoint = act && lane > 0;
+  const bool isbase = lane >= nb && lane < nb + 6;
+  const int kb = lane - nb; /* base dof of a base lane */
+  if (isbase) {
+    const int k = kb % 3;
+    const double rk[3] = {R0[k], R0[3 + k], R0[6 + k]};
+    if (kb < 3) { Sl_[0] = rk[0]; Sl_[1] = rk[1]; Sl_[2] = rk[2]; Sa_[0] = Sa_[1] = Sa_[2] = 0.0; }
+    else { cross3(p0, rk, Sl_); Sa_[0] = rk[0]; Sa_[1] = rk[1]; Sa_[2] = rk[2]; }
+  }
+  /* F = Yc S for the lane's column; nle, Jcom, Ag columns; M entries along the ancestors */
   double Fl[3], Fa[3];
   {
-    double mc = acc[0], hc[3] = {acc[1], acc[2], acc[3]}, t[3];
+    const double mc = isbase ? Y0[0] : acc[0];
+    double hc[3], Io[6], t[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) hc[k] = isbase ? Y0[1 + k] : acc[1 + k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) Io[k] = isbase ? Y0[4 + k] : acc[4 + k];
     cross3(Sa_, hc, t);
     Fl[0] = mc * Sl_[0] + t[0]; Fl[1] = mc * Sl_[1] + t[1]; Fl[2] = mc * Sl_[2] + t[2];
-    double Io[6] = {acc[4], acc[5], acc[6], acc[7], acc[8], acc[9]};
     Fa[0] = Io[0] * Sa_[0] + Io[1] * Sa_[1] + Io[2] * Sa_[2];
     Fa[1] = Io[1] * Sa_[0] + Io[3] * Sa_[1] + Io[4] * Sa_[2];
     Fa[2] = Io[2] * Sa_[0] + Io[4] * Sa_[1] + Io[5] * Sa_[2];
     cross3(hc, Sl_, t);
     Fa[0] += t[0]; Fa[1] += t[1]; Fa[2] += t[2];
-    if (act && lane > 0) {
-      const int c = 5 + b;
-      nle[c] = dot3(Sl_, &acc[10]) + dot3(Sa_, &acc[13]);
+    if (isjoint || isbase) {
+      const int c = isbase ? kb : 5 + b;
+      if (isjoint) nle[c] = dot3(Sl_, &acc[10]) + dot3(Sa_, &acc[13]);
       cross3(hc, Sa_, t);
 #pragma unroll
       for (int r = 0; r < 3; r++) Jcom[r * TSIDB_NVX + c] = (mc * Sl_[r] - t[r]) / mt;
@@ -444,8 +461,9 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int
       mtv3(R0, d, w);
 #pragma unroll
       for (int r = 0; r < 3; r++) {
-        Mm[r * SM_LDM + c] = u[r]; Mm[c * SM_LDM + r] = u[r];
-        Mm[(3 + r) * SM_LDM + c] = w[r]; Mm[c * SM_LDM + 3 + r] = w[r];
+        Mm[r * SM_LDM + c] = u[r];
+        Mm[(3 + r) * SM_LDM + c] = w[r];
+        if (isjoint) { Mm[c * SM_LDM + r] = u[r]; Mm[c * SM_LDM + 3 + r] = w[r]; }
       }
     }
   }
@@ -464,35 +482,6 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int
         j = pj;
       }
     }
-  }
-  /* base 6x6 block, base columns of Jcom/Ag, base nle: lanes 0..5, one base dof each */
-  if (lane < 6) {
-    const int k = lane % 3;
-    double rk[3] = {R0[k], R0[3 + k], R0[6 + k]};
-    double sl[3], sa[3];
-    if (lane < 3) { sl[0] = rk[0]; sl[1] = rk[1]; sl[2] = rk[2]; sa[0] = sa[1] = sa[2] = 0.0; }
-    else { cross3(p0, rk, sl); sa[0] = rk[0]; sa[1] = rk[1]; sa[2] = rk[2]; }
-    double hc[3] = {Y0[1], Y0[2], Y0[3]}, t[3], fl[3], fa[3];
-    cross3(sa, hc, t);
-    fl[0] = Y0[0] * sl[0] + t[0]; fl[1] = Y0[0] * sl[1] + t[1]; fl[2] = Y0[0] * sl[2] + t[2];
-    fa[0] = Y0[4] * sa[0] + Y0[5] * sa[1] + Y0[6] * sa[2];
-    fa[1] = Y0[5] * sa[0] + Y0[7] * sa[1] + Y0[8] * sa[2];
-    fa[2] = Y0[6] * sa[0] + Y0[8] * sa[1] + Y0[9] * sa[2];
-    cross3(hc, sl, t);
-    fa[0] += t[0]; fa[1] += t[1]; fa[2] += t[2];
-    double u[3], w[3];
-    mtv3(R0, fl, u);
-    cross3(p0, fl, t);
-    double d[3] = {fa[0] - t[0], fa[1] - t[1], fa[2] - t[2]};
-    mtv3(R0, d, w);
-#pragma unroll
-    for (int r = 0; r < 3; r++) { Mm[r * SM_LDM + lane] = u[r]; Mm[(3 + r) * SM_LDM + lane] = w[r]; }
-    cross3(hc, sa, t);
-#pragma unroll
-    for (int r = 0; r < 3; r++) Jcom[r * TSIDB_NVX + lane] = (Y0[0] * sl[r] - t[r]) / mt;
-    cross3(comw, fl, t);
-#pragma unroll
-    for (int r = 0; r < 3; r++) Ag[r * TSIDB_NVX + lane] = fa[r] - t[r];
   }
   {
     /* base nle = X0^T Fc_root; CoM quantities; centroidal angular momentum and its drift */
@@ -524,23 +513,47 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int
       }
     }
   }
-  /* operational frames (soles): placement, LOCAL velocity, classic-acceleration drift, LOCAL Jacobian */
-#pragma unroll
-  for (int f = 0; f < 2; f++) {
-    const int fb = C.foot_body[f];
-    /* every lane needs the placement of the foot's body (Jacobian columns); its twist and drift acceleration are
-     * only needed for the frame's own velocity terms, which the body's lane forms from its registers */
+  /* operational frames (soles): placement, LOCAL velocity, classic-acceleration drift, LOCAL Jacobian — ONE pass for both
+   * feet.  A joint lies on at most one foot's chain, so the joint lanes of the two legs form their columns at the same
+   * time, each with its own foot's frame; the base columns of foot 0 are formed by the base lanes nb..nb+5, those of
+   * foot 1 by the six lanes behind them (lane 0, the base body's, takes the one that does not fit below lane 32); the
+   * lanes of the two foot bodies form the frames' velocity terms.  (Round 1: a loop over the feet with three divergent
+   * blocks each.) */
+  {
+    static_assert(nb + 11 <= 32, "base columns of the second foot: five idle lanes and lane 0");
+    int fm = -1, col = 0; /* this lane's foot and Jacobian column */
+    if (isjoint) {
+      fm = ((C.foot_support[0] >> b) & 1u) ? 0 : (((C.foot_support[1] >> b) & 1u) ? 1 : -1);
+      col = 5 + b;
+    } else if (isbase) {
+      fm = 0; col = kb;
+    } else if (lane >= nb + 6 || lane == 0) {
+      const int k2 = (lane == 0) ? 32 - (nb + 6) : lane - (nb + 6); /* lanes nb+6..31 take dofs 0.., lane 0 the next one */
+      if (k2 < 6) {
+        fm = 1; col = k2;
+        const int k = k2 % 3;
+        const double rk[3] = {R0[k], R0[3 + k], R0[6 + k]};
+        if (k2 < 3) { Sl_[0] = rk[0]; Sl_[1] = rk[1]; Sl_[2] = rk[2]; Sa_[0] = Sa_[1] = Sa_[2] = 0.0; }
+        else { cross3(p0, rk, Sl_); Sa_[0] = rk[0]; Sa_[1] = rk[1]; Sa_[2] = rk[2]; }
+      }
+    }
+    const int fsel = fm < 0 ? 0 : fm;
+    const int fb = C.foot_body[fsel];
     double Rb[9], pb[3];
 #pragma unroll
     for (int k = 0; k < 9; k++) Rb[k] = shfl(R[k], fb);
 #pragma unroll
     for (int k = 0; k < 3; k++) pb[k] = shfl(p[k], fb);
+    double fRm[9], fpm[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) fRm[k] = fsel ? C.fR[1][k] : C.fR[0][k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) fpm[k] = fsel ? C.fp[1][k] : C.fp[0][k];
     double Rf[9], pf[3], t[3];
-    mm3(Rb, C.fR[f], Rf);
-    mv3(Rb, C.fp[f], pf);
+    mm3(Rb, fRm, Rf);
+    mv3(Rb, fpm, pf);
     pf[0] += pb[0]; pf[1] += pb[1]; pf[2] += pb[2];
-    /* column of this lane's own joint */
-    if (act && lane > 0 && ((C.foot_support[f] >> b) & 1u)) {
+    if (fm >= 0) {
       double la[3], ll[3];
       mtv3(Rf, Sa_, la);
       cross3(pf, Sa_, t);
@@ -548,27 +561,12 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int
       mtv3(Rf, d, ll);
 #pragma unroll
       for (int r = 0; r < 3; r++) {
-        JF[(f * 6 + r) * TSIDB_NVX + 5 + b] = ll[r];
-        JF[(f * 6 + 3 + r) * TSIDB_NVX + 5 + b] = la[r];
+        JF[(fm * 6 + r) * TSIDB_NVX + col] = ll[r];
+        JF[(fm * 6 + 3 + r) * TSIDB_NVX + col] = la[r];
       }
     }
-    if (lane < 6) {
-      const int k = lane % 3;
-      double rk[3] = {R0[k], R0[3 + k], R0[6 + k]}, sl[3], sa[3];
-      if (lane < 3) { sl[0] = rk[0]; sl[1] = rk[1]; sl[2] = rk[2]; sa[0] = sa[1] = sa[2] = 0.0; }
-      else { cross3(p0, rk, sl); sa[0] = rk[0]; sa[1] = rk[1]; sa[2] = rk[2]; }
-      double la[3], ll[3];
-      mtv3(Rf, sa, la);
-      cross3(pf, sa, t);
-      double d[3] = {sl[0] - t[0], sl[1] - t[1], sl[2] - t[2]};
-      mtv3(Rf, d, ll);
-#pragma unroll
-      for (int r = 0; r < 3; r++) {
-        JF[(f * 6 + r) * TSIDB_NVX + lane] = ll[r];
-        JF[(f * 6 + 3 + r) * TSIDB_NVX + lane] = la[r];
-      }
-    }
-    if (lane == fb) {
+    if (isjoint && lane == fb) {
+      const int f = fm;
       double vl[3], va[3], al[3], aa[3];
       mtv3(Rf, Va, va);
       cross3(pf, Va, t);
