@@ -698,11 +698,14 @@ TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, con
      * columns always do): the six rows of a foot are skipped for the column pairs off its chain — the arms' and the head's
      * pairs take neither foot, a leg's pairs one (the test is warp-uniform: t is the loop variable; adding the skipped
      * terms would add exact zeros, so the sums are unchanged bit for bit). */
-    const unsigned sup0 = C.foot_support[0], sup1 = C.foot_support[1];
+    /* bit t of pm0 / pm1 (t even): the column pair t, t+1 meets the chain of foot 0 / 1 (columns t >= 6 are the joints of
+     * bodies t-5, t-4; the base pairs always do) */
+    const unsigned pm0 = ((C.foot_support[0] | (C.foot_support[0] >> 1)) << 5) | 63u;
+    const unsigned pm1 = ((C.foot_support[1] | (C.foot_support[1] >> 1)) << 5) | 63u;
 #pragma unroll 1
     for (int t = 0; t < nv; t += 2) {
       double sa0 = 0.0, sa1 = 0.0, sb0 = 0.0, sb1 = 0.0, ca = 0.0, cb = 0.0, ma = 0.0, mb = 0.0;
-      const bool on0 = t < 6 || ((sup0 >> (t - 5)) & 3u) != 0u, on1 = t < 6 || ((sup1 >> (t - 5)) & 3u) != 0u;
+      const bool on0 = (pm0 >> t) & 1u, on1 = (pm1 >> t) & 1u;
 #pragma unroll
       for (int r = 0; r < 12; r += 2) {
         if (r < 6 ? on0 : on1) {
@@ -726,11 +729,12 @@ TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, con
         }
         ha += C.w_am * ma; hb += C.w_am * mb;
       }
-      if (t == j) ha += (j >= 6 ? C.w_post : 0.0) + C.hreg;
-      if (t + 1 == j) hb += (j >= 6 ? C.w_post : 0.0) + C.hreg;
       H[t * SM_LDM + j] = ha;
       H[(t + 1) * SM_LDM + j] = hb;
     }
+    /* the diagonal terms (posture weight on the joints, regulariser) go in after the loop: the lane that wrote H[j][j]
+     * adds them (inside the loop the two tests cost 28 instructions per trip, 7 % of the kernel) */
+    H[j * SM_LDM + j] += (j >= 6 ? C.w_post : 0.0) + C.hreg;
     double gf = 0.0, gc = 0.0, ga = 0.0;
 #pragma unroll
     for (int r = 0; r < 12; r++) gf += jf[r] * bv[BV_FOOT + r];
