@@ -33,6 +33,7 @@
 #ifndef TSIDB_KERNELS_CUH_
 #define TSIDB_KERNELS_CUH_
 
+#include <cstddef>
 #include "tsidb_const.h"
 
 #ifndef TSIDB_EMU
@@ -546,9 +547,9 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int
     for (int k = 0; k < 3; k++) pb[k] = shfl(p[k], fb);
     double fRm[9], fpm[3];
 #pragma unroll
-    for (int k = 0; k < 9; k++) fRm[k] = fsel ? C.fR[1][k] : C.fR[0][k];
+    for (int k = 0; k < 9; k++) fRm[k] = C.fR[fsel][k]; /* lane-indexed constant reads: two addresses per instruction */
 #pragma unroll
-    for (int k = 0; k < 3; k++) fpm[k] = fsel ? C.fp[1][k] : C.fp[0][k];
+    for (int k = 0; k < 3; k++) fpm[k] = C.fp[fsel][k];
     double Rf[9], pf[3], t[3];
     mm3(Rb, fRm, Rf);
     mv3(Rb, fpm, pf);
@@ -642,11 +643,14 @@ TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, con
     const int f = lane & 1;
     const bool is_contact = lane < 2;
     double b6[6], kp[6], kd[6];
+    /* kp_contact[6], kd_contact[6], kp_foot[6], kd_foot[6] are consecutive in DevConst: one lane-indexed constant read
+     * per gain instead of two reads and a select */
+    static_assert(offsetof(DevConst, kd_contact) == offsetof(DevConst, kp_contact) + 48 &&
+                  offsetof(DevConst, kp_foot) == offsetof(DevConst, kp_contact) + 96 &&
+                  offsetof(DevConst, kd_foot) == offsetof(DevConst, kp_contact) + 144, "gain tables are consecutive");
+    const double* gains = C.kp_contact + (is_contact ? 0 : 12);
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
-      kp[k] = is_contact ? C.kp_contact[k] : C.kp_foot[k];
-      kd[k] = is_contact ? C.kd_contact[k] : C.kd_foot[k];
-    }
+    for (int k = 0; k < 6; k++) { kp[k] = gains[k]; kd[k] = gains[6 + k]; }
     const double* ref = is_contact ? rf + RF_CONTACT + 12 * f : rf + RF_FOOT + 24 * f;
     se3_rhs(fr, f, kp, kd, ref, is_contact ? nullptr : ref + 12, is_contact ? nullptr : ref + 18, b6);
     double* dst = bv + (is_contact ? BV_MOT : BV_FOOT) + 6 * f;
@@ -706,15 +710,16 @@ TSIDB_DEV void k2_assemble(const DevConst& C, const double* mdl, double* sm, con
     for (int t = 0; t < nv; t += 2) {
       double sa0 = 0.0, sa1 = 0.0, sb0 = 0.0, sb1 = 0.0, ca = 0.0, cb = 0.0, ma = 0.0, mb = 0.0;
       const bool on0 = (pm0 >> t) & 1u, on1 = (pm1 >> t) & 1u;
-#pragma unroll
-      for (int r = 0; r < 12; r += 2) {
-        if (r < 6 ? on0 : on1) {
-          const double2 p = *reinterpret_cast<const double2*>(JF + r * TSIDB_NVX + t);
-          const double2 q = *reinterpret_cast<const double2*>(JF + (r + 1) * TSIDB_NVX + t);
-          sa0 += p.x * jf[r]; sb0 += p.y * jf[r];
-          sa1 += q.x * jf[r + 1]; sb1 += q.y * jf[r + 1];
-        }
-      }
+#define TSIDB_HFOOT(R0_)                                                                       \
+  _Pragma("unroll") for (int r = (R0_); r < (R0_) + 6; r += 2) {                                 \
+    const double2 p = *reinterpret_cast<const double2*>(JF + r * TSIDB_NVX + t);                 \
+    const double2 q = *reinterpret_cast<const double2*>(JF + (r + 1) * TSIDB_NVX + t);           \
+    sa0 += p.x * jf[r]; sb0 += p.y * jf[r];                                                      \
+    sa1 += q.x * jf[r + 1]; sb1 += q.y * jf[r + 1];                                              \
+  }
+      if (on0) { TSIDB_HFOOT(0) } /* one test per foot and trip (six, one per row pair, cost 145 instructions per env) */
+      if (on1) { TSIDB_HFOOT(6) }
+#undef TSIDB_HFOOT
 #pragma unroll
       for (int r = 0; r < 3; r++) {
         const double2 p = *reinterpret_cast<const double2*>(Jcom + r * TSIDB_NVX + t);
