@@ -116,13 +116,14 @@ def test_kinematics_match_oracle():
 
 
 @pytest.mark.parametrize("kind", ["v1", "v0"])
-def test_dynamics_terms_match_oracle(kind):
+def test_dynamics_terms_match_oracle(kind, monkeypatch):
     """SURVEY.md section 7 step 5 / rows a1-a2: what RobotWrapper::computeAllTerms and the solver's H, g build produce
     inside computeProblemData / solve (ref:main.py:119,121) — the joint-space inertia M, the non-linear effects h, the
     LOCAL sole Jacobians, the dv block of the Hessian and of the gradient — read back from the dynamics kernel's
     hand-off images (tsidb_debug_terms) and compared with the oracle's dump for every env of a small batch."""
     s = setup(kind)
     n = 24
+    monkeypatch.setenv("TSIDB_SMALL_N", "1024")  # read by tsidb_create: the single-launch path keeps slot == env
     ctrl = _controller(kind, n)
     q, v = synth.random_states(s["q0"], n, 17)
     step = (0.3, 0.2, 0.2, 0.5) if kind == "v1" else (0.1, 0.1275, 0.05, 0.7)
