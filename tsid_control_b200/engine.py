@@ -39,7 +39,12 @@ class TsidEngine:
         self.cm = model_to_c(model, lf_frame, rf_frame)
         self.cc = conf_to_c(conf, model, legacy=legacy)
         self.na, self.nv, self.nq = model.na, model.nv, model.nq
+        self._ref_dims = tuple(zip(REF_KEYS, (9, 24, 24, 12, 12, model.na)))
         self.device = torch.device("cuda", device)
+        self._dev_index = int(device)
+        self._tick_cache: Dict[tuple, TickOutput] = {}
+        self._refs_struct, self._aux_struct = TsidbRefs(), TsidbAuxOut()
+        self._refs_ref, self._aux_ref = C.byref(self._refs_struct), C.byref(self._aux_struct)
         self.max_envs = int(max_envs)
         h = C.c_void_p()
         check(self.lib.tsidb_create(C.byref(self.cm), C.byref(self.cc), self.max_envs, device, C.byref(h)), "tsidb_create")
@@ -59,12 +64,21 @@ class TsidEngine:
 
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> int:
-        return torch.cuda.current_stream(self.device).cuda_stream
+        """Raw handle of torch's current stream on the engine's device (the private fast getter when torch has it: the
+        public one builds a Stream object per call, 4 us of a 75 us single-robot tick)."""
+        try:
+            return torch._C._cuda_getCurrentRawStream(self._dev_index)
+        except AttributeError:
+            return torch.cuda.current_stream(self.device).cuda_stream
 
     def _chk(self, t: torch.Tensor, n: int, nd: int, name: str, dtype=torch.float64) -> torch.Tensor:
-        if not isinstance(t, torch.Tensor) or t.device != self.device or t.dtype != dtype:
+        try:
+            ok = t.is_cuda and t.dtype is dtype and t.get_device() == self._dev_index
+        except AttributeError:
+            ok = False
+        if not ok:
             raise TypeError(f"{name}: expected a {dtype} tensor on {self.device}")
-        if tuple(t.shape) != (n, nd) or not t.is_contiguous():
+        if t.shape != (n, nd) or not t.is_contiguous():
             raise ValueError(f"{name}: expected a contiguous [{n}, {nd}] tensor, got {tuple(t.shape)}")
         return t
 
@@ -85,15 +99,24 @@ class TsidEngine:
             # a few sizes stay resident (a single-robot kinematics()/solve() call between two batched ticks must
             # not evict the batch's buffers); the least recently created goes first
             while len(self._out_cache) >= 4:
-                self._out_cache.pop(next(iter(self._out_cache)))
+                old_n = next(iter(self._out_cache))
+                self._out_cache.pop(old_n)
+                for key in [k for k in self._tick_cache if k[0] == old_n]:
+                    self._tick_cache.pop(key)
             self._out_cache[n] = o
         return o
 
     def _tick_output(self, o: dict, aux: bool, want_active: bool) -> TickOutput:
-        """Fields the call did not write are None (never a stale or uninitialised buffer)."""
-        keys = ["tau", "ddq", "f", "status", "iters"] + (["active_set"] if want_active else []) + \
-               (["com", "foot_lf", "foot_rf", "wrench", "lam", "lam_row"] if aux else [])
-        return TickOutput(**{k: o[k] for k in keys})
+        """Fields the call did not write are None (never a stale or uninitialised buffer).  The view object is cached with
+        the buffers it wraps (the same tensors come back for the same batch size anyway)."""
+        key = (o["tau"].shape[0], aux, want_active)
+        t = self._tick_cache.get(key)
+        if t is None or t.tau is not o["tau"]:
+            keys = ["tau", "ddq", "f", "status", "iters"] + (["active_set"] if want_active else []) + \
+                   (["com", "foot_lf", "foot_rf", "wrench", "lam", "lam_row"] if aux else [])
+            t = TickOutput(**{k: o[k] for k in keys})
+            self._tick_cache[key] = t
+        return t
 
     # ------------------------------------------------------------------ API
     def set_default_refs(self, refs: Dict[str, np.ndarray]) -> None:
@@ -115,24 +138,27 @@ class TsidEngine:
         self._chk(q, n, self.nq, "q")
         self._chk(v, n, self.nv, "v")
         if contact_mask is not None:
-            if contact_mask.dtype != torch.uint8 or contact_mask.device != self.device or tuple(contact_mask.shape) != (n,):
+            if contact_mask.dtype is not torch.uint8 or not contact_mask.is_cuda or contact_mask.get_device() != self._dev_index \
+                    or contact_mask.shape != (n,):
                 raise TypeError("contact_mask: expected a uint8 [N] tensor on the engine's device")
-        r = TsidbRefs()
-        if refs:
-            for k, nd in zip(REF_KEYS, (9, 24, 24, 12, 12, self.na)):
-                t = refs.get(k)
-                if t is not None:
-                    setattr(r, k, self._chk(t, n, nd, f"refs[{k}]").data_ptr())
+        # the argument structs are reused from call to call (a single-robot tick is ~75 us: every microsecond of
+        # marshalling shows)
+        r = self._refs_struct
+        for k, nd in self._ref_dims:
+            t = refs.get(k) if refs else None
+            setattr(r, k, None if t is None else self._chk(t, n, nd, k).data_ptr())
         o = self._outputs(n, aux)
-        a = TsidbAuxOut()
         if aux:
+            a = self._aux_struct
             a.com, a.foot_lf, a.foot_rf, a.wrench = (o[k].data_ptr() for k in ("com", "foot_lf", "foot_rf", "wrench"))
             a.lambda_, a.lambda_row = o["lam"].data_ptr(), o["lam_row"].data_ptr()
+        ptrs = o.get("_ptrs")
+        if ptrs is None:
+            ptrs = o["_ptrs"] = tuple(o[k].data_ptr() for k in ("tau", "ddq", "f", "status", "iters", "active_set"))
         check(self.lib.tsidb_compute(
             self.h, n, 0, q.data_ptr(), v.data_ptr(), contact_mask.data_ptr() if contact_mask is not None else None,
-            C.byref(r), o["tau"].data_ptr(), o["ddq"].data_ptr(), o["f"].data_ptr(), o["status"].data_ptr(),
-            o["iters"].data_ptr(), o["active_set"].data_ptr() if want_active else None,
-            C.byref(a) if aux else None, self._stream()), "tsidb_compute")
+            self._refs_ref, ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5] if want_active else None,
+            self._aux_ref if aux else None, self._stream()), "tsidb_compute")
         return self._tick_output(o, aux, want_active)
 
     def host_buffers(self, n: int, pinned: bool = True) -> Dict[str, np.ndarray]:
