@@ -504,11 +504,12 @@ TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int
       cross3(comw, Pt, t);
       double t2[3];
       cross3(comw, fal, t2);
+      const double imt0 = 1.0 / mt; /* one reciprocal for this lane's six divisions by the total mass */
 #pragma unroll
       for (int r = 0; r < 3; r++) {
         fr[FR_COM + r] = comw[r];
-        fr[FR_COM + 3 + r] = Pt[r] / mt;
-        fr[FR_COM + 6 + r] = fal[r] / mt;
+        fr[FR_COM + 3 + r] = Pt[r] * imt0;
+        fr[FR_COM + 6 + r] = fal[r] * imt0;
         fr[FR_L + r] = Lt[r] - t[r];
         fr[FR_L + 3 + r] = faa[r] - t2[r];
       }
