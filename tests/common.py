@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import functools
 import importlib
+import os
 
 import numpy as np
 
@@ -291,3 +292,47 @@ def lambda_report(orc, mask, ok_idx, ref, lam_dev, lam_row_dev, na, nv):
         for r, a in ra.items():
             worst = max(worst, abs(rb[r] - a) / (1e-2 + abs(a)))
     return {"lambda_envs_compared": n_cmp, "lambda": worst, "lambda_min": float(min_lam)}
+
+
+# ------------------------------------------------------------------ reference-held model data (robot/v1/mujoco/robot.xml)
+def mjcf_golden():
+    """tests/golden/mjcf_v1.json: per-body tables and whole-body quantities of the reference's MuJoCo export of robot/v1
+    (made by tests/golden/make_mjcf_golden.py from ref:robot/v1/mujoco/robot.xml)."""
+    import json
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mjcf_v1.json")) as f:
+        return json.load(f)
+
+
+# the URDF hangs a frame-only dummy link on each foot (ref:robot/v1/urdf/robot_mod.urdf:176-191, :384-399: 0.01 kg,
+# 1e-4 kg m^2 isotropic, at the sole frame); Pinocchio merges it into the foot body, the MuJoCo export does not have it
+SOLE_DUMMY = {"left_ankle_roll": "left_sole_joint_fixed", "right_ankle_roll": "right_sole_joint_fixed"}
+
+
+def mjcf_case_q(model, case):
+    """Configuration of a golden case: torso at the origin with identity orientation, joints by name."""
+    q = np.zeros(model.nq)
+    q[6] = 1.0
+    for k, n in enumerate(model.joint_names):
+        q[7 + k] = case["q"][n]
+    return q
+
+
+def assert_whole_body_matches_mjcf(model, case, M, com):
+    """M: joint-space inertia of the configuration mjcf_case_q(case) (base block LOCAL), com: its centre of mass.  Total
+    mass, CoM and rotational inertia about the CoM in the torso frame, with the two sole dummies removed (placed with the
+    MuJoCo foot-body placements of the same configuration), against the MuJoCo file's values."""
+    mass, c = M[0, 0], np.asarray(com)
+    Io = M[3:6, 3:6]  # about the torso origin, torso axes
+    m2, mc2, I2 = mass, mass * c, Io.copy()
+    for jn, fn in SOLE_DUMMY.items():
+        fb = case["foot_bodies"][jn]
+        p = np.array(fb["p"]) + np.array(fb["R"]) @ model.frames[fn]["p"]
+        m2 -= 0.01
+        mc2 = mc2 - 0.01 * p
+        I2 -= 1e-4 * np.eye(3) + 0.01 * (p @ p * np.eye(3) - np.outer(p, p))
+    c2 = mc2 / m2
+    Ic2 = I2 - m2 * (c2 @ c2 * np.eye(3) - np.outer(c2, c2))
+    assert abs(m2 - case["mass"]) < 1e-9
+    assert np.abs(c2 - np.array(case["com"])).max() < 2e-6, np.abs(c2 - np.array(case["com"])).max()
+    assert np.abs(Ic2 - np.array(case["inertia_com"])).max() < 1e-5 * np.abs(Ic2).max()  # 0.707107-type literals

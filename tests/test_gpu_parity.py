@@ -148,6 +148,24 @@ def test_dynamics_terms_match_oracle(kind, monkeypatch):
     assert all(x < 1e-10 for x in worst.values()), worst
 
 
+def test_dynamics_kernel_against_the_references_mujoco_export(monkeypatch):
+    """Row a2 against reference-held data, no oracle in between: the joint-space inertia the dynamics kernel hands to the
+    solver (its base block = total mass and rotational inertia about the torso origin) and the CoM of the tick's aux outputs,
+    at the 12 configurations of tests/golden/mjcf_v1.json (made from ref:robot/v1/mujoco/robot.xml)."""
+    from common import assert_whole_body_matches_mjcf, mjcf_case_q, mjcf_golden
+
+    s, g = setup("v1"), mjcf_golden()
+    m, n = s["model"], len(g["cases"])
+    monkeypatch.setenv("TSIDB_SMALL_N", "1024")  # slot == env for tsidb_debug_terms
+    ctrl = _controller("v1", n)
+    q = np.stack([mjcf_case_q(m, c) for c in g["cases"]])
+    v = np.zeros((n, m.nv))
+    refs = {k: np.broadcast_to(a, (n,) + np.shape(a)).copy() for k, a in s["refs"].items()}
+    out = _run(ctrl, q, v, np.full(n, 3, dtype=np.uint8), refs)
+    for e, case in enumerate(g["cases"]):
+        assert_whole_body_matches_mjcf(m, case, ctrl.engine.debug_terms(e, 2)["M"], out["com"][e, :3])
+
+
 def test_constructor_references_match_reference_semantics():
     s = setup("v1")
     ctrl = _controller("v1", 4)

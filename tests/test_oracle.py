@@ -8,7 +8,7 @@
 import numpy as np
 import pytest
 
-from common import setup
+from common import SOLE_DUMMY, assert_whole_body_matches_mjcf, mjcf_case_q, mjcf_golden, setup
 from tsid_control_b200 import synth
 
 KINDS = ["v1", "v0"]
@@ -392,24 +392,11 @@ def test_integrate_matches_se3_exponential():
 
 
 # ------------------------------------------------------------------ reference-held model data (robot/v1/mujoco/robot.xml)
-def _mjcf_golden():
-    import json
-    import os
-
-    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mjcf_v1.json")) as f:
-        return json.load(f)
-
-
-# the URDF hangs a frame-only dummy link on each foot (ref:robot/v1/urdf/robot_mod.urdf:176-191, :384-399: 0.01 kg,
-# 1e-4 kg m^2 isotropic, at the sole frame); Pinocchio merges it into the foot body, the MuJoCo export does not have it
-_SOLE_DUMMY = {"left_ankle_roll": "left_sole_joint_fixed", "right_ankle_roll": "right_sole_joint_fixed"}
-
-
 def test_kat_model_tables_match_the_references_mujoco_export():
     """Body by body: joint placement, mass, lever and inertia tensor of the tables compiled from the URDF against the
     reference's independent MuJoCo export of the same CAD (tests/golden/make_mjcf_golden.py).  Tolerances are the
     print precision of the two files (6 significant digits; 1.5708 / 3.14159 literals in the URDF)."""
-    g, m = _mjcf_golden(), setup("v1")["model"]
+    g, m = mjcf_golden(), setup("v1")["model"]
     assert sorted(g["joint_names"]) == sorted(m.joint_names)
     body_of = {n: b + 1 for b, n in enumerate(m.joint_names)}
     body_of[None] = 0
@@ -420,8 +407,8 @@ def test_kat_model_tables_match_the_references_mujoco_export():
             assert np.abs(m.jp[b] - np.array(gb["pos"])).max() < 1e-8, gb["name"]
             assert np.abs(m.jR[b] - np.array(gb["R"])).max() < 2e-5, gb["name"]
         mass, com, I = m.mass[b], m.com[b], m.inertia[b]
-        if gb["joint"] in _SOLE_DUMMY:  # take the merged dummy link out again
-            fr = m.frames[_SOLE_DUMMY[gb["joint"]]]
+        if gb["joint"] in SOLE_DUMMY:  # take the merged dummy link out again
+            fr = m.frames[SOLE_DUMMY[gb["joint"]]]
             assert fr["body"] == b
             m2 = mass - 0.01
             c2 = (mass * com - 0.01 * fr["p"]) / m2
@@ -437,28 +424,9 @@ def test_kat_whole_body_quantities_match_the_references_mujoco_export():
     """The oracle's kinematics and CRBA (C code, tables from the URDF) against whole-body quantities evaluated from the
     MuJoCo file by an independent tree walk: total mass, CoM and rotational inertia about the CoM in the torso frame at
     12 joint configurations — joint order and sign, placements, levers and inertias all enter."""
-    g, s = _mjcf_golden(), setup("v1")
+    g, s = mjcf_golden(), setup("v1")
     m, orc = s["model"], s["oracle"]
     for case in g["cases"]:
-        q = np.zeros(m.nq)
-        q[6] = 1.0
-        for k, n in enumerate(m.joint_names):
-            q[7 + k] = case["q"][n]
+        q = mjcf_case_q(m, case)
         r = orc.tick(q, np.zeros(m.nv), 3, s["refs"], dump=True)
-        M = r["dump"]["M"]
-        mass, c = M[0, 0], r["com"][:3]
-        Io = M[3:6, 3:6]  # about the torso origin, torso axes (LOCAL base block of the CRBA)
-        Ic = Io - mass * (c @ c * np.eye(3) - np.outer(c, c))
-        # remove the two sole dummies, placed with the MuJoCo foot-body placements of the same configuration
-        m2, mc2, I2 = mass, mass * c, Io.copy()
-        for jn, fn in _SOLE_DUMMY.items():
-            fb = case["foot_bodies"][jn]
-            p = np.array(fb["p"]) + np.array(fb["R"]) @ m.frames[fn]["p"]
-            m2 -= 0.01
-            mc2 = mc2 - 0.01 * p
-            I2 -= 1e-4 * np.eye(3) + 0.01 * (p @ p * np.eye(3) - np.outer(p, p))
-        c2 = mc2 / m2
-        Ic2 = I2 - m2 * (c2 @ c2 * np.eye(3) - np.outer(c2, c2))
-        assert abs(m2 - case["mass"]) < 1e-9
-        assert np.abs(c2 - np.array(case["com"])).max() < 2e-6, np.abs(c2 - np.array(case["com"])).max()
-        assert np.abs(Ic2 - np.array(case["inertia_com"])).max() < 1e-5 * np.abs(Ic).max()  # 0.707107-type literals
+        assert_whole_body_matches_mjcf(m, case, r["dump"]["M"], r["com"][:3])
