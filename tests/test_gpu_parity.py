@@ -124,6 +124,7 @@ def test_dynamics_terms_match_oracle(kind, monkeypatch):
     s = setup(kind)
     n = 24
     monkeypatch.setenv("TSIDB_SMALL_N", "1024")  # read by tsidb_create: the single-launch path keeps slot == env
+    monkeypatch.setenv("TSIDB_SMALL_LOCAL_N", "0")  # ... and leaves its hand-off images in global memory
     ctrl = _controller(kind, n)
     q, v = synth.random_states(s["q0"], n, 17)
     step = (0.3, 0.2, 0.2, 0.5) if kind == "v1" else (0.1, 0.1275, 0.05, 0.7)
@@ -157,6 +158,7 @@ def test_dynamics_kernel_against_the_references_mujoco_export(monkeypatch):
     s, g = setup("v1"), mjcf_golden()
     m, n = s["model"], len(g["cases"])
     monkeypatch.setenv("TSIDB_SMALL_N", "1024")  # slot == env for tsidb_debug_terms
+    monkeypatch.setenv("TSIDB_SMALL_LOCAL_N", "0")  # hand-off images in global memory
     ctrl = _controller("v1", n)
     q = np.stack([mjcf_case_q(m, c) for c in g["cases"]])
     v = np.zeros((n, m.nv))

@@ -38,5 +38,5 @@ if __name__ == "__main__":
         probe()
     else:
         for small in os.environ.get("PROBE_SMALL", "1024,0").split(","):
-            r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, TSIDB_SMALL_N=small), capture_output=True, text=True)
+            r = subprocess.run([sys.executable, __file__, "child"], env={k: v for k, v in dict(os.environ, TSIDB_SMALL_N=small).items() if v != ""}, capture_output=True, text=True)
             print("TSIDB_SMALL_N=" + small, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:])

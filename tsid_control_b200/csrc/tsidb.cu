@@ -62,7 +62,9 @@ struct tsidb_handle {
   double* g_defaults;      /* device copy of the default references: com 9, feet 2x24, contacts 2x12 */
   int gait_ready;
   int gait_n;              /* envs initialised by the last tsidb_gait_reset */
+  double* tables;          /* TickArgs::tables */
   int small_n;             /* ticks of at most this many envs run as ONE launch (tsidb_tick_small_kernel); TSIDB_SMALL_N */
+  int small_local_n;       /* ... and of at most this many with the hand-off images in shared memory; TSIDB_SMALL_LOCAL_N */
 };
 
 /* ------------------------------------------------------------------ small kernels */
@@ -164,6 +166,10 @@ extern "C" const char* tsidb_last_error(void) { return g_err.c_str(); }
 static int upload_const(tsidb_handle* h) {
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpyToSymbol(g_const, &h->dc, sizeof(DevConst), (size_t)h->slot * sizeof(DevConst), cudaMemcpyHostToDevice));
+  /* the lane-indexed constants once more, as a global table in staging order (TickArgs::tables) */
+  tsidb_tables_kernel<<<1, 128>>>(h->slot, h->tables);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
   return 0;
 }
 
@@ -196,10 +202,16 @@ static int create_impl(tsidb_handle* h, const cudaDeviceProp& prop, int max_envs
   if (const char* e = getenv("TSIDB_D_CARVEOUT")) { const int v = atoi(e); if (v >= d_carve && v <= 100) d_carve = v; } /* tuning knob */
   TSIDB_ATTR(tsidb_dynamics_kernel<26>, smem, TSIDB_D_CTAS_PER_SM, "dynamics kernel", d_carve);
   TSIDB_ATTR(tsidb_dynamics_kernel<24>, smem, TSIDB_D_CTAS_PER_SM, "dynamics kernel", d_carve);
-  CK((cudaFuncSetAttribute(tsidb_tick_small_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSIDB_SMALL_SMEM_DOUBLES(26) * sizeof(double)))));
-  CK((cudaFuncSetAttribute(tsidb_tick_small_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSIDB_SMALL_SMEM_DOUBLES(24) * sizeof(double)))));
+  CK((cudaFuncSetAttribute(tsidb_tick_small_kernel<26, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSIDB_SMALL_SMEM_DOUBLES(26) * sizeof(double)))));
+  CK((cudaFuncSetAttribute(tsidb_tick_small_kernel<24, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSIDB_SMALL_SMEM_DOUBLES(24) * sizeof(double)))));
+  CK((cudaFuncSetAttribute(tsidb_tick_small_kernel<26, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSIDB_SMALL_LOCAL_SMEM_DOUBLES(26) * sizeof(double)))));
+  CK((cudaFuncSetAttribute(tsidb_tick_small_kernel<24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSIDB_SMALL_LOCAL_SMEM_DOUBLES(24) * sizeof(double)))));
   h->small_n = 1024;
   if (const char* e = getenv("TSIDB_SMALL_N")) h->small_n = atoi(e);
+  /* up to this many envs the single launch keeps the hand-off images in shared memory (3 envs per SM fit); the images of
+   * such a tick never reach global memory, so tsidb_debug_terms needs TSIDB_SMALL_LOCAL_N=0 */
+  h->small_local_n = 2 * prop.multiProcessorCount;
+  if (const char* e = getenv("TSIDB_SMALL_LOCAL_N")) h->small_local_n = atoi(e);
 #define TSIDB_E_SMEM(NV, NC) (((size_t)TSIDB_E_CTA_WARPS * e_per_env(NV, NC) + 144) * sizeof(double))
 #define TSIDB_E_ATTR(NV, NC, W) TSIDB_ATTR((tsidb_eliminate_kernel<NV, NC, W>), TSIDB_E_SMEM(NV, NC), (W) / TSIDB_E_CTA_WARPS, "elimination kernel", cudaSharedmemCarveoutMaxShared)
   TSIDB_E_ATTR(26, 2, TSIDB_E_WARPS); TSIDB_E_ATTR(26, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_ATTR(26, 0, TSIDB_E_WARPS_LIGHT);
@@ -211,6 +223,7 @@ static int create_impl(tsidb_handle* h, const cudaDeviceProp& prop, int max_envs
   CK(cudaMalloc(&h->ws3, (size_t)max_envs * SE_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->perm, (size_t)max_envs * sizeof(int32_t)));
   CK(cudaMalloc(&h->cls_pos, (size_t)max_envs * sizeof(int32_t)));
+  CK(cudaMalloc(&h->tables, TBL_SIZE * sizeof(double)));
   if (upload_const(h) != 0) return -2;
   /* host-call staging: inputs q(nq) v(nv) refs(9+24+24+12+12+na); outputs tau(na) ddq(nv) f(24) */
   const int na = h->dc.na, nv = h->dc.nv, nq = h->dc.nq;
@@ -290,7 +303,7 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
 extern "C" void tsidb_destroy(tsidb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaFree(h->counter); cudaFree(h->ws); cudaFree(h->ws3); cudaFree(h->perm); cudaFree(h->cls_pos);
+  cudaFree(h->counter); cudaFree(h->ws); cudaFree(h->ws3); cudaFree(h->perm); cudaFree(h->cls_pos); cudaFree(h->tables);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFree(h->d_in); cudaFree(h->d_out);
   cudaFreeHost(h->h_mask); cudaFree(h->d_mask);
   cudaFreeHost(h->h_int); cudaFree(h->d_int);
@@ -352,6 +365,7 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   int32_t* cls_pos = h->cls_pos + base;
   a.counter = counter;
   a.slot = h->slot;
+  a.tables = h->tables;
   a.ws = h->ws + (size_t)base * SA_IMAGE;
   a.ws3 = h->ws3 + (size_t)base * SE_IMAGE;
   a.perm = nullptr;
@@ -363,8 +377,13 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   if (!a.kin_only && !timed && n <= h->small_n) {
     /* small batch: one launch, one warp per env through all three stages (tsidb_tick_small_kernel) */
     NvtxRange r("tsidb:tick_small");
-    if (h->dc.nv == 26) tsidb_tick_small_kernel<26><<<n, 32, TSIDB_SMALL_SMEM_DOUBLES(26) * sizeof(double), st>>>(a);
-    else tsidb_tick_small_kernel<24><<<n, 32, TSIDB_SMALL_SMEM_DOUBLES(24) * sizeof(double), st>>>(a);
+    if (n <= h->small_local_n) {
+      if (h->dc.nv == 26) tsidb_tick_small_kernel<26, true><<<n, 32, TSIDB_SMALL_LOCAL_SMEM_DOUBLES(26) * sizeof(double), st>>>(a);
+      else tsidb_tick_small_kernel<24, true><<<n, 32, TSIDB_SMALL_LOCAL_SMEM_DOUBLES(24) * sizeof(double), st>>>(a);
+    } else {
+      if (h->dc.nv == 26) tsidb_tick_small_kernel<26, false><<<n, 32, TSIDB_SMALL_SMEM_DOUBLES(26) * sizeof(double), st>>>(a);
+      else tsidb_tick_small_kernel<24, false><<<n, 32, TSIDB_SMALL_SMEM_DOUBLES(24) * sizeof(double), st>>>(a);
+    }
     CK(cudaGetLastError());
     h->launches += 1;
     return 0;

@@ -81,6 +81,9 @@ struct DevConst {
 #define RF_POST 82
 #define SM_oQVn (SM_oRef + 106)         /* q (32) and v (32) of the warp's NEXT env, prefetched by asynchronous copies
                                            while the current env is computed         64 */
+#ifndef TSIDB_SMALL_PROFILE
+#define TSIDB_SMALL_PROFILE 0   /* 1: the single-launch kernel leaves clock stamps of its stages (tools/small_profile.py) */
+#endif
 #define SM_PER_ENV (SM_oQVn + 64)       /*                                       1608 */
 /* task vectors inside oBv */
 #define BV_MOT 0   /* 2 x 6 contact motion rhs, by foot */
@@ -131,6 +134,8 @@ struct TickArgs {
   const int32_t* perm; /* slot -> env (class sort), null = identity */
   int32_t kin_only;   /* stop after the kinematics (tsidb_kinematics) */
   int32_t slot;       /* constant-memory slot of the handle */
+  const double* tables; /* the lane-indexed constants in the order the kernels stage them in shared memory (TBL_*), made
+                         * once per handle by tsidb_tables_kernel: coalesced loads instead of lane-divergent constant reads */
 };
 
 #endif

@@ -197,6 +197,24 @@ TSIDB_DEV void stage_model(const DevConst& C, double* mdl, int tid, int nthreads
   }
 }
 
+/* the staged tables as one global array: [ model MDL_SIZE | Lf^-1 144 | LaneConst 19 x 32 ] */
+#define TBL_oMDL 0
+#define TBL_oLF ((MDL_SIZE + 1) & ~1)
+#define TBL_oLANE (TBL_oLF + 144)   /* LaneConst of the 32 lanes, value j of lane l at [j][l]: 19 x 32 */
+#define TBL_SIZE (TBL_oLANE + 19 * 32)
+TSIDB_DEV void load_table(double* dst, const double* src, int count /* even */, int tid, int nthreads) {
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+  double2* d2 = reinterpret_cast<double2*>(dst);
+  /* four loads in flight per trip: a single warp stages a table in three round trips to L2 instead of twelve */
+  for (int k0 = tid; k0 < count / 2; k0 += 4 * nthreads) {
+    double2 t[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int k = k0 + u * nthreads; if (k < count / 2) t[u] = s2[k]; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int k = k0 + u * nthreads; if (k < count / 2) d2[k] = t[u]; }
+  }
+}
+
 template <int NV>
 TSIDB_DEV void k1_dynamics(const DevConst& C, const double* mdl, double* sm, int lane) {
   constexpr int nb = NV - 5, nv = NV; /* bodies = floating base + NV - 6 revolute joints */
@@ -1310,6 +1328,17 @@ TSIDB_DEV void lane_const_init(const DevConst& C, LaneConst& K, int lane) {
   K.lb = K.ub = 0.0;
 }
 
+/* the same from the handle's table (TBL_oLANE): coalesced */
+TSIDB_DEV void lane_const_load(const double* tables, LaneConst& K, int lane) {
+  const double* t = tables + TBL_oLANE + lane;
+#pragma unroll
+  for (int j = 0; j < 12; j++) K.Trow[j] = t[j * 32];
+#pragma unroll
+  for (int j = 0; j < 3; j++) K.fric[j] = t[(12 + j) * 32];
+  K.tmin = t[15 * 32]; K.tmax = t[16 * 32]; K.vmin = t[17 * 32]; K.vmax = t[18 * 32];
+  K.lb = K.ub = 0.0;
+}
+
 /* s = CI x + ci0 for the rows this lane owns; invalid rows get +inf */
 TSIDB_DEV void eval_rows(const DevConst& C, const ASCtx& S, const LaneConst& K, int lane, int mask, double (&s)[6]) {
   const int na = S.na, nv = S.nv;
@@ -1907,14 +1936,18 @@ TSIDB_DEV void stage_refs_wait() {
  * `env_next` >= 0: ask for that env's q, v now — the copies travel with this env's references (one cp.async group, waited
  * for after K1), so the next call finds them without waiting on HBM (17.9 % of the kernel's samples were long-scoreboard
  * stalls, a third of them on these two loads at the head of an env). */
-template <int NV>
+/* LOCAL (single-launch small-batch kernel): a.ws / a.ws3 point at shared memory of the same CTA — the images are
+ * written with ordinary stores and the next stage works on them in place */
+template <int NV, bool LOCAL = false>
 TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, const TickArgs& a, int env, int slot, int lane,
                             bool prefetched = false, int env_next = -1) {
   constexpr int nv = NV, na = NV - 6, nq = NV + 1;
   PHASE_SYNC_D();
 #ifndef TSIDB_EMU
-  if (lane == 0) bulk_store_wait_read(); /* the previous env's image stores are done with this warp's shared memory */
-  __syncwarp();
+  if (!LOCAL) {
+    if (lane == 0) bulk_store_wait_read(); /* the previous env's image stores are done with this warp's shared memory */
+    __syncwarp();
+  }
 #endif
   /* stage q, v */
   if (prefetched) {
@@ -1987,7 +2020,15 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
   /* the two contiguous pieces (H | g, JF) leave as bulk asynchronous stores (TMA); the next env
    * of this warp waits for them to have read shared memory before it overwrites it */
   __syncwarp();
-  if (lane == 0) {
+  if (LOCAL) {
+    static_assert((SE_oH % 2) == 0 && (SM_oH % 2) == 0 && (SE_oJF % 2) == 0 && (SM_oJF % 2) == 0 && (TSIDB_NX % 2) == 0, "16-byte copies");
+    const double2* s0 = reinterpret_cast<const double2*>(sm + SM_oH);
+    double2* d0 = reinterpret_cast<double2*>(eimg + SE_oH);
+    for (int k = lane; k < (702 + TSIDB_NX) / 2; k += 32) d0[k] = s0[k];
+    const double2* s1 = reinterpret_cast<const double2*>(sm + SM_oJF);
+    double2* d1 = reinterpret_cast<double2*>(eimg + SE_oJF);
+    for (int k = lane; k < 312 / 2; k += 32) d1[k] = s1[k];
+  } else if (lane == 0) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     bulk_store(eimg + SE_oH, sm + SM_oH, (702 + TSIDB_NX) * sizeof(double)); /* SM_oGv follows SM_oH, SE_oG follows SE_oH */
     bulk_store(eimg + SE_oJF, sm + SM_oJF, 312 * sizeof(double));
@@ -2008,14 +2049,16 @@ TSIDB_DEV void dynamics_env(const DevConst& C, const double* mdl, double* sm, co
 template <int NV, int NC>
 TSIDB_DEV void j2_from_factor(const DevConst& C, const double* L, const double* ild, const double* tauq, const double* Vt,
                               double* img, int lane);
-template <int NV, int NC>
+template <int NV, int NC, bool LOCAL = false>
 TSIDB_DEV void eliminate_env(const DevConst& C, const double* lfinv_sm, double* sm, const TickArgs& a, int slot, int lane, unsigned& parity) {
   typedef EL<NV, NC> LE;
   __syncwarp(); /* every lane is done with the previous env's shared memory */
 #ifndef TSIDB_EMU
-  if (lane == 0) bulk_load(sm, a.ws3 + (size_t)slot * SE_IMAGE, SE_IMAGE * sizeof(double), sm + LE::oBar);
-  mbar_wait(sm + LE::oBar, parity);
-  parity ^= 1u;
+  if (!LOCAL) { /* LOCAL: sm IS the assembly image the dynamics stage left */
+    if (lane == 0) bulk_load(sm, a.ws3 + (size_t)slot * SE_IMAGE, SE_IMAGE * sizeof(double), sm + LE::oBar);
+    mbar_wait(sm + LE::oBar, parity);
+    parity ^= 1u;
+  }
 #else
   for (int k = lane; k < SE_IMAGE; k += 32) sm[k] = a.ws3[(size_t)slot * SE_IMAGE + k];
 #endif
@@ -2131,20 +2174,20 @@ TSIDB_DEV void j2_from_factor(const DevConst& C, const double* L, const double* 
 }
 
 /* ================================================================= kernel A: active set + decode of one env */
-template <int NV, int NC>
+template <int NV, int NC, bool LOCAL = false>
 TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const TickArgs& a, int env, int slot, int lane, unsigned& parity) {
   typedef AL<NV, NC> LA;
   constexpr int nv = NV, na = NV - 6;
   __syncwarp(); /* every lane is done with the previous env's shared memory */
 #ifndef TSIDB_EMU
-  /* the 21 KB solver image arrives as ONE bulk asynchronous copy (TMA); the warp waits on its mbarrier */
-  if (lane == 0) bulk_load(sm, a.ws + (size_t)slot * SA_IMAGE, LA::image * sizeof(double), sm + LA::oBar);
+  if (!LOCAL) { /* LOCAL: sm IS the solver image the two earlier stages filled */
+    /* the 21 KB solver image arrives as ONE bulk asynchronous copy (TMA); the warp waits on its mbarrier */
+    if (lane == 0) bulk_load(sm, a.ws + (size_t)slot * SA_IMAGE, LA::image * sizeof(double), sm + LA::oBar);
+    mbar_wait(sm + LA::oBar, parity);
+    parity ^= 1u;
+  }
 #else
   for (int k = lane; k < LA::image; k += 32) sm[k] = a.ws[(size_t)slot * SA_IMAGE + k];
-#endif
-#ifndef TSIDB_EMU
-  mbar_wait(sm + LA::oBar, parity);
-  parity ^= 1u;
 #endif
   __syncwarp();
   ASCtx S;
@@ -2213,6 +2256,21 @@ TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const 
 #ifndef TSIDB_EMU
 /* class sort: slots ordered double support, single support, flight, so that the warps of a CTA round in
  * kernel F have equal trip counts and kernel A starts with the longest jobs. */
+/* once per handle: the lane-indexed constants, laid out as the kernels stage them */
+__global__ void tsidb_tables_kernel(int slot, double* out) {
+  const DevConst& C = g_const[slot];
+  stage_model(C, out + TBL_oMDL, threadIdx.x, blockDim.x);
+  for (int i = threadIdx.x; i < 144; i += blockDim.x) out[TBL_oLF + i] = C.Lfinv[i / 12][i % 12];
+  if (threadIdx.x < 32) {
+    LaneConst K;
+    lane_const_init(C, K, threadIdx.x);
+    double* t = out + TBL_oLANE + threadIdx.x;
+    for (int j = 0; j < 12; j++) t[j * 32] = K.Trow[j];
+    for (int j = 0; j < 3; j++) t[(12 + j) * 32] = K.fric[j];
+    t[15 * 32] = K.tmin; t[16 * 32] = K.tmax; t[17 * 32] = K.vmin; t[18 * 32] = K.vmax;
+  }
+}
+
 __global__ void tsidb_classify_kernel(int n_envs, const uint8_t* mask, int32_t* cls_pos, int32_t* counts) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -2248,7 +2306,7 @@ tsidb_dynamics_kernel(const TickArgs a) {
   double* sm = smem + wid * SM_PER_ENV;
   const DevConst& C = g_const[a.slot];
   double* mdl = smem + TSIDB_WARPS_PER_BLOCK * SM_PER_ENV;
-  stage_model(C, mdl, threadIdx.x, blockDim.x);
+  load_table(mdl, a.tables + TBL_oMDL, MDL_SIZE, threadIdx.x, blockDim.x);
   __syncthreads();
   /* rounds: in every round the CTA's warps take consecutive slots and move through the phases together
    * (PHASE_SYNC).  A warp without a slot of its own in the last round repeats the last slot (it must reach
@@ -2303,7 +2361,7 @@ tsidb_eliminate_kernel(const TickArgs a) {
   if (count <= 0) return;
   /* the CTA's copy of the constant Lf^-1 (read with lane-dependent indices) */
   double* lfinv_sm = smem + TSIDB_E_CTA_WARPS * LE::per_env;
-  for (int i = threadIdx.x; i < 144; i += blockDim.x) lfinv_sm[i] = C.Lfinv[i / 12][i % 12];
+  load_table(lfinv_sm, a.tables + TBL_oLF, 144, threadIdx.x, blockDim.x);
   __syncthreads();
   int* counter = a.counter + 8 + NC;
   int k = 0;
@@ -2347,7 +2405,7 @@ tsidb_activeset_kernel(const TickArgs a) {
   if (lane == 0) mbar_init(sm + LA::oBar, 1);
   __syncwarp();
   LaneConst K;
-  lane_const_init(C, K, lane);
+  lane_const_load(a.tables, K, lane);
   unsigned parity = 0;
   int env = a.perm ? a.perm[start + k] : start + k;
   while (k < count) {
@@ -2383,52 +2441,84 @@ TSIDB_DEV void stage_handoff(int lane) {
   ((a_layout(NV, 2).per_env > e_per_env(NV, 2) + 144 ? a_layout(NV, 2).per_env : e_per_env(NV, 2) + 144) > SM_PER_ENV + MDL_SIZE \
        ? (a_layout(NV, 2).per_env > e_per_env(NV, 2) + 144 ? a_layout(NV, 2).per_env : e_per_env(NV, 2) + 144)         \
        : SM_PER_ENV + MDL_SIZE)
-template <int NV>
-__global__ void __launch_bounds__(32, 1) tsidb_tick_small_kernel(const TickArgs a) {
+/* LOCAL variant: the three stages own disjoint shared-memory regions (dynamics | elimination + Lf^-1 | active set); the
+ * dynamics stage writes the assembly image into the elimination's region and its part of the solver image into the
+ * active set's, the elimination adds x0 and the basis, and each stage works on its image IN PLACE: no store drain, no
+ * fence, no bulk load between the stages.  70 KB per env instead of 27, so the host uses it for the smallest batches
+ * only (TSIDB_SMALL_LOCAL_N). */
+#define TSIDB_SMALL_oE(NV) (even_up(SM_PER_ENV + MDL_SIZE))
+#define TSIDB_SMALL_oA(NV) (TSIDB_SMALL_oE(NV) + even_up(e_per_env(NV, 2) + 144))
+#define TSIDB_SMALL_LOCAL_SMEM_DOUBLES(NV) (TSIDB_SMALL_oA(NV) + even_up(a_layout(NV, 2).per_env))
+template <int NV, bool LOCAL>
+__global__ void __launch_bounds__(32, 1) tsidb_tick_small_kernel(const TickArgs a_in) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x;
   const int env = blockIdx.x; /* slot == env: no class sort */
-  const DevConst& C = g_const[a.slot];
-  double* sm = smem;
+  const DevConst& C = g_const[a_in.slot];
+  double* smE = LOCAL ? smem + TSIDB_SMALL_oE(NV) : smem;
+  double* smA = LOCAL ? smem + TSIDB_SMALL_oA(NV) : smem;
+  TickArgs a = a_in;
+  if (LOCAL) { a.ws = smA; a.ws3 = smE; }
+  const int slot = LOCAL ? 0 : env;
+#if TSIDB_SMALL_PROFILE
+  /* clock stamps of the stages of env 0 (tools/small_profile.py reads them back through tsidb_debug_terms) */
+  long long stamp[8];
+  int n_stamp = 0;
+#define TSIDB_STAMP() do { __syncwarp(); stamp[n_stamp++] = clock64(); } while (0)
+#else
+#define TSIDB_STAMP() ((void)0)
+#endif
+  TSIDB_STAMP();
   {
     double* mdl = smem + SM_PER_ENV;
-    stage_model(C, mdl, lane, 32);
+    load_table(mdl, a.tables + TBL_oMDL, MDL_SIZE, lane, 32);
     __syncwarp();
-    dynamics_env<NV>(C, mdl, sm, a, env, env, lane);
+    TSIDB_STAMP();
+    dynamics_env<NV, LOCAL>(C, mdl, smem, a, env, slot, lane);
   }
-  stage_handoff(lane);
+  if (LOCAL) __syncwarp(); else stage_handoff(lane);
+  TSIDB_STAMP();
   const int mask = a.mask ? (a.mask[env] & 3) : 3;
   const int nc = (mask & 1) + ((mask >> 1) & 1);
   {
-    double* lfinv_sm = smem + e_per_env(NV, 2);
-    for (int i = lane; i < 144; i += 32) lfinv_sm[i] = C.Lfinv[i / 12][i % 12];
+    double* lfinv_sm = smE + e_per_env(NV, 2);
+    load_table(lfinv_sm, a.tables + TBL_oLF, 144, lane, 32);
+    TSIDB_STAMP();
     unsigned parity = 0;
 #define TSIDB_SMALL_E(NC_)                                                                 \
   {                                                                                          \
-    double* bar = sm + EL<NV, NC_>::oBar;                                                    \
-    if (lane == 0) mbar_init(bar, 1);                                                        \
+    double* bar = smE + EL<NV, NC_>::oBar;                                                   \
+    if (!LOCAL && lane == 0) mbar_init(bar, 1);                                              \
     __syncwarp();                                                                            \
-    eliminate_env<NV, NC_>(C, lfinv_sm, sm, a, env, lane, parity);                           \
-    if (lane == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); \
+    eliminate_env<NV, NC_, LOCAL>(C, lfinv_sm, smE, a, slot, lane, parity);                  \
+    if (!LOCAL && lane == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); \
   }
     if (nc == 2) TSIDB_SMALL_E(2) else if (nc == 1) TSIDB_SMALL_E(1) else TSIDB_SMALL_E(0)
 #undef TSIDB_SMALL_E
   }
-  stage_handoff(lane);
+  if (LOCAL) __syncwarp(); else stage_handoff(lane);
+  TSIDB_STAMP();
   {
     LaneConst K;
-    lane_const_init(C, K, lane);
+    lane_const_load(a.tables, K, lane);
+    TSIDB_STAMP();
     unsigned parity = 0;
 #define TSIDB_SMALL_A(NC_)                                                                 \
   {                                                                                          \
-    double* bar = sm + AL<NV, NC_>::oBar;                                                    \
-    if (lane == 0) mbar_init(bar, 1);                                                        \
+    double* bar = smA + AL<NV, NC_>::oBar;                                                   \
+    if (!LOCAL && lane == 0) mbar_init(bar, 1);                                              \
     __syncwarp();                                                                            \
-    activeset_env<NV, NC_>(C, K, sm, a, env, env, lane, parity);                             \
+    activeset_env<NV, NC_, LOCAL>(C, K, smA, a, env, slot, lane, parity);                    \
   }
     if (nc == 2) TSIDB_SMALL_A(2) else if (nc == 1) TSIDB_SMALL_A(1) else TSIDB_SMALL_A(0)
 #undef TSIDB_SMALL_A
   }
+  TSIDB_STAMP();
+#if TSIDB_SMALL_PROFILE
+  if (env == 0 && lane == 0)
+    for (int k = 0; k < n_stamp; k++) a_in.ws3[k] = (double)(stamp[k] - stamp[0]);
+#endif
+#undef TSIDB_STAMP
 }
 #endif
 
