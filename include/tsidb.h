@@ -36,6 +36,8 @@
  *   TSIDB_CLASS_STREAMS=0   read by tsidb_create: keep every kernel of a tick on the caller's stream
  *   TSIDB_SMALL_N=n         read by tsidb_create: ticks of at most n envs (default 1024) run as ONE launch, one warp per env
  *                           through all three stages (no class sort, no per-class launches); 0 = always the batched pipeline
+ *   TSIDB_SMALL_LOCAL_N=n   read by tsidb_create: such ticks of at most n envs (default 2 per SM) keep the hand-off images
+ *                           between the stages in shared memory; 0 = always through global memory (tsidb_debug_terms needs it)
  *   TSIDB_HOST_CHUNKS=k     read by tsidb_compute_host: k equal chunks instead of the tapered 1/8,3/8,3/8,1/8 split
  *   TSIDB_HOST_TAPER=d      read by tsidb_compute_host: first/last chunk = 1/d of the batch
  *   TSIDB_HOST_SPLIT=a,b,.. read by tsidb_compute_host: chunk sizes in 64ths of the batch (sum 64), e.g. 8,16,24,16
@@ -221,7 +223,8 @@ int tsidb_compute_host_devrefs(tsidb_handle* h, int n_envs, const double* q, con
  * Hessian H [nv][nv] (lower triangle significant) and the dv part of the gradient g [nv] — what
  * RobotWrapper::computeAllTerms / the solver's H, g build produce inside ref:main.py:119,121.  Host pointers;
  * synchronous.  Valid when the last tick ran without a contact mask or with at most TSIDB_SMALL_N envs (no class sort:
- * slot == env); n_contacts = contacts of that env in that tick. */
+ * slot == env) on a handle created with TSIDB_SMALL_LOCAL_N=0 (the images of the smallest ticks otherwise stay in shared
+ * memory); n_contacts = contacts of that env in that tick. */
 int tsidb_debug_terms(tsidb_handle* h, int env, int n_contacts, double* M, double* nle, double* JF, double* H, double* g);
 
 /* controller.integrate_dv(q, v, dv, dt) (ref:ctrl/WalkController.py:291-295,
