@@ -285,12 +285,13 @@ def test_chunked_host_call_agrees_with_device_call(n, pinned):
     assert (t["ddq"] == -7.0).all() and (t["f"] == -7.0).all()
 
 
-@pytest.mark.parametrize("kind,n", [("v1", 1), ("v1", 97), ("v1", 1024), ("v0", 333)])
+@pytest.mark.parametrize("kind,n", [("v1", 1), ("v1", 97), ("v1", 1024), ("v0", 64), ("v0", 333)])
 def test_single_launch_small_batch_tick_equals_the_batched_pipeline(kind, n, monkeypatch):
     """Ticks of at most TSIDB_SMALL_N envs (default 1024) run as one launch (tsidb_tick_small_kernel: one warp per env
     through dynamics, elimination and active set).  It calls the stage functions of the batched kernels, so every
     output — tau, ddq, f, status, iters, working sets, multipliers, kinematics — must equal the batched pipeline's bit
-    for bit, on all three contact classes."""
+    for bit, on all three contact classes.  Up to 2 envs per SM (1, 97, 64 here) the kernel keeps its hand-off images in
+    shared memory (TSIDB_SMALL_LOCAL_N), above that (333, 1024) they travel through global memory: both variants are covered."""
     s = setup(kind)
     q, v = synth.random_states(s["q0"], n, 41)
     step = (0.3, 0.2, 0.2, 0.5) if kind == "v1" else (0.1, 0.1275, 0.05, 0.7)
