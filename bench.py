@@ -342,6 +342,14 @@ def main() -> None:
         replay = snaps
         fails = int((s.eng.gait_state()["fails"] > 0).sum().item())
 
+    # Scheduling hint (tsidb_set_sched_hint): envs of a contact class ordered by their iteration counts in the previous
+    # tick.  A synthetic batch that is ticked again unchanged would make that forecast exact, so the headline of the
+    # synthetic workloads is measured with the hint OFF; a replayed rollout (consecutive snapshots 10 ms apart) gives it
+    # the forecast a controller has, and is measured with it ON.  The other setting is timed afterwards and reported.
+    hint_main = replay is not None
+    for s in shards:
+        s.eng.set_sched_hint(hint_main)
+
     step_no = [0]
 
     def step():
@@ -396,6 +404,29 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     value = n_global * args.steps / (total_ms * 1e-3)
+
+    def timed_value(k):
+        """ticks/s over k more steps with the current hint setting (same flush, events and max over ranks)."""
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev = []
+        for _ in range(k):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step()
+            b.record()
+            ev.append((a, b))
+        torch.cuda.synchronize()
+        tot = sum(a.elapsed_time(b) for a, b in ev)
+        if world > 1:
+            tt = torch.tensor([tot], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tot = float(tt.item())
+        return n_global * k / (tot * 1e-3)
 
     status_np = np.concatenate([st.cpu().numpy() for st, _ in res])
     iters_np = np.concatenate([it.cpu().numpy() for _, it in res])
@@ -507,6 +538,22 @@ def main() -> None:
                    "api": "tsidb_compute_host_devrefs: q and v from pinned host buffers; references and contact phases resident on the "
                           "device (the gait state the device phase machine keeps), results into pinned host buffers"}
 
+    # ---- the other setting of the scheduling hint (see above), on every rank ----
+    for s in shards:
+        s.eng.set_sched_hint(not hint_main)
+    value_other = timed_value(max(3, min(args.steps, 10)))
+    for s in shards:
+        s.eng.set_sched_hint(hint_main)
+    sched_hint = {
+        "headline": "on" if hint_main else "off", "value_on": value if hint_main else value_other,
+        "value_off": value_other if hint_main else value, "unit": UNIT,
+        "note": ("envs of a contact class ordered by their iteration counts in the previous tick (tsidb_set_sched_hint; never "
+                 "changes a result).  " +
+                 ("Replayed rollout: the previous tick is the snapshot 10 ms earlier, the forecast a controller has - headline with it."
+                  if hint_main else
+                  "Synthetic batch ticked again unchanged: the forecast would be exact, so value / e2e are measured WITHOUT it; "
+                  "value_on is the same loop with it."))}
+
     # the sampler ran from the start of the timed region to here: the GPU was under the same tick load throughout
     # (timed steps, per-kernel timing steps, end-to-end steps), which gives nvidia-smi time for several samples
     clocks = sampler.stop()
@@ -558,6 +605,7 @@ def main() -> None:
         "clocks": clocks,
         "solver": {"mean_iters": float(iters_np.mean()), "max_iters": int(iters_np.max()),
                    "status_optimal_frac": float((status_np == 0).mean())},
+        "sched_hint": sched_hint,
         "tick_latency_1env_us_p50": lat,
         "tick_latency_1env_us_p50_by_class": lat_by_class or None,
     }

@@ -38,6 +38,7 @@
  *                           through all three stages (no class sort, no per-class launches); 0 = always the batched pipeline
  *   TSIDB_SMALL_LOCAL_N=n   read by tsidb_create: such ticks of at most n envs (default 2 per SM) keep the hand-off images
  *                           between the stages in shared memory; 0 = always through global memory (tsidb_debug_terms needs it)
+ *   TSIDB_SCHED_HINT=0      read by tsidb_create: no longest-first order inside the contact classes (tsidb_set_sched_hint)
  *   TSIDB_HOST_CHUNKS=k     read by tsidb_compute_host: k equal chunks instead of the tapered 1/8,3/8,3/8,1/8 split
  *   TSIDB_HOST_TAPER=d      read by tsidb_compute_host: first/last chunk = 1/d of the batch
  *   TSIDB_HOST_SPLIT=a,b,.. read by tsidb_compute_host: chunk sizes in 64ths of the batch (sum 64), e.g. 8,16,24,16
@@ -304,6 +305,13 @@ int64_t tsidb_launch_count(const tsidb_handle* h);
  * slightly more than an untimed tick takes.                                                      */
 int tsidb_set_timing(tsidb_handle* h, int on);
 int tsidb_last_tick_ms(tsidb_handle* h, float* ms5);
+
+/* Scheduling hint (no counterpart in the reference; never changes a result).  The class sort of a tick orders the envs
+ * of a contact class by their active-set iteration count in the handle's PREVIOUS tick, most iterations first, so the
+ * longest solves start first and the per-class kernels end with a shorter tail.  In closed loop the counts change slowly
+ * from tick to tick (a replayed rollout: tick -1.8 %); for a batch that is ticked again unchanged the forecast is exact
+ * (-5 %).  On by default (TSIDB_SCHED_HINT=0 at tsidb_create turns it off); off, every env of a class shares one bucket. */
+int tsidb_set_sched_hint(tsidb_handle* h, int on);
 
 /* ---- the reference's planners on the device, one thread per env ---------------------------
  * tsidb_foot_trajectory: FootTrajectory(t = [t0, t1], start, target, step_height, rise_ratio) of

@@ -25,6 +25,7 @@ class TickArgs(C.Structure):
         ("status", C.c_void_p), ("iters", C.c_void_p), ("active", C.c_void_p),
         ("o_com", C.c_void_p), ("o_foot", C.c_void_p * 2), ("o_wrench", C.c_void_p), ("o_lambda", C.c_void_p), ("o_lambda_row", C.c_void_p),
         ("counter", C.c_void_p), ("ws", C.c_void_p), ("ws3", C.c_void_p), ("perm", C.c_void_p), ("kin_only", C.c_int32), ("slot", C.c_int32),
+        ("pred", C.c_void_p), ("tables", C.c_void_p),
     ]
 
 

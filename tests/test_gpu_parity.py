@@ -695,6 +695,31 @@ def test_class_chains_on_streams_equal_the_single_stream_tick(monkeypatch):
     assert (outs[0]["status"] == 0).mean() > 0.99
 
 
+def test_longest_first_order_of_the_class_sort_changes_no_result(monkeypatch):
+    """tsidb_set_sched_hint: from the second tick of a handle on, the class sort orders the envs of a contact class by their
+    iteration counts in the previous tick.  The slot an env lands in must not matter: every output of a second tick with
+    the hint equals the tick of a handle without it bit for bit (and the hint can be switched per handle at run time)."""
+    kind, n = "v1", 6000
+    s = setup(kind)
+    q, v = synth.random_states(s["q0"], n, 77)
+    mask, refs = synth.walking_batch(s["refs"], n, 77, 0.3, 0.2, 0.2, 0.5, float(s["refs"]["com"][2]))
+    mask[11] = 0
+    monkeypatch.setenv("TSIDB_SMALL_N", "0")
+    monkeypatch.setenv("TSIDB_SCHED_HINT", "0")
+    plain = _run(_controller(kind, n), q, v, mask, refs)
+    monkeypatch.setenv("TSIDB_SCHED_HINT", "1")
+    ctrl = _controller(kind, n)
+    first = _run(ctrl, q, v, mask, refs)    # no previous tick: one bucket per class
+    second = _run(ctrl, q, v, mask, refs)   # ordered by the first tick's iteration counts
+    ctrl.engine.set_sched_hint(False)
+    third = _run(ctrl, q, v, mask, refs)
+    assert int(second["iters"].max()) >= 12  # several buckets are in use
+    for out in (first, second, third):
+        for k in plain:
+            if plain[k] is not None:
+                assert np.array_equal(out[k], plain[k], equal_nan=True), k
+
+
 @pytest.mark.parametrize("tag,rr", [("r50", 0.5), ("r10", 0.1)])
 def test_device_foot_trajectory_kernel_against_the_reference_golden(tag, rr):
     """tsidb_foot_trajectory (CUDA) against the samples of the reference's own scipy CubicSplines

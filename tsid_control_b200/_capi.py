@@ -235,6 +235,8 @@ def load_library() -> C.CDLL:
     lib.tsidb_launch_count.restype = C.c_int64
     lib.tsidb_set_timing.argtypes = [vp, ip]
     lib.tsidb_set_timing.restype = ip
+    lib.tsidb_set_sched_hint.argtypes = [vp, ip]
+    lib.tsidb_set_sched_hint.restype = ip
     lib.tsidb_last_tick_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.tsidb_last_tick_ms.restype = ip
     lib.tsidb_gait_reset.argtypes = [vp, ip, C.POINTER(TsidbGaitConf), vp, vp, vp]
@@ -268,7 +270,7 @@ def check(rc: int, what: str) -> None:
 EXPORTED_SYMBOLS = [
     "tsidb_create", "tsidb_destroy", "tsidb_last_error", "tsidb_sizes", "tsidb_set_default_refs",
     "tsidb_compute", "tsidb_compute_host", "tsidb_compute_host_devrefs", "tsidb_integrate", "tsidb_kinematics", "tsidb_ci_row",
-    "tsidb_fp64_peak", "tsidb_launch_count", "tsidb_set_timing", "tsidb_last_tick_ms",
+    "tsidb_fp64_peak", "tsidb_launch_count", "tsidb_set_timing", "tsidb_set_sched_hint", "tsidb_last_tick_ms",
     "tsidb_gait_reset", "tsidb_gait_state", "tsidb_gait_step", "tsidb_rollout", "tsidb_diagnostics",
     "tsidb_foot_trajectory", "tsidb_footstep_plan", "tsidb_gait_set_plan", "tsidb_debug_terms",
 ]

@@ -31,11 +31,12 @@ static bool g_slot_used[8][TSIDB_MAX_SLOTS]; /* per device */
 
 #define TSIDB_HOST_STREAMS 3   /* tsidb_compute_host: chunks rotate over these streams (copy/compute overlap) */
 #define TSIDB_MAX_CHUNKS 8     /* independent work counters / workspace windows */
+#define TSIDB_NCOUNTER 48      /* ints per chunk: 16 work counters and class sizes, then the bins of the class sort */
 
 struct tsidb_handle {
   int device, slot, max_envs, sm_count;
   DevConst dc;
-  int32_t* counter;      /* device, 16 per chunk: work counters of the active-set ([0],[4],[5]), elimination ([8..10]) and basis ([12..14]) kernels, [1..3] class sizes */
+  int32_t* counter;      /* device, TSIDB_NCOUNTER per chunk ([16..16+TSIDB_NKEY): sizes of the (class, bucket) bins of the class sort): work counters of the active-set ([0],[4],[5]), elimination ([8..10]) and basis ([12..14]) kernels, [1..3] class sizes */
   double* ws;            /* device: solver images, SA_IMAGE doubles per slot */
   double* ws3;           /* device: assembly images, SE_IMAGE doubles per slot */
   int32_t* perm;         /* device: slot -> env */
@@ -63,6 +64,8 @@ struct tsidb_handle {
   int gait_ready;
   int gait_n;              /* envs initialised by the last tsidb_gait_reset */
   double* tables;          /* TickArgs::tables */
+  int32_t* pred;           /* [max_envs] iteration counts of the previous tick (longest-first order of the class sort) */
+  int sched_hint;          /* TSIDB_SCHED_HINT (default 1): use them */
   int small_n;             /* ticks of at most this many envs run as ONE launch (tsidb_tick_small_kernel); TSIDB_SMALL_N */
   int small_local_n;       /* ... and of at most this many with the hand-off images in shared memory; TSIDB_SMALL_LOCAL_N */
 };
@@ -218,7 +221,11 @@ static int create_impl(tsidb_handle* h, const cudaDeviceProp& prop, int max_envs
   TSIDB_E_ATTR(24, 2, TSIDB_E_WARPS); TSIDB_E_ATTR(24, 1, TSIDB_E_WARPS_LIGHT); TSIDB_E_ATTR(24, 0, TSIDB_E_WARPS_LIGHT);
 #undef TSIDB_E_ATTR
 #undef TSIDB_ATTR
-  CK(cudaMalloc(&h->counter, 16 * TSIDB_MAX_CHUNKS * sizeof(int32_t)));
+  CK(cudaMalloc(&h->counter, TSIDB_NCOUNTER * TSIDB_MAX_CHUNKS * sizeof(int32_t)));
+  CK(cudaMalloc(&h->pred, (size_t)max_envs * sizeof(int32_t)));
+  CK(cudaMemset(h->pred, 0, (size_t)max_envs * sizeof(int32_t)));
+  h->sched_hint = 1;
+  if (const char* e = getenv("TSIDB_SCHED_HINT")) h->sched_hint = atoi(e);
   CK(cudaMalloc(&h->ws, (size_t)max_envs * SA_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->ws3, (size_t)max_envs * SE_IMAGE * sizeof(double)));
   CK(cudaMalloc(&h->perm, (size_t)max_envs * sizeof(int32_t)));
@@ -303,7 +310,7 @@ extern "C" int tsidb_create(const tsidb_model* model, const tsidb_conf* conf, in
 extern "C" void tsidb_destroy(tsidb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaFree(h->counter); cudaFree(h->ws); cudaFree(h->ws3); cudaFree(h->perm); cudaFree(h->cls_pos); cudaFree(h->tables);
+  cudaFree(h->counter); cudaFree(h->ws); cudaFree(h->ws3); cudaFree(h->perm); cudaFree(h->cls_pos); cudaFree(h->tables); cudaFree(h->pred);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFree(h->d_in); cudaFree(h->d_out);
   cudaFreeHost(h->h_mask); cudaFree(h->d_mask);
   cudaFreeHost(h->h_int); cudaFree(h->d_int);
@@ -360,12 +367,13 @@ extern "C" int tsidb_set_default_refs(tsidb_handle* h, const double* com9, const
 static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base = 0, int chunk = 0) {
   CK(cudaSetDevice(h->device));
   if (base + a.n_envs > h->max_envs) { g_err = "n_envs exceeds the handle's max_envs (workspace size)"; return -1; }
-  int32_t* counter = h->counter + 16 * chunk; /* [0],[4],[5]: active-set work counters per class, [1..3]: class sizes, [8..10]: elimination, [12..14]: basis work counters */
+  int32_t* counter = h->counter + TSIDB_NCOUNTER * chunk; /* [0],[4],[5]: active-set work counters per class, [1..3]: class sizes, [8..10]: elimination, [12..14]: basis work counters */
   int32_t* perm = h->perm + base;
   int32_t* cls_pos = h->cls_pos + base;
   a.counter = counter;
   a.slot = h->slot;
   a.tables = h->tables;
+  a.pred = h->pred + base;
   a.ws = h->ws + (size_t)base * SA_IMAGE;
   a.ws3 = h->ws3 + (size_t)base * SE_IMAGE;
   a.perm = nullptr;
@@ -390,12 +398,12 @@ static int launch_tick(tsidb_handle* h, TickArgs& a, cudaStream_t st, int base =
   }
   if (!a.kin_only) {
     NvtxRange r("tsidb:class_sort");
-    CK(cudaMemsetAsync(counter, 0, 16 * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(counter, 0, TSIDB_NCOUNTER * sizeof(int32_t), st));
     if (a.mask) {
       /* class sort (double support, single support, flight) -> slot order */
       const int th = 256;
-      tsidb_classify_kernel<<<(n + th - 1) / th, th, 0, st>>>(n, a.mask, cls_pos, counter + 1);
-      tsidb_permute_kernel<<<(n + th - 1) / th, th, 0, st>>>(n, cls_pos, counter + 1, perm);
+      tsidb_classify_kernel<<<(n + th - 1) / th, th, 0, st>>>(n, a.mask, h->sched_hint ? a.pred : nullptr, cls_pos, counter + 1, counter + 16);
+      tsidb_permute_kernel<<<(n + th - 1) / th, th, 0, st>>>(n, cls_pos, counter + 16, perm);
       a.perm = perm;
       h->launches += 2;
     }
@@ -964,6 +972,12 @@ extern "C" int tsidb_ci_row(const tsidb_handle* h, int block, int side, int i) {
 }
 
 extern "C" int64_t tsidb_launch_count(const tsidb_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int tsidb_set_sched_hint(tsidb_handle* h, int on) {
+  if (!h) { g_err = "tsidb_set_sched_hint: null handle"; return -1; }
+  h->sched_hint = on ? 1 : 0;
+  return 0;
+}
 
 extern "C" int tsidb_set_timing(tsidb_handle* h, int on) {
   if (!h) { g_err = "tsidb_set_timing: null handle"; return -1; }

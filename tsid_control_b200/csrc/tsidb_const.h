@@ -134,6 +134,7 @@ struct TickArgs {
   const int32_t* perm; /* slot -> env (class sort), null = identity */
   int32_t kin_only;   /* stop after the kinematics (tsidb_kinematics) */
   int32_t slot;       /* constant-memory slot of the handle */
+  int32_t* pred;      /* [n_envs] iteration counts of the previous tick on this handle (scheduling hint), may be null */
   const double* tables; /* the lane-indexed constants in the order the kernels stage them in shared memory (TBL_*), made
                          * once per handle by tsidb_tables_kernel: coalesced loads instead of lane-divergent constant reads */
 };

@@ -2244,6 +2244,7 @@ TSIDB_DEV void activeset_env(const DevConst& C, LaneConst& K, double* sm, const 
   if (lane == 0) {
     a.status[env] = status;
     a.iters[env] = iters;
+    if (a.pred) a.pred[env] = iters; /* next tick's longest-first order (tsidb_classify_kernel) */
     if (a.active) {
       a.active[env] = words[0];
       a.active[(size_t)a.n_envs + env] = words[1];
@@ -2271,31 +2272,50 @@ __global__ void tsidb_tables_kernel(int slot, double* out) {
   }
 }
 
-__global__ void tsidb_classify_kernel(int n_envs, const uint8_t* mask, int32_t* cls_pos, int32_t* counts) {
+/* Class sort with a longest-first order inside each class: the key of an env is (class, bucket), the bucket being its
+ * iteration count in the PREVIOUS tick of this handle (a.pred, 4 iterations per bucket, most iterations first; all envs
+ * share bucket 0 when there is no previous tick or the hint is off).  The persistent CTAs of the per-class kernels draw
+ * slots in this order, so the longest active-set solves of a class start first and the kernel's tail shrinks; the order
+ * of the slots never changes a result (every env is an independent problem). */
+#define TSIDB_NBUCKET 8
+#define TSIDB_NKEY (3 * TSIDB_NBUCKET)
+__global__ void tsidb_classify_kernel(int n_envs, const uint8_t* mask, const int32_t* pred, int32_t* cls_pos, int32_t* counts,
+                                      int32_t* bins) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  int cls = -1;
+  int key = -1;
   if (env < n_envs) {
     const int m = mask ? (mask[env] & 3) : 3;
-    cls = 2 - ((m & 1) + ((m >> 1) & 1)); /* 0: DS, 1: SS, 2: flight */
+    const int cls = 2 - ((m & 1) + ((m >> 1) & 1)); /* 0: DS, 1: SS, 2: flight */
+    int bucket = 0;
+    if (pred) {
+      const int it = pred[env] >> 2;
+      bucket = TSIDB_NBUCKET - 1 - (it < 0 ? 0 : (it > TSIDB_NBUCKET - 1 ? TSIDB_NBUCKET - 1 : it));
+    }
+    key = cls * TSIDB_NBUCKET + bucket;
   }
-  /* warp-aggregated: one atomic per warp and class instead of one per env */
-#pragma unroll
-  for (int c = 0; c < 3; c++) {
-    const unsigned peers = __ballot_sync(FULL, cls == c);
-    if (!peers) continue;
-    int base = 0;
-    if (lane == __ffs(peers) - 1) base = atomicAdd(&counts[c], __popc(peers));
-    base = __shfl_sync(FULL, base, __ffs(peers) - 1);
-    if (cls == c) cls_pos[env] = (c << 28) | (base + __popc(peers & ((1u << lane) - 1u)));
+  /* warp-aggregated: one atomic per warp and key (and one per class for the class sizes) instead of one per env */
+  const unsigned peers = __match_any_sync(FULL, key);
+  const int leader = __ffs(peers) - 1;
+  int base = 0;
+  if (key >= 0 && lane == leader) {
+    base = atomicAdd(&bins[key], __popc(peers));
+    atomicAdd(&counts[key / TSIDB_NBUCKET], __popc(peers));
   }
+  base = __shfl_sync(FULL, base, leader);
+  if (key >= 0) cls_pos[env] = (key << 26) | (base + __popc(peers & ((1u << lane) - 1u)));
 }
-__global__ void tsidb_permute_kernel(int n_envs, const int32_t* cls_pos, const int32_t* counts, int32_t* perm) {
+__global__ void tsidb_permute_kernel(int n_envs, const int32_t* cls_pos, const int32_t* bins, int32_t* perm) {
+  __shared__ int32_t start[TSIDB_NKEY];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k < TSIDB_NKEY; k++) { start[k] = acc; acc += bins[k]; }
+  }
+  __syncthreads();
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= n_envs) return;
-  const int cp = cls_pos[env], cls = cp >> 28, pos = cp & 0x0fffffff;
-  const int base = (cls > 0 ? counts[0] : 0) + (cls > 1 ? counts[1] : 0);
-  perm[base + pos] = env;
+  const int cp = cls_pos[env], key = cp >> 26, pos = cp & 0x03ffffff;
+  perm[start[key] + pos] = env;
 }
 
 template <int NV>

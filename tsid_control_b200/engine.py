@@ -405,6 +405,10 @@ class TsidEngine:
 
     KERNEL_NAMES = ("class_sort", "dynamics", "eliminate", "j2", "activeset")
 
+    def set_sched_hint(self, on: bool) -> None:
+        """Longest-first order of the envs inside a contact class by the previous tick's iteration counts (tsidb.h)."""
+        check(self.lib.tsidb_set_sched_hint(self.h, int(on)), "tsidb_set_sched_hint")
+
     def set_timing(self, on: bool) -> None:
         check(self.lib.tsidb_set_timing(self.h, int(on)), "tsidb_set_timing")
 
