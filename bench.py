@@ -271,6 +271,8 @@ def main() -> None:
     ap.add_argument("--data", default="synthetic", choices=["synthetic", "replay"],
                     help="replay: states, contact phases and references recorded from a closed-loop device rollout")
     ap.add_argument("--batch", type=int, default=0, help="override the config's env count (the metric is quoted at the config's own size)")
+    ap.add_argument("--replay-stride", type=int, default=5,
+                    help="--data replay: control steps (2 ms each) between consecutive snapshots; 1 = consecutive ticks of a controller")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true",
                     help="profiling runs only: skip the end-to-end and latency legs (the line then has no e2e)")
@@ -337,7 +339,7 @@ def main() -> None:
             snaps.append((qr.clone(), vr.clone(), gs["mask"].clone(),
                           {"com": gs["com"].clone(), "foot_lf": gs["foot_lf"].clone(), "foot_rf": gs["foot_rf"].clone(),
                            "contact_lf": gs["contact_lf"].clone(), "contact_rf": gs["contact_rf"].clone(), "posture": post}))
-            s.eng.rollout(qr, vr, 5, use_graph=True)  # 10 ms of closed loop between snapshots
+            s.eng.rollout(qr, vr, max(1, args.replay_stride), use_graph=True)  # 10 ms of closed loop between snapshots by default
         torch.cuda.synchronize()
         replay = snaps
         fails = int((s.eng.gait_state()["fails"] > 0).sum().item())
@@ -611,7 +613,7 @@ def main() -> None:
     }
     if replay is not None:
         line["config"]["replay"] = (f"{len(replay)} snapshots of a closed-loop device rollout (tsidb_rollout: tick -> integrate_dv -> gait "
-                                    f"phase machine), 5 control steps apart after a 25-step run-in; envs that ever failed a tick: {fails}")
+                                    f"phase machine), {max(1, args.replay_stride)} control steps apart after a 25-step run-in; envs that ever failed a tick: {fails}")
     if e2e:
         line["e2e"] = e2e
         line["e2e_device_refs"] = e2e_dev

@@ -309,8 +309,8 @@ int tsidb_last_tick_ms(tsidb_handle* h, float* ms5);
 /* Scheduling hint (no counterpart in the reference; never changes a result).  The class sort of a tick orders the envs
  * of a contact class by their active-set iteration count in the handle's PREVIOUS tick, most iterations first, so the
  * longest solves start first and the per-class kernels end with a shorter tail.  In closed loop the counts change slowly
- * from tick to tick (a replayed rollout: tick -1.8 %); for a batch that is ticked again unchanged the forecast is exact
- * (-5 %).  On by default (TSIDB_SCHED_HINT=0 at tsidb_create turns it off); off, every env of a class shares one bucket. */
+ * from tick to tick (consecutive ticks of a replayed rollout: +2.8 % ticks/s); for a batch that is ticked again unchanged
+ * the forecast is exact (+5 %).  On by default (TSIDB_SCHED_HINT=0 at tsidb_create turns it off); off, every env of a class shares one bucket. */
 int tsidb_set_sched_hint(tsidb_handle* h, int on);
 
 /* ---- the reference's planners on the device, one thread per env ---------------------------
