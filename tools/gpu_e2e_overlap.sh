@@ -10,7 +10,6 @@ run() { # tag, env...
 python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1
 run base A=1
 run base_carve100 TSIDB_D_CARVEOUT=100
-bash -c 'VAR_ONLY_BUILD=1 true'
 cp tsid_control_b200/csrc/tsidb_const.h /tmp/const.bak
 build() { (cd tsid_control_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared -o libtsidb.so tsidb.cu) || echo "build failed"; }
 sed -i -E 's/^#define TSIDB_WARPS_PER_BLOCK [0-9]+/#define TSIDB_WARPS_PER_BLOCK 8/; s/^#define TSIDB_D_CTAS_PER_SM [0-9]+/#define TSIDB_D_CTAS_PER_SM 2/' tsid_control_b200/csrc/tsidb_const.h
