@@ -2447,10 +2447,10 @@ tsidb_activeset_kernel(const TickArgs a) {
  * A CTA is one warp and takes one env through the three stages back to back (dynamics + assembly, elimination + basis,
  * active set + decode), branching on the env's contact class on the device: no class sort, no work counters, no
  * per-class launches, no launch gaps — a single robot's tick (the reference's operating point, ref:main.py:110-128)
- * is bound by the dependent chain of its ~30 k instructions, and nine launches plus a memset added a third to that.
- * The stage functions are the ones the batched kernels call; the hand-off images still travel through global memory
+ * is bound by the dependent chain (and the instruction fetch) of its ~12 k instructions; nine launches added a third.
+ * The stage functions are the ones the batched kernels call.  !LOCAL: the hand-off images travel through global memory
  * (L2), so between the stages the warp orders its generic-proxy stores and completed bulk stores ahead of the next
- * stage's bulk (async-proxy) load. */
+ * stage's bulk (async-proxy) load (stage_handoff).  LOCAL: they stay in shared memory, see below. */
 TSIDB_DEV void stage_handoff(int lane) {
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* bulk stores complete, not just read */
   __threadfence();
